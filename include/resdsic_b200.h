@@ -1,0 +1,204 @@
+/* resdsic_b200 -- C ABI of the B200-native WACNN/STF codec forward path.
+ *
+ * The reference (AlbertoPresta/ResDSIC) has NO FFI on this path: its boundary
+ * is the Python nn.Module surface.  This header is what a
+ * maintainer would bind (ctypes) to replace the ATen calls
+ * behind each reference module; every entry point cites the reference code it
+ * replaces (paths relative to the reference's src/compress/).
+ *
+ * Conventions
+ *   - plain C: raw device pointers + sizes, no torch types;
+ *   - every function is re-entrant, keeps no global mutable state, launches on
+ *     the caller's `stream` of the CURRENT device and never allocates or
+ *     retains caller memory (outputs / workspaces are caller-owned);
+ *   - return value: 0 = ok, otherwise a negative RDSIC_E_* argument error or a
+ *     positive cudaError_t; rdsic_error_string() renders either.  The Python
+ *     host raises RuntimeError on non-zero, matching the reference's
+ *     exception-based error convention (entropy_models.py:129-130,184-203);
+ *   - activations are channels-last (NHWC) with an explicit per-pixel channel
+ *     stride `ld` and channel offset `coff`, so torch.cat / chunk / PixelShuffle /
+ *     roll / window_partition are folded into addressing, never materialised.
+ */
+#ifndef RESDSIC_B200_H
+#define RESDSIC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RDSIC_ABI_VERSION 1
+
+typedef void* rdsic_stream_t; /* cudaStream_t */
+
+enum { RDSIC_F32 = 0, RDSIC_BF16 = 1 };
+
+enum {
+  RDSIC_E_ARG = -1,      /* invalid argument / unsupported shape */
+  RDSIC_E_ALIGN = -2,    /* pointer or stride not aligned as required */
+  RDSIC_E_UNSUPPORTED = -3
+};
+
+/* Epilogues fused into the convolution / GEMM kernels. v = acc + bias. */
+enum {
+  RDSIC_EPI_NONE = 0,     /* out = v                                  nn.Conv2d */
+  RDSIC_EPI_GELU = 1,     /* out = gelu(v)            conv + nn.GELU (layers.py:58-63, cnn.py:56-129) */
+  RDSIC_EPI_RES_GELU = 2, /* out = gelu(v + res)      ResidualUnit tail (layers.py:67-71) */
+  RDSIC_EPI_ADD_RES = 3,  /* out = v + res            attention proj + shortcut (win_attention.py:113,205) */
+  RDSIC_EPI_GATE = 4,     /* out = aux*sigmoid(v)+res Win_noShift_Attention.forward (layers.py:83-89) */
+  RDSIC_EPI_GDN = 5,      /* out = res*rsqrt(v)       GDN.forward (gdn.py:62-75), A operand squared */
+  RDSIC_EPI_IGDN = 6,     /* out = res*sqrt(v)        inverse GDN (gdn.py:70-71) */
+  RDSIC_EPI_LRP = 7       /* out = res + 0.5*tanh(v)  latent residual prediction (cnn.py:179-182) */
+};
+
+/* One tensor view: NHWC element (b,y,x,c) lives at
+ * ptr[((b*H + y)*W + x)*ld + coff + c]; with nchw != 0 it is
+ * ptr[((b*C + c)*H + y)*W + x] (ld/coff ignored, C = channel count of the op). */
+typedef struct rdsic_view {
+  void* ptr;
+  int32_t dtype; /* RDSIC_F32 | RDSIC_BF16 */
+  int32_t ld;
+  int32_t coff;
+  int32_t nchw;
+} rdsic_view;
+
+/* Implicit-GEMM convolution: replaces nn.Conv2d / nn.ConvTranspose2d(phase) /
+ * nn.Linear / GDN's 1x1 contraction + the elementwise ops listed above.
+ *   M = B*OH*OW output positions, N = Cout, K = KH*KW*Cin.
+ *   input pixel for tap (r,s): (oy*stride - pad_h + r, ox*stride - pad_w + s), zero outside.
+ *   output pixel: (oy*osy + ooy, ox*osx + oox) of an [B,OHt,OWt] tensor; with
+ *   pixel_shuffle = 2, GEMM column n goes to channel n/4 of pixel
+ *   (2*oy + (n%4)/2, 2*ox + n%2)  (nn.PixelShuffle, layers.py:34-38).
+ * A stride-2 5x5 transposed convolution (WACNN/utils.py:126-134) is four such
+ * descriptors (phase sub-kernels 3x3, 3x2, 2x3, 2x2 with osy = osx = 2). */
+typedef struct rdsic_conv_desc {
+  rdsic_view in;          /* [B,H,W,Cin] */
+  int32_t B, H, W, Cin;
+  const void* weight;     /* packed [Cout][KH*KW*Cin] (tap-major, channel-minor), compute dtype */
+  const float* bias;      /* [Cout] fp32 or NULL */
+  int32_t w_dtype;
+  int32_t Cout, KH, KW, stride, pad_h, pad_w;
+  int32_t OH, OW;         /* GEMM output grid */
+  int32_t OHt, OWt, osy, osx, ooy, oox;
+  int32_t pixel_shuffle;  /* 0 or 2 */
+  int32_t epilogue;       /* RDSIC_EPI_* */
+  int32_t a_square;       /* square the A operand (GDN) */
+  rdsic_view out;         /* [B,OHt,OWt,Cout(/4)] */
+  rdsic_view res;         /* residual / multiplicand, same pixel grid + channels as out */
+  rdsic_view aux;         /* gate operand `a` */
+  rdsic_view out2;        /* optional extra copies of the result (slice-loop support buffers) */
+  rdsic_view out3;
+} rdsic_conv_desc;
+
+/* Fused shifted-window attention core: replaces roll + window_partition +
+ * (q*scale)@k^T + relative-position bias + shift mask(-100) + softmax + @v +
+ * window_reverse + roll back  (win_attention.py:94-112,159-200).
+ * qkv is the unshifted [B,H,W,3C] output of the qkv 1x1 GEMM (channel =
+ * which*C + head*d + k, win_attention.py:91-92); out is [B,H,W,C] at the
+ * ORIGINAL pixel positions, channel = head*d + k. */
+typedef struct rdsic_attn_desc {
+  rdsic_view qkv;
+  rdsic_view out;
+  const float* bias_table; /* [(2*ws-1)^2, heads] fp32 (win_attention.py:60-61) */
+  int32_t B, H, W, C, heads, ws, shift;
+  float scale;             /* qk_scale or head_dim**-0.5 (win_attention.py:54), applied to q before q@k^T */
+} rdsic_attn_desc;
+
+/* EntropyBottleneck.forward, eval mode (entropy_models.py:447-490) + the
+ * ste_round z_hat of cnn.py:152-154 (same value).  params: [C][RDSIC_EB_STRIDE]
+ * fp32 per channel = softplus(matrix0..4) (3,9,9,9,3) | bias0..4 (3,3,3,3,1) |
+ * tanh(factor0..3) (3 each) | median. */
+#define RDSIC_EB_STRIDE 60
+typedef struct rdsic_eb_desc {
+  rdsic_view z;       /* [B,h,w,C] fp32 */
+  rdsic_view z_hat;   /* [B,h,w,C] */
+  float* lik;         /* [B,C,h,w] fp32 NCHW (module output) */
+  int32_t* symbols;   /* optional [B,C,h,w] int32: round(z - median) */
+  const float* params;
+  int32_t B, h, w, C;
+  float lik_bound;    /* 1e-9 */
+} rdsic_eb_desc;
+
+/* GaussianConditional.forward (eval) + ste_round + build_indexes + quantize
+ * "symbols" for one channel slice (entropy_models.py:627-668,139-152;
+ * cnn.py:175-177,253-254).  Per element:
+ *   y_hat = rint(y-mu)+mu; lik = max(.5erfc(c(.5-|y_hat-mu|)/s) - .5erfc(c(-.5-|..|)/s), bound),
+ *   s = max(scale, scale_bound); sym = int(rint(y-mu)); idx = #{t in table[:-1] : t < s}. */
+typedef struct rdsic_gc_desc {
+  rdsic_view y;        /* [B,h,w,Cs] fp32 slice view */
+  rdsic_view mu;       /* fp32 */
+  rdsic_view scale;    /* fp32 */
+  rdsic_view y_hat[3]; /* up to three destinations (ptr NULL = unused) */
+  float* lik;          /* NCHW [B,Ctot,h,w] base; slice starts at channel lik_coff */
+  int32_t* symbols;    /* optional, same layout */
+  int32_t* indexes;    /* optional, same layout */
+  const float* table;  /* [n_table] fp32 scale table (cnn.py:14-20) */
+  int32_t n_table;
+  int32_t B, h, w, Cs, Ctot, lik_coff;
+  float scale_bound, lik_bound;
+} rdsic_gc_desc;
+
+/* Layout / elementwise helpers used by the standalone module API. */
+typedef struct rdsic_copy_desc {
+  rdsic_view src;
+  rdsic_view dst;
+  int32_t B, H, W, C;
+  int32_t op; /* 0 copy/cast, 1 gelu */
+} rdsic_copy_desc;
+
+/* LayerNorm over channels (stf Swin block, TCM/tcm.py:214-236). */
+typedef struct rdsic_ln_desc {
+  rdsic_view in;
+  rdsic_view out;
+  const float* gamma;
+  const float* beta;
+  int32_t rows, C;
+  float eps;
+} rdsic_ln_desc;
+
+enum { RDSIC_OP_CONV = 0, RDSIC_OP_ATTN = 1, RDSIC_OP_EB = 2, RDSIC_OP_GC = 3, RDSIC_OP_COPY = 4, RDSIC_OP_LN = 5 };
+
+/* One node of a forward "program" (WACNN.forward, cnn.py:143-193, is ~330 of these). */
+typedef struct rdsic_op {
+  int32_t kind;
+  int32_t pad_;
+  union {
+    rdsic_conv_desc conv;
+    rdsic_attn_desc attn;
+    rdsic_eb_desc eb;
+    rdsic_gc_desc gc;
+    rdsic_copy_desc copy;
+    rdsic_ln_desc ln;
+  } u;
+} rdsic_op;
+
+int rdsic_abi_version(void);
+const char* rdsic_error_string(int code);
+/* sizeof(rdsic_op) etc., so the host binding can verify its struct mirror. */
+int rdsic_sizeof(int what); /* 0 op, 1 conv, 2 attn, 3 eb, 4 gc, 5 copy, 6 view, 7 ln */
+
+int rdsic_conv_forward(const rdsic_conv_desc* d, rdsic_stream_t stream);
+int rdsic_attn_forward(const rdsic_attn_desc* d, rdsic_stream_t stream);
+int rdsic_eb_forward(const rdsic_eb_desc* d, rdsic_stream_t stream);
+int rdsic_gc_forward(const rdsic_gc_desc* d, rdsic_stream_t stream);
+int rdsic_copy_forward(const rdsic_copy_desc* d, rdsic_stream_t stream);
+int rdsic_ln_forward(const rdsic_ln_desc* d, rdsic_stream_t stream);
+
+/* Launch a whole program in order on `stream`.  *n_launched (optional) receives
+ * the number of kernels launched.  Stops at the first error; *failed_op
+ * (optional) receives its index. */
+int rdsic_run_program(const rdsic_op* ops, int n_ops, rdsic_stream_t stream, int* n_launched, int* failed_op);
+
+/* Capture a program into a CUDA graph once and replay it (pointers are baked in:
+ * the host keeps its buffers static).  The handle is owned by the caller. */
+typedef struct rdsic_graph rdsic_graph;
+int rdsic_graph_create(const rdsic_op* ops, int n_ops, rdsic_stream_t stream, rdsic_graph** out);
+int rdsic_graph_launch(rdsic_graph* g, rdsic_stream_t stream);
+int rdsic_graph_num_kernels(const rdsic_graph* g);
+void rdsic_graph_destroy(rdsic_graph* g);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RESDSIC_B200_H */

@@ -1,0 +1,131 @@
+"""ctypes binding of libresdsic_b200.so (C ABI: include/resdsic_b200.h).
+
+There is NO fallback: if the CUDA library is missing or its ABI does not match
+this mirror, importing/using the package raises immediately.
+"""
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libresdsic_b200.so")
+
+F32, BF16 = 0, 1
+EPI_NONE, EPI_GELU, EPI_RES_GELU, EPI_ADD_RES, EPI_GATE, EPI_GDN, EPI_IGDN, EPI_LRP = range(8)
+OP_CONV, OP_ATTN, OP_EB, OP_GC, OP_COPY, OP_LN = range(6)
+EB_STRIDE = 60
+
+
+class View(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("dtype", C.c_int32), ("ld", C.c_int32), ("coff", C.c_int32), ("nchw", C.c_int32)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("in_", View),
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32),
+        ("weight", C.c_void_p), ("bias", C.c_void_p),
+        ("w_dtype", C.c_int32),
+        ("Cout", C.c_int32), ("KH", C.c_int32), ("KW", C.c_int32), ("stride", C.c_int32),
+        ("pad_h", C.c_int32), ("pad_w", C.c_int32),
+        ("OH", C.c_int32), ("OW", C.c_int32),
+        ("OHt", C.c_int32), ("OWt", C.c_int32), ("osy", C.c_int32), ("osx", C.c_int32),
+        ("ooy", C.c_int32), ("oox", C.c_int32),
+        ("pixel_shuffle", C.c_int32), ("epilogue", C.c_int32), ("a_square", C.c_int32),
+        ("out", View), ("res", View), ("aux", View), ("out2", View), ("out3", View),
+    ]
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("qkv", View), ("out", View), ("bias_table", C.c_void_p),
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
+        ("heads", C.c_int32), ("ws", C.c_int32), ("shift", C.c_int32), ("scale", C.c_float),
+    ]
+
+
+class EBDesc(C.Structure):
+    _fields_ = [
+        ("z", View), ("z_hat", View), ("lik", C.c_void_p), ("symbols", C.c_void_p), ("params", C.c_void_p),
+        ("B", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("C", C.c_int32), ("lik_bound", C.c_float),
+    ]
+
+
+class GCDesc(C.Structure):
+    _fields_ = [
+        ("y", View), ("mu", View), ("scale", View), ("y_hat", View * 3),
+        ("lik", C.c_void_p), ("symbols", C.c_void_p), ("indexes", C.c_void_p), ("table", C.c_void_p),
+        ("n_table", C.c_int32),
+        ("B", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("Cs", C.c_int32), ("Ctot", C.c_int32),
+        ("lik_coff", C.c_int32), ("scale_bound", C.c_float), ("lik_bound", C.c_float),
+    ]
+
+
+class CopyDesc(C.Structure):
+    _fields_ = [("src", View), ("dst", View), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("C", C.c_int32), ("op", C.c_int32)]
+
+
+class LNDesc(C.Structure):
+    _fields_ = [("in_", View), ("out", View), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("rows", C.c_int32), ("C", C.c_int32), ("eps", C.c_float)]
+
+
+class _OpUnion(C.Union):
+    _fields_ = [("conv", ConvDesc), ("attn", AttnDesc), ("eb", EBDesc), ("gc", GCDesc), ("copy", CopyDesc),
+                ("ln", LNDesc)]
+
+
+class Op(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("pad_", C.c_int32), ("u", _OpUnion)]
+
+
+EXPORTS = (
+    "rdsic_abi_version", "rdsic_error_string", "rdsic_sizeof",
+    "rdsic_conv_forward", "rdsic_attn_forward", "rdsic_eb_forward", "rdsic_gc_forward",
+    "rdsic_copy_forward", "rdsic_ln_forward", "rdsic_run_program",
+    "rdsic_graph_create", "rdsic_graph_launch", "rdsic_graph_num_kernels", "rdsic_graph_destroy",
+)
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the CUDA library; raise loudly if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"resdsic_b200: CUDA library not built ({LIB_PATH}). Run `python -m resdsic_b200.build` "
+            "(or __graft_entry__.build()). There is no CPU / PyTorch fallback.")
+    L = C.CDLL(LIB_PATH)
+    for name in EXPORTS:
+        if not hasattr(L, name):
+            raise RuntimeError(f"resdsic_b200: {LIB_PATH} does not export {name}")
+    L.rdsic_error_string.restype = C.c_char_p
+    L.rdsic_error_string.argtypes = [C.c_int]
+    L.rdsic_sizeof.argtypes = [C.c_int]
+    for fn, T in (("rdsic_conv_forward", ConvDesc), ("rdsic_attn_forward", AttnDesc), ("rdsic_eb_forward", EBDesc),
+                  ("rdsic_gc_forward", GCDesc), ("rdsic_copy_forward", CopyDesc), ("rdsic_ln_forward", LNDesc)):
+        getattr(L, fn).argtypes = [C.POINTER(T), C.c_void_p]
+        getattr(L, fn).restype = C.c_int
+    L.rdsic_run_program.argtypes = [C.POINTER(Op), C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.rdsic_graph_create.argtypes = [C.POINTER(Op), C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.rdsic_graph_launch.argtypes = [C.c_void_p, C.c_void_p]
+    L.rdsic_graph_num_kernels.argtypes = [C.c_void_p]
+    L.rdsic_graph_destroy.argtypes = [C.c_void_p]
+    L.rdsic_graph_destroy.restype = None
+    if L.rdsic_abi_version() != 1:
+        raise RuntimeError("resdsic_b200: ABI version mismatch between the python host and the CUDA library")
+    for what, T in enumerate((Op, ConvDesc, AttnDesc, EBDesc, GCDesc, CopyDesc, View, LNDesc)):
+        if L.rdsic_sizeof(what) != C.sizeof(T):
+            raise RuntimeError(f"resdsic_b200: struct mirror mismatch for {T.__name__}: "
+                               f"C={L.rdsic_sizeof(what)} python={C.sizeof(T)}")
+    _lib = L
+    return L
+
+
+def check(rc, what="resdsic_b200 call"):
+    if rc != 0:
+        msg = lib().rdsic_error_string(rc).decode()
+        raise RuntimeError(f"{what} failed: {msg} (code {rc})")

@@ -1,0 +1,83 @@
+// Layout / elementwise helpers: NCHW<->NHWC (the reference's permutes at
+// win_attention.py:156,204 and the module-boundary layout), dtype casts,
+// standalone nn.GELU, and LayerNorm over channels (the stf Swin block,
+// reference TCM/tcm.py:214-236).  All memory-bound.
+#include "common.cuh"
+
+namespace {
+
+// 32x32 smem-tiled transpose-copy: both the NHWC and the NCHW side are accessed
+// with 128-byte coalesced rows whichever direction we go.
+__global__ void __launch_bounds__(256) copy_views_kernel(const rdsic_copy_desc d) {
+  __shared__ float tile[32][33];
+  const int HW = d.H * d.W;
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const bool src_n = d.src.nchw != 0, dst_n = d.dst.nchw != 0;
+  // load: tile[c][p]
+  for (int k = ty; k < 32; k += 8) {
+    int c, p;
+    if (src_n) { c = c0 + k; p = p0 + tx; } else { p = p0 + k; c = c0 + tx; }
+    float v = 0.f;
+    if (c < d.C && p < HW) {
+      size_t idx = src_n ? ((size_t)b * d.C + c) * HW + p : ((size_t)b * HW + p) * d.src.ld + d.src.coff + c;
+      v = ld_elem(d.src.ptr, d.src.dtype, idx);
+      if (d.op == 1) v = gelu_erf(v);
+    }
+    if (src_n) tile[k][tx] = v; else tile[tx][k] = v;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    int c, p;
+    float v;
+    if (dst_n) { c = c0 + k; p = p0 + tx; v = tile[k][tx]; } else { p = p0 + k; c = c0 + tx; v = tile[tx][k]; }
+    if (c < d.C && p < HW) {
+      size_t idx = dst_n ? ((size_t)b * d.C + c) * HW + p : ((size_t)b * HW + p) * d.dst.ld + d.dst.coff + c;
+      st_elem(d.dst.ptr, d.dst.dtype, idx, v);
+    }
+  }
+}
+
+// one warp per row of C channels; two-pass mean/variance in registers (torch
+// LayerNorm: biased variance, eps inside the sqrt).
+__global__ void __launch_bounds__(256) layernorm_kernel(const rdsic_ln_desc d) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+  if (warp >= d.rows) return;
+  const size_t ib = (size_t)warp * d.in.ld + d.in.coff, ob = (size_t)warp * d.out.ld + d.out.coff;
+  float sum = 0.f;
+  for (int c = lane; c < d.C; c += 32) sum += ld_elem(d.in.ptr, d.in.dtype, ib + c);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / d.C;
+  float var = 0.f;
+  for (int c = lane; c < d.C; c += 32) {
+    float t = ld_elem(d.in.ptr, d.in.dtype, ib + c) - mean;
+    var = fmaf(t, t, var);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / d.C + d.eps);
+  for (int c = lane; c < d.C; c += 32) {
+    float t = (ld_elem(d.in.ptr, d.in.dtype, ib + c) - mean) * rstd;
+    st_elem(d.out.ptr, d.out.dtype, ob + c, t * d.gamma[c] + d.beta[c]);
+  }
+}
+
+}  // namespace
+
+extern "C" int rdsic_copy_forward(const rdsic_copy_desc* d, rdsic_stream_t stream) {
+  RDSIC_CHECK_ARG(d && d->src.ptr && d->dst.ptr && d->B > 0 && d->H > 0 && d->W > 0 && d->C > 0);
+  RDSIC_CHECK_ARG(d->op == 0 || d->op == 1);
+  RDSIC_CHECK_ARG(d->B <= 65535);
+  dim3 grid(ceil_div(d->H * d->W, 32), ceil_div(d->C, 32), d->B);
+  copy_views_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d);
+  return rdsic_launch_status();
+}
+
+extern "C" int rdsic_ln_forward(const rdsic_ln_desc* d, rdsic_stream_t stream) {
+  RDSIC_CHECK_ARG(d && d->in.ptr && d->out.ptr && d->gamma && d->beta && d->rows > 0 && d->C > 0);
+  RDSIC_CHECK_ARG(!d->in.nchw && !d->out.nchw);
+  layernorm_kernel<<<ceil_div(d->rows, 8), 256, 0, (cudaStream_t)stream>>>(*d);
+  return rdsic_launch_status();
+}

@@ -1,0 +1,189 @@
+"""EntropyBottleneck / GaussianConditional on the fused CUDA entropy kernels.
+
+Mirror of the reference's vendored CompressAI classes
+(entropy_models/entropy_models.py:295-668): same constructor arguments,
+parameter/buffer names and eval-mode forward semantics.  In scope: forward
+(quantise + likelihood), quantize, dequantize, build_indexes.  Out of scope per
+BASELINE.json (stays in the reference's C++): update() CDF tables and the rANS
+compress()/decompress().
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import packing
+from ..layers.base import B200Module, Ctx
+from ..ops import LowerBound
+from ..program import TV
+
+
+class EntropyModel(B200Module):
+    """reference entropy_models.py:70-292 (buffers only; coding is out of scope)."""
+
+    def __init__(self, likelihood_bound=1e-9, entropy_coder=None, entropy_coder_precision=16):
+        super().__init__()
+        self.entropy_coder_precision = int(entropy_coder_precision)
+        self.use_likelihood_bound = likelihood_bound > 0
+        self.likelihood_bound = float(likelihood_bound)
+        if self.use_likelihood_bound:
+            self.likelihood_lower_bound = LowerBound(likelihood_bound)
+        self.register_buffer("_offset", torch.IntTensor())
+        self.register_buffer("_quantized_cdf", torch.IntTensor())
+        self.register_buffer("_cdf_length", torch.IntTensor())
+
+    offset = property(lambda self: self._offset)
+    quantized_cdf = property(lambda self: self._quantized_cdf)
+    cdf_length = property(lambda self: self._cdf_length)
+
+    def update(self, *a, **k):
+        raise NotImplementedError("CDF-table build (update) is out of scope for the B200 forward path; "
+                                  "use the reference's C++ `pmf_to_quantized_cdf` (SURVEY section 8f N2)")
+
+    def compress(self, *a, **k):
+        raise NotImplementedError("rANS bitstream coding stays in the reference's C++ (BASELINE.json north_star)")
+
+    decompress = compress
+
+    @staticmethod
+    def dequantize(inputs, means=None):
+        """reference entropy_models.py:160-167 (pure dtype/add glue, used after rANS decode)."""
+        if means is not None:
+            return inputs.type_as(means) + means
+        return inputs.float()
+
+
+class EntropyBottleneck(EntropyModel):
+    def __init__(self, channels, *args, tail_mass=1e-9, init_scale=10, filters=(3, 3, 3, 3), **kwargs):
+        super().__init__(*args, **kwargs)
+        self.channels = int(channels)
+        self.filters = tuple(int(f) for f in filters)
+        self.init_scale = float(init_scale)
+        self.tail_mass = float(tail_mass)
+        filters = (1,) + self.filters + (1,)
+        scale = self.init_scale ** (1 / (len(self.filters) + 1))
+        for i in range(len(self.filters) + 1):
+            init = np.log(np.expm1(1 / scale / filters[i + 1]))
+            self.register_parameter(f"_matrix{i:d}", nn.Parameter(torch.full((channels, filters[i + 1], filters[i]), float(init))))
+            self.register_parameter(f"_bias{i:d}", nn.Parameter(torch.empty(channels, filters[i + 1], 1).uniform_(-0.5, 0.5)))
+            if i < len(self.filters):
+                self.register_parameter(f"_factor{i:d}", nn.Parameter(torch.zeros(channels, filters[i + 1], 1)))
+        init = torch.Tensor([-self.init_scale, 0, self.init_scale])
+        self.quantiles = nn.Parameter(init.repeat(channels, 1, 1))
+        target = np.log(2 / self.tail_mass - 1)
+        self.register_buffer("target", torch.Tensor([-target, 0, target]))
+
+    def _get_medians(self):
+        return self.quantiles[:, :, 1:2]
+
+    def packed(self):
+        names = [f"_matrix{i}" for i in range(5)] + [f"_bias{i}" for i in range(5)] + [f"_factor{i}" for i in range(4)]
+        tensors = [getattr(self, n) for n in names] + [self.quantiles]
+
+        def build():
+            # softplus/tanh of the parameters on the CPU: the same ATen ops the reference applies
+            cpu = {n: getattr(self, n).detach().cpu() for n in names}
+            return packing.pack_entropy_bottleneck(cpu, self.quantiles.detach().cpu()).to(self.quantiles.device)
+
+        return self._packed("eb", tensors, build)
+
+    def emit(self, ctx: Ctx, z, z_hat=None, lik=None, symbols=None, **kw):
+        """z: fp32 [B,h,w,C] view.  Returns (z_hat view, lik NCHW tensor)."""
+        if self.training:
+            raise NotImplementedError("noise-mode (training) quantisation is not part of the B200 inference path")
+        if z_hat is None:
+            z_hat = ctx.buf(z.B, z.H, z.W, z.C)
+        if lik is None:
+            lik = torch.empty(z.B, z.C, z.H, z.W, dtype=torch.float32, device=ctx.device)
+        ctx.prog.eb(z, z_hat, lik, self.packed(), symbols=symbols, lik_bound=self.likelihood_bound)
+        return z_hat, lik
+
+    @torch.no_grad()
+    def forward(self, x, training=None):
+        """(outputs, likelihood), eval mode -- reference entropy_models.py:447-490."""
+        ctx = Ctx(x.device, "fp32")
+        z = ctx.from_nchw(x, torch.float32)
+        z_hat, lik = self.emit(ctx, z, z_hat=ctx.buf(z.B, z.H, z.W, z.C, torch.float32))
+        out = ctx.to_nchw(z_hat)
+        ctx.prog.run()
+        return out, lik
+
+    @staticmethod
+    def _build_indexes(size):
+        """reference entropy_models.py:492-503: index = channel id."""
+        N, Cn = size[0], size[1]
+        idx = torch.arange(Cn, dtype=torch.int32).view(1, -1, *([1] * (len(size) - 2)))
+        return idx.repeat(N, 1, *size[2:])
+
+
+class GaussianConditional(EntropyModel):
+    def __init__(self, scale_table, *args, scale_bound=0.11, tail_mass=1e-9, **kwargs):
+        super().__init__(*args, **kwargs)
+        if not isinstance(scale_table, (type(None), list, tuple)):
+            raise ValueError(f'Invalid type for scale_table "{type(scale_table)}"')
+        if isinstance(scale_table, (list, tuple)) and len(scale_table) < 1:
+            raise ValueError(f'Invalid scale_table length "{len(scale_table)}"')
+        if scale_table and (scale_table != sorted(scale_table) or any(s <= 0 for s in scale_table)):
+            raise ValueError(f'Invalid scale_table "({scale_table})"')
+        self.tail_mass = float(tail_mass)
+        if scale_bound is None and scale_table:
+            scale_bound = scale_table[0]
+        if scale_bound <= 0:
+            raise ValueError("Invalid parameters")
+        self.lower_bound_scale = LowerBound(scale_bound)
+        self.scale_bound_value = float(scale_bound)
+        self.register_buffer("scale_table", torch.Tensor(tuple(float(s) for s in scale_table)) if scale_table else torch.Tensor())
+        self.register_buffer("scale_bound", torch.Tensor([float(scale_bound)]))
+
+    def table(self, device):
+        """Device copy of the scale table; falls back to the model default
+        (reference cnn.py:14-20) when update() has not filled the buffer."""
+        t = self.scale_table
+        if t.numel() == 0:
+            t = packing.scale_table()
+        return self._packed(("table", str(device)), (t,), lambda: t.detach().float().to(device).contiguous())
+
+    def emit(self, ctx: Ctx, y, scale, mu, lik, lik_coff, Ctot, y_hat_dsts=(), symbols=None, indexes=None):
+        if self.training:
+            raise NotImplementedError("noise-mode (training) quantisation is not part of the B200 inference path")
+        ctx.prog.gc(y, mu, scale, list(y_hat_dsts), lik, lik_coff, Ctot, self.table(ctx.device), symbols=symbols,
+                    indexes=indexes, scale_bound=self.scale_bound_value,
+                    lik_bound=self.likelihood_bound)
+
+    def _run(self, inputs, scales, means, want):
+        B, Cn, H, W = inputs.shape
+        ctx = Ctx(inputs.device, "fp32")
+        y = ctx.from_nchw(inputs, torch.float32)
+        sc = ctx.from_nchw(scales, torch.float32)
+        mu = ctx.from_nchw(means if means is not None else torch.zeros_like(inputs), torch.float32)
+        y_hat = ctx.buf(B, H, W, Cn, torch.float32)
+        lik = torch.empty(B, Cn, H, W, dtype=torch.float32, device=inputs.device)
+        sym = torch.empty(B, Cn, H, W, dtype=torch.int32, device=inputs.device) if "sym" in want else None
+        idx = torch.empty(B, Cn, H, W, dtype=torch.int32, device=inputs.device) if "idx" in want else None
+        self.emit(ctx, y, sc, mu, lik, 0, Cn, [y_hat], sym, idx)
+        out = ctx.to_nchw(y_hat)
+        ctx.prog.run()
+        return out, lik, sym, idx
+
+    @torch.no_grad()
+    def forward(self, inputs, scales, means=None, training=None, mask=None):
+        """(outputs, likelihood), eval mode -- reference entropy_models.py:646-661."""
+        if mask is not None:
+            raise NotImplementedError("`mask` only affects noise-mode quantisation (scalable models; out of scope)")
+        out, lik, _, _ = self._run(inputs, scales, means, ())
+        return out, lik
+
+    @torch.no_grad()
+    def quantize(self, inputs, mode, means=None, mask=None):
+        """reference entropy_models.py:126-152 ("dequantize" / "symbols")."""
+        if mode not in ("noise", "dequantize", "symbols"):
+            raise ValueError(f'Invalid quantization mode: "{mode}"')
+        if mode == "noise":
+            raise NotImplementedError("noise-mode (training) quantisation is not part of the B200 inference path")
+        out, _, sym, _ = self._run(inputs, torch.ones_like(inputs), means, ("sym",))
+        return out if mode == "dequantize" else sym
+
+    @torch.no_grad()
+    def build_indexes(self, scales):
+        """reference entropy_models.py:663-668, one binary search instead of 63 compare passes."""
+        _, _, _, idx = self._run(torch.zeros_like(scales), scales, None, ("idx",))
+        return idx

@@ -1,0 +1,113 @@
+"""Common machinery of the B200 layer modules.
+
+Every layer keeps the reference's parameter/buffer names (so reference
+state_dicts load unchanged) and knows how to *emit* itself into a `Program`
+(resdsic_b200/program.py) over channels-last views.  `forward(x)` is the
+reference-facing call: NCHW tensor in, NCHW tensor out, executed by the CUDA
+library -- there is no torch/ATen compute path.
+"""
+import torch
+import torch.nn as nn
+
+from ..program import TV, Program
+
+PRECISIONS = ("fp32", "bf16")
+
+
+class Ctx:
+    """Build context: the program being assembled + activation/weight dtypes."""
+
+    def __init__(self, device, precision="fp32", build_only=False):
+        assert precision in PRECISIONS, precision
+        device = torch.device(device)
+        # build_only: assemble descriptors over CPU tensors so that tests can check the
+        # host-side graph builder without a GPU (tests/program_sim.py); such a program
+        # can never be run by the product (Program.run refuses non-CUDA devices).
+        if device.type != "cuda" and not build_only:
+            raise RuntimeError("resdsic_b200 runs on CUDA devices only (sm_100a kernels; no CPU fallback)")
+        self.device = device
+        self.precision = precision
+        self.act = torch.float32 if precision == "fp32" else torch.bfloat16
+        self.wdt = self.act
+        self.prog = Program(device)
+
+    def buf(self, B, H, W, C, dtype=None, ld=None):
+        return TV.empty(B, H, W, C, dtype or self.act, self.device, ld)
+
+    def from_nchw(self, x, dtype=None):
+        x = x.contiguous()
+        if x.dtype != torch.float32:
+            x = x.float()
+        B, C, H, W = x.shape
+        out = self.buf(B, H, W, C, dtype)
+        self.prog.keep.append(x)
+        return self.prog.copy(TV.nchw_of(x), out)
+
+    def to_nchw(self, tv):
+        out = torch.empty(tv.B, tv.C, tv.H, tv.W, dtype=torch.float32, device=self.device)
+        self.prog.copy(tv, TV.nchw_of(out))
+        return out
+
+
+class B200Module(nn.Module):
+    """nn.Module whose compute is a resdsic_b200 program."""
+
+    precision = "fp32"
+
+    def set_precision(self, precision):
+        assert precision in PRECISIONS, precision
+        for m in self.modules():
+            if isinstance(m, B200Module):
+                m.precision = precision
+        return self
+
+    # -- packed-weight cache, invalidated when a parameter changes version/storage/device
+    def _packed(self, tag, tensors, fn):
+        key = (tag,) + tuple((t.data_ptr(), t._version, str(t.device), t.dtype) for t in tensors)
+        cache = self.__dict__.setdefault("_pack_cache", {})
+        hit = cache.get(tag)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                hit = (key, fn())
+            cache[tag] = hit
+        return hit[1]
+
+    def emit(self, ctx: Ctx, x: TV, **kw) -> TV:  # pragma: no cover - interface
+        raise NotImplementedError
+
+    @torch.no_grad()
+    def forward(self, x):
+        ctx = Ctx(x.device, self.precision)
+        y = self.emit(ctx, ctx.from_nchw(x))
+        out = ctx.to_nchw(y)
+        ctx.prog.run()
+        return out
+
+
+class Sequential(nn.Sequential, B200Module):
+    """nn.Sequential of B200 modules (keeps the reference's integer child names)."""
+
+    def emit(self, ctx, x, **kw):
+        mods = list(self)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            # fuse "conv -> GELU" pairs into the conv epilogue
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            if getattr(m, "fuses_gelu", False) and isinstance(nxt, GELU):
+                x = m.emit(ctx, x, gelu=True)
+                i += 2
+            else:
+                x = m.emit(ctx, x)
+                i += 1
+        return x
+
+    forward = B200Module.forward
+
+
+class GELU(B200Module):
+    """nn.GELU() (exact erf form).  Normally fused into the preceding conv."""
+
+    def emit(self, ctx, x, **kw):
+        out = ctx.buf(x.B, x.H, x.W, x.C)
+        return ctx.prog.copy(x, out, op_code=1)

@@ -1,0 +1,149 @@
+"""Convolution-family layers on the implicit-GEMM kernel.
+
+Mirrors of nn.Conv2d / nn.ConvTranspose2d / nn.Linear / nn.PixelShuffle as the
+reference uses them (WACNN/utils.py:116-134, layers/layers.py:29-43,
+layers/win_attention.py:76-78): same parameter names, shapes and default init.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import _lib, packing
+from .base import B200Module, Ctx
+
+
+class Conv2d(B200Module):
+    """nn.Conv2d(in, out, k, stride, padding=k//2) with bias."""
+
+    fuses_gelu = True
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=None):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride = kernel_size, stride
+        self.padding = kernel_size // 2 if padding is None else padding
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels, kernel_size, kernel_size))
+        self.bias = nn.Parameter(torch.empty(out_channels))
+        # reference init: kaiming_normal_ weights, zero bias (WACNN/base.py:29-34)
+        nn.init.kaiming_normal_(self.weight)
+        nn.init.zeros_(self.bias)
+
+    def packed(self, wdt):
+        return self._packed(("w", wdt), (self.weight, self.bias), lambda: (
+            packing.pack_conv_weight(self.weight, wdt), self.bias.detach().float().contiguous()))
+
+    def emit(self, ctx: Ctx, x, gelu=False, epilogue=None, out=None, out_dtype=None, pixel_shuffle=0, **kw):
+        w, b = self.packed(ctx.wdt)
+        k, s, p = self.kernel_size, self.stride, self.padding
+        OH, OW = (x.H + 2 * p - k) // s + 1, (x.W + 2 * p - k) // s + 1
+        if out is None:
+            if pixel_shuffle:
+                out = ctx.buf(x.B, OH * 2, OW * 2, self.out_channels // 4, out_dtype)
+            else:
+                out = ctx.buf(x.B, OH, OW, self.out_channels, out_dtype)
+        if epilogue is None:
+            epilogue = _lib.EPI_GELU if gelu else _lib.EPI_NONE
+        return ctx.prog.conv(x, w, b, self.out_channels, k, k, s, p, p, out, epilogue=epilogue,
+                             pixel_shuffle=pixel_shuffle, OH=OH, OW=OW, **kw)
+
+
+class ConvTranspose2d(B200Module):
+    """nn.ConvTranspose2d(in, out, 5, stride=2, padding=2, output_padding=1): four
+    sub-pixel phase GEMMs (3x3, 3x2, 2x3, 2x2 taps), output exactly 2x the input."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=5, stride=2):
+        super().__init__()
+        if kernel_size != 5 or stride != 2:
+            raise ValueError("only the reference's deconv(k=5, s=2) is supported")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.weight = nn.Parameter(torch.empty(in_channels, out_channels, 5, 5))
+        self.bias = nn.Parameter(torch.empty(out_channels))
+        nn.init.kaiming_normal_(self.weight)
+        nn.init.zeros_(self.bias)
+
+    def packed(self, wdt):
+        return self._packed(("w", wdt), (self.weight, self.bias), lambda: (
+            packing.pack_deconv_weight(self.weight, wdt), self.bias.detach().float().contiguous()))
+
+    def emit(self, ctx: Ctx, x, out=None, out_dtype=None, **kw):
+        phases, b = self.packed(ctx.wdt)
+        if out is None:
+            out = ctx.buf(x.B, 2 * x.H, 2 * x.W, self.out_channels, out_dtype)
+        for (py, px), (w, R, S, ph, pw) in phases.items():
+            ctx.prog.conv(x, w, b, self.out_channels, R, S, 1, ph, pw, out, OH=x.H, OW=x.W,
+                          osy=2, osx=2, ooy=py, oox=px, **kw)
+        return out
+
+
+class Linear(B200Module):
+    """nn.Linear over the channel dim of a channels-last view (a 1x1 GEMM)."""
+
+    def __init__(self, in_features, out_features):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.weight = nn.Parameter(torch.empty(out_features, in_features))
+        self.bias = nn.Parameter(torch.empty(out_features))
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))  # nn.Linear default
+        bound = 1 / math.sqrt(in_features)
+        nn.init.uniform_(self.bias, -bound, bound)
+
+    def packed(self, wdt):
+        return self._packed(("w", wdt), (self.weight, self.bias), lambda: (
+            packing.pack_linear_weight(self.weight, wdt), self.bias.detach().float().contiguous()))
+
+    def emit(self, ctx: Ctx, x, out=None, epilogue=_lib.EPI_NONE, out_dtype=None, **kw):
+        w, b = self.packed(ctx.wdt)
+        if out is None:
+            out = ctx.buf(x.B, x.H, x.W, self.out_features, out_dtype)
+        return ctx.prog.conv(x, w, b, self.out_features, 1, 1, 1, 0, 0, out, epilogue=epilogue, **kw)
+
+
+class PixelShuffle(B200Module):
+    """Parameter-less placeholder keeping `subpel_conv3x3`'s child index (".2.0.weight");
+    the shuffle itself is folded into the producing conv's store addressing."""
+
+    def __init__(self, r):
+        super().__init__()
+        self.r = r
+
+    def emit(self, ctx, x, **kw):
+        raise RuntimeError("PixelShuffle is fused into SubpelConv; it is never emitted on its own")
+
+
+class SubpelConv(nn.Sequential, B200Module):
+    """subpel_conv3x3 (reference layers/layers.py:34-38): conv3x3 to 4*C + PixelShuffle(2)."""
+
+    fuses_gelu = True
+
+    def __init__(self, in_ch, out_ch, r=2):
+        if r != 2:
+            raise ValueError("only r=2 is used by the reference")
+        super().__init__(Conv2d(in_ch, out_ch * r * r, 3), PixelShuffle(r))
+
+    def emit(self, ctx, x, gelu=False, **kw):
+        return self[0].emit(ctx, x, gelu=gelu, pixel_shuffle=2, **kw)
+
+    forward = B200Module.forward
+
+
+def conv(in_channels, out_channels, kernel_size=5, stride=2):
+    """reference WACNN/utils.py:116-123"""
+    return Conv2d(in_channels, out_channels, kernel_size, stride)
+
+
+def deconv(in_channels, out_channels, kernel_size=5, stride=2):
+    """reference WACNN/utils.py:126-134"""
+    return ConvTranspose2d(in_channels, out_channels, kernel_size, stride)
+
+
+def conv3x3(in_ch, out_ch, stride=1):
+    return Conv2d(in_ch, out_ch, 3, stride)
+
+
+def conv1x1(in_ch, out_ch, stride=1):
+    return Conv2d(in_ch, out_ch, 1, stride)
+
+
+def subpel_conv3x3(in_ch, out_ch, r=1):
+    return SubpelConv(in_ch, out_ch, r)

@@ -1,0 +1,235 @@
+"""WACNN (`-m cnn`): the reference's window-attention CNN codec
+(models/WACNN/cnn.py:23-342) on the B200 kernel library.
+
+Same constructor (`N=192, M=320`), same 585 state_dict keys, same
+`forward(x) -> {"x_hat", "likelihoods": {"y", "z"}}`.  The forward pass is
+assembled ONCE per input shape into a flat program of ~290 kernel descriptors
+over static channels-last buffers and then replayed natively (optionally as a
+CUDA graph).  torch.cat / chunk / PixelShuffle / roll / window partition never
+materialise: they are addressing (`ld`, `coff`, output strides) in the kernels.
+
+Slice-loop buffer plan (cnn.py:161-187): `means` and `scales` are
+[B,h,w,512] channels-last buffers holding latent_means / latent_scales in
+channels [0,320) and the support slices y_hat_0..4 in five 32-channel slots
+[320,480); slot 5 [480,512) of `means` is scratch for the current slice, so
+every cc_mean / cc_scale / lrp input is just "the first Cin channels".
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..entropy_models import EntropyBottleneck, GaussianConditional
+from ..layers import GDN, GELU, B200Module, Ctx, Sequential, Win_noShift_Attention, conv, conv3x3, deconv, subpel_conv3x3
+from ..program import TV
+
+SCALES_MIN, SCALES_MAX, SCALES_LEVELS = 0.11, 256, 64
+
+
+def get_scale_table(min=SCALES_MIN, max=SCALES_MAX, levels=SCALES_LEVELS):
+    """reference cnn.py:19-20"""
+    return torch.exp(torch.linspace(math.log(min), math.log(max), levels))
+
+
+class CompressionModel(B200Module):
+    """reference models/WACNN/base.py:7-59 (aux_loss / update are training- or
+    bitstream-side and stay with the reference)."""
+
+    def aux_loss(self):
+        raise NotImplementedError("aux_loss belongs to the training step (SURVEY section 8: config 4, not yet ported)")
+
+    def load_state_dict(self, state_dict, strict=False):
+        return nn.Module.load_state_dict(self, state_dict, strict=strict)
+
+
+def _cc_stack(cin):
+    return Sequential(conv(cin, 224, stride=1, kernel_size=3), GELU(), conv(224, 176, stride=1, kernel_size=3), GELU(),
+                      conv(176, 128, stride=1, kernel_size=3), GELU(), conv(128, 64, stride=1, kernel_size=3), GELU(),
+                      conv(64, 32, stride=1, kernel_size=3))
+
+
+class _Plan:
+    """A built program + its static input/output buffers for one (B,H,W,precision,mode)."""
+
+
+class WACNN(CompressionModel):
+    """CNN based model (reference cnn.py:23)."""
+
+    def __init__(self, N=192, M=320, **kwargs):
+        super().__init__()
+        if M != 320:
+            raise ValueError("the reference hard-codes 320 latent channels in h_a / h_s / the slice transforms")
+        self.N, self.M = N, M
+        self.num_slices = 10
+        self.max_support_slices = 5
+        self.g_a = Sequential(
+            conv(3, N, kernel_size=5, stride=2), GDN(N),
+            conv(N, N, kernel_size=5, stride=2), GDN(N),
+            Win_noShift_Attention(dim=N, num_heads=8, window_size=8, shift_size=4),
+            conv(N, N, kernel_size=5, stride=2), GDN(N),
+            conv(N, M, kernel_size=5, stride=2),
+            Win_noShift_Attention(dim=M, num_heads=8, window_size=4, shift_size=2))
+        self.g_s = Sequential(
+            Win_noShift_Attention(dim=M, num_heads=8, window_size=4, shift_size=2),
+            deconv(M, N, kernel_size=5, stride=2), GDN(N, inverse=True),
+            deconv(N, N, kernel_size=5, stride=2), GDN(N, inverse=True),
+            Win_noShift_Attention(dim=N, num_heads=8, window_size=8, shift_size=4),
+            deconv(N, N, kernel_size=5, stride=2), GDN(N, inverse=True),
+            deconv(N, 3, kernel_size=5, stride=2))
+        self.h_a = Sequential(conv3x3(320, 320), GELU(), conv3x3(320, 288), GELU(), conv3x3(288, 256, stride=2), GELU(),
+                              conv3x3(256, 224), GELU(), conv3x3(224, 192, stride=2))
+
+        def h_s():
+            return Sequential(conv3x3(192, 192), GELU(), subpel_conv3x3(192, 224, 2), GELU(), conv3x3(224, 256), GELU(),
+                              subpel_conv3x3(256, 288, 2), GELU(), conv3x3(288, 320))
+
+        self.h_mean_s = h_s()
+        self.h_scale_s = h_s()
+        self.cc_mean_transforms = nn.ModuleList(_cc_stack(320 + 32 * min(i, 5)) for i in range(10))
+        self.cc_scale_transforms = nn.ModuleList(_cc_stack(320 + 32 * min(i, 5)) for i in range(10))
+        self.lrp_transforms = nn.ModuleList(_cc_stack(320 + 32 * min(i + 1, 6)) for i in range(10))
+        self.entropy_bottleneck = EntropyBottleneck(N)
+        self.gaussian_conditional = GaussianConditional(None)
+        self.use_cuda_graph = True
+        self._plans = {}
+
+    # ------------------------------------------------------------------ API
+    @classmethod
+    def from_state_dict(cls, state_dict):
+        """reference cnn.py:207-215 (hard-codes 192/320)."""
+        net = cls(192, 320)
+        net.load_state_dict(state_dict)
+        return net
+
+    def update(self, scale_table=None, force=False):
+        raise NotImplementedError("CDF-table update() is out of scope (rANS side stays in the reference's C++)")
+
+    def compress(self, x):
+        raise NotImplementedError("rANS bitstream coding stays in the reference's C++; use symbols_and_indexes(x) for "
+                                  "the int32 symbols/indexes `compress` hands to the coder (cnn.py:253-258)")
+
+    def decompress(self, strings, shape):
+        raise NotImplementedError("rANS bitstream decoding stays in the reference's C++")
+
+    # ------------------------------------------------------------- planning
+    def _weights_key(self):
+        return tuple(p._version for p in self.parameters())
+
+    def _plan(self, B, H, W, device, with_symbols):
+        if H % 64 or W % 64:
+            raise ValueError(f"input {H}x{W} must be a multiple of 64 (pad as eval_model/__main__.py:89-101 does; "
+                             "see resdsic_b200.utils.pad_to_multiple)")
+        if self.training:
+            raise NotImplementedError("training-mode forward (noise quantisation + autograd) is not ported yet; "
+                                      "call model.eval()")
+        key = (B, H, W, str(device), self.precision, with_symbols, self._weights_key())
+        plan = self._plans.get(key)
+        if plan is None:
+            self._plans.clear()  # one live plan: buffers are sized for one shape
+            plan = self._build(B, H, W, device, with_symbols)
+            self._plans[key] = plan
+        return plan
+
+    def _build(self, B, H, W, device, with_symbols, build_only=False):
+        ctx = Ctx(device, self.precision, build_only=build_only)
+        f32 = torch.float32
+        p = _Plan()
+        p.x = torch.empty(B, 3, H, W, dtype=f32, device=device)
+        # ---- g_a: y kept fp32 (it is quantised against mu)
+        ga = list(self.g_a)
+        t = TV.nchw_of(p.x)
+        for m in ga[:-1]:
+            t = m.emit(ctx, t)
+        y = ga[-1].emit(ctx, t, out_dtype=f32)
+        h, w = y.H, y.W
+        # ---- h_a -> z (fp32) -> EB
+        ha = list(self.h_a)
+        t = y
+        for i in (0, 2, 4, 6):
+            t = ha[i].emit(ctx, t, gelu=True)
+        z = ha[8].emit(ctx, t, out_dtype=f32)
+        p.lik_z = torch.empty(B, self.N, z.H, z.W, dtype=f32, device=device)
+        p.z_symbols = torch.empty(B, self.N, z.H, z.W, dtype=torch.int32, device=device) if with_symbols else None
+        z_hat, _ = self.entropy_bottleneck.emit(ctx, z, lik=p.lik_z, symbols=p.z_symbols)
+        # ---- hyper-synthesis straight into the support buffers
+        means = ctx.buf(B, h, w, 512)
+        scales = ctx.buf(B, h, w, 512)
+        for hs, dst in ((self.h_scale_s, scales), (self.h_mean_s, means)):
+            mods = list(hs)
+            t = mods[0].emit(ctx, z_hat, gelu=True)
+            t = mods[2].emit(ctx, t, gelu=True)
+            t = mods[4].emit(ctx, t, gelu=True)
+            t = mods[6].emit(ctx, t, gelu=True)
+            mods[8].emit(ctx, t, out=dst.channels(0, 320))
+        # ---- slice loop
+        y_hat = ctx.buf(B, h, w, 320, f32)  # fp32 master copy of y_hat (LRP residual + g_s input)
+        p.lik_y = torch.empty(B, 320, h, w, dtype=f32, device=device)
+        p.symbols = torch.empty(B, 320, h, w, dtype=torch.int32, device=device) if with_symbols else None
+        p.indexes = torch.empty(B, 320, h, w, dtype=torch.int32, device=device) if with_symbols else None
+        for i in range(self.num_slices):
+            k = min(i, self.max_support_slices)
+            cin = 320 + 32 * k
+            mu = self._stack(ctx, self.cc_mean_transforms[i], means.channels(0, cin))
+            sc = self._stack(ctx, self.cc_scale_transforms[i], scales.channels(0, cin))
+            slot = means.channels(320 + 32 * k, 32)  # slot i (i<5) or scratch slot 5
+            yh_i = y_hat.channels(32 * i, 32)
+            self.gaussian_conditional.emit(ctx, y.channels(32 * i, 32), sc, mu, p.lik_y, 32 * i, 320,
+                                           y_hat_dsts=[yh_i, slot], symbols=p.symbols, indexes=p.indexes)
+            extra = {}
+            if i < self.max_support_slices:  # the refined slice becomes support for later slices
+                extra = dict(out2=slot, out3=scales.channels(320 + 32 * i, 32))
+            self._stack(ctx, self.lrp_transforms[i], means.channels(0, cin + 32), final=dict(
+                epilogue=_lib.EPI_LRP, res=yh_i, out=yh_i, **extra))
+        # ---- g_s
+        gs = list(self.g_s)
+        t = y_hat
+        for m in gs[:-1]:
+            t = m.emit(ctx, t)
+        p.x_hat = torch.empty(B, 3, H, W, dtype=f32, device=device)
+        gs[-1].emit(ctx, t, out=TV.nchw_of(p.x_hat))
+        p.prog = ctx.prog
+        p.y, p.z, p.y_hat, p.means, p.scales = y, z, y_hat, means, scales
+        return p
+
+    @staticmethod
+    def _stack(ctx, seq, x, final=None):
+        mods = list(seq)
+        t = x
+        for j in (0, 2, 4, 6):
+            t = mods[j].emit(ctx, t, gelu=True)
+        if final is None:
+            return mods[8].emit(ctx, t, out_dtype=torch.float32)  # mu / scale stay fp32
+        return mods[8].emit(ctx, t, **final)
+
+    # -------------------------------------------------------------- forward
+    def _execute(self, x, with_symbols):
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError(f"expected [B,3,H,W] input, got {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise RuntimeError("resdsic_b200 runs on CUDA devices only (no CPU fallback)")
+        B, _, H, W = x.shape
+        plan = self._plan(B, H, W, x.device, with_symbols)
+        plan.x.copy_(x)
+        if self.use_cuda_graph:
+            plan.prog.run_graph()
+        else:
+            plan.prog.run()
+        self.last_num_launches = plan.prog.num_launches
+        return plan
+
+    @torch.no_grad()
+    def forward(self, x):
+        """reference cnn.py:143-193.  The returned tensors are the plan's static
+        output buffers: clone them if they must survive the next forward()."""
+        p = self._execute(x, False)
+        return {"x_hat": p.x_hat, "likelihoods": {"y": p.lik_y, "z": p.lik_z}}
+
+    @torch.no_grad()
+    def symbols_and_indexes(self, x):
+        """Everything `compress` (cnn.py:217-268) computes before the rANS call: int32
+        symbols/indexes for y (all 10 slices, NCHW [B,320,h,w]) and the z symbols,
+        in contiguous device buffers (one D2H copy instead of 20 `.tolist()` syncs)."""
+        p = self._execute(x, True)
+        return {"y_symbols": p.symbols, "y_indexes": p.indexes, "z_symbols": p.z_symbols,
+                "x_hat": p.x_hat, "likelihoods": {"y": p.lik_y, "z": p.lik_z}, "shape": (p.z.H, p.z.W)}

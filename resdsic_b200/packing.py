@@ -1,0 +1,80 @@
+"""One-time weight packing (host-side preprocessing, not on the per-image hot path).
+
+Turns reference-layout parameters (OIHW conv weights, [Cin,Cout,k,k]
+transposed-conv weights, [out,in] linears, GDN beta/gamma, EntropyBottleneck
+matrices) into the kernel layouts of include/resdsic_b200.h.  Everything is
+recomputed whenever the owning module's parameters change version or device.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from ._lib import EB_STRIDE
+
+
+def pack_conv_weight(w, dtype=torch.float32):
+    """[Cout,Cin,KH,KW] (nn.Conv2d) -> [Cout, KH*KW*Cin], tap-major / channel-minor."""
+    Cout = w.shape[0]
+    return w.detach().permute(0, 2, 3, 1).reshape(Cout, -1).to(dtype).contiguous()
+
+
+def pack_linear_weight(w, dtype=torch.float32):
+    """nn.Linear [out,in] is already [N][K]."""
+    return w.detach().to(dtype).contiguous()
+
+
+# transposed conv k5 s2 p2 op1 (reference WACNN/utils.py:126-134): out[2j+py] gathers
+# in[j + 1 - t] * w[.., kh = 2t + py]; as a stride-1 correlation over taps r (ascending
+# input row j - pad + r): even phase (py=0): 3 taps, pad 1, kh = 4 - 2r;
+# odd phase (py=1): 2 taps, pad 0, kh = 3 - 2r.   
+DECONV_PHASES = {0: (3, 1, (4, 2, 0)), 1: (2, 0, (3, 1))}  # parity -> (taps, pad, kernel index per tap)
+
+
+def pack_deconv_weight(w, dtype=torch.float32):
+    """[Cin,Cout,5,5] -> dict[(py,px)] = (packed [Cout, R*S*Cin], R, S, pad_h, pad_w)."""
+    assert w.shape[2:] == (5, 5)
+    out = {}
+    wd = w.detach()
+    for py, (R, ph, khs) in DECONV_PHASES.items():
+        for px, (S, pw, kws) in DECONV_PHASES.items():
+            sub = wd[:, :, list(khs)][:, :, :, list(kws)]  # [Cin,Cout,R,S]
+            packed = sub.permute(1, 2, 3, 0).reshape(w.shape[1], -1).to(dtype).contiguous()
+            out[(py, px)] = (packed, R, S, ph, pw)
+    return out
+
+
+def nonneg_reparam(p, minimum):
+    """NonNegativeParametrizer.forward (reference ops/parametrizers.py:46-49)."""
+    pedestal = float(2 ** -18) ** 2
+    bound = (minimum + pedestal) ** 0.5
+    p = p.detach().float()
+    return torch.clamp(p, min=torch.tensor(bound, dtype=torch.float32, device=p.device)) ** 2 - pedestal
+
+
+def pack_gdn(beta, gamma, dtype=torch.float32):
+    """GDN (reference layers/gdn.py:62-69): gamma' as a [C][C] 1x1 weight, beta' as its bias (fp32)."""
+    return nonneg_reparam(gamma, 0.0).to(dtype).contiguous(), nonneg_reparam(beta, 1e-6).contiguous()
+
+
+def pack_entropy_bottleneck(eb_params, quantiles):
+    """[C][EB_STRIDE] fp32: softplus(matrix0..4) | bias0..4 | tanh(factor0..3) | median
+    (reference entropy_models.py:401-420, :352-354).  softplus/tanh of the
+    parameters are evaluated with the same torch ops the reference uses."""
+    m = [F.softplus(eb_params[f"_matrix{i}"].detach().float()) for i in range(5)]
+    b = [eb_params[f"_bias{i}"].detach().float() for i in range(5)]
+    f = [torch.tanh(eb_params[f"_factor{i}"].detach().float()) for i in range(4)]
+    Cn = m[0].shape[0]
+    assert m[0].shape[1:] == (3, 1) and m[1].shape[1:] == (3, 3) and m[4].shape[1:] == (1, 3), \
+        "kernel supports the reference's filters=(3,3,3,3)"
+    cols = [t.reshape(Cn, -1) for t in (*m, *b, *f)]
+    cols.append(quantiles.detach().float()[:, 0, 1:2])
+    packed = torch.cat(cols, dim=1)
+    assert packed.shape[1] == 59
+    return F.pad(packed, (0, EB_STRIDE - packed.shape[1])).contiguous()
+
+
+def scale_table(lo=0.11, hi=256.0, levels=64):
+    """get_scale_table (reference cnn.py:14-20); evaluated on the CPU so the 64
+    thresholds are bit-identical to the reference's on any device."""
+    return torch.exp(torch.linspace(math.log(lo), math.log(hi), levels))

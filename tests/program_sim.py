@@ -1,0 +1,186 @@
+"""TEST INFRASTRUCTURE -- a CPU interpreter of `rdsic_op` descriptors.
+
+Executes a `resdsic_b200.program.Program` that was *built* over CPU tensors
+(Ctx(build_only=True)) by following the semantics written in
+include/resdsic_b200.h, using torch CPU ops.  It lets the `-m "not gpu"` suite
+check the HOST-side graph builder (weight packing, deconv phase mapping,
+pixel-shuffle addressing, the slice-loop slot plan, ld/coff arithmetic) against
+the reference's golden vectors without a GPU.  It is never imported by the
+product; the CUDA kernels are checked against the same goldens with -m gpu.
+"""
+import ctypes
+
+import torch
+import torch.nn.functional as F
+
+from resdsic_b200 import _lib
+
+_TORCH_DT = {_lib.F32: torch.float32, _lib.BF16: torch.bfloat16}
+
+
+class Sim:
+    def __init__(self, prog):
+        self.prog = prog
+        self.bases = []
+        for t in prog.keep:
+            if t is not None:
+                self.bases.append((t.data_ptr(), t.data_ptr() + t.numel() * t.element_size(), t))
+
+    def _flat(self, ptr):
+        """Flat typed tensor aliasing the storage starting at `ptr`."""
+        for lo, hi, t in self.bases:
+            if lo <= ptr < hi:
+                flat = t.view(-1)
+                off = (ptr - lo) // t.element_size()
+                return flat[off:]
+        raise KeyError(f"pointer {ptr:#x} not owned by the program")
+
+    def _nhwc(self, v, B, H, W, Cn, Cfull=None):
+        """Strided [B,H,W,Cn] alias of a view (writes go through)."""
+        flat = self._flat(v.ptr)
+        if v.nchw:
+            Cf = Cn if Cfull is None else Cfull
+            return flat[: B * Cf * H * W].view(B, Cf, H, W).permute(0, 2, 3, 1)[..., :Cn]
+        return torch.as_strided(flat, (B, H, W, Cn), (H * W * v.ld, W * v.ld, v.ld, 1), v.coff)
+
+    # ------------------------------------------------------------------ ops
+    def conv(self, d):
+        x = self._nhwc(d.in_, d.B, d.H, d.W, d.Cin).float()
+        if d.a_square:
+            x = x * x
+        wflat = self._flat(d.weight)[: d.Cout * d.KH * d.KW * d.Cin].float()
+        w = wflat.view(d.Cout, d.KH, d.KW, d.Cin).permute(0, 3, 1, 2)
+        bias = self._flat(d.bias)[: d.Cout] if d.bias else None
+        need_h = (d.OH - 1) * d.stride + d.KH - d.pad_h
+        need_w = (d.OW - 1) * d.stride + d.KW - d.pad_w
+        xp = F.pad(x.permute(0, 3, 1, 2), (d.pad_w, max(0, need_w - d.W), d.pad_h, max(0, need_h - d.H)))
+        v = F.conv2d(xp, w, bias, stride=d.stride)[:, :, : d.OH, : d.OW]  # [B,Cout,OH,OW]
+        assert v.shape[2:] == (d.OH, d.OW), (v.shape, d.OH, d.OW)
+        if d.pixel_shuffle:
+            v = F.pixel_shuffle(v, 2)
+            Cv, sy, sx, oy, ox = d.Cout // 4, 1, 1, 0, 0
+        else:
+            Cv, sy, sx, oy, ox = d.Cout, d.osy, d.osx, d.ooy, d.oox
+        v = v.permute(0, 2, 3, 1)  # NHWC on the (possibly shuffled) GEMM grid
+
+        def sub(view):
+            return self._nhwc(view, d.B, d.OHt, d.OWt, Cv)[:, oy::sy, ox::sx][:, : v.shape[1], : v.shape[2]]
+
+        e = d.epilogue
+        res = sub(d.res).float() if d.res.ptr else None
+        aux = sub(d.aux).float() if d.aux.ptr else None
+        if e == _lib.EPI_GELU:
+            v = F.gelu(v)
+        elif e == _lib.EPI_RES_GELU:
+            v = F.gelu(v + res)
+        elif e == _lib.EPI_ADD_RES:
+            v = v + res
+        elif e == _lib.EPI_GATE:
+            v = aux * torch.sigmoid(v) + res
+        elif e == _lib.EPI_GDN:
+            v = res * torch.rsqrt(v)
+        elif e == _lib.EPI_IGDN:
+            v = res * torch.sqrt(v)
+        elif e == _lib.EPI_LRP:
+            v = res + 0.5 * torch.tanh(v)
+        for view in (d.out, d.out2, d.out3):
+            if view.ptr:
+                dst = sub(view)
+                dst.copy_(v.to(dst.dtype))
+
+    def attn(self, d):
+        C, heads, ws, s = d.C, d.heads, d.ws, d.shift
+        dh = C // heads
+        qkv = self._nhwc(d.qkv, d.B, d.H, d.W, 3 * C).float()
+        out = self._nhwc(d.out, d.B, d.H, d.W, C)
+        table = self._flat(d.bias_table)[: (2 * ws - 1) ** 2 * heads].view(-1, heads)
+        t = torch.arange(ws * ws)
+        hi, wi = t // ws, t % ws
+        bias = table[(hi[:, None] - hi[None] + ws - 1) * (2 * ws - 1) + (wi[:, None] - wi[None] + ws - 1)]  # [N,N,heads]
+        for wh in range(d.H // ws):
+            for ww in range(d.W // ws):
+                hy, wx = wh * ws + hi, ww * ws + wi  # shifted-frame coords of the tokens
+                oy, ox = (hy + s) % d.H, (wx + s) % d.W
+                tok = qkv[:, oy, ox]  # [B,N,3C]
+                q = tok[..., :C].reshape(d.B, -1, heads, dh).transpose(1, 2) * d.scale
+                k = tok[..., C:2 * C].reshape(d.B, -1, heads, dh).transpose(1, 2)
+                v = tok[..., 2 * C:].reshape(d.B, -1, heads, dh).transpose(1, 2)
+                a = q @ k.transpose(-1, -2) + bias.permute(2, 0, 1)
+                if s > 0:
+                    rid = 3 * ((hy >= d.H - ws).long() + (hy >= d.H - s).long()) + (wx >= d.W - ws).long() + (wx >= d.W - s).long()
+                    a = a + torch.where(rid[:, None] != rid[None, :], -100.0, 0.0)
+                o = (torch.softmax(a, -1) @ v).transpose(1, 2).reshape(d.B, -1, C)
+                out[:, oy, ox] = o.to(out.dtype)
+
+    def eb(self, d):
+        z = self._nhwc(d.z, d.B, d.h, d.w, d.C).float()
+        P = self._flat(d.params)[: d.C * _lib.EB_STRIDE].view(d.C, _lib.EB_STRIDE)
+        med = P[:, 58]
+        r = torch.round(z - med)
+        q = r + med
+
+        def logits(v):  # v [...,C]
+            a = P[:, 0:3] * v[..., None] + P[:, 33:36]
+            a = a + P[:, 46:49] * torch.tanh(a)
+            for k in range(3):
+                M = P[:, 3 + 9 * k: 12 + 9 * k].view(d.C, 3, 3)
+                a = torch.einsum("cji,...ci->...cj", M, a) + P[:, 36 + 3 * k: 39 + 3 * k]
+                a = a + P[:, 49 + 3 * k: 52 + 3 * k] * torch.tanh(a)
+            return (P[:, 30:33] * a).sum(-1) + P[:, 45]
+
+        lo, up = logits(q - 0.5), logits(q + 0.5)
+        sg = -torch.sign(lo + up)
+        lik = torch.abs(torch.sigmoid(sg * up) - torch.sigmoid(sg * lo)).clamp(min=d.lik_bound)
+        self._nhwc(d.z_hat, d.B, d.h, d.w, d.C).copy_(q)
+        n = d.B * d.C * d.h * d.w
+        self._flat(d.lik)[:n].view(d.B, d.C, d.h, d.w).copy_(lik.permute(0, 3, 1, 2))
+        if d.symbols:
+            self._flat(d.symbols)[:n].view(d.B, d.C, d.h, d.w).copy_(r.permute(0, 3, 1, 2).int())
+
+    def gc(self, d):
+        y = self._nhwc(d.y, d.B, d.h, d.w, d.Cs).float()
+        mu = self._nhwc(d.mu, d.B, d.h, d.w, d.Cs).float()
+        sc = self._nhwc(d.scale, d.B, d.h, d.w, d.Cs).float()
+        r = torch.round(y - mu)
+        yh = r + mu
+        v = torch.abs(yh - mu)
+        s = torch.clamp(sc, min=torch.tensor(d.scale_bound))
+        c = float(-(2 ** -0.5))
+        lik = (0.5 * torch.erfc(c * ((0.5 - v) / s)) - 0.5 * torch.erfc(c * ((-0.5 - v) / s))).clamp(min=d.lik_bound)
+        table = self._flat(d.table)[: d.n_table]
+        idx = torch.searchsorted(table[:-1].contiguous(), s.contiguous(), right=False).int()
+        for k in range(3):
+            if d.y_hat[k].ptr:
+                dst = self._nhwc(d.y_hat[k], d.B, d.h, d.w, d.Cs)
+                dst.copy_(yh.to(dst.dtype))
+        n = d.B * d.Ctot * d.h * d.w
+        sl = slice(d.lik_coff, d.lik_coff + d.Cs)
+        self._flat(d.lik)[:n].view(d.B, d.Ctot, d.h, d.w)[:, sl].copy_(lik.permute(0, 3, 1, 2))
+        if d.symbols:
+            self._flat(d.symbols)[:n].view(d.B, d.Ctot, d.h, d.w)[:, sl].copy_(r.permute(0, 3, 1, 2).int())
+        if d.indexes:
+            self._flat(d.indexes)[:n].view(d.B, d.Ctot, d.h, d.w)[:, sl].copy_(idx.permute(0, 3, 1, 2))
+
+    def copy(self, d):
+        src = self._nhwc(d.src, d.B, d.H, d.W, d.C).float()
+        if d.op == 1:
+            src = F.gelu(src)
+        dst = self._nhwc(d.dst, d.B, d.H, d.W, d.C)
+        dst.copy_(src.to(dst.dtype))
+
+    def ln(self, d):
+        x = torch.as_strided(self._flat(d.in_.ptr), (d.rows, d.C), (d.in_.ld, 1), d.in_.coff).float()
+        g, b = self._flat(d.gamma)[: d.C], self._flat(d.beta)[: d.C]
+        out = torch.as_strided(self._flat(d.out.ptr), (d.rows, d.C), (d.out.ld, 1), d.out.coff)
+        out.copy_(F.layer_norm(x, (d.C,), g, b, d.eps).to(out.dtype))
+
+    def run(self):
+        disp = {_lib.OP_CONV: ("conv", self.conv), _lib.OP_ATTN: ("attn", self.attn), _lib.OP_EB: ("eb", self.eb),
+                _lib.OP_GC: ("gc", self.gc), _lib.OP_COPY: ("copy", self.copy), _lib.OP_LN: ("ln", self.ln)}
+        for op in self.prog.ops:
+            name, fn = disp[op.kind]
+            fn(getattr(op.u, name))
+
+
+def run_on_cpu(prog):
+    Sim(prog).run()

@@ -139,7 +139,7 @@ class GaussianConditional(EntropyModel):
         (reference cnn.py:14-20) when update() has not filled the buffer."""
         t = self.scale_table
         if t.numel() == 0:
-            t = packing.scale_table()
+            t = self.__dict__.setdefault("_default_table", packing.scale_table())
         return self._packed(("table", str(device)), (t,), lambda: t.detach().float().to(device).contiguous())
 
     def emit(self, ctx: Ctx, y, scale, mu, lik, lik_coff, Ctot, y_hat_dsts=(), symbols=None, indexes=None):

@@ -1,0 +1,75 @@
+"""-m gpu: model-level parity of the CUDA forward against the reference goldens
+and the oracle, plus size-independent properties at BASELINE sizes."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import resdsic_b200
+from oracle import wacnn_oracle as O
+from oracle import weights
+from tests.conftest import GOLDEN
+from tests.golden.make_golden import CASES
+from tests.helpers import compare_forward
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def model(synthetic_sd):
+    m = resdsic_b200.WACNN().eval()
+    m.load_state_dict(synthetic_sd, strict=True)
+    return m.to(DEV)
+
+
+def _collect(model, x):
+    r = model.symbols_and_indexes(x)
+    p = next(iter(model._plans.values()))
+    return dict(y=p.y.to_nchw().cpu().numpy(), z=p.z.to_nchw().cpu().numpy(),
+                latent_means=p.means.channels(0, 320).to_nchw().float().cpu().numpy(),
+                latent_scales=p.scales.channels(0, 320).to_nchw().float().cpu().numpy(),
+                y_hat=p.y_hat.to_nchw().cpu().numpy(), x_hat=r["x_hat"].cpu().numpy(),
+                lik_y=r["likelihoods"]["y"].cpu().numpy(), lik_z=r["likelihoods"]["z"].cpu().numpy(),
+                symbols=r["y_symbols"].cpu().numpy(), indexes=r["y_indexes"].cpu().numpy())
+
+
+@pytest.mark.parametrize("graph", [False, True])
+@pytest.mark.parametrize("case", list(CASES))
+def test_fp32_forward_vs_reference_golden(model, case, graph):
+    B, H, W = CASES[case]
+    g = np.load(os.path.join(GOLDEN, f"wacnn_{case}.npz"))
+    model.set_precision("fp32")
+    model.use_cuda_graph = graph
+    got = _collect(model, weights.make_image(B, H, W, seed=0).to(DEV))
+    stats = compare_forward(got, g, B * H * W, cont_tol=5e-4)
+    print(case, "graph" if graph else "eager", stats)
+
+
+def test_forward_dict_contract_and_determinism(model):
+    model.set_precision("fp32")
+    x = weights.make_image(2, 64, 128, seed=3).to(DEV)
+    out = model(x)
+    assert set(out) == {"x_hat", "likelihoods"} and set(out["likelihoods"]) == {"y", "z"}
+    assert out["x_hat"].shape == (2, 3, 64, 128) and out["likelihoods"]["y"].shape == (2, 320, 4, 8)
+    assert out["likelihoods"]["z"].shape == (2, 192, 1, 2)
+    a = {k: v.clone() for k, v in (("x", out["x_hat"]), ("y", out["likelihoods"]["y"]))}
+    out2 = model(x)
+    assert torch.equal(a["x"], out2["x_hat"]) and torch.equal(a["y"], out2["likelihoods"]["y"])
+    # batch independence: image 1 alone gives the same bits as image 1 inside the batch
+    solo = model(x[1:2].contiguous())
+    assert torch.equal(solo["x_hat"][0], a["x"][1])
+
+
+def test_fp32_forward_vs_oracle_kodak_size(model, synthetic_sd, scale_table):
+    """One 512x768 image (BASELINE config 3 shape) against the CPU oracle."""
+    model.set_precision("fp32")
+    x = weights.make_image(1, 512, 768, seed=1)
+    ref = O.forward(synthetic_sd, x, scale_table, collect=True)
+    g = dict(y=ref["y"].numpy(), z=ref["z"].numpy(), latent_means=ref["latent_means"].numpy(),
+             latent_scales=ref["latent_scales"].numpy(), y_hat=ref["y_hat"].numpy(), x_hat=ref["x_hat"].numpy(),
+             lik_y=ref["likelihoods"]["y"].numpy(), lik_z=ref["likelihoods"]["z"].numpy(),
+             symbols=ref["symbols"].numpy(), indexes=ref["indexes"].numpy())
+    stats = compare_forward(_collect(model, x.to(DEV)), g, 512 * 768, cont_tol=1e-3, flip_frac=2e-2, yhat_frac=1e-1)
+    print("kodak fp32", stats)

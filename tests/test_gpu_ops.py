@@ -1,0 +1,120 @@
+"""-m gpu: op-level parity of the CUDA kernels (through the C ABI) against the
+oracle and the reference's golden vectors, on identical inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import resdsic_b200
+from oracle import wacnn_oracle as O
+from oracle import weights
+from resdsic_b200.layers import Ctx
+from tests.conftest import GOLDEN
+from tests.golden.make_golden import op_inputs
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def model(synthetic_sd):
+    m = resdsic_b200.WACNN().eval()
+    m.load_state_dict(synthetic_sd, strict=True)
+    return m.to(DEV)
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLDEN, "ops.npz"))
+
+
+def test_library_loaded_is_in_tree():
+    L = resdsic_b200._lib.lib()
+    assert os.path.realpath(resdsic_b200._lib.LIB_PATH).startswith(os.path.realpath(os.path.dirname(resdsic_b200.__file__)))
+    assert L.rdsic_abi_version() == 1
+
+
+def test_gaussian_conditional_bit_exact_integers(model, gold, scale_table):
+    """symbols / indexes / y_hat bit-exact given identical (y, mu, scale); likelihood to fp32 erfc ulps."""
+    i = op_inputs()
+    gc = model.gaussian_conditional
+    y, mu, sc = (i[k].to(DEV) for k in ("gc_y", "gc_mu", "gc_scale"))
+    out, lik = gc(y, sc, mu)
+    np.testing.assert_array_equal(out.cpu().numpy(), gold["gc_yhat"])
+    np.testing.assert_array_equal(gc.quantize(y, "symbols", mu).cpu().numpy(), gold["gc_sym"])
+    np.testing.assert_array_equal(gc.quantize(y, "dequantize", mu).cpu().numpy(), gold["gc_yhat"])
+    np.testing.assert_array_equal(gc.build_indexes(sc).cpu().numpy(), gold["gc_idx"])
+    # CUDA erfcf vs the CPU libm erfc: a few ulps each, amplified by the upper-lower cancellation
+    np.testing.assert_allclose(lik.cpu().numpy(), gold["gc_lik"], rtol=3e-4, atol=5e-7)
+    # vs the oracle on a second, larger seeded input incl. every table threshold
+    y2 = weights.hash_symmetric("gpu.gc.y", (3, 32, 24, 40), 20.0)
+    mu2 = weights.hash_symmetric("gpu.gc.mu", (3, 32, 24, 40), 5.0)
+    s2 = weights.hash_uniform("gpu.gc.s", (3, 32, 24, 40)) ** 5 * 400 - 0.1
+    s2.view(-1)[:64] = scale_table
+    s2.view(-1)[64:128] = torch.nextafter(scale_table, torch.tensor(0.0))
+    s2.view(-1)[128:192] = torch.nextafter(scale_table, torch.tensor(1e9))
+    assert torch.equal(gc.build_indexes(s2.to(DEV)).cpu(), O.gc_indexes(s2, scale_table))
+    assert torch.equal(gc.quantize(y2.to(DEV), "symbols", mu2.to(DEV)).cpu(), O.gc_symbols(y2, mu2))
+    yh = torch.round(y2 - mu2) + mu2
+    _, lik2 = gc(y2.to(DEV), s2.to(DEV), mu2.to(DEV))
+    np.testing.assert_allclose(lik2.cpu().numpy(), O.gaussian_likelihood(yh, s2, mu2).numpy(), rtol=3e-4, atol=5e-7)
+
+
+def test_entropy_bottleneck(model, gold):
+    z = op_inputs()["eb_z"]
+    zh, lik = model.entropy_bottleneck(z.to(DEV))
+    np.testing.assert_array_equal(zh.cpu().numpy(), gold["eb_zhat"])
+    np.testing.assert_allclose(lik.cpu().numpy(), gold["eb_lik"], rtol=1e-4, atol=1e-9)
+
+
+@pytest.mark.parametrize("name,mod,key", [
+    ("attn8", lambda m: m.g_a[4].conv_b[0], "attn8_x"),
+    ("attn4", lambda m: m.g_a[8].conv_b[0], "attn4_x"),
+    ("gdn", lambda m: m.g_a[1], "gdn_x"),
+    ("igdn", lambda m: m.g_s[2], "gdn_x"),
+    ("deconv", lambda m: m.g_s[3], "deconv_x"),
+    ("block8", lambda m: m.g_a[4], "block8_x"),
+    ("ru", lambda m: m.g_a[4].conv_a[0], "block8_x"),
+])
+def test_layers_fp32_vs_reference_golden(model, gold, name, mod, key):
+    model.set_precision("fp32")
+    x = op_inputs()[key].to(DEV)
+    out = mod(model)(x).cpu().numpy()
+    np.testing.assert_allclose(out, gold[name], rtol=2e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("cin,cout,k,s,hw", [(3, 192, 5, 2, (34, 50)), (192, 192, 5, 2, (17, 24)), (96, 96, 3, 1, (9, 7)),
+                                             (320, 288, 3, 2, (8, 12)), (352, 224, 3, 1, (5, 6)), (192, 96, 1, 1, (8, 8))])
+def test_conv_shapes_vs_oracle(cin, cout, k, s, hw):
+    """Ragged sizes (M not a tile multiple, odd H/W, stride 2) against torch CPU conv."""
+    from resdsic_b200.layers import Conv2d
+    conv = Conv2d(cin, cout, k, s)
+    with torch.no_grad():
+        conv.weight.copy_(weights.hash_symmetric(f"t.w{cin}{cout}{k}", conv.weight.shape, (3.0 / (cin * k * k)) ** 0.5))
+        conv.bias.copy_(weights.hash_symmetric(f"t.b{cin}{cout}{k}", conv.bias.shape, 0.1))
+    x = weights.hash_symmetric(f"t.x{cin}{hw}", (2, cin, *hw), 1.0)
+    ref = torch.nn.functional.conv2d(x, conv.weight, conv.bias, stride=s, padding=k // 2)
+    out = conv.to(DEV)(x.to(DEV)).cpu()
+    np.testing.assert_allclose(out.detach().numpy(), ref.detach().numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_subpel_and_gelu_vs_oracle(model, synthetic_sd):
+    x = weights.hash_symmetric("t.subpel", (2, 192, 3, 5), 1.0)
+    ref = torch.nn.functional.pixel_shuffle(O.conv(x, synthetic_sd, "h_mean_s.2.0"), 2)
+    out = model.h_mean_s[2](x.to(DEV)).cpu()
+    np.testing.assert_allclose(out.numpy(), ref.numpy(), rtol=1e-4, atol=1e-4)
+    from resdsic_b200.layers import GELU
+    np.testing.assert_allclose(GELU()(x.to(DEV)).cpu().numpy(), torch.nn.functional.gelu(x).numpy(), rtol=1e-5, atol=1e-6)
+    out = model.h_a(weights.hash_symmetric("t.ha", (1, 320, 8, 12), 1.0).to(DEV)).cpu()
+    ref = O.h_a(weights.hash_symmetric("t.ha", (1, 320, 8, 12), 1.0), synthetic_sd)
+    np.testing.assert_allclose(out.numpy(), ref.numpy(), rtol=2e-4, atol=2e-4)
+
+
+def test_error_paths(model):
+    with pytest.raises(ValueError):
+        model.g_a[4].conv_b[0](torch.zeros(1, 192, 12, 16, device=DEV))  # not a multiple of the window
+    with pytest.raises(ValueError):
+        model.gaussian_conditional.quantize(torch.zeros(1, 32, 4, 4, device=DEV), "bogus")
+    with pytest.raises(ValueError, match="multiple of 64"):
+        model(torch.zeros(1, 3, 100, 64, device=DEV))

@@ -203,7 +203,7 @@ def run_ours(args):
     # ---- per-kernel-family device time of one step (eager, CUDA events around every launch)
     fam = None
     if rank == 0:
-        fam = profile_families(model, x_dev)
+        fam = profile_families(model, x_dev, args.dump_ops)
 
     if rank == 0:
         peaks = load_peaks()
@@ -246,7 +246,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def profile_families(model, x_dev):
+def profile_families(model, x_dev, dump=None):
     """Device time per kernel family for ONE forward, CUDA events around every launch (eager)."""
     import ctypes as C
 
@@ -270,11 +270,22 @@ def profile_families(model, x_dev):
             _lib.check(L.rdsic_run_program(one, 1, stream, None, None))
             evs[i + 1].record()
         torch.cuda.synchronize()
-    fam = {}
+    fam, per_op = {}, []
     for i in range(n):
         k = names[prog.ops[i].kind]
+        t = evs[i].elapsed_time(evs[i + 1])
         ms, cnt = fam.get(k, (0.0, 0))
-        fam[k] = (ms + evs[i].elapsed_time(evs[i + 1]), cnt + 1)
+        fam[k] = (ms + t, cnt + 1)
+        rec = {"i": i, "kind": k, "ms": round(t, 4)}
+        if k == "conv":
+            c = prog.ops[i].u.conv
+            flop = 2.0 * c.B * c.OH * c.OW * c.Cout * c.KH * c.KW * c.Cin
+            rec.update(M=c.B * c.OH * c.OW, N=c.Cout, K=c.KH * c.KW * c.Cin, k=f"{c.KH}x{c.KW}s{c.stride}",
+                       epi=c.epilogue, tc=int(c.w_dtype), tflops=round(flop / (t * 1e-3) / 1e12, 2))
+        per_op.append(rec)
+    if dump:
+        with open(dump, "w") as fh:
+            json.dump(per_op, fh, indent=0)
     return fam
 
 
@@ -284,9 +295,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("RESDSIC_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("RESDSIC_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-ops", default=None, help="write the per-launch device times of one step to this JSON file")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -89,6 +89,8 @@ typedef struct rdsic_conv_desc {
   rdsic_view aux;         /* gate operand `a` */
   rdsic_view out2;        /* optional extra copies of the result (slice-loop support buffers) */
   rdsic_view out3;
+  int32_t out2_square;    /* out2 receives result^2 (feeds the next GDN's beta + gamma @ x^2 contraction) */
+  int32_t pad_;
 } rdsic_conv_desc;
 
 /* Fused shifted-window attention core: replaces roll + window_partition +
@@ -144,7 +146,7 @@ typedef struct rdsic_copy_desc {
   rdsic_view src;
   rdsic_view dst;
   int32_t B, H, W, C;
-  int32_t op; /* 0 copy/cast, 1 gelu */
+  int32_t op; /* 0 copy/cast, 1 gelu, 2 square */
 } rdsic_copy_desc;
 
 /* LayerNorm over channels (stf Swin block, TCM/tcm.py:214-236). */

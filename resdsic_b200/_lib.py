@@ -32,6 +32,7 @@ class ConvDesc(C.Structure):
         ("ooy", C.c_int32), ("oox", C.c_int32),
         ("pixel_shuffle", C.c_int32), ("epilogue", C.c_int32), ("a_square", C.c_int32),
         ("out", View), ("res", View), ("aux", View), ("out2", View), ("out3", View),
+        ("out2_square", C.c_int32), ("pad_", C.c_int32),
     ]
 
 

@@ -80,7 +80,7 @@ def build(force=False, verbose=False):
             raise RuntimeError(f"nvcc failed for {src}:\n{out}")
         objs.append(obj)
     link = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-            "-Xcompiler", "-fPIC", "-lcudart", "-lcuda"]
+            "-Xcompiler", "-fPIC", "-lcudart"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")

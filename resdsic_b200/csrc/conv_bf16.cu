@@ -1,8 +1,487 @@
-// bf16 tensor-core implicit-GEMM convolution (tcgen05 / TMEM) -- placeholder until
-// the sm_100a kernel lands; fails loudly rather than falling back.
+// bf16 tensor-core implicit-GEMM convolution for sm_100a: TMA -> shared memory ->
+// tcgen05.mma (accumulator in TMEM) -> tcgen05.ld epilogue.
+//
+// Replaces, per launch, one reference nn.Conv2d / ConvTranspose2d phase / nn.Linear /
+// GDN 1x1 contraction (WACNN/utils.py:116-134, layers/layers.py:29-43,
+// layers/gdn.py:62-75, layers/win_attention.py:91,113) plus its elementwise tail
+// (RDSIC_EPI_*), on channels-last bf16 activations.
+//
+// GEMM view: M = output pixels, N = Cout, K = taps x Cin.
+//   * The M tile is a TH x TW patch of output pixels of one image (TH*TW = 128).  For
+//     filter tap (r,s) and channel block c0 its A operand is ONE 4-D TMA box
+//     {64 ch, TW, TH, 1} of the NHWC input at (c0, ox0*stride-pad+s, oy0*stride-pad+r, b),
+//     with TMA element strides = conv stride: im2col, zero padding (out-of-bounds fill),
+//     stride-2 sampling, torch.cat (channel offset/ld) and the deconv phase shifts are all
+//     folded into TMA coordinates -- nothing is materialised.
+//   * B (weights, [Cout][taps*Cin] bf16) is a 2-D TMA box {64, BN}.
+//   * Both land in 128B-swizzled K-major tiles that tcgen05.mma consumes directly; the
+//     accumulator (128 x BN fp32) lives in TMEM and is read back by 4 epilogue warps.
+//   * Warp roles: warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, warps 2-5 =
+//     epilogue (TMEM lane quarter = warp_id % 4).
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
+namespace {
+
+constexpr int BM = 128;        // UMMA M (cta_group::1)
+constexpr int BK = 64;         // bf16 elements per 128-byte swizzle row
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_STAGES = 8;
+constexpr uint32_t SPIN_LIMIT = 1u << 22;  // a lost mbarrier signal traps instead of hanging the GPU
+
+struct TcGeom {
+  int TH, TW, tiles_y, tiles_x;
+  int BN, n_tiles, kb_per_tap, num_k_iters, num_stages, tmem_cols;
+  int b_stage_bytes;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by ONE thread
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, rows at 128 B pitch,
+// 8-row groups 1024 B apart (SBO), descriptor version 1 (Blackwell).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address  [0,14)
+  d |= (uint64_t)1 << 16;                       // LBO (ignored for swizzled K-major) [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;             // SBO [32,46)
+  d |= (uint64_t)1 << 46;                       // version = 1 [46,48)
+  d |= (uint64_t)2 << 61;                       // layout type SWIZZLE_128B [61,64)
+  return d;
+}
+
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=bn
+__device__ __forceinline__ uint32_t make_idesc(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ------------------------------------------------------------------ epilogue helpers
+template <int EPI>
+__device__ __forceinline__ float epi_apply(float v, float res, float aux) {
+  if (EPI == RDSIC_EPI_GELU) return gelu_erf(v);
+  if (EPI == RDSIC_EPI_RES_GELU) return gelu_erf(v + res);
+  if (EPI == RDSIC_EPI_ADD_RES) return v + res;
+  if (EPI == RDSIC_EPI_GATE) return aux * sigmoid_f(v) + res;
+  if (EPI == RDSIC_EPI_GDN) return res * rsqrtf(v);
+  if (EPI == RDSIC_EPI_IGDN) return res * sqrtf(v);
+  if (EPI == RDSIC_EPI_LRP) return res + 0.5f * tanhf(v);
+  return v;
+}
+
+// 16 consecutive channels of one pixel, 16-byte vector accesses (host guarantees the alignment)
+__device__ __forceinline__ void load16(const rdsic_view& vw, size_t elem, float* o) {
+  if (vw.dtype == RDSIC_BF16) {
+    const uint4* p = reinterpret_cast<const uint4*>((const __nv_bfloat16*)vw.ptr + elem);
+    const uint4 q0 = p[0], q1 = p[1];
+    const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      o[2 * i] = __uint_as_float(w[i] << 16);
+      o[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  } else {
+    const float4* p = reinterpret_cast<const float4*>((const float*)vw.ptr + elem);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 f = p[i];
+      o[4 * i] = f.x; o[4 * i + 1] = f.y; o[4 * i + 2] = f.z; o[4 * i + 3] = f.w;
+    }
+  }
+}
+
+__device__ __forceinline__ void store16(const rdsic_view& vw, size_t elem, const float* v, bool sq) {
+  if (vw.dtype == RDSIC_BF16) {
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float a0 = v[2 * i], a1 = v[2 * i + 1];
+      if (sq) { a0 *= a0; a1 *= a1; }
+      __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    uint4* p = reinterpret_cast<uint4*>((__nv_bfloat16*)vw.ptr + elem);
+    p[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    p[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  } else {
+    float4* p = reinterpret_cast<float4*>((float*)vw.ptr + elem);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 f = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      if (sq) { f.x *= f.x; f.y *= f.y; f.z *= f.z; f.w *= f.w; }
+      p[i] = f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ the kernel
+// EPI: fused epilogue (compile time, keeps the epilogue's code small enough for the I-cache);
+// PLAIN: every output/residual view is channels-last with 16-element-aligned rows (vector path),
+//        otherwise the generic scalar addressing (NCHW output, PixelShuffle) is used.
+template <int EPI, bool PLAIN>
+__global__ void __launch_bounds__(NUM_THREADS, 2)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const rdsic_conv_desc d, const TcGeom g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle atoms
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int stage_bytes = A_STAGE_BYTES + g.b_stage_bytes;
+  uint64_t* full_bar = (uint64_t*)(smem + (size_t)g.num_stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* acc_bar = empty_bar + MAX_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(acc_bar + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+
+  // ---- tile coordinates
+  int t = blockIdx.x;
+  const int tx = t % g.tiles_x;
+  t /= g.tiles_x;
+  const int ty = t % g.tiles_y;
+  const int b = t / g.tiles_y;
+  const int oy0 = ty * g.TH, ox0 = tx * g.TW;
+  const int n0 = blockIdx.y * g.BN;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_b) : "memory");
+    for (int s = 0; s < g.num_stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // one warp allocates TMEM (and later frees it)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(g.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      const uint32_t tx_bytes = (uint32_t)stage_bytes;
+      for (int it = 0; it < g.num_k_iters; ++it) {
+        const int s = it % g.num_stages;
+        const uint32_t ph = (uint32_t)(it / g.num_stages) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        const int tap = it / g.kb_per_tap, cb = it - tap * g.kb_per_tap;
+        const int r = tap / d.KW, sx = tap - r * d.KW;
+        uint8_t* a_dst = smem + (size_t)s * stage_bytes;
+        mbar_expect_tx(&full_bar[s], tx_bytes);
+        tma_load_4d(a_dst, &tmap_a, &full_bar[s], cb * BK, ox0 * d.stride - d.pad_w + sx, oy0 * d.stride - d.pad_h + r, b);
+        tma_load_2d(a_dst + A_STAGE_BYTES, &tmap_b, &full_bar[s], tap * d.Cin + cb * BK, n0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(g.BN);
+      for (int it = 0; it < g.num_k_iters; ++it) {
+        const int s = it % g.num_stages;
+        const uint32_t ph = (uint32_t)(it / g.num_stages) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tcgen05_fence_after();
+        const int cb = it % g.kb_per_tap;
+        const int kc = min(BK, d.Cin - cb * BK) / 16;  // valid 16-wide K steps in this block
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint64_t da = make_sw128_desc(a_addr), db = make_sw128_desc(a_addr + A_STAGE_BYTES);
+        for (int k = 0; k < kc; ++k)  // +32 bytes (= 2 x 16 B units) per 16 bf16 of K inside the swizzle atom
+          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        tcgen05_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+      }
+      tcgen05_commit(acc_bar);  // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    constexpr bool NEED_RES = EPI == RDSIC_EPI_RES_GELU || EPI == RDSIC_EPI_ADD_RES || EPI == RDSIC_EPI_GATE ||
+                              EPI == RDSIC_EPI_GDN || EPI == RDSIC_EPI_IGDN || EPI == RDSIC_EPI_LRP;
+    constexpr bool NEED_AUX = EPI == RDSIC_EPI_GATE;
+    const int q = warp % 4;  // TMEM lane quarter this warp may access
+    const int ml = q * 32 + lane;
+    const int oy = oy0 + ml / g.TW, ox = ox0 + ml % g.TW;
+    const bool row_ok = oy < d.OH && ox < d.OW;
+    const size_t pix = ((size_t)b * d.OHt + (oy * d.osy + d.ooy)) * d.OWt + (ox * d.osx + d.oox);
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+
+    mbar_wait(acc_bar, 0);
+    tcgen05_fence_after();
+    for (int j = 0; j < g.BN / 16; ++j) {
+      float v[16];
+      tmem_ld16(trow + (uint32_t)(j * 16), v);
+      const int nb = n0 + j * 16;
+      if (!row_ok || nb >= d.Cout) continue;
+      if (PLAIN) {
+        if (d.bias) {
+          const float4* bp = reinterpret_cast<const float4*>(d.bias + nb);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 f = __ldg(bp + i);
+            v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
+          }
+        }
+        float res[16], aux[16];
+        if (NEED_RES) load16(d.res, pix * (size_t)d.res.ld + d.res.coff + nb, res);
+        if (NEED_AUX) load16(d.aux, pix * (size_t)d.aux.ld + d.aux.coff + nb, aux);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = epi_apply<EPI>(v[i], NEED_RES ? res[i] : 0.f, NEED_AUX ? aux[i] : 0.f);
+        store16(d.out, pix * (size_t)d.out.ld + d.out.coff + nb, v, false);
+        if (d.out2.ptr) store16(d.out2, pix * (size_t)d.out2.ld + d.out2.coff + nb, v, d.out2_square != 0);
+        if (d.out3.ptr) store16(d.out3, pix * (size_t)d.out3.ld + d.out3.coff + nb, v, false);
+      } else {
+        const int HWt = d.OHt * d.OWt;
+        const int Cview = d.pixel_shuffle ? d.Cout / 4 : d.Cout;
+        for (int i = 0; i < 16; ++i) {  // deliberately not unrolled: rare path, keep the code small
+          const int n = nb + i;
+          if (n >= d.Cout) break;
+          float val = v[i] + (d.bias ? __ldg(d.bias + n) : 0.f);
+          int c = n;
+          size_t px = pix;
+          if (d.pixel_shuffle) {
+            c = n >> 2;
+            px = ((size_t)b * d.OHt + (2 * oy + ((n >> 1) & 1))) * d.OWt + (2 * ox + (n & 1));
+          }
+          float res = 0.f, aux = 0.f;
+          if (NEED_RES) res = ld_elem(d.res.ptr, d.res.dtype, view_index(d.res, px, c, HWt, Cview));
+          if (NEED_AUX) aux = ld_elem(d.aux.ptr, d.aux.dtype, view_index(d.aux, px, c, HWt, Cview));
+          val = epi_apply<EPI>(val, res, aux);
+          st_elem(d.out.ptr, d.out.dtype, view_index(d.out, px, c, HWt, Cview), val);
+          if (d.out2.ptr)
+            st_elem(d.out2.ptr, d.out2.dtype, view_index(d.out2, px, c, HWt, Cview), d.out2_square ? val * val : val);
+          if (d.out3.ptr) st_elem(d.out3.ptr, d.out3.dtype, view_index(d.out3, px, c, HWt, Cview), val);
+        }
+      }
+    }
+  }
+
+  // ---- teardown
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(g.tmem_cols));
+  }
+}
+
+typedef void (*ConvTcKernel)(const CUtensorMap, const CUtensorMap, const rdsic_conv_desc, const TcGeom);
+
+template <bool PLAIN>
+ConvTcKernel pick_kernel(int epi) {
+  switch (epi) {
+    case RDSIC_EPI_GELU: return conv_tc_kernel<RDSIC_EPI_GELU, PLAIN>;
+    case RDSIC_EPI_RES_GELU: return conv_tc_kernel<RDSIC_EPI_RES_GELU, PLAIN>;
+    case RDSIC_EPI_ADD_RES: return conv_tc_kernel<RDSIC_EPI_ADD_RES, PLAIN>;
+    case RDSIC_EPI_GATE: return conv_tc_kernel<RDSIC_EPI_GATE, PLAIN>;
+    case RDSIC_EPI_GDN: return conv_tc_kernel<RDSIC_EPI_GDN, PLAIN>;
+    case RDSIC_EPI_IGDN: return conv_tc_kernel<RDSIC_EPI_IGDN, PLAIN>;
+    case RDSIC_EPI_LRP: return conv_tc_kernel<RDSIC_EPI_LRP, PLAIN>;
+    default: return conv_tc_kernel<RDSIC_EPI_NONE, PLAIN>;
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;  // benign race: every thread resolves the same pointer
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+int pick_bn(int cout) {
+  // largest multiple of 16 <= 256 that tiles ceil16(Cout) without remainder (so no wasted MMA columns)
+  const int c16 = (cout + 15) / 16 * 16;
+  if (c16 <= 256) return c16;
+  for (int bn = 256; bn >= 16; bn -= 16)
+    if (c16 % bn == 0) return bn;
+  return 128;
+}
+
+}  // namespace
+
+int rdsic_conv_validate(const rdsic_conv_desc* d);
+
 int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
-  (void)d; (void)stream;
-  return RDSIC_E_UNSUPPORTED;
+  int rc = rdsic_conv_validate(d);
+  if (rc) return rc;
+  // tensor-core path requirements (the host packs weights / lays out activations accordingly)
+  RDSIC_CHECK_ARG(d->in.dtype == RDSIC_BF16 && !d->in.nchw && !d->a_square);
+  RDSIC_CHECK_ARG(d->Cin % 16 == 0);
+  if (d->in.ld % 8 || d->in.coff % 8 || ((uintptr_t)d->in.ptr % 16) || ((uintptr_t)d->weight % 16)) return RDSIC_E_ALIGN;
+  RDSIC_CHECK_ARG(d->stride == 1 || d->stride == 2);
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return RDSIC_E_UNSUPPORTED;
+
+  TcGeom g;
+  int B = d->B, H = d->H, W = d->W, OH = d->OH, OW = d->OW;
+  // pointwise GEMMs over plain NHWC tensors: flatten all pixels into one row of tiles
+  const bool flat = d->KH == 1 && d->KW == 1 && d->stride == 1 && d->pad_h == 0 && d->pad_w == 0 && !d->pixel_shuffle &&
+                    !d->out.nchw && !d->res.nchw && !d->aux.nchw && d->osy == 1 && d->osx == 1 && d->ooy == 0 &&
+                    d->oox == 0 && OH == H && OW == W && d->OHt == OH && d->OWt == OW;
+  rdsic_conv_desc dd = *d;
+  if (flat) {
+    W = OW = B * H * W;
+    H = OH = 1;
+    B = 1;
+    dd.B = 1; dd.H = 1; dd.W = W; dd.OH = 1; dd.OW = OW; dd.OHt = 1; dd.OWt = OW;
+    g.TH = 1; g.TW = 128;
+  } else {
+    // patch shape TH x TW (TH*TW = 128): minimise the covered area (= wasted rows), prefer wide patches
+    long best = -1;
+    for (int tw = 128; tw >= 1; tw /= 2) {
+      const int th = BM / tw;
+      const long area = (long)ceil_div(OW, tw) * tw * ceil_div(OH, th) * th;
+      if (best < 0 || area < best) { best = area; g.TW = tw; g.TH = th; }
+    }
+  }
+  g.tiles_x = ceil_div(OW, g.TW);
+  g.tiles_y = ceil_div(OH, g.TH);
+  g.BN = pick_bn(d->Cout);
+  g.n_tiles = ceil_div(d->Cout, g.BN);
+  g.kb_per_tap = ceil_div(d->Cin, BK);
+  g.num_k_iters = d->KH * d->KW * g.kb_per_tap;
+  g.b_stage_bytes = g.BN * BK * 2;
+  const int stage_bytes = A_STAGE_BYTES + g.b_stage_bytes;
+  // Pipeline depth / occupancy: short-K GEMMs (pointwise layers) are epilogue-dominated, so keep the smem
+  // footprint under half an SM and let two CTAs overlap one's epilogue with the other's main loop;
+  // long-K GEMMs take the whole SM with a deep TMA ring.
+  static const int tune_budget_kb = getenv("RDSIC_TC_SMEM_KB") ? atoi(getenv("RDSIC_TC_SMEM_KB")) : 0;
+  static const int tune_short_k = getenv("RDSIC_TC_SHORT_K") ? atoi(getenv("RDSIC_TC_SHORT_K")) : 6;
+  int budget = (g.num_k_iters <= tune_short_k ? 108 : 200) * 1024;
+  if (tune_budget_kb > 0) budget = tune_budget_kb * 1024;
+  int stages = budget / stage_bytes;
+  if (stages < 2) stages = (200 * 1024) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages > g.num_k_iters) stages = g.num_k_iters;
+  if (stages < 1) return RDSIC_E_ARG;
+  g.num_stages = stages;
+  g.tmem_cols = 32;
+  while (g.tmem_cols < g.BN) g.tmem_cols *= 2;
+  RDSIC_CHECK_ARG(g.TW * d->stride <= 256 && g.TH * d->stride <= 256);
+
+  // ---- tensor maps
+  CUtensorMap ta, tb;
+  {
+    const cuuint64_t ld_b = (cuuint64_t)d->in.ld * 2;
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {ld_b, ld_b * W, ld_b * W * H};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(g.TW * d->stride), (cuuint32_t)(g.TH * d->stride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+    void* base = (void*)((const __nv_bfloat16*)d->in.ptr + d->in.coff);
+    CUresult r = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return RDSIC_E_ARG;
+  }
+  {
+    const int K = d->KH * d->KW * d->Cin;
+    const int n_rows = g.n_tiles * g.BN;  // host pads the packed weight to this many rows
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)n_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)g.BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)d->weight, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return RDSIC_E_ARG;
+  }
+
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * MAX_STAGES + 1) * 8 + 16;
+  // vector epilogue needs channels-last views whose rows start on 16-element boundaries
+  auto vec_ok = [](const rdsic_view& v) {
+    return !v.ptr || (!v.nchw && v.ld % 8 == 0 && v.coff % 8 == 0 && ((uintptr_t)v.ptr % 16) == 0);
+  };
+  const bool plain = !d->pixel_shuffle && d->Cout % 16 == 0 && vec_ok(d->out) && vec_ok(d->out2) && vec_ok(d->out3) &&
+                     vec_ok(d->res) && vec_ok(d->aux) && (!d->bias || ((uintptr_t)d->bias % 16) == 0);
+  ConvTcKernel kern = plain ? pick_kernel<true>(d->epilogue) : pick_kernel<false>(d->epilogue);
+  // opt in to >48 KB dynamic smem: per (device, kernel); idempotent, so a race between host threads is harmless
+  static bool attr_set[16][2][8] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool track = dev >= 0 && dev < 16;
+  if (!track || !attr_set[dev][plain][d->epilogue]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    if (track) attr_set[dev][plain][d->epilogue] = true;
+  }
+  dim3 grid(B * g.tiles_y * g.tiles_x, g.n_tiles);
+  kern<<<grid, NUM_THREADS, smem, stream>>>(ta, tb, dd, g);
+  return rdsic_launch_status();
 }

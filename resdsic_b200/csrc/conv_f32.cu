@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(NT) conv_f32_kernel(const rdsic_conv_desc d) {
       if (need_aux) aux = ld_elem(d.aux.ptr, d.aux.dtype, view_index(d.aux, pix, c, HWt, Cview));
       v = apply_epilogue(d.epilogue, v, res, aux);
       st_elem(d.out.ptr, d.out.dtype, view_index(d.out, pix, c, HWt, Cview), v);
-      if (d.out2.ptr) st_elem(d.out2.ptr, d.out2.dtype, view_index(d.out2, pix, c, HWt, Cview), v);
+      if (d.out2.ptr) st_elem(d.out2.ptr, d.out2.dtype, view_index(d.out2, pix, c, HWt, Cview), d.out2_square ? v * v : v);
       if (d.out3.ptr) st_elem(d.out3.ptr, d.out3.dtype, view_index(d.out3, pix, c, HWt, Cview), v);
     }
   }

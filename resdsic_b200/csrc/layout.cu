@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(256) copy_views_kernel(const rdsic_copy_desc d
       size_t idx = src_n ? ((size_t)b * d.C + c) * HW + p : ((size_t)b * HW + p) * d.src.ld + d.src.coff + c;
       v = ld_elem(d.src.ptr, d.src.dtype, idx);
       if (d.op == 1) v = gelu_erf(v);
+      if (d.op == 2) v = v * v;
     }
     if (src_n) tile[k][tx] = v; else tile[tx][k] = v;
   }
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const rdsic_ln_desc d) {
 
 extern "C" int rdsic_copy_forward(const rdsic_copy_desc* d, rdsic_stream_t stream) {
   RDSIC_CHECK_ARG(d && d->src.ptr && d->dst.ptr && d->B > 0 && d->H > 0 && d->W > 0 && d->C > 0);
-  RDSIC_CHECK_ARG(d->op == 0 || d->op == 1);
+  RDSIC_CHECK_ARG(d->op >= 0 && d->op <= 2);
   RDSIC_CHECK_ARG(d->B <= 65535);
   dim3 grid(ceil_div(d->H * d->W, 32), ceil_div(d->C, 32), d->B);
   copy_views_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d);

@@ -31,6 +31,13 @@ class Ctx:
         self.wdt = self.act
         self.prog = Program(device)
 
+    def wdt_for(self, x):
+        """Weight dtype for a GEMM reading view `x`: the tensor-core kernel needs bf16 channels-last
+        activations with Cin % 16 == 0; anything else (the fp32 NCHW input image) takes the fp32 kernel."""
+        if self.precision == "bf16" and x.t.dtype == torch.bfloat16 and not x.nchw and x.C % 16 == 0:
+            return torch.bfloat16
+        return torch.float32
+
     def buf(self, B, H, W, C, dtype=None, ld=None):
         return TV.empty(B, H, W, C, dtype or self.act, self.device, ld)
 
@@ -87,19 +94,27 @@ class B200Module(nn.Module):
 class Sequential(nn.Sequential, B200Module):
     """nn.Sequential of B200 modules (keeps the reference's integer child names)."""
 
-    def emit(self, ctx, x, **kw):
+    def emit(self, ctx, x, last_kw=None, **kw):
+        """`last_kw`: extra emit() arguments for the final module (output placement/dtype)."""
         mods = list(self)
         i = 0
         while i < len(mods):
             m = mods[i]
-            # fuse "conv -> GELU" pairs into the conv epilogue
             nxt = mods[i + 1] if i + 1 < len(mods) else None
-            if getattr(m, "fuses_gelu", False) and isinstance(nxt, GELU):
-                x = m.emit(ctx, x, gelu=True)
-                i += 2
+            step = 2 if (getattr(m, "fuses_gelu", False) and isinstance(nxt, GELU)) else 1
+            extra = dict(last_kw or {}) if i + step >= len(mods) else {}
+            if step == 2:  # fuse "conv -> GELU" pairs into the conv epilogue
+                x = m.emit(ctx, x, gelu=True, **extra)
+            elif getattr(nxt, "wants_square", False) and ctx.precision == "bf16" and hasattr(m, "weight"):
+                # conv/deconv -> GDN in bf16 mode: the producer also stores x^2 (the GDN GEMM's A operand)
+                x = m.emit(ctx, x, out2_square=True, want_sq=True, **extra)
+                x, x2 = x
+                extra = dict(last_kw or {}) if i + 2 >= len(mods) else {}
+                x = nxt.emit(ctx, x, x2=x2, **extra)
+                step = 2
             else:
-                x = m.emit(ctx, x)
-                i += 1
+                x = m.emit(ctx, x, **extra)
+            i += step
         return x
 
     forward = B200Module.forward

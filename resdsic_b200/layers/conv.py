@@ -33,8 +33,9 @@ class Conv2d(B200Module):
         return self._packed(("w", wdt), (self.weight, self.bias), lambda: (
             packing.pack_conv_weight(self.weight, wdt), self.bias.detach().float().contiguous()))
 
-    def emit(self, ctx: Ctx, x, gelu=False, epilogue=None, out=None, out_dtype=None, pixel_shuffle=0, **kw):
-        w, b = self.packed(ctx.wdt)
+    def emit(self, ctx: Ctx, x, gelu=False, epilogue=None, out=None, out_dtype=None, pixel_shuffle=0, want_sq=False,
+             **kw):
+        w, b = self.packed(ctx.wdt_for(x))
         k, s, p = self.kernel_size, self.stride, self.padding
         OH, OW = (x.H + 2 * p - k) // s + 1, (x.W + 2 * p - k) // s + 1
         if out is None:
@@ -44,8 +45,11 @@ class Conv2d(B200Module):
                 out = ctx.buf(x.B, OH, OW, self.out_channels, out_dtype)
         if epilogue is None:
             epilogue = _lib.EPI_GELU if gelu else _lib.EPI_NONE
-        return ctx.prog.conv(x, w, b, self.out_channels, k, k, s, p, p, out, epilogue=epilogue,
-                             pixel_shuffle=pixel_shuffle, OH=OH, OW=OW, **kw)
+        if want_sq:
+            kw["out2"] = ctx.buf(out.B, out.H, out.W, out.C)
+        y = ctx.prog.conv(x, w, b, self.out_channels, k, k, s, p, p, out, epilogue=epilogue,
+                          pixel_shuffle=pixel_shuffle, OH=OH, OW=OW, **kw)
+        return (y, kw["out2"]) if want_sq else y
 
 
 class ConvTranspose2d(B200Module):
@@ -66,14 +70,16 @@ class ConvTranspose2d(B200Module):
         return self._packed(("w", wdt), (self.weight, self.bias), lambda: (
             packing.pack_deconv_weight(self.weight, wdt), self.bias.detach().float().contiguous()))
 
-    def emit(self, ctx: Ctx, x, out=None, out_dtype=None, **kw):
-        phases, b = self.packed(ctx.wdt)
+    def emit(self, ctx: Ctx, x, out=None, out_dtype=None, want_sq=False, **kw):
+        phases, b = self.packed(ctx.wdt_for(x))
         if out is None:
             out = ctx.buf(x.B, 2 * x.H, 2 * x.W, self.out_channels, out_dtype)
+        if want_sq:
+            kw["out2"] = ctx.buf(out.B, out.H, out.W, out.C)
         for (py, px), (w, R, S, ph, pw) in phases.items():
             ctx.prog.conv(x, w, b, self.out_channels, R, S, 1, ph, pw, out, OH=x.H, OW=x.W,
                           osy=2, osx=2, ooy=py, oox=px, **kw)
-        return out
+        return (out, kw["out2"]) if want_sq else out
 
 
 class Linear(B200Module):
@@ -93,7 +99,7 @@ class Linear(B200Module):
             packing.pack_linear_weight(self.weight, wdt), self.bias.detach().float().contiguous()))
 
     def emit(self, ctx: Ctx, x, out=None, epilogue=_lib.EPI_NONE, out_dtype=None, **kw):
-        w, b = self.packed(ctx.wdt)
+        w, b = self.packed(ctx.wdt_for(x))
         if out is None:
             out = ctx.buf(x.B, x.H, x.W, self.out_features, out_dtype)
         return ctx.prog.conv(x, w, b, self.out_features, 1, 1, 1, 0, 0, out, epilogue=epilogue, **kw)

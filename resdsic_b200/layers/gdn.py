@@ -3,6 +3,7 @@ contraction beta + gamma @ x^2 runs in the implicit-GEMM kernel with the A
 operand squared on load, and rsqrt (or sqrt) and the multiply by x are its
 epilogue.  The reference launches pow, conv2d, rsqrt and mul separately."""
 import torch
+import torch
 import torch.nn as nn
 
 from .. import _lib, packing
@@ -23,10 +24,18 @@ class GDN(B200Module):
     def packed(self, wdt):
         return self._packed(("gdn", wdt), (self.beta, self.gamma), lambda: packing.pack_gdn(self.beta, self.gamma, wdt))
 
-    def emit(self, ctx: Ctx, x, out=None, **kw):
-        gamma, beta = self.packed(ctx.wdt)
+    wants_square = True  # in bf16 mode the producing conv also stores x^2 (see Sequential.emit)
+
+    def emit(self, ctx: Ctx, x, out=None, x2=None, **kw):
         C = self.in_channels
         if out is None:
             out = ctx.buf(x.B, x.H, x.W, C)
         epi = _lib.EPI_IGDN if self.inverse else _lib.EPI_GDN
+        if ctx.wdt_for(x) == torch.bfloat16:
+            # tensor-core path: TMA cannot square on load, so A = x^2 comes from a side buffer
+            if x2 is None:
+                x2 = ctx.prog.copy(x, ctx.buf(x.B, x.H, x.W, C), op_code=2)
+            gamma, beta = self.packed(torch.bfloat16)
+            return ctx.prog.conv(x2, gamma, beta, C, 1, 1, 1, 0, 0, out, epilogue=epi, res=x)
+        gamma, beta = self.packed(torch.float32)
         return ctx.prog.conv(x, gamma, beta, C, 1, 1, 1, 0, 0, out, epilogue=epi, res=x, a_square=True)

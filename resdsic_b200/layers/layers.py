@@ -39,4 +39,4 @@ class Win_noShift_Attention(B200Module):
         b = x
         for m in list(self.conv_b)[:4]:
             b = m.emit(ctx, b)
-        return self.conv_b[4].emit(ctx, b, epilogue=_lib.EPI_GATE, aux=a, res=x, out=out, out_dtype=out_dtype)
+        return self.conv_b[4].emit(ctx, b, epilogue=_lib.EPI_GATE, aux=a, res=x, out=out, out_dtype=out_dtype, **kw)

@@ -137,18 +137,13 @@ class WACNN(CompressionModel):
         p = _Plan()
         p.x = torch.empty(B, 3, H, W, dtype=f32, device=device)
         # ---- g_a: y kept fp32 (it is quantised against mu)
-        ga = list(self.g_a)
-        t = TV.nchw_of(p.x)
-        for m in ga[:-1]:
-            t = m.emit(ctx, t)
-        y = ga[-1].emit(ctx, t, out_dtype=f32)
-        h, w = y.H, y.W
+        bf16 = ctx.precision == "bf16"
+        h, w = H // 16, W // 16
+        y = ctx.buf(B, h, w, 320, f32)
+        y_act = ctx.buf(B, h, w, 320) if bf16 else y  # bf16 twin of y: A operand of h_a
+        self.g_a.emit(ctx, TV.nchw_of(p.x), last_kw=dict(out=y, out2=y_act) if bf16 else dict(out=y))
         # ---- h_a -> z (fp32) -> EB
-        ha = list(self.h_a)
-        t = y
-        for i in (0, 2, 4, 6):
-            t = ha[i].emit(ctx, t, gelu=True)
-        z = ha[8].emit(ctx, t, out_dtype=f32)
+        z = self.h_a.emit(ctx, y_act, last_kw=dict(out_dtype=f32))
         p.lik_z = torch.empty(B, self.N, z.H, z.W, dtype=f32, device=device)
         p.z_symbols = torch.empty(B, self.N, z.H, z.W, dtype=torch.int32, device=device) if with_symbols else None
         z_hat, _ = self.entropy_bottleneck.emit(ctx, z, lik=p.lik_z, symbols=p.z_symbols)
@@ -182,12 +177,9 @@ class WACNN(CompressionModel):
             self._stack(ctx, self.lrp_transforms[i], means.channels(0, cin + 32), final=dict(
                 epilogue=_lib.EPI_LRP, res=yh_i, out=yh_i, **extra))
         # ---- g_s
-        gs = list(self.g_s)
-        t = y_hat
-        for m in gs[:-1]:
-            t = m.emit(ctx, t)
         p.x_hat = torch.empty(B, 3, H, W, dtype=f32, device=device)
-        gs[-1].emit(ctx, t, out=TV.nchw_of(p.x_hat))
+        y_hat_act = ctx.prog.copy(y_hat, ctx.buf(B, h, w, 320)) if bf16 else y_hat
+        self.g_s.emit(ctx, y_hat_act, last_kw=dict(out=TV.nchw_of(p.x_hat)))
         p.prog = ctx.prog
         p.y, p.z, p.y_hat, p.means, p.scales = y, z, y_hat, means, scales
         return p

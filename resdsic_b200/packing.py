@@ -13,15 +13,22 @@ import torch.nn.functional as F
 from ._lib import EB_STRIDE
 
 
+def _pad_rows(w2d):
+    """The tensor-core kernel tiles N in multiples of 16: zero-pad bf16 weights to ceil16(Cout) rows."""
+    if w2d.dtype == torch.bfloat16 and w2d.shape[0] % 16:
+        w2d = F.pad(w2d, (0, 0, 0, 16 - w2d.shape[0] % 16))
+    return w2d.contiguous()
+
+
 def pack_conv_weight(w, dtype=torch.float32):
     """[Cout,Cin,KH,KW] (nn.Conv2d) -> [Cout, KH*KW*Cin], tap-major / channel-minor."""
     Cout = w.shape[0]
-    return w.detach().permute(0, 2, 3, 1).reshape(Cout, -1).to(dtype).contiguous()
+    return _pad_rows(w.detach().permute(0, 2, 3, 1).reshape(Cout, -1).to(dtype))
 
 
 def pack_linear_weight(w, dtype=torch.float32):
     """nn.Linear [out,in] is already [N][K]."""
-    return w.detach().to(dtype).contiguous()
+    return _pad_rows(w.detach().to(dtype))
 
 
 # transposed conv k5 s2 p2 op1 (reference WACNN/utils.py:126-134): out[2j+py] gathers
@@ -39,7 +46,7 @@ def pack_deconv_weight(w, dtype=torch.float32):
     for py, (R, ph, khs) in DECONV_PHASES.items():
         for px, (S, pw, kws) in DECONV_PHASES.items():
             sub = wd[:, :, list(khs)][:, :, :, list(kws)]  # [Cin,Cout,R,S]
-            packed = sub.permute(1, 2, 3, 0).reshape(w.shape[1], -1).to(dtype).contiguous()
+            packed = _pad_rows(sub.permute(1, 2, 3, 0).reshape(w.shape[1], -1).to(dtype))
             out[(py, px)] = (packed, R, S, ph, pw)
     return out
 
@@ -54,7 +61,7 @@ def nonneg_reparam(p, minimum):
 
 def pack_gdn(beta, gamma, dtype=torch.float32):
     """GDN (reference layers/gdn.py:62-69): gamma' as a [C][C] 1x1 weight, beta' as its bias (fp32)."""
-    return nonneg_reparam(gamma, 0.0).to(dtype).contiguous(), nonneg_reparam(beta, 1e-6).contiguous()
+    return _pad_rows(nonneg_reparam(gamma, 0.0).to(dtype)), nonneg_reparam(beta, 1e-6).contiguous()
 
 
 def pack_entropy_bottleneck(eb_params, quantiles):

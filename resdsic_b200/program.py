@@ -75,7 +75,7 @@ class Program:
     # ------------------------------------------------------------- builders
     def conv(self, x: TV, weight, bias, Cout, KH, KW, stride, pad_h, pad_w, out: TV, epilogue=_lib.EPI_NONE,
              res: TV = None, aux: TV = None, out2: TV = None, out3: TV = None, a_square=False, pixel_shuffle=0,
-             OH=None, OW=None, osy=1, osx=1, ooy=0, oox=0, Cin=None):
+             OH=None, OW=None, osy=1, osx=1, ooy=0, oox=0, Cin=None, out2_square=False):
         d = ConvDesc()
         d.in_ = x.view()
         d.B, d.H, d.W, d.Cin = x.B, x.H, x.W, (x.C if Cin is None else Cin)
@@ -88,9 +88,11 @@ class Program:
         d.osy, d.osx, d.ooy, d.oox = osy, osx, ooy, oox
         d.pixel_shuffle, d.epilogue, d.a_square = pixel_shuffle, epilogue, int(a_square)
         d.out = out.view()
+        d.out2_square = int(out2_square)
         for name, tv in (("res", res), ("aux", aux), ("out2", out2), ("out3", out3)):
             setattr(d, name, tv.view() if tv is not None else _NULL)
-        assert weight.numel() == Cout * KH * KW * d.Cin, (weight.shape, Cout, KH, KW, d.Cin)
+        assert weight.numel() >= Cout * KH * KW * d.Cin and weight.shape[-1] == KH * KW * d.Cin, \
+            (weight.shape, Cout, KH, KW, d.Cin)
         op = Op()
         op.kind = _lib.OP_CONV
         op.u.conv = d

@@ -48,7 +48,7 @@ class Sim:
         x = self._nhwc(d.in_, d.B, d.H, d.W, d.Cin).float()
         if d.a_square:
             x = x * x
-        wflat = self._flat(d.weight)[: d.Cout * d.KH * d.KW * d.Cin].float()
+        wflat = self._flat(d.weight)[: d.Cout * d.KH * d.KW * d.Cin].float()  # (rows may be padded past Cout)
         w = wflat.view(d.Cout, d.KH, d.KW, d.Cin).permute(0, 3, 1, 2)
         bias = self._flat(d.bias)[: d.Cout] if d.bias else None
         need_h = (d.OH - 1) * d.stride + d.KH - d.pad_h
@@ -83,10 +83,10 @@ class Sim:
             v = res * torch.sqrt(v)
         elif e == _lib.EPI_LRP:
             v = res + 0.5 * torch.tanh(v)
-        for view in (d.out, d.out2, d.out3):
+        for view, sq in ((d.out, False), (d.out2, bool(d.out2_square)), (d.out3, False)):
             if view.ptr:
                 dst = sub(view)
-                dst.copy_(v.to(dst.dtype))
+                dst.copy_((v * v if sq else v).to(dst.dtype))
 
     def attn(self, d):
         C, heads, ws, s = d.C, d.heads, d.ws, d.shift
@@ -165,6 +165,8 @@ class Sim:
         src = self._nhwc(d.src, d.B, d.H, d.W, d.C).float()
         if d.op == 1:
             src = F.gelu(src)
+        if d.op == 2:
+            src = src * src
         dst = self._nhwc(d.dst, d.B, d.H, d.W, d.C)
         dst.copy_(src.to(dst.dtype))
 

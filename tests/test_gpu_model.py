@@ -71,5 +71,30 @@ def test_fp32_forward_vs_oracle_kodak_size(model, synthetic_sd, scale_table):
              latent_scales=ref["latent_scales"].numpy(), y_hat=ref["y_hat"].numpy(), x_hat=ref["x_hat"].numpy(),
              lik_y=ref["likelihoods"]["y"].numpy(), lik_z=ref["likelihoods"]["z"].numpy(),
              symbols=ref["symbols"].numpy(), indexes=ref["indexes"].numpy())
-    stats = compare_forward(_collect(model, x.to(DEV)), g, 512 * 768, cont_tol=1e-3, flip_frac=2e-2, yhat_frac=1e-1)
+    stats = compare_forward(_collect(model, x.to(DEV)), g, 512 * 768, cont_tol=1e-3, flip_frac=2e-2, yhat_frac=1.0,
+                            xhat_max=0.1, xhat_psnr=40.0)  # a flipped symbol legitimately perturbs all later slices
     print("kodak fp32", stats)
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_bf16_forward_vs_reference_golden(model, case):
+    """bf16 (tcgen05) mode against the fp32 reference.  Symbols can no longer be bit-exact (y itself moves by
+    ~1e-2); the gate is statistical: rate within 1 %, reconstruction close, few symbol flips."""
+    B, H, W = CASES[case]
+    g = np.load(os.path.join(GOLDEN, f"wacnn_{case}.npz"))
+    model.set_precision("bf16")
+    try:
+        got = _collect(model, weights.make_image(B, H, W, seed=0).to(DEV))
+    finally:
+        model.set_precision("fp32")
+    dy = np.abs(got["y"] - g["y"])
+    assert dy.max() <= 0.25 and dy.mean() <= 0.03, (dy.max(), dy.mean())
+    dx = np.abs(got["x_hat"] - g["x_hat"])
+    flips = (got["symbols"] != g["symbols"]).mean()
+    n = B * H * W
+    from tests.helpers import bpp_of
+    b_got, b_ref = bpp_of(got["lik_y"], got["lik_z"], n), bpp_of(g["lik_y"], g["lik_z"], n)
+    print(case, "bf16: x_hat max", dx.max(), "mean", dx.mean(), "symbol flips", flips, "bpp", b_got, "ref", b_ref)
+    assert dx.max() <= 0.15 and dx.mean() <= 0.02
+    assert flips <= 0.15
+    assert abs(b_got - b_ref) <= 1e-2 * b_ref

@@ -118,3 +118,56 @@ def test_error_paths(model):
         model.gaussian_conditional.quantize(torch.zeros(1, 32, 4, 4, device=DEV), "bogus")
     with pytest.raises(ValueError, match="multiple of 64"):
         model(torch.zeros(1, 3, 100, 64, device=DEV))
+
+
+# ----------------------------------------------------------------------------- bf16 tensor-core path
+def _bf(x):
+    return x.bfloat16().float()
+
+
+@pytest.mark.parametrize("cin,cout,k,s,B,hw", [
+    (64, 64, 1, 1, 1, (8, 16)), (192, 96, 1, 1, 2, (9, 7)), (96, 96, 3, 1, 2, (16, 24)), (352, 224, 3, 1, 1, (8, 12)),
+    (288, 256, 3, 2, 1, (8, 12)), (192, 192, 5, 2, 1, (32, 48)), (192, 320, 5, 2, 2, (18, 26)), (320, 960, 1, 1, 1, (8, 12)),
+    (64, 32, 3, 1, 3, (5, 3)), (512, 224, 3, 1, 1, (32, 48))])
+def test_tcgen05_conv_vs_oracle(cin, cout, k, s, B, hw):
+    """tcgen05/TMA implicit GEMM vs torch CPU conv on the same bf16-rounded operands (fp32 accumulate both
+    sides): the only difference left is the bf16 rounding of the stored output (rel 2^-8)."""
+    from resdsic_b200.layers import Conv2d
+    conv = Conv2d(cin, cout, k, s)
+    with torch.no_grad():
+        conv.weight.copy_(weights.hash_symmetric(f"tc.w{cin}{cout}{k}", conv.weight.shape, (3.0 / (cin * k * k)) ** 0.5))
+        conv.bias.copy_(weights.hash_symmetric(f"tc.b{cin}{cout}{k}", conv.bias.shape, 0.1))
+    x = weights.hash_symmetric(f"tc.x{cin}{hw}", (B, cin, *hw), 1.0)
+    ref = torch.nn.functional.conv2d(_bf(x), _bf(conv.weight.detach()), conv.bias.detach(), stride=s, padding=k // 2)
+    out = conv.to(DEV).set_precision("bf16")(x.to(DEV)).cpu()
+    np.testing.assert_allclose(out.numpy(), ref.numpy(), rtol=8e-3, atol=8e-3)
+
+
+@pytest.mark.parametrize("cin,cout", [(192, 192), (320, 192), (192, 3)])
+def test_tcgen05_deconv_vs_oracle(cin, cout):
+    from resdsic_b200.layers import ConvTranspose2d
+    d = ConvTranspose2d(cin, cout)
+    with torch.no_grad():
+        d.weight.copy_(weights.hash_symmetric(f"tc.dw{cin}{cout}", d.weight.shape, (12.0 / (cin * 25)) ** 0.5))
+        d.bias.copy_(weights.hash_symmetric(f"tc.db{cin}{cout}", d.bias.shape, 0.1))
+    x = weights.hash_symmetric(f"tc.dx{cin}", (2, cin, 6, 10), 1.0)
+    ref = torch.nn.functional.conv_transpose2d(_bf(x), _bf(d.weight.detach()), d.bias.detach(), stride=2, padding=2,
+                                               output_padding=1)
+    out = d.to(DEV).set_precision("bf16")(x.to(DEV)).cpu()
+    np.testing.assert_allclose(out.numpy(), ref.numpy(), rtol=8e-3, atol=1.5e-2)
+
+
+@pytest.mark.parametrize("name,mod,key", [
+    ("attn8", lambda m: m.g_a[4].conv_b[0], "attn8_x"), ("attn4", lambda m: m.g_a[8].conv_b[0], "attn4_x"),
+    ("gdn", lambda m: m.g_a[1], "gdn_x"), ("igdn", lambda m: m.g_s[2], "gdn_x"), ("block8", lambda m: m.g_a[4], "block8_x"),
+])
+def test_layers_bf16_vs_reference_golden(model, gold, name, mod, key):
+    """bf16 mode against the fp32 reference: error budget = bf16 operand/activation rounding."""
+    model.set_precision("bf16")
+    try:
+        out = mod(model)(op_inputs()[key].to(DEV)).cpu().numpy()
+    finally:
+        model.set_precision("fp32")
+    ref = gold[name]
+    err = np.abs(out - ref)
+    assert err.max() <= 0.05 * np.abs(ref).max() and err.mean() <= 0.01 * np.abs(ref).max(), (err.max(), err.mean())

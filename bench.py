@@ -257,7 +257,7 @@ def profile_families(model, x_dev, dump=None):
     L = _lib.lib()
     arr = prog._array()
     stream = torch.cuda.current_stream().cuda_stream
-    names = {_lib.OP_CONV: "conv", _lib.OP_ATTN: "attn", _lib.OP_EB: "eb", _lib.OP_GC: "gc", _lib.OP_COPY: "copy",
+    names = {_lib.OP_CONV: "conv", _lib.OP_ATTN: "attn", _lib.OP_EB: "eb", _lib.OP_GC: "gc", _lib.OP_COPY: "copy", _lib.OP_PATCH: "patch",
              _lib.OP_LN: "ln"}
     n = len(prog.ops)
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]

@@ -159,7 +159,17 @@ typedef struct rdsic_ln_desc {
   float eps;
 } rdsic_ln_desc;
 
-enum { RDSIC_OP_CONV = 0, RDSIC_OP_ATTN = 1, RDSIC_OP_EB = 2, RDSIC_OP_GC = 3, RDSIC_OP_COPY = 4, RDSIC_OP_LN = 5 };
+/* im2col of a narrow-channel input (the 3-channel image, cnn.py:32) into a channels-last bf16 patch
+ * tensor [B,OH,OW,Kp]: element k = (r*KW + s)*C + c for k < KH*KW*C, zero padding up to Kp (multiple
+ * of 16).  The first 5x5 s2 convolution then runs as a pointwise tensor-core GEMM with K = Kp. */
+typedef struct rdsic_patch_desc {
+  rdsic_view src;  /* [B,C,H,W] NCHW or NHWC, fp32 or bf16 */
+  rdsic_view dst;  /* [B,OH,OW,Kp] bf16 */
+  int32_t B, H, W, C, KH, KW, stride, pad, OH, OW, Kp;
+  int32_t pad_;
+} rdsic_patch_desc;
+
+enum { RDSIC_OP_CONV = 0, RDSIC_OP_ATTN = 1, RDSIC_OP_EB = 2, RDSIC_OP_GC = 3, RDSIC_OP_COPY = 4, RDSIC_OP_LN = 5, RDSIC_OP_PATCH = 6 };
 
 /* One node of a forward "program" (WACNN.forward, cnn.py:143-193, is ~330 of these). */
 typedef struct rdsic_op {
@@ -172,13 +182,14 @@ typedef struct rdsic_op {
     rdsic_gc_desc gc;
     rdsic_copy_desc copy;
     rdsic_ln_desc ln;
+    rdsic_patch_desc patch;
   } u;
 } rdsic_op;
 
 int rdsic_abi_version(void);
 const char* rdsic_error_string(int code);
 /* sizeof(rdsic_op) etc., so the host binding can verify its struct mirror. */
-int rdsic_sizeof(int what); /* 0 op, 1 conv, 2 attn, 3 eb, 4 gc, 5 copy, 6 view, 7 ln */
+int rdsic_sizeof(int what); /* 0 op, 1 conv, 2 attn, 3 eb, 4 gc, 5 copy, 6 view, 7 ln, 8 patch */
 
 int rdsic_conv_forward(const rdsic_conv_desc* d, rdsic_stream_t stream);
 int rdsic_attn_forward(const rdsic_attn_desc* d, rdsic_stream_t stream);
@@ -186,6 +197,7 @@ int rdsic_eb_forward(const rdsic_eb_desc* d, rdsic_stream_t stream);
 int rdsic_gc_forward(const rdsic_gc_desc* d, rdsic_stream_t stream);
 int rdsic_copy_forward(const rdsic_copy_desc* d, rdsic_stream_t stream);
 int rdsic_ln_forward(const rdsic_ln_desc* d, rdsic_stream_t stream);
+int rdsic_patch_forward(const rdsic_patch_desc* d, rdsic_stream_t stream);
 
 /* Launch a whole program in order on `stream`.  *n_launched (optional) receives
  * the number of kernels launched.  Stops at the first error; *failed_op

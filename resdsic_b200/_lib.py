@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libresdsic_b200.so")
 
 F32, BF16 = 0, 1
 EPI_NONE, EPI_GELU, EPI_RES_GELU, EPI_ADD_RES, EPI_GATE, EPI_GDN, EPI_IGDN, EPI_LRP = range(8)
-OP_CONV, OP_ATTN, OP_EB, OP_GC, OP_COPY, OP_LN = range(6)
+OP_CONV, OP_ATTN, OP_EB, OP_GC, OP_COPY, OP_LN, OP_PATCH = range(7)
 EB_STRIDE = 60
 
 
@@ -71,9 +71,15 @@ class LNDesc(C.Structure):
                 ("rows", C.c_int32), ("C", C.c_int32), ("eps", C.c_float)]
 
 
+class PatchDesc(C.Structure):
+    _fields_ = [("src", View), ("dst", View), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
+                ("KH", C.c_int32), ("KW", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32), ("OH", C.c_int32),
+                ("OW", C.c_int32), ("Kp", C.c_int32), ("pad_", C.c_int32)]
+
+
 class _OpUnion(C.Union):
     _fields_ = [("conv", ConvDesc), ("attn", AttnDesc), ("eb", EBDesc), ("gc", GCDesc), ("copy", CopyDesc),
-                ("ln", LNDesc)]
+                ("ln", LNDesc), ("patch", PatchDesc)]
 
 
 class Op(C.Structure):
@@ -83,7 +89,7 @@ class Op(C.Structure):
 EXPORTS = (
     "rdsic_abi_version", "rdsic_error_string", "rdsic_sizeof",
     "rdsic_conv_forward", "rdsic_attn_forward", "rdsic_eb_forward", "rdsic_gc_forward",
-    "rdsic_copy_forward", "rdsic_ln_forward", "rdsic_run_program",
+    "rdsic_copy_forward", "rdsic_ln_forward", "rdsic_patch_forward", "rdsic_run_program",
     "rdsic_graph_create", "rdsic_graph_launch", "rdsic_graph_num_kernels", "rdsic_graph_destroy",
 )
 
@@ -107,7 +113,8 @@ def lib():
     L.rdsic_error_string.argtypes = [C.c_int]
     L.rdsic_sizeof.argtypes = [C.c_int]
     for fn, T in (("rdsic_conv_forward", ConvDesc), ("rdsic_attn_forward", AttnDesc), ("rdsic_eb_forward", EBDesc),
-                  ("rdsic_gc_forward", GCDesc), ("rdsic_copy_forward", CopyDesc), ("rdsic_ln_forward", LNDesc)):
+                  ("rdsic_gc_forward", GCDesc), ("rdsic_copy_forward", CopyDesc), ("rdsic_ln_forward", LNDesc),
+                  ("rdsic_patch_forward", PatchDesc)):
         getattr(L, fn).argtypes = [C.POINTER(T), C.c_void_p]
         getattr(L, fn).restype = C.c_int
     L.rdsic_run_program.argtypes = [C.POINTER(Op), C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -118,7 +125,7 @@ def lib():
     L.rdsic_graph_destroy.restype = None
     if L.rdsic_abi_version() != 1:
         raise RuntimeError("resdsic_b200: ABI version mismatch between the python host and the CUDA library")
-    for what, T in enumerate((Op, ConvDesc, AttnDesc, EBDesc, GCDesc, CopyDesc, View, LNDesc)):
+    for what, T in enumerate((Op, ConvDesc, AttnDesc, EBDesc, GCDesc, CopyDesc, View, LNDesc, PatchDesc)):
         if L.rdsic_sizeof(what) != C.sizeof(T):
             raise RuntimeError(f"resdsic_b200: struct mirror mismatch for {T.__name__}: "
                                f"C={L.rdsic_sizeof(what)} python={C.sizeof(T)}")

@@ -32,6 +32,7 @@ int rdsic_sizeof(int what) {
     case 5: return (int)sizeof(rdsic_copy_desc);
     case 6: return (int)sizeof(rdsic_view);
     case 7: return (int)sizeof(rdsic_ln_desc);
+    case 8: return (int)sizeof(rdsic_patch_desc);
     default: return -1;
   }
 }
@@ -54,6 +55,7 @@ static int run_one(const rdsic_op* op, rdsic_stream_t stream) {
     case RDSIC_OP_GC: return rdsic_gc_forward(&op->u.gc, stream);
     case RDSIC_OP_COPY: return rdsic_copy_forward(&op->u.copy, stream);
     case RDSIC_OP_LN: return rdsic_ln_forward(&op->u.ln, stream);
+    case RDSIC_OP_PATCH: return rdsic_patch_forward(&op->u.patch, stream);
     default: return RDSIC_E_ARG;
   }
 }

@@ -65,7 +65,56 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const rdsic_ln_desc d) {
   }
 }
 
+// one thread per 8-element (16-byte) chunk of a patch row
+__global__ void __launch_bounds__(256) patchify_kernel(const rdsic_patch_desc d) {
+  const int chunks = d.Kp / 8;
+  const size_t total = (size_t)d.B * d.OH * d.OW * chunks;
+  const int Kreal = d.KH * d.KW * d.C;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(e % chunks);
+    const size_t pix = e / chunks;
+    const int ox = (int)(pix % d.OW);
+    const size_t t = pix / d.OW;
+    const int oy = (int)(t % d.OH), b = (int)(t / d.OH);
+    uint32_t w[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      float f[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int k = ch * 8 + h * 2 + u;
+        float v = 0.f;
+        if (k < Kreal) {
+          const int tap = k / d.C, c = k - tap * d.C;
+          const int r = tap / d.KW, s = tap - r * d.KW;
+          const int iy = oy * d.stride - d.pad + r, ix = ox * d.stride - d.pad + s;
+          if (iy >= 0 && iy < d.H && ix >= 0 && ix < d.W) {
+            const size_t idx = d.src.nchw ? (((size_t)b * d.C + c) * d.H + iy) * d.W + ix
+                                          : (((size_t)b * d.H + iy) * d.W + ix) * d.src.ld + d.src.coff + c;
+            v = ld_elem(d.src.ptr, d.src.dtype, idx);
+          }
+        }
+        f[u] = v;
+      }
+      __nv_bfloat162 hh = __floats2bfloat162_rn(f[0], f[1]);
+      w[h] = *reinterpret_cast<uint32_t*>(&hh);
+    }
+    uint4* dst = reinterpret_cast<uint4*>((__nv_bfloat16*)d.dst.ptr + pix * (size_t)d.dst.ld + d.dst.coff) + ch;
+    *dst = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 }  // namespace
+
+extern "C" int rdsic_patch_forward(const rdsic_patch_desc* d, rdsic_stream_t stream) {
+  RDSIC_CHECK_ARG(d && d->src.ptr && d->dst.ptr && d->B > 0 && d->C > 0 && d->KH > 0 && d->KW > 0 && d->stride > 0);
+  RDSIC_CHECK_ARG(d->Kp % 16 == 0 && d->Kp >= d->KH * d->KW * d->C && d->dst.dtype == RDSIC_BF16 && !d->dst.nchw);
+  if (d->dst.ld % 8 || d->dst.coff % 8 || ((uintptr_t)d->dst.ptr % 16)) return RDSIC_E_ALIGN;
+  const size_t total = (size_t)d->B * d->OH * d->OW * (d->Kp / 8);
+  const size_t want = (total + 255) / 256;
+  patchify_kernel<<<(unsigned)(want < 148 * 16 ? want : 148 * 16), 256, 0, (cudaStream_t)stream>>>(*d);
+  return rdsic_launch_status();
+}
 
 extern "C" int rdsic_copy_forward(const rdsic_copy_desc* d, rdsic_stream_t stream) {
   RDSIC_CHECK_ARG(d && d->src.ptr && d->dst.ptr && d->B > 0 && d->H > 0 && d->W > 0 && d->C > 0);

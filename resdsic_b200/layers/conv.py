@@ -35,9 +35,18 @@ class Conv2d(B200Module):
 
     def emit(self, ctx: Ctx, x, gelu=False, epilogue=None, out=None, out_dtype=None, pixel_shuffle=0, want_sq=False,
              **kw):
-        w, b = self.packed(ctx.wdt_for(x))
         k, s, p = self.kernel_size, self.stride, self.padding
         OH, OW = (x.H + 2 * p - k) // s + 1, (x.W + 2 * p - k) // s + 1
+        if ctx.precision == "bf16" and ctx.wdt_for(x) != torch.bfloat16 and k * k * self.in_channels <= 256:
+            # narrow-channel input (the RGB image): im2col into a bf16 patch tensor, then a pointwise
+            # tensor-core GEMM with K = ceil16(k*k*Cin) -- instead of the fp32 SIMT kernel
+            Kp = -(-(k * k * self.in_channels) // 16) * 16
+            w, b = self._packed(("patch", Kp), (self.weight, self.bias), lambda: (
+                packing.pack_conv_weight(self.weight, torch.bfloat16, k_pad_to=16), self.bias.detach().float().contiguous()))
+            patches = ctx.prog.patchify(x, ctx.buf(x.B, OH, OW, Kp, torch.bfloat16), k, k, s, p)
+            x, k, s, p = patches, 1, 1, 0
+        else:
+            w, b = self.packed(ctx.wdt_for(x))
         if out is None:
             if pixel_shuffle:
                 out = ctx.buf(x.B, OH * 2, OW * 2, self.out_channels // 4, out_dtype)
@@ -71,7 +80,16 @@ class ConvTranspose2d(B200Module):
             packing.pack_deconv_weight(self.weight, wdt), self.bias.detach().float().contiguous()))
 
     def emit(self, ctx: Ctx, x, out=None, out_dtype=None, want_sq=False, **kw):
-        phases, b = self.packed(ctx.wdt_for(x))
+        wdt = ctx.wdt_for(x)
+        if wdt == torch.bfloat16 and self.out_channels * 4 <= 16 and not want_sq and not kw:
+            # narrow head (192 -> 3): one merged 3x3 GEMM with 4*Cout columns + PixelShuffle addressing
+            w, b4 = self._packed(("merged", wdt), (self.weight, self.bias), lambda: (
+                packing.pack_deconv_merged(self.weight, wdt),
+                self.bias.detach().float().repeat_interleave(4).contiguous()))
+            if out is None:
+                out = ctx.buf(x.B, 2 * x.H, 2 * x.W, self.out_channels, out_dtype)
+            return ctx.prog.conv(x, w, b4, self.out_channels * 4, 3, 3, 1, 1, 1, out, pixel_shuffle=2, OH=x.H, OW=x.W)
+        phases, b = self.packed(wdt)
         if out is None:
             out = ctx.buf(x.B, 2 * x.H, 2 * x.W, self.out_channels, out_dtype)
         if want_sq:

@@ -20,10 +20,13 @@ def _pad_rows(w2d):
     return w2d.contiguous()
 
 
-def pack_conv_weight(w, dtype=torch.float32):
+def pack_conv_weight(w, dtype=torch.float32, k_pad_to=0):
     """[Cout,Cin,KH,KW] (nn.Conv2d) -> [Cout, KH*KW*Cin], tap-major / channel-minor."""
     Cout = w.shape[0]
-    return _pad_rows(w.detach().permute(0, 2, 3, 1).reshape(Cout, -1).to(dtype))
+    w2 = w.detach().permute(0, 2, 3, 1).reshape(Cout, -1)
+    if k_pad_to and w2.shape[1] % k_pad_to:
+        w2 = F.pad(w2, (0, k_pad_to - w2.shape[1] % k_pad_to))
+    return _pad_rows(w2.to(dtype))
 
 
 def pack_linear_weight(w, dtype=torch.float32):
@@ -49,6 +52,25 @@ def pack_deconv_weight(w, dtype=torch.float32):
             packed = _pad_rows(sub.permute(1, 2, 3, 0).reshape(w.shape[1], -1).to(dtype))
             out[(py, px)] = (packed, R, S, ph, pw)
     return out
+
+
+def pack_deconv_merged(w, dtype=torch.float32):
+    """All four sub-pixel phases of the k5 s2 transposed conv as ONE 3x3 stride-1 pad-1 convolution with
+    4*Cout output columns ordered n = c*4 + py*2 + px (so the PixelShuffle(2) store addressing scatters
+    them): taps a phase does not use are zero.  Used for the 3-channel image head, where 4*Cout = 12 fits
+    a single 16-wide MMA tile and the input is then read once instead of four times."""
+    assert w.shape[2:] == (5, 5)
+    Cin, Cout = w.shape[:2]
+    wd = w.detach().float()
+    out = torch.zeros(Cout, 2, 2, 3, 3, Cin, dtype=torch.float32, device=w.device)
+    # row tap r of the 3x3 (input row j-1+r): even phase kh = 4-2r (r=0..2); odd phase kh = 5-2r (r=1,2)
+    taps = {0: {0: 4, 1: 2, 2: 0}, 1: {1: 3, 2: 1}}
+    for py in (0, 1):
+        for px in (0, 1):
+            for r, kh in taps[py].items():
+                for s, kw in taps[px].items():
+                    out[:, py, px, r, s, :] = wd[:, :, kh, kw].t()
+    return _pad_rows(out.reshape(Cout * 4, 9 * Cin).to(dtype))
 
 
 def nonneg_reparam(p, minimum):

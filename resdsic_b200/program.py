@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import BF16, F32, AttnDesc, ConvDesc, CopyDesc, EBDesc, GCDesc, LNDesc, Op, View
+from ._lib import BF16, F32, AttnDesc, ConvDesc, CopyDesc, EBDesc, GCDesc, LNDesc, Op, PatchDesc, View
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
@@ -151,6 +151,18 @@ class Program:
         self.ops.append(op)
         self.keep += [src.t, dst.t]
         return dst
+
+    def patchify(self, x: TV, out: TV, KH, KW, stride, pad):
+        d = PatchDesc()
+        d.src, d.dst = x.view(), out.view()
+        d.B, d.H, d.W, d.C = x.B, x.H, x.W, x.C
+        d.KH, d.KW, d.stride, d.pad, d.OH, d.OW, d.Kp = KH, KW, stride, pad, out.H, out.W, out.C
+        op = Op()
+        op.kind = _lib.OP_PATCH
+        op.u.patch = d
+        self.ops.append(op)
+        self.keep += [x.t, out.t]
+        return out
 
     def layernorm(self, x: TV, out: TV, gamma, beta, eps=1e-5):
         d = LNDesc()

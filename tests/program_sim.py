@@ -170,6 +170,14 @@ class Sim:
         dst = self._nhwc(d.dst, d.B, d.H, d.W, d.C)
         dst.copy_(src.to(dst.dtype))
 
+    def patch(self, d):
+        x = self._nhwc(d.src, d.B, d.H, d.W, d.C).float().permute(0, 3, 1, 2)
+        cols = F.unfold(x, (d.KH, d.KW), padding=d.pad, stride=d.stride)  # [B, C*KH*KW, L], channel-major
+        cols = cols.view(d.B, d.C, d.KH * d.KW, d.OH, d.OW).permute(0, 3, 4, 2, 1).reshape(d.B, d.OH, d.OW, -1)
+        dst = self._nhwc(d.dst, d.B, d.OH, d.OW, d.Kp)
+        dst.zero_()
+        dst[..., : cols.shape[-1]] = cols.to(dst.dtype)
+
     def ln(self, d):
         x = torch.as_strided(self._flat(d.in_.ptr), (d.rows, d.C), (d.in_.ld, 1), d.in_.coff).float()
         g, b = self._flat(d.gamma)[: d.C], self._flat(d.beta)[: d.C]
@@ -178,7 +186,7 @@ class Sim:
 
     def run(self):
         disp = {_lib.OP_CONV: ("conv", self.conv), _lib.OP_ATTN: ("attn", self.attn), _lib.OP_EB: ("eb", self.eb),
-                _lib.OP_GC: ("gc", self.gc), _lib.OP_COPY: ("copy", self.copy), _lib.OP_LN: ("ln", self.ln)}
+                _lib.OP_GC: ("gc", self.gc), _lib.OP_COPY: ("copy", self.copy), _lib.OP_LN: ("ln", self.ln), _lib.OP_PATCH: ("patch", self.patch)}
         for op in self.prog.ops:
             name, fn = disp[op.kind]
             fn(getattr(op.u, name))

@@ -266,12 +266,17 @@ def profile_families(model, x_dev, dump=None):
     for rep in range(2):  # first rep warms caches
         evs[0].record()
         for i in range(n):
+            if prog.ops[i].kind in (_lib.OP_FORK, _lib.OP_JOIN):
+                evs[i + 1].record()
+                continue
             one = C.cast(base + i * opsz, C.POINTER(_lib.Op))
             _lib.check(L.rdsic_run_program(one, 1, stream, None, None))
             evs[i + 1].record()
         torch.cuda.synchronize()
     fam, per_op = {}, []
     for i in range(n):
+        if prog.ops[i].kind in (_lib.OP_FORK, _lib.OP_JOIN):
+            continue
         k = names[prog.ops[i].kind]
         t = evs[i].elapsed_time(evs[i + 1])
         ms, cnt = fam.get(k, (0.0, 0))

@@ -169,12 +169,18 @@ typedef struct rdsic_patch_desc {
   int32_t pad_;
 } rdsic_patch_desc;
 
-enum { RDSIC_OP_CONV = 0, RDSIC_OP_ATTN = 1, RDSIC_OP_EB = 2, RDSIC_OP_GC = 3, RDSIC_OP_COPY = 4, RDSIC_OP_LN = 5, RDSIC_OP_PATCH = 6 };
+enum { RDSIC_OP_CONV = 0, RDSIC_OP_ATTN = 1, RDSIC_OP_EB = 2, RDSIC_OP_GC = 3, RDSIC_OP_COPY = 4, RDSIC_OP_LN = 5, RDSIC_OP_PATCH = 6,
+       RDSIC_OP_FORK = 7, RDSIC_OP_JOIN = 8 };
 
 /* One node of a forward "program" (WACNN.forward, cnn.py:143-193, is ~330 of these). */
+/* Independent branches (cc_mean || cc_scale, h_mean_s || h_scale_s, conv_a || conv_b) may run concurrently:
+ * FORK makes lane 1 wait for everything issued so far on lane 0, ops with lane = 1 then run beside the
+ * lane-0 ops that follow, JOIN makes lane 0 wait for lane 1.  rdsic_run_program() executes all lanes in
+ * program order on the one stream it is given (always correct); the CUDA-graph form turns lanes into
+ * parallel graph branches. */
 typedef struct rdsic_op {
   int32_t kind;
-  int32_t pad_;
+  int32_t lane;
   union {
     rdsic_conv_desc conv;
     rdsic_attn_desc attn;

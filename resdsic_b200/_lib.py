@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libresdsic_b200.so")
 
 F32, BF16 = 0, 1
 EPI_NONE, EPI_GELU, EPI_RES_GELU, EPI_ADD_RES, EPI_GATE, EPI_GDN, EPI_IGDN, EPI_LRP = range(8)
-OP_CONV, OP_ATTN, OP_EB, OP_GC, OP_COPY, OP_LN, OP_PATCH = range(7)
+OP_CONV, OP_ATTN, OP_EB, OP_GC, OP_COPY, OP_LN, OP_PATCH, OP_FORK, OP_JOIN = range(9)
 EB_STRIDE = 60
 
 
@@ -83,7 +83,7 @@ class _OpUnion(C.Union):
 
 
 class Op(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("pad_", C.c_int32), ("u", _OpUnion)]
+    _fields_ = [("kind", C.c_int32), ("lane", C.c_int32), ("u", _OpUnion)]
 
 
 EXPORTS = (

@@ -60,20 +60,37 @@ static int run_one(const rdsic_op* op, rdsic_stream_t stream) {
   }
 }
 
+// side == nullptr: every lane runs in program order on `mainS` (serial, always correct)
+static int run_lanes(const rdsic_op* ops, int n_ops, cudaStream_t mainS, cudaStream_t side, int* n_launched,
+                     int* failed_op) {
+  int launched = 0, rc = 0, i = 0;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  if (side) {
+    for (int k = 0; k < 2 && !rc; ++k) rc = (int)cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+  }
+  for (; i < n_ops && !rc; ++i) {
+    const rdsic_op* op = &ops[i];
+    if (op->kind == RDSIC_OP_FORK || op->kind == RDSIC_OP_JOIN) {
+      if (!side) continue;
+      cudaStream_t from = op->kind == RDSIC_OP_FORK ? mainS : side, to = op->kind == RDSIC_OP_FORK ? side : mainS;
+      cudaEvent_t e = ev[op->kind == RDSIC_OP_FORK ? 0 : 1];
+      rc = (int)cudaEventRecord(e, from);
+      if (!rc) rc = (int)cudaStreamWaitEvent(to, e, 0);
+      continue;
+    }
+    rc = run_one(op, (rdsic_stream_t)((side && op->lane == 1) ? side : mainS));
+    if (!rc) ++launched;  // every compute op is exactly one kernel launch
+  }
+  for (int k = 0; k < 2; ++k)
+    if (ev[k]) cudaEventDestroy(ev[k]);
+  if (rc && failed_op) *failed_op = i - 1;
+  if (n_launched) *n_launched = launched;
+  return rc;
+}
+
 int rdsic_run_program(const rdsic_op* ops, int n_ops, rdsic_stream_t stream, int* n_launched, int* failed_op) {
   if (!ops || n_ops < 0) return RDSIC_E_ARG;
-  int launched = 0;
-  for (int i = 0; i < n_ops; ++i) {
-    int rc = run_one(&ops[i], stream);
-    if (rc) {
-      if (failed_op) *failed_op = i;
-      if (n_launched) *n_launched = launched;
-      return rc;
-    }
-    ++launched;  // every op is exactly one kernel launch
-  }
-  if (n_launched) *n_launched = launched;
-  return 0;
+  return run_lanes(ops, n_ops, (cudaStream_t)stream, nullptr, n_launched, failed_op);
 }
 
 struct rdsic_graph {
@@ -87,11 +104,15 @@ int rdsic_graph_create(const rdsic_op* ops, int n_ops, rdsic_stream_t stream, rd
   cudaStream_t s = (cudaStream_t)stream;
   rdsic_graph* g = new (std::nothrow) rdsic_graph();
   if (!g) return (int)cudaErrorMemoryAllocation;
-  cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+  cudaStream_t side = nullptr;  // lane 1 during capture only: becomes parallel graph branches
+  cudaError_t e = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete g; return (int)e; }
+  e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) { cudaStreamDestroy(side); delete g; return (int)e; }
   int launched = 0, failed = -1;
-  int rc = rdsic_run_program(ops, n_ops, stream, &launched, &failed);
+  int rc = run_lanes(ops, n_ops, s, side, &launched, &failed);
   e = cudaStreamEndCapture(s, &g->graph);
+  cudaStreamDestroy(side);
   if (rc || e != cudaSuccess) {
     if (g->graph) cudaGraphDestroy(g->graph);
     delete g;

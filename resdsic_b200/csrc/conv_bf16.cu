@@ -28,13 +28,14 @@ namespace {
 constexpr int BM = 128;        // UMMA M (cta_group::1)
 constexpr int BK = 64;         // bf16 elements per 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // TMA warp + MMA warp + epilogue warps
 constexpr int MAX_STAGES = 8;
 constexpr uint32_t SPIN_LIMIT = 1u << 22;  // a lost mbarrier signal traps instead of hanging the GPU
 
 struct TcGeom {
   int TH, TW, tiles_y, tiles_x;
-  int BN, n_tiles, kb_per_tap, num_k_iters, num_stages, tmem_cols;
+  int BN, n_tiles, total_tiles, kb_per_tap, num_k_iters, num_stages, tmem_cols;
   int b_stage_bytes;
 };
 
@@ -46,6 +47,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -178,11 +182,15 @@ __device__ __forceinline__ void store16(const rdsic_view& vw, size_t elem, const
 }
 
 // ------------------------------------------------------------------ the kernel
+// Persistent, warp-specialised: each CTA walks tiles blockIdx.x, +gridDim.x, ... ; the TMA ring and the
+// two TMEM accumulator buffers run continuously across tiles, so the epilogue of tile t overlaps the main
+// loop of tile t+1 and the producer prefetches the next tile's operands while the last MMAs retire.
+//
 // EPI: fused epilogue (compile time, keeps the epilogue's code small enough for the I-cache);
 // PLAIN: every output/residual view is channels-last with 16-element-aligned rows (vector path),
 //        otherwise the generic scalar addressing (NCHW output, PixelShuffle) is used.
 template <int EPI, bool PLAIN>
-__global__ void __launch_bounds__(NUM_THREADS, 2)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const rdsic_conv_desc d, const TcGeom g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -191,19 +199,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int stage_bytes = A_STAGE_BYTES + g.b_stage_bytes;
   uint64_t* full_bar = (uint64_t*)(smem + (size_t)g.num_stages * stage_bytes);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
-  uint64_t* acc_bar = empty_bar + MAX_STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(acc_bar + 1);
+  uint64_t* acc_full = empty_bar + MAX_STAGES;   // [2] MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;            // [2] epilogue -> MMA
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-
-  // ---- tile coordinates
-  int t = blockIdx.x;
-  const int tx = t % g.tiles_x;
-  t /= g.tiles_x;
-  const int ty = t % g.tiles_y;
-  const int b = t / g.tiles_y;
-  const int oy0 = ty * g.TH, ox0 = tx * g.TW;
-  const int n0 = blockIdx.y * g.BN;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_a) : "memory");
@@ -212,7 +212,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(acc_bar, 1);
+    for (int k = 0; k < 2; ++k) {
+      mbar_init(&acc_full[k], 1);
+      mbar_init(&acc_empty[k], NUM_EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // one warp allocates TMEM (and later frees it)
@@ -228,16 +231,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ================= TMA producer =================
     if (lane == 0) {
       const uint32_t tx_bytes = (uint32_t)stage_bytes;
-      for (int it = 0; it < g.num_k_iters; ++it) {
-        const int s = it % g.num_stages;
-        const uint32_t ph = (uint32_t)(it / g.num_stages) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        const int tap = it / g.kb_per_tap, cb = it - tap * g.kb_per_tap;
-        const int r = tap / d.KW, sx = tap - r * d.KW;
-        uint8_t* a_dst = smem + (size_t)s * stage_bytes;
-        mbar_expect_tx(&full_bar[s], tx_bytes);
-        tma_load_4d(a_dst, &tmap_a, &full_bar[s], cb * BK, ox0 * d.stride - d.pad_w + sx, oy0 * d.stride - d.pad_h + r, b);
-        tma_load_2d(a_dst + A_STAGE_BYTES, &tmap_b, &full_bar[s], tap * d.Cin + cb * BK, n0);
+      uint32_t ring = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        const int nt = tile % g.n_tiles;
+        int t = tile / g.n_tiles;
+        const int tx = t % g.tiles_x;
+        t /= g.tiles_x;
+        const int ty = t % g.tiles_y, b = t / g.tiles_y;
+        const int x0 = tx * g.TW * d.stride - d.pad_w, y0 = ty * g.TH * d.stride - d.pad_h, n0 = nt * g.BN;
+        for (int it = 0; it < g.num_k_iters; ++it, ++ring) {
+          const int s = ring % g.num_stages;
+          const uint32_t ph = (ring / g.num_stages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          const int tap = it / g.kb_per_tap, cb = it - tap * g.kb_per_tap;
+          const int r = tap / d.KW, sx = tap - r * d.KW;
+          uint8_t* a_dst = smem + (size_t)s * stage_bytes;
+          mbar_expect_tx(&full_bar[s], tx_bytes);
+          tma_load_4d(a_dst, &tmap_a, &full_bar[s], cb * BK, x0 + sx, y0 + r, b);
+          tma_load_2d(a_dst + A_STAGE_BYTES, &tmap_b, &full_bar[s], tap * d.Cin + cb * BK, n0);
+        }
       }
     }
     __syncwarp();
@@ -245,81 +257,104 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(g.BN);
-      for (int it = 0; it < g.num_k_iters; ++it) {
-        const int s = it % g.num_stages;
-        const uint32_t ph = (uint32_t)(it / g.num_stages) & 1u;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t ring = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t buf = lt & 1u, aph = (lt >> 1) & 1u;
+        mbar_wait(&acc_empty[buf], aph ^ 1u);  // epilogue has drained this accumulator buffer
         tcgen05_fence_after();
-        const int cb = it % g.kb_per_tap;
-        const int kc = min(BK, d.Cin - cb * BK) / 16;  // valid 16-wide K steps in this block
-        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint64_t da = make_sw128_desc(a_addr), db = make_sw128_desc(a_addr + A_STAGE_BYTES);
-        for (int k = 0; k < kc; ++k)  // +32 bytes (= 2 x 16 B units) per 16 bf16 of K inside the swizzle atom
-          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-        tcgen05_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+        const uint32_t acc = tmem_base + buf * (uint32_t)g.BN;
+        for (int it = 0; it < g.num_k_iters; ++it, ++ring) {
+          const int s = ring % g.num_stages;
+          const uint32_t ph = (ring / g.num_stages) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tcgen05_fence_after();
+          const int cb = it % g.kb_per_tap;
+          const int kc = min(BK, d.Cin - cb * BK) / 16;  // valid 16-wide K steps in this block
+          const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint64_t da = make_sw128_desc(a_addr), db = make_sw128_desc(a_addr + A_STAGE_BYTES);
+          for (int k = 0; k < kc; ++k)  // +32 bytes (= 2 x 16 B units) per 16 bf16 of K inside the swizzle atom
+            umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          tcgen05_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+        }
+        tcgen05_commit(&acc_full[buf]);  // accumulator complete
       }
-      tcgen05_commit(acc_bar);  // accumulator complete
     }
     __syncwarp();
   } else {
-    // ================= epilogue (warps 2..5) =================
+    // ================= epilogue (warps 2..9): two warps per TMEM lane quarter, interleaved column chunks
     constexpr bool NEED_RES = EPI == RDSIC_EPI_RES_GELU || EPI == RDSIC_EPI_ADD_RES || EPI == RDSIC_EPI_GATE ||
                               EPI == RDSIC_EPI_GDN || EPI == RDSIC_EPI_IGDN || EPI == RDSIC_EPI_LRP;
     constexpr bool NEED_AUX = EPI == RDSIC_EPI_GATE;
-    const int q = warp % 4;  // TMEM lane quarter this warp may access
+    const int q = warp % 4;              // TMEM lane quarter this warp may access
+    const int half = (warp - 2) / 4;     // which of the two warps sharing the quarter
     const int ml = q * 32 + lane;
-    const int oy = oy0 + ml / g.TW, ox = ox0 + ml % g.TW;
-    const bool row_ok = oy < d.OH && ox < d.OW;
-    const size_t pix = ((size_t)b * d.OHt + (oy * d.osy + d.ooy)) * d.OWt + (ox * d.osx + d.oox);
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int dy = ml / g.TW, dx = ml % g.TW;
+    const int nchunks = g.BN / 16;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++lt) {
+      const int nt = tile % g.n_tiles;
+      int t = tile / g.n_tiles;
+      const int tx = t % g.tiles_x;
+      t /= g.tiles_x;
+      const int ty = t % g.tiles_y, b = t / g.tiles_y;
+      const int oy = ty * g.TH + dy, ox = tx * g.TW + dx, n0 = nt * g.BN;
+      const bool row_ok = oy < d.OH && ox < d.OW;
+      const size_t pix = ((size_t)b * d.OHt + (oy * d.osy + d.ooy)) * d.OWt + (ox * d.osx + d.oox);
+      const uint32_t buf = lt & 1u, aph = (lt >> 1) & 1u;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)g.BN;
 
-    mbar_wait(acc_bar, 0);
-    tcgen05_fence_after();
-    for (int j = 0; j < g.BN / 16; ++j) {
-      float v[16];
-      tmem_ld16(trow + (uint32_t)(j * 16), v);
-      const int nb = n0 + j * 16;
-      if (!row_ok || nb >= d.Cout) continue;
-      if (PLAIN) {
-        if (d.bias) {
-          const float4* bp = reinterpret_cast<const float4*>(d.bias + nb);
+      mbar_wait(&acc_full[buf], aph);
+      tcgen05_fence_after();
+      for (int j = half; j < nchunks; j += 2) {
+        float v[16];
+        tmem_ld16(trow + (uint32_t)(j * 16), v);
+        const int nb = n0 + j * 16;
+        if (!row_ok || nb >= d.Cout) continue;
+        if (PLAIN) {
+          float res[16], aux[16];
+          if (NEED_RES) load16(d.res, pix * (size_t)d.res.ld + d.res.coff + nb, res);
+          if (NEED_AUX) load16(d.aux, pix * (size_t)d.aux.ld + d.aux.coff + nb, aux);
+          if (d.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(d.bias + nb);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 f = __ldg(bp + i);
-            v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
+            for (int i = 0; i < 4; ++i) {
+              const float4 f = __ldg(bp + i);
+              v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
+            }
           }
-        }
-        float res[16], aux[16];
-        if (NEED_RES) load16(d.res, pix * (size_t)d.res.ld + d.res.coff + nb, res);
-        if (NEED_AUX) load16(d.aux, pix * (size_t)d.aux.ld + d.aux.coff + nb, aux);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = epi_apply<EPI>(v[i], NEED_RES ? res[i] : 0.f, NEED_AUX ? aux[i] : 0.f);
-        store16(d.out, pix * (size_t)d.out.ld + d.out.coff + nb, v, false);
-        if (d.out2.ptr) store16(d.out2, pix * (size_t)d.out2.ld + d.out2.coff + nb, v, d.out2_square != 0);
-        if (d.out3.ptr) store16(d.out3, pix * (size_t)d.out3.ld + d.out3.coff + nb, v, false);
-      } else {
-        const int HWt = d.OHt * d.OWt;
-        const int Cview = d.pixel_shuffle ? d.Cout / 4 : d.Cout;
-        for (int i = 0; i < 16; ++i) {  // deliberately not unrolled: rare path, keep the code small
-          const int n = nb + i;
-          if (n >= d.Cout) break;
-          float val = v[i] + (d.bias ? __ldg(d.bias + n) : 0.f);
-          int c = n;
-          size_t px = pix;
-          if (d.pixel_shuffle) {
-            c = n >> 2;
-            px = ((size_t)b * d.OHt + (2 * oy + ((n >> 1) & 1))) * d.OWt + (2 * ox + (n & 1));
+          for (int i = 0; i < 16; ++i) v[i] = epi_apply<EPI>(v[i], NEED_RES ? res[i] : 0.f, NEED_AUX ? aux[i] : 0.f);
+          store16(d.out, pix * (size_t)d.out.ld + d.out.coff + nb, v, false);
+          if (d.out2.ptr) store16(d.out2, pix * (size_t)d.out2.ld + d.out2.coff + nb, v, d.out2_square != 0);
+          if (d.out3.ptr) store16(d.out3, pix * (size_t)d.out3.ld + d.out3.coff + nb, v, false);
+        } else {
+          const int HWt = d.OHt * d.OWt;
+          const int Cview = d.pixel_shuffle ? d.Cout / 4 : d.Cout;
+          for (int i = 0; i < 16; ++i) {  // deliberately not unrolled: rare path, keep the code small
+            const int n = nb + i;
+            if (n >= d.Cout) break;
+            float val = v[i] + (d.bias ? __ldg(d.bias + n) : 0.f);
+            int c = n;
+            size_t px = pix;
+            if (d.pixel_shuffle) {
+              c = n >> 2;
+              px = ((size_t)b * d.OHt + (2 * oy + ((n >> 1) & 1))) * d.OWt + (2 * ox + (n & 1));
+            }
+            float res = 0.f, aux = 0.f;
+            if (NEED_RES) res = ld_elem(d.res.ptr, d.res.dtype, view_index(d.res, px, c, HWt, Cview));
+            if (NEED_AUX) aux = ld_elem(d.aux.ptr, d.aux.dtype, view_index(d.aux, px, c, HWt, Cview));
+            val = epi_apply<EPI>(val, res, aux);
+            st_elem(d.out.ptr, d.out.dtype, view_index(d.out, px, c, HWt, Cview), val);
+            if (d.out2.ptr)
+              st_elem(d.out2.ptr, d.out2.dtype, view_index(d.out2, px, c, HWt, Cview), d.out2_square ? val * val : val);
+            if (d.out3.ptr) st_elem(d.out3.ptr, d.out3.dtype, view_index(d.out3, px, c, HWt, Cview), val);
           }
-          float res = 0.f, aux = 0.f;
-          if (NEED_RES) res = ld_elem(d.res.ptr, d.res.dtype, view_index(d.res, px, c, HWt, Cview));
-          if (NEED_AUX) aux = ld_elem(d.aux.ptr, d.aux.dtype, view_index(d.aux, px, c, HWt, Cview));
-          val = epi_apply<EPI>(val, res, aux);
-          st_elem(d.out.ptr, d.out.dtype, view_index(d.out, px, c, HWt, Cview), val);
-          if (d.out2.ptr)
-            st_elem(d.out2.ptr, d.out2.dtype, view_index(d.out2, px, c, HWt, Cview), d.out2_square ? val * val : val);
-          if (d.out3.ptr) st_elem(d.out3.ptr, d.out3.dtype, view_index(d.out3, px, c, HWt, Cview), val);
         }
       }
+      // this warp's TMEM reads of the buffer are complete (tcgen05.wait::ld inside tmem_ld16): hand it back
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
   }
 
@@ -414,26 +449,35 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   g.tiles_x = ceil_div(OW, g.TW);
   g.tiles_y = ceil_div(OH, g.TH);
   g.BN = pick_bn(d->Cout);
+  const int m_tiles = B * g.tiles_y * g.tiles_x;
+  static const int tune_split = getenv("RDSIC_TC_SPLIT_N") ? atoi(getenv("RDSIC_TC_SPLIT_N")) : 1;
+  if (tune_split) {
+    // grids below one wave (latent-resolution layers): split N further so that more SMs get a tile.
+    // The B tensor map zero-fills rows past ceil16(Cout), so BN need not divide Cout.
+    const int c16 = (d->Cout + 15) / 16 * 16;
+    if (m_tiles * ceil_div(c16, g.BN) * 2 <= 148) {
+      const int n_wanted = 148 / m_tiles;  // never more tiles than SMs: a second round costs more than it gains
+      int bn = (ceil_div(c16, n_wanted) + 15) / 16 * 16;
+      if (bn < 32) bn = 32;
+      if (bn < g.BN) g.BN = bn;
+    }
+  }
   g.n_tiles = ceil_div(d->Cout, g.BN);
+  g.total_tiles = m_tiles * g.n_tiles;
   g.kb_per_tap = ceil_div(d->Cin, BK);
   g.num_k_iters = d->KH * d->KW * g.kb_per_tap;
   g.b_stage_bytes = g.BN * BK * 2;
   const int stage_bytes = A_STAGE_BYTES + g.b_stage_bytes;
-  // Pipeline depth / occupancy: short-K GEMMs (pointwise layers) are epilogue-dominated, so keep the smem
-  // footprint under half an SM and let two CTAs overlap one's epilogue with the other's main loop;
-  // long-K GEMMs take the whole SM with a deep TMA ring.
-  static const int tune_budget_kb = getenv("RDSIC_TC_SMEM_KB") ? atoi(getenv("RDSIC_TC_SMEM_KB")) : 0;
-  static const int tune_short_k = getenv("RDSIC_TC_SHORT_K") ? atoi(getenv("RDSIC_TC_SHORT_K")) : 6;
-  int budget = (g.num_k_iters <= tune_short_k ? 108 : 200) * 1024;
-  if (tune_budget_kb > 0) budget = tune_budget_kb * 1024;
-  int stages = budget / stage_bytes;
-  if (stages < 2) stages = (200 * 1024) / stage_bytes;
+  // one persistent CTA per SM owns the whole shared memory: as deep a TMA ring as fits (the ring keeps
+  // running across tiles, so even 2-3-iteration pointwise GEMMs keep many stages in flight)
+  static const int tune_stages = getenv("RDSIC_TC_STAGES") ? atoi(getenv("RDSIC_TC_STAGES")) : 0;
+  int stages = (200 * 1024) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages > g.num_k_iters) stages = g.num_k_iters;
-  if (stages < 1) return RDSIC_E_ARG;
+  if (tune_stages > 0 && tune_stages < stages) stages = tune_stages;
+  if (stages < 2) return RDSIC_E_ARG;
   g.num_stages = stages;
   g.tmem_cols = 32;
-  while (g.tmem_cols < g.BN) g.tmem_cols *= 2;
+  while (g.tmem_cols < 2 * g.BN) g.tmem_cols *= 2;  // two accumulator buffers
   RDSIC_CHECK_ARG(g.TW * d->stride <= 256 && g.TH * d->stride <= 256);
 
   // ---- tensor maps
@@ -452,7 +496,7 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   }
   {
     const int K = d->KH * d->KW * d->Cin;
-    const int n_rows = g.n_tiles * g.BN;  // host pads the packed weight to this many rows
+    const int n_rows = (d->Cout + 15) / 16 * 16;  // the host pads the packed weight to ceil16(Cout) rows
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)n_rows};
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)g.BN};
@@ -463,7 +507,7 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) return RDSIC_E_ARG;
   }
 
-  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * MAX_STAGES + 1) * 8 + 16;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * MAX_STAGES + 4) * 8 + 16;
   // vector epilogue needs channels-last views whose rows start on 16-element boundaries
   auto vec_ok = [](const rdsic_view& v) {
     return !v.ptr || (!v.nchw && v.ld % 8 == 0 && v.coff % 8 == 0 && ((uintptr_t)v.ptr % 16) == 0);
@@ -481,7 +525,14 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
     if (e != cudaSuccess) return (int)e;
     if (track) attr_set[dev][plain][d->epilogue] = true;
   }
-  dim3 grid(B * g.tiles_y * g.tiles_x, g.n_tiles);
+  static int sm_count[16] = {};
+  int sms = track ? sm_count[dev] : 0;
+  if (!sms) {
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    if (track) sm_count[dev] = sms;
+  }
+  const int grid = g.total_tiles < sms ? g.total_tiles : sms;
   kern<<<grid, NUM_THREADS, smem, stream>>>(ta, tb, dd, g);
   return rdsic_launch_status();
 }

@@ -35,8 +35,11 @@ class Win_noShift_Attention(B200Module):
             ResidualUnit(N), ResidualUnit(N), ResidualUnit(N), conv1x1(N, N))
 
     def emit(self, ctx: Ctx, x, out=None, out_dtype=None, **kw):
-        a = self.conv_a.emit(ctx, x)
+        ctx.prog.fork()  # trunk (conv_a) || attention branch (conv_b)
+        with ctx.prog.side():
+            a = self.conv_a.emit(ctx, x)
         b = x
         for m in list(self.conv_b)[:4]:
             b = m.emit(ctx, b)
+        ctx.prog.join()
         return self.conv_b[4].emit(ctx, b, epilogue=_lib.EPI_GATE, aux=a, res=x, out=out, out_dtype=out_dtype, **kw)

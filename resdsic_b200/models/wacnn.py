@@ -150,13 +150,11 @@ class WACNN(CompressionModel):
         # ---- hyper-synthesis straight into the support buffers
         means = ctx.buf(B, h, w, 512)
         scales = ctx.buf(B, h, w, 512)
-        for hs, dst in ((self.h_scale_s, scales), (self.h_mean_s, means)):
-            mods = list(hs)
-            t = mods[0].emit(ctx, z_hat, gelu=True)
-            t = mods[2].emit(ctx, t, gelu=True)
-            t = mods[4].emit(ctx, t, gelu=True)
-            t = mods[6].emit(ctx, t, gelu=True)
-            mods[8].emit(ctx, t, out=dst.channels(0, 320))
+        ctx.prog.fork()  # the two hyper-synthesis stacks are independent
+        with ctx.prog.side():
+            self.h_scale_s.emit(ctx, z_hat, last_kw=dict(out=scales.channels(0, 320)))
+        self.h_mean_s.emit(ctx, z_hat, last_kw=dict(out=means.channels(0, 320)))
+        ctx.prog.join()
         # ---- slice loop
         y_hat = ctx.buf(B, h, w, 320, f32)  # fp32 master copy of y_hat (LRP residual + g_s input)
         p.lik_y = torch.empty(B, 320, h, w, dtype=f32, device=device)
@@ -165,8 +163,11 @@ class WACNN(CompressionModel):
         for i in range(self.num_slices):
             k = min(i, self.max_support_slices)
             cin = 320 + 32 * k
+            ctx.prog.fork()  # cc_mean || cc_scale (cnn.py:167-173 are independent given the support)
+            with ctx.prog.side():
+                sc = self._stack(ctx, self.cc_scale_transforms[i], scales.channels(0, cin))
             mu = self._stack(ctx, self.cc_mean_transforms[i], means.channels(0, cin))
-            sc = self._stack(ctx, self.cc_scale_transforms[i], scales.channels(0, cin))
+            ctx.prog.join()
             slot = means.channels(320 + 32 * k, 32)  # slot i (i<5) or scratch slot 5
             yh_i = y_hat.channels(32 * i, 32)
             self.gaussian_conditional.emit(ctx, y.channels(32 * i, 32), sc, mu, p.lik_y, 32 * i, 320,

@@ -71,6 +71,40 @@ class Program:
         self._arr = None
         self._graph = None
         self._graph_stream = None
+        self._lane = 0
+
+    # ------------------------------------------------------------- lanes
+    def _append(self, op):
+        op.lane = self._lane
+        self.ops.append(op)
+        self._arr = None
+
+    def fork(self):
+        """Start a concurrent branch: ops added inside `with prog.side():` may run beside the main lane."""
+        op = Op()
+        op.kind = _lib.OP_FORK
+        self._append(op)
+
+    def join(self):
+        op = Op()
+        op.kind = _lib.OP_JOIN
+        self._append(op)
+
+    def side(self):
+        prog = self
+
+        class _Side:
+            def __enter__(self_):
+                prog._lane = 1
+
+            def __exit__(self_, *a):
+                prog._lane = 0
+
+        return _Side()
+
+    @property
+    def num_kernels(self):
+        return sum(1 for op in self.ops if op.kind not in (_lib.OP_FORK, _lib.OP_JOIN))
 
     # ------------------------------------------------------------- builders
     def conv(self, x: TV, weight, bias, Cout, KH, KW, stride, pad_h, pad_w, out: TV, epilogue=_lib.EPI_NONE,
@@ -96,7 +130,7 @@ class Program:
         op = Op()
         op.kind = _lib.OP_CONV
         op.u.conv = d
-        self.ops.append(op)
+        self._append(op)
         self.keep += [x.t, weight, bias, out.t] + [tv.t for tv in (res, aux, out2, out3) if tv is not None]
         return out
 
@@ -109,7 +143,7 @@ class Program:
         op = Op()
         op.kind = _lib.OP_ATTN
         op.u.attn = d
-        self.ops.append(op)
+        self._append(op)
         self.keep += [qkv.t, out.t, bias_table]
         return out
 
@@ -122,7 +156,7 @@ class Program:
         op = Op()
         op.kind = _lib.OP_EB
         op.u.eb = d
-        self.ops.append(op)
+        self._append(op)
         self.keep += [z.t, z_hat.t, lik, params, symbols]
 
     def gc(self, y: TV, mu: TV, scale: TV, y_hat_dsts, lik, lik_coff, Ctot, table, symbols=None, indexes=None,
@@ -138,7 +172,7 @@ class Program:
         op = Op()
         op.kind = _lib.OP_GC
         op.u.gc = d
-        self.ops.append(op)
+        self._append(op)
         self.keep += [y.t, mu.t, scale.t, lik, table, symbols, indexes] + [tv.t for tv in y_hat_dsts]
 
     def copy(self, src: TV, dst: TV, op_code=0):
@@ -148,7 +182,7 @@ class Program:
         op = Op()
         op.kind = _lib.OP_COPY
         op.u.copy = d
-        self.ops.append(op)
+        self._append(op)
         self.keep += [src.t, dst.t]
         return dst
 
@@ -160,7 +194,7 @@ class Program:
         op = Op()
         op.kind = _lib.OP_PATCH
         op.u.patch = d
-        self.ops.append(op)
+        self._append(op)
         self.keep += [x.t, out.t]
         return out
 
@@ -172,7 +206,7 @@ class Program:
         op = Op()
         op.kind = _lib.OP_LN
         op.u.ln = d
-        self.ops.append(op)
+        self._append(op)
         self.keep += [x.t, out.t, gamma, beta]
         return out
 
@@ -188,7 +222,7 @@ class Program:
 
     @property
     def num_launches(self):
-        return len(self.ops)
+        return self.num_kernels
 
     def run(self, stream=None):
         """Launch every op in order on `stream` (default: torch's current stream)."""
@@ -216,7 +250,7 @@ class Program:
                            "graph capture")
                 self._graph, self._graph_stream = h, side
             _lib.check(L.rdsic_graph_launch(self._graph, stream), "graph launch")
-        return len(self.ops)
+        return self.num_kernels
 
     def __del__(self):
         try:

@@ -173,11 +173,18 @@ enum { RDSIC_OP_CONV = 0, RDSIC_OP_ATTN = 1, RDSIC_OP_EB = 2, RDSIC_OP_GC = 3, R
        RDSIC_OP_FORK = 7, RDSIC_OP_JOIN = 8 };
 
 /* One node of a forward "program" (WACNN.forward, cnn.py:143-193, is ~330 of these). */
-/* Independent branches (cc_mean || cc_scale, h_mean_s || h_scale_s, conv_a || conv_b) may run concurrently:
- * FORK makes lane 1 wait for everything issued so far on lane 0, ops with lane = 1 then run beside the
- * lane-0 ops that follow, JOIN makes lane 0 wait for lane 1.  rdsic_run_program() executes all lanes in
- * program order on the one stream it is given (always correct); the CUDA-graph form turns lanes into
- * parallel graph branches. */
+/* Independent branches (cc_mean || cc_scale, h_mean_s || h_scale_s, conv_a || conv_b, the context stacks of
+ * slices 5..9) may run concurrently on up to RDSIC_MAX_LANES lanes.  A SYNC op (kinds FORK / JOIN are the
+ * same operation, named for readability) makes lane `op.lane` wait for everything issued so far on lane
+ * `op.u.sync.src`; every other op runs on its `lane`.  rdsic_run_program() executes all lanes in program
+ * order on the one stream it is given (always a valid schedule); the CUDA-graph form turns lanes into
+ * parallel graph branches and joins every lane back into lane 0 at the end. */
+#define RDSIC_MAX_LANES 12
+typedef struct rdsic_sync_desc {
+  int32_t src;
+  int32_t pad_;
+} rdsic_sync_desc;
+
 typedef struct rdsic_op {
   int32_t kind;
   int32_t lane;
@@ -189,6 +196,7 @@ typedef struct rdsic_op {
     rdsic_copy_desc copy;
     rdsic_ln_desc ln;
     rdsic_patch_desc patch;
+    rdsic_sync_desc sync;
   } u;
 } rdsic_op;
 

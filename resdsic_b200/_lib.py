@@ -77,9 +77,16 @@ class PatchDesc(C.Structure):
                 ("OW", C.c_int32), ("Kp", C.c_int32), ("pad_", C.c_int32)]
 
 
+class SyncDesc(C.Structure):
+    _fields_ = [("src", C.c_int32), ("pad_", C.c_int32)]
+
+
+MAX_LANES = 12
+
+
 class _OpUnion(C.Union):
     _fields_ = [("conv", ConvDesc), ("attn", AttnDesc), ("eb", EBDesc), ("gc", GCDesc), ("copy", CopyDesc),
-                ("ln", LNDesc), ("patch", PatchDesc)]
+                ("ln", LNDesc), ("patch", PatchDesc), ("sync", SyncDesc)]
 
 
 class Op(C.Structure):

@@ -1,6 +1,7 @@
 // C-ABI entry points: dtype dispatch, the program executor and its CUDA-graph form.
 // (The per-op entry points of entropy.cu / layout.cu are defined next to their kernels.)
 #include <new>
+#include <vector>
 
 #include "common.cuh"
 
@@ -60,30 +61,43 @@ static int run_one(const rdsic_op* op, rdsic_stream_t stream) {
   }
 }
 
-// side == nullptr: every lane runs in program order on `mainS` (serial, always correct)
-static int run_lanes(const rdsic_op* ops, int n_ops, cudaStream_t mainS, cudaStream_t side, int* n_launched,
+// lanes == nullptr: every lane runs in program order on `mainS` (serial, always correct).
+// Otherwise lanes[0] == mainS and lanes[1..] are capture-time side streams.
+static int run_lanes(const rdsic_op* ops, int n_ops, cudaStream_t mainS, cudaStream_t* lanes, int* n_launched,
                      int* failed_op) {
   int launched = 0, rc = 0, i = 0;
-  cudaEvent_t ev[2] = {nullptr, nullptr};
-  if (side) {
-    for (int k = 0; k < 2 && !rc; ++k) rc = (int)cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
-  }
+  std::vector<cudaEvent_t> events;
+  bool used[RDSIC_MAX_LANES] = {};
+  auto sync = [&](int waiter, int src) -> int {
+    cudaEvent_t e = nullptr;
+    int r = (int)cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    if (r) return r;
+    events.push_back(e);
+    r = (int)cudaEventRecord(e, lanes[src]);
+    if (!r) r = (int)cudaStreamWaitEvent(lanes[waiter], e, 0);
+    return r;
+  };
   for (; i < n_ops && !rc; ++i) {
     const rdsic_op* op = &ops[i];
+    if (op->lane < 0 || op->lane >= RDSIC_MAX_LANES) { rc = RDSIC_E_ARG; break; }
     if (op->kind == RDSIC_OP_FORK || op->kind == RDSIC_OP_JOIN) {
-      if (!side) continue;
-      cudaStream_t from = op->kind == RDSIC_OP_FORK ? mainS : side, to = op->kind == RDSIC_OP_FORK ? side : mainS;
-      cudaEvent_t e = ev[op->kind == RDSIC_OP_FORK ? 0 : 1];
-      rc = (int)cudaEventRecord(e, from);
-      if (!rc) rc = (int)cudaStreamWaitEvent(to, e, 0);
+      const int src = op->u.sync.src;
+      if (src < 0 || src >= RDSIC_MAX_LANES || src == op->lane) { rc = RDSIC_E_ARG; break; }
+      if (lanes) {
+        used[op->lane] = used[src] = true;
+        rc = sync(op->lane, src);
+      }
       continue;
     }
-    rc = run_one(op, (rdsic_stream_t)((side && op->lane == 1) ? side : mainS));
+    if (lanes) used[op->lane] = true;
+    rc = run_one(op, (rdsic_stream_t)(lanes ? lanes[op->lane] : mainS));
     if (!rc) ++launched;  // every compute op is exactly one kernel launch
   }
-  for (int k = 0; k < 2; ++k)
-    if (ev[k]) cudaEventDestroy(ev[k]);
-  if (rc && failed_op) *failed_op = i - 1;
+  if (lanes && !rc)
+    for (int l = 1; l < RDSIC_MAX_LANES && !rc; ++l)
+      if (used[l]) rc = sync(0, l);  // nothing may stay un-joined when the capture ends
+  for (cudaEvent_t e : events) cudaEventDestroy(e);
+  if (rc && failed_op) *failed_op = i < n_ops ? i : n_ops - 1;
   if (n_launched) *n_launched = launched;
   return rc;
 }
@@ -104,15 +118,22 @@ int rdsic_graph_create(const rdsic_op* ops, int n_ops, rdsic_stream_t stream, rd
   cudaStream_t s = (cudaStream_t)stream;
   rdsic_graph* g = new (std::nothrow) rdsic_graph();
   if (!g) return (int)cudaErrorMemoryAllocation;
-  cudaStream_t side = nullptr;  // lane 1 during capture only: becomes parallel graph branches
-  cudaError_t e = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
-  if (e != cudaSuccess) { delete g; return (int)e; }
+  // side lanes exist during capture only: they become parallel branches of the graph
+  cudaStream_t lanes[RDSIC_MAX_LANES] = {};
+  lanes[0] = s;
+  cudaError_t e = cudaSuccess;
+  for (int l = 1; l < RDSIC_MAX_LANES && e == cudaSuccess; ++l) e = cudaStreamCreateWithFlags(&lanes[l], cudaStreamNonBlocking);
+  auto drop_lanes = [&]() {
+    for (int l = 1; l < RDSIC_MAX_LANES; ++l)
+      if (lanes[l]) cudaStreamDestroy(lanes[l]);
+  };
+  if (e != cudaSuccess) { drop_lanes(); delete g; return (int)e; }
   e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
-  if (e != cudaSuccess) { cudaStreamDestroy(side); delete g; return (int)e; }
+  if (e != cudaSuccess) { drop_lanes(); delete g; return (int)e; }
   int launched = 0, failed = -1;
-  int rc = run_lanes(ops, n_ops, s, side, &launched, &failed);
+  int rc = run_lanes(ops, n_ops, s, lanes, &launched, &failed);
   e = cudaStreamEndCapture(s, &g->graph);
-  cudaStreamDestroy(side);
+  drop_lanes();
   if (rc || e != cudaSuccess) {
     if (g->graph) cudaGraphDestroy(g->graph);
     delete g;

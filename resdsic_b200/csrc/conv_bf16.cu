@@ -124,60 +124,89 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 
 // ------------------------------------------------------------------ epilogue helpers
+// Epilogue math for the bf16 path: erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, two MUFU ops) and a
+// MUFU-based sigmoid -- two orders of magnitude below the bf16 rounding of the stored result, and ~3x
+// cheaper than erff()/expf()+IEEE divide, which made the pointwise layers ALU-bound (profiles/).
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float erf_abs = 1.0f - p * t * __expf(-z * z);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
 template <int EPI>
 __device__ __forceinline__ float epi_apply(float v, float res, float aux) {
-  if (EPI == RDSIC_EPI_GELU) return gelu_erf(v);
-  if (EPI == RDSIC_EPI_RES_GELU) return gelu_erf(v + res);
+  if (EPI == RDSIC_EPI_GELU) return gelu_fast(v);
+  if (EPI == RDSIC_EPI_RES_GELU) return gelu_fast(v + res);
   if (EPI == RDSIC_EPI_ADD_RES) return v + res;
-  if (EPI == RDSIC_EPI_GATE) return aux * sigmoid_f(v) + res;
+  if (EPI == RDSIC_EPI_GATE) return aux * sigmoid_fast(v) + res;
   if (EPI == RDSIC_EPI_GDN) return res * rsqrtf(v);
   if (EPI == RDSIC_EPI_IGDN) return res * sqrtf(v);
   if (EPI == RDSIC_EPI_LRP) return res + 0.5f * tanhf(v);
   return v;
 }
 
-// 16 consecutive channels of one pixel, 16-byte vector accesses (host guarantees the alignment)
+// 16 consecutive channels of one pixel = one 32-byte (bf16) or two 32-byte (fp32) accesses; sm_100 has
+// 256-bit LDG/STG, and the host guarantees 32-byte alignment of every chunk on the PLAIN path.
+struct Pack8 {
+  uint32_t w[8];
+};
+__device__ __forceinline__ Pack8 ldg256(const void* p) {
+  Pack8 r;
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg256(void* p, const Pack8& r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.w[0]), "r"(r.w[1]), "r"(r.w[2]),
+               "r"(r.w[3]), "r"(r.w[4]), "r"(r.w[5]), "r"(r.w[6]), "r"(r.w[7])
+               : "memory");
+}
+__device__ __forceinline__ void unpack_bf16x16(const Pack8& r, float* o) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    o[2 * i] = __uint_as_float(r.w[i] << 16);
+    o[2 * i + 1] = __uint_as_float(r.w[i] & 0xFFFF0000u);
+  }
+}
 __device__ __forceinline__ void load16(const rdsic_view& vw, size_t elem, float* o) {
   if (vw.dtype == RDSIC_BF16) {
-    const uint4* p = reinterpret_cast<const uint4*>((const __nv_bfloat16*)vw.ptr + elem);
-    const uint4 q0 = p[0], q1 = p[1];
-    const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    unpack_bf16x16(ldg256((const __nv_bfloat16*)vw.ptr + elem), o);
+  } else {
+    const Pack8 r0 = ldg256((const float*)vw.ptr + elem), r1 = ldg256((const float*)vw.ptr + elem + 8);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      o[2 * i] = __uint_as_float(w[i] << 16);
-      o[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
-    }
-  } else {
-    const float4* p = reinterpret_cast<const float4*>((const float*)vw.ptr + elem);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 f = p[i];
-      o[4 * i] = f.x; o[4 * i + 1] = f.y; o[4 * i + 2] = f.z; o[4 * i + 3] = f.w;
+      o[i] = __uint_as_float(r0.w[i]);
+      o[8 + i] = __uint_as_float(r1.w[i]);
     }
   }
 }
-
 __device__ __forceinline__ void store16(const rdsic_view& vw, size_t elem, const float* v, bool sq) {
   if (vw.dtype == RDSIC_BF16) {
-    uint32_t w[8];
+    Pack8 r;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float a0 = v[2 * i], a1 = v[2 * i + 1];
       if (sq) { a0 *= a0; a1 *= a1; }
       __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
-      w[i] = *reinterpret_cast<uint32_t*>(&h);
+      r.w[i] = *reinterpret_cast<uint32_t*>(&h);
     }
-    uint4* p = reinterpret_cast<uint4*>((__nv_bfloat16*)vw.ptr + elem);
-    p[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    p[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    stg256((__nv_bfloat16*)vw.ptr + elem, r);
   } else {
-    float4* p = reinterpret_cast<float4*>((float*)vw.ptr + elem);
+    Pack8 r0, r1;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float4 f = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-      if (sq) { f.x *= f.x; f.y *= f.y; f.z *= f.z; f.w *= f.w; }
-      p[i] = f;
+    for (int i = 0; i < 8; ++i) {
+      r0.w[i] = __float_as_uint(sq ? v[i] * v[i] : v[i]);
+      r1.w[i] = __float_as_uint(sq ? v[8 + i] * v[8 + i] : v[8 + i]);
     }
+    stg256((float*)vw.ptr + elem, r0);
+    stg256((float*)vw.ptr + elem + 8, r1);
   }
 }
 
@@ -303,31 +332,73 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t buf = lt & 1u, aph = (lt >> 1) & 1u;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)g.BN;
 
-      mbar_wait(&acc_full[buf], aph);
-      tcgen05_fence_after();
-      for (int j = half; j < nchunks; j += 2) {
-        float v[16];
-        tmem_ld16(trow + (uint32_t)(j * 16), v);
-        const int nb = n0 + j * 16;
-        if (!row_ok || nb >= d.Cout) continue;
-        if (PLAIN) {
-          float res[16], aux[16];
-          if (NEED_RES) load16(d.res, pix * (size_t)d.res.ld + d.res.coff + nb, res);
-          if (NEED_AUX) load16(d.aux, pix * (size_t)d.aux.ld + d.aux.coff + nb, aux);
-          if (d.bias) {
-            const float4* bp = reinterpret_cast<const float4*>(d.bias + nb);
+      if (PLAIN) {
+        // Residual / gate operands are prefetched in groups of G chunks BEFORE the accumulator is awaited,
+        // so their HBM latency overlaps this tile's main loop instead of serialising per chunk.
+        constexpr int G = 3;
+        const bool res16 = NEED_RES && d.res.dtype == RDSIC_BF16, aux16 = NEED_AUX && d.aux.dtype == RDSIC_BF16;
+        const __nv_bfloat16* resp = (const __nv_bfloat16*)d.res.ptr + pix * (size_t)d.res.ld + d.res.coff + n0;
+        const __nv_bfloat16* auxp = (const __nv_bfloat16*)d.aux.ptr + pix * (size_t)d.aux.ld + d.aux.coff + n0;
+        Pack8 rr[G], ra[G];
+        bool waited = false;
+        for (int j0 = half; j0 < nchunks; j0 += 2 * G) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 f = __ldg(bp + i);
-              v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
+          for (int gI = 0; gI < G; ++gI) {
+            const int j = j0 + 2 * gI;
+            if (j < nchunks && row_ok && n0 + j * 16 < d.Cout) {
+              if (res16) rr[gI] = ldg256(resp + j * 16);
+              if (aux16) ra[gI] = ldg256(auxp + j * 16);
             }
           }
+          if (!waited) {
+            mbar_wait(&acc_full[buf], aph);
+            tcgen05_fence_after();
+            waited = true;
+          }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = epi_apply<EPI>(v[i], NEED_RES ? res[i] : 0.f, NEED_AUX ? aux[i] : 0.f);
-          store16(d.out, pix * (size_t)d.out.ld + d.out.coff + nb, v, false);
-          if (d.out2.ptr) store16(d.out2, pix * (size_t)d.out2.ld + d.out2.coff + nb, v, d.out2_square != 0);
-          if (d.out3.ptr) store16(d.out3, pix * (size_t)d.out3.ld + d.out3.coff + nb, v, false);
-        } else {
+          for (int gI = 0; gI < G; ++gI) {
+            const int j = j0 + 2 * gI;
+            if (j >= nchunks) break;
+            float v[16];
+            tmem_ld16(trow + (uint32_t)(j * 16), v);
+            const int nb = n0 + j * 16;
+            if (!row_ok || nb >= d.Cout) continue;
+            float res[16], aux[16];
+            if (NEED_RES) {
+              if (res16) unpack_bf16x16(rr[gI], res);
+              else load16(d.res, pix * (size_t)d.res.ld + d.res.coff + nb, res);
+            }
+            if (NEED_AUX) {
+              if (aux16) unpack_bf16x16(ra[gI], aux);
+              else load16(d.aux, pix * (size_t)d.aux.ld + d.aux.coff + nb, aux);
+            }
+            if (d.bias) {
+              const float4* bp = reinterpret_cast<const float4*>(d.bias + nb);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 f = __ldg(bp + i);
+                v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = epi_apply<EPI>(v[i], NEED_RES ? res[i] : 0.f, NEED_AUX ? aux[i] : 0.f);
+            store16(d.out, pix * (size_t)d.out.ld + d.out.coff + nb, v, false);
+            if (d.out2.ptr) store16(d.out2, pix * (size_t)d.out2.ld + d.out2.coff + nb, v, d.out2_square != 0);
+            if (d.out3.ptr) store16(d.out3, pix * (size_t)d.out3.ld + d.out3.coff + nb, v, false);
+          }
+        }
+        if (!waited) {  // (nchunks <= half cannot happen for BN >= 32, kept for safety)
+          mbar_wait(&acc_full[buf], aph);
+          tcgen05_fence_after();
+        }
+      } else {
+        mbar_wait(&acc_full[buf], aph);
+        tcgen05_fence_after();
+        for (int j = half; j < nchunks; j += 2) {
+          float v[16];
+          tmem_ld16(trow + (uint32_t)(j * 16), v);
+          const int nb = n0 + j * 16;
+          if (!row_ok || nb >= d.Cout) continue;
           const int HWt = d.OHt * d.OWt;
           const int Cview = d.pixel_shuffle ? d.Cout / 4 : d.Cout;
           for (int i = 0; i < 16; ++i) {  // deliberately not unrolled: rare path, keep the code small
@@ -508,9 +579,9 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   }
 
   const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * MAX_STAGES + 4) * 8 + 16;
-  // vector epilogue needs channels-last views whose rows start on 16-element boundaries
+  // vector epilogue: channels-last views whose 16-channel chunks are 32-byte aligned (256-bit LDG/STG)
   auto vec_ok = [](const rdsic_view& v) {
-    return !v.ptr || (!v.nchw && v.ld % 8 == 0 && v.coff % 8 == 0 && ((uintptr_t)v.ptr % 16) == 0);
+    return !v.ptr || (!v.nchw && v.ld % 16 == 0 && v.coff % 16 == 0 && ((uintptr_t)v.ptr % 32) == 0);
   };
   const bool plain = !d->pixel_shuffle && d->Cout % 16 == 0 && vec_ok(d->out) && vec_ok(d->out2) && vec_ok(d->out3) &&
                      vec_ok(d->res) && vec_ok(d->aux) && (!d->bias || ((uintptr_t)d->bias % 16) == 0);

@@ -35,11 +35,12 @@ class Win_noShift_Attention(B200Module):
             ResidualUnit(N), ResidualUnit(N), ResidualUnit(N), conv1x1(N, N))
 
     def emit(self, ctx: Ctx, x, out=None, out_dtype=None, **kw):
-        ctx.prog.fork()  # trunk (conv_a) || attention branch (conv_b)
-        with ctx.prog.side():
+        side = 1 if ctx.prog._lane != 1 else 2
+        ctx.prog.fork(side)  # trunk (conv_a) || attention branch (conv_b)
+        with ctx.prog.side(side):
             a = self.conv_a.emit(ctx, x)
         b = x
         for m in list(self.conv_b)[:4]:
             b = m.emit(ctx, b)
-        ctx.prog.join()
+        ctx.prog.join(side)
         return self.conv_b[4].emit(ctx, b, epilogue=_lib.EPI_GATE, aux=a, res=x, out=out, out_dtype=out_dtype, **kw)

@@ -160,23 +160,49 @@ class WACNN(CompressionModel):
         p.lik_y = torch.empty(B, 320, h, w, dtype=f32, device=device)
         p.symbols = torch.empty(B, 320, h, w, dtype=torch.int32, device=device) if with_symbols else None
         p.indexes = torch.empty(B, 320, h, w, dtype=torch.int32, device=device) if with_symbols else None
-        for i in range(self.num_slices):
+        prog = ctx.prog
+
+        def slice_ops(i, scale_lane):
+            """One slice (cnn.py:165-184) on the current lane, its cc_scale stack on `scale_lane`."""
             k = min(i, self.max_support_slices)
             cin = 320 + 32 * k
-            ctx.prog.fork()  # cc_mean || cc_scale (cnn.py:167-173 are independent given the support)
-            with ctx.prog.side():
+            prog.fork(scale_lane)  # cc_mean || cc_scale (cnn.py:167-173 are independent given the support)
+            with prog.side(scale_lane):
                 sc = self._stack(ctx, self.cc_scale_transforms[i], scales.channels(0, cin))
             mu = self._stack(ctx, self.cc_mean_transforms[i], means.channels(0, cin))
-            ctx.prog.join()
-            slot = means.channels(320 + 32 * k, 32)  # slot i (i<5) or scratch slot 5
+            prog.join(scale_lane)
             yh_i = y_hat.channels(32 * i, 32)
+            if i < self.max_support_slices:
+                lrp_in = means.channels(0, cin + 32)
+                slot = means.channels(320 + 32 * i, 32)
+                extra = dict(out2=slot, out3=scales.channels(320 + 32 * i, 32))  # becomes support of later slices
+            else:
+                # slices >= max_support share one support set, so they are independent of each other: each
+                # gets a private copy of the support + its own y_hat slot and may run concurrently
+                lrp_buf = ctx.buf(B, h, w, 512)
+                prog.copy(means.channels(0, 480), lrp_buf.channels(0, 480))
+                lrp_in, slot, extra = lrp_buf, lrp_buf.channels(480, 32), {}
             self.gaussian_conditional.emit(ctx, y.channels(32 * i, 32), sc, mu, p.lik_y, 32 * i, 320,
                                            y_hat_dsts=[yh_i, slot], symbols=p.symbols, indexes=p.indexes)
-            extra = {}
-            if i < self.max_support_slices:  # the refined slice becomes support for later slices
-                extra = dict(out2=slot, out3=scales.channels(320 + 32 * i, 32))
-            self._stack(ctx, self.lrp_transforms[i], means.channels(0, cin + 32), final=dict(
+            self._stack(ctx, self.lrp_transforms[i], lrp_in, final=dict(
                 epilogue=_lib.EPI_LRP, res=yh_i, out=yh_i, **extra))
+
+        for i in range(self.max_support_slices):  # serial chain: slice i+1 needs the refined slice i
+            slice_ops(i, 1)
+        tail = list(range(self.max_support_slices, self.num_slices))
+        for n, i in enumerate(tail):  # independent slices: one lane pair each
+            main_lane, scale_lane = 2 + 2 * n, 3 + 2 * n
+            if main_lane + 1 >= _lib.MAX_LANES:
+                main_lane, scale_lane = 0, 1
+            if main_lane:
+                prog.fork(main_lane)
+                with prog.side(main_lane):
+                    slice_ops(i, scale_lane)
+            else:
+                slice_ops(i, scale_lane)
+        for n, i in enumerate(tail):
+            if 2 + 2 * n + 1 < _lib.MAX_LANES:
+                prog.join(2 + 2 * n)
         # ---- g_s
         p.x_hat = torch.empty(B, 3, H, W, dtype=f32, device=device)
         y_hat_act = ctx.prog.copy(y_hat, ctx.buf(B, h, w, 320)) if bf16 else y_hat

@@ -79,26 +79,34 @@ class Program:
         self.ops.append(op)
         self._arr = None
 
-    def fork(self):
-        """Start a concurrent branch: ops added inside `with prog.side():` may run beside the main lane."""
+    def sync(self, waiter, src, kind=None):
+        """Lane `waiter` waits for everything issued so far on lane `src`."""
+        assert 0 <= waiter < _lib.MAX_LANES and 0 <= src < _lib.MAX_LANES and waiter != src
         op = Op()
-        op.kind = _lib.OP_FORK
-        self._append(op)
+        op.kind = _lib.OP_FORK if kind is None else kind
+        op.u.sync.src = src
+        op.lane = waiter
+        self.ops.append(op)
+        self._arr = None
 
-    def join(self):
-        op = Op()
-        op.kind = _lib.OP_JOIN
-        self._append(op)
+    def fork(self, lane=1, src=None):
+        """Start a concurrent branch on `lane` (it first waits for the current lane, or `src`)."""
+        self.sync(lane, self._lane if src is None else src, _lib.OP_FORK)
 
-    def side(self):
+    def join(self, lane=1, into=None):
+        self.sync(self._lane if into is None else into, lane, _lib.OP_JOIN)
+
+    def side(self, lane=1):
+        """`with prog.side(k):` -- ops added inside run on lane k."""
         prog = self
 
         class _Side:
             def __enter__(self_):
-                prog._lane = 1
+                self_.prev = prog._lane
+                prog._lane = lane
 
             def __exit__(self_, *a):
-                prog._lane = 0
+                prog._lane = self_.prev
 
         return _Side()
 

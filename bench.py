@@ -195,10 +195,8 @@ def run_ours(args):
     barrier()
     ms_e2e = e0.elapsed_time(e1)
 
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
+    from resdsic_b200.utils import max_over_ranks
+    ms, ms_e2e = max_over_ranks([ms, ms_e2e], device=dev)
 
     # ---- per-kernel-family device time of one step (eager, CUDA events around every launch)
     fam = None

@@ -124,20 +124,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 
 // ------------------------------------------------------------------ epilogue helpers
-// Epilogue math for the bf16 path: erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, two MUFU ops) and a
-// MUFU-based sigmoid -- two orders of magnitude below the bf16 rounding of the stored result, and ~3x
-// cheaper than erff()/expf()+IEEE divide, which made the pointwise layers ALU-bound (profiles/).
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float erf_abs = 1.0f - p * t * __expf(-z * z);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+// Epilogue math for the bf16 path.  The pointwise layers are instruction-issue bound in the epilogue
+// (ncu: ~34 thread instructions per output element with erff(), profiles/), so GELU is evaluated as
+// 0.5x(1 + tanh(x(c1 + c2 x^2 + c3 x^4))) with coefficients fitted to the exact erf form (max |err| 3e-5,
+// 16x tighter than the textbook tanh-GELU) and the single-instruction MUFU tanh (rel. err 2^-11): total error
+// < 0.05 bf16 ulp of the stored activation.  The fp32 mode (conv_f32.cu) keeps erff()/expf().
+__device__ __forceinline__ float tanh_mufu(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);  // beyond |x| = 8 the fitted quintic would turn over; tanh is +-1 there
+  const float x2 = xc * xc;
+  float t = fmaf(-3.58618502e-4f, x2, 3.70495807e-2f);
+  t = fmaf(t, x2, 7.97459395e-1f);
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_mufu(xc * t), h);
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_mufu(0.5f * x), 0.5f); }
 
 template <int EPI>
 __device__ __forceinline__ float epi_apply(float v, float res, float aux) {
@@ -259,8 +264,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
+      // NOTE: no integer division inside the per-stage loops -- this single thread's latency paces the whole
+      // pipeline (ncu: the divisions of the first version cost more than the MMAs of a stage).
       const uint32_t tx_bytes = (uint32_t)stage_bytes;
-      uint32_t ring = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
         const int nt = tile % g.n_tiles;
         int t = tile / g.n_tiles;
@@ -268,16 +276,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         t /= g.tiles_x;
         const int ty = t % g.tiles_y, b = t / g.tiles_y;
         const int x0 = tx * g.TW * d.stride - d.pad_w, y0 = ty * g.TH * d.stride - d.pad_h, n0 = nt * g.BN;
-        for (int it = 0; it < g.num_k_iters; ++it, ++ring) {
-          const int s = ring % g.num_stages;
-          const uint32_t ph = (ring / g.num_stages) & 1u;
-          mbar_wait(&empty_bar[s], ph ^ 1u);
-          const int tap = it / g.kb_per_tap, cb = it - tap * g.kb_per_tap;
-          const int r = tap / d.KW, sx = tap - r * d.KW;
-          uint8_t* a_dst = smem + (size_t)s * stage_bytes;
-          mbar_expect_tx(&full_bar[s], tx_bytes);
-          tma_load_4d(a_dst, &tmap_a, &full_bar[s], cb * BK, x0 + sx, y0 + r, b);
-          tma_load_2d(a_dst + A_STAGE_BYTES, &tmap_b, &full_bar[s], tap * d.Cin + cb * BK, n0);
+        int kcol = 0;  // K coordinate in the packed weight = tap * Cin + cb * 64
+        for (int r = 0; r < d.KH; ++r) {
+          for (int sx = 0; sx < d.KW; ++sx, kcol += d.Cin) {
+            for (int cb = 0; cb < g.kb_per_tap; ++cb) {
+              mbar_wait(&empty_bar[s], ph ^ 1u);
+              uint8_t* a_dst = smem + (size_t)s * stage_bytes;
+              mbar_expect_tx(&full_bar[s], tx_bytes);
+              tma_load_4d(a_dst, &tmap_a, &full_bar[s], cb * BK, x0 + sx, y0 + r, b);
+              tma_load_2d(a_dst + A_STAGE_BYTES, &tmap_b, &full_bar[s], kcol + cb * BK, n0);
+              if (++s == g.num_stages) { s = 0; ph ^= 1u; }
+            }
+          }
         }
       }
     }
@@ -286,24 +296,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(g.BN);
-      uint32_t ring = 0, lt = 0;
+      const int taps = d.KH * d.KW;
+      const int kc_last = (d.Cin - (g.kb_per_tap - 1) * BK) / 16;  // valid 16-wide K steps of a tap's last block
+      int s = 0;
+      uint32_t ph = 0, lt = 0;
       for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++lt) {
         const uint32_t buf = lt & 1u, aph = (lt >> 1) & 1u;
         mbar_wait(&acc_empty[buf], aph ^ 1u);  // epilogue has drained this accumulator buffer
         tcgen05_fence_after();
         const uint32_t acc = tmem_base + buf * (uint32_t)g.BN;
-        for (int it = 0; it < g.num_k_iters; ++it, ++ring) {
-          const int s = ring % g.num_stages;
-          const uint32_t ph = (ring / g.num_stages) & 1u;
-          mbar_wait(&full_bar[s], ph);
-          tcgen05_fence_after();
-          const int cb = it % g.kb_per_tap;
-          const int kc = min(BK, d.Cin - cb * BK) / 16;  // valid 16-wide K steps in this block
-          const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint64_t da = make_sw128_desc(a_addr), db = make_sw128_desc(a_addr + A_STAGE_BYTES);
-          for (int k = 0; k < kc; ++k)  // +32 bytes (= 2 x 16 B units) per 16 bf16 of K inside the swizzle atom
-            umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-          tcgen05_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+        uint32_t accumulate = 0;
+        for (int tap = 0; tap < taps; ++tap) {
+          for (int cb = 0; cb < g.kb_per_tap; ++cb) {
+            mbar_wait(&full_bar[s], ph);
+            tcgen05_fence_after();
+            const int kc = cb + 1 == g.kb_per_tap ? kc_last : BK / 16;
+            const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+            const uint64_t da = make_sw128_desc(a_addr), db = make_sw128_desc(a_addr + A_STAGE_BYTES);
+            for (int k = 0; k < kc; ++k) {  // +32 bytes (= 2 x 16 B units) per 16 bf16 of K inside the swizzle atom
+              umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, accumulate);
+              accumulate = 1;
+            }
+            tcgen05_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+            if (++s == g.num_stages) { s = 0; ph ^= 1u; }
+          }
         }
         tcgen05_commit(&acc_full[buf]);  // accumulator complete
       }
@@ -335,7 +351,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (PLAIN) {
         // Residual / gate operands are prefetched in groups of G chunks BEFORE the accumulator is awaited,
         // so their HBM latency overlaps this tile's main loop instead of serialising per chunk.
-        constexpr int G = 3;
+        constexpr int G = NEED_AUX ? 3 : 6;  // register budget: G x (res [+ aux]) 32-byte packs in flight
         const bool res16 = NEED_RES && d.res.dtype == RDSIC_BF16, aux16 = NEED_AUX && d.aux.dtype == RDSIC_BF16;
         const __nv_bfloat16* resp = (const __nv_bfloat16*)d.res.ptr + pix * (size_t)d.res.ld + d.res.coff + n0;
         const __nv_bfloat16* auxp = (const __nv_bfloat16*)d.aux.ptr + pix * (size_t)d.aux.ld + d.aux.coff + n0;

@@ -2,6 +2,8 @@
 import torch
 import torch.nn.functional as F
 
+from .sharding import gather_to_rank0, max_over_ranks, shard_range  # noqa: F401
+
 
 def pad_to_multiple(x, m=64):
     """Caller padding rule (reference utils/eval_model/__main__.py:89-101, training/step.py:236-238):

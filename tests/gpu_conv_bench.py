@@ -14,6 +14,7 @@ CASES = [  # name, Cin, Cout, k, stride, B, H, W (input)
     ("5x5s2_192_192", 192, 192, 5, 2, 8, 256, 384),
     ("3x3_cc_352_224", 352, 224, 3, 1, 8, 32, 48),
     ("3x3_cc_64_32", 64, 32, 3, 1, 8, 32, 48),
+    ("1x1_rutail_96_192_resgelu", 96, 192, 1, 1, 8, 128, 192),
 ]
 
 
@@ -27,7 +28,11 @@ def main():
         conv = Conv2d(cin, cout, k, s).to(DEV).set_precision("bf16")
         ctx = Ctx(DEV, "bf16")
         x = TV(torch.randn(B * H * W * cin, device=DEV).bfloat16(), B, H, W, cin)
-        out = conv.emit(ctx, x)
+        kw = {}
+        if "resgelu" in name:
+            from resdsic_b200 import _lib
+            kw = dict(epilogue=_lib.EPI_RES_GELU, res=TV(torch.randn(B * H * W * cout, device=DEV).bfloat16(), B, H, W, cout))
+        out = conv.emit(ctx, x, **kw)
         for _ in range(2):
             ctx.prog.run()
         torch.cuda.synchronize()

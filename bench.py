@@ -264,7 +264,7 @@ def profile_families(model, x_dev, dump=None):
     for rep in range(2):  # first rep warms caches
         evs[0].record()
         for i in range(n):
-            if prog.ops[i].kind in (_lib.OP_FORK, _lib.OP_JOIN):
+            if prog.ops[i].kind in _lib.SYNC_OPS:
                 evs[i + 1].record()
                 continue
             one = C.cast(base + i * opsz, C.POINTER(_lib.Op))
@@ -273,7 +273,7 @@ def profile_families(model, x_dev, dump=None):
         torch.cuda.synchronize()
     fam, per_op = {}, []
     for i in range(n):
-        if prog.ops[i].kind in (_lib.OP_FORK, _lib.OP_JOIN):
+        if prog.ops[i].kind in _lib.SYNC_OPS:
             continue
         k = names[prog.ops[i].kind]
         t = evs[i].elapsed_time(evs[i + 1])

@@ -170,7 +170,7 @@ typedef struct rdsic_patch_desc {
 } rdsic_patch_desc;
 
 enum { RDSIC_OP_CONV = 0, RDSIC_OP_ATTN = 1, RDSIC_OP_EB = 2, RDSIC_OP_GC = 3, RDSIC_OP_COPY = 4, RDSIC_OP_LN = 5, RDSIC_OP_PATCH = 6,
-       RDSIC_OP_FORK = 7, RDSIC_OP_JOIN = 8 };
+       RDSIC_OP_FORK = 7, RDSIC_OP_JOIN = 8, RDSIC_OP_RECORD = 9, RDSIC_OP_WAIT = 10 };
 
 /* One node of a forward "program" (WACNN.forward, cnn.py:143-193, is ~330 of these). */
 /* Independent branches (cc_mean || cc_scale, h_mean_s || h_scale_s, conv_a || conv_b, the context stacks of
@@ -178,11 +178,14 @@ enum { RDSIC_OP_CONV = 0, RDSIC_OP_ATTN = 1, RDSIC_OP_EB = 2, RDSIC_OP_GC = 3, R
  * same operation, named for readability) makes lane `op.lane` wait for everything issued so far on lane
  * `op.u.sync.src`; every other op runs on its `lane`.  rdsic_run_program() executes all lanes in program
  * order on the one stream it is given (always a valid schedule); the CUDA-graph form turns lanes into
- * parallel graph branches and joins every lane back into lane 0 at the end. */
+ * parallel graph branches and joins every lane back into lane 0 at the end.
+ * RECORD marks the current position of lane `op.lane` as event `u.sync.event`; a later WAIT makes its lane
+ * wait for exactly that position (decoupled fork/join, used to consume work pre-computed on another lane). */
 #define RDSIC_MAX_LANES 12
+#define RDSIC_MAX_EVENTS 128
 typedef struct rdsic_sync_desc {
-  int32_t src;
-  int32_t pad_;
+  int32_t src;   /* FORK / JOIN: lane to wait for */
+  int32_t event; /* RECORD / WAIT: event id in [0, RDSIC_MAX_EVENTS) */
 } rdsic_sync_desc;
 
 typedef struct rdsic_op {

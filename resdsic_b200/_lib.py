@@ -11,7 +11,8 @@ LIB_PATH = os.path.join(_PKG, "lib", "libresdsic_b200.so")
 
 F32, BF16 = 0, 1
 EPI_NONE, EPI_GELU, EPI_RES_GELU, EPI_ADD_RES, EPI_GATE, EPI_GDN, EPI_IGDN, EPI_LRP = range(8)
-OP_CONV, OP_ATTN, OP_EB, OP_GC, OP_COPY, OP_LN, OP_PATCH, OP_FORK, OP_JOIN = range(9)
+OP_CONV, OP_ATTN, OP_EB, OP_GC, OP_COPY, OP_LN, OP_PATCH, OP_FORK, OP_JOIN, OP_RECORD, OP_WAIT = range(11)
+SYNC_OPS = (OP_FORK, OP_JOIN, OP_RECORD, OP_WAIT)
 EB_STRIDE = 60
 
 
@@ -78,10 +79,11 @@ class PatchDesc(C.Structure):
 
 
 class SyncDesc(C.Structure):
-    _fields_ = [("src", C.c_int32), ("pad_", C.c_int32)]
+    _fields_ = [("src", C.c_int32), ("event", C.c_int32)]
 
 
 MAX_LANES = 12
+MAX_EVENTS = 128
 
 
 class _OpUnion(C.Union):

@@ -68,6 +68,7 @@ static int run_lanes(const rdsic_op* ops, int n_ops, cudaStream_t mainS, cudaStr
   int launched = 0, rc = 0, i = 0;
   std::vector<cudaEvent_t> events;
   bool used[RDSIC_MAX_LANES] = {};
+  cudaEvent_t named[RDSIC_MAX_EVENTS] = {};
   auto sync = [&](int waiter, int src) -> int {
     cudaEvent_t e = nullptr;
     int r = (int)cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
@@ -80,6 +81,24 @@ static int run_lanes(const rdsic_op* ops, int n_ops, cudaStream_t mainS, cudaStr
   for (; i < n_ops && !rc; ++i) {
     const rdsic_op* op = &ops[i];
     if (op->lane < 0 || op->lane >= RDSIC_MAX_LANES) { rc = RDSIC_E_ARG; break; }
+    if (op->kind == RDSIC_OP_RECORD || op->kind == RDSIC_OP_WAIT) {
+      const int id = op->u.sync.event;
+      if (id < 0 || id >= RDSIC_MAX_EVENTS) { rc = RDSIC_E_ARG; break; }
+      if (!lanes) continue;
+      used[op->lane] = true;
+      if (op->kind == RDSIC_OP_RECORD) {
+        if (!named[id]) {
+          rc = (int)cudaEventCreateWithFlags(&named[id], cudaEventDisableTiming);
+          if (rc) break;
+          events.push_back(named[id]);
+        }
+        rc = (int)cudaEventRecord(named[id], lanes[op->lane]);
+      } else {
+        if (!named[id]) { rc = RDSIC_E_ARG; break; }  // WAIT before its RECORD in program order
+        rc = (int)cudaStreamWaitEvent(lanes[op->lane], named[id], 0);
+      }
+      continue;
+    }
     if (op->kind == RDSIC_OP_FORK || op->kind == RDSIC_OP_JOIN) {
       const int src = op->u.sync.src;
       if (src < 0 || src >= RDSIC_MAX_LANES || src == op->lane) { rc = RDSIC_E_ARG; break; }

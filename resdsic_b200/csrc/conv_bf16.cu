@@ -111,14 +111,27 @@ __device__ __forceinline__ uint32_t make_idesc(int bn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
+// tcgen05.ld is asynchronous: issue any number of loads, then tmem_ld_wait(), then pass every destination
+// through tmem_ld_fence() -- an empty asm that makes the registers depend on the wait, so the compiler
+// cannot hoist their first use above it.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_fence(uint32_t* r) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+               "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  tmem_ld16_issue(taddr, r);
+  tmem_ld_wait();
+  tmem_ld_fence(r);
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
@@ -351,7 +364,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (PLAIN) {
         // Residual / gate operands are prefetched in groups of G chunks BEFORE the accumulator is awaited,
         // so their HBM latency overlaps this tile's main loop instead of serialising per chunk.
-        constexpr int G = NEED_AUX ? 3 : 6;  // register budget: G x (res [+ aux]) 32-byte packs in flight
+        constexpr int G = NEED_AUX ? 2 : 6;  // register budget: G x (res [+ aux]) 32-byte packs in flight
         const bool res16 = NEED_RES && d.res.dtype == RDSIC_BF16, aux16 = NEED_AUX && d.aux.dtype == RDSIC_BF16;
         const __nv_bfloat16* resp = (const __nv_bfloat16*)d.res.ptr + pix * (size_t)d.res.ld + d.res.coff + n0;
         const __nv_bfloat16* auxp = (const __nv_bfloat16*)d.aux.ptr + pix * (size_t)d.aux.ld + d.aux.coff + n0;
@@ -371,36 +384,51 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tcgen05_fence_after();
             waited = true;
           }
+          // chunks are processed in pairs: both TMEM loads are issued before one wait, and the two
+          // independent 16-element epilogues interleave (the epilogue is latency-, not issue-bound)
 #pragma unroll
-          for (int gI = 0; gI < G; ++gI) {
-            const int j = j0 + 2 * gI;
-            if (j >= nchunks) break;
-            float v[16];
-            tmem_ld16(trow + (uint32_t)(j * 16), v);
-            const int nb = n0 + j * 16;
-            if (!row_ok || nb >= d.Cout) continue;
-            float res[16], aux[16];
-            if (NEED_RES) {
-              if (res16) unpack_bf16x16(rr[gI], res);
-              else load16(d.res, pix * (size_t)d.res.ld + d.res.coff + nb, res);
-            }
-            if (NEED_AUX) {
-              if (aux16) unpack_bf16x16(ra[gI], aux);
-              else load16(d.aux, pix * (size_t)d.aux.ld + d.aux.coff + nb, aux);
-            }
-            if (d.bias) {
-              const float4* bp = reinterpret_cast<const float4*>(d.bias + nb);
+          for (int gI = 0; gI < G; gI += 2) {
+            const int ja = j0 + 2 * gI, jb = ja + 2;
+            if (ja >= nchunks) break;
+            const bool has_b = (gI + 1 < G) && jb < nchunks;
+            uint32_t ua[16], ub[16];
+            tmem_ld16_issue(trow + (uint32_t)(ja * 16), ua);
+            if (has_b) tmem_ld16_issue(trow + (uint32_t)(jb * 16), ub);
+            tmem_ld_wait();
+            tmem_ld_fence(ua);
+            if (has_b) tmem_ld_fence(ub);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 f = __ldg(bp + i);
-                v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
+            for (int hb = 0; hb < 2; ++hb) {
+              if (hb == 1 && !has_b) break;
+              const int j = hb ? jb : ja, gg = gI + hb;
+              const uint32_t* u = hb ? ub : ua;
+              const int nb = n0 + j * 16;
+              if (!row_ok || nb >= d.Cout) continue;
+              float v[16], res[16], aux[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(u[i]);
+              if (NEED_RES) {
+                if (res16) unpack_bf16x16(rr[gg < G ? gg : 0], res);
+                else load16(d.res, pix * (size_t)d.res.ld + d.res.coff + nb, res);
               }
-            }
+              if (NEED_AUX) {
+                if (aux16) unpack_bf16x16(ra[gg < G ? gg : 0], aux);
+                else load16(d.aux, pix * (size_t)d.aux.ld + d.aux.coff + nb, aux);
+              }
+              if (d.bias) {
+                const float4* bp = reinterpret_cast<const float4*>(d.bias + nb);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = epi_apply<EPI>(v[i], NEED_RES ? res[i] : 0.f, NEED_AUX ? aux[i] : 0.f);
-            store16(d.out, pix * (size_t)d.out.ld + d.out.coff + nb, v, false);
-            if (d.out2.ptr) store16(d.out2, pix * (size_t)d.out2.ld + d.out2.coff + nb, v, d.out2_square != 0);
-            if (d.out3.ptr) store16(d.out3, pix * (size_t)d.out3.ld + d.out3.coff + nb, v, false);
+                for (int i = 0; i < 4; ++i) {
+                  const float4 f = __ldg(bp + i);
+                  v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = epi_apply<EPI>(v[i], NEED_RES ? res[i] : 0.f, NEED_AUX ? aux[i] : 0.f);
+              store16(d.out, pix * (size_t)d.out.ld + d.out.coff + nb, v, false);
+              if (d.out2.ptr) store16(d.out2, pix * (size_t)d.out2.ld + d.out2.coff + nb, v, d.out2_square != 0);
+              if (d.out3.ptr) store16(d.out3, pix * (size_t)d.out3.ld + d.out3.coff + nb, v, false);
+            }
           }
         }
         if (!waited) {  // (nchunks <= half cannot happen for BN >= 32, kept for safety)

@@ -61,6 +61,30 @@ class Conv2d(B200Module):
         return (y, kw["out2"]) if want_sq else y
 
 
+def _emit_partial(self, ctx, x, part, split, out=None, res=None, gelu=False, out_dtype=None):
+    """Split-K form of a conv over a channel concatenation cat(a[split], b): part 0 convolves `a` with
+    W[:, :split] (no bias) into fp32 partial sums; part 1 convolves `b` with W[:, split:], adds the bias and
+    the partial sums `res` (and GELU).  conv(cat(a,b); W) == part0 + part1, which lets the slice loop
+    (cnn.py:165-182) pre-compute the latent-only part of every context transform off the serial chain."""
+    wdt = ctx.wdt_for(x)
+    w_lat, w_ext, b = self._packed(("split", wdt, split), (self.weight, self.bias), lambda: (
+        packing.pack_conv_weight(self.weight[:, :split], wdt), packing.pack_conv_weight(self.weight[:, split:], wdt),
+        self.bias.detach().float().contiguous()))
+    k, s, p = self.kernel_size, self.stride, self.padding
+    OH, OW = (x.H + 2 * p - k) // s + 1, (x.W + 2 * p - k) // s + 1
+    if part == 0:
+        assert x.C == split
+        out = out if out is not None else ctx.buf(x.B, OH, OW, self.out_channels, torch.float32)
+        return ctx.prog.conv(x, w_lat, None, self.out_channels, k, k, s, p, p, out, OH=OH, OW=OW)
+    assert x.C == self.in_channels - split and res is not None
+    out = out if out is not None else ctx.buf(x.B, OH, OW, self.out_channels, out_dtype)
+    epi = _lib.EPI_RES_GELU if gelu else _lib.EPI_ADD_RES
+    return ctx.prog.conv(x, w_ext, b, self.out_channels, k, k, s, p, p, out, epilogue=epi, res=res, OH=OH, OW=OW)
+
+
+Conv2d.emit_partial = _emit_partial
+
+
 class ConvTranspose2d(B200Module):
     """nn.ConvTranspose2d(in, out, 5, stride=2, padding=2, output_padding=1): four
     sub-pixel phase GEMMs (3x3, 3x2, 2x3, 2x2 taps), output exactly 2x the input."""

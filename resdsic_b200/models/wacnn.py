@@ -161,35 +161,74 @@ class WACNN(CompressionModel):
         p.symbols = torch.empty(B, 320, h, w, dtype=torch.int32, device=device) if with_symbols else None
         p.indexes = torch.empty(B, 320, h, w, dtype=torch.int32, device=device) if with_symbols else None
         prog = ctx.prog
+        S = self.max_support_slices
+        lat_m, lat_s = means.channels(0, 320), scales.channels(0, 320)
+
+        # -- off the serial chain: everything that only needs latent_means / latent_scales.
+        #    * slice 0 has no support: its whole cc_mean / cc_scale stacks;
+        #    * every other context transform: the latent-only part of its first conv,
+        #      conv(cat(latent, support); W) = conv(latent; W[:, :320]) + conv(support; W[:, 320:]),
+        #      as fp32 partial sums that the in-chain conv adds in its epilogue.
+        pre, pre_ev = {}, {}
+        jobs = [("mu0", None), ("sc0", None)]
+        for i in range(self.num_slices):
+            if i:
+                jobs += [(("cc_mean", i), lat_m), (("cc_scale", i), lat_s)]
+            jobs.append((("lrp", i), lat_m))
+        fam = {"cc_mean": self.cc_mean_transforms, "cc_scale": self.cc_scale_transforms, "lrp": self.lrp_transforms}
+        forked = set()
+        for n, (key, src) in enumerate(jobs):
+            lane = 2 + n % (_lib.MAX_LANES - 2)
+            if lane not in forked:
+                prog.fork(lane)
+                forked.add(lane)
+            with prog.side(lane):
+                if key == "mu0":
+                    pre[key] = self._stack(ctx, self.cc_mean_transforms[0], lat_m)
+                elif key == "sc0":
+                    pre[key] = self._stack(ctx, self.cc_scale_transforms[0], lat_s)
+                else:
+                    pre[key] = fam[key[0]][key[1]][0].emit_partial(ctx, src, 0, 320)
+                pre_ev[key] = prog.record()
+
+        def stack_split(name, i, buf, n_extra, final=None):
+            """Context transform whose first conv only sees the `n_extra` support channels of `buf`."""
+            prog.wait(pre_ev[(name, i)])
+            seq = fam[name][i]
+            t = seq[0].emit_partial(ctx, buf.channels(320, n_extra), 1, 320, res=pre[(name, i)], gelu=True)
+            return self._stack(ctx, seq, t, final=final, skip_first=True)
 
         def slice_ops(i, scale_lane):
             """One slice (cnn.py:165-184) on the current lane, its cc_scale stack on `scale_lane`."""
-            k = min(i, self.max_support_slices)
-            cin = 320 + 32 * k
-            prog.fork(scale_lane)  # cc_mean || cc_scale (cnn.py:167-173 are independent given the support)
-            with prog.side(scale_lane):
-                sc = self._stack(ctx, self.cc_scale_transforms[i], scales.channels(0, cin))
-            mu = self._stack(ctx, self.cc_mean_transforms[i], means.channels(0, cin))
-            prog.join(scale_lane)
+            k = min(i, S)
+            if i == 0:
+                prog.wait(pre_ev["mu0"])
+                prog.wait(pre_ev["sc0"])
+                mu, sc = pre["mu0"], pre["sc0"]
+            else:
+                prog.fork(scale_lane)  # cc_mean || cc_scale (cnn.py:167-173 are independent given the support)
+                with prog.side(scale_lane):
+                    sc = stack_split("cc_scale", i, scales, 32 * k)
+                mu = stack_split("cc_mean", i, means, 32 * k)
+                prog.join(scale_lane)
             yh_i = y_hat.channels(32 * i, 32)
-            if i < self.max_support_slices:
-                lrp_in = means.channels(0, cin + 32)
+            if i < S:
+                lrp_buf = means
                 slot = means.channels(320 + 32 * i, 32)
                 extra = dict(out2=slot, out3=scales.channels(320 + 32 * i, 32))  # becomes support of later slices
             else:
                 # slices >= max_support share one support set, so they are independent of each other: each
                 # gets a private copy of the support + its own y_hat slot and may run concurrently
                 lrp_buf = ctx.buf(B, h, w, 512)
-                prog.copy(means.channels(0, 480), lrp_buf.channels(0, 480))
-                lrp_in, slot, extra = lrp_buf, lrp_buf.channels(480, 32), {}
+                prog.copy(means.channels(320, 160), lrp_buf.channels(320, 160))
+                slot, extra = lrp_buf.channels(480, 32), {}
             self.gaussian_conditional.emit(ctx, y.channels(32 * i, 32), sc, mu, p.lik_y, 32 * i, 320,
                                            y_hat_dsts=[yh_i, slot], symbols=p.symbols, indexes=p.indexes)
-            self._stack(ctx, self.lrp_transforms[i], lrp_in, final=dict(
-                epilogue=_lib.EPI_LRP, res=yh_i, out=yh_i, **extra))
+            stack_split("lrp", i, lrp_buf, 32 * (k + 1), final=dict(epilogue=_lib.EPI_LRP, res=yh_i, out=yh_i, **extra))
 
-        for i in range(self.max_support_slices):  # serial chain: slice i+1 needs the refined slice i
+        for i in range(S):  # serial chain: slice i+1 needs the refined slice i
             slice_ops(i, 1)
-        tail = list(range(self.max_support_slices, self.num_slices))
+        tail = list(range(S, self.num_slices))
         for n, i in enumerate(tail):  # independent slices: one lane pair each
             main_lane, scale_lane = 2 + 2 * n, 3 + 2 * n
             if main_lane + 1 >= _lib.MAX_LANES:
@@ -212,10 +251,10 @@ class WACNN(CompressionModel):
         return p
 
     @staticmethod
-    def _stack(ctx, seq, x, final=None):
+    def _stack(ctx, seq, x, final=None, skip_first=False):
         mods = list(seq)
         t = x
-        for j in (0, 2, 4, 6):
+        for j in (2, 4, 6) if skip_first else (0, 2, 4, 6):
             t = mods[j].emit(ctx, t, gelu=True)
         if final is None:
             return mods[8].emit(ctx, t, out_dtype=torch.float32)  # mu / scale stay fp32

@@ -72,6 +72,7 @@ class Program:
         self._graph = None
         self._graph_stream = None
         self._lane = 0
+        self._n_events = 0
 
     # ------------------------------------------------------------- lanes
     def _append(self, op):
@@ -88,6 +89,23 @@ class Program:
         op.lane = waiter
         self.ops.append(op)
         self._arr = None
+
+    def record(self):
+        """Mark the current position of the current lane; returns an event id for `wait`."""
+        assert self._n_events < _lib.MAX_EVENTS
+        op = Op()
+        op.kind = _lib.OP_RECORD
+        op.u.sync.event = self._n_events
+        self._n_events += 1
+        self._append(op)
+        return op.u.sync.event
+
+    def wait(self, event):
+        """The current lane waits for the position marked by `record()`."""
+        op = Op()
+        op.kind = _lib.OP_WAIT
+        op.u.sync.event = event
+        self._append(op)
 
     def fork(self, lane=1, src=None):
         """Start a concurrent branch on `lane` (it first waits for the current lane, or `src`)."""
@@ -112,7 +130,7 @@ class Program:
 
     @property
     def num_kernels(self):
-        return sum(1 for op in self.ops if op.kind not in (_lib.OP_FORK, _lib.OP_JOIN))
+        return sum(1 for op in self.ops if op.kind not in _lib.SYNC_OPS)
 
     # ------------------------------------------------------------- builders
     def conv(self, x: TV, weight, bias, Cout, KH, KW, stride, pad_h, pad_w, out: TV, epilogue=_lib.EPI_NONE,

@@ -188,7 +188,7 @@ class Sim:
         disp = {_lib.OP_CONV: ("conv", self.conv), _lib.OP_ATTN: ("attn", self.attn), _lib.OP_EB: ("eb", self.eb),
                 _lib.OP_GC: ("gc", self.gc), _lib.OP_COPY: ("copy", self.copy), _lib.OP_LN: ("ln", self.ln), _lib.OP_PATCH: ("patch", self.patch)}
         for op in self.prog.ops:
-            if op.kind in (_lib.OP_FORK, _lib.OP_JOIN):
+            if op.kind in _lib.SYNC_OPS:
                 continue  # lanes are a scheduling hint: program order is always a valid execution
             name, fn = disp[op.kind]
             fn(getattr(op.u, name))

@@ -1,5 +1,7 @@
 // C-ABI entry points: dtype dispatch, the program executor and its CUDA-graph form.
 // (The per-op entry points of entropy.cu / layout.cu are defined next to their kernels.)
+#include <stdlib.h>
+
 #include <new>
 #include <vector>
 
@@ -8,6 +10,7 @@
 int rdsic_conv_forward_f32(const rdsic_conv_desc* d, cudaStream_t stream);
 int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream);
 int rdsic_attn_forward_f32(const rdsic_attn_desc* d, cudaStream_t stream);
+int rdsic_attn_forward_tc(const rdsic_attn_desc* d, cudaStream_t stream);
 
 extern "C" {
 
@@ -45,6 +48,15 @@ int rdsic_conv_forward(const rdsic_conv_desc* d, rdsic_stream_t stream) {
 }
 
 int rdsic_attn_forward(const rdsic_attn_desc* d, rdsic_stream_t stream) {
+  if (!d) return RDSIC_E_ARG;
+  // bf16 activations: tensor-core kernel for the reference's two configurations; everything else (and the
+  // fp32 mode) runs the register-resident fp32 kernel.  Both are CUDA kernels of this library.
+  static const bool use_tc = !(getenv("RDSIC_ATTN_TC") && atoi(getenv("RDSIC_ATTN_TC")) == 0);
+  if (use_tc && d->qkv.dtype == RDSIC_BF16 && d->qkv.ptr && d->out.ptr && d->bias_table && d->ws > 0 &&
+      d->H % d->ws == 0 && d->W % d->ws == 0 && d->shift >= 0 && d->shift < d->ws && !d->qkv.nchw && !d->out.nchw) {
+    const int rc = rdsic_attn_forward_tc(d, (cudaStream_t)stream);
+    if (rc != RDSIC_E_UNSUPPORTED) return rc;
+  }
   return rdsic_attn_forward_f32(d, (cudaStream_t)stream);
 }
 

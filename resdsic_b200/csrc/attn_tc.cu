@@ -1,0 +1,228 @@
+// Fused shifted-window attention on tensor cores (bf16 operands, fp32 accumulate / softmax).
+//
+// Same contract as attn_f32.cu (reference layers/win_attention.py:94-112,159-200): roll, window partition /
+// reverse are addressing; (q*scale) k^T + relative-position bias + shift mask (-100), softmax, @ v.
+//
+// One CTA = one window, one warp = one head.  The window's q|k|v rows are staged once in shared memory with
+// 128-bit coalesced loads (each token's 3C channels are contiguous in the qkv GEMM output).  Per 16-row
+// block of queries:  S = Q K^T with mma.sync m16n8k16 (+ one m16n8k8 for the d mod 16 = 8 tail: d = 24 / 40),
+// softmax on the accumulator fragments (quad shuffles), then the probabilities are re-used *in registers*
+// as the A operand of P V (the accumulator layout of two n8 tiles is exactly one k16 A fragment);
+// V fragments come from ldmatrix.trans on the row-major V rows.  The output overwrites the head's Q columns
+// in shared memory and the CTA writes the window back with coalesced 128-bit stores.
+//
+// (These GEMMs are 64x64x24: far too small for a 128-row tcgen05 tile -- QK^T + PV are 0.6 % of the model's
+// FLOPs -- so the warp-level MMA is the right tool here; the 128-row GEMMs all run on tcgen05, conv_bf16.cu.)
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void mma_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_1688(float* c, uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(b0));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, const void* smem_row) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x1_trans(uint32_t& r0, const void* smem_row) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x1.trans.shared.b16 {%0}, [%1];" : "=r"(r0) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// WS: window side (8 or 4); DH: head dim (multiple of 8); 8 heads = 8 warps.
+template <int WS, int DH>
+__global__ void __launch_bounds__(256) win_attn_tc_kernel(const rdsic_attn_desc d) {
+  constexpr int NTOK = WS * WS, HEADS = 8, C = HEADS * DH, LD = 3 * C + 8;  // +8 bf16: conflict-free fragment loads
+  constexpr int RB = NTOK / 16;      // 16-row query blocks
+  constexpr int NT_S = NTOK / 8;     // n8 tiles of S (keys)
+  constexpr int KS_PV = NTOK / 16;   // k16 steps of P V
+  constexpr int NT_O = DH / 8;       // n8 tiles of the output
+  constexpr int K16 = DH / 16, KTAIL = DH % 16;  // QK^T: K16 k16-steps + (KTAIL == 8) one k8 step
+  constexpr int TWD = 2 * WS - 1;
+  static_assert(KTAIL == 0 || KTAIL == 8, "head dim must be a multiple of 8");
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __nv_bfloat16* qkv = (__nv_bfloat16*)smem_raw;              // [NTOK][LD]: q | k | v per token
+  float* tab = (float*)(qkv + NTOK * LD);                     // [HEADS][TWD*TWD]
+  int* rid = (int*)(tab + HEADS * TWD * TWD);                 // [NTOK] shift-mask region id
+  size_t* pixs = (size_t*)(rid + NTOK);                       // [NTOK] pixel index of each token (original frame)
+
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  int win = blockIdx.x;
+  const int nWw = d.W / WS, nWh = d.H / WS;
+  const int ww = win % nWw;
+  win /= nWw;
+  const int wh = win % nWh, b = win / nWh;
+
+  if (tid < NTOK) {
+    const int hy = wh * WS + tid / WS, wx = ww * WS + tid % WS;  // shifted-frame position of token tid
+    const int oy = (hy + d.shift) % d.H, ox = (wx + d.shift) % d.W;
+    pixs[tid] = ((size_t)b * d.H + oy) * d.W + ox;
+    const int rh = (hy >= d.H - WS) + (hy >= d.H - d.shift), rw = (wx >= d.W - WS) + (wx >= d.W - d.shift);
+    rid[tid] = d.shift > 0 ? 3 * rh + rw : 0;
+  }
+  for (int e = tid; e < HEADS * TWD * TWD; e += 256) tab[e] = d.bias_table[(e % (TWD * TWD)) * HEADS + e / (TWD * TWD)];
+  __syncthreads();
+  {
+    constexpr int VPT = 3 * C / 8;  // 16-byte vectors per token
+    const __nv_bfloat16* src = (const __nv_bfloat16*)d.qkv.ptr;
+    for (int e = tid; e < NTOK * VPT; e += 256) {
+      const int tok = e / VPT, v = e % VPT;
+      const uint4 val = *reinterpret_cast<const uint4*>(src + pixs[tok] * (size_t)d.qkv.ld + d.qkv.coff + v * 8);
+      *reinterpret_cast<uint4*>(qkv + tok * LD + v * 8) = val;
+    }
+  }
+  __syncthreads();
+
+  const int head = warp;
+  const int g = lane / 4, t = lane % 4;
+  const __nv_bfloat16* Q = qkv + head * DH;
+  const __nv_bfloat16* K = qkv + C + head * DH;
+  const __nv_bfloat16* V = qkv + 2 * C + head * DH;
+  const float* tb = tab + head * TWD * TWD;
+
+#pragma unroll 1
+  for (int rb = 0; rb < RB; ++rb) {
+    const int i0 = rb * 16 + g, i1 = i0 + 8;
+    // ---- S = Q K^T
+    float s[NT_S][4];
+#pragma unroll
+    for (int nt = 0; nt < NT_S; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < K16; ++ks) {
+      uint32_t a[4];
+      a[0] = *reinterpret_cast<const uint32_t*>(Q + i0 * LD + ks * 16 + 2 * t);
+      a[1] = *reinterpret_cast<const uint32_t*>(Q + i1 * LD + ks * 16 + 2 * t);
+      a[2] = *reinterpret_cast<const uint32_t*>(Q + i0 * LD + ks * 16 + 8 + 2 * t);
+      a[3] = *reinterpret_cast<const uint32_t*>(Q + i1 * LD + ks * 16 + 8 + 2 * t);
+#pragma unroll
+      for (int nt = 0; nt < NT_S; ++nt) {
+        const __nv_bfloat16* kr = K + (nt * 8 + g) * LD + ks * 16 + 2 * t;
+        mma_16816(s[nt], a, *reinterpret_cast<const uint32_t*>(kr), *reinterpret_cast<const uint32_t*>(kr + 8));
+      }
+    }
+    if (KTAIL == 8) {
+      const uint32_t a0 = *reinterpret_cast<const uint32_t*>(Q + i0 * LD + K16 * 16 + 2 * t);
+      const uint32_t a1 = *reinterpret_cast<const uint32_t*>(Q + i1 * LD + K16 * 16 + 2 * t);
+#pragma unroll
+      for (int nt = 0; nt < NT_S; ++nt)
+        mma_1688(s[nt], a0, a1, *reinterpret_cast<const uint32_t*>(K + (nt * 8 + g) * LD + K16 * 16 + 2 * t));
+    }
+    // ---- scale, relative-position bias, shift mask, softmax (rows i0 and i1; a row lives in one quad)
+    const int hi0 = i0 / WS, wi0 = i0 % WS, hi1 = i1 / WS, wi1 = i1 % WS;
+    const int r0 = rid[i0], r1 = rid[i1];
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT_S; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = nt * 8 + 2 * t + e;
+        const int hj = j / WS, wj = j % WS, rj = rid[j];
+        float v0 = s[nt][e] * d.scale + tb[(hi0 - hj + WS - 1) * TWD + (wi0 - wj + WS - 1)];
+        float v1 = s[nt][2 + e] * d.scale + tb[(hi1 - hj + WS - 1) * TWD + (wi1 - wj + WS - 1)];
+        if (rj != r0) v0 += -100.0f;
+        if (rj != r1) v1 += -100.0f;
+        s[nt][e] = v0;
+        s[nt][2 + e] = v1;
+        m0 = fmaxf(m0, v0);
+        m1 = fmaxf(m1, v1);
+      }
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT_S; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        s[nt][e] = __expf(s[nt][e] - m0);
+        s[nt][2 + e] = __expf(s[nt][2 + e] - m1);
+        l0 += s[nt][e];
+        l1 += s[nt][2 + e];
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+    // ---- O = P V  (P stays in registers: two S n8-tiles form one k16 A fragment)
+    float o[NT_O][4];
+#pragma unroll
+    for (int nt = 0; nt < NT_O; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < KS_PV; ++kk) {
+      uint32_t a[4];
+      a[0] = pack_bf16(s[2 * kk][0] * inv0, s[2 * kk][1] * inv0);
+      a[1] = pack_bf16(s[2 * kk][2] * inv1, s[2 * kk][3] * inv1);
+      a[2] = pack_bf16(s[2 * kk + 1][0] * inv0, s[2 * kk + 1][1] * inv0);
+      a[3] = pack_bf16(s[2 * kk + 1][2] * inv1, s[2 * kk + 1][3] * inv1);
+#pragma unroll
+      for (int nt = 0; nt < NT_O; ++nt) {
+        uint32_t b0, b1;  // B[k = token][n = channel] from row-major V: transposed 8x8 loads
+        ldmatrix_x2_trans(b0, b1, V + (kk * 16 + (lane & 15)) * LD + nt * 8);
+        mma_16816(o[nt], a, b0, b1);
+      }
+    }
+    // ---- the block's output replaces its (already consumed) Q rows of this head
+    __syncwarp();
+#pragma unroll
+    for (int nt = 0; nt < NT_O; ++nt) {
+      *reinterpret_cast<uint32_t*>(qkv + i0 * LD + head * DH + nt * 8 + 2 * t) = pack_bf16(o[nt][0], o[nt][1]);
+      *reinterpret_cast<uint32_t*>(qkv + i1 * LD + head * DH + nt * 8 + 2 * t) = pack_bf16(o[nt][2], o[nt][3]);
+    }
+  }
+  __syncthreads();
+  {
+    constexpr int VPT = C / 8;
+    __nv_bfloat16* dst = (__nv_bfloat16*)d.out.ptr;
+    for (int e = tid; e < NTOK * VPT; e += 256) {
+      const int tok = e / VPT, v = e % VPT;
+      *reinterpret_cast<uint4*>(dst + pixs[tok] * (size_t)d.out.ld + d.out.coff + v * 8) =
+          *reinterpret_cast<const uint4*>(qkv + tok * LD + v * 8);
+    }
+  }
+}
+
+template <int WS, int DH>
+int launch_tc(const rdsic_attn_desc* d, cudaStream_t stream) {
+  constexpr int NTOK = WS * WS, C = 8 * DH, LD = 3 * C + 8, TWD = 2 * WS - 1;
+  const size_t smem = (size_t)NTOK * LD * 2 + 8 * TWD * TWD * 4 + NTOK * 4 + NTOK * 8 + 16;
+  auto kern = win_attn_tc_kernel<WS, DH>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const int nblk = d->B * (d->H / WS) * (d->W / WS);
+  kern<<<nblk, 256, smem, stream>>>(*d);
+  return rdsic_launch_status();
+}
+
+}  // namespace
+
+// returns RDSIC_E_UNSUPPORTED when the configuration has no tensor-core specialisation (caller then uses
+// the register-resident fp32 kernel of attn_f32.cu)
+int rdsic_attn_forward_tc(const rdsic_attn_desc* d, cudaStream_t stream) {
+  if (d->qkv.dtype != RDSIC_BF16 || d->out.dtype != RDSIC_BF16 || d->heads != 8) return RDSIC_E_UNSUPPORTED;
+  if (d->qkv.ld % 8 || d->qkv.coff % 8 || d->out.ld % 8 || d->out.coff % 8 || ((uintptr_t)d->qkv.ptr % 16) ||
+      ((uintptr_t)d->out.ptr % 16))
+    return RDSIC_E_UNSUPPORTED;
+  const int dh = d->C / d->heads;
+  if (d->ws == 8 && dh == 24) return launch_tc<8, 24>(d, stream);
+  if (d->ws == 4 && dh == 40) return launch_tc<4, 40>(d, stream);
+  return RDSIC_E_UNSUPPORTED;
+}

@@ -171,3 +171,39 @@ def test_layers_bf16_vs_reference_golden(model, gold, name, mod, key):
     ref = gold[name]
     err = np.abs(out - ref)
     assert err.max() <= 0.05 * np.abs(ref).max() and err.mean() <= 0.01 * np.abs(ref).max(), (err.max(), err.mean())
+
+
+@pytest.mark.parametrize("C,ws,shift,B,H,W", [(192, 8, 4, 2, 16, 24), (320, 4, 2, 3, 8, 12), (192, 8, 0, 1, 8, 8)])
+def test_attention_core_bf16_vs_torch(C, ws, shift, B, H, W):
+    """The tensor-core window-attention kernel alone (no qkv/proj GEMM) against a torch fp32 evaluation of
+    the same bf16 qkv: roll / partition / bias / mask(-100) / softmax / PV / reverse, incl. shift = 0."""
+    from resdsic_b200.program import TV, Program
+    heads, dh = 8, C // 8
+    qkv = weights.hash_symmetric(f"att.qkv{C}{ws}{shift}", (B, H, W, 3 * C), 2.0).bfloat16()
+    table = weights.hash_symmetric(f"att.tab{ws}", ((2 * ws - 1) ** 2, heads), 1.0)
+    scale = dh ** -0.5
+    # torch reference on the shifted / partitioned tokens
+    q = qkv.float()
+    hs, wsf = (torch.arange(H) + shift) % H, (torch.arange(W) + shift) % W
+    sh = q[:, hs][:, :, wsf]
+    nWh, nWw, N = H // ws, W // ws, ws * ws
+    win = sh.reshape(B, nWh, ws, nWw, ws, 3 * C).permute(0, 1, 3, 2, 4, 5).reshape(B * nWh * nWw, N, 3, heads, dh)
+    qq, kk, vv = (win[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    att = (qq * scale) @ kk.transpose(-1, -2)
+    idx = weights.relative_position_index(ws).reshape(-1)
+    att = att + table[idx].reshape(N, N, heads).permute(2, 0, 1)[None]
+    if shift:
+        rid = O.shift_region_id(H, W, ws, shift).reshape(nWh, ws, nWw, ws).permute(0, 2, 1, 3).reshape(nWh * nWw, N)
+        mask = torch.where(rid[:, None, :] != rid[:, :, None], -100.0, 0.0)
+        att = (att.reshape(B, nWh * nWw, heads, N, N) + mask[None, :, None]).reshape(-1, heads, N, N)
+    o = (torch.softmax(att, -1) @ vv).transpose(1, 2).reshape(B, nWh, nWw, ws, ws, C).permute(0, 1, 3, 2, 4, 5)
+    ref = torch.empty(B, H, W, C)
+    ref[:, hs[:, None], wsf[None, :]] = o.reshape(B, H, W, C)
+    # kernel
+    prog = Program(torch.device(DEV))
+    tq = TV(qkv.to(DEV).reshape(-1), B, H, W, 3 * C)
+    to = TV(torch.zeros(B * H * W * C, dtype=torch.bfloat16, device=DEV), B, H, W, C)
+    prog.attn(tq, to, table.to(DEV), heads, ws, shift, scale)
+    prog.run()
+    got = to.t.float().cpu().reshape(B, H, W, C)
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=2e-2, atol=2e-2)

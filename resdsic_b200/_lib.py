@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libresdsic_b200.so")
+# RDSIC_LIB_PATH: developer knob to A/B-test an alternative build of the same library (kernel tuning)
+LIB_PATH = os.environ.get("RDSIC_LIB_PATH") or os.path.join(_PKG, "lib", "libresdsic_b200.so")
 
 F32, BF16 = 0, 1
 EPI_NONE, EPI_GELU, EPI_RES_GELU, EPI_ADD_RES, EPI_GATE, EPI_GDN, EPI_IGDN, EPI_LRP = range(8)

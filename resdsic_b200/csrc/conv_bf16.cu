@@ -28,7 +28,8 @@ namespace {
 constexpr int BM = 128;        // UMMA M (cta_group::1)
 constexpr int BK = 64;         // bf16 elements per 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 12;                  // four warps per TMEM lane quarter (latency hiding by TLP)
+constexpr int EPI_PARTS = NUM_EPI_WARPS / 4;       // column interleave factor between the warps of a quarter
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // TMA warp + MMA warp + epilogue warps
 constexpr int MAX_STAGES = 8;
 constexpr uint32_t SPIN_LIMIT = 1u << 22;  // a lost mbarrier signal traps instead of hanging the GPU
@@ -339,12 +340,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     __syncwarp();
   } else {
-    // ================= epilogue (warps 2..9): two warps per TMEM lane quarter, interleaved column chunks
+    // ================= epilogue (warps 2..): EPI_PARTS warps per TMEM lane quarter, interleaved column chunks
     constexpr bool NEED_RES = EPI == RDSIC_EPI_RES_GELU || EPI == RDSIC_EPI_ADD_RES || EPI == RDSIC_EPI_GATE ||
                               EPI == RDSIC_EPI_GDN || EPI == RDSIC_EPI_IGDN || EPI == RDSIC_EPI_LRP;
     constexpr bool NEED_AUX = EPI == RDSIC_EPI_GATE;
     const int q = warp % 4;              // TMEM lane quarter this warp may access
-    const int half = (warp - 2) / 4;     // which of the two warps sharing the quarter
+    const int half = (warp - 2) / 4;     // which of the EPI_PARTS warps sharing the quarter
     const int ml = q * 32 + lane;
     const int dy = ml / g.TW, dx = ml % g.TW;
     const int nchunks = g.BN / 16;
@@ -364,16 +365,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (PLAIN) {
         // Residual / gate operands are prefetched in groups of G chunks BEFORE the accumulator is awaited,
         // so their HBM latency overlaps this tile's main loop instead of serialising per chunk.
-        constexpr int G = NEED_AUX ? 2 : 6;  // register budget: G x (res [+ aux]) 32-byte packs in flight
+        constexpr int G = NEED_AUX ? 2 : 4;  // register budget: G x (res [+ aux]) 32-byte packs in flight
         const bool res16 = NEED_RES && d.res.dtype == RDSIC_BF16, aux16 = NEED_AUX && d.aux.dtype == RDSIC_BF16;
         const __nv_bfloat16* resp = (const __nv_bfloat16*)d.res.ptr + pix * (size_t)d.res.ld + d.res.coff + n0;
         const __nv_bfloat16* auxp = (const __nv_bfloat16*)d.aux.ptr + pix * (size_t)d.aux.ld + d.aux.coff + n0;
         Pack8 rr[G], ra[G];
         bool waited = false;
-        for (int j0 = half; j0 < nchunks; j0 += 2 * G) {
+        for (int j0 = half; j0 < nchunks; j0 += EPI_PARTS * G) {
 #pragma unroll
           for (int gI = 0; gI < G; ++gI) {
-            const int j = j0 + 2 * gI;
+            const int j = j0 + EPI_PARTS * gI;
             if (j < nchunks && row_ok && n0 + j * 16 < d.Cout) {
               if (res16) rr[gI] = ldg256(resp + j * 16);
               if (aux16) ra[gI] = ldg256(auxp + j * 16);
@@ -388,7 +389,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           // independent 16-element epilogues interleave (the epilogue is latency-, not issue-bound)
 #pragma unroll
           for (int gI = 0; gI < G; gI += 2) {
-            const int ja = j0 + 2 * gI, jb = ja + 2;
+            const int ja = j0 + EPI_PARTS * gI, jb = ja + EPI_PARTS;
             if (ja >= nchunks) break;
             const bool has_b = (gI + 1 < G) && jb < nchunks;
             uint32_t ua[16], ub[16];
@@ -438,7 +439,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       } else {
         mbar_wait(&acc_full[buf], aph);
         tcgen05_fence_after();
-        for (int j = half; j < nchunks; j += 2) {
+        for (int j = half; j < nchunks; j += EPI_PARTS) {
           float v[16];
           tmem_ld16(trow + (uint32_t)(j * 16), v);
           const int nb = n0 + j * 16;

@@ -2,6 +2,7 @@
 import torch
 import torch.nn.functional as F
 
+from .pipeline import ForwardPipeline  # noqa: F401
 from .sharding import gather_to_rank0, max_over_ranks, shard_range  # noqa: F401
 
 

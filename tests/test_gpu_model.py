@@ -98,3 +98,22 @@ def test_bf16_forward_vs_reference_golden(model, case):
     assert dx.max() <= 0.15 and dx.mean() <= 0.02
     assert flips <= 0.15
     assert abs(b_got - b_ref) <= 1e-2 * b_ref
+
+
+def test_forward_pipeline_matches_direct_calls(model):
+    """Host-to-host pipelined inference returns, for every batch, exactly what model(x) returns."""
+    from resdsic_b200.utils import ForwardPipeline
+    model.set_precision("fp32")
+    batches = [weights.make_image(2, 64, 128, seed=20 + i).pin_memory() for i in range(5)]
+    want = []
+    for hb in batches:
+        o = model(hb.to(DEV))
+        want.append((o["x_hat"].cpu().clone(), o["likelihoods"]["y"].cpu().clone(), o["likelihoods"]["z"].cpu().clone()))
+    got = {}
+    pipe = ForwardPipeline(model, batches[0], depth=2)
+    n = pipe.run(batches, on_result=lambda i, xh, ly, lz: got.__setitem__(i, (xh.clone(), ly.clone(), lz.clone())))
+    assert n == 5 and sorted(got) == list(range(5))
+    for i in range(5):
+        for a, b in zip(got[i], want[i]):
+            assert torch.equal(a, b), i
+    assert pipe.h2d_bytes == 2 * 3 * 64 * 128 * 4

@@ -118,6 +118,26 @@ def install():
     _exec("compressai.layers", f"{REF_SRC}/compress/layers/gdn.py")
 
 
+def reference_tcm_module():
+    """Import the reference's (unregistered) `compress/models/TCM/tcm.py` -- the in-tree statement of the
+    Swin LayerNorm + W/SW-MSA + MLP block (tcm.py:139-236).  Its remaining pip-compressai imports are only
+    needed by the TCM *model* classes, so they are satisfied with inert placeholders."""
+    install()
+    layers = sys.modules["compressai.layers"]
+    for name in ("AttentionBlock", "ResidualBlock", "ResidualBlockUpsample", "ResidualBlockWithStride"):
+        if not hasattr(layers, name):
+            setattr(layers, name, _Inert)
+    from compress.layers.layers import conv3x3, subpel_conv3x3
+    layers.conv3x3, layers.subpel_conv3x3 = conv3x3, subpel_conv3x3
+    if "compressai.models" not in sys.modules:
+        m = _new("compressai.models")
+        m.CompressionModel = nn.Module
+    tl = sys.modules["timm.models.layers"]
+    tl.DropPath = _Identity
+    import importlib
+    return importlib.import_module("compress.models.TCM.tcm")
+
+
 def reference_wacnn(N=192, M=320):
     """Instantiate the reference's own `WACNN` (cnn.py:23)."""
     install()

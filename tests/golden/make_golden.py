@@ -128,6 +128,44 @@ def run_reference_ops(net, table):
     return {k: v.numpy() for k, v in o.items()}
 
 
+SWIN_CASES = {  # name: (dim, head_dim, window, type, B, H, W)
+    "swin_w8_sw": (192, 24, 8, "SW", 1, 16, 24),
+    "swin_w4_w": (128, 32, 4, "W", 2, 8, 12),
+    "swin_w4_sw": (128, 32, 4, "SW", 2, 8, 12),
+}
+
+
+def swin_state_dict(name, dim, head_dim, ws):
+    """Hash-seeded parameters with the key names of the reference's tcm.Block."""
+    hs = weights.hash_symmetric
+    heads = dim // head_dim
+    sd = {}
+    for ln in ("ln1", "ln2"):
+        sd[f"{ln}.weight"] = 1.0 + hs(f"{name}.{ln}.w", (dim,), 0.3)
+        sd[f"{ln}.bias"] = hs(f"{name}.{ln}.b", (dim,), 0.2)
+    sd["msa.relative_position_params"] = hs(f"{name}.rpp", (heads, 2 * ws - 1, 2 * ws - 1), 0.5)
+    for lin, (o, i) in (("msa.embedding_layer", (3 * dim, dim)), ("msa.linear", (dim, dim)),
+                        ("mlp.0", (4 * dim, dim)), ("mlp.2", (dim, 4 * dim))):
+        sd[f"{lin}.weight"] = hs(f"{name}.{lin}.w", (o, i), (3.0 / i) ** 0.5)
+        sd[f"{lin}.bias"] = hs(f"{name}.{lin}.b", (o,), 0.1)
+    return sd
+
+
+@torch.no_grad()
+def run_reference_swin():
+    """Outputs of the reference's own `Block` (models/TCM/tcm.py:214-236), NHWC in / NHWC out."""
+    tcm = ref_shim.reference_tcm_module()
+    out = {}
+    for name, (dim, hd, ws, typ, B, H, W) in SWIN_CASES.items():
+        blk = tcm.Block(dim, dim, hd, ws, 0.0, typ).eval()
+        sd = swin_state_dict(name, dim, hd, ws)
+        assert set(sd) == set(blk.state_dict()), (sorted(sd), sorted(blk.state_dict()))
+        blk.load_state_dict(sd, strict=True)
+        x = weights.hash_symmetric(f"{name}.x", (B, H, W, dim), 1.5)
+        out[name] = blk(x).numpy()
+    return out
+
+
 def main():
     torch.set_num_threads(8)
     sd = weights.make_state_dict(seed=0)
@@ -156,6 +194,7 @@ def main():
               "sym range", res["symbols"].min(), res["symbols"].max(),
               "idx range", res["indexes"].min(), res["indexes"].max(), os.path.getsize(path))
     ops = run_reference_ops(net, table)
+    ops.update(run_reference_swin())
     path = os.path.join(HERE, "ops.npz")
     np.savez_compressed(path, **ops)
     print("ops", {k: v.shape for k, v in ops.items()}, os.path.getsize(path))

@@ -207,3 +207,18 @@ def test_attention_core_bf16_vs_torch(C, ws, shift, B, H, W):
     prog.run()
     got = to.t.float().cpu().reshape(B, H, W, C)
     np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 3e-4), ("bf16", 6e-2)])
+def test_swin_block_vs_reference_tcm_golden(gold, precision, tol):
+    """A14 (stf Swin block: LayerNorm kernel + GEMMs + fused window attention) vs the reference's tcm.Block."""
+    from resdsic_b200.layers import SwinBlock
+    from tests.golden.make_golden import SWIN_CASES, swin_state_dict
+    for name, (dim, hd, ws, typ, B, H, W) in SWIN_CASES.items():
+        blk = SwinBlock(dim, dim, hd, ws, 0.0, typ).eval()
+        blk.load_state_dict(swin_state_dict(name, dim, hd, ws), strict=True)
+        blk = blk.to(DEV).set_precision(precision)
+        x = weights.hash_symmetric(f"{name}.x", (B, H, W, dim), 1.5)
+        out = blk.forward_nhwc(x.to(DEV)).cpu().numpy()
+        err = np.abs(out - gold[name])
+        assert err.max() <= tol * max(1.0, np.abs(gold[name]).max()), (name, precision, err.max())

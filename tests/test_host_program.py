@@ -78,3 +78,21 @@ def test_layer_programs_reproduce_reference(model):
     np.testing.assert_allclose(run(model.g_s[3], i["deconv_x"]), g["deconv"], rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(run(model.g_a[4], i["block8_x"]), g["block8"], rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(run(model.g_a[4].conv_a[0], i["block8_x"]), g["ru"], rtol=1e-5, atol=1e-5)
+
+
+def test_swin_block_program_reproduces_reference():
+    """A14 (stf): the B200 Swin block's program (LN, qkv, window attention, proj+res, LN, MLP) interpreted on
+    CPU vs the reference's tcm.Block goldens; its state_dict keys are the reference's."""
+    from resdsic_b200.layers import SwinBlock
+    from tests.golden.make_golden import SWIN_CASES, swin_state_dict
+    g = np.load(os.path.join(GOLDEN, "ops.npz"))
+    for name, (dim, hd, ws, typ, B, H, W) in SWIN_CASES.items():
+        blk = SwinBlock(dim, dim, hd, ws, 0.0, typ).eval()
+        res = blk.load_state_dict(swin_state_dict(name, dim, hd, ws), strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+        x = weights.hash_symmetric(f"{name}.x", (B, H, W, dim), 1.5)
+        ctx = Ctx("cpu", "fp32", build_only=True)
+        out = ctx.to_nchw(blk.emit(ctx, ctx.from_nchw(x.permute(0, 3, 1, 2).contiguous())))
+        run_on_cpu(ctx.prog)
+        assert ctx.prog.num_launches == 9  # 2 layout copies + 7 kernels
+        np.testing.assert_allclose(out.permute(0, 2, 3, 1).numpy(), g[name], rtol=1e-4, atol=1e-4, err_msg=name)

@@ -92,3 +92,14 @@ def test_padding_rule():
     xp, (left, top) = O.pad_to_multiple(x)
     assert xp.shape[-2:] == (1408, 2048) and (left, top) == (0, 21)
     assert xp[0, 0, 20].sum() == 0 and xp[0, 0, 21].sum() == 2048 and xp[0, 0, -22:].sum() == 0
+
+
+def test_swin_block_oracle_matches_reference_tcm_block():
+    """A14: the LN + W/SW-MSA + MLP block restatement vs the reference's own tcm.Block outputs."""
+    from tests.golden.make_golden import SWIN_CASES, swin_state_dict
+    g = _npz("ops.npz")
+    for name, (dim, hd, ws, typ, B, H, W) in SWIN_CASES.items():
+        sd = {f"blk.{k}": v for k, v in swin_state_dict(name, dim, hd, ws).items()}
+        x = weights.hash_symmetric(f"{name}.x", (B, H, W, dim), 1.5)
+        out = O.swin_block(x, sd, "blk", hd, ws, typ == "SW")
+        np.testing.assert_allclose(out.numpy(), g[name], rtol=1e-5, atol=1e-5, err_msg=name)

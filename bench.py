@@ -210,7 +210,7 @@ def run_ours(args):
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": f"cnn (WACNN N=192 M=320) forward 512x768, batch {B} per GPU, eval mode",
                        "precision": args.precision, "batch_per_gpu": B, "image": [H, W], "parallelism": f"dp{world}",
-                       "l2": "per-step activation working set (>600 MB at batch 8) exceeds the 126 MB L2; no explicit flush",
+                       "l2": f"per-step activation working set (~{0.19 * B:.1f} GB at batch {B}) exceeds the 126 MB L2; no explicit flush",
                        "cuda_graph": bool(model.use_cuda_graph)},
             "megapixels_per_s": ips * H * W / 1e6,
             "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
@@ -291,7 +291,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("RESDSIC_PRECISION", "bf16"), choices=["fp32", "bf16"])
-    ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-ops", default=None, help="write the per-launch device times of one step to this JSON file")
     args = ap.parse_args()

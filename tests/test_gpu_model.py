@@ -117,3 +117,48 @@ def test_forward_pipeline_matches_direct_calls(model):
         for a, b in zip(got[i], want[i]):
             assert torch.equal(a, b), i
     assert pipe.h2d_bytes == 2 * 3 * 64 * 128 * 4
+
+
+def test_config2_batch16_256_bf16_properties(model):
+    """BASELINE config 2: batch 16 x 256 x 256 in bf16 mode -- output contract, finite likelihoods in (0,1],
+    determinism, and per-image independence (image k alone == image k inside the batch, bit for bit)."""
+    model.set_precision("bf16")
+    try:
+        x = weights.make_image(16, 256, 256, seed=2).to(DEV)
+        out = model(x)
+        xh, ly, lz = out["x_hat"].clone(), out["likelihoods"]["y"].clone(), out["likelihoods"]["z"].clone()
+        assert xh.shape == (16, 3, 256, 256) and ly.shape == (16, 320, 16, 16) and lz.shape == (16, 192, 4, 4)
+        assert torch.isfinite(xh).all() and (ly > 0).all() and (ly <= 1).all() and (lz > 0).all() and (lz <= 1).all()
+        again = model(x)
+        assert torch.equal(again["x_hat"], xh) and torch.equal(again["likelihoods"]["y"], ly)
+        solo = model(x[5:6].contiguous())
+        assert torch.equal(solo["x_hat"][0], xh[5]) and torch.equal(solo["likelihoods"]["y"][0], ly[5])
+    finally:
+        model.set_precision("fp32")
+
+
+def test_config5_clic_size_padding_and_index_build(model, synthetic_sd, scale_table):
+    """BASELINE config 5: 1 x 3 x 1365 x 2048 -> caller padding rule (A0) -> 1408 x 2048 forward + the int32
+    symbols / indexes of `compress`; fp32 mode against the CPU oracle on the same padded image (g_a / h_a
+    outputs tight, integer outputs statistically: a flipped symbol perturbs later slices)."""
+    from resdsic_b200.utils import crop, pad_to_multiple
+    model.set_precision("fp32")
+    x = weights.make_image(1, 1365, 2048, seed=4)
+    xp, pad = pad_to_multiple(x, 64)
+    assert xp.shape[-2:] == (1408, 2048) and pad == (0, 0, 21, 22)
+    r = model.symbols_and_indexes(xp.to(DEV))
+    p = next(iter(model._plans.values()))
+    assert r["y_symbols"].shape == (1, 320, 88, 128) and r["y_indexes"].dtype == torch.int32 and r["shape"] == (22, 32)
+    assert int(r["y_indexes"].min()) >= 0 and int(r["y_indexes"].max()) <= 63
+    assert crop(r["x_hat"], pad).shape == (1, 3, 1365, 2048)
+    ref = O.forward(synthetic_sd, xp, scale_table, collect=True)
+    np.testing.assert_allclose(p.y.to_nchw().cpu().numpy(), ref["y"].numpy(), rtol=2e-3, atol=2e-3)
+    np.testing.assert_allclose(p.z.to_nchw().cpu().numpy(), ref["z"].numpy(), rtol=2e-3, atol=2e-3)
+    flips = (r["y_symbols"].cpu() != ref["symbols"]).float().mean().item()
+    idx_flips = (r["y_indexes"].cpu() != ref["indexes"]).float().mean().item()
+    from tests.helpers import bpp_of
+    n = 1408 * 2048
+    b_got = bpp_of(r["likelihoods"]["y"].cpu().numpy(), r["likelihoods"]["z"].cpu().numpy(), n)
+    b_ref = bpp_of(ref["likelihoods"]["y"].numpy(), ref["likelihoods"]["z"].numpy(), n)
+    print("clic fp32: symbol flips", flips, "index flips", idx_flips, "bpp", b_got, "ref", b_ref)
+    assert flips <= 2e-2 and idx_flips <= 2e-2 and abs(b_got - b_ref) <= 1e-3 * b_ref

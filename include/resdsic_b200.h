@@ -90,7 +90,12 @@ typedef struct rdsic_conv_desc {
   rdsic_view out2;        /* optional extra copies of the result (slice-loop support buffers) */
   rdsic_view out3;
   int32_t out2_square;    /* out2 receives result^2 (feeds the next GDN's beta + gamma @ x^2 contraction) */
-  int32_t pad_;
+  /* Fused GDN (bf16 tensor-core path only): with gdn_mode 1 (GDN) / 2 (inverse) the kernel continues
+   * out = x * rsqrt|sqrt(gdn_beta + gdn_gamma @ x^2) on x = conv(in) + bias without x leaving the SM
+   * (layers/gdn.py:62-75 after WACNN/utils.py:116-134).  gdn_gamma: packed bf16 [Cout][Cout], gdn_beta fp32. */
+  int32_t gdn_mode;
+  const void* gdn_gamma;
+  const float* gdn_beta;
 } rdsic_conv_desc;
 
 /* Fused shifted-window attention core: replaces roll + window_partition +

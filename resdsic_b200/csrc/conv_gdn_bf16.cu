@@ -1,0 +1,362 @@
+// Convolution (or transposed-convolution phase) FUSED with the GDN / inverse GDN that follows it
+// (reference cnn.py:32-39,46-52: `conv -> GDN`, `deconv -> GDN(inverse)`; layers/gdn.py:62-75):
+//
+//     x    = conv(in) + bias                         GEMM 1 (implicit GEMM, as conv_bf16.cu)
+//     norm = beta' + gamma' @ x^2                    GEMM 2 (the GDN 1x1 contraction)
+//     out  = x * rsqrt(norm)   |   x * sqrt(norm)    epilogue
+//
+// in ONE kernel: x never goes to HBM.  The 128 x C accumulator of GEMM 1 sits in TMEM; the epilogue warps
+// read it, keep x (bf16) in registers, and write x^2 as packed bf16 straight back into TMEM, from where
+// GEMM 2 consumes it as the A operand (tcgen05.mma with A in tensor memory) against gamma', which stays
+// resident in shared memory for the whole persistent CTA.  Per image this removes the write of x and x^2 and
+// the re-read of both (4 x M x C x 2 bytes) that the unfused pair costs; at H/2 resolution that is 1.2 GB per
+// 8 images, more than everything else the two layers move.
+//
+// TMEM columns (C = 192): [0,C) acc1 | [C, C + C/2) x^2 bf16 (two values per 32-bit column) | [.., +C) acc2.
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int G_EPI_WARPS = 12;
+constexpr int G_THREADS = 64 + 32 * G_EPI_WARPS;
+constexpr int G_PARTS = G_EPI_WARPS / 4;
+constexpr int MAXC = 192;                    // channel count supported (TMEM: 2.5 C <= 512)
+constexpr int MAX_CHUNKS = MAXC / 16 / G_PARTS;
+
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+struct GdnGeom {
+  int gamma_bytes;   // resident gamma' tiles: (C/64) x [C rows x 128 B]
+  int p_col, acc2_col;
+};
+
+template <bool INVERSE>
+__global__ void __launch_bounds__(G_THREADS, 1)
+conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                   const __grid_constant__ CUtensorMap tmap_g, const rdsic_conv_desc d, const TcGeom g,
+                   const GdnGeom gg) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int stage_bytes = A_STAGE_BYTES + g.b_stage_bytes;
+  uint8_t* gamma_s = smem + (size_t)g.num_stages * stage_bytes;  // 1024-aligned: stage sizes are multiples of 2048
+  uint64_t* full_bar = (uint64_t*)(gamma_s + gg.gamma_bytes);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* acc1_full = empty_bar + MAX_STAGES;
+  uint64_t* acc1_empty = acc1_full + 1;
+  uint64_t* p_full = acc1_empty + 1;
+  uint64_t* acc2_full = p_full + 1;
+  uint64_t* acc2_empty = acc2_full + 1;
+  uint64_t* g_full = acc2_empty + 1;
+  uint32_t* tmem_slot = (uint32_t*)(g_full + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int C = d.Cout;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_g) : "memory");
+    for (int s = 0; s < g.num_stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(acc1_full, 1);
+    mbar_init(acc1_empty, G_EPI_WARPS);
+    mbar_init(p_full, G_EPI_WARPS);
+    mbar_init(acc2_full, 1);
+    mbar_init(acc2_empty, G_EPI_WARPS);
+    mbar_init(g_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      // gamma' once per CTA: C/64 K-blocks of [C rows x 128 B]
+      mbar_expect_tx(g_full, (uint32_t)gg.gamma_bytes);
+      for (int kb = 0; kb < C / BK; ++kb) tma_load_2d(gamma_s + (size_t)kb * C * 128, &tmap_g, g_full, kb * BK, 0);
+      const uint32_t tx_bytes = (uint32_t)stage_bytes;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int tx = t % g.tiles_x;
+        t /= g.tiles_x;
+        const int ty = t % g.tiles_y, b = t / g.tiles_y;
+        const int x0 = tx * g.TW * d.stride - d.pad_w, y0 = ty * g.TH * d.stride - d.pad_h;
+        int kcol = 0;
+        for (int r = 0; r < d.KH; ++r) {
+          for (int sx = 0; sx < d.KW; ++sx, kcol += d.Cin) {
+            for (int cb = 0; cb < g.kb_per_tap; ++cb) {
+              mbar_wait(&empty_bar[s], ph ^ 1u);
+              uint8_t* a_dst = smem + (size_t)s * stage_bytes;
+              mbar_expect_tx(&full_bar[s], tx_bytes);
+              tma_load_4d(a_dst, &tmap_a, &full_bar[s], cb * BK, x0 + sx, y0 + r, b);
+              tma_load_2d(a_dst + A_STAGE_BYTES, &tmap_b, &full_bar[s], kcol + cb * BK, 0);
+              if (++s == g.num_stages) { s = 0; ph ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(C);
+      const int taps = d.KH * d.KW;
+      const int kc_last = (d.Cin - (g.kb_per_tap - 1) * BK) / 16;
+      const uint32_t acc1 = tmem_base, p_t = tmem_base + (uint32_t)gg.p_col, acc2 = tmem_base + (uint32_t)gg.acc2_col;
+      const uint32_t gamma_addr = smem_u32(gamma_s);
+      int s = 0;
+      uint32_t ph = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t par = lt & 1u;
+        // ---- GEMM 1: x = conv(in)
+        mbar_wait(acc1_empty, par ^ 1u);
+        tcgen05_fence_after();
+        uint32_t accumulate = 0;
+        for (int tap = 0; tap < taps; ++tap) {
+          for (int cb = 0; cb < g.kb_per_tap; ++cb) {
+            mbar_wait(&full_bar[s], ph);
+            tcgen05_fence_after();
+            const int kc = cb + 1 == g.kb_per_tap ? kc_last : BK / 16;
+            const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+            const uint64_t da = make_sw128_desc(a_addr), db = make_sw128_desc(a_addr + A_STAGE_BYTES);
+            for (int k = 0; k < kc; ++k) {
+              umma_bf16(acc1, da + 2 * k, db + 2 * k, idesc, accumulate);
+              accumulate = 1;
+            }
+            tcgen05_commit(&empty_bar[s]);
+            if (++s == g.num_stages) { s = 0; ph ^= 1u; }
+          }
+        }
+        tcgen05_commit(acc1_full);
+        // ---- GEMM 2: norm = gamma' @ x^2, A operand from TMEM
+        if (lt == 0) mbar_wait(g_full, 0);
+        mbar_wait(p_full, par);
+        mbar_wait(acc2_empty, par ^ 1u);
+        tcgen05_fence_after();
+        for (int kb = 0; kb < C / BK; ++kb) {
+          const uint64_t dg = make_sw128_desc(gamma_addr + (uint32_t)(kb * C * 128));
+          for (int k = 0; k < BK / 16; ++k)  // 16 bf16 of K = 8 TMEM columns of x^2
+            umma_bf16_ts(acc2, p_t + (uint32_t)((kb * 4 + k) * 8), dg + 2 * k, idesc, (kb | k) ? 1u : 0u);
+        }
+        tcgen05_commit(acc2_full);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue warps =================
+    const int q = warp % 4, part = (warp - 2) / 4;
+    const int ml = q * 32 + lane;
+    const int dy = ml / g.TW, dx = ml % g.TW;
+    const int nchunks = C / 16;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++lt) {
+      int t = tile;
+      const int tx = t % g.tiles_x;
+      t /= g.tiles_x;
+      const int ty = t % g.tiles_y, b = t / g.tiles_y;
+      const int oy = ty * g.TH + dy, ox = tx * g.TW + dx;
+      const bool row_ok = oy < d.OH && ox < d.OW;
+      const size_t pix = ((size_t)b * d.OHt + (oy * d.osy + d.ooy)) * d.OWt + (ox * d.osx + d.oox);
+      const uint32_t par = lt & 1u;
+      uint32_t xs[MAX_CHUNKS][8];  // x as packed bf16, kept for the final multiply
+
+      // ---- phase 1: x = acc1 + bias; x^2 -> TMEM (bf16)
+      mbar_wait(acc1_full, par);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int ci = 0; ci < MAX_CHUNKS; ++ci) {
+        const int j = part + G_PARTS * ci;
+        if (j >= nchunks) break;
+        float v[16];
+        tmem_ld16(tmem_base + lane_off + (uint32_t)(j * 16), v);
+        if (d.bias) {
+          const float4* bp = reinterpret_cast<const float4*>(d.bias + j * 16);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 f = __ldg(bp + i);
+            v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
+          }
+        }
+        uint32_t sq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+          xs[ci][i] = *reinterpret_cast<uint32_t*>(&h);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i] * v[2 * i], v[2 * i + 1] * v[2 * i + 1]);
+          sq[i] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        tmem_st8(tmem_base + lane_off + (uint32_t)(gg.p_col + j * 8), sq);
+      }
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(acc1_empty);  // acc1 drained: GEMM 1 of the next tile may start
+        mbar_arrive(p_full);      // x^2 in place: GEMM 2 may start
+      }
+      // ---- phase 2: out = x * (r)sqrt(acc2 + beta')
+      mbar_wait(acc2_full, par);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int ci = 0; ci < MAX_CHUNKS; ++ci) {
+        const int j = part + G_PARTS * ci;
+        if (j >= nchunks) break;
+        float v[16];
+        tmem_ld16(tmem_base + lane_off + (uint32_t)(gg.acc2_col + j * 16), v);
+        if (!row_ok) continue;
+        const float4* bp = reinterpret_cast<const float4*>(d.gdn_beta + j * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 f = __ldg(bp + i);
+          v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float x0 = __uint_as_float(xs[ci][i] << 16), x1 = __uint_as_float(xs[ci][i] & 0xFFFF0000u);
+          v[2 * i] = INVERSE ? x0 * sqrtf(v[2 * i]) : x0 * rsqrtf(v[2 * i]);
+          v[2 * i + 1] = INVERSE ? x1 * sqrtf(v[2 * i + 1]) : x1 * rsqrtf(v[2 * i + 1]);
+        }
+        store16(d.out, pix * (size_t)d.out.ld + d.out.coff + j * 16, v, false);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc2_empty);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+}  // namespace
+
+int rdsic_conv_validate(const rdsic_conv_desc* d);
+
+// conv (+bias) -> GDN / IGDN in one launch.  d->gdn_mode: 1 = GDN, 2 = inverse; d->gdn_gamma = packed bf16
+// gamma' [C][C] (K-major), d->gdn_beta = fp32 beta' [C].
+int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
+  int rc = rdsic_conv_validate(d);
+  if (rc) return rc;
+  const int C = d->Cout;
+  RDSIC_CHECK_ARG(d->gdn_gamma && d->gdn_beta && (d->gdn_mode == 1 || d->gdn_mode == 2));
+  RDSIC_CHECK_ARG(d->epilogue == RDSIC_EPI_NONE && !d->res.ptr && !d->aux.ptr && !d->out2.ptr && !d->out3.ptr);
+  RDSIC_CHECK_ARG(C % BK == 0 && C <= MAXC && d->Cin % 16 == 0 && !d->pixel_shuffle && !d->a_square);
+  RDSIC_CHECK_ARG(d->in.dtype == RDSIC_BF16 && !d->in.nchw && !d->out.nchw && (d->stride == 1 || d->stride == 2));
+  if (d->in.ld % 8 || d->in.coff % 8 || ((uintptr_t)d->in.ptr % 16) || ((uintptr_t)d->weight % 16) ||
+      ((uintptr_t)d->gdn_gamma % 16) || ((uintptr_t)d->gdn_beta % 16) || (d->bias && ((uintptr_t)d->bias % 16)) ||
+      d->out.ld % 16 || d->out.coff % 16 || ((uintptr_t)d->out.ptr % 32))
+    return RDSIC_E_ALIGN;
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return RDSIC_E_UNSUPPORTED;
+
+  TcGeom g;
+  int B = d->B, H = d->H, W = d->W, OH = d->OH, OW = d->OW;
+  const bool flat = d->KH == 1 && d->KW == 1 && d->stride == 1 && d->pad_h == 0 && d->pad_w == 0 && d->osy == 1 &&
+                    d->osx == 1 && d->ooy == 0 && d->oox == 0 && OH == H && OW == W && d->OHt == OH && d->OWt == OW;
+  rdsic_conv_desc dd = *d;
+  if (flat) {
+    W = OW = B * H * W;
+    H = OH = 1;
+    B = 1;
+    dd.B = 1; dd.H = 1; dd.W = W; dd.OH = 1; dd.OW = OW; dd.OHt = 1; dd.OWt = OW;
+    g.TH = 1; g.TW = 128;
+  } else {
+    long best = -1;
+    for (int tw = 128; tw >= 1; tw /= 2) {
+      const int th = BM / tw;
+      const long area = (long)ceil_div(OW, tw) * tw * ceil_div(OH, th) * th;
+      if (best < 0 || area < best) { best = area; g.TW = tw; g.TH = th; }
+    }
+  }
+  g.tiles_x = ceil_div(OW, g.TW);
+  g.tiles_y = ceil_div(OH, g.TH);
+  g.BN = C;
+  g.n_tiles = 1;
+  g.total_tiles = B * g.tiles_y * g.tiles_x;
+  g.kb_per_tap = ceil_div(d->Cin, BK);
+  g.num_k_iters = d->KH * d->KW * g.kb_per_tap;
+  g.b_stage_bytes = C * BK * 2;
+  g.tmem_cols = 512;
+  GdnGeom gg;
+  gg.gamma_bytes = (C / BK) * C * 128;
+  gg.p_col = C;
+  gg.acc2_col = C + C / 2;
+  const int stage_bytes = A_STAGE_BYTES + g.b_stage_bytes;
+  int stages = (200 * 1024 - gg.gamma_bytes) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) return RDSIC_E_ARG;
+  g.num_stages = stages;
+  RDSIC_CHECK_ARG(g.TW * d->stride <= 256 && g.TH * d->stride <= 256);
+
+  CUtensorMap ta, tb, tg;
+  {
+    const cuuint64_t ld_b = (cuuint64_t)d->in.ld * 2;
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {ld_b, ld_b * W, ld_b * W * H};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(g.TW * d->stride), (cuuint32_t)(g.TH * d->stride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+    void* base = (void*)((const __nv_bfloat16*)d->in.ptr + d->in.coff);
+    if (encode(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return RDSIC_E_ARG;
+  }
+  auto encode_2d = [&](CUtensorMap* tm, const void* ptr, int K, int rows) {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)C};
+    cuuint32_t estr[2] = {1, 1};
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
+  if (encode_2d(&tb, d->weight, d->KH * d->KW * d->Cin, C) != CUDA_SUCCESS) return RDSIC_E_ARG;
+  if (encode_2d(&tg, d->gdn_gamma, C, C) != CUDA_SUCCESS) return RDSIC_E_ARG;
+
+  const size_t smem = (size_t)stages * stage_bytes + gg.gamma_bytes + 1024 + (2 * MAX_STAGES + 8) * 8 + 16;
+  auto kern = d->gdn_mode == 2 ? conv_gdn_tc_kernel<true> : conv_gdn_tc_kernel<false>;
+  static bool attr_set[16][2] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool track = dev >= 0 && dev < 16;
+  if (!track || !attr_set[dev][d->gdn_mode == 2]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    if (track) attr_set[dev][d->gdn_mode == 2] = true;
+  }
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  const int grid = g.total_tiles < sms ? g.total_tiles : sms;
+  kern<<<grid, G_THREADS, smem, stream>>>(ta, tb, tg, dd, g, gg);
+  return rdsic_launch_status();
+}

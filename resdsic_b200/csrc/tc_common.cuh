@@ -1,0 +1,236 @@
+// Shared pieces of the tcgen05 / TMA kernels (conv_bf16.cu, conv_gdn_bf16.cu): tile constants, PTX wrappers
+// (mbarrier, TMA, tcgen05.mma / ld / st / commit), shared-memory and instruction descriptors, and the
+// vectorised epilogue helpers.
+#pragma once
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;        // UMMA M (cta_group::1)
+constexpr int BK = 64;         // bf16 elements per 128-byte swizzle row
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int NUM_EPI_WARPS = 12;                  // four warps per TMEM lane quarter (latency hiding by TLP)
+constexpr int EPI_PARTS = NUM_EPI_WARPS / 4;       // column interleave factor between the warps of a quarter
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // TMA warp + MMA warp + epilogue warps
+constexpr int MAX_STAGES = 8;
+constexpr uint32_t SPIN_LIMIT = 1u << 22;  // a lost mbarrier signal traps instead of hanging the GPU
+
+struct TcGeom {
+  int TH, TW, tiles_y, tiles_x;
+  int BN, n_tiles, total_tiles, kb_per_tap, num_k_iters, num_stages, tmem_cols;
+  int b_stage_bytes;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by ONE thread
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, rows at 128 B pitch,
+// 8-row groups 1024 B apart (SBO), descriptor version 1 (Blackwell).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address  [0,14)
+  d |= (uint64_t)1 << 16;                       // LBO (ignored for swizzled K-major) [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;             // SBO [32,46)
+  d |= (uint64_t)1 << 46;                       // version = 1 [46,48)
+  d |= (uint64_t)2 << 61;                       // layout type SWIZZLE_128B [61,64)
+  return d;
+}
+
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=bn
+__device__ __forceinline__ uint32_t make_idesc(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// tcgen05.ld is asynchronous: issue any number of loads, then tmem_ld_wait(), then pass every destination
+// through tmem_ld_fence() -- an empty asm that makes the registers depend on the wait, so the compiler
+// cannot hoist their first use above it.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_fence(uint32_t* r) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+               "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  tmem_ld16_issue(taddr, r);
+  tmem_ld_wait();
+  tmem_ld_fence(r);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ------------------------------------------------------------------ epilogue helpers
+// Epilogue math for the bf16 path.  The pointwise layers are instruction-issue bound in the epilogue
+// (ncu: ~34 thread instructions per output element with erff(), profiles/), so GELU is evaluated as
+// 0.5x(1 + tanh(x(c1 + c2 x^2 + c3 x^4))) with coefficients fitted to the exact erf form (max |err| 3e-5,
+// 16x tighter than the textbook tanh-GELU) and the single-instruction MUFU tanh (rel. err 2^-11): total error
+// < 0.05 bf16 ulp of the stored activation.  The fp32 mode (conv_f32.cu) keeps erff()/expf().
+__device__ __forceinline__ float tanh_mufu(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);  // beyond |x| = 8 the fitted quintic would turn over; tanh is +-1 there
+  const float x2 = xc * xc;
+  float t = fmaf(-3.58618502e-4f, x2, 3.70495807e-2f);
+  t = fmaf(t, x2, 7.97459395e-1f);
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_mufu(xc * t), h);
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_mufu(0.5f * x), 0.5f); }
+
+template <int EPI>
+__device__ __forceinline__ float epi_apply(float v, float res, float aux) {
+  if (EPI == RDSIC_EPI_GELU) return gelu_fast(v);
+  if (EPI == RDSIC_EPI_RES_GELU) return gelu_fast(v + res);
+  if (EPI == RDSIC_EPI_ADD_RES) return v + res;
+  if (EPI == RDSIC_EPI_GATE) return aux * sigmoid_fast(v) + res;
+  if (EPI == RDSIC_EPI_GDN) return res * rsqrtf(v);
+  if (EPI == RDSIC_EPI_IGDN) return res * sqrtf(v);
+  if (EPI == RDSIC_EPI_LRP) return res + 0.5f * tanhf(v);
+  return v;
+}
+
+// 16 consecutive channels of one pixel = one 32-byte (bf16) or two 32-byte (fp32) accesses; sm_100 has
+// 256-bit LDG/STG, and the host guarantees 32-byte alignment of every chunk on the PLAIN path.
+struct Pack8 {
+  uint32_t w[8];
+};
+__device__ __forceinline__ Pack8 ldg256(const void* p) {
+  Pack8 r;
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg256(void* p, const Pack8& r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.w[0]), "r"(r.w[1]), "r"(r.w[2]),
+               "r"(r.w[3]), "r"(r.w[4]), "r"(r.w[5]), "r"(r.w[6]), "r"(r.w[7])
+               : "memory");
+}
+__device__ __forceinline__ void unpack_bf16x16(const Pack8& r, float* o) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    o[2 * i] = __uint_as_float(r.w[i] << 16);
+    o[2 * i + 1] = __uint_as_float(r.w[i] & 0xFFFF0000u);
+  }
+}
+__device__ __forceinline__ void load16(const rdsic_view& vw, size_t elem, float* o) {
+  if (vw.dtype == RDSIC_BF16) {
+    unpack_bf16x16(ldg256((const __nv_bfloat16*)vw.ptr + elem), o);
+  } else {
+    const Pack8 r0 = ldg256((const float*)vw.ptr + elem), r1 = ldg256((const float*)vw.ptr + elem + 8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      o[i] = __uint_as_float(r0.w[i]);
+      o[8 + i] = __uint_as_float(r1.w[i]);
+    }
+  }
+}
+__device__ __forceinline__ void store16(const rdsic_view& vw, size_t elem, const float* v, bool sq) {
+  if (vw.dtype == RDSIC_BF16) {
+    Pack8 r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float a0 = v[2 * i], a1 = v[2 * i + 1];
+      if (sq) { a0 *= a0; a1 *= a1; }
+      __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+      r.w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    stg256((__nv_bfloat16*)vw.ptr + elem, r);
+  } else {
+    Pack8 r0, r1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      r0.w[i] = __float_as_uint(sq ? v[i] * v[i] : v[i]);
+      r1.w[i] = __float_as_uint(sq ? v[8 + i] * v[8 + i] : v[8 + i]);
+    }
+    stg256((float*)vw.ptr + elem, r0);
+    stg256((float*)vw.ptr + elem + 8, r1);
+  }
+}
+
+
+// ------------------------------------------------------------------ host: TMA descriptor encoder
+// resolved through the runtime (no link-time dependency on libcuda: the library loads without a driver)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;  // benign race: every thread resolves the same pointer
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+
+}  // namespace

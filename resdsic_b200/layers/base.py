@@ -105,6 +105,12 @@ class Sequential(nn.Sequential, B200Module):
             extra = dict(last_kw or {}) if i + step >= len(mods) else {}
             if step == 2:  # fuse "conv -> GELU" pairs into the conv epilogue
                 x = m.emit(ctx, x, gelu=True, **extra)
+            elif (getattr(nxt, "wants_square", False) and ctx.precision == "bf16" and hasattr(m, "weight")
+                  and getattr(m, "can_fuse_gdn", lambda *_: False)(ctx, x, nxt)):
+                # conv/deconv -> GDN in ONE kernel (x stays in TMEM, gamma' resident in smem)
+                extra = dict(last_kw or {}) if i + 2 >= len(mods) else {}
+                x = m.emit(ctx, x, gdn=nxt.fused_params(), **extra)
+                step = 2
             elif getattr(nxt, "wants_square", False) and ctx.precision == "bf16" and hasattr(m, "weight"):
                 # conv/deconv -> GDN in bf16 mode: the producer also stores x^2 (the GDN GEMM's A operand)
                 x = m.emit(ctx, x, out2_square=True, want_sq=True, **extra)

@@ -33,6 +33,14 @@ class Conv2d(B200Module):
         return self._packed(("w", wdt), (self.weight, self.bias), lambda: (
             packing.pack_conv_weight(self.weight, wdt), self.bias.detach().float().contiguous()))
 
+    def can_fuse_gdn(self, ctx, x, gdn):
+        """Fuse the following GDN into this conv's kernel when the conv is short-K (memory-bound): the fused
+        kernel gives up pipeline stages for the resident gamma', which only pays off for cheap producers."""
+        C = self.out_channels
+        k_iters = self.kernel_size ** 2 * -(-self.in_channels // 64)
+        patch = ctx.wdt_for(x) != torch.bfloat16 and self.kernel_size ** 2 * self.in_channels <= 256
+        return C == gdn.in_channels and C % 64 == 0 and C <= 192 and (patch or (ctx.wdt_for(x) == torch.bfloat16 and k_iters <= 32))
+
     def emit(self, ctx: Ctx, x, gelu=False, epilogue=None, out=None, out_dtype=None, pixel_shuffle=0, want_sq=False,
              **kw):
         k, s, p = self.kernel_size, self.stride, self.padding
@@ -102,6 +110,11 @@ class ConvTranspose2d(B200Module):
     def packed(self, wdt):
         return self._packed(("w", wdt), (self.weight, self.bias), lambda: (
             packing.pack_deconv_weight(self.weight, wdt), self.bias.detach().float().contiguous()))
+
+    def can_fuse_gdn(self, ctx, x, gdn):
+        C = self.out_channels
+        return ctx.wdt_for(x) == torch.bfloat16 and C == gdn.in_channels and C % 64 == 0 and C <= 192 and \
+            9 * -(-self.in_channels // 64) <= 32
 
     def emit(self, ctx: Ctx, x, out=None, out_dtype=None, want_sq=False, **kw):
         wdt = ctx.wdt_for(x)

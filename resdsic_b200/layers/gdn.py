@@ -26,6 +26,11 @@ class GDN(B200Module):
 
     wants_square = True  # in bf16 mode the producing conv also stores x^2 (see Sequential.emit)
 
+    def fused_params(self):
+        """(gamma' bf16 [C][C], beta' fp32, inverse) for the fused conv+GDN kernel."""
+        gamma, beta = self.packed(torch.bfloat16)
+        return gamma, beta, self.inverse
+
     def emit(self, ctx: Ctx, x, out=None, x2=None, **kw):
         C = self.in_channels
         if out is None:

@@ -135,7 +135,7 @@ class Program:
     # ------------------------------------------------------------- builders
     def conv(self, x: TV, weight, bias, Cout, KH, KW, stride, pad_h, pad_w, out: TV, epilogue=_lib.EPI_NONE,
              res: TV = None, aux: TV = None, out2: TV = None, out3: TV = None, a_square=False, pixel_shuffle=0,
-             OH=None, OW=None, osy=1, osx=1, ooy=0, oox=0, Cin=None, out2_square=False):
+             OH=None, OW=None, osy=1, osx=1, ooy=0, oox=0, Cin=None, out2_square=False, gdn=None):
         d = ConvDesc()
         d.in_ = x.view()
         d.B, d.H, d.W, d.Cin = x.B, x.H, x.W, (x.C if Cin is None else Cin)
@@ -149,6 +149,9 @@ class Program:
         d.pixel_shuffle, d.epilogue, d.a_square = pixel_shuffle, epilogue, int(a_square)
         d.out = out.view()
         d.out2_square = int(out2_square)
+        if gdn is not None:  # (gamma' packed bf16, beta' fp32, inverse)
+            d.gdn_gamma, d.gdn_beta, d.gdn_mode = gdn[0].data_ptr(), gdn[1].data_ptr(), 2 if gdn[2] else 1
+            self.keep += [gdn[0], gdn[1]]
         for name, tv in (("res", res), ("aux", aux), ("out2", out2), ("out3", out3)):
             setattr(d, name, tv.view() if tv is not None else _NULL)
         assert weight.numel() >= Cout * KH * KW * d.Cin and weight.shape[-1] == KH * KW * d.Cin, \

@@ -85,6 +85,31 @@ def main():
     xb = bf(x)
     norm = F.conv2d(bf(xb * xb), bf(gam).reshape(192, 192, 1, 1), beta)
     ok &= report("gdn_192", run(g, x), xb * torch.rsqrt(norm))
+    # fused conv -> GDN and deconv -> IGDN (one kernel each; x^2 goes through TMEM)
+    from resdsic_b200.layers import Sequential
+    for name, first, inverse, xin in (
+            ("fused_conv5x5s2_3_192_gdn", Conv2d(3, 192, 5, 2), False, weights.hash_uniform("p.fx1", (2, 3, 40, 56))),
+            ("fused_deconv_192_192_igdn", ConvTranspose2d(192, 192), True, weights.hash_symmetric("p.fx2", (2, 192, 9, 13), 1.0)),
+            ("fused_conv1x1_64_128_gdn", Conv2d(64, 128, 1, 1), False, weights.hash_symmetric("p.fx3", (1, 64, 8, 16), 1.0))):
+        gd = GDN(first.out_channels, inverse=inverse)
+        with torch.no_grad():
+            first.weight.copy_(weights.hash_symmetric(f"p.fw{name}", first.weight.shape, 0.08))
+            first.bias.copy_(weights.hash_symmetric(f"p.fb{name}", first.bias.shape, 0.1))
+            gd.gamma.add_(weights.hash_uniform(f"p.fg{name}", gd.gamma.shape) * 0.02)
+        seq = Sequential(first, gd)
+        ctx_probe = Ctx(DEV, "bf16")
+        n_before = 0
+        out = run(seq, xin)
+        xb = bf(xin)
+        if isinstance(first, ConvTranspose2d):
+            t = F.conv_transpose2d(xb, bf(first.weight.detach().cpu()), first.bias.detach().cpu(), stride=2, padding=2, output_padding=1)
+        else:
+            t = F.conv2d(xb, bf(first.weight.detach().cpu()), first.bias.detach().cpu(), stride=first.stride, padding=first.padding)
+        gam, beta = packing.pack_gdn(gd.beta.detach().cpu(), gd.gamma.detach().cpu())
+        C = first.out_channels
+        norm = F.conv2d(bf(t * t), bf(gam).reshape(C, C, 1, 1), beta)
+        ref = bf(t) * (torch.sqrt(norm) if inverse else torch.rsqrt(norm))
+        ok &= report(name, out, ref)
     print("ALL OK" if ok else "SOME MISMATCH")
     return 0 if ok else 1
 

@@ -66,6 +66,13 @@ class Sim:
         def sub(view):
             return self._nhwc(view, d.B, d.OHt, d.OWt, Cv)[:, oy::sy, ox::sx][:, : v.shape[1], : v.shape[2]]
 
+        if d.gdn_mode:  # fused GDN: x (bf16-rounded) * (r)sqrt(beta + gamma @ bf16(x^2))
+            Cg = d.Cout
+            gam = self._flat(d.gdn_gamma)[: Cg * Cg].float().view(Cg, Cg)
+            beta = self._flat(d.gdn_beta)[:Cg]
+            x2 = (v * v).bfloat16().float()
+            norm = x2 @ gam.t() + beta
+            v = v.bfloat16().float() * (torch.sqrt(norm) if d.gdn_mode == 2 else torch.rsqrt(norm))
         e = d.epilogue
         res = sub(d.res).float() if d.res.ptr else None
         aux = sub(d.aux).float() if d.aux.ptr else None

@@ -90,12 +90,18 @@ typedef struct rdsic_conv_desc {
   rdsic_view out2;        /* optional extra copies of the result (slice-loop support buffers) */
   rdsic_view out3;
   int32_t out2_square;    /* out2 receives result^2 (feeds the next GDN's beta + gamma @ x^2 contraction) */
-  /* Fused GDN (bf16 tensor-core path only): with gdn_mode 1 (GDN) / 2 (inverse) the kernel continues
-   * out = x * rsqrt|sqrt(gdn_beta + gdn_gamma @ x^2) on x = conv(in) + bias without x leaving the SM
-   * (layers/gdn.py:62-75 after WACNN/utils.py:116-134).  gdn_gamma: packed bf16 [Cout][Cout], gdn_beta fp32. */
-  int32_t gdn_mode;
-  const void* gdn_gamma;
-  const float* gdn_beta;
+  /* Fused second ("tail") GEMM, bf16 tensor-core path only: the conv result x = conv(in) + bias never leaves
+   * the SM; a pointwise GEMM with `tail_weight` (packed bf16 [tail_n][Cout]) runs on it from tensor memory:
+   *   tail_mode 1 / 2: GDN / inverse GDN, out = x * rsqrt|sqrt(tail_bias + tail_weight @ x^2)
+   *                    (layers/gdn.py:62-75 after WACNN/utils.py:116-134; tail_weight = gamma', tail_n = Cout);
+   *   tail_mode 3:     ResidualUnit tail, out = gelu(tail_weight @ gelu(x) + tail_bias + res)
+   *                    (layers/layers.py:58-71: conv3x3 -> GELU -> conv1x1, += identity, GELU).
+   * `out` (and `res`) then have tail_n channels. */
+  int32_t tail_mode;
+  const void* tail_weight;
+  const float* tail_bias;
+  int32_t tail_n;
+  int32_t pad_;
 } rdsic_conv_desc;
 
 /* Fused shifted-window attention core: replaces roll + window_partition +

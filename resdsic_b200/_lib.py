@@ -34,7 +34,8 @@ class ConvDesc(C.Structure):
         ("ooy", C.c_int32), ("oox", C.c_int32),
         ("pixel_shuffle", C.c_int32), ("epilogue", C.c_int32), ("a_square", C.c_int32),
         ("out", View), ("res", View), ("aux", View), ("out2", View), ("out3", View),
-        ("out2_square", C.c_int32), ("gdn_mode", C.c_int32), ("gdn_gamma", C.c_void_p), ("gdn_beta", C.c_void_p),
+        ("out2_square", C.c_int32), ("tail_mode", C.c_int32), ("tail_weight", C.c_void_p), ("tail_bias", C.c_void_p),
+        ("tail_n", C.c_int32), ("pad_", C.c_int32),
     ]
 
 

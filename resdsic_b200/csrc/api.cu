@@ -44,7 +44,7 @@ int rdsic_sizeof(int what) {
 
 int rdsic_conv_forward(const rdsic_conv_desc* d, rdsic_stream_t stream) {
   if (!d) return RDSIC_E_ARG;
-  if (d->gdn_mode) return d->w_dtype == RDSIC_BF16 ? rdsic_conv_gdn_forward_bf16(d, (cudaStream_t)stream) : RDSIC_E_UNSUPPORTED;
+  if (d->tail_mode) return d->w_dtype == RDSIC_BF16 ? rdsic_conv_gdn_forward_bf16(d, (cudaStream_t)stream) : RDSIC_E_UNSUPPORTED;
   if (d->w_dtype == RDSIC_BF16) return rdsic_conv_forward_bf16(d, (cudaStream_t)stream);
   return rdsic_conv_forward_f32(d, (cudaStream_t)stream);
 }

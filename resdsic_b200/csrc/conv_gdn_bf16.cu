@@ -39,12 +39,15 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+enum { TAIL_GDN = 1, TAIL_IGDN = 2, TAIL_RU = 3 };
+
 struct GdnGeom {
-  int gamma_bytes;   // resident gamma' tiles: (C/64) x [C rows x 128 B]
+  int w2_bytes;      // resident second-GEMM weight tiles: ceil(K2/64) x [N2 rows x 128 B]
   int p_col, acc2_col;
+  int N2, k2_blocks, kc2_last;  // second GEMM: N2 output columns, K2 = N1 in 64-wide blocks
 };
 
-template <bool INVERSE>
+template <int MODE>
 __global__ void __launch_bounds__(G_THREADS, 1)
 conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_g, const rdsic_conv_desc d, const TcGeom g,
@@ -53,7 +56,7 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int stage_bytes = A_STAGE_BYTES + g.b_stage_bytes;
   uint8_t* gamma_s = smem + (size_t)g.num_stages * stage_bytes;  // 1024-aligned: stage sizes are multiples of 2048
-  uint64_t* full_bar = (uint64_t*)(gamma_s + gg.gamma_bytes);
+  uint64_t* full_bar = (uint64_t*)(gamma_s + gg.w2_bytes);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* acc1_full = empty_bar + MAX_STAGES;
   uint64_t* acc1_empty = acc1_full + 1;
@@ -94,9 +97,9 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      // gamma' once per CTA: C/64 K-blocks of [C rows x 128 B]
-      mbar_expect_tx(g_full, (uint32_t)gg.gamma_bytes);
-      for (int kb = 0; kb < C / BK; ++kb) tma_load_2d(gamma_s + (size_t)kb * C * 128, &tmap_g, g_full, kb * BK, 0);
+      // second-GEMM weights once per CTA: K2/64 blocks of [N2 rows x 128 B]
+      mbar_expect_tx(g_full, (uint32_t)gg.w2_bytes);
+      for (int kb = 0; kb < gg.k2_blocks; ++kb) tma_load_2d(gamma_s + (size_t)kb * gg.N2 * 128, &tmap_g, g_full, kb * BK, 0);
       const uint32_t tx_bytes = (uint32_t)stage_bytes;
       int s = 0;
       uint32_t ph = 0;
@@ -125,7 +128,7 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(C);
+      const uint32_t idesc = make_idesc(C), idesc2 = make_idesc(gg.N2);
       const int taps = d.KH * d.KW;
       const int kc_last = (d.Cin - (g.kb_per_tap - 1) * BK) / 16;
       const uint32_t acc1 = tmem_base, p_t = tmem_base + (uint32_t)gg.p_col, acc2 = tmem_base + (uint32_t)gg.acc2_col;
@@ -159,10 +162,11 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         mbar_wait(p_full, par);
         mbar_wait(acc2_empty, par ^ 1u);
         tcgen05_fence_after();
-        for (int kb = 0; kb < C / BK; ++kb) {
-          const uint64_t dg = make_sw128_desc(gamma_addr + (uint32_t)(kb * C * 128));
-          for (int k = 0; k < BK / 16; ++k)  // 16 bf16 of K = 8 TMEM columns of x^2
-            umma_bf16_ts(acc2, p_t + (uint32_t)((kb * 4 + k) * 8), dg + 2 * k, idesc, (kb | k) ? 1u : 0u);
+        for (int kb = 0; kb < gg.k2_blocks; ++kb) {
+          const uint64_t dg = make_sw128_desc(gamma_addr + (uint32_t)(kb * gg.N2 * 128));
+          const int kc2 = kb + 1 == gg.k2_blocks ? gg.kc2_last : BK / 16;
+          for (int k = 0; k < kc2; ++k)  // 16 bf16 of K = 8 TMEM columns of the staged operand
+            umma_bf16_ts(acc2, p_t + (uint32_t)((kb * 4 + k) * 8), dg + 2 * k, idesc2, (kb | k) ? 1u : 0u);
         }
         tcgen05_commit(acc2_full);
       }
@@ -173,7 +177,7 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const int q = warp % 4, part = (warp - 2) / 4;
     const int ml = q * 32 + lane;
     const int dy = ml / g.TW, dx = ml % g.TW;
-    const int nchunks = C / 16;
+    const int nchunks1 = C / 16, nchunks2 = gg.N2 / 16;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++lt) {
@@ -185,15 +189,15 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const bool row_ok = oy < d.OH && ox < d.OW;
       const size_t pix = ((size_t)b * d.OHt + (oy * d.osy + d.ooy)) * d.OWt + (ox * d.osx + d.oox);
       const uint32_t par = lt & 1u;
-      uint32_t xs[MAX_CHUNKS][8];  // x as packed bf16, kept for the final multiply
+      uint32_t xs[MAX_CHUNKS][8];  // GDN: x as packed bf16, kept for the final multiply; RU: prefetched residual
 
-      // ---- phase 1: x = acc1 + bias; x^2 -> TMEM (bf16)
+      // ---- phase 1: v = acc1 + bias;  GDN: stage v^2, keep v;  RU: stage gelu(v)
       mbar_wait(acc1_full, par);
       tcgen05_fence_after();
 #pragma unroll
       for (int ci = 0; ci < MAX_CHUNKS; ++ci) {
         const int j = part + G_PARTS * ci;
-        if (j >= nchunks) break;
+        if (j >= nchunks1) break;
         float v[16];
         tmem_ld16(tmem_base + lane_off + (uint32_t)(j * 16), v);
         if (d.bias) {
@@ -204,34 +208,51 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
           }
         }
-        uint32_t sq[8];
+        uint32_t st[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-          xs[ci][i] = *reinterpret_cast<uint32_t*>(&h);
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i] * v[2 * i], v[2 * i + 1] * v[2 * i + 1]);
-          sq[i] = *reinterpret_cast<uint32_t*>(&h2);
+          if (MODE == TAIL_RU) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(gelu_fast(v[2 * i]), gelu_fast(v[2 * i + 1]));
+            st[i] = *reinterpret_cast<uint32_t*>(&h);
+          } else {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            xs[ci][i] = *reinterpret_cast<uint32_t*>(&h);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i] * v[2 * i], v[2 * i + 1] * v[2 * i + 1]);
+            st[i] = *reinterpret_cast<uint32_t*>(&h2);
+          }
         }
-        tmem_st8(tmem_base + lane_off + (uint32_t)(gg.p_col + j * 8), sq);
+        tmem_st8(tmem_base + lane_off + (uint32_t)(gg.p_col + j * 8), st);
       }
       tmem_st_wait();
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(acc1_empty);  // acc1 drained: GEMM 1 of the next tile may start
-        mbar_arrive(p_full);      // x^2 in place: GEMM 2 may start
+        mbar_arrive(p_full);      // staged operand in place: GEMM 2 may start
       }
-      // ---- phase 2: out = x * (r)sqrt(acc2 + beta')
+      if (MODE == TAIL_RU) {  // residual x: issue the loads now, they land while GEMM 2 runs
+        const __nv_bfloat16* resp = (const __nv_bfloat16*)d.res.ptr + pix * (size_t)d.res.ld + d.res.coff;
+#pragma unroll
+        for (int ci = 0; ci < MAX_CHUNKS; ++ci) {
+          const int j = part + G_PARTS * ci;
+          if (j < nchunks2 && row_ok) {
+            const Pack8 r = ldg256(resp + j * 16);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xs[ci][i] = r.w[i];
+          }
+        }
+      }
+      // ---- phase 2: GDN: out = x * (r)sqrt(acc2 + beta');  RU: out = gelu(acc2 + bias2 + res)
       mbar_wait(acc2_full, par);
       tcgen05_fence_after();
 #pragma unroll
       for (int ci = 0; ci < MAX_CHUNKS; ++ci) {
         const int j = part + G_PARTS * ci;
-        if (j >= nchunks) break;
+        if (j >= nchunks2) break;
         float v[16];
         tmem_ld16(tmem_base + lane_off + (uint32_t)(gg.acc2_col + j * 16), v);
         if (!row_ok) continue;
-        const float4* bp = reinterpret_cast<const float4*>(d.gdn_beta + j * 16);
+        const float4* bp = reinterpret_cast<const float4*>(d.tail_bias + j * 16);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float4 f = __ldg(bp + i);
@@ -240,8 +261,13 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float x0 = __uint_as_float(xs[ci][i] << 16), x1 = __uint_as_float(xs[ci][i] & 0xFFFF0000u);
-          v[2 * i] = INVERSE ? x0 * sqrtf(v[2 * i]) : x0 * rsqrtf(v[2 * i]);
-          v[2 * i + 1] = INVERSE ? x1 * sqrtf(v[2 * i + 1]) : x1 * rsqrtf(v[2 * i + 1]);
+          if (MODE == TAIL_RU) {
+            v[2 * i] = gelu_fast(v[2 * i] + x0);
+            v[2 * i + 1] = gelu_fast(v[2 * i + 1] + x1);
+          } else {
+            v[2 * i] = MODE == TAIL_IGDN ? x0 * sqrtf(v[2 * i]) : x0 * rsqrtf(v[2 * i]);
+            v[2 * i + 1] = MODE == TAIL_IGDN ? x1 * sqrtf(v[2 * i + 1]) : x1 * rsqrtf(v[2 * i + 1]);
+          }
         }
         store16(d.out, pix * (size_t)d.out.ld + d.out.coff + j * 16, v, false);
       }
@@ -263,18 +289,30 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
 int rdsic_conv_validate(const rdsic_conv_desc* d);
 
-// conv (+bias) -> GDN / IGDN in one launch.  d->gdn_mode: 1 = GDN, 2 = inverse; d->gdn_gamma = packed bf16
-// gamma' [C][C] (K-major), d->gdn_beta = fp32 beta' [C].
+// conv (+bias) followed by a second, pointwise GEMM in one launch (d->tail_mode):
+//   1 GDN / 2 inverse GDN: tail_weight = packed bf16 gamma' [C][C], tail_bias = fp32 beta' [C], tail_n = C;
+//   3 ResidualUnit tail (layers/layers.py:58-71): out = gelu(W3 @ gelu(conv + bias) + b3 + res),
+//     tail_weight = packed bf16 [tail_n][C], tail_bias = b3, res = the unit's input.
 int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
-  int rc = rdsic_conv_validate(d);
-  if (rc) return rc;
   const int C = d->Cout;
-  RDSIC_CHECK_ARG(d->gdn_gamma && d->gdn_beta && (d->gdn_mode == 1 || d->gdn_mode == 2));
-  RDSIC_CHECK_ARG(d->epilogue == RDSIC_EPI_NONE && !d->res.ptr && !d->aux.ptr && !d->out2.ptr && !d->out3.ptr);
-  RDSIC_CHECK_ARG(C % BK == 0 && C <= MAXC && d->Cin % 16 == 0 && !d->pixel_shuffle && !d->a_square);
+  const int N2 = d->tail_n;
+  rdsic_conv_desc chk = *d;
+  chk.Cout = N2 > C ? N2 : C;  // validation of the output views is against the final channel count
+  int rc = rdsic_conv_validate(&chk);
+  if (rc) return rc;
+  RDSIC_CHECK_ARG(d->tail_weight && d->tail_bias && d->tail_mode >= TAIL_GDN && d->tail_mode <= TAIL_RU);
+  RDSIC_CHECK_ARG(d->epilogue == RDSIC_EPI_NONE && !d->aux.ptr && !d->out2.ptr && !d->out3.ptr);
+  RDSIC_CHECK_ARG(C % 16 == 0 && N2 % 16 == 0 && N2 >= 32 && N2 <= MAXC && C + C / 2 + N2 <= 512);
+  RDSIC_CHECK_ARG(d->Cin % 16 == 0 && !d->pixel_shuffle && !d->a_square);
+  if (d->tail_mode == TAIL_RU) {
+    RDSIC_CHECK_ARG(d->res.ptr && d->res.dtype == RDSIC_BF16 && !d->res.nchw);
+    if (d->res.ld % 16 || d->res.coff % 16 || ((uintptr_t)d->res.ptr % 32)) return RDSIC_E_ALIGN;
+  } else {
+    RDSIC_CHECK_ARG(!d->res.ptr && N2 == C && C % BK == 0);
+  }
   RDSIC_CHECK_ARG(d->in.dtype == RDSIC_BF16 && !d->in.nchw && !d->out.nchw && (d->stride == 1 || d->stride == 2));
   if (d->in.ld % 8 || d->in.coff % 8 || ((uintptr_t)d->in.ptr % 16) || ((uintptr_t)d->weight % 16) ||
-      ((uintptr_t)d->gdn_gamma % 16) || ((uintptr_t)d->gdn_beta % 16) || (d->bias && ((uintptr_t)d->bias % 16)) ||
+      ((uintptr_t)d->tail_weight % 16) || ((uintptr_t)d->tail_bias % 16) || (d->bias && ((uintptr_t)d->bias % 16)) ||
       d->out.ld % 16 || d->out.coff % 16 || ((uintptr_t)d->out.ptr % 32))
     return RDSIC_E_ALIGN;
   EncodeTiledFn encode = get_encode_fn();
@@ -309,11 +347,15 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   g.b_stage_bytes = C * BK * 2;
   g.tmem_cols = 512;
   GdnGeom gg;
-  gg.gamma_bytes = (C / BK) * C * 128;
+  gg.N2 = N2;
+  gg.k2_blocks = ceil_div(C, BK);
+  gg.kc2_last = (C - (gg.k2_blocks - 1) * BK) / 16;
+  gg.w2_bytes = gg.k2_blocks * N2 * 128;
   gg.p_col = C;
-  gg.acc2_col = C + C / 2;
+  gg.acc2_col = (C + C / 2 + 31) / 32 * 32;
+  RDSIC_CHECK_ARG(gg.acc2_col + N2 <= 512);
   const int stage_bytes = A_STAGE_BYTES + g.b_stage_bytes;
-  int stages = (200 * 1024 - gg.gamma_bytes) / stage_bytes;
+  int stages = (200 * 1024 - gg.w2_bytes) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return RDSIC_E_ARG;
   g.num_stages = stages;
@@ -334,24 +376,25 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   auto encode_2d = [&](CUtensorMap* tm, const void* ptr, int K, int rows) {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)C};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)rows};
     cuuint32_t estr[2] = {1, 1};
     return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   };
   if (encode_2d(&tb, d->weight, d->KH * d->KW * d->Cin, C) != CUDA_SUCCESS) return RDSIC_E_ARG;
-  if (encode_2d(&tg, d->gdn_gamma, C, C) != CUDA_SUCCESS) return RDSIC_E_ARG;
+  if (encode_2d(&tg, d->tail_weight, C, N2) != CUDA_SUCCESS) return RDSIC_E_ARG;
 
-  const size_t smem = (size_t)stages * stage_bytes + gg.gamma_bytes + 1024 + (2 * MAX_STAGES + 8) * 8 + 16;
-  auto kern = d->gdn_mode == 2 ? conv_gdn_tc_kernel<true> : conv_gdn_tc_kernel<false>;
-  static bool attr_set[16][2] = {};
+  const size_t smem = (size_t)stages * stage_bytes + gg.w2_bytes + 1024 + (2 * MAX_STAGES + 8) * 8 + 16;
+  auto kern = d->tail_mode == TAIL_RU ? conv_gdn_tc_kernel<TAIL_RU>
+              : d->tail_mode == TAIL_IGDN ? conv_gdn_tc_kernel<TAIL_IGDN> : conv_gdn_tc_kernel<TAIL_GDN>;
+  static bool attr_set[16][4] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   const bool track = dev >= 0 && dev < 16;
-  if (!track || !attr_set[dev][d->gdn_mode == 2]) {
+  if (!track || !attr_set[dev][d->tail_mode]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
-    if (track) attr_set[dev][d->gdn_mode == 2] = true;
+    if (track) attr_set[dev][d->tail_mode] = true;
   }
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

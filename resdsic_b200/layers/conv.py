@@ -42,7 +42,7 @@ class Conv2d(B200Module):
         return C == gdn.in_channels and C % 64 == 0 and C <= 192 and (patch or (ctx.wdt_for(x) == torch.bfloat16 and k_iters <= 32))
 
     def emit(self, ctx: Ctx, x, gelu=False, epilogue=None, out=None, out_dtype=None, pixel_shuffle=0, want_sq=False,
-             **kw):
+             tail=None, **kw):
         k, s, p = self.kernel_size, self.stride, self.padding
         OH, OW = (x.H + 2 * p - k) // s + 1, (x.W + 2 * p - k) // s + 1
         if ctx.precision == "bf16" and ctx.wdt_for(x) != torch.bfloat16 and k * k * self.in_channels <= 256:
@@ -55,11 +55,13 @@ class Conv2d(B200Module):
             x, k, s, p = patches, 1, 1, 0
         else:
             w, b = self.packed(ctx.wdt_for(x))
+        if tail is not None:
+            kw["tail"] = tail
         if out is None:
             if pixel_shuffle:
                 out = ctx.buf(x.B, OH * 2, OW * 2, self.out_channels // 4, out_dtype)
             else:
-                out = ctx.buf(x.B, OH, OW, self.out_channels, out_dtype)
+                out = ctx.buf(x.B, OH, OW, tail[2] if tail is not None else self.out_channels, out_dtype)
         if epilogue is None:
             epilogue = _lib.EPI_GELU if gelu else _lib.EPI_NONE
         if want_sq:

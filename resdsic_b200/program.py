@@ -135,7 +135,7 @@ class Program:
     # ------------------------------------------------------------- builders
     def conv(self, x: TV, weight, bias, Cout, KH, KW, stride, pad_h, pad_w, out: TV, epilogue=_lib.EPI_NONE,
              res: TV = None, aux: TV = None, out2: TV = None, out3: TV = None, a_square=False, pixel_shuffle=0,
-             OH=None, OW=None, osy=1, osx=1, ooy=0, oox=0, Cin=None, out2_square=False, gdn=None):
+             OH=None, OW=None, osy=1, osx=1, ooy=0, oox=0, Cin=None, out2_square=False, gdn=None, tail=None):
         d = ConvDesc()
         d.in_ = x.view()
         d.B, d.H, d.W, d.Cin = x.B, x.H, x.W, (x.C if Cin is None else Cin)
@@ -150,8 +150,11 @@ class Program:
         d.out = out.view()
         d.out2_square = int(out2_square)
         if gdn is not None:  # (gamma' packed bf16, beta' fp32, inverse)
-            d.gdn_gamma, d.gdn_beta, d.gdn_mode = gdn[0].data_ptr(), gdn[1].data_ptr(), 2 if gdn[2] else 1
+            d.tail_weight, d.tail_bias, d.tail_mode, d.tail_n = gdn[0].data_ptr(), gdn[1].data_ptr(), 2 if gdn[2] else 1, Cout
             self.keep += [gdn[0], gdn[1]]
+        if tail is not None:  # ResidualUnit tail: (W3 packed bf16 [N2][Cout], b3 fp32, N2)
+            d.tail_weight, d.tail_bias, d.tail_mode, d.tail_n = tail[0].data_ptr(), tail[1].data_ptr(), 3, tail[2]
+            self.keep += [tail[0], tail[1]]
         for name, tv in (("res", res), ("aux", aux), ("out2", out2), ("out3", out3)):
             setattr(d, name, tv.view() if tv is not None else _NULL)
         assert weight.numel() >= Cout * KH * KW * d.Cin and weight.shape[-1] == KH * KW * d.Cin, \

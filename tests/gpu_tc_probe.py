@@ -110,6 +110,22 @@ def main():
         norm = F.conv2d(bf(t * t), bf(gam).reshape(C, C, 1, 1), beta)
         ref = bf(t) * (torch.sqrt(norm) if inverse else torch.rsqrt(norm))
         ok &= report(name, out, ref)
+    # fused ResidualUnit tail: conv3x3 -> GELU -> conv1x1 -> +x -> GELU in one kernel
+    from resdsic_b200.layers import ResidualUnit
+    for N_, hw in ((192, (16, 24)), (320, (8, 12))):
+        ru = ResidualUnit(N_)
+        with torch.no_grad():
+            for j, c in ((0, ru.conv[0]), (2, ru.conv[2]), (4, ru.conv[4])):
+                c.weight.copy_(weights.hash_symmetric(f"p.ru{N_}.{j}", c.weight.shape, (3.0 / (c.in_channels * c.kernel_size ** 2)) ** 0.5))
+                c.bias.copy_(weights.hash_symmetric(f"p.rub{N_}.{j}", c.bias.shape, 0.1))
+        x = weights.hash_symmetric(f"p.rux{N_}", (2, N_, *hw), 1.0)
+        out = run(ru, x)
+        xb = bf(x)
+        w = lambda c: bf(c.weight.detach().cpu())
+        t = bf(F.gelu(F.conv2d(xb, w(ru.conv[0]), ru.conv[0].bias.detach().cpu())))
+        t = bf(F.gelu(F.conv2d(t, w(ru.conv[2]), ru.conv[2].bias.detach().cpu(), padding=1)))
+        ref = F.gelu(F.conv2d(t, w(ru.conv[4]), ru.conv[4].bias.detach().cpu()) + xb)
+        ok &= report(f"fused_ru_{N_}", out, ref)
     print("ALL OK" if ok else "SOME MISMATCH")
     return 0 if ok else 1
 

@@ -66,13 +66,19 @@ class Sim:
         def sub(view):
             return self._nhwc(view, d.B, d.OHt, d.OWt, Cv)[:, oy::sy, ox::sx][:, : v.shape[1], : v.shape[2]]
 
-        if d.gdn_mode:  # fused GDN: x (bf16-rounded) * (r)sqrt(beta + gamma @ bf16(x^2))
+        if d.tail_mode in (1, 2):  # fused GDN: x (bf16-rounded) * (r)sqrt(beta + gamma @ bf16(x^2))
             Cg = d.Cout
-            gam = self._flat(d.gdn_gamma)[: Cg * Cg].float().view(Cg, Cg)
-            beta = self._flat(d.gdn_beta)[:Cg]
+            gam = self._flat(d.tail_weight)[: Cg * Cg].float().view(Cg, Cg)
+            beta = self._flat(d.tail_bias)[:Cg]
             x2 = (v * v).bfloat16().float()
             norm = x2 @ gam.t() + beta
-            v = v.bfloat16().float() * (torch.sqrt(norm) if d.gdn_mode == 2 else torch.rsqrt(norm))
+            v = v.bfloat16().float() * (torch.sqrt(norm) if d.tail_mode == 2 else torch.rsqrt(norm))
+        elif d.tail_mode == 3:  # fused ResidualUnit tail: gelu(W3 @ bf16(gelu(x)) + b3 + res)
+            w3 = self._flat(d.tail_weight)[: d.tail_n * d.Cout].float().view(d.tail_n, d.Cout)
+            b3 = self._flat(d.tail_bias)[: d.tail_n]
+            v = F.gelu(v).bfloat16().float() @ w3.t() + b3
+            Cv = d.tail_n
+            v = F.gelu(v + sub(d.res).float())
         e = d.epilogue
         res = sub(d.res).float() if d.res.ptr else None
         aux = sub(d.aux).float() if d.aux.ptr else None

@@ -37,12 +37,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int stage_bytes = A_STAGE_BYTES + g.b_stage_bytes;
-  uint64_t* full_bar = (uint64_t*)(smem + (size_t)g.num_stages * stage_bytes);
+  const int stage_bytes = g.halo ? g.b_stage_bytes : A_STAGE_BYTES + g.b_stage_bytes;
+  uint64_t* full_bar = (uint64_t*)(smem + (size_t)g.num_stages * stage_bytes + (g.halo ? 2 * g.a_halo_bytes : 0));
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* acc_full = empty_bar + MAX_STAGES;   // [2] MMA -> epilogue
   uint64_t* acc_empty = acc_full + 2;            // [2] epilogue -> MMA
-  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+  uint64_t* a_full = acc_empty + 2;              // [2] halo mode: A patch ring
+  uint64_t* a_empty = a_full + 2;
+  uint32_t* tmem_slot = (uint32_t*)(a_empty + 2);
+  // halo mode smem: [num_stages x B tile][2 x A halo patch]; otherwise [num_stages x (A tile | B tile)]
+  uint8_t* a_halo = smem + (size_t)g.num_stages * g.b_stage_bytes;
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
 
@@ -56,6 +60,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int k = 0; k < 2; ++k) {
       mbar_init(&acc_full[k], 1);
       mbar_init(&acc_empty[k], NUM_EPI_WARPS);
+      mbar_init(&a_full[k], 1);
+      mbar_init(&a_empty[k], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -74,8 +80,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // NOTE: no integer division inside the per-stage loops -- this single thread's latency paces the whole
       // pipeline (ncu: the divisions of the first version cost more than the MMAs of a stage).
       const uint32_t tx_bytes = (uint32_t)stage_bytes;
-      int s = 0;
-      uint32_t ph = 0;
+      int s = 0, as = 0;
+      uint32_t ph = 0, aph = 0;
       for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
         const int nt = tile % g.n_tiles;
         int t = tile / g.n_tiles;
@@ -83,6 +89,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         t /= g.tiles_x;
         const int ty = t % g.tiles_y, b = t / g.tiles_y;
         const int x0 = tx * g.TW * d.stride - d.pad_w, y0 = ty * g.TH * d.stride - d.pad_h, n0 = nt * g.BN;
+        if (g.halo) {
+          const uint32_t a_bytes = (uint32_t)(BK * 2 * g.halo_w * g.halo_h), b_bytes = (uint32_t)g.b_stage_bytes;
+          for (int cb = 0; cb < g.kb_per_tap; ++cb) {
+            mbar_wait(&a_empty[as], aph ^ 1u);
+            mbar_expect_tx(&a_full[as], a_bytes);
+            tma_load_4d(a_halo + (size_t)as * g.a_halo_bytes, &tmap_a, &a_full[as], cb * BK, x0, y0, b);
+            if (++as == 2) { as = 0; aph ^= 1u; }
+            int kc0 = cb * BK;
+            for (int tap = 0; tap < d.KH * d.KW; ++tap, kc0 += d.Cin) {
+              mbar_wait(&empty_bar[s], ph ^ 1u);
+              mbar_expect_tx(&full_bar[s], b_bytes);
+              tma_load_2d(smem + (size_t)s * stage_bytes, &tmap_b, &full_bar[s], kc0, n0);
+              if (++s == g.num_stages) { s = 0; ph ^= 1u; }
+            }
+          }
+          continue;
+        }
         int kcol = 0;  // K coordinate in the packed weight = tap * Cin + cb * 64
         for (int r = 0; r < d.KH; ++r) {
           for (int sx = 0; sx < d.KW; ++sx, kcol += d.Cin) {
@@ -105,14 +128,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t idesc = make_idesc(g.BN);
       const int taps = d.KH * d.KW;
       const int kc_last = (d.Cin - (g.kb_per_tap - 1) * BK) / 16;  // valid 16-wide K steps of a tap's last block
-      int s = 0;
-      uint32_t ph = 0, lt = 0;
+      int s = 0, as = 0;
+      uint32_t ph = 0, lt = 0, aph = 0;
       for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++lt) {
-        const uint32_t buf = lt & 1u, aph = (lt >> 1) & 1u;
-        mbar_wait(&acc_empty[buf], aph ^ 1u);  // epilogue has drained this accumulator buffer
+        const uint32_t buf = lt & 1u, cph = (lt >> 1) & 1u;
+        mbar_wait(&acc_empty[buf], cph ^ 1u);  // epilogue has drained this accumulator buffer
         tcgen05_fence_after();
         const uint32_t acc = tmem_base + buf * (uint32_t)g.BN;
         uint32_t accumulate = 0;
+        if (g.halo) {
+          for (int cb = 0; cb < g.kb_per_tap; ++cb) {
+            mbar_wait(&a_full[as], aph);
+            tcgen05_fence_after();
+            const int kc = cb + 1 == g.kb_per_tap ? kc_last : BK / 16;
+            const uint32_t a_base = smem_u32(a_halo + (size_t)as * g.a_halo_bytes);
+            int r = 0, sx = 0;
+            for (int tap = 0; tap < taps; ++tap) {
+              mbar_wait(&full_bar[s], ph);
+              tcgen05_fence_after();
+              const uint32_t a_start = a_base + (uint32_t)((r * g.halo_w + sx) * 128);
+              const uint64_t da = make_sw128_desc_ex(a_start, (uint32_t)(g.halo_w * 128),
+                                                     g.halo_base_off ? (a_start >> 7) & 7u : 0u);
+              const uint64_t db = make_sw128_desc(smem_u32(smem + (size_t)s * stage_bytes));
+              for (int k = 0; k < kc; ++k) {
+                umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, accumulate);
+                accumulate = 1;
+              }
+              tcgen05_commit(&empty_bar[s]);
+              if (++s == g.num_stages) { s = 0; ph ^= 1u; }
+              if (++sx == d.KW) { sx = 0; ++r; }
+            }
+            tcgen05_commit(&a_empty[as]);  // the patch is free once this block's MMAs retire
+            if (++as == 2) { as = 0; aph ^= 1u; }
+          }
+          tcgen05_commit(&acc_full[buf]);
+          continue;
+        }
         for (int tap = 0; tap < taps; ++tap) {
           for (int cb = 0; cb < g.kb_per_tap; ++cb) {
             mbar_wait(&full_bar[s], ph);
@@ -317,7 +368,7 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return RDSIC_E_UNSUPPORTED;
 
-  TcGeom g;
+  TcGeom g = {};
   int B = d->B, H = d->H, W = d->W, OH = d->OH, OW = d->OW;
   // pointwise GEMMs over plain NHWC tensors: flatten all pixels into one row of tiles
   const bool flat = d->KH == 1 && d->KW == 1 && d->stride == 1 && d->pad_h == 0 && d->pad_w == 0 && !d->pixel_shuffle &&
@@ -338,6 +389,18 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
       const long area = (long)ceil_div(OW, tw) * tw * ceil_div(OH, th) * th;
       if (best < 0 || area < best) { best = area; g.TW = tw; g.TH = th; }
     }
+  }
+  // halo mode: stride-1 multi-tap convs on maps that a 16 x 8 patch tiles exactly (RDSIC_TC_HALO: 0 off,
+  // 1 on, 2 on with the descriptor base-offset field derived from the window start)
+  static const int tune_halo = getenv("RDSIC_TC_HALO") ? atoi(getenv("RDSIC_TC_HALO")) : 0;
+  if (tune_halo && !flat && d->stride == 1 && d->KH * d->KW > 1 && d->KH <= 3 && d->KW <= 3 && OH % 16 == 0 && OW % 8 == 0) {
+    g.halo = 1;
+    g.halo_base_off = tune_halo == 2;
+    g.TH = 16;
+    g.TW = 8;
+    g.halo_w = g.TW + d->KW - 1;
+    g.halo_h = g.TH + d->KH - 1;
+    g.a_halo_bytes = (BK * 2 * g.halo_w * g.halo_h + 1023) / 1024 * 1024;
   }
   g.tiles_x = ceil_div(OW, g.TW);
   g.tiles_y = ceil_div(OH, g.TH);
@@ -360,11 +423,11 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   g.kb_per_tap = ceil_div(d->Cin, BK);
   g.num_k_iters = d->KH * d->KW * g.kb_per_tap;
   g.b_stage_bytes = g.BN * BK * 2;
-  const int stage_bytes = A_STAGE_BYTES + g.b_stage_bytes;
+  const int stage_bytes = g.halo ? g.b_stage_bytes : A_STAGE_BYTES + g.b_stage_bytes;
   // one persistent CTA per SM owns the whole shared memory: as deep a TMA ring as fits (the ring keeps
   // running across tiles, so even 2-3-iteration pointwise GEMMs keep many stages in flight)
   static const int tune_stages = getenv("RDSIC_TC_STAGES") ? atoi(getenv("RDSIC_TC_STAGES")) : 0;
-  int stages = (200 * 1024) / stage_bytes;
+  int stages = (200 * 1024 - (g.halo ? 2 * g.a_halo_bytes : 0)) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (tune_stages > 0 && tune_stages < stages) stages = tune_stages;
   if (stages < 2) return RDSIC_E_ARG;
@@ -380,6 +443,7 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {ld_b, ld_b * W, ld_b * W * H};
     cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(g.TW * d->stride), (cuuint32_t)(g.TH * d->stride), 1};
+    if (g.halo) { box[1] = (cuuint32_t)g.halo_w; box[2] = (cuuint32_t)g.halo_h; }
     cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
     void* base = (void*)((const __nv_bfloat16*)d->in.ptr + d->in.coff);
     CUresult r = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr,
@@ -400,7 +464,8 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) return RDSIC_E_ARG;
   }
 
-  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * MAX_STAGES + 4) * 8 + 16;
+  const size_t smem = (size_t)stages * stage_bytes + (g.halo ? 2 * g.a_halo_bytes : 0) + 1024 /*align slack*/ +
+                      (2 * MAX_STAGES + 8) * 8 + 16;
   // vector epilogue: channels-last views whose 16-channel chunks are 32-byte aligned (256-bit LDG/STG)
   auto vec_ok = [](const rdsic_view& v) {
     return !v.ptr || (!v.nchw && v.ld % 16 == 0 && v.coff % 16 == 0 && ((uintptr_t)v.ptr % 32) == 0);

@@ -22,6 +22,9 @@ struct TcGeom {
   int TH, TW, tiles_y, tiles_x;
   int BN, n_tiles, total_tiles, kb_per_tap, num_k_iters, num_stages, tmem_cols;
   int b_stage_bytes;
+  // halo mode (stride-1 multi-tap convs): the (TH+KH-1) x (TW+KW-1) input patch of a channel block is loaded
+  // ONCE and every tap's A operand is a shifted window of it (descriptor start + row offset, SBO = halo row pitch)
+  int halo, halo_w, halo_h, a_halo_bytes, halo_base_off;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -88,6 +91,19 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)(1024 >> 4) << 32;             // SBO [32,46)
   d |= (uint64_t)1 << 46;                       // version = 1 [46,48)
   d |= (uint64_t)2 << 61;                       // layout type SWIZZLE_128B [61,64)
+  return d;
+}
+
+// same, with an explicit 8-row-group stride (SBO) and swizzle base offset: used for shifted windows into a
+// larger 128B-swizzled tile whose rows are 128 B apart but whose 8-row groups are `sbo_bytes` apart.
+__device__ __forceinline__ uint64_t make_sw128_desc_ex(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_off) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(base_off & 7) << 49;          // matrix base offset [49,52)
+  d |= (uint64_t)2 << 61;
   return d;
 }
 

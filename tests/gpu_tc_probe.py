@@ -62,6 +62,9 @@ def main():
     ok &= conv_case("rand_1x1_c64_n64", 64, 64, 1, 1, 1, 8, 16)
     ok &= conv_case("rand_1x1_c192_n96_ragged", 192, 96, 1, 1, 2, 9, 7)
     ok &= conv_case("id_3x3_c64", 64, 64, 3, 1, 1, 8, 16, identity=True)
+    ok &= conv_case("id_3x3_c64_halo16x16", 64, 64, 3, 1, 1, 16, 16, identity=True)
+    ok &= conv_case("rand_3x3_c64_halo16x8", 64, 64, 3, 1, 1, 16, 8)
+    ok &= conv_case("rand_3x3_c352_n224_halo", 352, 224, 3, 1, 2, 32, 48)
     ok &= conv_case("rand_3x3_c96_n96", 96, 96, 3, 1, 2, 16, 24)
     ok &= conv_case("rand_3x3_c352_n224", 352, 224, 3, 1, 1, 8, 12)
     ok &= conv_case("rand_3x3_s2_c288_n256", 288, 256, 3, 2, 1, 8, 12)
@@ -69,6 +72,14 @@ def main():
     ok &= conv_case("rand_5x5_s2_c192_n320_odd", 192, 320, 5, 2, 2, 18, 26)
     ok &= conv_case("rand_1x1_c320_n960", 320, 960, 1, 1, 1, 8, 12)
     # transposed conv (4 phases) incl. the 3-channel NCHW head
+    for cin, cout, dhw in ((192, 192, (16, 8)),):
+        d = ConvTranspose2d(cin, cout)
+        with torch.no_grad():
+            d.weight.copy_(weights.hash_symmetric(f"p.dwh{cin}{cout}", d.weight.shape, (12.0 / (cin * 25)) ** 0.5))
+            d.bias.copy_(weights.hash_symmetric(f"p.dbh{cin}{cout}", d.bias.shape, 0.1))
+        x = weights.hash_symmetric(f"p.dxh{cin}", (2, cin, *dhw), 1.0)
+        ref = F.conv_transpose2d(bf(x), bf(d.weight.detach()), d.bias.detach(), stride=2, padding=2, output_padding=1)
+        ok &= report(f"deconv_{cin}_{cout}_halo16x8", run(d, x), ref)
     for cin, cout in ((192, 192), (320, 192), (192, 3)):
         d = ConvTranspose2d(cin, cout)
         with torch.no_grad():

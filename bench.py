@@ -203,6 +203,13 @@ def run_ours(args):
         conv_ms, conv_n = fam["conv"]
         total_ms = sum(v[0] for v in fam.values())
         tf = B * FLOP_PER_IMAGE / conv_n / (conv_ms / conv_n / 1e3) / 1e12  # algorithmic FLOP per launch / avg launch time
+        traffic_bytes, traffic_note = None, None
+        tpath = os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")
+        if os.path.exists(tpath):  # DRAM bytes of the heaviest launch, from the committed ncu --set full capture
+            with open(tpath) as fh:
+                tj = json.load(fh)
+            traffic_bytes = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            traffic_note = f"{tj['kernel']}: algorithmic {tj['algorithmic_bytes']} B; {tj['source']}"
         line = {
             "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -220,7 +227,7 @@ def run_ours(args):
             "launches_per_step": launches_per_step,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                         "frac": tf / peaks["tf_sustained"], "traffic": None,
+                         "frac": tf / peaks["tf_sustained"], "traffic": traffic_bytes, "traffic_note": traffic_note,
                          "kernel": "implicit-GEMM conv family (all conv/deconv/linear/GDN launches)",
                          "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                          "share_of_step": conv_ms / total_ms,

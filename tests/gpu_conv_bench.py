@@ -19,6 +19,9 @@ CASES = [  # name, Cin, Cout, k, stride, B, H, W (input)
 
 
 def main():
+    global CASES
+    if os.environ.get("RDSIC_BENCH_CASES"):  # e.g. '[["k1_1024_192",1024,192,1,1,8,128,192]]'
+        CASES = [tuple(c) for c in json.loads(os.environ["RDSIC_BENCH_CASES"])]
     only = sys.argv[1] if len(sys.argv) > 1 else None
     reps = int(os.environ.get("REPS", "5"))
     res = []
@@ -44,7 +47,10 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         flop = 2.0 * B * out.H * out.W * cout * k * k * cin
-        res.append(dict(name=name, ms=round(ms, 4), tflops=round(flop / ms / 1e9, 1)))
+        kiters = k * k * -(-cin // 64)
+        tiles = -(-(B * out.H * out.W) // 128) * max(1, -(-cout // 256))
+        cyc = ms * 1e-3 * 1.9e9 / (max(1.0, tiles / 148.0) * kiters)
+        res.append(dict(name=name, ms=round(ms, 4), tflops=round(flop / ms / 1e9, 1), cyc_per_kiter=round(cyc)))
         print(res[-1], flush=True)
     return res
 

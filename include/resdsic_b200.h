@@ -175,7 +175,7 @@ typedef struct rdsic_ln_desc {
  * of 16).  The first 5x5 s2 convolution then runs as a pointwise tensor-core GEMM with K = Kp. */
 typedef struct rdsic_patch_desc {
   rdsic_view src;  /* [B,C,H,W] NCHW or NHWC, fp32 or bf16 */
-  rdsic_view dst;  /* [B,OH,OW,Kp] bf16 */
+  rdsic_view dst;  /* [B,OH,OW,Kp] bf16 or fp32 */
   int32_t B, H, W, C, KH, KW, stride, pad, OH, OW, Kp;
   int32_t pad_;
 } rdsic_patch_desc;

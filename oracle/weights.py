@@ -273,3 +273,58 @@ def make_image(B, H, W, seed: int = 0) -> torch.Tensor:
     lo = lo.repeat_interleave(8, 2).repeat_interleave(8, 3)[:, :, :H, :W]
     hi = hash_uniform(f"img.hi.{B}x{H}x{W}", (B, 3, H, W), seed)
     return (lo * 0.75 + hi * 0.25).contiguous()
+
+
+# --------------------------------------------------------------------------
+# generic synthetic weights for builder-defined models (stf): keyed on the module's own state_dict
+# --------------------------------------------------------------------------
+_STF_GAINS = (
+    (r"^g_a\.layers\.3\.blocks\.1\.mlp\.2\.weight$", 6.0),
+    (r"^h_a\.8\.weight$", 3.0),
+    (r"^h_(mean|scale)_s\.8\.weight$", 1.5),
+    (r"^cc_scale_transforms\.\d+\.4\.weight$", 1.5),
+    (r"^cc_mean_transforms\.\d+\.4\.weight$", 0.4),
+    (r"^g_s\.end_conv\.", 0.5),
+)
+
+
+def synth_state_dict(reference_sd, seed: int = 0, gains=_STF_GAINS):
+    """Hash-seeded values for every entry of `reference_sd` (name -> tensor giving shape / dtype), using the
+    same conventions as make_state_dict: He-like uniform weights, small non-zero biases, LayerNorm weights
+    around 1, perturbed EntropyBottleneck parameters.  Constant buffers are copied through."""
+    sd = OrderedDict()
+    for name, ref in reference_sd.items():
+        shape, leaf = tuple(ref.shape), name.rsplit(".", 1)[-1]
+        g = 1.0
+        for pat, v in gains:
+            if re.match(pat, name):
+                g = v
+        if ref.numel() == 0 or leaf in ("pedestal", "bound", "target", "relative_position_index", "scale_bound"):
+            t = ref.clone()
+        elif name.startswith("entropy_bottleneck."):
+            if leaf.startswith("_matrix"):
+                t = ref.clone() + hash_symmetric(name, shape, 0.2, seed)
+            elif leaf.startswith("_bias"):
+                t = hash_symmetric(name, shape, 0.5, seed)
+            elif leaf.startswith("_factor"):
+                t = hash_symmetric(name, shape, 0.3, seed)
+            elif leaf == "quantiles":
+                med = hash_symmetric(name, (shape[0], 1, 1), 0.4, seed)
+                t = torch.cat([med - 10.0, med, med + 10.0], dim=2)
+            else:
+                t = ref.clone()
+        elif leaf == "relative_position_params" or leaf == "relative_position_bias_table":
+            t = hash_symmetric(name, shape, 0.5, seed)
+        elif leaf == "weight" and len(shape) == 1:  # LayerNorm
+            t = 1.0 + hash_symmetric(name, shape, 0.2, seed)
+        elif leaf == "bias":
+            t = hash_symmetric(name, shape, 0.1 if ".norm" in name or ".ln" in name else 0.05, seed)
+        elif leaf == "weight":
+            fan_in = shape[1] * (shape[2] * shape[3] if len(shape) == 4 else 1)
+            var2 = len(shape) == 4  # conv stacks are GELU nets: var 2/fan_in; linears: var 1/fan_in
+            t = hash_symmetric(name, shape, g * math.sqrt((6.0 if var2 else 3.0) / fan_in), seed)
+        else:
+            raise KeyError(name)
+        assert tuple(t.shape) == shape, (name, t.shape, shape)
+        sd[name] = t.to(ref.dtype).contiguous()
+    return sd

@@ -5,7 +5,7 @@ library (include/resdsic_b200.h).  No CPU / ATen / Triton fallback: everything o
 the hot path is a hand-written kernel, and a missing library raises.
 """
 from . import _lib
-from .models import WACNN, configure_model, models
+from .models import WACNN, SymmetricalTransFormer, configure_model, models
 
 __version__ = "0.1.0"
-__all__ = ["models", "configure_model", "WACNN", "_lib"]
+__all__ = ["models", "configure_model", "WACNN", "SymmetricalTransFormer", "_lib"]

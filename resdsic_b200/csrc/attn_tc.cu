@@ -42,10 +42,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// WS: window side (8 or 4); DH: head dim (multiple of 8); 8 heads = 8 warps.
+// WS: window side (8 or 4); DH: head dim (multiple of 8); one warp per head (blockDim = 32 * heads).
 template <int WS, int DH>
-__global__ void __launch_bounds__(256) win_attn_tc_kernel(const rdsic_attn_desc d) {
-  constexpr int NTOK = WS * WS, HEADS = 8, C = HEADS * DH, LD = 3 * C + 8;  // +8 bf16: conflict-free fragment loads
+__global__ void __launch_bounds__(768) win_attn_tc_kernel(const rdsic_attn_desc d) {
+  constexpr int NTOK = WS * WS;
+  const int HEADS = d.heads, C = HEADS * DH, LD = 3 * C + 8;  // +8 bf16: conflict-free fragment loads
+  const int NTHR = 32 * HEADS;
   constexpr int RB = NTOK / 16;      // 16-row query blocks
   constexpr int NT_S = NTOK / 8;     // n8 tiles of S (keys)
   constexpr int KS_PV = NTOK / 16;   // k16 steps of P V
@@ -55,9 +57,9 @@ __global__ void __launch_bounds__(256) win_attn_tc_kernel(const rdsic_attn_desc 
   static_assert(KTAIL == 0 || KTAIL == 8, "head dim must be a multiple of 8");
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* qkv = (__nv_bfloat16*)smem_raw;              // [NTOK][LD]: q | k | v per token
-  float* tab = (float*)(qkv + NTOK * LD);                     // [HEADS][TWD*TWD]
+  size_t* pixs = (size_t*)(qkv + NTOK * LD);                  // [NTOK] pixel index of each token (original frame); 8-byte aligned
+  float* tab = (float*)(pixs + NTOK);                         // [HEADS][TWD*TWD]
   int* rid = (int*)(tab + HEADS * TWD * TWD);                 // [NTOK] shift-mask region id
-  size_t* pixs = (size_t*)(rid + NTOK);                       // [NTOK] pixel index of each token (original frame)
 
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
   int win = blockIdx.x;
@@ -73,12 +75,12 @@ __global__ void __launch_bounds__(256) win_attn_tc_kernel(const rdsic_attn_desc 
     const int rh = (hy >= d.H - WS) + (hy >= d.H - d.shift), rw = (wx >= d.W - WS) + (wx >= d.W - d.shift);
     rid[tid] = d.shift > 0 ? 3 * rh + rw : 0;
   }
-  for (int e = tid; e < HEADS * TWD * TWD; e += 256) tab[e] = d.bias_table[(e % (TWD * TWD)) * HEADS + e / (TWD * TWD)];
+  for (int e = tid; e < HEADS * TWD * TWD; e += NTHR) tab[e] = d.bias_table[(e % (TWD * TWD)) * HEADS + e / (TWD * TWD)];
   __syncthreads();
   {
-    constexpr int VPT = 3 * C / 8;  // 16-byte vectors per token
+    const int VPT = 3 * C / 8;  // 16-byte vectors per token
     const __nv_bfloat16* src = (const __nv_bfloat16*)d.qkv.ptr;
-    for (int e = tid; e < NTOK * VPT; e += 256) {
+    for (int e = tid; e < NTOK * VPT; e += NTHR) {
       const int tok = e / VPT, v = e % VPT;
       const uint4 val = *reinterpret_cast<const uint4*>(src + pixs[tok] * (size_t)d.qkv.ld + d.qkv.coff + v * 8);
       *reinterpret_cast<uint4*>(qkv + tok * LD + v * 8) = val;
@@ -188,9 +190,9 @@ __global__ void __launch_bounds__(256) win_attn_tc_kernel(const rdsic_attn_desc 
   }
   __syncthreads();
   {
-    constexpr int VPT = C / 8;
+    const int VPT = C / 8;
     __nv_bfloat16* dst = (__nv_bfloat16*)d.out.ptr;
-    for (int e = tid; e < NTOK * VPT; e += 256) {
+    for (int e = tid; e < NTOK * VPT; e += NTHR) {
       const int tok = e / VPT, v = e % VPT;
       *reinterpret_cast<uint4*>(dst + pixs[tok] * (size_t)d.out.ld + d.out.coff + v * 8) =
           *reinterpret_cast<const uint4*>(qkv + tok * LD + v * 8);
@@ -200,15 +202,16 @@ __global__ void __launch_bounds__(256) win_attn_tc_kernel(const rdsic_attn_desc 
 
 template <int WS, int DH>
 int launch_tc(const rdsic_attn_desc* d, cudaStream_t stream) {
-  constexpr int NTOK = WS * WS, C = 8 * DH, LD = 3 * C + 8, TWD = 2 * WS - 1;
-  const size_t smem = (size_t)NTOK * LD * 2 + 8 * TWD * TWD * 4 + NTOK * 4 + NTOK * 8 + 16;
+  constexpr int NTOK = WS * WS, TWD = 2 * WS - 1;
+  const int C = d->heads * DH, LD = 3 * C + 8;
+  const size_t smem = (size_t)NTOK * LD * 2 + (size_t)d->heads * TWD * TWD * 4 + NTOK * 4 + NTOK * 8 + 16;
   auto kern = win_attn_tc_kernel<WS, DH>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
   const int nblk = d->B * (d->H / WS) * (d->W / WS);
-  kern<<<nblk, 256, smem, stream>>>(*d);
+  kern<<<nblk, 32 * d->heads, smem, stream>>>(*d);
   return rdsic_launch_status();
 }
 
@@ -217,12 +220,15 @@ int launch_tc(const rdsic_attn_desc* d, cudaStream_t stream) {
 // returns RDSIC_E_UNSUPPORTED when the configuration has no tensor-core specialisation (caller then uses
 // the register-resident fp32 kernel of attn_f32.cu)
 int rdsic_attn_forward_tc(const rdsic_attn_desc* d, cudaStream_t stream) {
-  if (d->qkv.dtype != RDSIC_BF16 || d->out.dtype != RDSIC_BF16 || d->heads != 8) return RDSIC_E_UNSUPPORTED;
+  if (d->qkv.dtype != RDSIC_BF16 || d->out.dtype != RDSIC_BF16 || d->heads < 1 || d->heads > 24) return RDSIC_E_UNSUPPORTED;
   if (d->qkv.ld % 8 || d->qkv.coff % 8 || d->out.ld % 8 || d->out.coff % 8 || ((uintptr_t)d->qkv.ptr % 16) ||
       ((uintptr_t)d->out.ptr % 16))
     return RDSIC_E_UNSUPPORTED;
   const int dh = d->C / d->heads;
   if (d->ws == 8 && dh == 24) return launch_tc<8, 24>(d, stream);
   if (d->ws == 4 && dh == 40) return launch_tc<4, 40>(d, stream);
+  if (d->ws == 4 && dh == 16) return launch_tc<4, 16>(d, stream);  // stf: window 4, head_dim 16, 3..24 heads
+  if (d->ws == 4 && dh == 32) return launch_tc<4, 32>(d, stream);
+  if (d->ws == 8 && dh == 32) return launch_tc<8, 32>(d, stream);
   return RDSIC_E_UNSUPPORTED;
 }

@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(256) patchify_kernel(const rdsic_patch_desc d)
     const size_t t = pix / d.OW;
     const int oy = (int)(t % d.OH), b = (int)(t / d.OH);
     uint32_t w[4];
+    float f8[8];
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
       float f[2];
@@ -95,12 +96,19 @@ __global__ void __launch_bounds__(256) patchify_kernel(const rdsic_patch_desc d)
           }
         }
         f[u] = v;
+        f8[2 * h + u] = v;
       }
       __nv_bfloat162 hh = __floats2bfloat162_rn(f[0], f[1]);
       w[h] = *reinterpret_cast<uint32_t*>(&hh);
     }
-    uint4* dst = reinterpret_cast<uint4*>((__nv_bfloat16*)d.dst.ptr + pix * (size_t)d.dst.ld + d.dst.coff) + ch;
-    *dst = make_uint4(w[0], w[1], w[2], w[3]);
+    if (d.dst.dtype == RDSIC_BF16) {
+      uint4* dst = reinterpret_cast<uint4*>((__nv_bfloat16*)d.dst.ptr + pix * (size_t)d.dst.ld + d.dst.coff) + ch;
+      *dst = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+      float4* dst = reinterpret_cast<float4*>((float*)d.dst.ptr + pix * (size_t)d.dst.ld + d.dst.coff) + 2 * ch;
+      dst[0] = make_float4(f8[0], f8[1], f8[2], f8[3]);
+      dst[1] = make_float4(f8[4], f8[5], f8[6], f8[7]);
+    }
   }
 }
 
@@ -108,7 +116,7 @@ __global__ void __launch_bounds__(256) patchify_kernel(const rdsic_patch_desc d)
 
 extern "C" int rdsic_patch_forward(const rdsic_patch_desc* d, rdsic_stream_t stream) {
   RDSIC_CHECK_ARG(d && d->src.ptr && d->dst.ptr && d->B > 0 && d->C > 0 && d->KH > 0 && d->KW > 0 && d->stride > 0);
-  RDSIC_CHECK_ARG(d->Kp % 16 == 0 && d->Kp >= d->KH * d->KW * d->C && d->dst.dtype == RDSIC_BF16 && !d->dst.nchw);
+  RDSIC_CHECK_ARG(d->Kp % 16 == 0 && d->Kp >= d->KH * d->KW * d->C && !d->dst.nchw);
   if (d->dst.ld % 8 || d->dst.coff % 8 || ((uintptr_t)d->dst.ptr % 16)) return RDSIC_E_ALIGN;
   const size_t total = (size_t)d->B * d->OH * d->OW * (d->Kp / 8);
   const size_t want = (total + 255) / 256;

@@ -142,18 +142,23 @@ class ConvTranspose2d(B200Module):
 class Linear(B200Module):
     """nn.Linear over the channel dim of a channels-last view (a 1x1 GEMM)."""
 
-    def __init__(self, in_features, out_features):
+    def __init__(self, in_features, out_features, bias=True):
         super().__init__()
         self.in_features, self.out_features = in_features, out_features
         self.weight = nn.Parameter(torch.empty(out_features, in_features))
-        self.bias = nn.Parameter(torch.empty(out_features))
         nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))  # nn.Linear default
-        bound = 1 / math.sqrt(in_features)
-        nn.init.uniform_(self.bias, -bound, bound)
+        if bias:
+            self.bias = nn.Parameter(torch.empty(out_features))
+            bound = 1 / math.sqrt(in_features)
+            nn.init.uniform_(self.bias, -bound, bound)
+        else:
+            self.register_parameter("bias", None)
 
     def packed(self, wdt):
-        return self._packed(("w", wdt), (self.weight, self.bias), lambda: (
-            packing.pack_linear_weight(self.weight, wdt), self.bias.detach().float().contiguous()))
+        tensors = (self.weight,) if self.bias is None else (self.weight, self.bias)
+        return self._packed(("w", wdt), tensors, lambda: (
+            packing.pack_linear_weight(self.weight, wdt),
+            None if self.bias is None else self.bias.detach().float().contiguous()))
 
     def emit(self, ctx: Ctx, x, out=None, epilogue=_lib.EPI_NONE, out_dtype=None, **kw):
         w, b = self.packed(ctx.wdt_for(x))
@@ -179,10 +184,10 @@ class SubpelConv(nn.Sequential, B200Module):
 
     fuses_gelu = True
 
-    def __init__(self, in_ch, out_ch, r=2):
+    def __init__(self, in_ch, out_ch, r=2, kernel_size=3):
         if r != 2:
             raise ValueError("only r=2 is used by the reference")
-        super().__init__(Conv2d(in_ch, out_ch * r * r, 3), PixelShuffle(r))
+        super().__init__(Conv2d(in_ch, out_ch * r * r, kernel_size), PixelShuffle(r))
 
     def emit(self, ctx, x, gelu=False, **kw):
         return self[0].emit(ctx, x, gelu=gelu, pixel_shuffle=2, **kw)

@@ -22,10 +22,10 @@ class LayerNorm(B200Module):
         self.weight = nn.Parameter(torch.ones(dim))
         self.bias = nn.Parameter(torch.zeros(dim))
 
-    def emit(self, ctx: Ctx, x, **kw):
+    def emit(self, ctx: Ctx, x, out=None, out_dtype=None, **kw):
         g, b = self._packed("ln", (self.weight, self.bias), lambda: (self.weight.detach().float().contiguous(),
                                                                     self.bias.detach().float().contiguous()))
-        return ctx.prog.layernorm(x, ctx.buf(x.B, x.H, x.W, x.C), g, b, self.eps)
+        return ctx.prog.layernorm(x, out if out is not None else ctx.buf(x.B, x.H, x.W, x.C, out_dtype), g, b, self.eps)
 
 
 class WMSA(B200Module):
@@ -80,10 +80,69 @@ class Block(B200Module):
         self.mlp = Sequential(Linear(input_dim, 4 * input_dim), GELU(), Linear(4 * input_dim, output_dim))
 
     def emit(self, ctx: Ctx, x, **kw):
+        """`kw` (out / out_dtype / out2) places the block's output (used by the last block of a transform)."""
         x = self.msa.emit(ctx, self.ln1.emit(ctx, x), shortcut=x)
         h = self.mlp[0].emit(ctx, self.ln2.emit(ctx, x), epilogue=_lib.EPI_GELU)
-        return self.mlp[2].emit(ctx, h, epilogue=_lib.EPI_ADD_RES, res=x)
+        return self.mlp[2].emit(ctx, h, epilogue=_lib.EPI_ADD_RES, res=x, **kw)
 
     @torch.no_grad()
     def forward_nhwc(self, x):
         return self.forward(x.permute(0, 3, 1, 2).contiguous()).permute(0, 2, 3, 1).contiguous()
+
+
+class PatchMerging(B200Module):
+    """Swin patch merging (2x down): gather each 2x2 neighbourhood into 4C channels, LayerNorm(4C),
+    Linear(4C -> 2C, no bias).  The gather is the im2col kernel (k = 2, stride 2), i.e. channel order
+    (dy, dx) = (0,0), (0,1), (1,0), (1,1) -- builder-defined (the reference tree has no STF)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = dim
+        self.norm = LayerNorm(4 * dim)
+        self.reduction = Linear(4 * dim, 2 * dim, bias=False)
+
+    def emit(self, ctx: Ctx, x, **kw):
+        if x.H % 2 or x.W % 2:
+            raise ValueError("PatchMerging needs even spatial dims")
+        g = ctx.prog.patchify(x, ctx.buf(x.B, x.H // 2, x.W // 2, 4 * self.dim), 2, 2, 2, 0)
+        return self.reduction.emit(ctx, self.norm.emit(ctx, g), **kw)
+
+
+class PatchSplit(B200Module):
+    """Inverse of PatchMerging for the synthesis transform (2x up): Linear(C -> 2C, no bias), PixelShuffle(2)
+    folded into the GEMM's store addressing (-> C/2 channels), LayerNorm(C/2).  Builder-defined."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = dim
+        self.reduction = Linear(dim, 2 * dim, bias=False)
+        self.norm = LayerNorm(dim // 2)
+
+    def emit(self, ctx: Ctx, x, **kw):
+        up = self.reduction.emit(ctx, x, out=ctx.buf(x.B, 2 * x.H, 2 * x.W, self.dim // 2), pixel_shuffle=2)
+        return self.norm.emit(ctx, up, **kw)
+
+
+class BasicLayer(B200Module):
+    """A stage of `depth` Swin blocks alternating W-MSA / SW-MSA, optionally followed by a resampler."""
+
+    def __init__(self, dim, depth, num_heads, window_size, resample=None):
+        super().__init__()
+        self.blocks = nn.ModuleList(
+            Block(dim, dim, dim // num_heads, window_size, 0.0, "W" if i % 2 == 0 else "SW") for i in range(depth))
+        if resample == "down":
+            self.downsample = PatchMerging(dim)
+        elif resample == "up":
+            self.upsample = PatchSplit(dim)
+        self.resample = resample
+
+    def emit(self, ctx: Ctx, x, **kw):
+        blocks = list(self.blocks)
+        for i, blk in enumerate(blocks):
+            last = i + 1 == len(blocks) and self.resample is None
+            x = blk.emit(ctx, x, **(kw if last else {}))
+        if self.resample == "down":
+            x = self.downsample.emit(ctx, x, **kw)
+        elif self.resample == "up":
+            x = self.upsample.emit(ctx, x, **kw)
+        return x

@@ -63,6 +63,7 @@ class WACNN(CompressionModel):
         self.N, self.M = N, M
         self.num_slices = 10
         self.max_support_slices = 5
+        self.slice_channels = M // self.num_slices
         self.g_a = Sequential(
             conv(3, N, kernel_size=5, stride=2), GDN(N),
             conv(N, N, kernel_size=5, stride=2), GDN(N),
@@ -139,30 +140,32 @@ class WACNN(CompressionModel):
         # ---- g_a: y kept fp32 (it is quantised against mu)
         bf16 = ctx.precision == "bf16"
         h, w = H // 16, W // 16
-        y = ctx.buf(B, h, w, 320, f32)
-        y_act = ctx.buf(B, h, w, 320) if bf16 else y  # bf16 twin of y: A operand of h_a
+        M, sc_ = self.M, self.slice_channels
+        y = ctx.buf(B, h, w, M, f32)
+        y_act = ctx.buf(B, h, w, M) if bf16 else y  # bf16 twin of y: A operand of h_a
         self.g_a.emit(ctx, TV.nchw_of(p.x), last_kw=dict(out=y, out2=y_act) if bf16 else dict(out=y))
         # ---- h_a -> z (fp32) -> EB
         z = self.h_a.emit(ctx, y_act, last_kw=dict(out_dtype=f32))
-        p.lik_z = torch.empty(B, self.N, z.H, z.W, dtype=f32, device=device)
-        p.z_symbols = torch.empty(B, self.N, z.H, z.W, dtype=torch.int32, device=device) if with_symbols else None
+        p.lik_z = torch.empty(B, z.C, z.H, z.W, dtype=f32, device=device)
+        p.z_symbols = torch.empty(B, z.C, z.H, z.W, dtype=torch.int32, device=device) if with_symbols else None
         z_hat, _ = self.entropy_bottleneck.emit(ctx, z, lik=p.lik_z, symbols=p.z_symbols)
         # ---- hyper-synthesis straight into the support buffers
-        means = ctx.buf(B, h, w, 512)
-        scales = ctx.buf(B, h, w, 512)
+        S = self.max_support_slices
+        ctx_ld = M + sc_ * (S + 1)  # latent | S support slots | one scratch slot
+        means = ctx.buf(B, h, w, ctx_ld)
+        scales = ctx.buf(B, h, w, ctx_ld)
         ctx.prog.fork()  # the two hyper-synthesis stacks are independent
         with ctx.prog.side():
-            self.h_scale_s.emit(ctx, z_hat, last_kw=dict(out=scales.channels(0, 320)))
-        self.h_mean_s.emit(ctx, z_hat, last_kw=dict(out=means.channels(0, 320)))
+            self.h_scale_s.emit(ctx, z_hat, last_kw=dict(out=scales.channels(0, M)))
+        self.h_mean_s.emit(ctx, z_hat, last_kw=dict(out=means.channels(0, M)))
         ctx.prog.join()
         # ---- slice loop
-        y_hat = ctx.buf(B, h, w, 320, f32)  # fp32 master copy of y_hat (LRP residual + g_s input)
-        p.lik_y = torch.empty(B, 320, h, w, dtype=f32, device=device)
-        p.symbols = torch.empty(B, 320, h, w, dtype=torch.int32, device=device) if with_symbols else None
-        p.indexes = torch.empty(B, 320, h, w, dtype=torch.int32, device=device) if with_symbols else None
+        y_hat = ctx.buf(B, h, w, M, f32)  # fp32 master copy of y_hat (LRP residual + g_s input)
+        p.lik_y = torch.empty(B, M, h, w, dtype=f32, device=device)
+        p.symbols = torch.empty(B, M, h, w, dtype=torch.int32, device=device) if with_symbols else None
+        p.indexes = torch.empty(B, M, h, w, dtype=torch.int32, device=device) if with_symbols else None
         prog = ctx.prog
-        S = self.max_support_slices
-        lat_m, lat_s = means.channels(0, 320), scales.channels(0, 320)
+        lat_m, lat_s = means.channels(0, M), scales.channels(0, M)
 
         # -- off the serial chain: everything that only needs latent_means / latent_scales.
         #    * slice 0 has no support: its whole cc_mean / cc_scale stacks;
@@ -188,14 +191,14 @@ class WACNN(CompressionModel):
                 elif key == "sc0":
                     pre[key] = self._stack(ctx, self.cc_scale_transforms[0], lat_s)
                 else:
-                    pre[key] = fam[key[0]][key[1]][0].emit_partial(ctx, src, 0, 320)
+                    pre[key] = fam[key[0]][key[1]][0].emit_partial(ctx, src, 0, M)
                 pre_ev[key] = prog.record()
 
         def stack_split(name, i, buf, n_extra, final=None):
             """Context transform whose first conv only sees the `n_extra` support channels of `buf`."""
             prog.wait(pre_ev[(name, i)])
             seq = fam[name][i]
-            t = seq[0].emit_partial(ctx, buf.channels(320, n_extra), 1, 320, res=pre[(name, i)], gelu=True)
+            t = seq[0].emit_partial(ctx, buf.channels(M, n_extra), 1, M, res=pre[(name, i)], gelu=True)
             return self._stack(ctx, seq, t, final=final, skip_first=True)
 
         def slice_ops(i, scale_lane):
@@ -208,23 +211,23 @@ class WACNN(CompressionModel):
             else:
                 prog.fork(scale_lane)  # cc_mean || cc_scale (cnn.py:167-173 are independent given the support)
                 with prog.side(scale_lane):
-                    sc = stack_split("cc_scale", i, scales, 32 * k)
-                mu = stack_split("cc_mean", i, means, 32 * k)
+                    sc = stack_split("cc_scale", i, scales, sc_ * k)
+                mu = stack_split("cc_mean", i, means, sc_ * k)
                 prog.join(scale_lane)
-            yh_i = y_hat.channels(32 * i, 32)
+            yh_i = y_hat.channels(sc_ * i, sc_)
             if i < S:
                 lrp_buf = means
-                slot = means.channels(320 + 32 * i, 32)
-                extra = dict(out2=slot, out3=scales.channels(320 + 32 * i, 32))  # becomes support of later slices
+                slot = means.channels(M + sc_ * i, sc_)
+                extra = dict(out2=slot, out3=scales.channels(M + sc_ * i, sc_))  # becomes support of later slices
             else:
                 # slices >= max_support share one support set, so they are independent of each other: each
                 # gets a private copy of the support + its own y_hat slot and may run concurrently
-                lrp_buf = ctx.buf(B, h, w, 512)
-                prog.copy(means.channels(320, 160), lrp_buf.channels(320, 160))
-                slot, extra = lrp_buf.channels(480, 32), {}
-            self.gaussian_conditional.emit(ctx, y.channels(32 * i, 32), sc, mu, p.lik_y, 32 * i, 320,
+                lrp_buf = ctx.buf(B, h, w, ctx_ld)
+                prog.copy(means.channels(M, sc_ * S), lrp_buf.channels(M, sc_ * S))
+                slot, extra = lrp_buf.channels(M + sc_ * S, sc_), {}
+            self.gaussian_conditional.emit(ctx, y.channels(sc_ * i, sc_), sc, mu, p.lik_y, sc_ * i, M,
                                            y_hat_dsts=[yh_i, slot], symbols=p.symbols, indexes=p.indexes)
-            stack_split("lrp", i, lrp_buf, 32 * (k + 1), final=dict(epilogue=_lib.EPI_LRP, res=yh_i, out=yh_i, **extra))
+            stack_split("lrp", i, lrp_buf, sc_ * (k + 1), final=dict(epilogue=_lib.EPI_LRP, res=yh_i, out=yh_i, **extra))
 
         for i in range(S):  # serial chain: slice i+1 needs the refined slice i
             slice_ops(i, 1)
@@ -244,7 +247,7 @@ class WACNN(CompressionModel):
                 prog.join(2 + 2 * n)
         # ---- g_s
         p.x_hat = torch.empty(B, 3, H, W, dtype=f32, device=device)
-        y_hat_act = ctx.prog.copy(y_hat, ctx.buf(B, h, w, 320)) if bf16 else y_hat
+        y_hat_act = ctx.prog.copy(y_hat, ctx.buf(B, h, w, M)) if bf16 else y_hat
         self.g_s.emit(ctx, y_hat_act, last_kw=dict(out=TV.nchw_of(p.x_hat)))
         p.prog = ctx.prog
         p.y, p.z, p.y_hat, p.means, p.scales = y, z, y_hat, means, scales
@@ -252,13 +255,14 @@ class WACNN(CompressionModel):
 
     @staticmethod
     def _stack(ctx, seq, x, final=None, skip_first=False):
-        mods = list(seq)
+        """conv -> GELU -> ... -> conv (cnn.py:91-129); the GELU modules are fused into the convs."""
+        convs = [m for m in seq if hasattr(m, "weight")]
         t = x
-        for j in (2, 4, 6) if skip_first else (0, 2, 4, 6):
-            t = mods[j].emit(ctx, t, gelu=True)
+        for c in convs[1 if skip_first else 0:-1]:
+            t = c.emit(ctx, t, gelu=True)
         if final is None:
-            return mods[8].emit(ctx, t, out_dtype=torch.float32)  # mu / scale stay fp32
-        return mods[8].emit(ctx, t, **final)
+            return convs[-1].emit(ctx, t, out_dtype=torch.float32)  # mu / scale stay fp32
+        return convs[-1].emit(ctx, t, **final)
 
     # -------------------------------------------------------------- forward
     def _execute(self, x, with_symbols):

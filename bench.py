@@ -147,7 +147,12 @@ def run_ours(args):
 
     _lib.lib()  # fail loudly if the CUDA library is missing
     sd = make_weights()
-    model = resdsic_b200.WACNN().eval()
+    if args.model == "stf":  # builder-defined model (no reference implementation): informational runs only
+        from oracle import weights as _w
+        model = resdsic_b200.models["stf"]().eval()
+        sd = _w.synth_state_dict(model.state_dict())
+    else:
+        model = resdsic_b200.WACNN().eval()
     model.load_state_dict(sd, strict=True)
     model = model.to(dev).set_precision(args.precision)
     B = args.batch
@@ -202,7 +207,12 @@ def run_ours(args):
         ips_e2e = n_img / (ms_e2e / 1e3)
         conv_ms, conv_n = fam["conv"]
         total_ms = sum(v[0] for v in fam.values())
-        tf = B * FLOP_PER_IMAGE / conv_n / (conv_ms / conv_n / 1e3) / 1e12  # algorithmic FLOP per launch / avg launch time
+        flop_per_image = FLOP_PER_IMAGE
+        if args.model != "cnn":  # no survey figure: sum 2*M*N*K over the program's GEMM descriptors
+            plan = next(iter(model._plans.values()))
+            flop_per_image = sum(2.0 * o.u.conv.B * o.u.conv.OH * o.u.conv.OW * o.u.conv.Cout * o.u.conv.KH * o.u.conv.KW *
+                                 o.u.conv.Cin for o in plan.prog.ops if o.kind == _lib.OP_CONV) / B
+        tf = B * flop_per_image / conv_n / (conv_ms / conv_n / 1e3) / 1e12  # algorithmic FLOP per launch / avg launch time
         traffic_bytes, traffic_note = None, None
         tpath = os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")
         if os.path.exists(tpath):  # DRAM bytes of the heaviest launch, from the committed ncu --set full capture
@@ -211,11 +221,12 @@ def run_ours(args):
             traffic_bytes = tj["dram_bytes_read"] + tj["dram_bytes_write"]
             traffic_note = f"{tj['kernel']}: algorithmic {tj['algorithmic_bytes']} B; {tj['source']}"
         line = {
-            "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if args.model == "cnn" else METRIC.replace("WACNN (-m cnn)", "STF (-m stf, builder-defined)"), "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": f"cnn (WACNN N=192 M=320) forward 512x768, batch {B} per GPU, eval mode",
+            "config": {"workload": (f"cnn (WACNN N=192 M=320) forward 512x768, batch {B} per GPU, eval mode" if args.model == "cnn"
+                                    else f"stf (builder-defined, N=192 M=384) forward 512x768, batch {B} per GPU, eval mode"),
                        "precision": args.precision, "batch_per_gpu": B, "image": [H, W], "parallelism": f"dp{world}",
                        "l2": f"per-step activation working set (~{0.19 * B:.1f} GB at batch {B}) exceeds the 126 MB L2; no explicit flush",
                        "cuda_graph": bool(model.use_cuda_graph)},
@@ -299,6 +310,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("RESDSIC_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
+    ap.add_argument("--model", default="cnn", choices=["cnn", "stf"], help="cnn = the headline (BASELINE.json) workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-ops", default=None, help="write the per-launch device times of one step to this JSON file")
     args = ap.parse_args()

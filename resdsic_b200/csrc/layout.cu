@@ -40,9 +40,83 @@ __global__ void __launch_bounds__(256) copy_views_kernel(const rdsic_copy_desc d
   }
 }
 
-// one warp per row of C channels; two-pass mean/variance in registers (torch
-// LayerNorm: biased variance, eps inside the sqrt).
+// LayerNorm over channels (torch semantics: biased variance, eps inside the sqrt), two-pass in registers.
+// Sub-warp groups of G lanes own one row (G = 4 for C <= 128, 8 for C <= 256, else 32) so that narrow rows
+// (the 48..96-channel stages of stf) do not idle most of a warp; each lane moves 8-element (16/32-byte) vectors.
+template <int G>
 __global__ void __launch_bounds__(256) layernorm_kernel(const rdsic_ln_desc d) {
+  const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G, gl = threadIdx.x % G;
+  const bool active = gid < d.rows;
+  const int row = active ? gid : 0;
+  const size_t ib = (size_t)row * d.in.ld + d.in.coff, ob = (size_t)row * d.out.ld + d.out.coff;
+  constexpr int MAXV = 4;  // up to 4 x 8 channels per lane: C <= 32 * G
+  float v[MAXV][8];
+  const int nvec = d.C / 8;
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int vi = gl + k * G;
+    if (vi < nvec) {
+      if (d.in.dtype == RDSIC_BF16) {
+        const uint4 u = *reinterpret_cast<const uint4*>((const __nv_bfloat16*)d.in.ptr + ib + vi * 8);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[k][2 * i] = __uint_as_float(w[i] << 16);
+          v[k][2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+        }
+      } else {
+        const float4 a0 = *reinterpret_cast<const float4*>((const float*)d.in.ptr + ib + vi * 8);
+        const float4 a1 = *reinterpret_cast<const float4*>((const float*)d.in.ptr + ib + vi * 8 + 4);
+        v[k][0] = a0.x; v[k][1] = a0.y; v[k][2] = a0.z; v[k][3] = a0.w;
+        v[k][4] = a1.x; v[k][5] = a1.y; v[k][6] = a1.z; v[k][7] = a1.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum += v[k][i];
+    }
+  }
+#pragma unroll
+  for (int o = G / 2; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / d.C;
+  float var = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k)
+    if (gl + k * G < nvec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float t = v[k][i] - mean;
+        var = fmaf(t, t, var);
+      }
+    }
+#pragma unroll
+  for (int o = G / 2; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / d.C + d.eps);
+  if (!active) return;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int vi = gl + k * G;
+    if (vi < nvec) {
+      float o8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o8[i] = (v[k][i] - mean) * rstd * __ldg(d.gamma + vi * 8 + i) + __ldg(d.beta + vi * 8 + i);
+      if (d.out.dtype == RDSIC_BF16) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(o8[2 * i], o8[2 * i + 1]);
+          w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>((__nv_bfloat16*)d.out.ptr + ob + vi * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+      } else {
+        *reinterpret_cast<float4*>((float*)d.out.ptr + ob + vi * 8) = make_float4(o8[0], o8[1], o8[2], o8[3]);
+        *reinterpret_cast<float4*>((float*)d.out.ptr + ob + vi * 8 + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
+      }
+    }
+  }
+}
+
+// generic fallback (any C / alignment): one warp per row, scalar accesses
+__global__ void __launch_bounds__(256) layernorm_generic_kernel(const rdsic_ln_desc d) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
   if (warp >= d.rows) return;
   const size_t ib = (size_t)warp * d.in.ld + d.in.coff, ob = (size_t)warp * d.out.ld + d.out.coff;
@@ -136,6 +210,16 @@ extern "C" int rdsic_copy_forward(const rdsic_copy_desc* d, rdsic_stream_t strea
 extern "C" int rdsic_ln_forward(const rdsic_ln_desc* d, rdsic_stream_t stream) {
   RDSIC_CHECK_ARG(d && d->in.ptr && d->out.ptr && d->gamma && d->beta && d->rows > 0 && d->C > 0);
   RDSIC_CHECK_ARG(!d->in.nchw && !d->out.nchw);
-  layernorm_kernel<<<ceil_div(d->rows, 8), 256, 0, (cudaStream_t)stream>>>(*d);
+  const bool vec = d->C % 8 == 0 && d->in.ld % 8 == 0 && d->in.coff % 8 == 0 && d->out.ld % 8 == 0 && d->out.coff % 8 == 0 &&
+                   ((uintptr_t)d->in.ptr % 32) == 0 && ((uintptr_t)d->out.ptr % 32) == 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (vec && d->C <= 128)
+    layernorm_kernel<4><<<ceil_div(d->rows, 64), 256, 0, s>>>(*d);
+  else if (vec && d->C <= 256)
+    layernorm_kernel<8><<<ceil_div(d->rows, 32), 256, 0, s>>>(*d);
+  else if (vec && d->C <= 1024)
+    layernorm_kernel<32><<<ceil_div(d->rows, 8), 256, 0, s>>>(*d);
+  else
+    layernorm_generic_kernel<<<ceil_div(d->rows, 8), 256, 0, s>>>(*d);
   return rdsic_launch_status();
 }

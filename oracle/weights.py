@@ -179,15 +179,30 @@ _GAINS = (
 )
 
 
-def _layer_gain(name):
+# "lowrate" profile: the same weights with the latent / hyper-latent amplitudes scaled down, so that most
+# symbols are zero (bpp ~4 instead of ~14 on the synthetic images) -- the regime a trained codec operates in,
+# and the one on which the bf16 tolerances of BASELINE.json (x_hat 1e-2, bpp 0.1 %, PSNR 0.02 dB) are asserted.
+_LOWRATE = (
+    (r"^g_a\.7\.weight$", 0.25),
+    (r"^h_a\.8\.weight$", 0.5),
+    (r"^h_(mean|scale)_s\.8\.weight$", 0.5),
+    (r"^cc_(mean|scale)_transforms\.\d\.8\.weight$", 0.5),
+)
+
+
+def _layer_gain(name, profile="stress"):
     g = 1.0
     for pat, v in _GAINS:
         if re.match(pat, name):
             g = v  # last match wins
+    if profile == "lowrate":
+        for pat, v in _LOWRATE:
+            if re.match(pat, name):
+                g *= v
     return g
 
 
-def make_state_dict(seed: int = 0, N=192, M=320, gain: float = 1.0):
+def make_state_dict(seed: int = 0, N=192, M=320, gain: float = 1.0, profile: str = "stress"):
     """Synthetic but *non-degenerate* weights: conv/linear weights are uniform
     with Kaiming-like variance (so activations neither vanish nor explode),
     biases are non-zero, GDN beta/gamma and the EntropyBottleneck parameters
@@ -257,7 +272,7 @@ def make_state_dict(seed: int = 0, N=192, M=320, gain: float = 1.0):
                 fan_in = (shape[0] * shape[2] * shape[3] / 4.0) if is_deconv else shape[1] * shape[2] * shape[3]
             else:
                 fan_in = shape[1]
-            amp = gain * _layer_gain(name) * math.sqrt(6.0 / fan_in)  # var = 2/fan_in (GELU nets)
+            amp = gain * _layer_gain(name, profile) * math.sqrt(6.0 / fan_in)  # var = 2/fan_in (GELU nets)
             t = hash_symmetric(name, shape, amp, seed)
         else:
             raise KeyError(name)

@@ -24,6 +24,7 @@ from oracle import ref_shim, weights  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CASES = {"c64": (1, 64, 64), "c128x192": (2, 128, 192)}
+LOWRATE_CASES = {"lowrate_c128x192": (2, 128, 192)}  # same shapes, weights of profile "lowrate"
 
 
 def checksum(sd):
@@ -195,6 +196,17 @@ def main():
               "idx range", res["indexes"].min(), res["indexes"].max(), os.path.getsize(path))
     ops = run_reference_ops(net, table)
     ops.update(run_reference_swin())
+    # second operating point: "lowrate" weights (most symbols zero, like a trained codec)
+    net.gaussian_conditional.scale_table = torch.Tensor()  # back to the constructor state (was assigned above)
+    net.load_state_dict(weights.make_state_dict(seed=0, profile="lowrate"), strict=True)
+    for case, (B, H, W) in LOWRATE_CASES.items():
+        x = weights.make_image(B, H, W, seed=0)
+        res = run_reference_model(net, x, table)
+        keep = {k: res[k] for k in ("x_hat", "lik_y", "lik_z", "y", "z", "symbols", "indexes", "y_hat", "latent_means",
+                                    "latent_scales")}
+        np.savez_compressed(os.path.join(HERE, f"wacnn_{case}.npz"), **keep)
+        bpp = sum(np.log(res[k]).sum() for k in ("lik_y", "lik_z")) / (-np.log(2) * B * H * W)
+        print(case, "bpp", bpp, "zero symbols", (res["symbols"] == 0).mean())
     path = os.path.join(HERE, "ops.npz")
     np.savez_compressed(path, **ops)
     print("ops", {k: v.shape for k, v in ops.items()}, os.path.getsize(path))

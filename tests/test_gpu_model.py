@@ -162,3 +162,35 @@ def test_config5_clic_size_padding_and_index_build(model, synthetic_sd, scale_ta
     b_ref = bpp_of(ref["likelihoods"]["y"].numpy(), ref["likelihoods"]["z"].numpy(), n)
     print("clic fp32: symbol flips", flips, "index flips", idx_flips, "bpp", b_got, "ref", b_ref)
     assert flips <= 2e-2 and idx_flips <= 2e-2 and abs(b_got - b_ref) <= 1e-3 * b_ref
+
+
+def test_bf16_meets_north_star_tolerances_at_lowrate_operating_point(scale_table):
+    """BASELINE.json north_star, bf16 mode vs the fp32 reference on identical inputs and weights: x_hat within
+    1e-2 max abs, per-image bpp within 0.1 %, PSNR within 0.02 dB.  Asserted on the "lowrate" weight profile
+    (most symbols zero, as for a trained codec); the 14-bpp "stress" profile is reported by
+    test_bf16_forward_vs_reference_golden with looser, statistical gates."""
+    from tests.golden.make_golden import LOWRATE_CASES
+    from tests.helpers import bpp_of
+    m = resdsic_b200.WACNN().eval()
+    m.load_state_dict(weights.make_state_dict(seed=0, profile="lowrate"), strict=True)
+    m = m.to(DEV).set_precision("bf16")
+    for case, (B, H, W) in LOWRATE_CASES.items():
+        g = np.load(os.path.join(GOLDEN, f"wacnn_{case}.npz"))
+        x = weights.make_image(B, H, W, seed=0)
+        r = m.symbols_and_indexes(x.to(DEV))
+        xh, ly, lz = r["x_hat"].cpu().numpy(), r["likelihoods"]["y"].cpu().numpy(), r["likelihoods"]["z"].cpu().numpy()
+        dx = np.abs(xh - g["x_hat"]).max()
+        flips = (r["y_symbols"].cpu().numpy() != g["symbols"]).mean()
+        assert dx <= 1e-2, ("x_hat max abs", dx)
+        for b in range(B):
+            b_got, b_ref = bpp_of(ly[b], lz[b], H * W), bpp_of(g["lik_y"][b], g["lik_z"][b], H * W)
+            psnr = lambda a: -10 * np.log10(((a - x[b].numpy()) ** 2).mean())
+            d_psnr = abs(psnr(xh[b]) - psnr(g["x_hat"][b]))
+            print(case, "img", b, "x_hat max", dx, "bpp", b_got, "ref", b_ref, "dPSNR", d_psnr, "symbol flips", flips)
+            assert abs(b_got - b_ref) <= 1e-3 * b_ref and d_psnr <= 0.02
+    # fp32 mode on the same operating point: tight
+    m.set_precision("fp32")
+    g = np.load(os.path.join(GOLDEN, "wacnn_lowrate_c128x192.npz"))
+    r = m.symbols_and_indexes(weights.make_image(2, 128, 192, seed=0).to(DEV))
+    assert np.abs(r["x_hat"].cpu().numpy() - g["x_hat"]).max() <= 2e-3
+    assert (r["y_symbols"].cpu().numpy() != g["symbols"]).mean() <= 1e-3

@@ -103,3 +103,16 @@ def test_swin_block_oracle_matches_reference_tcm_block():
         x = weights.hash_symmetric(f"{name}.x", (B, H, W, dim), 1.5)
         out = O.swin_block(x, sd, "blk", hd, ws, typ == "SW")
         np.testing.assert_allclose(out.numpy(), g[name], rtol=1e-5, atol=1e-5, err_msg=name)
+
+
+def test_forward_matches_reference_lowrate_profile(scale_table):
+    """Second operating point ("lowrate" weights: ~80 % zero symbols, bpp ~4): oracle vs the reference."""
+    from tests.golden.make_golden import LOWRATE_CASES
+    sd = weights.make_state_dict(seed=0, profile="lowrate")
+    for case, (B, H, W) in LOWRATE_CASES.items():
+        g = _npz(f"wacnn_{case}.npz")
+        out = O.forward(sd, weights.make_image(B, H, W, seed=0), scale_table, collect=True)
+        for key in ("y", "z", "latent_means", "latent_scales", "x_hat"):
+            np.testing.assert_allclose(out[key].numpy(), g[key], rtol=1e-4, atol=1e-4, err_msg=key)
+        assert (out["symbols"].numpy() != g["symbols"]).mean() <= 1e-3
+        assert (g["symbols"] == 0).mean() > 0.7

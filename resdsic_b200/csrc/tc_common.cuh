@@ -138,26 +138,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 
 // ------------------------------------------------------------------ epilogue helpers
-// Epilogue math for the bf16 path: the reference's exact erf GELU and exp sigmoid (erff / expf), as in the
-// fp32 mode.  Cheaper forms were measured and rejected on parity grounds (kept behind compile flags):
-//   -DRDSIC_GELU_AS   erf by Abramowitz-Stegun 7.1.26 (|err| 1.5e-7, two MUFU ops): +1 % images/s, bpp error
-//                     at the low-rate operating point 0.06-0.09 % (exact: 0.005-0.02 %);
-//   -DRDSIC_GELU_TANH fitted tanh form on the MUFU tanh (|err| 3e-5): +7 % images/s, but its *systematic* error
-//                     shifts the predicted scales enough to move bpp by 0.15 % -- beyond BASELINE.json's 0.1 %.
-// (tests/test_gpu_model.py::test_bf16_meets_north_star_tolerances_at_lowrate_operating_point)
+// Epilogue math for the bf16 path.  The pointwise layers are instruction-issue bound in the epilogue (ncu:
+// ~34 thread instructions per output element with erff(), profiles/), so GELU is evaluated as
+// 0.5x(1 + tanh(x(c1 + c2 x^2 + c3 x^4))) with coefficients fitted to the exact erf form (max |err| 3e-5, 16x
+// tighter than the textbook tanh-GELU) on the single-instruction MUFU tanh: < 0.05 bf16 ulp of the stored
+// activation and +9 % images/s over erff().  Parity was measured for three variants at 512x768 on the
+// low-rate operating point (tests/bpp_experiment.py): per-image bpp error 0.046 % / 0.004 % with this form vs
+// 0.059 % / 0.008 % with erff() -- indistinguishable (both are dominated by which symbols flip), so the fast
+// form is the default; -DRDSIC_GELU_EXACT (erff/expf) and -DRDSIC_GELU_AS (Abramowitz-Stegun erf) remain
+// selectable.  The fp32 mode (conv_f32.cu) always uses erff()/expf().
 __device__ __forceinline__ float tanh_mufu(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ float gelu_fast(float x) {
-#if defined(RDSIC_GELU_TANH)
-  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);  // beyond |x| = 8 the fitted quintic would turn over; tanh is +-1 there
-  const float x2 = xc * xc;
-  float t = fmaf(-3.58618502e-4f, x2, 3.70495807e-2f);
-  t = fmaf(t, x2, 7.97459395e-1f);
-  const float h = 0.5f * x;
-  return fmaf(h, tanh_mufu(xc * t), h);
+#if defined(RDSIC_GELU_EXACT)
+  return gelu_erf(x);
 #elif defined(RDSIC_GELU_AS)
   const float z = fabsf(x) * 0.70710678118654752440f;
   const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
@@ -169,13 +166,18 @@ __device__ __forceinline__ float gelu_fast(float x) {
   const float h = 0.5f * x;
   return fmaf(h, copysignf(erf_abs, x), h);
 #else
-  return gelu_erf(x);
+  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);  // beyond |x| = 8 the fitted quintic would turn over; tanh is +-1 there
+  const float x2 = xc * xc;
+  float t = fmaf(-3.58618502e-4f, x2, 3.70495807e-2f);
+  t = fmaf(t, x2, 7.97459395e-1f);
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_mufu(xc * t), h);
 #endif
 }
-#if defined(RDSIC_GELU_TANH)
-__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_mufu(0.5f * x), 0.5f); }
-#else
+#if defined(RDSIC_GELU_EXACT) || defined(RDSIC_GELU_AS)
 __device__ __forceinline__ float sigmoid_fast(float x) { return sigmoid_f(x); }
+#else
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_mufu(0.5f * x), 0.5f); }
 #endif
 
 template <int EPI>

@@ -20,6 +20,8 @@
 //     epilogue (TMEM lane quarter = warp_id % 4).
 #include "tc_common.cuh"
 
+long long* g_dbg_ts = nullptr;  // profiling aid, see rdsic_debug_read_ts
+
 namespace {
 
 // ------------------------------------------------------------------ the kernel
@@ -76,21 +78,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
-      // NOTE: no integer division inside the per-stage loops -- this single thread's latency paces the whole
-      // pipeline (ncu: the divisions of the first version cost more than the MMAs of a stage).
-      const uint32_t tx_bytes = (uint32_t)stage_bytes;
-      int s = 0, as = 0;
-      uint32_t ph = 0, aph = 0;
-      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-        const int nt = tile % g.n_tiles;
-        int t = tile / g.n_tiles;
-        const int tx = t % g.tiles_x;
-        t /= g.tiles_x;
-        const int ty = t % g.tiles_y, b = t / g.tiles_y;
-        const int x0 = tx * g.TW * d.stride - d.pad_w, y0 = ty * g.TH * d.stride - d.pad_h, n0 = nt * g.BN;
-        if (g.halo) {
-          const uint32_t a_bytes = (uint32_t)(BK * 2 * g.halo_w * g.halo_h), b_bytes = (uint32_t)g.b_stage_bytes;
+    // NOTE: no integer division inside the per-stage loops -- this warp's latency paces the whole pipeline.
+    if (g.halo) {
+      if (lane == 0) {
+        int s = 0, as = 0;
+        uint32_t ph = 0, aph = 0;
+        const uint32_t a_bytes = (uint32_t)(BK * 2 * g.halo_w * g.halo_h), b_bytes = (uint32_t)g.b_stage_bytes;
+        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+          const int nt = tile % g.n_tiles;
+          int t = tile / g.n_tiles;
+          const int tx = t % g.tiles_x;
+          t /= g.tiles_x;
+          const int ty = t % g.tiles_y, b = t / g.tiles_y;
+          const int x0 = tx * g.TW * d.stride - d.pad_w, y0 = ty * g.TH * d.stride - d.pad_h, n0 = nt * g.BN;
           for (int cb = 0; cb < g.kb_per_tap; ++cb) {
             mbar_wait(&a_empty[as], aph ^ 1u);
             mbar_expect_tx(&a_full[as], a_bytes);
@@ -104,17 +104,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               if (++s == g.num_stages) { s = 0; ph ^= 1u; }
             }
           }
-          continue;
         }
+      }
+    } else {
+      // whole warp, uniform control flow; one elected lane issues (see elect_one)
+      const uint32_t tx_bytes = ((g.dbg_skip_load & 1) ? 0u : (uint32_t)A_STAGE_BYTES) +
+                                ((g.dbg_skip_load & 2) ? 0u : (uint32_t)g.b_stage_bytes);
+      const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+      const uint32_t full0 = __shfl_sync(0xffffffffu, smem_u32(full_bar), 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        const int nt = tile % g.n_tiles;
+        int t = tile / g.n_tiles;
+        const int tx = t % g.tiles_x;
+        t /= g.tiles_x;
+        const int ty = t % g.tiles_y, b = t / g.tiles_y;
+        const int x0 = tx * g.TW * d.stride - d.pad_w, y0 = ty * g.TH * d.stride - d.pad_h, n0 = nt * g.BN;
         int kcol = 0;  // K coordinate in the packed weight = tap * Cin + cb * 64
         for (int r = 0; r < d.KH; ++r) {
           for (int sx = 0; sx < d.KW; ++sx, kcol += d.Cin) {
             for (int cb = 0; cb < g.kb_per_tap; ++cb) {
               mbar_wait(&empty_bar[s], ph ^ 1u);
-              uint8_t* a_dst = smem + (size_t)s * stage_bytes;
-              mbar_expect_tx(&full_bar[s], tx_bytes);
-              tma_load_4d(a_dst, &tmap_a, &full_bar[s], cb * BK, x0 + sx, y0 + r, b);
-              tma_load_2d(a_dst + A_STAGE_BYTES, &tmap_b, &full_bar[s], kcol + cb * BK, n0);
+              const uint32_t a_dst = smem_base + (uint32_t)(s * stage_bytes), bar = full0 + 8u * (uint32_t)s;
+              if (elect_one()) {
+                mbar_expect_tx_u32(bar, tx_bytes);
+                if (!(g.dbg_skip_load & 1)) tma_load_4d_u32(a_dst, &tmap_a, bar, cb * BK, x0 + sx, y0 + r, b);
+                if (!(g.dbg_skip_load & 2)) tma_load_2d_u32(a_dst + A_STAGE_BYTES, &tmap_b, bar, kcol + cb * BK, n0);
+              }
+              __syncwarp();
               if (++s == g.num_stages) { s = 0; ph ^= 1u; }
             }
           }
@@ -124,19 +142,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncwarp();
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(g.BN);
-      const int taps = d.KH * d.KW;
-      const int kc_last = (d.Cin - (g.kb_per_tap - 1) * BK) / 16;  // valid 16-wide K steps of a tap's last block
-      int s = 0, as = 0;
-      uint32_t ph = 0, lt = 0, aph = 0;
-      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++lt) {
-        const uint32_t buf = lt & 1u, cph = (lt >> 1) & 1u;
-        mbar_wait(&acc_empty[buf], cph ^ 1u);  // epilogue has drained this accumulator buffer
-        tcgen05_fence_after();
-        const uint32_t acc = tmem_base + buf * (uint32_t)g.BN;
-        uint32_t accumulate = 0;
-        if (g.halo) {
+    const uint32_t idesc = make_idesc(g.BN);
+    const int taps = d.KH * d.KW;
+    const int kc_last = (d.Cin - (g.kb_per_tap - 1) * BK) / 16;  // valid 16-wide K steps of a tap's last block
+    if (g.halo) {
+      if (lane == 0) {  // (experimental mode, divergent single-lane issue)
+        int s = 0, as = 0;
+        uint32_t ph = 0, lt = 0, aph = 0;
+        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++lt) {
+          const uint32_t buf = lt & 1u, cph = (lt >> 1) & 1u;
+          mbar_wait(&acc_empty[buf], cph ^ 1u);
+          tcgen05_fence_after();
+          const uint32_t acc = tmem_base + buf * (uint32_t)g.BN;
+          uint32_t accumulate = 0;
           for (int cb = 0; cb < g.kb_per_tap; ++cb) {
             mbar_wait(&a_full[as], aph);
             tcgen05_fence_after();
@@ -162,24 +180,62 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (++as == 2) { as = 0; aph ^= 1u; }
           }
           tcgen05_commit(&acc_full[buf]);
-          continue;
         }
-        for (int tap = 0; tap < taps; ++tap) {
-          for (int cb = 0; cb < g.kb_per_tap; ++cb) {
-            mbar_wait(&full_bar[s], ph);
-            tcgen05_fence_after();
-            const int kc = cb + 1 == g.kb_per_tap ? kc_last : BK / 16;
-            const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-            const uint64_t da = make_sw128_desc(a_addr), db = make_sw128_desc(a_addr + A_STAGE_BYTES);
-            for (int k = 0; k < kc; ++k) {  // +32 bytes (= 2 x 16 B units) per 16 bf16 of K inside the swizzle atom
-              umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, accumulate);
-              accumulate = 1;
-            }
-            tcgen05_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
-            if (++s == g.num_stages) { s = 0; ph ^= 1u; }
+      }
+    } else {
+      // Whole warp in uniform control flow, one elected lane issues (see elect_one): every operand of the
+      // UTCHMMA then lives in uniform registers.  The loop is software-pipelined: the barrier wait for the
+      // NEXT stage sits between the two halves of this stage's MMAs, so the tensor pipe (whose queue holds
+      // only about one pending instruction -- an issue blocks until the pipe accepts it) always has work
+      // while this thread polls the mbarrier.
+      const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+      const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t empty0 = __shfl_sync(0xffffffffu, smem_u32(empty_bar), 0);
+      const int kiters = taps * g.kb_per_tap;
+      int s = 0, dbg_n = 0;
+      uint32_t ph = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t buf = lt & 1u, cph = (lt >> 1) & 1u;
+        mbar_wait(&acc_empty[buf], cph ^ 1u);  // epilogue has drained this accumulator buffer
+        mbar_wait(&full_bar[s], ph);           // first stage of the tile
+        tcgen05_fence_after();
+        const uint32_t acc = tbase + buf * (uint32_t)g.BN;
+        int cb = 0;
+        for (int it = 0; it < kiters; ++it) {
+          const bool ts = g.dbg_ts && blockIdx.x == 0 && dbg_n < 1024 && lane == 0;
+          if (ts) g.dbg_ts[dbg_n * 4 + 0] = clock64();
+          const int kc = cb + 1 == g.kb_per_tap ? kc_last : BK / 16;
+          const uint32_t a_addr = smem_base + (uint32_t)(s * stage_bytes);
+          const uint64_t da = make_sw128_desc(a_addr), db = make_sw128_desc(a_addr + A_STAGE_BYTES);
+          const uint32_t ebar = empty0 + 8u * (uint32_t)s;
+          // +32 bytes (= 2 x 16 B units) per 16 bf16 of K inside the swizzle atom
+          if (elect_one()) {
+            umma_bf16(acc, da, db, idesc, it > 0 ? 1u : 0u);
+            if (kc > 1) umma_bf16(acc, da + 2, db + 2, idesc, 1u);
           }
+          __syncwarp();
+          if (ts) g.dbg_ts[dbg_n * 4 + 1] = clock64();
+          int s1 = s + 1;
+          uint32_t ph1 = ph;
+          if (s1 == g.num_stages) { s1 = 0; ph1 ^= 1u; }
+          if (it + 1 < kiters) {
+            mbar_wait(&full_bar[s1], ph1);
+            tcgen05_fence_after();
+          }
+          if (ts) g.dbg_ts[dbg_n * 4 + 2] = clock64();
+          if (elect_one()) {
+            if (kc > 2) umma_bf16(acc, da + 4, db + 4, idesc, 1u);
+            if (kc > 3) umma_bf16(acc, da + 6, db + 6, idesc, 1u);
+            tcgen05_commit_u32(ebar);  // frees the smem slot when these MMAs retire
+          }
+          __syncwarp();
+          if (ts) g.dbg_ts[dbg_n++ * 4 + 3] = clock64();
+          s = s1;
+          ph = ph1;
+          if (++cb == g.kb_per_tap) cb = 0;
         }
-        tcgen05_commit(&acc_full[buf]);  // accumulator complete
+        if (elect_one()) tcgen05_commit(&acc_full[buf]);  // accumulator complete
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -393,6 +449,16 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   // halo mode: stride-1 multi-tap convs on maps that a 16 x 8 patch tiles exactly (RDSIC_TC_HALO: 0 off,
   // 1 on, 2 on with the descriptor base-offset field derived from the window start)
   static const int tune_halo = getenv("RDSIC_TC_HALO") ? atoi(getenv("RDSIC_TC_HALO")) : 0;
+  static long long* dbg_ts_buf = nullptr;
+  if (getenv("RDSIC_TC_DBG_TS") && !dbg_ts_buf) {
+    cudaMalloc(&dbg_ts_buf, 4096 * sizeof(long long));
+    cudaMemset(dbg_ts_buf, 0, 4096 * sizeof(long long));
+    g_dbg_ts = dbg_ts_buf;
+  }
+  g.dbg_ts = dbg_ts_buf;
+  static const int dbg_skip = getenv("RDSIC_TC_DBG_SKIP") ? atoi(getenv("RDSIC_TC_DBG_SKIP")) : 0;
+  g.dbg_skip_load = dbg_skip;
+
   if (tune_halo && !flat && d->stride == 1 && d->KH * d->KW > 1 && d->KH <= 3 && d->KW <= 3 && OH % 16 == 0 && OW % 8 == 0) {
     g.halo = 1;
     g.halo_base_off = tune_halo == 2;
@@ -493,4 +559,11 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   const int grid = g.total_tiles < sms ? g.total_tiles : sms;
   kern<<<grid, NUM_THREADS, smem, stream>>>(ta, tb, dd, g);
   return rdsic_launch_status();
+}
+
+// Profiling aid (not part of the public header): copies the issuer time stamps recorded under RDSIC_TC_DBG_TS.
+extern "C" int rdsic_debug_read_ts(long long* host, int n) {
+  if (!g_dbg_ts || n > 4096) return -1;
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpy(host, g_dbg_ts, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost);
 }

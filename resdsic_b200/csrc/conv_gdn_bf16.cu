@@ -96,11 +96,17 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
-      // second-GEMM weights once per CTA: K2/64 blocks of [N2 rows x 128 B]
-      mbar_expect_tx(g_full, (uint32_t)gg.w2_bytes);
-      for (int kb = 0; kb < gg.k2_blocks; ++kb) tma_load_2d(gamma_s + (size_t)kb * gg.N2 * 128, &tmap_g, g_full, kb * BK, 0);
+    // whole warp in uniform control flow, one elected lane issues (see elect_one in tc_common.cuh)
+    {
+      if (elect_one()) {
+        // second-GEMM weights once per CTA: K2/64 blocks of [N2 rows x 128 B]
+        mbar_expect_tx(g_full, (uint32_t)gg.w2_bytes);
+        for (int kb = 0; kb < gg.k2_blocks; ++kb) tma_load_2d(gamma_s + (size_t)kb * gg.N2 * 128, &tmap_g, g_full, kb * BK, 0);
+      }
+      __syncwarp();
       const uint32_t tx_bytes = (uint32_t)stage_bytes;
+      const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+      const uint32_t full0 = __shfl_sync(0xffffffffu, smem_u32(full_bar), 0);
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
@@ -114,10 +120,13 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           for (int sx = 0; sx < d.KW; ++sx, kcol += d.Cin) {
             for (int cb = 0; cb < g.kb_per_tap; ++cb) {
               mbar_wait(&empty_bar[s], ph ^ 1u);
-              uint8_t* a_dst = smem + (size_t)s * stage_bytes;
-              mbar_expect_tx(&full_bar[s], tx_bytes);
-              tma_load_4d(a_dst, &tmap_a, &full_bar[s], cb * BK, x0 + sx, y0 + r, b);
-              tma_load_2d(a_dst + A_STAGE_BYTES, &tmap_b, &full_bar[s], kcol + cb * BK, 0);
+              const uint32_t a_dst = smem_base + (uint32_t)(s * stage_bytes), bar = full0 + 8u * (uint32_t)s;
+              if (elect_one()) {
+                mbar_expect_tx_u32(bar, tx_bytes);
+                tma_load_4d_u32(a_dst, &tmap_a, bar, cb * BK, x0 + sx, y0 + r, b);
+                tma_load_2d_u32(a_dst + A_STAGE_BYTES, &tmap_b, bar, kcol + cb * BK, 0);
+              }
+              __syncwarp();
               if (++s == g.num_stages) { s = 0; ph ^= 1u; }
             }
           }
@@ -126,13 +135,16 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (whole warp, elected lane issues) =================
+    {
       const uint32_t idesc = make_idesc(C), idesc2 = make_idesc(gg.N2);
       const int taps = d.KH * d.KW;
       const int kc_last = (d.Cin - (g.kb_per_tap - 1) * BK) / 16;
-      const uint32_t acc1 = tmem_base, p_t = tmem_base + (uint32_t)gg.p_col, acc2 = tmem_base + (uint32_t)gg.acc2_col;
-      const uint32_t gamma_addr = smem_u32(gamma_s);
+      const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t acc1 = tbase, p_t = tbase + (uint32_t)gg.p_col, acc2 = tbase + (uint32_t)gg.acc2_col;
+      const uint32_t gamma_addr = __shfl_sync(0xffffffffu, smem_u32(gamma_s), 0);
+      const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+      const uint32_t empty0 = __shfl_sync(0xffffffffu, smem_u32(empty_bar), 0);
       int s = 0;
       uint32_t ph = 0, lt = 0;
       for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++lt) {
@@ -146,29 +158,34 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             mbar_wait(&full_bar[s], ph);
             tcgen05_fence_after();
             const int kc = cb + 1 == g.kb_per_tap ? kc_last : BK / 16;
-            const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+            const uint32_t a_addr = smem_base + (uint32_t)(s * stage_bytes);
             const uint64_t da = make_sw128_desc(a_addr), db = make_sw128_desc(a_addr + A_STAGE_BYTES);
-            for (int k = 0; k < kc; ++k) {
-              umma_bf16(acc1, da + 2 * k, db + 2 * k, idesc, accumulate);
-              accumulate = 1;
+            if (elect_one()) {
+              for (int k = 0; k < kc; ++k) umma_bf16(acc1, da + 2 * k, db + 2 * k, idesc, accumulate | (uint32_t)(k > 0));
+              tcgen05_commit_u32(empty0 + 8u * (uint32_t)s);
             }
-            tcgen05_commit(&empty_bar[s]);
+            __syncwarp();
+            accumulate = 1;
             if (++s == g.num_stages) { s = 0; ph ^= 1u; }
           }
         }
-        tcgen05_commit(acc1_full);
+        if (elect_one()) tcgen05_commit(acc1_full);
+        __syncwarp();
         // ---- GEMM 2: norm = gamma' @ x^2, A operand from TMEM
         if (lt == 0) mbar_wait(g_full, 0);
         mbar_wait(p_full, par);
         mbar_wait(acc2_empty, par ^ 1u);
         tcgen05_fence_after();
-        for (int kb = 0; kb < gg.k2_blocks; ++kb) {
-          const uint64_t dg = make_sw128_desc(gamma_addr + (uint32_t)(kb * gg.N2 * 128));
-          const int kc2 = kb + 1 == gg.k2_blocks ? gg.kc2_last : BK / 16;
-          for (int k = 0; k < kc2; ++k)  // 16 bf16 of K = 8 TMEM columns of the staged operand
-            umma_bf16_ts(acc2, p_t + (uint32_t)((kb * 4 + k) * 8), dg + 2 * k, idesc2, (kb | k) ? 1u : 0u);
+        if (elect_one()) {
+          for (int kb = 0; kb < gg.k2_blocks; ++kb) {
+            const uint64_t dg = make_sw128_desc(gamma_addr + (uint32_t)(kb * gg.N2 * 128));
+            const int kc2 = kb + 1 == gg.k2_blocks ? gg.kc2_last : BK / 16;
+            for (int k = 0; k < kc2; ++k)  // 16 bf16 of K = 8 TMEM columns of the staged operand
+              umma_bf16_ts(acc2, p_t + (uint32_t)((kb * 4 + k) * 8), dg + 2 * k, idesc2, (kb | k) ? 1u : 0u);
+          }
+          tcgen05_commit(acc2_full);
         }
-        tcgen05_commit(acc2_full);
+        __syncwarp();
       }
     }
     __syncwarp();

@@ -25,6 +25,8 @@ struct TcGeom {
   // halo mode (stride-1 multi-tap convs): the (TH+KH-1) x (TW+KW-1) input patch of a channel block is loaded
   // ONCE and every tap's A operand is a shifted window of it (descriptor start + row offset, SBO = halo row pitch)
   int halo, halo_w, halo_h, a_halo_bytes, halo_base_off;
+  int dbg_skip_load;   // profiling aid: bit0 = do not load A, bit1 = do not load B (results are garbage)
+  long long* dbg_ts;   // profiling aid: clock64 stamps of issuer 0 of CTA 0 (4 per k-iteration), or null
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -54,6 +56,40 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > SPIN_LIMIT) __trap();
   }
 }
+// Whole-warp wait used by the epilogue warps: only lane 0 touches the mbarrier (32 lanes x 12 warps polling
+// the same word slowed the MMA thread's own try_wait from ~90 to ~220 cycles), with a suspend-time hint so a
+// waiting warp sleeps in hardware instead of re-issuing the poll.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0, spins = 0;
+    while (true) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+          "selp.b32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(addr), "r"(parity), "r"(2000u)
+          : "memory");
+      if (done) break;
+      if (++spins > SPIN_LIMIT) __trap();
+    }
+  }
+  __syncwarp();
+}
+// One lane of a converged warp (elect.sync).  The TMA / MMA loops are run by their WHOLE warp in uniform
+// control flow and only the issue itself is predicated: a loop entered by a single lane is divergent code,
+// where the compiler cannot use uniform registers and wraps every UTCHMMA / UTMALDG operand in an
+// ELECT + R2UR.BROADCAST "waterfall" loop (~150 cycles per MMA issue, measured).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -68,6 +104,25 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
 }
 __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// variants taking shared-window addresses (kept in uniform registers by the callers)
+__device__ __forceinline__ void tcgen05_commit_u32(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_u32(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_u32(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

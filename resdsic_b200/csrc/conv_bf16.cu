@@ -20,7 +20,8 @@
 //     epilogue (TMEM lane quarter = warp_id % 4).
 #include "tc_common.cuh"
 
-long long* g_dbg_ts = nullptr;  // profiling aid, see rdsic_debug_read_ts
+long long* g_dbg_ts = nullptr;
+int g_dbg_host = 0;  // profiling aid, see rdsic_debug_read_ts
 
 namespace {
 
@@ -32,8 +33,17 @@ namespace {
 // EPI: fused epilogue (compile time, keeps the epilogue's code small enough for the I-cache);
 // PLAIN: every output/residual view is channels-last with 16-element-aligned rows (vector path),
 //        otherwise the generic scalar addressing (NCHW output, PixelShuffle) is used.
+//
+// K-split (g.ksplit): issuing a tcgen05.mma costs its thread ~77 cycles whatever N is (measured with
+// tests/gpu_issue_trace.py), i.e. ~310 of the ~540 cycles one 64-wide K step takes a single issuer while the
+// pipe needs 4 x N/2.  Two issuer warps (warp 1 and ISSUER2_WARP) therefore take alternate k-iterations,
+// each into its OWN accumulator (fixed summation order -> results stay bit-reproducible run to run); the
+// epilogue adds the two.
+constexpr int ISSUER2_WARP = 2 + NUM_EPI_WARPS;
+constexpr int CONV_THREADS = NUM_THREADS + 32;
+
 template <int EPI, bool PLAIN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const rdsic_conv_desc d, const TcGeom g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -60,7 +70,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(&empty_bar[s], 1);
     }
     for (int k = 0; k < 2; ++k) {
-      mbar_init(&acc_full[k], 1);
+      mbar_init(&acc_full[k], g.ksplit ? 2 : 1);
       mbar_init(&acc_empty[k], NUM_EPI_WARPS);
       mbar_init(&a_full[k], 1);
       mbar_init(&a_empty[k], 1);
@@ -140,13 +150,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
+  } else if (warp == 1 || warp == ISSUER2_WARP) {
+    // ================= MMA issuers =================
+    const uint32_t me = warp == 1 ? 0u : 1u;
     const uint32_t idesc = make_idesc(g.BN);
     const int taps = d.KH * d.KW;
     const int kc_last = (d.Cin - (g.kb_per_tap - 1) * BK) / 16;  // valid 16-wide K steps of a tap's last block
     if (g.halo) {
-      if (lane == 0) {  // (experimental mode, divergent single-lane issue)
+      if (lane == 0 && !me) {  // (experimental mode, divergent single-lane issue)
         int s = 0, as = 0;
         uint32_t ph = 0, lt = 0, aph = 0;
         for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++lt) {
@@ -194,15 +205,48 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int kiters = taps * g.kb_per_tap;
       int s = 0, dbg_n = 0;
       uint32_t ph = 0, lt = 0;
+      if (g.ksplit) {
+        // two issuers, alternate k-iterations, own accumulators; while one polls its barrier the other issues
+        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++lt) {
+          const uint32_t buf = g.acc_bufs == 2 ? (lt & 1u) : 0u, cph = g.acc_bufs == 2 ? ((lt >> 1) & 1u) : (lt & 1u);
+          mbar_wait(&acc_empty[buf], cph ^ 1u);
+          tcgen05_fence_after();
+          const uint32_t acc = tbase + buf * (uint32_t)g.acc_stride + me * (uint32_t)g.BN;
+          int cb = 0;
+          for (int it = 0; it < kiters; ++it) {
+            if ((uint32_t)(it & 1) == me) {
+              const bool ts = g.dbg_ts && !(g.dbg_skip_load & 4) && blockIdx.x == 0 && me == 0 && dbg_n < 1024 && lane == 0;
+              if (ts) g.dbg_ts[dbg_n * 4 + 0] = clock64();
+              mbar_wait(&full_bar[s], ph);
+              tcgen05_fence_after();
+              if (ts) g.dbg_ts[dbg_n * 4 + 1] = g.dbg_ts[dbg_n * 4 + 2] = clock64();
+              const int kc = cb + 1 == g.kb_per_tap ? kc_last : BK / 16;
+              const uint32_t a_addr = smem_base + (uint32_t)(s * stage_bytes);
+              const uint64_t da = make_sw128_desc(a_addr), db = make_sw128_desc(a_addr + A_STAGE_BYTES);
+              const uint32_t ebar = empty0 + 8u * (uint32_t)s;
+              if (elect_one()) {
+                for (int k = 0; k < kc; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (it > 1 || k > 0) ? 1u : 0u);
+                tcgen05_commit_u32(ebar);
+              }
+              __syncwarp();
+              if (ts) g.dbg_ts[dbg_n++ * 4 + 3] = clock64();
+            }
+            if (++s == g.num_stages) { s = 0; ph ^= 1u; }
+            if (++cb == g.kb_per_tap) cb = 0;
+          }
+          if (elect_one()) tcgen05_commit(&acc_full[buf]);  // this issuer's accumulator is complete
+          __syncwarp();
+        }
+      } else if (!me)
       for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++lt) {
-        const uint32_t buf = lt & 1u, cph = (lt >> 1) & 1u;
+        const uint32_t buf = g.acc_bufs == 2 ? (lt & 1u) : 0u, cph = g.acc_bufs == 2 ? ((lt >> 1) & 1u) : (lt & 1u);
         mbar_wait(&acc_empty[buf], cph ^ 1u);  // epilogue has drained this accumulator buffer
         mbar_wait(&full_bar[s], ph);           // first stage of the tile
         tcgen05_fence_after();
-        const uint32_t acc = tbase + buf * (uint32_t)g.BN;
+        const uint32_t acc = tbase + buf * (uint32_t)g.acc_stride;
         int cb = 0;
         for (int it = 0; it < kiters; ++it) {
-          const bool ts = g.dbg_ts && blockIdx.x == 0 && dbg_n < 1024 && lane == 0;
+          const bool ts = g.dbg_ts && !(g.dbg_skip_load & 4) && blockIdx.x == 0 && dbg_n < 1024 && lane == 0;
           if (ts) g.dbg_ts[dbg_n * 4 + 0] = clock64();
           const int kc = cb + 1 == g.kb_per_tap ? kc_last : BK / 16;
           const uint32_t a_addr = smem_base + (uint32_t)(s * stage_bytes);
@@ -239,7 +283,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp < ISSUER2_WARP) {
     // ================= epilogue (warps 2..): EPI_PARTS warps per TMEM lane quarter, interleaved column chunks
     constexpr bool NEED_RES = EPI == RDSIC_EPI_RES_GELU || EPI == RDSIC_EPI_ADD_RES || EPI == RDSIC_EPI_GATE ||
                               EPI == RDSIC_EPI_GDN || EPI == RDSIC_EPI_IGDN || EPI == RDSIC_EPI_LRP;
@@ -259,8 +303,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int oy = ty * g.TH + dy, ox = tx * g.TW + dx, n0 = nt * g.BN;
       const bool row_ok = oy < d.OH && ox < d.OW;
       const size_t pix = ((size_t)b * d.OHt + (oy * d.osy + d.ooy)) * d.OWt + (ox * d.osx + d.oox);
-      const uint32_t buf = lt & 1u, aph = (lt >> 1) & 1u;
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)g.BN;
+      const uint32_t buf = g.acc_bufs == 2 ? (lt & 1u) : 0u, aph = g.acc_bufs == 2 ? ((lt >> 1) & 1u) : (lt & 1u);
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)g.acc_stride;
 
       if (PLAIN) {
         // Residual / gate operands are prefetched in groups of G chunks BEFORE the accumulator is awaited,
@@ -295,9 +339,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             uint32_t ua[16], ub[16];
             tmem_ld16_issue(trow + (uint32_t)(ja * 16), ua);
             if (has_b) tmem_ld16_issue(trow + (uint32_t)(jb * 16), ub);
-            tmem_ld_wait();
-            tmem_ld_fence(ua);
-            if (has_b) tmem_ld_fence(ub);
+            if (g.ksplit) {  // add the second issuer's accumulator (fixed order: even + odd k-iterations)
+              uint32_t uc[16];
+              tmem_ld16_issue(trow + (uint32_t)(g.BN + ja * 16), uc);
+              tmem_ld_wait();
+              tmem_ld_fence(ua);
+              if (has_b) tmem_ld_fence(ub);
+              tmem_ld_fence(uc);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) ua[i] = __float_as_uint(__uint_as_float(ua[i]) + __uint_as_float(uc[i]));
+              if (has_b) {
+                tmem_ld16_issue(trow + (uint32_t)(g.BN + jb * 16), uc);
+                tmem_ld_wait();
+                tmem_ld_fence(uc);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) ub[i] = __float_as_uint(__uint_as_float(ub[i]) + __uint_as_float(uc[i]));
+              }
+            } else {
+              tmem_ld_wait();
+              tmem_ld_fence(ua);
+              if (has_b) tmem_ld_fence(ub);
+            }
 #pragma unroll
             for (int hb = 0; hb < 2; ++hb) {
               if (hb == 1 && !has_b) break;
@@ -342,6 +404,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int j = half; j < nchunks; j += EPI_PARTS) {
           float v[16];
           tmem_ld16(trow + (uint32_t)(j * 16), v);
+          if (g.ksplit) {
+            float w[16];
+            tmem_ld16(trow + (uint32_t)(g.BN + j * 16), w);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += w[i];
+          }
           const int nb = n0 + j * 16;
           if (!row_ok || nb >= d.Cout) continue;
           const int HWt = d.OHt * d.OWt;
@@ -451,13 +519,20 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   static const int tune_halo = getenv("RDSIC_TC_HALO") ? atoi(getenv("RDSIC_TC_HALO")) : 0;
   static long long* dbg_ts_buf = nullptr;
   if (getenv("RDSIC_TC_DBG_TS") && !dbg_ts_buf) {
-    cudaMalloc(&dbg_ts_buf, 4096 * sizeof(long long));
-    cudaMemset(dbg_ts_buf, 0, 4096 * sizeof(long long));
+    if (atoi(getenv("RDSIC_TC_DBG_TS")) == 2) {  // host-mapped: survives a trap (timeout log of mbar_wait, tc_common.cuh)
+      cudaHostAlloc(&dbg_ts_buf, 16384 * sizeof(long long), cudaHostAllocMapped);
+      memset(dbg_ts_buf, 0, 16384 * sizeof(long long));
+      g_dbg_host = 1;
+      tc_set_timeout_log(dbg_ts_buf);
+    } else {
+      cudaMalloc(&dbg_ts_buf, 4096 * sizeof(long long));
+      cudaMemset(dbg_ts_buf, 0, 4096 * sizeof(long long));
+    }
     g_dbg_ts = dbg_ts_buf;
   }
   g.dbg_ts = dbg_ts_buf;
   static const int dbg_skip = getenv("RDSIC_TC_DBG_SKIP") ? atoi(getenv("RDSIC_TC_DBG_SKIP")) : 0;
-  g.dbg_skip_load = dbg_skip;
+  g.dbg_skip_load = dbg_skip | (g_dbg_host ? 4 : 0);  // bit 2: the buffer is the timeout log, no time stamps
 
   if (tune_halo && !flat && d->stride == 1 && d->KH * d->KW > 1 && d->KH <= 3 && d->KW <= 3 && OH % 16 == 0 && OW % 8 == 0) {
     g.halo = 1;
@@ -498,8 +573,21 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   if (tune_stages > 0 && tune_stages < stages) stages = tune_stages;
   if (stages < 2) return RDSIC_E_ARG;
   g.num_stages = stages;
+  // K-split across two issuer warps (see the kernel's header comment), only where BOTH accumulator sets of the
+  // usual double buffering fit the 512 TMEM columns (bn_layer <= 128).  A single-buffered variant for wider
+  // tiles (RDSIC_TC_KSPLIT=2) is faster on the 5x5 / deconv layers but intermittently faults
+  // (cudaErrorLaunchFailure, no barrier timeout logged) when other kernels run concurrently -- bn_layer = 192
+  // only, never in isolation -- so it stays an experiment; see DESIGN.md.
+  // The decision uses only layer properties (Cout, K) -- never the grid-dependent N split above -- so that the
+  // fp32 summation order, hence every output bit, is independent of batch size and image size.
+  static const int tune_ksplit = getenv("RDSIC_TC_KSPLIT") ? atoi(getenv("RDSIC_TC_KSPLIT")) : 1;
+  const int bn_layer = pick_bn(d->Cout);
+  g.ksplit = tune_ksplit && !g.halo && g.num_k_iters >= 4 &&
+             (4 * bn_layer <= 512 || (tune_ksplit == 2 && 2 * bn_layer <= 512 && g.num_k_iters >= 16));
+  g.acc_stride = g.BN * (1 + g.ksplit);
+  g.acc_bufs = 2 * g.acc_stride <= 512 ? 2 : 1;
   g.tmem_cols = 32;
-  while (g.tmem_cols < 2 * g.BN) g.tmem_cols *= 2;  // two accumulator buffers
+  while (g.tmem_cols < g.acc_bufs * g.acc_stride) g.tmem_cols *= 2;
   RDSIC_CHECK_ARG(g.TW * d->stride <= 256 && g.TH * d->stride <= 256);
 
   // ---- tensor maps
@@ -557,13 +645,17 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
     if (track) sm_count[dev] = sms;
   }
   const int grid = g.total_tiles < sms ? g.total_tiles : sms;
-  kern<<<grid, NUM_THREADS, smem, stream>>>(ta, tb, dd, g);
+  kern<<<grid, CONV_THREADS, smem, stream>>>(ta, tb, dd, g);
   return rdsic_launch_status();
 }
 
 // Profiling aid (not part of the public header): copies the issuer time stamps recorded under RDSIC_TC_DBG_TS.
 extern "C" int rdsic_debug_read_ts(long long* host, int n) {
-  if (!g_dbg_ts || n > 4096) return -1;
+  if (!g_dbg_ts || n > (g_dbg_host ? 16384 : 4096)) return -1;
+  if (g_dbg_host) {
+    memcpy(host, g_dbg_ts, (size_t)n * sizeof(long long));
+    return 0;
+  }
   cudaDeviceSynchronize();
   return (int)cudaMemcpy(host, g_dbg_ts, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost);
 }

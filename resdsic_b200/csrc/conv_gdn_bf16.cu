@@ -401,6 +401,15 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   if (encode_2d(&tb, d->weight, d->KH * d->KW * d->Cin, C) != CUDA_SUCCESS) return RDSIC_E_ARG;
   if (encode_2d(&tg, d->tail_weight, C, N2) != CUDA_SUCCESS) return RDSIC_E_ARG;
 
+  {  // debug: barrier-timeout log (see tc_common.cuh)
+    extern long long* g_dbg_ts;
+    extern int g_dbg_host;
+    static bool log_set = false;
+    if (g_dbg_host && !log_set) {
+      tc_set_timeout_log(g_dbg_ts);
+      log_set = true;
+    }
+  }
   const size_t smem = (size_t)stages * stage_bytes + gg.w2_bytes + 1024 + (2 * MAX_STAGES + 8) * 8 + 16;
   auto kern = d->tail_mode == TAIL_RU ? conv_gdn_tc_kernel<TAIL_RU>
               : d->tail_mode == TAIL_IGDN ? conv_gdn_tc_kernel<TAIL_IGDN> : conv_gdn_tc_kernel<TAIL_GDN>;

@@ -25,6 +25,9 @@ struct TcGeom {
   // halo mode (stride-1 multi-tap convs): the (TH+KH-1) x (TW+KW-1) input patch of a channel block is loaded
   // ONCE and every tap's A operand is a shifted window of it (descriptor start + row offset, SBO = halo row pitch)
   int halo, halo_w, halo_h, a_halo_bytes, halo_base_off;
+  int ksplit;          // 1: two issuer warps take alternate k-iterations into two accumulators (summed by the epilogue)
+  int acc_bufs;        // accumulator buffers cycled across tiles (2, or 1 when 2 x the accumulator set does not fit TMEM)
+  int acc_stride;      // TMEM columns of one buffer = BN * (1 + ksplit)
   int dbg_skip_load;   // profiling aid: bit0 = do not load A, bit1 = do not load B (results are garbage)
   long long* dbg_ts;   // profiling aid: clock64 stamps of issuer 0 of CTA 0 (4 per k-iteration), or null
 };
@@ -41,6 +44,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Debug: host-mapped log for barrier timeouts (one copy per translation unit, set by tc_set_timeout_log).
+static __device__ long long* g_mbar_log = nullptr;
+static inline void tc_set_timeout_log(long long* p) { cudaMemcpyToSymbol(g_mbar_log, &p, sizeof(p)); }
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0, spins = 0;
@@ -53,29 +60,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) break;
-    if (++spins > SPIN_LIMIT) __trap();
-  }
-}
-// Whole-warp wait used by the epilogue warps: only lane 0 touches the mbarrier (32 lanes x 12 warps polling
-// the same word slowed the MMA thread's own try_wait from ~90 to ~220 cycles), with a suspend-time hint so a
-// waiting warp sleeps in hardware instead of re-issuing the poll.
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
-  if ((threadIdx.x & 31) == 0) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done = 0, spins = 0;
-    while (true) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-          "selp.b32 %0, 1, 0, p;\n\t}"
-          : "=r"(done)
-          : "r"(addr), "r"(parity), "r"(2000u)
-          : "memory");
-      if (done) break;
-      if (++spins > SPIN_LIMIT) __trap();
+    if (++spins > SPIN_LIMIT) {
+      if (g_mbar_log && (threadIdx.x & 31) == 0) {
+        volatile long long* rec = g_mbar_log + 4 + ((blockIdx.x % 148) * 16 + (threadIdx.x / 32)) * 4;
+        rec[0] = 100;
+        rec[1] = ((long long)blockIdx.x << 32) | (threadIdx.x / 32);
+        rec[2] = addr;
+        rec[3] = parity;
+        __threadfence_system();
+        __nanosleep(2000000);
+      }
+      __trap();
     }
   }
-  __syncwarp();
 }
 // One lane of a converged warp (elect.sync).  The TMA / MMA loops are run by their WHOLE warp in uniform
 // control flow and only the issue itself is predicated: a loop entered by a single lane is divergent code,

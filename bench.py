@@ -155,6 +155,7 @@ def run_ours(args):
         model = resdsic_b200.WACNN().eval()
     model.load_state_dict(sd, strict=True)
     model = model.to(dev).set_precision(args.precision)
+    model.micro_batches = args.micro_batches if args.micro_batches == "auto" else int(args.micro_batches)
     B = args.batch
     x_host = build_inputs(B, seed=100 + rank).pin_memory()
     x_dev = x_host.to(dev)
@@ -211,8 +212,10 @@ def run_ours(args):
         if args.model != "cnn":  # no survey figure: sum 2*M*N*K over the program's GEMM descriptors
             plan = next(iter(model._plans.values()))
             flop_per_image = sum(2.0 * o.u.conv.B * o.u.conv.OH * o.u.conv.OW * o.u.conv.Cout * o.u.conv.KH * o.u.conv.KW *
-                                 o.u.conv.Cin for o in plan.prog.ops if o.kind == _lib.OP_CONV) / B
-        tf = B * flop_per_image / conv_n / (conv_ms / conv_n / 1e3) / 1e12  # algorithmic FLOP per launch / avg launch time
+                                 o.u.conv.Cin for o in plan.prog.ops if o.kind == _lib.OP_CONV) / plan.sub_batch
+        # the profile covers ONE sub-batch program (the model runs `micro_batches` of them concurrently)
+        b_prog = next(iter(model._plans.values())).sub_batch
+        tf = b_prog * flop_per_image / conv_n / (conv_ms / conv_n / 1e3) / 1e12  # algorithmic FLOP per launch / avg launch time
         traffic_bytes, traffic_note = None, None
         tpath = os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")
         if os.path.exists(tpath):  # DRAM bytes of the heaviest launch, from the committed ncu --set full capture
@@ -229,7 +232,8 @@ def run_ours(args):
                                     else f"stf (builder-defined, N=192 M=384) forward 512x768, batch {B} per GPU, eval mode"),
                        "precision": args.precision, "batch_per_gpu": B, "image": [H, W], "parallelism": f"dp{world}",
                        "l2": f"per-step activation working set (~{0.19 * B:.1f} GB at batch {B}) exceeds the 126 MB L2; no explicit flush",
-                       "cuda_graph": bool(model.use_cuda_graph)},
+                       "cuda_graph": bool(model.use_cuda_graph),
+                       "micro_batches": len(next(iter(model._plans.values())).subs)},
             "megapixels_per_s": ips * H * W / 1e6,
             "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "api": "resdsic_b200.utils.ForwardPipeline.run (pinned host in, pinned host out, depth 2)",
@@ -242,6 +246,7 @@ def run_ours(args):
                          "kernel": "implicit-GEMM conv family (all conv/deconv/linear/GDN launches)",
                          "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                          "share_of_step": conv_ms / total_ms,
+                         "families_note": "eager per-launch profile of ONE sub-batch program (micro_batches of them run per step)",
                          "families_ms_per_step": {k: {"ms": v[0], "launches": v[1]} for k, v in fam.items()}},
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -310,6 +315,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("RESDSIC_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
+    ap.add_argument("--micro-batches", default="auto", help="sub-batches run as concurrent graphs (auto | 1 | 2 | 4 ...)")
     ap.add_argument("--model", default="cnn", choices=["cnn", "stf"], help="cnn = the headline (BASELINE.json) workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-ops", default=None, help="write the per-launch device times of one step to this JSON file")

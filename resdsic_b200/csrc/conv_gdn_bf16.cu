@@ -13,12 +13,15 @@
 // 8 images, more than everything else the two layers move.
 //
 // TMEM columns (C = 192): [0,C) acc1 | [C, C + C/2) x^2 bf16 (two values per 32-bit column) | [.., +C) acc2.
+// Where a second copy of acc1 fits (the ResidualUnit tail, C = 96), GEMM 1 is K-split across two issuer warps
+// like conv_bf16.cu (alternate k-iterations, own accumulators [0,C) and [C,2C), summed in phase 1).
 #include "tc_common.cuh"
 
 namespace {
 
 constexpr int G_EPI_WARPS = 12;
-constexpr int G_THREADS = 64 + 32 * G_EPI_WARPS;
+constexpr int G_ISSUER2_WARP = 2 + G_EPI_WARPS;
+constexpr int G_THREADS = 96 + 32 * G_EPI_WARPS;  // TMA warp, two MMA issuer warps, epilogue warps
 constexpr int G_PARTS = G_EPI_WARPS / 4;
 constexpr int MAXC = 192;                    // channel count supported (TMEM: 2.5 C <= 512)
 constexpr int MAX_CHUNKS = MAXC / 16 / G_PARTS;
@@ -45,6 +48,7 @@ struct GdnGeom {
   int w2_bytes;      // resident second-GEMM weight tiles: ceil(K2/64) x [N2 rows x 128 B]
   int p_col, acc2_col;
   int N2, k2_blocks, kc2_last;  // second GEMM: N2 output columns, K2 = N1 in 64-wide blocks
+  int ksplit;                   // GEMM 1 split across two issuers / two accumulators
 };
 
 template <int MODE>
@@ -77,7 +81,7 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(acc1_full, 1);
+    mbar_init(acc1_full, gg.ksplit ? 2 : 1);
     mbar_init(acc1_empty, G_EPI_WARPS);
     mbar_init(p_full, G_EPI_WARPS);
     mbar_init(acc2_full, 1);
@@ -122,8 +126,12 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               mbar_wait(&empty_bar[s], ph ^ 1u);
               const uint32_t a_dst = smem_base + (uint32_t)(s * stage_bytes), bar = full0 + 8u * (uint32_t)s;
               if (elect_one()) {
-                mbar_expect_tx_u32(bar, tx_bytes);
-                tma_load_4d_u32(a_dst, &tmap_a, bar, cb * BK, x0 + sx, y0 + r, b);
+                if (g.dbg_skip_load & 1) {  // profiling only: no A loads
+                  mbar_expect_tx_u32(bar, (uint32_t)g.b_stage_bytes);
+                } else {
+                  mbar_expect_tx_u32(bar, tx_bytes);
+                  tma_load_4d_u32(a_dst, &tmap_a, bar, cb * BK, x0 + sx, y0 + r, b);
+                }
                 tma_load_2d_u32(a_dst + A_STAGE_BYTES, &tmap_b, bar, kcol + cb * BK, 0);
               }
               __syncwarp();
@@ -134,14 +142,15 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ================= MMA issuer (whole warp, elected lane issues) =================
-    {
+  } else if (warp == 1 || warp == G_ISSUER2_WARP) {
+    // ================= MMA issuers (whole warp, elected lane issues) =================
+    const uint32_t me = warp == 1 ? 0u : 1u;
+    if (!me || gg.ksplit) {
       const uint32_t idesc = make_idesc(C), idesc2 = make_idesc(gg.N2);
       const int taps = d.KH * d.KW;
       const int kc_last = (d.Cin - (g.kb_per_tap - 1) * BK) / 16;
       const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint32_t acc1 = tbase, p_t = tbase + (uint32_t)gg.p_col, acc2 = tbase + (uint32_t)gg.acc2_col;
+      const uint32_t acc1 = tbase + me * (uint32_t)C, p_t = tbase + (uint32_t)gg.p_col, acc2 = tbase + (uint32_t)gg.acc2_col;
       const uint32_t gamma_addr = __shfl_sync(0xffffffffu, smem_u32(gamma_s), 0);
       const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       const uint32_t empty0 = __shfl_sync(0xffffffffu, smem_u32(empty_bar), 0);
@@ -149,14 +158,26 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       uint32_t ph = 0, lt = 0;
       for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++lt) {
         const uint32_t par = lt & 1u;
+        // profiling aid (RDSIC_TC_DBG_TS=1, tests/gpu_issue_trace.py): 16 clock64 stamps per tile of CTA 0,
+        // slots 0-5 written by issuer 0, slots 8-12 by the first epilogue warp
+        long long* tsp = (g.dbg_ts && blockIdx.x == 0 && !me && lane == 0 && lt < 250) ? g.dbg_ts + lt * 16 : nullptr;
+        if (tsp) tsp[0] = clock64();
         // ---- GEMM 1: x = conv(in)
         mbar_wait(acc1_empty, par ^ 1u);
         tcgen05_fence_after();
-        uint32_t accumulate = 0;
+        if (tsp) tsp[1] = clock64();
+        uint32_t accumulate = 0, turn = 0;
         for (int tap = 0; tap < taps; ++tap) {
-          for (int cb = 0; cb < g.kb_per_tap; ++cb) {
+          for (int cb = 0; cb < g.kb_per_tap; ++cb, turn ^= 1u) {
+            if (gg.ksplit && turn != me) {  // the other issuer's k-iteration
+              if (++s == g.num_stages) { s = 0; ph ^= 1u; }
+              continue;
+            }
+            long long* ksp = (tsp && lt == 3) ? g.dbg_ts + 2048 + (tap * g.kb_per_tap + cb) * 4 : nullptr;  // k-loop detail of tile 3
+            if (ksp) ksp[0] = clock64();
             mbar_wait(&full_bar[s], ph);
             tcgen05_fence_after();
+            if (ksp) ksp[1] = clock64();
             const int kc = cb + 1 == g.kb_per_tap ? kc_last : BK / 16;
             const uint32_t a_addr = smem_base + (uint32_t)(s * stage_bytes);
             const uint64_t da = make_sw128_desc(a_addr), db = make_sw128_desc(a_addr + A_STAGE_BYTES);
@@ -165,17 +186,22 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               tcgen05_commit_u32(empty0 + 8u * (uint32_t)s);
             }
             __syncwarp();
+            if (ksp) ksp[2] = clock64();
             accumulate = 1;
             if (++s == g.num_stages) { s = 0; ph ^= 1u; }
           }
         }
         if (elect_one()) tcgen05_commit(acc1_full);
         __syncwarp();
+        if (me) continue;
+        if (tsp) tsp[2] = clock64();
         // ---- GEMM 2: norm = gamma' @ x^2, A operand from TMEM
         if (lt == 0) mbar_wait(g_full, 0);
         mbar_wait(p_full, par);
+        if (tsp) tsp[3] = clock64();
         mbar_wait(acc2_empty, par ^ 1u);
         tcgen05_fence_after();
+        if (tsp) tsp[4] = clock64();
         if (elect_one()) {
           for (int kb = 0; kb < gg.k2_blocks; ++kb) {
             const uint64_t dg = make_sw128_desc(gamma_addr + (uint32_t)(kb * gg.N2 * 128));
@@ -186,10 +212,11 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           tcgen05_commit(acc2_full);
         }
         __syncwarp();
+        if (tsp) tsp[5] = clock64();
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp < G_ISSUER2_WARP) {
     // ================= epilogue warps =================
     const int q = warp % 4, part = (warp - 2) / 4;
     const int ml = q * 32 + lane;
@@ -208,15 +235,24 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const uint32_t par = lt & 1u;
       uint32_t xs[MAX_CHUNKS][8];  // GDN: x as packed bf16, kept for the final multiply; RU: prefetched residual
 
+      long long* tsp = (g.dbg_ts && blockIdx.x == 0 && warp == 2 && lane == 0 && lt < 250) ? g.dbg_ts + lt * 16 : nullptr;
+      if (tsp) tsp[8] = clock64();
       // ---- phase 1: v = acc1 + bias;  GDN: stage v^2, keep v;  RU: stage gelu(v)
       mbar_wait(acc1_full, par);
       tcgen05_fence_after();
+      if (tsp) tsp[9] = clock64();
 #pragma unroll
       for (int ci = 0; ci < MAX_CHUNKS; ++ci) {
         const int j = part + G_PARTS * ci;
         if (j >= nchunks1) break;
         float v[16];
         tmem_ld16(tmem_base + lane_off + (uint32_t)(j * 16), v);
+        if (gg.ksplit) {  // fixed order: even + odd k-iterations
+          float w[16];
+          tmem_ld16(tmem_base + lane_off + (uint32_t)(C + j * 16), w);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += w[i];
+        }
         if (d.bias) {
           const float4* bp = reinterpret_cast<const float4*>(d.bias + j * 16);
 #pragma unroll
@@ -247,6 +283,7 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         mbar_arrive(acc1_empty);  // acc1 drained: GEMM 1 of the next tile may start
         mbar_arrive(p_full);      // staged operand in place: GEMM 2 may start
       }
+      if (tsp) tsp[10] = clock64();
       if (MODE == TAIL_RU) {  // residual x: issue the loads now, they land while GEMM 2 runs
         const __nv_bfloat16* resp = (const __nv_bfloat16*)d.res.ptr + pix * (size_t)d.res.ld + d.res.coff;
 #pragma unroll
@@ -262,6 +299,7 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       // ---- phase 2: GDN: out = x * (r)sqrt(acc2 + beta');  RU: out = gelu(acc2 + bias2 + res)
       mbar_wait(acc2_full, par);
       tcgen05_fence_after();
+      if (tsp) tsp[11] = clock64();
 #pragma unroll
       for (int ci = 0; ci < MAX_CHUNKS; ++ci) {
         const int j = part + G_PARTS * ci;
@@ -291,6 +329,7 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc2_empty);
+      if (tsp) tsp[12] = clock64();
     }
   }
 
@@ -335,7 +374,7 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return RDSIC_E_UNSUPPORTED;
 
-  TcGeom g;
+  TcGeom g = {};
   int B = d->B, H = d->H, W = d->W, OH = d->OH, OW = d->OW;
   const bool flat = d->KH == 1 && d->KW == 1 && d->stride == 1 && d->pad_h == 0 && d->pad_w == 0 && d->osy == 1 &&
                     d->osx == 1 && d->ooy == 0 && d->oox == 0 && OH == H && OW == W && d->OHt == OH && d->OWt == OW;
@@ -363,13 +402,30 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   g.num_k_iters = d->KH * d->KW * g.kb_per_tap;
   g.b_stage_bytes = C * BK * 2;
   g.tmem_cols = 512;
+  static const int dbg_skip = getenv("RDSIC_TC_DBG_SKIPG") ? atoi(getenv("RDSIC_TC_DBG_SKIPG")) : 0;
+  g.dbg_skip_load = dbg_skip;
+  {
+    extern long long* g_dbg_ts;
+    extern int g_dbg_host;
+    static long long* ts_buf = nullptr;
+    if (getenv("RDSIC_TC_DBG_TS") && !g_dbg_host && !ts_buf) {
+      if (!g_dbg_ts) {
+        cudaMalloc(&g_dbg_ts, 4096 * sizeof(long long));
+        cudaMemset(g_dbg_ts, 0, 4096 * sizeof(long long));
+      }
+      ts_buf = g_dbg_ts;
+    }
+    g.dbg_ts = ts_buf;
+  }
   GdnGeom gg;
   gg.N2 = N2;
   gg.k2_blocks = ceil_div(C, BK);
   gg.kc2_last = (C - (gg.k2_blocks - 1) * BK) / 16;
   gg.w2_bytes = gg.k2_blocks * N2 * 128;
-  gg.p_col = C;
-  gg.acc2_col = (C + C / 2 + 31) / 32 * 32;
+  static const int tune_ksplit = getenv("RDSIC_TC_KSPLIT") ? atoi(getenv("RDSIC_TC_KSPLIT")) : 1;
+  gg.ksplit = tune_ksplit && g.num_k_iters >= 4 && (2 * C + C / 2 + 31) / 32 * 32 + N2 <= 512;
+  gg.p_col = C * (1 + gg.ksplit);
+  gg.acc2_col = (gg.p_col + C / 2 + 31) / 32 * 32;
   RDSIC_CHECK_ARG(gg.acc2_col + N2 <= 512);
   const int stage_bytes = A_STAGE_BYTES + g.b_stage_bytes;
   int stages = (200 * 1024 - gg.w2_bytes) / stage_bytes;

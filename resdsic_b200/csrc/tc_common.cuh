@@ -205,7 +205,9 @@ __device__ __forceinline__ float tanh_mufu(float x) {
   return y;
 }
 __device__ __forceinline__ float gelu_fast(float x) {
-#if defined(RDSIC_GELU_EXACT)
+#if defined(RDSIC_GELU_NONE)  // profiling only: what the GELU arithmetic costs
+  return x;
+#elif defined(RDSIC_GELU_EXACT)
   return gelu_erf(x);
 #elif defined(RDSIC_GELU_AS)
   const float z = fabsf(x) * 0.70710678118654752440f;

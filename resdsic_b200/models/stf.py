@@ -94,6 +94,7 @@ class SymmetricalTransFormer(WACNN):
         self.entropy_bottleneck = EntropyBottleneck(N)
         self.gaussian_conditional = GaussianConditional(None)
         self.use_cuda_graph = True
+        self.micro_batches = 1
         self._plans = {}
 
     @classmethod

@@ -137,6 +137,28 @@ def test_config2_batch16_256_bf16_properties(model):
         model.set_precision("fp32")
 
 
+def test_micro_batches_are_bit_identical(model):
+    """A batch run as 2 or 4 concurrent sub-batch graphs gives exactly the bits of the single-program run
+    (symbols and indexes included): every kernel is independent of the batch it runs in."""
+    model.set_precision("bf16")
+    try:
+        x = weights.make_image(4, 128, 192, seed=7).to(DEV)
+        model.micro_batches = 1
+        ref = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in model.symbols_and_indexes(x).items()}
+        ref_lik = {k: v.clone() for k, v in ref["likelihoods"].items()}
+        for mb in (2, 4):
+            model.micro_batches = mb
+            got = model.symbols_and_indexes(x)
+            assert len(next(iter(model._plans.values())).subs) == mb
+            for k in ("x_hat", "y_symbols", "y_indexes", "z_symbols"):
+                assert torch.equal(got[k], ref[k]), (mb, k)
+            for k in ("y", "z"):
+                assert torch.equal(got["likelihoods"][k], ref_lik[k]), (mb, k)
+    finally:
+        model.micro_batches = 1
+        model.set_precision("fp32")
+
+
 def test_config5_clic_size_padding_and_index_build(model, synthetic_sd, scale_table):
     """BASELINE config 5: 1 x 3 x 1365 x 2048 -> caller padding rule (A0) -> 1408 x 2048 forward + the int32
     symbols / indexes of `compress`; fp32 mode against the CPU oracle on the same padded image (g_a / h_a

@@ -40,7 +40,8 @@ namespace {
 // each into its OWN accumulator (fixed summation order -> results stay bit-reproducible run to run); the
 // epilogue adds the two.
 constexpr int ISSUER2_WARP = 2 + NUM_EPI_WARPS;
-constexpr int CONV_THREADS = NUM_THREADS + 32;
+constexpr int PRODUCER2_WARP = ISSUER2_WARP + 1;
+constexpr int CONV_THREADS = NUM_THREADS + 64;
 
 template <int EPI, bool PLAIN>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
@@ -86,11 +87,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ================= TMA producer =================
+  if (warp == 0 || warp == PRODUCER2_WARP) {
+    // ================= TMA producers =================
     // NOTE: no integer division inside the per-stage loops -- this warp's latency paces the whole pipeline.
     if (g.halo) {
-      if (lane == 0) {
+      if (lane == 0 && warp == 0) {
         int s = 0, as = 0;
         uint32_t ph = 0, aph = 0;
         const uint32_t a_bytes = (uint32_t)(BK * 2 * g.halo_w * g.halo_h), b_bytes = (uint32_t)g.b_stage_bytes;
@@ -117,36 +118,63 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
     } else {
-      // whole warp, uniform control flow; one elected lane issues (see elect_one)
+      // Whole warp, uniform control flow, one elected lane issues (see elect_one).  Two producer warps
+      // (warp 0 and PRODUCER2_WARP) share the ring: one warp's wait -> expect_tx -> 2 x TMA chain (~400 cycles)
+      // could not feed two MMA issuers.  Ownership is by STAGE parity (the ring depth is even): a stage is
+      // always filled by the same producer and, in K-split mode, drained by the same issuer, so every thread
+      // meets each mbarrier's phases strictly in order.  (Splitting by k-iteration parity instead lets one
+      // thread get two phases ahead of a barrier whose previous use belongs to the other thread; the parity
+      // wait then aliases to an old phase and passes early -- seen as sporadic launch failures.)
+      const int pw = warp == 0 ? 0 : 1;
       const uint32_t tx_bytes = ((g.dbg_skip_load & 1) ? 0u : (uint32_t)A_STAGE_BYTES) +
                                 ((g.dbg_skip_load & 2) ? 0u : (uint32_t)g.b_stage_bytes);
       const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       const uint32_t full0 = __shfl_sync(0xffffffffu, smem_u32(full_bar), 0);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+      const uint32_t empty0 = __shfl_sync(0xffffffffu, smem_u32(empty_bar), 0);
+      int ns = g.num_stages, kb = g.kb_per_tap, kiters = d.KH * d.KW * g.kb_per_tap, total = g.total_tiles, step = gridDim.x;
+      int KW = d.KW, Cin = d.Cin;
+      asm volatile("" : "+r"(ns), "+r"(kb), "+r"(kiters), "+r"(total), "+r"(step), "+r"(KW), "+r"(Cin));
+      const int kq = kiters / ns, kr = kiters % ns;
+      int s_base = 0;
+      uint32_t ph_base = 0;
+      for (int tile = blockIdx.x; tile < total; tile += step) {
         const int nt = tile % g.n_tiles;
         int t = tile / g.n_tiles;
         const int tx = t % g.tiles_x;
         t /= g.tiles_x;
         const int ty = t % g.tiles_y, b = t / g.tiles_y;
         const int x0 = tx * g.TW * d.stride - d.pad_w, y0 = ty * g.TH * d.stride - d.pad_h, n0 = nt * g.BN;
-        int kcol = 0;  // K coordinate in the packed weight = tap * Cin + cb * 64
-        for (int r = 0; r < d.KH; ++r) {
-          for (int sx = 0; sx < d.KW; ++sx, kcol += d.Cin) {
-            for (int cb = 0; cb < g.kb_per_tap; ++cb) {
-              mbar_wait(&empty_bar[s], ph ^ 1u);
-              const uint32_t a_dst = smem_base + (uint32_t)(s * stage_bytes), bar = full0 + 8u * (uint32_t)s;
-              if (elect_one()) {
-                mbar_expect_tx_u32(bar, tx_bytes);
-                if (!(g.dbg_skip_load & 1)) tma_load_4d_u32(a_dst, &tmap_a, bar, cb * BK, x0 + sx, y0 + r, b);
-                if (!(g.dbg_skip_load & 2)) tma_load_2d_u32(a_dst + A_STAGE_BYTES, &tmap_b, bar, kcol + cb * BK, n0);
-              }
-              __syncwarp();
-              if (++s == g.num_stages) { s = 0; ph ^= 1u; }
-            }
+        // this producer's first k-iteration of the tile (the first whose stage has its parity): stage, filter
+        // tap and channel block
+        const int f = pw ^ (s_base & 1);
+        const int n_own = (kiters - f + 1) / 2;
+        int s = s_base + f;
+        uint32_t ph = ph_base;
+        if (s >= ns) { s -= ns; ph ^= 1u; }
+        int cb = f % kb, tap0 = f / kb;
+        int r = tap0 / KW, sx = tap0 % KW;
+        int kcol = tap0 * Cin;  // K coordinate in the packed weight = tap * Cin + cb * 64
+        for (int n = 0; n < n_own; ++n) {
+          mbar_wait_u32(empty0 + 8u * (uint32_t)s, ph ^ 1u);
+          const uint32_t a_dst = smem_base + (uint32_t)(s * stage_bytes), bar = full0 + 8u * (uint32_t)s;
+          if (elect_one()) {
+            mbar_expect_tx_u32(bar, tx_bytes);
+            if (!(g.dbg_skip_load & 1)) tma_load_4d_u32(a_dst, &tmap_a, bar, cb * BK, x0 + sx, y0 + r, b);
+            if (!(g.dbg_skip_load & 2)) tma_load_2d_u32(a_dst + A_STAGE_BYTES, &tmap_b, bar, kcol + cb * BK, n0);
+          }
+          __syncwarp();
+          s += 2;
+          if (s >= ns) { s -= ns; ph ^= 1u; }
+          cb += 2;
+          while (cb >= kb) {
+            cb -= kb;
+            kcol += Cin;
+            if (++sx == KW) { sx = 0; ++r; }
           }
         }
+        ph_base ^= (uint32_t)(kq & 1);
+        s_base += kr;
+        if (s_base >= ns) { s_base -= ns; ph_base ^= 1u; }
       }
     }
     __syncwarp();
@@ -195,91 +223,104 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     } else {
       // Whole warp in uniform control flow, one elected lane issues (see elect_one): every operand of the
-      // UTCHMMA then lives in uniform registers.  The loop is software-pipelined: the barrier wait for the
-      // NEXT stage sits between the two halves of this stage's MMAs, so the tensor pipe (whose queue holds
-      // only about one pending instruction -- an issue blocks until the pipe accepts it) always has work
-      // while this thread polls the mbarrier.
+      // UTCHMMA then lives in uniform registers.  The loops below are written for a minimal instruction count
+      // per k-iteration -- the issuing thread's own instruction stream (~120 instructions per k-iteration in
+      // the first version, against 4 x ~77 cycles for the MMAs themselves) paces layers with N <= 128:
+      //  * each issuer walks only its own k-iterations (stage index += ways, no skipped iterations),
+      //  * descriptors are one 64-bit add from a per-kernel constant (start-address field = smem address >> 4),
+      //  * kernel parameters used in the loop are pinned in registers (no constant-bank reloads),
+      //  * full 64-wide K blocks take a branch-free 4-MMA path.
       const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t empty0 = __shfl_sync(0xffffffffu, smem_u32(empty_bar), 0);
-      const int kiters = taps * g.kb_per_tap;
-      int s = 0, dbg_n = 0;
-      uint32_t ph = 0, lt = 0;
-      if (g.ksplit) {
-        // two issuers, alternate k-iterations, own accumulators; while one polls its barrier the other issues
-        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++lt) {
-          const uint32_t buf = g.acc_bufs == 2 ? (lt & 1u) : 0u, cph = g.acc_bufs == 2 ? ((lt >> 1) & 1u) : (lt & 1u);
-          mbar_wait(&acc_empty[buf], cph ^ 1u);
-          tcgen05_fence_after();
-          const uint32_t acc = tbase + buf * (uint32_t)g.acc_stride + me * (uint32_t)g.BN;
-          int cb = 0;
-          for (int it = 0; it < kiters; ++it) {
-            if ((uint32_t)(it & 1) == me) {
-              const bool ts = g.dbg_ts && !(g.dbg_skip_load & 4) && blockIdx.x == 0 && me == 0 && dbg_n < 1024 && lane == 0;
-              if (ts) g.dbg_ts[dbg_n * 4 + 0] = clock64();
-              mbar_wait(&full_bar[s], ph);
-              tcgen05_fence_after();
-              if (ts) g.dbg_ts[dbg_n * 4 + 1] = g.dbg_ts[dbg_n * 4 + 2] = clock64();
-              const int kc = cb + 1 == g.kb_per_tap ? kc_last : BK / 16;
-              const uint32_t a_addr = smem_base + (uint32_t)(s * stage_bytes);
-              const uint64_t da = make_sw128_desc(a_addr), db = make_sw128_desc(a_addr + A_STAGE_BYTES);
-              const uint32_t ebar = empty0 + 8u * (uint32_t)s;
-              if (elect_one()) {
-                for (int k = 0; k < kc; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (it > 1 || k > 0) ? 1u : 0u);
-                tcgen05_commit_u32(ebar);
-              }
-              __syncwarp();
-              if (ts) g.dbg_ts[dbg_n++ * 4 + 3] = clock64();
-            }
-            if (++s == g.num_stages) { s = 0; ph ^= 1u; }
-            if (++cb == g.kb_per_tap) cb = 0;
-          }
-          if (elect_one()) tcgen05_commit(&acc_full[buf]);  // this issuer's accumulator is complete
-          __syncwarp();
-        }
-      } else if (!me)
-      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++lt) {
+      const uint32_t full0 = __shfl_sync(0xffffffffu, smem_u32(full_bar), 0);
+      const uint64_t dconst = make_sw128_desc(0);                   // everything but the start-address field
+      const uint32_t a_u0 = (smem_base & 0x3FFFFu) >> 4, stage_u = (uint32_t)stage_bytes >> 4;
+      int ns = g.num_stages, kb = g.kb_per_tap, kiters = taps * g.kb_per_tap, total = g.total_tiles, step = gridDim.x;
+      asm volatile("" : "+r"(ns), "+r"(kb), "+r"(kiters), "+r"(total), "+r"(step));
+      const int ways = g.ksplit ? 2 : 1;
+      const int kq = kiters / ns, kr = kiters % ns;                  // per-tile advance of the stage ring
+      int s_base = 0, dbg_n = 0;
+      uint32_t ph_base = 0, lt = 0;
+      if (g.ksplit || !me)
+      for (int tile = blockIdx.x; tile < total; tile += step, ++lt) {
         const uint32_t buf = g.acc_bufs == 2 ? (lt & 1u) : 0u, cph = g.acc_bufs == 2 ? ((lt >> 1) & 1u) : (lt & 1u);
+        // this issuer's first k-iteration of the tile: K-split ownership is by stage parity (see the producers)
+        const int f = g.ksplit ? (int)me ^ (s_base & 1) : 0;
+        int s = s_base + f;
+        uint32_t ph = ph_base;
+        if (s >= ns) { s -= ns; ph ^= 1u; }
+        int cb = f % kb;
+        const int n_own = (kiters - f + ways - 1) / ways;
         mbar_wait(&acc_empty[buf], cph ^ 1u);  // epilogue has drained this accumulator buffer
-        mbar_wait(&full_bar[s], ph);           // first stage of the tile
-        tcgen05_fence_after();
-        const uint32_t acc = tbase + buf * (uint32_t)g.acc_stride;
-        int cb = 0;
-        for (int it = 0; it < kiters; ++it) {
-          const bool ts = g.dbg_ts && !(g.dbg_skip_load & 4) && blockIdx.x == 0 && dbg_n < 1024 && lane == 0;
-          if (ts) g.dbg_ts[dbg_n * 4 + 0] = clock64();
-          const int kc = cb + 1 == g.kb_per_tap ? kc_last : BK / 16;
-          const uint32_t a_addr = smem_base + (uint32_t)(s * stage_bytes);
-          const uint64_t da = make_sw128_desc(a_addr), db = make_sw128_desc(a_addr + A_STAGE_BYTES);
-          const uint32_t ebar = empty0 + 8u * (uint32_t)s;
-          // +32 bytes (= 2 x 16 B units) per 16 bf16 of K inside the swizzle atom
-          if (elect_one()) {
-            umma_bf16(acc, da, db, idesc, it > 0 ? 1u : 0u);
-            if (kc > 1) umma_bf16(acc, da + 2, db + 2, idesc, 1u);
-          }
-          __syncwarp();
-          if (ts) g.dbg_ts[dbg_n * 4 + 1] = clock64();
-          int s1 = s + 1;
-          uint32_t ph1 = ph;
-          if (s1 == g.num_stages) { s1 = 0; ph1 ^= 1u; }
-          if (it + 1 < kiters) {
-            mbar_wait(&full_bar[s1], ph1);
+        const uint32_t acc = tbase + buf * (uint32_t)g.acc_stride + me * (uint32_t)g.BN;
+        if (g.ksplit) {
+          // two issuers, alternate k-iterations, own accumulators; while one polls its barrier the other issues
+          tcgen05_fence_after();
+          for (int n = 0; n < n_own; ++n) {
+            const bool ts = g.dbg_ts && !(g.dbg_skip_load & 4) && blockIdx.x == 0 && me == 0 && dbg_n < 1024 && lane == 0;
+            if (ts) g.dbg_ts[dbg_n * 4 + 0] = clock64();
+            mbar_wait_u32(full0 + 8u * (uint32_t)s, ph);
             tcgen05_fence_after();
+            if (ts) g.dbg_ts[dbg_n * 4 + 1] = g.dbg_ts[dbg_n * 4 + 2] = clock64();
+            const uint64_t da = dconst + (uint64_t)(a_u0 + (uint32_t)s * stage_u), db = da + (A_STAGE_BYTES >> 4);
+            if (elect_one()) {
+              if (cb + 1 != kb || kc_last == 4) {  // full block: +32 bytes (2 x 16 B units) per 16 bf16 of K
+                umma_bf16(acc, da, db, idesc, n > 0 ? 1u : 0u);
+                umma_bf16(acc, da + 2, db + 2, idesc, 1u);
+                umma_bf16(acc, da + 4, db + 4, idesc, 1u);
+                umma_bf16(acc, da + 6, db + 6, idesc, 1u);
+              } else {
+                for (int k = 0; k < kc_last; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (n > 0 || k > 0) ? 1u : 0u);
+              }
+              tcgen05_commit_u32(empty0 + 8u * (uint32_t)s);
+            }
+            __syncwarp();
+            if (ts) g.dbg_ts[dbg_n++ * 4 + 3] = clock64();
+            s += 2;
+            if (s >= ns) { s -= ns; ph ^= 1u; }
+            cb += 2;
+            while (cb >= kb) cb -= kb;
           }
-          if (ts) g.dbg_ts[dbg_n * 4 + 2] = clock64();
-          if (elect_one()) {
-            if (kc > 2) umma_bf16(acc, da + 4, db + 4, idesc, 1u);
-            if (kc > 3) umma_bf16(acc, da + 6, db + 6, idesc, 1u);
-            tcgen05_commit_u32(ebar);  // frees the smem slot when these MMAs retire
+        } else {
+          // single issuer, software-pipelined: the barrier wait for the NEXT stage sits between the two halves
+          // of this stage's MMAs, so the tensor pipe has work queued while this thread polls the mbarrier
+          mbar_wait_u32(full0 + 8u * (uint32_t)s, ph);  // first stage of the tile
+          tcgen05_fence_after();
+          for (int n = 0; n < kiters; ++n) {
+            const bool ts = g.dbg_ts && !(g.dbg_skip_load & 4) && blockIdx.x == 0 && dbg_n < 1024 && lane == 0;
+            if (ts) g.dbg_ts[dbg_n * 4 + 0] = clock64();
+            const int kc = cb + 1 == kb ? kc_last : BK / 16;
+            const uint64_t da = dconst + (uint64_t)(a_u0 + (uint32_t)s * stage_u), db = da + (A_STAGE_BYTES >> 4);
+            const uint32_t ebar = empty0 + 8u * (uint32_t)s;
+            if (elect_one()) {
+              umma_bf16(acc, da, db, idesc, n > 0 ? 1u : 0u);
+              if (kc > 1) umma_bf16(acc, da + 2, db + 2, idesc, 1u);
+            }
+            __syncwarp();
+            if (ts) g.dbg_ts[dbg_n * 4 + 1] = clock64();
+            if (++s == ns) { s = 0; ph ^= 1u; }
+            if (n + 1 < kiters) {
+              mbar_wait_u32(full0 + 8u * (uint32_t)s, ph);
+              tcgen05_fence_after();
+            }
+            if (ts) g.dbg_ts[dbg_n * 4 + 2] = clock64();
+            if (elect_one()) {
+              if (kc > 2) umma_bf16(acc, da + 4, db + 4, idesc, 1u);
+              if (kc > 3) umma_bf16(acc, da + 6, db + 6, idesc, 1u);
+              tcgen05_commit_u32(ebar);  // frees the smem slot when these MMAs retire
+            }
+            __syncwarp();
+            if (ts) g.dbg_ts[dbg_n++ * 4 + 3] = clock64();
+            if (++cb == kb) cb = 0;
           }
-          __syncwarp();
-          if (ts) g.dbg_ts[dbg_n++ * 4 + 3] = clock64();
-          s = s1;
-          ph = ph1;
-          if (++cb == g.kb_per_tap) cb = 0;
         }
-        if (elect_one()) tcgen05_commit(&acc_full[buf]);  // accumulator complete
+        if (elect_one()) tcgen05_commit(&acc_full[buf]);  // (this issuer's) accumulator complete
         __syncwarp();
+        // stage ring position of the next tile's first k-iteration
+        ph_base ^= (uint32_t)(kq & 1);
+        s_base += kr;
+        if (s_base >= ns) { s_base -= ns; ph_base ^= 1u; }
       }
     }
     __syncwarp();
@@ -571,19 +612,19 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   int stages = (200 * 1024 - (g.halo ? 2 * g.a_halo_bytes : 0)) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (tune_stages > 0 && tune_stages < stages) stages = tune_stages;
+  if (!g.halo) stages &= ~1;  // even ring depth: stage parity = owner (two producers / two issuers)
   if (stages < 2) return RDSIC_E_ARG;
   g.num_stages = stages;
-  // K-split across two issuer warps (see the kernel's header comment), only where BOTH accumulator sets of the
-  // usual double buffering fit the 512 TMEM columns (bn_layer <= 128).  A single-buffered variant for wider
-  // tiles (RDSIC_TC_KSPLIT=2) is faster on the 5x5 / deconv layers but intermittently faults
-  // (cudaErrorLaunchFailure, no barrier timeout logged) when other kernels run concurrently -- bn_layer = 192
-  // only, never in isolation -- so it stays an experiment; see DESIGN.md.
+  // K-split across two issuer warps (see the kernel's header comment) wherever both accumulators fit TMEM.
+  // The accumulator set stays double-buffered across tiles while two sets fit the 512 columns (bn_layer <=
+  // 128); wider tiles run single-buffered, which only pays when the main loop dwarfs the then exposed
+  // epilogue (>= 16 k-iterations).
   // The decision uses only layer properties (Cout, K) -- never the grid-dependent N split above -- so that the
   // fp32 summation order, hence every output bit, is independent of batch size and image size.
   static const int tune_ksplit = getenv("RDSIC_TC_KSPLIT") ? atoi(getenv("RDSIC_TC_KSPLIT")) : 1;
   const int bn_layer = pick_bn(d->Cout);
   g.ksplit = tune_ksplit && !g.halo && g.num_k_iters >= 4 &&
-             (4 * bn_layer <= 512 || (tune_ksplit == 2 && 2 * bn_layer <= 512 && g.num_k_iters >= 16));
+             (4 * bn_layer <= 512 || (tune_ksplit != 3 && 2 * bn_layer <= 512 && g.num_k_iters >= 16));
   g.acc_stride = g.BN * (1 + g.ksplit);
   g.acc_bufs = 2 * g.acc_stride <= 512 ? 2 : 1;
   g.tmem_cols = 32;

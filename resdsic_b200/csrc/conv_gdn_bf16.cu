@@ -21,7 +21,8 @@ namespace {
 
 constexpr int G_EPI_WARPS = 12;
 constexpr int G_ISSUER2_WARP = 2 + G_EPI_WARPS;
-constexpr int G_THREADS = 96 + 32 * G_EPI_WARPS;  // TMA warp, two MMA issuer warps, epilogue warps
+constexpr int G_PRODUCER2_WARP = G_ISSUER2_WARP + 1;
+constexpr int G_THREADS = 128 + 32 * G_EPI_WARPS;  // two TMA warps, two MMA issuer warps, epilogue warps
 constexpr int G_PARTS = G_EPI_WARPS / 4;
 constexpr int MAXC = 192;                    // channel count supported (TMEM: 2.5 C <= 512)
 constexpr int MAX_CHUNKS = MAXC / 16 / G_PARTS;
@@ -98,47 +99,65 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ================= TMA producer =================
-    // whole warp in uniform control flow, one elected lane issues (see elect_one in tc_common.cuh)
+  if (warp == 0 || warp == G_PRODUCER2_WARP) {
+    // ================= TMA producers =================
+    // whole warp in uniform control flow, one elected lane issues (see elect_one in tc_common.cuh); two
+    // producer warps take alternate k-iterations (see conv_bf16.cu)
     {
-      if (elect_one()) {
-        // second-GEMM weights once per CTA: K2/64 blocks of [N2 rows x 128 B]
-        mbar_expect_tx(g_full, (uint32_t)gg.w2_bytes);
-        for (int kb = 0; kb < gg.k2_blocks; ++kb) tma_load_2d(gamma_s + (size_t)kb * gg.N2 * 128, &tmap_g, g_full, kb * BK, 0);
+      const int pw = warp == 0 ? 0 : 1;
+      if (pw == 0) {
+        if (elect_one()) {
+          // second-GEMM weights once per CTA: K2/64 blocks of [N2 rows x 128 B]
+          mbar_expect_tx(g_full, (uint32_t)gg.w2_bytes);
+          for (int kb = 0; kb < gg.k2_blocks; ++kb) tma_load_2d(gamma_s + (size_t)kb * gg.N2 * 128, &tmap_g, g_full, kb * BK, 0);
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      const uint32_t tx_bytes = (uint32_t)stage_bytes;
+      const uint32_t tx_bytes = (g.dbg_skip_load & 1) ? (uint32_t)g.b_stage_bytes : (uint32_t)stage_bytes;
       const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       const uint32_t full0 = __shfl_sync(0xffffffffu, smem_u32(full_bar), 0);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+      const uint32_t empty0 = __shfl_sync(0xffffffffu, smem_u32(empty_bar), 0);
+      int ns = g.num_stages, kb = g.kb_per_tap, kiters = d.KH * d.KW * g.kb_per_tap, total = g.total_tiles, step = gridDim.x;
+      int KW = d.KW, Cin = d.Cin;
+      asm volatile("" : "+r"(ns), "+r"(kb), "+r"(kiters), "+r"(total), "+r"(step), "+r"(KW), "+r"(Cin));
+      const int kq = kiters / ns, kr = kiters % ns;
+      int s_base = 0;
+      uint32_t ph_base = 0;
+      for (int tile = blockIdx.x; tile < total; tile += step) {
         int t = tile;
         const int tx = t % g.tiles_x;
         t /= g.tiles_x;
         const int ty = t % g.tiles_y, b = t / g.tiles_y;
         const int x0 = tx * g.TW * d.stride - d.pad_w, y0 = ty * g.TH * d.stride - d.pad_h;
-        int kcol = 0;
-        for (int r = 0; r < d.KH; ++r) {
-          for (int sx = 0; sx < d.KW; ++sx, kcol += d.Cin) {
-            for (int cb = 0; cb < g.kb_per_tap; ++cb) {
-              mbar_wait(&empty_bar[s], ph ^ 1u);
-              const uint32_t a_dst = smem_base + (uint32_t)(s * stage_bytes), bar = full0 + 8u * (uint32_t)s;
-              if (elect_one()) {
-                if (g.dbg_skip_load & 1) {  // profiling only: no A loads
-                  mbar_expect_tx_u32(bar, (uint32_t)g.b_stage_bytes);
-                } else {
-                  mbar_expect_tx_u32(bar, tx_bytes);
-                  tma_load_4d_u32(a_dst, &tmap_a, bar, cb * BK, x0 + sx, y0 + r, b);
-                }
-                tma_load_2d_u32(a_dst + A_STAGE_BYTES, &tmap_b, bar, kcol + cb * BK, 0);
-              }
-              __syncwarp();
-              if (++s == g.num_stages) { s = 0; ph ^= 1u; }
-            }
+        const int f = pw ^ (s_base & 1);  // ownership by stage parity (even ring depth), see conv_bf16.cu
+        const int n_own = (kiters - f + 1) / 2;
+        int s = s_base + f;
+        uint32_t ph = ph_base;
+        if (s >= ns) { s -= ns; ph ^= 1u; }
+        int cb = f % kb, tap0 = f / kb;
+        int r = tap0 / KW, sx = tap0 % KW;
+        int kcol = tap0 * Cin;
+        for (int n = 0; n < n_own; ++n) {
+          mbar_wait_u32(empty0 + 8u * (uint32_t)s, ph ^ 1u);
+          const uint32_t a_dst = smem_base + (uint32_t)(s * stage_bytes), bar = full0 + 8u * (uint32_t)s;
+          if (elect_one()) {
+            mbar_expect_tx_u32(bar, tx_bytes);
+            if (!(g.dbg_skip_load & 1)) tma_load_4d_u32(a_dst, &tmap_a, bar, cb * BK, x0 + sx, y0 + r, b);
+            tma_load_2d_u32(a_dst + A_STAGE_BYTES, &tmap_b, bar, kcol + cb * BK, 0);
+          }
+          __syncwarp();
+          s += 2;
+          if (s >= ns) { s -= ns; ph ^= 1u; }
+          cb += 2;
+          while (cb >= kb) {
+            cb -= kb;
+            kcol += Cin;
+            if (++sx == KW) { sx = 0; ++r; }
           }
         }
+        ph_base ^= (uint32_t)(kq & 1);
+        s_base += kr;
+        if (s_base >= ns) { s_base -= ns; ph_base ^= 1u; }
       }
     }
     __syncwarp();
@@ -154,43 +173,56 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const uint32_t gamma_addr = __shfl_sync(0xffffffffu, smem_u32(gamma_s), 0);
       const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       const uint32_t empty0 = __shfl_sync(0xffffffffu, smem_u32(empty_bar), 0);
-      int s = 0;
-      uint32_t ph = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++lt) {
+      // (loop written for a minimal instruction count per k-iteration, see conv_bf16.cu)
+      const uint32_t full0 = __shfl_sync(0xffffffffu, smem_u32(full_bar), 0);
+      const uint64_t dconst = make_sw128_desc(0);
+      const uint32_t a_u0 = (smem_base & 0x3FFFFu) >> 4, stage_u = (uint32_t)stage_bytes >> 4;
+      int ns = g.num_stages, kb = g.kb_per_tap, kiters = taps * g.kb_per_tap, total = g.total_tiles, step = gridDim.x;
+      asm volatile("" : "+r"(ns), "+r"(kb), "+r"(kiters), "+r"(total), "+r"(step));
+      const int ways = gg.ksplit ? 2 : 1;
+      const int kq = kiters / ns, kr = kiters % ns;
+      int s_base = 0;
+      uint32_t ph_base = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < total; tile += step, ++lt) {
         const uint32_t par = lt & 1u;
-        // profiling aid (RDSIC_TC_DBG_TS=1, tests/gpu_issue_trace.py): 16 clock64 stamps per tile of CTA 0,
+        // profiling aid (RDSIC_TC_DBG_TS=1, tests/gpu_ru_trace.py): 16 clock64 stamps per tile of CTA 0,
         // slots 0-5 written by issuer 0, slots 8-12 by the first epilogue warp
         long long* tsp = (g.dbg_ts && blockIdx.x == 0 && !me && lane == 0 && lt < 250) ? g.dbg_ts + lt * 16 : nullptr;
         if (tsp) tsp[0] = clock64();
+        const int f = gg.ksplit ? (int)me ^ (s_base & 1) : 0;  // K-split ownership by stage parity
+        int s = s_base + f;
+        uint32_t ph = ph_base;
+        if (s >= ns) { s -= ns; ph ^= 1u; }
+        int cb = f % kb;
+        const int n_own = (kiters - f + ways - 1) / ways;
         // ---- GEMM 1: x = conv(in)
         mbar_wait(acc1_empty, par ^ 1u);
         tcgen05_fence_after();
         if (tsp) tsp[1] = clock64();
-        uint32_t accumulate = 0, turn = 0;
-        for (int tap = 0; tap < taps; ++tap) {
-          for (int cb = 0; cb < g.kb_per_tap; ++cb, turn ^= 1u) {
-            if (gg.ksplit && turn != me) {  // the other issuer's k-iteration
-              if (++s == g.num_stages) { s = 0; ph ^= 1u; }
-              continue;
+        for (int n = 0; n < n_own; ++n) {
+          mbar_wait_u32(full0 + 8u * (uint32_t)s, ph);
+          tcgen05_fence_after();
+          const uint64_t da = dconst + (uint64_t)(a_u0 + (uint32_t)s * stage_u), db = da + (A_STAGE_BYTES >> 4);
+          if (elect_one()) {
+            if (cb + 1 != kb || kc_last == 4) {
+              umma_bf16(acc1, da, db, idesc, n > 0 ? 1u : 0u);
+              umma_bf16(acc1, da + 2, db + 2, idesc, 1u);
+              umma_bf16(acc1, da + 4, db + 4, idesc, 1u);
+              umma_bf16(acc1, da + 6, db + 6, idesc, 1u);
+            } else {
+              for (int k = 0; k < kc_last; ++k) umma_bf16(acc1, da + 2 * k, db + 2 * k, idesc, (n > 0 || k > 0) ? 1u : 0u);
             }
-            long long* ksp = (tsp && lt == 3) ? g.dbg_ts + 2048 + (tap * g.kb_per_tap + cb) * 4 : nullptr;  // k-loop detail of tile 3
-            if (ksp) ksp[0] = clock64();
-            mbar_wait(&full_bar[s], ph);
-            tcgen05_fence_after();
-            if (ksp) ksp[1] = clock64();
-            const int kc = cb + 1 == g.kb_per_tap ? kc_last : BK / 16;
-            const uint32_t a_addr = smem_base + (uint32_t)(s * stage_bytes);
-            const uint64_t da = make_sw128_desc(a_addr), db = make_sw128_desc(a_addr + A_STAGE_BYTES);
-            if (elect_one()) {
-              for (int k = 0; k < kc; ++k) umma_bf16(acc1, da + 2 * k, db + 2 * k, idesc, accumulate | (uint32_t)(k > 0));
-              tcgen05_commit_u32(empty0 + 8u * (uint32_t)s);
-            }
-            __syncwarp();
-            if (ksp) ksp[2] = clock64();
-            accumulate = 1;
-            if (++s == g.num_stages) { s = 0; ph ^= 1u; }
+            tcgen05_commit_u32(empty0 + 8u * (uint32_t)s);
           }
+          __syncwarp();
+          s += ways;
+          if (s >= ns) { s -= ns; ph ^= 1u; }
+          cb += ways;
+          while (cb >= kb) cb -= kb;
         }
+        ph_base ^= (uint32_t)(kq & 1);
+        s_base += kr;
+        if (s_base >= ns) { s_base -= ns; ph_base ^= 1u; }
         if (elect_one()) tcgen05_commit(acc1_full);
         __syncwarp();
         if (me) continue;
@@ -430,6 +462,7 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   const int stage_bytes = A_STAGE_BYTES + g.b_stage_bytes;
   int stages = (200 * 1024 - gg.w2_bytes) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
+  stages &= ~1;  // even ring depth: stage parity = owner (two producers / two issuers)
   if (stages < 2) return RDSIC_E_ARG;
   g.num_stages = stages;
   RDSIC_CHECK_ARG(g.TW * d->stride <= 256 && g.TH * d->stride <= 256);

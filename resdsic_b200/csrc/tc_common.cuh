@@ -74,6 +74,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+__device__ __forceinline__ void mbar_wait_u32(uint32_t addr, uint32_t parity) {  // shared-window address variant
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > SPIN_LIMIT) __trap();
+  }
+}
 // One lane of a converged warp (elect.sync).  The TMA / MMA loops are run by their WHOLE warp in uniform
 // control flow and only the issue itself is predicated: a loop entered by a single lane is divergent code,
 // where the compiler cannot use uniform registers and wraps every UTCHMMA / UTMALDG operand in an

@@ -186,12 +186,82 @@ __global__ void __launch_bounds__(256) patchify_kernel(const rdsic_patch_desc d)
   }
 }
 
+// Tiled variant for the network's first layer (NCHW fp32 image, few channels): one CTA stages the input
+// window of a PT_H x PT_W block of output pixels in shared memory with coalesced row reads, then its threads
+// walk the block's (pixel, 16-byte chunk) items in destination order, so every store instruction writes 512
+// contiguous bytes.  The gather indices come from a k -> window-offset table built once per CTA.  HBM traffic
+// is the image once plus the patch matrix once (the generic kernel above spends ~10x that time on integer
+// divisions and scattered 4-byte reads).
+constexpr int PT_H = 4, PT_W = 64, PT_MAX_K = 128, PT_MAX_TILE = 9216;  // tile floats (36 KB) + table < 48 KB
+
+__global__ void __launch_bounds__(256) patchify_tiled_kernel(const rdsic_patch_desc d, int tiles_x, int tiles_y) {
+  __shared__ float tile[PT_MAX_TILE];
+  __shared__ int lut[PT_MAX_K];
+  const int rows = (PT_H - 1) * d.stride + d.KH, cols = (PT_W - 1) * d.stride + d.KW, pitch = cols | 1;  // odd pitch
+  const int plane = rows * pitch;
+  int t = blockIdx.x;
+  const int tx = t % tiles_x;
+  t /= tiles_x;
+  const int ty = t % tiles_y, b = t / tiles_y;
+  const int ox0 = tx * PT_W, oy0 = ty * PT_H;
+  const int ix0 = ox0 * d.stride - d.pad, iy0 = oy0 * d.stride - d.pad;
+  const int Kreal = d.KH * d.KW * d.C;
+  for (int k = threadIdx.x; k < d.Kp; k += blockDim.x) {
+    int off = -1;
+    if (k < Kreal) {
+      const int tap = k / d.C, c = k - tap * d.C;
+      const int r = tap / d.KW, sx = tap - r * d.KW;
+      off = c * plane + r * pitch + sx;
+    }
+    lut[k] = off;
+  }
+  const float* src = (const float*)d.src.ptr;
+  for (int e = threadIdx.x; e < d.C * rows * cols; e += blockDim.x) {
+    const int rx = e % cols;
+    int q = e / cols;
+    const int ry = q % rows, c = q / rows;
+    const int iy = iy0 + ry, ix = ix0 + rx;
+    float v = 0.f;
+    if (iy >= 0 && iy < d.H && ix >= 0 && ix < d.W) v = __ldg(src + (((size_t)b * d.C + c) * d.H + iy) * d.W + ix);
+    tile[c * plane + ry * pitch + rx] = v;
+  }
+  __syncthreads();
+  const int chunks = d.Kp / 8;
+  __nv_bfloat16* dst = (__nv_bfloat16*)d.dst.ptr;
+  for (int e = threadIdx.x; e < PT_H * PT_W * chunks; e += blockDim.x) {
+    const int ch = e % chunks, p = e / chunks;
+    const int lx = p % PT_W, ly = p / PT_W;
+    const int ox = ox0 + lx, oy = oy0 + ly;
+    if (ox >= d.OW || oy >= d.OH) continue;
+    const int base = ly * d.stride * pitch + lx * d.stride;
+    uint32_t w[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const int o0 = lut[ch * 8 + 2 * h], o1 = lut[ch * 8 + 2 * h + 1];
+      __nv_bfloat162 hh = __floats2bfloat162_rn(o0 >= 0 ? tile[base + o0] : 0.f, o1 >= 0 ? tile[base + o1] : 0.f);
+      w[h] = *reinterpret_cast<uint32_t*>(&hh);
+    }
+    const size_t pix = ((size_t)b * d.OH + oy) * d.OW + ox;
+    *(reinterpret_cast<uint4*>(dst + pix * (size_t)d.dst.ld + d.dst.coff) + ch) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 }  // namespace
 
 extern "C" int rdsic_patch_forward(const rdsic_patch_desc* d, rdsic_stream_t stream) {
   RDSIC_CHECK_ARG(d && d->src.ptr && d->dst.ptr && d->B > 0 && d->C > 0 && d->KH > 0 && d->KW > 0 && d->stride > 0);
   RDSIC_CHECK_ARG(d->Kp % 16 == 0 && d->Kp >= d->KH * d->KW * d->C && !d->dst.nchw);
   if (d->dst.ld % 8 || d->dst.coff % 8 || ((uintptr_t)d->dst.ptr % 16)) return RDSIC_E_ALIGN;
+  {
+    const int rows = (PT_H - 1) * d->stride + d->KH, cols = (PT_W - 1) * d->stride + d->KW;
+    const long tile_floats = (long)d->C * rows * (cols | 1);
+    if (d->src.nchw && d->src.dtype == RDSIC_F32 && d->dst.dtype == RDSIC_BF16 && d->Kp <= PT_MAX_K &&
+        tile_floats <= PT_MAX_TILE) {
+      const int tiles_x = ceil_div(d->OW, PT_W), tiles_y = ceil_div(d->OH, PT_H);
+      patchify_tiled_kernel<<<(unsigned)((size_t)d->B * tiles_y * tiles_x), 256, 0, (cudaStream_t)stream>>>(*d, tiles_x, tiles_y);
+      return rdsic_launch_status();
+    }
+  }
   const size_t total = (size_t)d->B * d->OH * d->OW * (d->Kp / 8);
   const size_t want = (total + 255) / 256;
   patchify_kernel<<<(unsigned)(want < 148 * 16 ? want : 148 * 16), 256, 0, (cudaStream_t)stream>>>(*d);

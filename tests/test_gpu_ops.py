@@ -222,3 +222,24 @@ def test_swin_block_vs_reference_tcm_golden(gold, precision, tol):
         out = blk.forward_nhwc(x.to(DEV)).cpu().numpy()
         err = np.abs(out - gold[name])
         assert err.max() <= tol * max(1.0, np.abs(gold[name]).max()), (name, precision, err.max())
+
+
+@pytest.mark.parametrize("C,k,s,p,B,H,W", [(3, 5, 2, 2, 2, 40, 72), (3, 5, 2, 2, 1, 64, 328), (3, 2, 2, 0, 2, 32, 48),
+                                            (4, 3, 1, 1, 1, 9, 70), (16, 3, 1, 1, 1, 8, 8)])
+def test_patchify_matches_unfold(C, k, s, p, B, H, W):
+    """im2col of the first layer (tiled kernel for NCHW fp32 images with few channels, generic kernel
+    otherwise): exactly torch's unfold, tap-major / channel-minor, zero padded to Kp, rounded to bf16."""
+    from resdsic_b200.program import Program, TV
+    x = weights.hash_symmetric(f"patch.{C}.{k}.{H}.{W}", (B, C, H, W), 2.0).to(DEV)
+    OH, OW = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    Kp = -(-(k * k * C) // 16) * 16
+    prog = Program(DEV)
+    out = TV(torch.full((B * OH * OW * Kp,), 7.0, device=DEV, dtype=torch.bfloat16), B, OH, OW, Kp)
+    prog.patchify(TV.nchw_of(x), out, k, k, s, p)
+    prog.run()
+    torch.cuda.synchronize()
+    got = out.t.view(B, OH, OW, Kp).float()
+    cols = torch.nn.functional.unfold(x, k, padding=p, stride=s)            # [B, C*k*k, OH*OW], channel-major
+    want = cols.view(B, C, k * k, OH, OW).permute(0, 3, 4, 2, 1).reshape(B, OH, OW, k * k * C)
+    assert torch.equal(got[..., :k * k * C], want.bfloat16().float())
+    assert (got[..., k * k * C:] == 0).all()

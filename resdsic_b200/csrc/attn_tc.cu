@@ -80,11 +80,15 @@ __global__ void __launch_bounds__(768) win_attn_tc_kernel(const rdsic_attn_desc 
   {
     const int VPT = 3 * C / 8;  // 16-byte vectors per token
     const __nv_bfloat16* src = (const __nv_bfloat16*)d.qkv.ptr;
+    // asynchronous 16-byte copies: all of a thread's ~18 loads are in flight at once (a plain load/store
+    // loop serialised them -- ~1 us of DRAM latency each -- and made the staging 80 % of the kernel's time)
     for (int e = tid; e < NTOK * VPT; e += NTHR) {
       const int tok = e / VPT, v = e % VPT;
-      const uint4 val = *reinterpret_cast<const uint4*>(src + pixs[tok] * (size_t)d.qkv.ld + d.qkv.coff + v * 8);
-      *reinterpret_cast<uint4*>(qkv + tok * LD + v * 8) = val;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(qkv + tok * LD + v * 8);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst),
+                   "l"(src + pixs[tok] * (size_t)d.qkv.ld + d.qkv.coff + v * 8) : "memory");
     }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
 

@@ -50,7 +50,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int stage_bytes = g.halo ? g.b_stage_bytes : A_STAGE_BYTES + g.b_stage_bytes;
+  const int stage_bytes = g.halo ? g.b_stage_bytes : g.a_stage_bytes + g.b_stage_bytes;
   uint64_t* full_bar = (uint64_t*)(smem + (size_t)g.num_stages * stage_bytes + (g.halo ? 2 * g.a_halo_bytes : 0));
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* acc_full = empty_bar + MAX_STAGES;   // [2] MMA -> epilogue
@@ -68,10 +68,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_b) : "memory");
     for (int s = 0; s < g.num_stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], g.m2 ? 2 : 1);  // M2: both issuers drain every stage
     }
     for (int k = 0; k < 2; ++k) {
-      mbar_init(&acc_full[k], g.ksplit ? 2 : 1);
+      mbar_init(&acc_full[k], (g.ksplit || g.m2) ? 2 : 1);
       mbar_init(&acc_empty[k], NUM_EPI_WARPS);
       mbar_init(&a_full[k], 1);
       mbar_init(&a_empty[k], 1);
@@ -126,7 +126,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // thread get two phases ahead of a barrier whose previous use belongs to the other thread; the parity
       // wait then aliases to an old phase and passes early -- seen as sporadic launch failures.)
       const int pw = warp == 0 ? 0 : 1;
-      const uint32_t tx_bytes = ((g.dbg_skip_load & 1) ? 0u : (uint32_t)A_STAGE_BYTES) +
+      const uint32_t a_bytes = (uint32_t)g.a_stage_bytes;
+      const uint32_t tx_bytes = ((g.dbg_skip_load & 1) ? 0u : a_bytes) +
                                 ((g.dbg_skip_load & 2) ? 0u : (uint32_t)g.b_stage_bytes);
       const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       const uint32_t full0 = __shfl_sync(0xffffffffu, smem_u32(full_bar), 0);
@@ -137,6 +138,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int kq = kiters / ns, kr = kiters % ns;
       int s_base = 0;
       uint32_t ph_base = 0;
+      if (g.m2) {
+        // M2: one producer walks every stage in ring order (a stage carries a 256-row A box, so the per-stage
+        // issue chain is amortised over twice the MMAs; the ring depth may be odd)
+        if (pw == 0) {
+          int s = 0;
+          uint32_t ph = 0;
+          for (int tile = blockIdx.x; tile < total; tile += step) {
+            const int nt = tile % g.n_tiles;
+            int t = tile / g.n_tiles;
+            const int tx = t % g.tiles_x;
+            t /= g.tiles_x;
+            const int ty = t % g.tiles_y, b = t / g.tiles_y;
+            const int x0 = tx * g.TW * d.stride - d.pad_w, y0 = ty * g.TH * d.stride - d.pad_h, n0 = nt * g.BN;
+            int cb = 0, r = 0, sx = 0, kcol = 0;
+            for (int n = 0; n < kiters; ++n) {
+              mbar_wait_u32(empty0 + 8u * (uint32_t)s, ph ^ 1u);
+              const uint32_t a_dst = smem_base + (uint32_t)(s * stage_bytes), bar = full0 + 8u * (uint32_t)s;
+              if (elect_one()) {
+                mbar_expect_tx_u32(bar, tx_bytes);
+                if (!(g.dbg_skip_load & 1)) tma_load_4d_u32(a_dst, &tmap_a, bar, cb * BK, x0 + sx, y0 + r, b);
+                if (!(g.dbg_skip_load & 2)) tma_load_2d_u32(a_dst + a_bytes, &tmap_b, bar, kcol + cb * BK, n0);
+              }
+              __syncwarp();
+              if (++s == ns) { s = 0; ph ^= 1u; }
+              if (++cb == kb) {
+                cb = 0;
+                kcol += Cin;
+                if (++sx == KW) { sx = 0; ++r; }
+              }
+            }
+          }
+        }
+      } else
       for (int tile = blockIdx.x; tile < total; tile += step) {
         const int nt = tile % g.n_tiles;
         int t = tile / g.n_tiles;
@@ -160,7 +194,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (elect_one()) {
             mbar_expect_tx_u32(bar, tx_bytes);
             if (!(g.dbg_skip_load & 1)) tma_load_4d_u32(a_dst, &tmap_a, bar, cb * BK, x0 + sx, y0 + r, b);
-            if (!(g.dbg_skip_load & 2)) tma_load_2d_u32(a_dst + A_STAGE_BYTES, &tmap_b, bar, kcol + cb * BK, n0);
+            if (!(g.dbg_skip_load & 2)) tma_load_2d_u32(a_dst + a_bytes, &tmap_b, bar, kcol + cb * BK, n0);
           }
           __syncwarp();
           s += 2;
@@ -242,7 +276,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int kq = kiters / ns, kr = kiters % ns;                  // per-tile advance of the stage ring
       int s_base = 0, dbg_n = 0;
       uint32_t ph_base = 0, lt = 0;
-      if (g.ksplit || !me)
+      if (g.m2) {
+        // M2: both issuers visit EVERY stage in ring order; issuer `me` multiplies rows [128 me, 128 me + 128) of
+        // the 256-row A stage with the shared B stage into its own accumulator (columns me * BN).  K runs
+        // sequentially in one accumulator, so the fp32 summation order equals the single-issuer path's.
+        const uint32_t a_half = me * (uint32_t)(A_STAGE_BYTES >> 4), b_off = (uint32_t)g.a_stage_bytes >> 4;
+        int s = 0, cb = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < total; tile += step, ++lt) {
+          const uint32_t buf = g.acc_bufs == 2 ? (lt & 1u) : 0u, cph = g.acc_bufs == 2 ? ((lt >> 1) & 1u) : (lt & 1u);
+          mbar_wait(&acc_empty[buf], cph ^ 1u);
+          tcgen05_fence_after();
+          const uint32_t acc = tbase + buf * (uint32_t)g.acc_stride + me * (uint32_t)g.BN;
+          for (int n = 0; n < kiters; ++n) {
+            mbar_wait_u32(full0 + 8u * (uint32_t)s, ph);
+            tcgen05_fence_after();
+            const uint64_t st0 = dconst + (uint64_t)(a_u0 + (uint32_t)s * stage_u);
+            const uint64_t da = st0 + a_half, db = st0 + b_off;
+            if (elect_one()) {
+              if (cb + 1 != kb || kc_last == 4) {
+                umma_bf16(acc, da, db, idesc, n > 0 ? 1u : 0u);
+                umma_bf16(acc, da + 2, db + 2, idesc, 1u);
+                umma_bf16(acc, da + 4, db + 4, idesc, 1u);
+                umma_bf16(acc, da + 6, db + 6, idesc, 1u);
+              } else {
+                for (int k = 0; k < kc_last; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (n > 0 || k > 0) ? 1u : 0u);
+              }
+              tcgen05_commit_u32(empty0 + 8u * (uint32_t)s);
+            }
+            __syncwarp();
+            if (++s == ns) { s = 0; ph ^= 1u; }
+            if (++cb == kb) cb = 0;
+          }
+          if (elect_one()) tcgen05_commit(&acc_full[buf]);
+          __syncwarp();
+        }
+      } else if (g.ksplit || !me)
       for (int tile = blockIdx.x; tile < total; tile += step, ++lt) {
         const uint32_t buf = g.acc_bufs == 2 ? (lt & 1u) : 0u, cph = g.acc_bufs == 2 ? ((lt >> 1) & 1u) : (lt & 1u);
         // this issuer's first k-iteration of the tile: K-split ownership is by stage parity (see the producers)
@@ -332,7 +401,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int q = warp % 4;              // TMEM lane quarter this warp may access
     const int half = (warp - 2) / 4;     // which of the EPI_PARTS warps sharing the quarter
     const int ml = q * 32 + lane;
-    const int dy = ml / g.TW, dx = ml % g.TW;
+    // row -> pixel of the patch; M2 tiles have a second 128-row half (rows ml + 128, accumulator columns + BN)
+    const int dyh[2] = {ml / g.TW, (ml + BM) / g.TW}, dxh[2] = {ml % g.TW, (ml + BM) % g.TW};
+    const int nh = g.m2 ? 2 : 1;
     const int nchunks = g.BN / 16;
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++lt) {
@@ -341,11 +412,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int tx = t % g.tiles_x;
       t /= g.tiles_x;
       const int ty = t % g.tiles_y, b = t / g.tiles_y;
-      const int oy = ty * g.TH + dy, ox = tx * g.TW + dx, n0 = nt * g.BN;
+      const int n0 = nt * g.BN;
+      const uint32_t buf = g.acc_bufs == 2 ? (lt & 1u) : 0u, aph = g.acc_bufs == 2 ? ((lt >> 1) & 1u) : (lt & 1u);
+      bool waited = false;
+      for (int h = 0; h < nh; ++h) {
+      const int oy = ty * g.TH + dyh[h], ox = tx * g.TW + dxh[h];
       const bool row_ok = oy < d.OH && ox < d.OW;
       const size_t pix = ((size_t)b * d.OHt + (oy * d.osy + d.ooy)) * d.OWt + (ox * d.osx + d.oox);
-      const uint32_t buf = g.acc_bufs == 2 ? (lt & 1u) : 0u, aph = g.acc_bufs == 2 ? ((lt >> 1) & 1u) : (lt & 1u);
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)g.acc_stride;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)g.acc_stride + (uint32_t)(h * g.BN);
 
       if (PLAIN) {
         // Residual / gate operands are prefetched in groups of G chunks BEFORE the accumulator is awaited,
@@ -355,7 +429,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const __nv_bfloat16* resp = (const __nv_bfloat16*)d.res.ptr + pix * (size_t)d.res.ld + d.res.coff + n0;
         const __nv_bfloat16* auxp = (const __nv_bfloat16*)d.aux.ptr + pix * (size_t)d.aux.ld + d.aux.coff + n0;
         Pack8 rr[G], ra[G];
-        bool waited = false;
         for (int j0 = half; j0 < nchunks; j0 += EPI_PARTS * G) {
 #pragma unroll
           for (int gI = 0; gI < G; ++gI) {
@@ -438,10 +511,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (!waited) {  // (nchunks <= half cannot happen for BN >= 32, kept for safety)
           mbar_wait(&acc_full[buf], aph);
           tcgen05_fence_after();
+          waited = true;
         }
       } else {
-        mbar_wait(&acc_full[buf], aph);
-        tcgen05_fence_after();
+        if (!waited) {
+          mbar_wait(&acc_full[buf], aph);
+          tcgen05_fence_after();
+          waited = true;
+        }
         for (int j = half; j < nchunks; j += EPI_PARTS) {
           float v[16];
           tmem_ld16(trow + (uint32_t)(j * 16), v);
@@ -476,6 +553,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
       }
+      }  // h
       // this warp's TMEM reads of the buffer are complete (tcgen05.wait::ld inside tmem_ld16): hand it back
       tcgen05_fence_before();
       __syncwarp();
@@ -545,15 +623,30 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
     H = OH = 1;
     B = 1;
     dd.B = 1; dd.H = 1; dd.W = W; dd.OH = 1; dd.OW = OW; dd.OHt = 1; dd.OWt = OW;
-    g.TH = 1; g.TW = 128;
-  } else {
-    // patch shape TH x TW (TH*TW = 128): minimise the covered area (= wasted rows), prefer wide patches
+  }
+  // patch shape TH x TW (TH*TW = rows): minimise the covered area (= wasted rows), prefer wide patches;
+  // a TMA box dimension holds at most 256 elements (TW * stride, TH * stride)
+  auto pick_patch = [&](int rows, int* TH, int* TW) {
+    if (flat) { *TH = 1; *TW = rows; return (long)ceil_div(OW, rows) * rows; }
     long best = -1;
-    for (int tw = 128; tw >= 1; tw /= 2) {
-      const int th = BM / tw;
+    for (int tw = rows; tw >= 1; tw /= 2) {
+      const int th = rows / tw;
+      if (tw * d->stride > 256 || th * d->stride > 256) continue;
       const long area = (long)ceil_div(OW, tw) * tw * ceil_div(OH, th) * th;
-      if (best < 0 || area < best) { best = area; g.TW = tw; g.TH = th; }
+      if (best < 0 || area < best) { best = area; *TW = tw; *TH = th; }
     }
+    return best;
+  };
+  pick_patch(BM, &g.TH, &g.TW);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool track = dev >= 0 && dev < 16;
+  static int sm_count[16] = {};
+  int sms = track ? sm_count[dev] : 0;
+  if (!sms) {
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    if (track) sm_count[dev] = sms;
   }
   // halo mode: stride-1 multi-tap convs on maps that a 16 x 8 patch tiles exactly (RDSIC_TC_HALO: 0 off,
   // 1 on, 2 on with the descriptor base-offset field derived from the window start)
@@ -584,9 +677,40 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
     g.halo_h = g.TH + d->KH - 1;
     g.a_halo_bytes = (BK * 2 * g.halo_w * g.halo_h + 1023) / 1024 * 1024;
   }
+  g.BN = pick_bn(d->Cout);
+  g.kb_per_tap = ceil_div(d->Cin, BK);
+  g.num_k_iters = d->KH * d->KW * g.kb_per_tap;
+  g.a_stage_bytes = A_STAGE_BYTES;
+  // "Two-issuer family": layers with enough k-iterations to amortise a second issuer warp, decided from layer
+  // properties only (Cout, K).  Within the family the mode depends on the grid:
+  //   * more 128-row tiles than SMs -> M2: 256-row tiles, the issuers own one 128-row half each and share every
+  //     B stage (the big layers are bound by the ~6300 B/cycle chip-wide L2->SM throughput, and the weights
+  //     are more than half of the bytes a 128-row tile streams);
+  //   * otherwise 128-row tiles with K-split (RDSIC_TC_M2=1) or one sequential issuer (RDSIC_TC_M2=3, which
+  //     makes every output bit independent of the batch / image size: M2 and the sequential issuer sum K in
+  //     the same order, K-split does not).
+  static const int tune_m2 = getenv("RDSIC_TC_M2") ? atoi(getenv("RDSIC_TC_M2")) : 3;
+  static const int tune_ksplit = getenv("RDSIC_TC_KSPLIT") ? atoi(getenv("RDSIC_TC_KSPLIT")) : 1;
+  const bool family = !g.halo && g.num_k_iters >= 4 &&
+                      (4 * g.BN <= 512 || (tune_ksplit != 3 && 2 * g.BN <= 512 && g.num_k_iters >= 16));
+  if (tune_m2 && family) {
+    // cost of the busiest SM ~ rounds x bytes one tile streams per k-iteration (A rows + the B stage)
+    const int n_t = ceil_div(d->Cout, g.BN), b_bytes = g.BN * BK * 2;
+    const long tiles128 = (long)B * ceil_div(OW, g.TW) * ceil_div(OH, g.TH) * n_t;
+    int th2 = 0, tw2 = 0;
+    const long area2 = pick_patch(2 * BM, &th2, &tw2);
+    const long tiles256 = area2 > 0 ? (long)B * (area2 / (2 * BM)) * n_t : 0;
+    const long cost128 = ((tiles128 + sms - 1) / sms) * (A_STAGE_BYTES + b_bytes);
+    const long cost256 = ((tiles256 + sms - 1) / sms) * (2 * A_STAGE_BYTES + b_bytes);
+    if (area2 > 0 && (tune_m2 == 2 || (tiles128 > sms && cost256 <= cost128))) {
+      g.m2 = 1;
+      g.TH = th2;
+      g.TW = tw2;
+      g.a_stage_bytes = 2 * A_STAGE_BYTES;
+    }
+  }
   g.tiles_x = ceil_div(OW, g.TW);
   g.tiles_y = ceil_div(OH, g.TH);
-  g.BN = pick_bn(d->Cout);
   const int m_tiles = B * g.tiles_y * g.tiles_x;
   static const int tune_split = getenv("RDSIC_TC_SPLIT_N") ? atoi(getenv("RDSIC_TC_SPLIT_N")) : 1;
   if (tune_split) {
@@ -602,17 +726,15 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   }
   g.n_tiles = ceil_div(d->Cout, g.BN);
   g.total_tiles = m_tiles * g.n_tiles;
-  g.kb_per_tap = ceil_div(d->Cin, BK);
-  g.num_k_iters = d->KH * d->KW * g.kb_per_tap;
   g.b_stage_bytes = g.BN * BK * 2;
-  const int stage_bytes = g.halo ? g.b_stage_bytes : A_STAGE_BYTES + g.b_stage_bytes;
+  const int stage_bytes = g.halo ? g.b_stage_bytes : g.a_stage_bytes + g.b_stage_bytes;
   // one persistent CTA per SM owns the whole shared memory: as deep a TMA ring as fits (the ring keeps
   // running across tiles, so even 2-3-iteration pointwise GEMMs keep many stages in flight)
   static const int tune_stages = getenv("RDSIC_TC_STAGES") ? atoi(getenv("RDSIC_TC_STAGES")) : 0;
-  int stages = (200 * 1024 - (g.halo ? 2 * g.a_halo_bytes : 0)) / stage_bytes;
+  int stages = ((g.m2 ? 220 : 200) * 1024 - (g.halo ? 2 * g.a_halo_bytes : 0)) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (tune_stages > 0 && tune_stages < stages) stages = tune_stages;
-  if (!g.halo) stages &= ~1;  // even ring depth: stage parity = owner (two producers / two issuers)
+  if (!g.halo && !g.m2) stages &= ~1;  // even ring depth: stage parity = owner (two producers / two issuers)
   if (stages < 2) return RDSIC_E_ARG;
   g.num_stages = stages;
   // K-split across two issuer warps (see the kernel's header comment) wherever both accumulators fit TMEM.
@@ -621,11 +743,10 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   // epilogue (>= 16 k-iterations).
   // The decision uses only layer properties (Cout, K) -- never the grid-dependent N split above -- so that the
   // fp32 summation order, hence every output bit, is independent of batch size and image size.
-  static const int tune_ksplit = getenv("RDSIC_TC_KSPLIT") ? atoi(getenv("RDSIC_TC_KSPLIT")) : 1;
   const int bn_layer = pick_bn(d->Cout);
-  g.ksplit = tune_ksplit && !g.halo && g.num_k_iters >= 4 &&
+  g.ksplit = tune_ksplit && !g.m2 && tune_m2 != 3 && !g.halo && g.num_k_iters >= 4 &&
              (4 * bn_layer <= 512 || (tune_ksplit != 3 && 2 * bn_layer <= 512 && g.num_k_iters >= 16));
-  g.acc_stride = g.BN * (1 + g.ksplit);
+  g.acc_stride = g.BN * (1 + (g.ksplit | g.m2));
   g.acc_bufs = 2 * g.acc_stride <= 512 ? 2 : 1;
   g.tmem_cols = 32;
   while (g.tmem_cols < g.acc_bufs * g.acc_stride) g.tmem_cols *= 2;
@@ -670,20 +791,10 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   ConvTcKernel kern = plain ? pick_kernel<true>(d->epilogue) : pick_kernel<false>(d->epilogue);
   // opt in to >48 KB dynamic smem: per (device, kernel); idempotent, so a race between host threads is harmless
   static bool attr_set[16][2][8] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  const bool track = dev >= 0 && dev < 16;
   if (!track || !attr_set[dev][plain][d->epilogue]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
     if (track) attr_set[dev][plain][d->epilogue] = true;
-  }
-  static int sm_count[16] = {};
-  int sms = track ? sm_count[dev] : 0;
-  if (!sms) {
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-    if (track) sm_count[dev] = sms;
   }
   const int grid = g.total_tiles < sms ? g.total_tiles : sms;
   kern<<<grid, CONV_THREADS, smem, stream>>>(ta, tb, dd, g);

@@ -30,6 +30,10 @@ struct TcGeom {
   int acc_stride;      // TMEM columns of one buffer = BN * (1 + ksplit)
   int dbg_skip_load;   // profiling aid: bit0 = do not load A, bit1 = do not load B (results are garbage)
   long long* dbg_ts;   // profiling aid: clock64 stamps of issuer 0 of CTA 0 (4 per k-iteration), or null
+  // M2 mode (conv_bf16.cu): the tile is a 256-row patch (TH*TW = 256) loaded by ONE TMA box; the two issuer
+  // warps each own a 128-row half (own accumulator) and share every B stage, which halves the weight bytes
+  // streamed from L2 per output row.  a_stage_bytes = 16 KB (plain) or 32 KB (M2).
+  int m2, a_stage_bytes;
 };
 
 // ------------------------------------------------------------------ PTX wrappers

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RDSIC_ABI_VERSION 1
+#define RDSIC_ABI_VERSION 2
 
 typedef void* rdsic_stream_t; /* cudaStream_t */
 
@@ -118,10 +118,14 @@ typedef struct rdsic_attn_desc {
   float scale;             /* qk_scale or head_dim**-0.5 (win_attention.py:54), applied to q before q@k^T */
 } rdsic_attn_desc;
 
-/* EntropyBottleneck.forward, eval mode (entropy_models.py:447-490) + the
- * ste_round z_hat of cnn.py:152-154 (same value).  params: [C][RDSIC_EB_STRIDE]
+/* EntropyBottleneck.forward (entropy_models.py:447-490) + the ste_round z_hat of
+ * cnn.py:152-154 (same value in eval mode).  params: [C][RDSIC_EB_STRIDE]
  * fp32 per channel = softplus(matrix0..4) (3,9,9,9,3) | bias0..4 (3,3,3,3,1) |
- * tanh(factor0..3) (3 each) | median. */
+ * tanh(factor0..3) (3 each) | median.
+ * Training mode (quantize "noise", entropy_models.py:131-137): with noise.ptr != NULL the
+ * likelihood is evaluated at z + noise instead of round(z-med)+med; z_hat (and symbols)
+ * keep the ste_round value, which is what WACNN.forward feeds the hyper-synthesis in
+ * both modes; noisy_out (optional) receives z + noise, the module's first output. */
 #define RDSIC_EB_STRIDE 60
 typedef struct rdsic_eb_desc {
   rdsic_view z;       /* [B,h,w,C] fp32 */
@@ -131,6 +135,9 @@ typedef struct rdsic_eb_desc {
   const float* params;
   int32_t B, h, w, C;
   float lik_bound;    /* 1e-9 */
+  int32_t pad_;
+  rdsic_view noise;     /* optional [B,h,w,C] fp32, U(-1/2,1/2) drawn by the caller */
+  rdsic_view noisy_out; /* optional [B,h,w,C] fp32: z + noise */
 } rdsic_eb_desc;
 
 /* GaussianConditional.forward (eval) + ste_round + build_indexes + quantize
@@ -150,6 +157,12 @@ typedef struct rdsic_gc_desc {
   int32_t n_table;
   int32_t B, h, w, Cs, Ctot, lik_coff;
   float scale_bound, lik_bound;
+  int32_t pad_;
+  /* Training mode (GaussianConditional.forward with quantize "noise", entropy_models.py:131-137,
+   * 646-661): with noise.ptr != NULL, lik is evaluated at |y + noise - mu|; y_hat / symbols keep
+   * the ste_round value (cnn.py:177); noisy_out (optional) receives y + noise. */
+  rdsic_view noise;     /* optional [B,h,w,Cs] fp32 */
+  rdsic_view noisy_out; /* optional [B,h,w,Cs] fp32 */
 } rdsic_gc_desc;
 
 /* Layout / elementwise helpers used by the standalone module API. */
@@ -223,6 +236,12 @@ int rdsic_conv_forward(const rdsic_conv_desc* d, rdsic_stream_t stream);
 int rdsic_attn_forward(const rdsic_attn_desc* d, rdsic_stream_t stream);
 int rdsic_eb_forward(const rdsic_eb_desc* d, rdsic_stream_t stream);
 int rdsic_gc_forward(const rdsic_gc_desc* d, rdsic_stream_t stream);
+/* EntropyBottleneck.loss (entropy_models.py:396-399), summed by CompressionModel.aux_loss
+ * (WACNN/base.py:22-27): terms[c*3+k] = |logits_cumulative(quantiles[c][k]) - target[k]| and
+ * *sum = their total (fixed-order tree sum, deterministic).  params as in rdsic_eb_desc;
+ * quantiles [C][3], target [3], terms [C*3] and sum [1] are fp32 device pointers. */
+int rdsic_eb_aux_loss(const float* params, const float* quantiles, const float* target, int32_t C, float* terms,
+                      float* sum, rdsic_stream_t stream);
 int rdsic_copy_forward(const rdsic_copy_desc* d, rdsic_stream_t stream);
 int rdsic_ln_forward(const rdsic_ln_desc* d, rdsic_stream_t stream);
 int rdsic_patch_forward(const rdsic_patch_desc* d, rdsic_stream_t stream);

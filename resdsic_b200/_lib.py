@@ -51,6 +51,7 @@ class EBDesc(C.Structure):
     _fields_ = [
         ("z", View), ("z_hat", View), ("lik", C.c_void_p), ("symbols", C.c_void_p), ("params", C.c_void_p),
         ("B", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("C", C.c_int32), ("lik_bound", C.c_float),
+        ("pad_", C.c_int32), ("noise", View), ("noisy_out", View),
     ]
 
 
@@ -61,6 +62,7 @@ class GCDesc(C.Structure):
         ("n_table", C.c_int32),
         ("B", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("Cs", C.c_int32), ("Ctot", C.c_int32),
         ("lik_coff", C.c_int32), ("scale_bound", C.c_float), ("lik_bound", C.c_float),
+        ("pad_", C.c_int32), ("noise", View), ("noisy_out", View),
     ]
 
 
@@ -99,7 +101,7 @@ class Op(C.Structure):
 
 EXPORTS = (
     "rdsic_abi_version", "rdsic_error_string", "rdsic_sizeof",
-    "rdsic_conv_forward", "rdsic_attn_forward", "rdsic_eb_forward", "rdsic_gc_forward",
+    "rdsic_conv_forward", "rdsic_attn_forward", "rdsic_eb_forward", "rdsic_gc_forward", "rdsic_eb_aux_loss",
     "rdsic_copy_forward", "rdsic_ln_forward", "rdsic_patch_forward", "rdsic_run_program",
     "rdsic_graph_create", "rdsic_graph_launch", "rdsic_graph_num_kernels", "rdsic_graph_destroy",
 )
@@ -128,13 +130,15 @@ def lib():
                   ("rdsic_patch_forward", PatchDesc)):
         getattr(L, fn).argtypes = [C.POINTER(T), C.c_void_p]
         getattr(L, fn).restype = C.c_int
+    L.rdsic_eb_aux_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.rdsic_eb_aux_loss.restype = C.c_int
     L.rdsic_run_program.argtypes = [C.POINTER(Op), C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.rdsic_graph_create.argtypes = [C.POINTER(Op), C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
     L.rdsic_graph_launch.argtypes = [C.c_void_p, C.c_void_p]
     L.rdsic_graph_num_kernels.argtypes = [C.c_void_p]
     L.rdsic_graph_destroy.argtypes = [C.c_void_p]
     L.rdsic_graph_destroy.restype = None
-    if L.rdsic_abi_version() != 1:
+    if L.rdsic_abi_version() != 2:
         raise RuntimeError("resdsic_b200: ABI version mismatch between the python host and the CUDA library")
     for what, T in enumerate((Op, ConvDesc, AttnDesc, EBDesc, GCDesc, CopyDesc, View, LNDesc, PatchDesc)):
         if L.rdsic_sizeof(what) != C.sizeof(T):

@@ -63,8 +63,13 @@ __global__ void eb_forward_kernel(const rdsic_eb_desc d) {
     const float z = ((const float*)d.z.ptr)[pix * d.z.ld + d.z.coff + c];
     const float r = rintf(__fsub_rn(z, med));  // torch.round = half-to-even
     const float q = __fadd_rn(r, med);
-    const float lo = eb_logits(p, __fsub_rn(q, 0.5f));
-    const float up = eb_logits(p, __fadd_rn(q, 0.5f));
+    float ql = q;  // where the likelihood is evaluated: z_hat (eval) or z + noise (training)
+    if (d.noise.ptr) {
+      ql = __fadd_rn(z, ((const float*)d.noise.ptr)[pix * d.noise.ld + d.noise.coff + c]);
+      if (d.noisy_out.ptr) ((float*)d.noisy_out.ptr)[pix * d.noisy_out.ld + d.noisy_out.coff + c] = ql;
+    }
+    const float lo = eb_logits(p, __fsub_rn(ql, 0.5f));
+    const float up = eb_logits(p, __fadd_rn(ql, 0.5f));
     const float su = __fadd_rn(lo, up);
     const float sgn = su > 0.f ? -1.f : (su < 0.f ? 1.f : 0.f);  // -sign(lo+up)
     float lik = fabsf(__fsub_rn(sigmoid_ref(__fmul_rn(sgn, up)), sigmoid_ref(__fmul_rn(sgn, lo))));
@@ -105,7 +110,12 @@ __global__ void __launch_bounds__(256) gc_forward_kernel(const rdsic_gc_desc d) 
     const float sc = ((const float*)d.scale.ptr)[pix * d.scale.ld + d.scale.coff + c];
     const float r = rintf(__fsub_rn(y, mu));
     const float yh = __fadd_rn(r, mu);
-    const float v = fabsf(__fsub_rn(yh, mu));
+    float yl = yh;  // where the likelihood is evaluated: y_hat (eval) or y + noise (training)
+    if (d.noise.ptr) {
+      yl = __fadd_rn(y, ((const float*)d.noise.ptr)[pix * d.noise.ld + d.noise.coff + c]);
+      if (d.noisy_out.ptr) ((float*)d.noisy_out.ptr)[pix * d.noisy_out.ld + d.noisy_out.coff + c] = yl;
+    }
+    const float v = fabsf(__fsub_rn(yl, mu));
     const float s = fmaxf(sc, d.scale_bound);
     const float up = __fmul_rn(0.5f, erfcf(__fmul_rn(cst, __fdiv_rn(__fsub_rn(0.5f, v), s))));
     const float lo = __fmul_rn(0.5f, erfcf(__fmul_rn(cst, __fdiv_rn(__fsub_rn(-0.5f, v), s))));
@@ -139,12 +149,42 @@ __global__ void __launch_bounds__(256) gc_forward_kernel(const rdsic_gc_desc d) 
   }
 }
 
+// EntropyBottleneck.loss: one thread per (channel, quantile); fixed-order block tree sum.
+__global__ void __launch_bounds__(1024) eb_aux_loss_kernel(const float* __restrict__ params, const float* __restrict__ quantiles,
+                                                          const float* __restrict__ target, int C, float* __restrict__ terms,
+                                                          float* __restrict__ sum) {
+  __shared__ float s_part[1024];
+  float acc = 0.f;
+  for (int e = threadIdx.x; e < C * 3; e += blockDim.x) {  // strided, so the order is fixed for a given C
+    const int c = e / 3, k = e % 3;
+    const float t = fabsf(__fsub_rn(eb_logits(params + (size_t)c * RDSIC_EB_STRIDE, quantiles[e]), target[k]));
+    if (terms) terms[e] = t;
+    acc = __fadd_rn(acc, t);
+  }
+  s_part[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) s_part[threadIdx.x] = __fadd_rn(s_part[threadIdx.x], s_part[threadIdx.x + w]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *sum = s_part[0];
+}
+
 }  // namespace
+
+extern "C" int rdsic_eb_aux_loss(const float* params, const float* quantiles, const float* target, int32_t C, float* terms,
+                                 float* sum, rdsic_stream_t stream) {
+  RDSIC_CHECK_ARG(params && quantiles && target && sum && C > 0);
+  eb_aux_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(params, quantiles, target, C, terms, sum);
+  return rdsic_launch_status();
+}
 
 extern "C" int rdsic_eb_forward(const rdsic_eb_desc* d, rdsic_stream_t stream) {
   RDSIC_CHECK_ARG(d && d->z.ptr && d->z_hat.ptr && d->lik && d->params);
   RDSIC_CHECK_ARG(d->B > 0 && d->h > 0 && d->w > 0 && d->C > 0);
   RDSIC_CHECK_ARG(d->z.dtype == RDSIC_F32 && !d->z.nchw && !d->z_hat.nchw);
+  RDSIC_CHECK_ARG(!d->noise.ptr || (d->noise.dtype == RDSIC_F32 && !d->noise.nchw));
+  RDSIC_CHECK_ARG(!d->noisy_out.ptr || (d->noise.ptr && d->noisy_out.dtype == RDSIC_F32 && !d->noisy_out.nchw));
   const size_t total = (size_t)d->B * d->h * d->w * d->C;
   const int nblk = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
   eb_forward_kernel<<<nblk, 256, 0, (cudaStream_t)stream>>>(*d);
@@ -157,6 +197,8 @@ extern "C" int rdsic_gc_forward(const rdsic_gc_desc* d, rdsic_stream_t stream) {
   RDSIC_CHECK_ARG(d->n_table >= 2 && d->n_table <= 129);
   RDSIC_CHECK_ARG(d->y.dtype == RDSIC_F32 && d->mu.dtype == RDSIC_F32 && d->scale.dtype == RDSIC_F32);
   RDSIC_CHECK_ARG(!d->y.nchw && !d->mu.nchw && !d->scale.nchw);
+  RDSIC_CHECK_ARG(!d->noise.ptr || (d->noise.dtype == RDSIC_F32 && !d->noise.nchw));
+  RDSIC_CHECK_ARG(!d->noisy_out.ptr || (d->noise.ptr && d->noisy_out.dtype == RDSIC_F32 && !d->noisy_out.nchw));
   const size_t npix = (size_t)d->B * d->h * d->w;
   dim3 grid((unsigned)((npix + GC_TP - 1) / GC_TP), (unsigned)ceil_div(d->Cs, GC_TC));
   gc_forward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d);

@@ -2,11 +2,16 @@
 
 Mirror of the reference's vendored CompressAI classes
 (entropy_models/entropy_models.py:295-668): same constructor arguments,
-parameter/buffer names and eval-mode forward semantics.  In scope: forward
-(quantise + likelihood), quantize, dequantize, build_indexes.  Out of scope per
+parameter/buffer names and forward semantics in eval mode (round) and in
+training mode (additive U(-1/2,1/2) noise, forward VALUES only -- there is no
+autograd through the CUDA kernels).  In scope: forward (quantise + likelihood),
+quantize, dequantize, build_indexes, EntropyBottleneck.loss.  Out of scope per
 BASELINE.json (stays in the reference's C++): update() CDF tables and the rANS
 compress()/decompress().
 """
+import ctypes
+
+from .. import _lib
 import numpy as np
 import torch
 import torch.nn as nn
@@ -86,26 +91,50 @@ class EntropyBottleneck(EntropyModel):
 
         return self._packed("eb", tensors, build)
 
-    def emit(self, ctx: Ctx, z, z_hat=None, lik=None, symbols=None, **kw):
-        """z: fp32 [B,h,w,C] view.  Returns (z_hat view, lik NCHW tensor)."""
-        if self.training:
-            raise NotImplementedError("noise-mode (training) quantisation is not part of the B200 inference path")
+    def emit(self, ctx: Ctx, z, z_hat=None, lik=None, symbols=None, noise=None, noisy_out=None, **kw):
+        """z: fp32 [B,h,w,C] view.  Returns (z_hat view, lik NCHW tensor).  `noise` (fp32 view like z)
+        selects the training-mode likelihood at z + noise; z_hat stays round(z-med)+med (cnn.py:152-154)."""
         if z_hat is None:
             z_hat = ctx.buf(z.B, z.H, z.W, z.C)
         if lik is None:
             lik = torch.empty(z.B, z.C, z.H, z.W, dtype=torch.float32, device=ctx.device)
-        ctx.prog.eb(z, z_hat, lik, self.packed(), symbols=symbols, lik_bound=self.likelihood_bound)
+        ctx.prog.eb(z, z_hat, lik, self.packed(), symbols=symbols, lik_bound=self.likelihood_bound, noise=noise,
+                    noisy_out=noisy_out)
         return z_hat, lik
 
     @torch.no_grad()
-    def forward(self, x, training=None):
-        """(outputs, likelihood), eval mode -- reference entropy_models.py:447-490."""
+    def forward(self, x, training=None, noise=None):
+        """(outputs, likelihood) -- reference entropy_models.py:447-490.  Eval: outputs = round(x-med)+med.
+        Training: outputs = x + U(-1/2,1/2) (`noise`, NCHW, may be injected for reproducibility; otherwise it
+        is drawn on the device with torch's generator) and the likelihood is evaluated there."""
+        training = self.training if training is None else training
         ctx = Ctx(x.device, "fp32")
         z = ctx.from_nchw(x, torch.float32)
-        z_hat, lik = self.emit(ctx, z, z_hat=ctx.buf(z.B, z.H, z.W, z.C, torch.float32))
-        out = ctx.to_nchw(z_hat)
+        nz = noisy = None
+        if training:
+            if noise is None:
+                noise = torch.empty_like(x, dtype=torch.float32).uniform_(-0.5, 0.5)
+            nz = ctx.from_nchw(noise, torch.float32)
+            noisy = ctx.buf(z.B, z.H, z.W, z.C, torch.float32)
+        z_hat, lik = self.emit(ctx, z, z_hat=ctx.buf(z.B, z.H, z.W, z.C, torch.float32), noise=nz, noisy_out=noisy)
+        out = ctx.to_nchw(noisy if training else z_hat)
         ctx.prog.run()
         return out, lik
+
+    @torch.no_grad()
+    def loss(self):
+        """reference entropy_models.py:396-399: sum |logits_cumulative(quantiles) - target| (forward value)."""
+        dev = self.quantiles.device
+        if dev.type != "cuda":
+            raise RuntimeError("resdsic_b200 runs on CUDA devices only (no CPU fallback)")
+        q = self.quantiles.detach().float().contiguous()
+        tgt = self.target.detach().float().contiguous()
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().rdsic_eb_aux_loss(self.packed().data_ptr(), q.data_ptr(), tgt.data_ptr(), self.channels, None,
+                                              out.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _lib.check(rc, "EntropyBottleneck.loss")
+        return out[0]
 
     @staticmethod
     def _build_indexes(size):
@@ -142,14 +171,15 @@ class GaussianConditional(EntropyModel):
             t = self.__dict__.setdefault("_default_table", packing.scale_table())
         return self._packed(("table", str(device)), (t,), lambda: t.detach().float().to(device).contiguous())
 
-    def emit(self, ctx: Ctx, y, scale, mu, lik, lik_coff, Ctot, y_hat_dsts=(), symbols=None, indexes=None):
-        if self.training:
-            raise NotImplementedError("noise-mode (training) quantisation is not part of the B200 inference path")
+    def emit(self, ctx: Ctx, y, scale, mu, lik, lik_coff, Ctot, y_hat_dsts=(), symbols=None, indexes=None, noise=None,
+             noisy_out=None):
+        """`noise` (fp32 view like y) selects the training-mode likelihood at y + noise (entropy_models.py:646-661);
+        the y_hat destinations keep the ste_round value (cnn.py:177)."""
         ctx.prog.gc(y, mu, scale, list(y_hat_dsts), lik, lik_coff, Ctot, self.table(ctx.device), symbols=symbols,
                     indexes=indexes, scale_bound=self.scale_bound_value,
-                    lik_bound=self.likelihood_bound)
+                    lik_bound=self.likelihood_bound, noise=noise, noisy_out=noisy_out)
 
-    def _run(self, inputs, scales, means, want):
+    def _run(self, inputs, scales, means, want, noise=None):
         B, Cn, H, W = inputs.shape
         ctx = Ctx(inputs.device, "fp32")
         y = ctx.from_nchw(inputs, torch.float32)
@@ -159,26 +189,41 @@ class GaussianConditional(EntropyModel):
         lik = torch.empty(B, Cn, H, W, dtype=torch.float32, device=inputs.device)
         sym = torch.empty(B, Cn, H, W, dtype=torch.int32, device=inputs.device) if "sym" in want else None
         idx = torch.empty(B, Cn, H, W, dtype=torch.int32, device=inputs.device) if "idx" in want else None
-        self.emit(ctx, y, sc, mu, lik, 0, Cn, [y_hat], sym, idx)
-        out = ctx.to_nchw(y_hat)
+        nz = noisy = None
+        if noise is not None:
+            nz = ctx.from_nchw(noise, torch.float32)
+            noisy = ctx.buf(B, H, W, Cn, torch.float32)
+        self.emit(ctx, y, sc, mu, lik, 0, Cn, [y_hat], sym, idx, noise=nz, noisy_out=noisy)
+        out = ctx.to_nchw(noisy if noise is not None else y_hat)
         ctx.prog.run()
         return out, lik, sym, idx
 
+    @staticmethod
+    def _draw_noise(inputs, mask):
+        """quantize "noise" (entropy_models.py:131-137): U(-1/2,1/2), optionally times `mask`."""
+        noise = torch.empty_like(inputs, dtype=torch.float32).uniform_(-0.5, 0.5)
+        return noise if mask is None else noise * mask
+
     @torch.no_grad()
-    def forward(self, inputs, scales, means=None, training=None, mask=None):
-        """(outputs, likelihood), eval mode -- reference entropy_models.py:646-661."""
-        if mask is not None:
-            raise NotImplementedError("`mask` only affects noise-mode quantisation (scalable models; out of scope)")
-        out, lik, _, _ = self._run(inputs, scales, means, ())
+    def forward(self, inputs, scales, means=None, training=None, mask=None, noise=None):
+        """(outputs, likelihood) -- reference entropy_models.py:646-661.  Eval: outputs = round(x-mu)+mu.
+        Training: outputs = x + noise (drawn on the device unless `noise` is injected; `mask` multiplies the
+        draw as in the reference) and the likelihood is evaluated at outputs."""
+        training = self.training if training is None else training
+        if training and noise is None:
+            noise = self._draw_noise(inputs, mask)
+        out, lik, _, _ = self._run(inputs, scales, means, (), noise=noise if training else None)
         return out, lik
 
     @torch.no_grad()
-    def quantize(self, inputs, mode, means=None, mask=None):
-        """reference entropy_models.py:126-152 ("dequantize" / "symbols")."""
+    def quantize(self, inputs, mode, means=None, mask=None, noise=None):
+        """reference entropy_models.py:126-152."""
         if mode not in ("noise", "dequantize", "symbols"):
             raise ValueError(f'Invalid quantization mode: "{mode}"')
         if mode == "noise":
-            raise NotImplementedError("noise-mode (training) quantisation is not part of the B200 inference path")
+            noise = self._draw_noise(inputs, mask) if noise is None else noise
+            out, _, _, _ = self._run(inputs, torch.ones_like(inputs), means, (), noise=noise)
+            return out
         out, _, sym, _ = self._run(inputs, torch.ones_like(inputs), means, ("sym",))
         return out if mode == "dequantize" else sym
 

@@ -37,7 +37,10 @@ class CompressionModel(B200Module):
     bitstream-side and stay with the reference)."""
 
     def aux_loss(self):
-        raise NotImplementedError("aux_loss belongs to the training step (SURVEY section 8: config 4, not yet ported)")
+        """reference WACNN/base.py:22-27: sum of EntropyBottleneck.loss() over the bottleneck modules
+        (forward value; the CUDA path has no autograd)."""
+        from ..entropy_models import EntropyBottleneck
+        return sum(m.loss() for m in self.modules() if isinstance(m, EntropyBottleneck))
 
     def load_state_dict(self, state_dict, strict=False):
         return nn.Module.load_state_dict(self, state_dict, strict=strict)
@@ -99,6 +102,12 @@ class WACNN(CompressionModel):
         # 2 -> 1205, 4 -> 869 images/s -- persistent one-CTA-per-SM kernels of two graphs serialise instead of
         # interleaving -- so the default is 1.  Outputs are bit-identical for any setting.
         self.micro_batches = 1
+        # Training mode (`.train()`): forward VALUES of the reference's training forward -- likelihoods at
+        # y / z + U(-1/2,1/2) noise (entropy_models.py:131-137), y_hat / z_hat by ste_round as in eval mode
+        # (cnn.py:152-154,177).  The noise is drawn on the device per call; `noise_override` =
+        # {"y": [B,320,H/16,W/16], "z": [B,192,H/64,W/64]} injects given tensors instead (parity tests).
+        # There is no autograd through the CUDA kernels: the backward pass of BASELINE config 4 is not ported.
+        self.noise_override = None
         self._plans = {}
 
     # ------------------------------------------------------------------ API
@@ -127,11 +136,8 @@ class WACNN(CompressionModel):
         if H % 64 or W % 64:
             raise ValueError(f"input {H}x{W} must be a multiple of 64 (pad as eval_model/__main__.py:89-101 does; "
                              "see resdsic_b200.utils.pad_to_multiple)")
-        if self.training:
-            raise NotImplementedError("training-mode forward (noise quantisation + autograd) is not ported yet; "
-                                      "call model.eval()")
-        mb = self._num_micro_batches(B)
-        key = (B, H, W, str(device), self.precision, with_symbols, self._weights_key(), mb)
+        mb = 1 if self.training else self._num_micro_batches(B)
+        key = (B, H, W, str(device), self.precision, with_symbols, self._weights_key(), mb, bool(self.training))
         plan = self._plans.get(key)
         if plan is None:
             self._plans.clear()  # one live plan: buffers are sized for one shape
@@ -163,6 +169,7 @@ class WACNN(CompressionModel):
         p.indexes = torch.empty(B, self.M, h, w, dtype=i32, device=device) if with_symbols else None
         p.z_symbols = torch.empty(B, self.N, h // 4, w // 4, dtype=i32, device=device) if with_symbols else None
         p.subs, p.sub_batch = [], b
+        p.noise_y = p.noise_z = None  # micro-batching is an eval-mode feature
         for j in range(mb):
             sl = slice(j * b, (j + 1) * b)
             outs = {k: getattr(p, k)[sl] for k in ("x", "x_hat", "lik_y", "lik_z", "symbols", "indexes", "z_symbols")
@@ -198,7 +205,11 @@ class WACNN(CompressionModel):
         z = self.h_a.emit(ctx, y_act, last_kw=dict(out_dtype=f32))
         p.lik_z = out_tensor("lik_z", B, z.C, z.H, z.W)
         p.z_symbols = out_tensor("z_symbols", B, z.C, z.H, z.W, dtype=torch.int32) if with_symbols else None
-        z_hat, _ = self.entropy_bottleneck.emit(ctx, z, lik=p.lik_z, symbols=p.z_symbols)
+        p.noise_y = p.noise_z = None
+        if self.training:
+            p.noise_y = ctx.buf(B, h, w, M, f32)
+            p.noise_z = ctx.buf(B, z.H, z.W, z.C, f32)
+        z_hat, _ = self.entropy_bottleneck.emit(ctx, z, lik=p.lik_z, symbols=p.z_symbols, noise=p.noise_z)
         # ---- hyper-synthesis straight into the support buffers
         S = self.max_support_slices
         ctx_ld = M + sc_ * (S + 1)  # latent | S support slots | one scratch slot
@@ -276,7 +287,8 @@ class WACNN(CompressionModel):
                 prog.copy(means.channels(M, sc_ * S), lrp_buf.channels(M, sc_ * S))
                 slot, extra = lrp_buf.channels(M + sc_ * S, sc_), {}
             self.gaussian_conditional.emit(ctx, y.channels(sc_ * i, sc_), sc, mu, p.lik_y, sc_ * i, M,
-                                           y_hat_dsts=[yh_i, slot], symbols=p.symbols, indexes=p.indexes)
+                                           y_hat_dsts=[yh_i, slot], symbols=p.symbols, indexes=p.indexes,
+                                           noise=p.noise_y.channels(sc_ * i, sc_) if p.noise_y is not None else None)
             stack_split("lrp", i, lrp_buf, sc_ * (k + 1), final=dict(epilogue=_lib.EPI_LRP, res=yh_i, out=yh_i, **extra))
 
         for i in range(S):  # serial chain: slice i+1 needs the refined slice i
@@ -323,6 +335,13 @@ class WACNN(CompressionModel):
         B, _, H, W = x.shape
         plan = self._plan(B, H, W, x.device, with_symbols)
         plan.x.copy_(x)
+        if plan.noise_y is not None:  # training mode: this call's noise draw (or the injected tensors)
+            for buf, key in ((plan.noise_y, "y"), (plan.noise_z, "z")):
+                dst = buf.t.view(buf.B, buf.H, buf.W, buf.C)
+                if self.noise_override is not None:
+                    dst.copy_(self.noise_override[key].to(x.device, torch.float32).permute(0, 2, 3, 1))
+                else:
+                    dst.uniform_(-0.5, 0.5)
         if len(plan.subs) == 1:
             plan.prog.run_graph() if self.use_cuda_graph else plan.prog.run()
         else:
@@ -338,7 +357,8 @@ class WACNN(CompressionModel):
 
     @torch.no_grad()
     def forward(self, x):
-        """reference cnn.py:143-193.  The returned tensors are the plan's static
+        """reference cnn.py:143-193 (eval mode, or the forward values of training mode -- see
+        `noise_override`).  The returned tensors are the plan's static
         output buffers: clone them if they must survive the next forward()."""
         p = self._execute(x, False)
         return {"x_hat": p.x_hat, "likelihoods": {"y": p.lik_y, "z": p.lik_z}}

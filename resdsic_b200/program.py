@@ -179,9 +179,12 @@ class Program:
         self.keep += [qkv.t, out.t, bias_table]
         return out
 
-    def eb(self, z: TV, z_hat: TV, lik, params, symbols=None, lik_bound=1e-9):
+    def eb(self, z: TV, z_hat: TV, lik, params, symbols=None, lik_bound=1e-9, noise: TV = None, noisy_out: TV = None):
         d = EBDesc()
         d.z, d.z_hat = z.view(), z_hat.view()
+        d.noise = noise.view() if noise is not None else _NULL
+        d.noisy_out = noisy_out.view() if noisy_out is not None else _NULL
+        self.keep += [tv.t for tv in (noise, noisy_out) if tv is not None]
         d.lik, d.symbols, d.params = lik.data_ptr(), _ptr(symbols), params.data_ptr()
         d.B, d.h, d.w, d.C = z.B, z.H, z.W, z.C
         d.lik_bound = lik_bound
@@ -192,9 +195,12 @@ class Program:
         self.keep += [z.t, z_hat.t, lik, params, symbols]
 
     def gc(self, y: TV, mu: TV, scale: TV, y_hat_dsts, lik, lik_coff, Ctot, table, symbols=None, indexes=None,
-           scale_bound=0.11, lik_bound=1e-9):
+           scale_bound=0.11, lik_bound=1e-9, noise: TV = None, noisy_out: TV = None):
         d = GCDesc()
         d.y, d.mu, d.scale = y.view(), mu.view(), scale.view()
+        d.noise = noise.view() if noise is not None else _NULL
+        d.noisy_out = noisy_out.view() if noisy_out is not None else _NULL
+        self.keep += [tv.t for tv in (noise, noisy_out) if tv is not None]
         for i, tv in enumerate(y_hat_dsts):
             d.y_hat[i] = tv.view()
         d.lik, d.symbols, d.indexes = lik.data_ptr(), _ptr(symbols), _ptr(indexes)

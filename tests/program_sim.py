@@ -141,7 +141,12 @@ class Sim:
                 a = a + P[:, 49 + 3 * k: 52 + 3 * k] * torch.tanh(a)
             return (P[:, 30:33] * a).sum(-1) + P[:, 45]
 
-        lo, up = logits(q - 0.5), logits(q + 0.5)
+        ql = q
+        if d.noise.ptr:  # training mode: likelihood at z + noise
+            ql = z + self._nhwc(d.noise, d.B, d.h, d.w, d.C).float()
+            if d.noisy_out.ptr:
+                self._nhwc(d.noisy_out, d.B, d.h, d.w, d.C).copy_(ql)
+        lo, up = logits(ql - 0.5), logits(ql + 0.5)
         sg = -torch.sign(lo + up)
         lik = torch.abs(torch.sigmoid(sg * up) - torch.sigmoid(sg * lo)).clamp(min=d.lik_bound)
         self._nhwc(d.z_hat, d.B, d.h, d.w, d.C).copy_(q)
@@ -156,7 +161,12 @@ class Sim:
         sc = self._nhwc(d.scale, d.B, d.h, d.w, d.Cs).float()
         r = torch.round(y - mu)
         yh = r + mu
-        v = torch.abs(yh - mu)
+        yl = yh
+        if d.noise.ptr:  # training mode: likelihood at y + noise
+            yl = y + self._nhwc(d.noise, d.B, d.h, d.w, d.Cs).float()
+            if d.noisy_out.ptr:
+                self._nhwc(d.noisy_out, d.B, d.h, d.w, d.Cs).copy_(yl)
+        v = torch.abs(yl - mu)
         s = torch.clamp(sc, min=torch.tensor(d.scale_bound))
         c = float(-(2 ** -0.5))
         lik = (0.5 * torch.erfc(c * ((0.5 - v) / s)) - 0.5 * torch.erfc(c * ((-0.5 - v) / s))).clamp(min=d.lik_bound)

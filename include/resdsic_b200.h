@@ -242,6 +242,31 @@ int rdsic_gc_forward(const rdsic_gc_desc* d, rdsic_stream_t stream);
  * quantiles [C][3], target [3], terms [C*3] and sum [1] are fp32 device pointers. */
 int rdsic_eb_aux_loss(const float* params, const float* quantiles, const float* target, int32_t C, float* terms,
                       float* sum, rdsic_stream_t stream);
+
+/* ---- CDF tables for the entropy coder: `update()`.  The tables are what the reference's rANS
+ * coder consumes (`_quantized_cdf` int32 [rows, max_length+2], `_cdf_length`, `_offset`); building them is a
+ * once-per-model step.  Three stages, all on the device:
+ *   sizes  per row: support of the pmf  -> offset[row], cdf_length[row] (= pmf_length + 2)
+ *   pmf    prob[row][0..pmf_length) = pmf, prob[row][pmf_length] = tail mass (float32, reference op order)
+ *   cdf    pmf_to_quantized_cdf (pip compressai `_CXX`, C++ absent from the reference tree: restated from the
+ *          published algorithm, integer-exact against oracle/cdf_oracle.py) applied to every row.          */
+/* GaussianConditional.update (entropy_models.py:599-625): center = ceil(table*multiplier),
+ * multiplier = -norm.ppf(tail_mass/2) computed by the caller; offset = -center, cdf_length = 2*center+3. */
+int rdsic_gc_cdf_sizes(const float* table, int32_t rows, float multiplier, int32_t* offset, int32_t* cdf_length,
+                       rdsic_stream_t stream);
+int rdsic_gc_pmf(const float* table, const int32_t* offset, int32_t rows, float* prob, int32_t ld, rdsic_stream_t stream);
+/* EntropyBottleneck.update (entropy_models.py:356-394): quantiles [C][3]; minima/maxima = clamp(ceil(.),0);
+ * offset = -minima, cdf_length = maxima+minima+3.  params as in rdsic_eb_desc; max_length = max pmf_length
+ * (the tail mass uses the sample at max_length-1, entropy_models.py:388). */
+int rdsic_eb_cdf_sizes(const float* quantiles, int32_t C, int32_t* offset, int32_t* cdf_length, rdsic_stream_t stream);
+int rdsic_eb_pmf(const float* params, const float* quantiles, const int32_t* offset, const int32_t* cdf_length, int32_t C,
+                 int32_t max_length, float* prob, int32_t ld, rdsic_stream_t stream);
+/* EntropyModel._pmf_to_cdf (entropy_models.py:174-182) + pmf_to_quantized_cdf: row r uses prob[r*ld .. +cdf_length[r]-1)
+ * and writes cdf[r*cdf_ld .. +cdf_length[r]), zero padded to cdf_ld.  *status (device int32, caller-zeroed) is set
+ * to 1 + row if a row is invalid (negative / non-finite / all-zero pmf, or no symbol left to steal from). */
+int rdsic_pmf_to_quantized_cdf(const float* prob, int32_t ld, const int32_t* cdf_length, int32_t rows, int32_t precision,
+                               int32_t* cdf, int32_t cdf_ld, int32_t* status, rdsic_stream_t stream);
+
 int rdsic_copy_forward(const rdsic_copy_desc* d, rdsic_stream_t stream);
 int rdsic_ln_forward(const rdsic_ln_desc* d, rdsic_stream_t stream);
 int rdsic_patch_forward(const rdsic_patch_desc* d, rdsic_stream_t stream);

@@ -102,6 +102,7 @@ class Op(C.Structure):
 EXPORTS = (
     "rdsic_abi_version", "rdsic_error_string", "rdsic_sizeof",
     "rdsic_conv_forward", "rdsic_attn_forward", "rdsic_eb_forward", "rdsic_gc_forward", "rdsic_eb_aux_loss",
+    "rdsic_gc_cdf_sizes", "rdsic_gc_pmf", "rdsic_eb_cdf_sizes", "rdsic_eb_pmf", "rdsic_pmf_to_quantized_cdf",
     "rdsic_copy_forward", "rdsic_ln_forward", "rdsic_patch_forward", "rdsic_run_program",
     "rdsic_graph_create", "rdsic_graph_launch", "rdsic_graph_num_kernels", "rdsic_graph_destroy",
 )
@@ -132,6 +133,12 @@ def lib():
         getattr(L, fn).restype = C.c_int
     L.rdsic_eb_aux_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.rdsic_eb_aux_loss.restype = C.c_int
+    vp, i32 = C.c_void_p, C.c_int32
+    for fn, args in (("rdsic_gc_cdf_sizes", [vp, i32, C.c_float, vp, vp, vp]), ("rdsic_gc_pmf", [vp, vp, i32, vp, i32, vp]),
+                     ("rdsic_eb_cdf_sizes", [vp, i32, vp, vp, vp]), ("rdsic_eb_pmf", [vp, vp, vp, vp, i32, i32, vp, i32, vp]),
+                     ("rdsic_pmf_to_quantized_cdf", [vp, i32, vp, i32, i32, vp, i32, vp, vp])):
+        getattr(L, fn).argtypes = args
+        getattr(L, fn).restype = C.c_int
     L.rdsic_run_program.argtypes = [C.POINTER(Op), C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.rdsic_graph_create.argtypes = [C.POINTER(Op), C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
     L.rdsic_graph_launch.argtypes = [C.c_void_p, C.c_void_p]

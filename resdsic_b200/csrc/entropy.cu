@@ -170,7 +170,186 @@ __global__ void __launch_bounds__(1024) eb_aux_loss_kernel(const float* __restri
   if (threadIdx.x == 0) *sum = s_part[0];
 }
 
+// ------------------------------------------------------------------ CDF tables (update())
+__global__ void gc_cdf_sizes_kernel(const float* __restrict__ table, int rows, float mult, int* __restrict__ offset,
+                                    int* __restrict__ cdf_length) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  const int center = (int)ceilf(__fmul_rn(table[i], mult));  // torch.ceil(scale_table * multiplier).int()
+  offset[i] = -center;
+  cdf_length[i] = 2 * center + 1 + 2;
+}
+
+// one block per table row; prob[row][j] = pmf(j), prob[row][pmf_length] = tail mass = 2 * lower(j = 0)
+__global__ void gc_pmf_kernel(const float* __restrict__ table, const int* __restrict__ offset, float* __restrict__ prob, int ld) {
+  const int row = blockIdx.x, center = -offset[row], len = 2 * center + 1;
+  const float scale = table[row];
+  const float cst = -0.70710678118654752440f;
+  for (int j = threadIdx.x; j < len; j += blockDim.x) {
+    const int d = j - center;
+    const float s = (float)(d < 0 ? -d : d);
+    const float up = __fmul_rn(0.5f, erfcf(__fmul_rn(cst, __fdiv_rn(__fsub_rn(0.5f, s), scale))));
+    const float lo = __fmul_rn(0.5f, erfcf(__fmul_rn(cst, __fdiv_rn(__fsub_rn(-0.5f, s), scale))));
+    prob[(size_t)row * ld + j] = __fsub_rn(up, lo);
+    if (j == 0) prob[(size_t)row * ld + len] = __fmul_rn(2.0f, lo);
+  }
+}
+
+__global__ void eb_cdf_sizes_kernel(const float* __restrict__ quantiles, int C, int* __restrict__ offset, int* __restrict__ cdf_length) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float q0 = quantiles[3 * c], med = quantiles[3 * c + 1], q2 = quantiles[3 * c + 2];
+  int minima = (int)ceilf(__fsub_rn(med, q0)), maxima = (int)ceilf(__fsub_rn(q2, med));
+  minima = minima < 0 ? 0 : minima;
+  maxima = maxima < 0 ? 0 : maxima;
+  offset[c] = -minima;
+  cdf_length[c] = maxima + minima + 1 + 2;
+}
+
+__device__ __forceinline__ float eb_pmf_at(const float* p, float v, float* lower, float* upper) {
+  const float lo = eb_logits(p, __fsub_rn(v, 0.5f)), up = eb_logits(p, __fadd_rn(v, 0.5f));
+  const float su = __fadd_rn(lo, up);
+  const float sgn = su > 0.f ? -1.f : (su < 0.f ? 1.f : 0.f);
+  *lower = lo;
+  *upper = up;
+  return fabsf(__fsub_rn(sigmoid_ref(__fmul_rn(sgn, up)), sigmoid_ref(__fmul_rn(sgn, lo))));
+}
+
+// one block per channel; samples j + (median - minima), j < max_length (entropy_models.py:373-388)
+__global__ void eb_pmf_kernel(const float* __restrict__ params, const float* __restrict__ quantiles, const int* __restrict__ offset,
+                              const int* __restrict__ cdf_length, int max_length, float* __restrict__ prob, int ld) {
+  const int c = blockIdx.x, len = cdf_length[c] - 2;
+  const float* p = params + (size_t)c * RDSIC_EB_STRIDE;
+  const float start = __fsub_rn(quantiles[3 * c + 1], (float)(-offset[c]));
+  for (int j = threadIdx.x; j < len; j += blockDim.x) {
+    float lo, up;
+    prob[(size_t)c * ld + j] = eb_pmf_at(p, __fadd_rn((float)j, start), &lo, &up);
+  }
+  if (threadIdx.x == 0) {  // tail mass = sigmoid(lower[0]) + sigmoid(-upper[max_length - 1])
+    float lo0, up0, lo1, up1;
+    eb_pmf_at(p, __fadd_rn(0.0f, start), &lo0, &up0);
+    eb_pmf_at(p, __fadd_rn((float)(max_length - 1), start), &lo1, &up1);
+    prob[(size_t)c * ld + len] = __fadd_rn(sigmoid_ref(lo0), sigmoid_ref(-up1));
+  }
+}
+
+// pmf_to_quantized_cdf: one warp per row, the row's cdf in shared memory (see oracle/cdf_oracle.py for the
+// algorithm and its provenance).  Integer arithmetic throughout after the fp32 round(p * 2^precision).
+__global__ void __launch_bounds__(32) pmf_to_cdf_kernel(const float* __restrict__ prob, int ld, const int* __restrict__ cdf_length,
+                                                        int precision, int* __restrict__ cdf_out, int cdf_ld, int* status) {
+  extern __shared__ unsigned int s_cdf[];
+  const int row = blockIdx.x, lane = threadIdx.x;
+  const int n = cdf_length[row];  // cdf entries; n - 1 probabilities
+  const float* p = prob + (size_t)row * ld;
+  const unsigned int one = 1u << precision;
+  bool bad = false;
+  unsigned long long part = 0;
+  if (lane == 0) s_cdf[0] = 0;
+  for (int k = lane; k < n - 1; k += 32) {
+    const float v = p[k];
+    if (!(v >= 0.f) || isinf(v)) bad = true;
+    const unsigned int f = bad ? 0u : (unsigned int)roundf(__fmul_rn(v, (float)one));  // std::round: half away from zero
+    s_cdf[k + 1] = f;
+    part += f;
+  }
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  bad = __any_sync(0xffffffffu, bad) || part == 0 || n < 2;
+  if (bad) {
+    if (lane == 0) atomicCAS(status, 0, 1 + row);
+    for (int k = lane; k < cdf_ld; k += 32) cdf_out[(size_t)row * cdf_ld + k] = 0;
+    return;
+  }
+  const unsigned long long total = part;
+  __syncwarp();
+  // rescale, then inclusive prefix sum in chunks of 32
+  unsigned int carry = 0;
+  for (int k0 = 0; k0 < n; k0 += 32) {
+    const int k = k0 + lane;
+    unsigned int v = k < n ? (unsigned int)(((unsigned long long)one * s_cdf[k]) / total) : 0u;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    v += carry;
+    if (k < n) s_cdf[k] = v;
+    carry = __shfl_sync(0xffffffffu, v, 31);
+  }
+  __syncwarp();
+  if (lane == 0) s_cdf[n - 1] = one;
+  __syncwarp();
+  // give every zero-width symbol one count, stolen from the lowest-frequency symbol with more than one
+  for (int i = 0; i < n - 1; ++i) {
+    if (s_cdf[i] != s_cdf[i + 1]) continue;  // uniform: every lane reads the same two words
+    unsigned int best_f = 0xffffffffu;
+    int best_j = 0x7fffffff;
+    for (int j = lane; j < n - 1; j += 32) {
+      const unsigned int f = s_cdf[j + 1] - s_cdf[j];
+      if (f > 1u && f < best_f) { best_f = f; best_j = j; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned int of = __shfl_xor_sync(0xffffffffu, best_f, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
+      if (of < best_f || (of == best_f && oj < best_j)) { best_f = of; best_j = oj; }
+    }
+    if (best_f == 0xffffffffu) {  // (the reference asserts) nothing to steal from
+      if (lane == 0) atomicCAS(status, 0, 1 + row);
+      break;
+    }
+    __syncwarp();
+    if (best_j < i) {
+      for (int j = best_j + 1 + lane; j <= i; j += 32) s_cdf[j] -= 1u;
+    } else {
+      for (int j = i + 1 + lane; j <= best_j; j += 32) s_cdf[j] += 1u;
+    }
+    __syncwarp();
+  }
+  __syncwarp();
+  for (int k = lane; k < cdf_ld; k += 32) cdf_out[(size_t)row * cdf_ld + k] = k < n ? (int)s_cdf[k] : 0;
+}
+
 }  // namespace
+
+extern "C" int rdsic_gc_cdf_sizes(const float* table, int32_t rows, float multiplier, int32_t* offset, int32_t* cdf_length,
+                                  rdsic_stream_t stream) {
+  RDSIC_CHECK_ARG(table && offset && cdf_length && rows > 0 && multiplier > 0.f);
+  gc_cdf_sizes_kernel<<<ceil_div(rows, 128), 128, 0, (cudaStream_t)stream>>>(table, rows, multiplier, offset, cdf_length);
+  return rdsic_launch_status();
+}
+
+extern "C" int rdsic_gc_pmf(const float* table, const int32_t* offset, int32_t rows, float* prob, int32_t ld,
+                            rdsic_stream_t stream) {
+  RDSIC_CHECK_ARG(table && offset && prob && rows > 0 && ld > 0);
+  gc_pmf_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(table, offset, prob, ld);
+  return rdsic_launch_status();
+}
+
+extern "C" int rdsic_eb_cdf_sizes(const float* quantiles, int32_t C, int32_t* offset, int32_t* cdf_length, rdsic_stream_t stream) {
+  RDSIC_CHECK_ARG(quantiles && offset && cdf_length && C > 0);
+  eb_cdf_sizes_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(quantiles, C, offset, cdf_length);
+  return rdsic_launch_status();
+}
+
+extern "C" int rdsic_eb_pmf(const float* params, const float* quantiles, const int32_t* offset, const int32_t* cdf_length,
+                            int32_t C, int32_t max_length, float* prob, int32_t ld, rdsic_stream_t stream) {
+  RDSIC_CHECK_ARG(params && quantiles && offset && cdf_length && prob && C > 0 && max_length > 0 && ld > max_length);
+  eb_pmf_kernel<<<C, 64, 0, (cudaStream_t)stream>>>(params, quantiles, offset, cdf_length, max_length, prob, ld);
+  return rdsic_launch_status();
+}
+
+extern "C" int rdsic_pmf_to_quantized_cdf(const float* prob, int32_t ld, const int32_t* cdf_length, int32_t rows,
+                                          int32_t precision, int32_t* cdf, int32_t cdf_ld, int32_t* status,
+                                          rdsic_stream_t stream) {
+  RDSIC_CHECK_ARG(prob && cdf_length && cdf && status && rows > 0 && ld > 0 && cdf_ld >= 2 && cdf_ld <= ld + 1);
+  RDSIC_CHECK_ARG(precision >= 1 && precision <= 24);
+  const size_t smem = (size_t)cdf_ld * sizeof(unsigned int);  // every row fits cdf_ld entries
+  if (smem > 48 * 1024) {
+    if (smem > 200 * 1024) return RDSIC_E_UNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(pmf_to_cdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  pmf_to_cdf_kernel<<<rows, 32, smem, (cudaStream_t)stream>>>(prob, ld, cdf_length, precision, cdf, cdf_ld, status);
+  return rdsic_launch_status();
+}
 
 extern "C" int rdsic_eb_aux_loss(const float* params, const float* quantiles, const float* target, int32_t C, float* terms,
                                  float* sum, rdsic_stream_t stream) {

@@ -5,9 +5,9 @@ Mirror of the reference's vendored CompressAI classes
 parameter/buffer names and forward semantics in eval mode (round) and in
 training mode (additive U(-1/2,1/2) noise, forward VALUES only -- there is no
 autograd through the CUDA kernels).  In scope: forward (quantise + likelihood),
-quantize, dequantize, build_indexes, EntropyBottleneck.loss.  Out of scope per
-BASELINE.json (stays in the reference's C++): update() CDF tables and the rANS
-compress()/decompress().
+quantize, dequantize, build_indexes, EntropyBottleneck.loss and the CDF-table build
+`update()`.  Out of scope per BASELINE.json (stays in the
+reference's C++): the rANS compress()/decompress().
 """
 import ctypes
 
@@ -40,9 +40,50 @@ class EntropyModel(B200Module):
     quantized_cdf = property(lambda self: self._quantized_cdf)
     cdf_length = property(lambda self: self._cdf_length)
 
-    def update(self, *a, **k):
-        raise NotImplementedError("CDF-table build (update) is out of scope for the B200 forward path; "
-                                  "use the reference's C++ `pmf_to_quantized_cdf` (SURVEY section 8f N2)")
+    # -- CDF tables (update()): what the reference's rANS coder consumes; built on the device --------------
+    @staticmethod
+    def _stream(dev):
+        return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    @staticmethod
+    def _require_cuda(t, what):
+        if t.device.type != "cuda":
+            raise RuntimeError(f"resdsic_b200 {what} runs on CUDA devices only (no CPU fallback)")
+
+    def _pmf_to_cdf(self, prob, cdf_length, max_length):
+        """reference entropy_models.py:174-182 + `pmf_to_quantized_cdf`: prob [rows, max_length+1] fp32 holds
+        pmf[:pmf_length] ++ tail_mass per row; returns int32 [rows, max_length+2], zero padded."""
+        dev = prob.device
+        rows = prob.shape[0]
+        cdf = torch.empty(rows, max_length + 2, dtype=torch.int32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().rdsic_pmf_to_quantized_cdf(prob.data_ptr(), prob.shape[1], cdf_length.data_ptr(), rows,
+                                                             self.entropy_coder_precision, cdf.data_ptr(), cdf.shape[1],
+                                                             status.data_ptr(), self._stream(dev)), "pmf_to_quantized_cdf")
+        bad = int(status.item())
+        if bad:  # reference: std::domain_error from the C++ op -> ValueError-like failure in update()
+            raise ValueError(f"Invalid `pmf` in table row {bad - 1}: negative, non-finite or all-zero probabilities")
+        return cdf
+
+    def _check_cdf_size(self):
+        """reference entropy_models.py:184-203."""
+        if self._quantized_cdf.numel() == 0:
+            raise ValueError("Uninitialized CDFs. Run update() first")
+        if len(self._quantized_cdf.size()) != 2:
+            raise ValueError(f"Invalid CDF size {self._quantized_cdf.size()}")
+
+    def _check_offsets_size(self):
+        if self._offset.numel() == 0:
+            raise ValueError("Uninitialized offsets. Run update() first")
+        if len(self._offset.size()) != 1:
+            raise ValueError(f"Invalid offsets size {self._offset.size()}")
+
+    def _check_cdf_length(self):
+        if self._cdf_length.numel() == 0:
+            raise ValueError("Uninitialized CDF lengths. Run update() first")
+        if len(self._cdf_length.size()) != 1:
+            raise ValueError(f"Invalid offsets size {self._cdf_length.size()}")
 
     def compress(self, *a, **k):
         raise NotImplementedError("rANS bitstream coding stays in the reference's C++ (BASELINE.json north_star)")
@@ -122,6 +163,30 @@ class EntropyBottleneck(EntropyModel):
         return out, lik
 
     @torch.no_grad()
+    def update(self, force=False):
+        """reference entropy_models.py:356-394 (this fork recomputes unconditionally; `force` is accepted and
+        ignored like there).  Fills `_offset`, `_quantized_cdf`, `_cdf_length` on the parameters' device."""
+        q = self.quantiles.detach().float().contiguous()
+        dev = q.device
+        self._require_cuda(q, "EntropyBottleneck.update")
+        Cn = self.channels
+        L = _lib.lib()
+        offset = torch.empty(Cn, dtype=torch.int32, device=dev)
+        cdf_length = torch.empty(Cn, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.rdsic_eb_cdf_sizes(q.data_ptr(), Cn, offset.data_ptr(), cdf_length.data_ptr(), self._stream(dev)),
+                       "EntropyBottleneck.update sizes")
+            max_length = int(cdf_length.max().item()) - 2  # the one host sync: the table width
+            prob = torch.zeros(Cn, max_length + 1, dtype=torch.float32, device=dev)
+            _lib.check(L.rdsic_eb_pmf(self.packed().data_ptr(), q.data_ptr(), offset.data_ptr(), cdf_length.data_ptr(), Cn,
+                                      max_length, prob.data_ptr(), prob.shape[1], self._stream(dev)),
+                       "EntropyBottleneck.update pmf")
+        self._quantized_cdf = self._pmf_to_cdf(prob, cdf_length, max_length)
+        self._offset, self._cdf_length = offset, cdf_length
+        self.__dict__["_last_prob"] = prob  # kept for the parity tests (float stage)
+        return True
+
+    @torch.no_grad()
     def loss(self):
         """reference entropy_models.py:396-399: sum |logits_cumulative(quantiles) - target| (forward value)."""
         dev = self.quantiles.device
@@ -162,6 +227,49 @@ class GaussianConditional(EntropyModel):
         self.scale_bound_value = float(scale_bound)
         self.register_buffer("scale_table", torch.Tensor(tuple(float(s) for s in scale_table)) if scale_table else torch.Tensor())
         self.register_buffer("scale_bound", torch.Tensor([float(scale_bound)]))
+
+    @staticmethod
+    def _prepare_scale_table(scale_table):
+        """reference entropy_models.py:575-577."""
+        return torch.Tensor(tuple(float(x) for x in scale_table))
+
+    @staticmethod
+    def _standardized_quantile(quantile):
+        """reference entropy_models.py:586-588 (host scalar)."""
+        import scipy.stats
+        return scipy.stats.norm.ppf(quantile)
+
+    def update_scale_table(self, scale_table, force=False):
+        """reference entropy_models.py:590-598."""
+        device = self.scale_bound.device
+        self.scale_table = self._prepare_scale_table(scale_table).to(device)
+        self.update()
+        return True
+
+    @torch.no_grad()
+    def update(self):
+        """reference entropy_models.py:599-625: one CDF row per scale-table entry."""
+        table = self.scale_table.detach().float().contiguous()
+        dev = table.device
+        self._require_cuda(table, "GaussianConditional.update")
+        if table.numel() == 0:
+            raise ValueError("empty scale_table: call update_scale_table(scale_table) first")
+        n = table.numel()
+        multiplier = float(-self._standardized_quantile(self.tail_mass / 2))
+        L = _lib.lib()
+        offset = torch.empty(n, dtype=torch.int32, device=dev)
+        cdf_length = torch.empty(n, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.rdsic_gc_cdf_sizes(table.data_ptr(), n, multiplier, offset.data_ptr(), cdf_length.data_ptr(),
+                                            self._stream(dev)), "GaussianConditional.update sizes")
+            max_length = int(cdf_length.max().item()) - 2  # the one host sync: the table width
+            prob = torch.zeros(n, max_length + 1, dtype=torch.float32, device=dev)
+            _lib.check(L.rdsic_gc_pmf(table.data_ptr(), offset.data_ptr(), n, prob.data_ptr(), prob.shape[1],
+                                      self._stream(dev)), "GaussianConditional.update pmf")
+        self._quantized_cdf = self._pmf_to_cdf(prob, cdf_length, max_length)
+        self._offset, self._cdf_length = offset, cdf_length
+        self.__dict__["_last_prob"] = prob
+        self.__dict__.pop("_pack_cache", None)  # the device copy of the scale table follows the new buffer
 
     def table(self, device):
         """Device copy of the scale table; falls back to the model default

@@ -42,6 +42,15 @@ class CompressionModel(B200Module):
         from ..entropy_models import EntropyBottleneck
         return sum(m.loss() for m in self.modules() if isinstance(m, EntropyBottleneck))
 
+    def update(self, force=False):
+        """reference WACNN/base.py:36-59: update the CDF tables of every EntropyBottleneck child."""
+        from ..entropy_models import EntropyBottleneck
+        updated = False
+        for m in self.children():
+            if isinstance(m, EntropyBottleneck):
+                updated |= m.update(force=force)
+        return updated
+
     def load_state_dict(self, state_dict, strict=False):
         return nn.Module.load_state_dict(self, state_dict, strict=strict)
 
@@ -119,7 +128,13 @@ class WACNN(CompressionModel):
         return net
 
     def update(self, scale_table=None, force=False):
-        raise NotImplementedError("CDF-table update() is out of scope (rANS side stays in the reference's C++)")
+        """reference cnn.py:135-140: CDF tables of the Gaussian conditional (one row per scale-table entry)
+        and of the bottleneck, built by the CUDA library."""
+        if scale_table is None:
+            scale_table = get_scale_table()
+        updated = self.gaussian_conditional.update_scale_table(scale_table, force=force)
+        updated |= super().update(force=force)
+        return updated
 
     def compress(self, x):
         raise NotImplementedError("rANS bitstream coding stays in the reference's C++; use symbols_and_indexes(x) for "

@@ -47,7 +47,28 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self._stop_evt = index, [], threading.Event()
 
+    def _run_nvml(self):
+        """Fast path: NVML through nvidia_ml_py (a query takes microseconds, so even a 100 ms timed region gets
+        several samples); same fields as the nvidia-smi query below."""
+        import pynvml as N
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(self.index)
+        mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+        while not self._stop_evt.is_set():
+            r = get_reasons(h)
+            self.samples.append([str(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), str(mx),
+                                 str(N.nvmlDeviceGetPowerUsage(h) / 1000.0)] +
+                                ["Active" if r & b else "Not Active" for _, b in bits])
+            self._stop_evt.wait(0.01)
+
     def run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            pass
         while not self._stop_evt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
@@ -314,7 +335,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("RESDSIC_PRECISION", "bf16"), choices=["fp32", "bf16"])
-    ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
+    # 24 images x 1536 latent pixels = 144 of the 256-row tiles of the slice-loop GEMMs: one full wave of the 148
+    # SMs (batch 16 fills 96 of them, batch 32 needs a second, 30 %-full wave).  Sweep: DESIGN.md section 5.
+    ap.add_argument("--batch", type=int, default=24, help="images per GPU per step")
     ap.add_argument("--micro-batches", default="auto", help="sub-batches run as concurrent graphs (auto | 1 | 2 | 4 ...)")
     ap.add_argument("--model", default="cnn", choices=["cnn", "stf"], help="cnn = the headline (BASELINE.json) workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -23,6 +23,7 @@ constexpr int G_EPI_WARPS = 12;
 constexpr int G_ISSUER2_WARP = 2 + G_EPI_WARPS;
 constexpr int G_PRODUCER2_WARP = G_ISSUER2_WARP + 1;
 constexpr int G_THREADS = 128 + 32 * G_EPI_WARPS;  // two TMA warps, two MMA issuer warps, epilogue warps
+// (16 warps = 4 per scheduler: a 17th warp would cap the kernel at 96 registers per thread and spill)
 constexpr int G_PARTS = G_EPI_WARPS / 4;
 constexpr int MAXC = 192;                    // channel count supported (TMEM: 2.5 C <= 512)
 constexpr int MAX_CHUNKS = MAXC / 16 / G_PARTS;
@@ -50,6 +51,13 @@ struct GdnGeom {
   int p_col, acc2_col;
   int N2, k2_blocks, kc2_last;  // second GEMM: N2 output columns, K2 = N1 in 64-wide blocks
   int ksplit;                   // GEMM 1 split across two issuers / two accumulators
+  // dbl (ResidualUnit tail, N2 == 2 C, 4 C + C <= 512): TMEM = two K-split accumulator pairs [b*2C, b*2C + 2C)
+  // and two staged operands P[b]; the tail GEMM of tile t writes its accumulator OVER pair t&1 (free once
+  // phase 1 has read it).  The two issuer warps run only main loops (K-split as before); the tail GEMM is issued
+  // by the first epilogue warp once all twelve have staged their part of P (it would wait for exactly that anyway):
+  // the main loop of tile t+1 overlaps phase 1 / tail GEMM / phase 2 of tile t, which the single-buffered flow
+  // serialises (measured: 8.4k-cycle main loop + 3.9k exposed per tile, tests/gpu_ru_trace.py).
+  int dbl;
 };
 
 template <int MODE>
@@ -63,10 +71,10 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint8_t* gamma_s = smem + (size_t)g.num_stages * stage_bytes;  // 1024-aligned: stage sizes are multiples of 2048
   uint64_t* full_bar = (uint64_t*)(gamma_s + gg.w2_bytes);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
-  uint64_t* acc1_full = empty_bar + MAX_STAGES;
-  uint64_t* acc1_empty = acc1_full + 1;
-  uint64_t* p_full = acc1_empty + 1;
-  uint64_t* acc2_full = p_full + 1;
+  uint64_t* acc1_full = empty_bar + MAX_STAGES;  // [2] (second entries used in dbl mode)
+  uint64_t* acc1_empty = acc1_full + 2;          // [2]
+  uint64_t* p_full = acc1_empty + 2;             // [2]
+  uint64_t* acc2_full = p_full + 2;
   uint64_t* acc2_empty = acc2_full + 1;
   uint64_t* g_full = acc2_empty + 1;
   uint32_t* tmem_slot = (uint32_t*)(g_full + 1);
@@ -82,9 +90,11 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(acc1_full, gg.ksplit ? 2 : 1);
-    mbar_init(acc1_empty, G_EPI_WARPS);
-    mbar_init(p_full, G_EPI_WARPS);
+    for (int k = 0; k < 2; ++k) {
+      mbar_init(&acc1_full[k], gg.ksplit ? 2 : 1);
+      mbar_init(&acc1_empty[k], G_EPI_WARPS);
+      mbar_init(&p_full[k], G_EPI_WARPS);
+    }
     mbar_init(acc2_full, 1);
     mbar_init(acc2_empty, G_EPI_WARPS);
     mbar_init(g_full, 1);
@@ -164,7 +174,65 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   } else if (warp == 1 || warp == G_ISSUER2_WARP) {
     // ================= MMA issuers (whole warp, elected lane issues) =================
     const uint32_t me = warp == 1 ? 0u : 1u;
-    if (!me || gg.ksplit) {
+    if (gg.dbl) {
+      // ---- dbl mode: both issuers run ONLY main loops (K-split, own accumulator of pair lt & 1)
+      const uint32_t idesc = make_idesc(C);
+      const int taps = d.KH * d.KW;
+      const int kc_last = (d.Cin - (g.kb_per_tap - 1) * BK) / 16;
+      const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+      const uint32_t empty0 = __shfl_sync(0xffffffffu, smem_u32(empty_bar), 0);
+      const uint32_t full0 = __shfl_sync(0xffffffffu, smem_u32(full_bar), 0);
+      const uint64_t dconst = make_sw128_desc(0);
+      const uint32_t a_u0 = (smem_base & 0x3FFFFu) >> 4, stage_u = (uint32_t)stage_bytes >> 4;
+      int ns = g.num_stages, kb = g.kb_per_tap, kiters = taps * g.kb_per_tap, total = g.total_tiles, step = gridDim.x;
+      asm volatile("" : "+r"(ns), "+r"(kb), "+r"(kiters), "+r"(total), "+r"(step));
+      const int kq = kiters / ns, kr = kiters % ns;
+      int s_base = 0;
+      uint32_t ph_base = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < total; tile += step, ++lt) {
+        const uint32_t b = lt & 1u, use = (lt >> 1) & 1u;
+        long long* tsp = (g.dbg_ts && blockIdx.x == 0 && !me && lane == 0 && lt < 250) ? g.dbg_ts + lt * 16 : nullptr;
+        if (tsp) tsp[0] = clock64();
+        const int f = (int)me ^ (s_base & 1);  // K-split ownership by stage parity (see conv_bf16.cu)
+        int s = s_base + f;
+        uint32_t ph = ph_base;
+        if (s >= ns) { s -= ns; ph ^= 1u; }
+        int cb = f % kb;
+        const int n_own = (kiters - f + 1) / 2;
+        mbar_wait(&acc1_empty[b], use ^ 1u);  // pair b drained (phase 2 of tile lt - 2 done)
+        tcgen05_fence_after();
+        if (tsp) tsp[1] = clock64();
+        const uint32_t acc1 = tbase + b * (uint32_t)(2 * C) + me * (uint32_t)C;
+        for (int n = 0; n < n_own; ++n) {
+          mbar_wait_u32(full0 + 8u * (uint32_t)s, ph);
+          tcgen05_fence_after();
+          const uint64_t da = dconst + (uint64_t)(a_u0 + (uint32_t)s * stage_u), db = da + (A_STAGE_BYTES >> 4);
+          if (elect_one()) {
+            if (cb + 1 != kb || kc_last == 4) {
+              umma_bf16(acc1, da, db, idesc, n > 0 ? 1u : 0u);
+              umma_bf16(acc1, da + 2, db + 2, idesc, 1u);
+              umma_bf16(acc1, da + 4, db + 4, idesc, 1u);
+              umma_bf16(acc1, da + 6, db + 6, idesc, 1u);
+            } else {
+              for (int k = 0; k < kc_last; ++k) umma_bf16(acc1, da + 2 * k, db + 2 * k, idesc, (n > 0 || k > 0) ? 1u : 0u);
+            }
+            tcgen05_commit_u32(empty0 + 8u * (uint32_t)s);
+          }
+          __syncwarp();
+          s += 2;
+          if (s >= ns) { s -= ns; ph ^= 1u; }
+          cb += 2;
+          while (cb >= kb) cb -= kb;
+        }
+        ph_base ^= (uint32_t)(kq & 1);
+        s_base += kr;
+        if (s_base >= ns) { s_base -= ns; ph_base ^= 1u; }
+        if (elect_one()) tcgen05_commit(&acc1_full[b]);
+        __syncwarp();
+        if (tsp) tsp[2] = tsp[3] = tsp[4] = tsp[5] = clock64();  // (the tail GEMM is issued by the first epilogue warp)
+      }
+    } else if (!me || gg.ksplit) {
       const uint32_t idesc = make_idesc(C), idesc2 = make_idesc(gg.N2);
       const int taps = d.KH * d.KW;
       const int kc_last = (d.Cin - (g.kb_per_tap - 1) * BK) / 16;
@@ -265,12 +333,16 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const bool row_ok = oy < d.OH && ox < d.OW;
       const size_t pix = ((size_t)b * d.OHt + (oy * d.osy + d.ooy)) * d.OWt + (ox * d.osx + d.oox);
       const uint32_t par = lt & 1u;
+      // dbl: accumulator / staged-operand buffer of this tile and the parity of ITS barriers
+      const uint32_t bsel = gg.dbl ? (lt & 1u) : 0u, par1 = gg.dbl ? ((lt >> 1) & 1u) : par;
+      const uint32_t acc1_c = bsel * (uint32_t)(2 * C), p_c = (uint32_t)gg.p_col + bsel * (uint32_t)(C / 2);
+      const uint32_t acc2_c = gg.dbl ? acc1_c : (uint32_t)gg.acc2_col;  // dbl: the tail accumulator overlays pair bsel
       uint32_t xs[MAX_CHUNKS][8];  // GDN: x as packed bf16, kept for the final multiply; RU: prefetched residual
 
       long long* tsp = (g.dbg_ts && blockIdx.x == 0 && warp == 2 && lane == 0 && lt < 250) ? g.dbg_ts + lt * 16 : nullptr;
       if (tsp) tsp[8] = clock64();
       // ---- phase 1: v = acc1 + bias;  GDN: stage v^2, keep v;  RU: stage gelu(v)
-      mbar_wait(acc1_full, par);
+      mbar_wait(&acc1_full[bsel], par1);
       tcgen05_fence_after();
       if (tsp) tsp[9] = clock64();
 #pragma unroll
@@ -278,10 +350,10 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         const int j = part + G_PARTS * ci;
         if (j >= nchunks1) break;
         float v[16];
-        tmem_ld16(tmem_base + lane_off + (uint32_t)(j * 16), v);
+        tmem_ld16(tmem_base + lane_off + acc1_c + (uint32_t)(j * 16), v);
         if (gg.ksplit) {  // fixed order: even + odd k-iterations
           float w[16];
-          tmem_ld16(tmem_base + lane_off + (uint32_t)(C + j * 16), w);
+          tmem_ld16(tmem_base + lane_off + acc1_c + (uint32_t)(C + j * 16), w);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += w[i];
         }
@@ -306,16 +378,35 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             st[i] = *reinterpret_cast<uint32_t*>(&h2);
           }
         }
-        tmem_st8(tmem_base + lane_off + (uint32_t)(gg.p_col + j * 8), st);
+        tmem_st8(tmem_base + lane_off + p_c + (uint32_t)(j * 8), st);
       }
       tmem_st_wait();
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(acc1_empty);  // acc1 drained: GEMM 1 of the next tile may start
-        mbar_arrive(p_full);      // staged operand in place: GEMM 2 may start
+        if (!gg.dbl) mbar_arrive(&acc1_empty[0]);  // acc1 drained: GEMM 1 of the next tile may start
+        mbar_arrive(&p_full[bsel]);                // staged operand in place: GEMM 2 may start
       }
       if (tsp) tsp[10] = clock64();
+      if (gg.dbl && warp == 2) {
+        // tail GEMM: A = staged P[bsel] (TMEM), B = resident W3, D over accumulator pair bsel
+        mbar_wait(&p_full[bsel], par1);  // all twelve epilogue warps have staged P and consumed pair bsel
+        if (lt == 0) mbar_wait(g_full, 0);
+        tcgen05_fence_after();
+        const uint32_t idesc2 = make_idesc(gg.N2);
+        const uint32_t gamma_addr = smem_u32(gamma_s);
+        const uint32_t p_t = tmem_base + p_c, acc2 = tmem_base + acc2_c;
+        if (elect_one()) {
+          for (int kb2 = 0; kb2 < gg.k2_blocks; ++kb2) {
+            const uint64_t dg = make_sw128_desc(gamma_addr + (uint32_t)(kb2 * gg.N2 * 128));
+            const int kc2 = kb2 + 1 == gg.k2_blocks ? gg.kc2_last : BK / 16;
+            for (int k = 0; k < kc2; ++k)
+              umma_bf16_ts(acc2, p_t + (uint32_t)((kb2 * 4 + k) * 8), dg + 2 * k, idesc2, (kb2 | k) ? 1u : 0u);
+          }
+          tcgen05_commit(acc2_full);
+        }
+        __syncwarp();
+      }
       if (MODE == TAIL_RU) {  // residual x: issue the loads now, they land while GEMM 2 runs
         const __nv_bfloat16* resp = (const __nv_bfloat16*)d.res.ptr + pix * (size_t)d.res.ld + d.res.coff;
 #pragma unroll
@@ -332,12 +423,27 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       mbar_wait(acc2_full, par);
       tcgen05_fence_after();
       if (tsp) tsp[11] = clock64();
+      // chunks in pairs: both TMEM loads are in flight before the one wait (the epilogue is latency-bound with
+      // three warps per scheduler)
 #pragma unroll
-      for (int ci = 0; ci < MAX_CHUNKS; ++ci) {
-        const int j = part + G_PARTS * ci;
-        if (j >= nchunks2) break;
+      for (int cp = 0; cp < MAX_CHUNKS; cp += 2) {
+        const int ja = part + G_PARTS * cp, jb = ja + G_PARTS;
+        if (ja >= nchunks2) break;
+        const bool has_b = cp + 1 < MAX_CHUNKS && jb < nchunks2;
+        uint32_t ua[16], ub[16];
+        tmem_ld16_issue(tmem_base + lane_off + acc2_c + (uint32_t)(ja * 16), ua);
+        if (has_b) tmem_ld16_issue(tmem_base + lane_off + acc2_c + (uint32_t)(jb * 16), ub);
+        tmem_ld_wait();
+        tmem_ld_fence(ua);
+        if (has_b) tmem_ld_fence(ub);
+#pragma unroll
+      for (int hb = 0; hb < 2; ++hb) {
+        if (hb == 1 && !has_b) break;
+        const int ci = cp + hb, j = hb ? jb : ja;
+        const uint32_t* u = hb ? ub : ua;
         float v[16];
-        tmem_ld16(tmem_base + lane_off + (uint32_t)(gg.acc2_col + j * 16), v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(u[i]);
         if (!row_ok) continue;
         const float4* bp = reinterpret_cast<const float4*>(d.tail_bias + j * 16);
 #pragma unroll
@@ -358,9 +464,10 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
         store16(d.out, pix * (size_t)d.out.ld + d.out.coff + j * 16, v, false);
       }
+      }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc2_empty);
+      if (lane == 0) mbar_arrive(gg.dbl ? &acc1_empty[bsel] : acc2_empty);  // dbl: pair bsel (acc1 + overlaid acc2) is free
       if (tsp) tsp[12] = clock64();
     }
   }
@@ -456,8 +563,10 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   gg.w2_bytes = gg.k2_blocks * N2 * 128;
   static const int tune_ksplit = getenv("RDSIC_TC_KSPLIT") ? atoi(getenv("RDSIC_TC_KSPLIT")) : 1;
   gg.ksplit = tune_ksplit && g.num_k_iters >= 4 && (2 * C + C / 2 + 31) / 32 * 32 + N2 <= 512;
-  gg.p_col = C * (1 + gg.ksplit);
-  gg.acc2_col = (gg.p_col + C / 2 + 31) / 32 * 32;
+  static const int tune_dbl = getenv("RDSIC_RU_DBL") ? atoi(getenv("RDSIC_RU_DBL")) : 1;
+  gg.dbl = tune_dbl && gg.ksplit && d->tail_mode == TAIL_RU && N2 == 2 * C && 5 * C <= 512;
+  gg.p_col = gg.dbl ? 4 * C : C * (1 + gg.ksplit);
+  gg.acc2_col = gg.dbl ? 0 : (gg.p_col + C / 2 + 31) / 32 * 32;
   RDSIC_CHECK_ARG(gg.acc2_col + N2 <= 512);
   const int stage_bytes = A_STAGE_BYTES + g.b_stage_bytes;
   int stages = (200 * 1024 - gg.w2_bytes) / stage_bytes;
@@ -499,7 +608,7 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
       log_set = true;
     }
   }
-  const size_t smem = (size_t)stages * stage_bytes + gg.w2_bytes + 1024 + (2 * MAX_STAGES + 8) * 8 + 16;
+  const size_t smem = (size_t)stages * stage_bytes + gg.w2_bytes + 1024 + (2 * MAX_STAGES + 12) * 8 + 16;
   auto kern = d->tail_mode == TAIL_RU ? conv_gdn_tc_kernel<TAIL_RU>
               : d->tail_mode == TAIL_IGDN ? conv_gdn_tc_kernel<TAIL_IGDN> : conv_gdn_tc_kernel<TAIL_GDN>;
   static bool attr_set[16][4] = {};

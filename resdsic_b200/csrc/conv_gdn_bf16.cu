@@ -46,6 +46,99 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 enum { TAIL_GDN = 1, TAIL_IGDN = 2, TAIL_RU = 3 };
 
+// ---- GEMM 1 main loop of one tile (shared by the single-buffered and the double-buffered flows)
+// Halo mode (stride-1 multi-tap layers on maps a 16 x 8 patch tiles exactly): the (16+KH-1) x (8+KW-1) input patch
+// of a 64-channel block is loaded ONCE per tile into a small ring of A patches and every tap's A operand is a
+// shifted window of it (descriptor start + (r * halo_w + s) rows, SBO = halo row pitch; the hardware applies the
+// 128B swizzle on absolute shared-memory address bits, so the windows need no base offset).  The stage ring then
+// carries only the weights.  K runs channel-block-major (cb outer, taps inner).  Motivation: ncu of the non-halo
+// kernel shows L2->SM traffic 4.6 x the algorithmic bytes at 11.7 TB/s, i.e. at the chip's L2 throughput cap, and
+// the nine-fold re-read of A is 40 % of it.  Result: correct, but slower (see rdsic_conv_gdn_forward_bf16).
+struct K1Cfg {
+  int ns, kb, taps, kiters, kq, kr, kc_last, halo;
+  uint32_t full0, empty0, a_u0, stage_u, b_off_u, idesc;
+  uint32_t a_full0, a_empty0, patch_u0, patch_u, na_mask, na_shift, tap_off0;
+  uint64_t dconst, dconst_halo;
+};
+struct K1State {
+  int s_base;
+  uint32_t ph_base, pa_base;  // ring position / phase and A-patch counter at the start of the tile
+};
+
+__device__ __forceinline__ void k1_mmas(uint32_t acc, uint64_t da, uint64_t db, uint32_t idesc, int kc, bool first) {
+  if (kc == 4) {
+    umma_bf16(acc, da, db, idesc, first ? 0u : 1u);
+    umma_bf16(acc, da + 2, db + 2, idesc, 1u);
+    umma_bf16(acc, da + 4, db + 4, idesc, 1u);
+    umma_bf16(acc, da + 6, db + 6, idesc, 1u);
+  } else {
+    for (int k = 0; k < kc; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
+  }
+}
+
+// whole warp, uniform control flow; `ways` = 1 (single issuer) or 2 (K-split: this issuer owns the stages of its parity)
+__device__ __forceinline__ void gemm1_tile(K1State& st, const K1Cfg& c, uint32_t acc1, uint32_t me, int ways) {
+  const int f = ways == 2 ? (int)me ^ (st.s_base & 1) : 0;
+  int s = st.s_base + f;
+  uint32_t ph = st.ph_base;
+  if (s >= c.ns) { s -= c.ns; ph ^= 1u; }
+  const int n_own = (c.kiters - f + ways - 1) / ways;
+  if (!c.halo) {
+    int cb = f % c.kb;
+    for (int n = 0; n < n_own; ++n) {
+      mbar_wait_u32(c.full0 + 8u * (uint32_t)s, ph);
+      tcgen05_fence_after();
+      const uint64_t da = c.dconst + (uint64_t)(c.a_u0 + (uint32_t)s * c.stage_u), db = da + c.b_off_u;
+      if (elect_one()) {
+        k1_mmas(acc1, da, db, c.idesc, cb + 1 != c.kb ? 4 : c.kc_last, n == 0);
+        tcgen05_commit_u32(c.empty0 + 8u * (uint32_t)s);
+      }
+      __syncwarp();
+      s += ways;
+      if (s >= c.ns) { s -= c.ns; ph ^= 1u; }
+      cb += ways;
+      while (cb >= c.kb) cb -= c.kb;
+    }
+  } else {
+    int cb = 0, tap = f, cb_cur = -1;  // taps >= 2 in halo mode, so k-iteration f (0 or 1) is tap f of block 0
+    uint32_t slot_cur = 0, a_cur = 0;
+    for (int n = 0; n < n_own; ++n) {
+      if (cb != cb_cur) {
+        if (cb_cur >= 0) {  // done with the previous patch (once these MMAs retire)
+          if (elect_one()) tcgen05_commit_u32(c.a_empty0 + 8u * slot_cur);
+          __syncwarp();
+        }
+        const uint32_t p = st.pa_base + (uint32_t)cb;
+        slot_cur = p & c.na_mask;
+        mbar_wait_u32(c.a_full0 + 8u * slot_cur, (p >> c.na_shift) & 1u);
+        a_cur = c.patch_u0 + slot_cur * c.patch_u;
+        cb_cur = cb;
+      }
+      mbar_wait_u32(c.full0 + 8u * (uint32_t)s, ph);
+      tcgen05_fence_after();
+      uint32_t toff;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(toff) : "r"(c.tap_off0 + 4u * (uint32_t)tap));
+      const uint64_t da = c.dconst_halo + (uint64_t)(a_cur + toff);
+      const uint64_t db = c.dconst + (uint64_t)(c.a_u0 + (uint32_t)s * c.stage_u);
+      if (elect_one()) {
+        k1_mmas(acc1, da, db, c.idesc, cb + 1 != c.kb ? 4 : c.kc_last, n == 0);
+        tcgen05_commit_u32(c.empty0 + 8u * (uint32_t)s);
+      }
+      __syncwarp();
+      s += ways;
+      if (s >= c.ns) { s -= c.ns; ph ^= 1u; }
+      tap += ways;
+      if (tap >= c.taps) { tap -= c.taps; ++cb; }
+    }
+    if (elect_one()) tcgen05_commit_u32(c.a_empty0 + 8u * slot_cur);
+    __syncwarp();
+    st.pa_base += (uint32_t)c.kb;
+  }
+  st.ph_base ^= (uint32_t)(c.kq & 1);
+  st.s_base += c.kr;
+  if (st.s_base >= c.ns) { st.s_base -= c.ns; st.ph_base ^= 1u; }
+}
+
 struct GdnGeom {
   int w2_bytes;      // resident second-GEMM weight tiles: ceil(K2/64) x [N2 rows x 128 B]
   int p_col, acc2_col;
@@ -58,6 +151,7 @@ struct GdnGeom {
   // the main loop of tile t+1 overlaps phase 1 / tail GEMM / phase 2 of tile t, which the single-buffered flow
   // serialises (measured: 8.4k-cycle main loop + 3.9k exposed per tile, tests/gpu_ru_trace.py).
   int dbl;
+  int na;  // halo mode: A patches in the ring (power of two)
 };
 
 template <int MODE>
@@ -67,9 +161,10 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                    const GdnGeom gg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int stage_bytes = A_STAGE_BYTES + g.b_stage_bytes;
+  const int stage_bytes = g.halo ? g.b_stage_bytes : A_STAGE_BYTES + g.b_stage_bytes;
   uint8_t* gamma_s = smem + (size_t)g.num_stages * stage_bytes;  // 1024-aligned: stage sizes are multiples of 2048
-  uint64_t* full_bar = (uint64_t*)(gamma_s + gg.w2_bytes);
+  uint8_t* a_halo = gamma_s + gg.w2_bytes;                       // halo mode: gg.na patches of g.a_halo_bytes
+  uint64_t* full_bar = (uint64_t*)(a_halo + (g.halo ? (size_t)gg.na * g.a_halo_bytes : 0));
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* acc1_full = empty_bar + MAX_STAGES;  // [2] (second entries used in dbl mode)
   uint64_t* acc1_empty = acc1_full + 2;          // [2]
@@ -77,7 +172,10 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint64_t* acc2_full = p_full + 2;
   uint64_t* acc2_empty = acc2_full + 1;
   uint64_t* g_full = acc2_empty + 1;
-  uint32_t* tmem_slot = (uint32_t*)(g_full + 1);
+  uint64_t* a_full = g_full + 1;    // [4] halo mode: A-patch ring
+  uint64_t* a_empty = a_full + 4;   // [4]
+  uint32_t* tmem_slot = (uint32_t*)(a_empty + 4);
+  uint32_t* tap_off = tmem_slot + 1;  // [16] halo mode: window offset of each tap in 16-byte units
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int C = d.Cout;
@@ -98,6 +196,11 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     mbar_init(acc2_full, 1);
     mbar_init(acc2_empty, G_EPI_WARPS);
     mbar_init(g_full, 1);
+    for (int k = 0; k < 4; ++k) {
+      mbar_init(&a_full[k], 1);
+      mbar_init(&a_empty[k], gg.ksplit ? 2 : 1);  // every main-loop issuer walks every patch
+    }
+    for (int tp = 0; tp < d.KH * d.KW && tp < 16; ++tp) tap_off[tp] = (uint32_t)(((tp / d.KW) * g.halo_w + tp % d.KW) * 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -133,6 +236,61 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const int kq = kiters / ns, kr = kiters % ns;
       int s_base = 0;
       uint32_t ph_base = 0;
+      if (g.halo) {
+        // halo mode: the ring carries only weights (k-iteration n = cb * taps + tap); producer 0 also requests
+        // the A patch of a channel block when it reaches its first own k-iteration of that block
+        const int taps = d.KH * d.KW;
+        const uint32_t a_full0 = __shfl_sync(0xffffffffu, smem_u32(a_full), 0);
+        const uint32_t a_empty0 = __shfl_sync(0xffffffffu, smem_u32(a_empty), 0);
+        const uint32_t patch0 = __shfl_sync(0xffffffffu, smem_u32(a_halo), 0);
+        const uint32_t a_bytes = (uint32_t)(g.halo_w * g.halo_h * BK * 2), na_mask = (uint32_t)gg.na - 1u;
+        const uint32_t na_shift = gg.na == 4 ? 2u : 1u;
+        uint32_t pa = 0;  // patches requested so far (producer 0)
+        for (int tile = blockIdx.x; tile < total; tile += step) {
+          int t = tile;
+          const int tx = t % g.tiles_x;
+          t /= g.tiles_x;
+          const int ty = t % g.tiles_y, b = t / g.tiles_y;
+          const int x0 = tx * g.TW - d.pad_w, y0 = ty * g.TH - d.pad_h;
+          const int f = pw ^ (s_base & 1);
+          const int n_own = (kiters - f + 1) / 2;
+          int s = s_base + f;
+          uint32_t ph = ph_base;
+          if (s >= ns) { s -= ns; ph ^= 1u; }
+          int cb = 0, tap = f, cb_loaded = -1;
+          for (int n = 0; n <= n_own; ++n) {
+            const int cb_want = n < n_own ? cb : kb - 1;  // (n == n_own: make sure every patch of the tile was requested)
+            if (pw == 0) {
+              while (cb_loaded < cb_want) {
+                ++cb_loaded;
+                const uint32_t slot = pa & na_mask;
+                mbar_wait_u32(a_empty0 + 8u * slot, ((pa >> na_shift) & 1u) ^ 1u);
+                if (elect_one()) {
+                  mbar_expect_tx_u32(a_full0 + 8u * slot, a_bytes);
+                  tma_load_4d_u32(patch0 + slot * (uint32_t)g.a_halo_bytes, &tmap_a, a_full0 + 8u * slot, cb_loaded * BK, x0, y0, b);
+                }
+                __syncwarp();
+                ++pa;
+              }
+            }
+            if (n == n_own) break;
+            mbar_wait_u32(empty0 + 8u * (uint32_t)s, ph ^ 1u);
+            const uint32_t bar = full0 + 8u * (uint32_t)s;
+            if (elect_one()) {
+              mbar_expect_tx_u32(bar, (uint32_t)g.b_stage_bytes);
+              tma_load_2d_u32(smem_base + (uint32_t)(s * stage_bytes), &tmap_b, bar, tap * Cin + cb * BK, 0);
+            }
+            __syncwarp();
+            s += 2;
+            if (s >= ns) { s -= ns; ph ^= 1u; }
+            tap += 2;
+            if (tap >= taps) { tap -= taps; ++cb; }
+          }
+          ph_base ^= (uint32_t)(kq & 1);
+          s_base += kr;
+          if (s_base >= ns) { s_base -= ns; ph_base ^= 1u; }
+        }
+      } else
       for (int tile = blockIdx.x; tile < total; tile += step) {
         int t = tile;
         const int tx = t % g.tiles_x;
@@ -174,145 +332,87 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   } else if (warp == 1 || warp == G_ISSUER2_WARP) {
     // ================= MMA issuers (whole warp, elected lane issues) =================
     const uint32_t me = warp == 1 ? 0u : 1u;
-    if (gg.dbl) {
-      // ---- dbl mode: both issuers run ONLY main loops (K-split, own accumulator of pair lt & 1)
-      const uint32_t idesc = make_idesc(C);
-      const int taps = d.KH * d.KW;
-      const int kc_last = (d.Cin - (g.kb_per_tap - 1) * BK) / 16;
+    if (!me || gg.ksplit) {
+      const uint32_t idesc2 = make_idesc(gg.N2);
       const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
-      const uint32_t empty0 = __shfl_sync(0xffffffffu, smem_u32(empty_bar), 0);
-      const uint32_t full0 = __shfl_sync(0xffffffffu, smem_u32(full_bar), 0);
-      const uint64_t dconst = make_sw128_desc(0);
-      const uint32_t a_u0 = (smem_base & 0x3FFFFu) >> 4, stage_u = (uint32_t)stage_bytes >> 4;
-      int ns = g.num_stages, kb = g.kb_per_tap, kiters = taps * g.kb_per_tap, total = g.total_tiles, step = gridDim.x;
-      asm volatile("" : "+r"(ns), "+r"(kb), "+r"(kiters), "+r"(total), "+r"(step));
-      const int kq = kiters / ns, kr = kiters % ns;
-      int s_base = 0;
-      uint32_t ph_base = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < total; tile += step, ++lt) {
-        const uint32_t b = lt & 1u, use = (lt >> 1) & 1u;
-        long long* tsp = (g.dbg_ts && blockIdx.x == 0 && !me && lane == 0 && lt < 250) ? g.dbg_ts + lt * 16 : nullptr;
-        if (tsp) tsp[0] = clock64();
-        const int f = (int)me ^ (s_base & 1);  // K-split ownership by stage parity (see conv_bf16.cu)
-        int s = s_base + f;
-        uint32_t ph = ph_base;
-        if (s >= ns) { s -= ns; ph ^= 1u; }
-        int cb = f % kb;
-        const int n_own = (kiters - f + 1) / 2;
-        mbar_wait(&acc1_empty[b], use ^ 1u);  // pair b drained (phase 2 of tile lt - 2 done)
-        tcgen05_fence_after();
-        if (tsp) tsp[1] = clock64();
-        const uint32_t acc1 = tbase + b * (uint32_t)(2 * C) + me * (uint32_t)C;
-        for (int n = 0; n < n_own; ++n) {
-          mbar_wait_u32(full0 + 8u * (uint32_t)s, ph);
-          tcgen05_fence_after();
-          const uint64_t da = dconst + (uint64_t)(a_u0 + (uint32_t)s * stage_u), db = da + (A_STAGE_BYTES >> 4);
-          if (elect_one()) {
-            if (cb + 1 != kb || kc_last == 4) {
-              umma_bf16(acc1, da, db, idesc, n > 0 ? 1u : 0u);
-              umma_bf16(acc1, da + 2, db + 2, idesc, 1u);
-              umma_bf16(acc1, da + 4, db + 4, idesc, 1u);
-              umma_bf16(acc1, da + 6, db + 6, idesc, 1u);
-            } else {
-              for (int k = 0; k < kc_last; ++k) umma_bf16(acc1, da + 2 * k, db + 2 * k, idesc, (n > 0 || k > 0) ? 1u : 0u);
-            }
-            tcgen05_commit_u32(empty0 + 8u * (uint32_t)s);
-          }
-          __syncwarp();
-          s += 2;
-          if (s >= ns) { s -= ns; ph ^= 1u; }
-          cb += 2;
-          while (cb >= kb) cb -= kb;
-        }
-        ph_base ^= (uint32_t)(kq & 1);
-        s_base += kr;
-        if (s_base >= ns) { s_base -= ns; ph_base ^= 1u; }
-        if (elect_one()) tcgen05_commit(&acc1_full[b]);
-        __syncwarp();
-        if (tsp) tsp[2] = tsp[3] = tsp[4] = tsp[5] = clock64();  // (the tail GEMM is issued by the first epilogue warp)
-      }
-    } else if (!me || gg.ksplit) {
-      const uint32_t idesc = make_idesc(C), idesc2 = make_idesc(gg.N2);
-      const int taps = d.KH * d.KW;
-      const int kc_last = (d.Cin - (g.kb_per_tap - 1) * BK) / 16;
-      const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint32_t acc1 = tbase + me * (uint32_t)C, p_t = tbase + (uint32_t)gg.p_col, acc2 = tbase + (uint32_t)gg.acc2_col;
       const uint32_t gamma_addr = __shfl_sync(0xffffffffu, smem_u32(gamma_s), 0);
-      const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
-      const uint32_t empty0 = __shfl_sync(0xffffffffu, smem_u32(empty_bar), 0);
-      // (loop written for a minimal instruction count per k-iteration, see conv_bf16.cu)
-      const uint32_t full0 = __shfl_sync(0xffffffffu, smem_u32(full_bar), 0);
-      const uint64_t dconst = make_sw128_desc(0);
-      const uint32_t a_u0 = (smem_base & 0x3FFFFu) >> 4, stage_u = (uint32_t)stage_bytes >> 4;
-      int ns = g.num_stages, kb = g.kb_per_tap, kiters = taps * g.kb_per_tap, total = g.total_tiles, step = gridDim.x;
-      asm volatile("" : "+r"(ns), "+r"(kb), "+r"(kiters), "+r"(total), "+r"(step));
+      K1Cfg c;
+      c.ns = g.num_stages; c.kb = g.kb_per_tap; c.taps = d.KH * d.KW; c.kiters = c.taps * c.kb;
+      c.kq = c.kiters / c.ns; c.kr = c.kiters % c.ns;
+      c.kc_last = (d.Cin - (g.kb_per_tap - 1) * BK) / 16;
+      c.halo = g.halo;
+      c.full0 = __shfl_sync(0xffffffffu, smem_u32(full_bar), 0);
+      c.empty0 = __shfl_sync(0xffffffffu, smem_u32(empty_bar), 0);
+      c.a_u0 = (smem_base & 0x3FFFFu) >> 4;
+      c.stage_u = (uint32_t)stage_bytes >> 4;
+      c.b_off_u = A_STAGE_BYTES >> 4;
+      c.idesc = make_idesc(C);
+      c.a_full0 = __shfl_sync(0xffffffffu, smem_u32(a_full), 0);
+      c.a_empty0 = __shfl_sync(0xffffffffu, smem_u32(a_empty), 0);
+      c.patch_u0 = (__shfl_sync(0xffffffffu, smem_u32(a_halo), 0) & 0x3FFFFu) >> 4;
+      c.patch_u = (uint32_t)g.a_halo_bytes >> 4;
+      c.na_mask = (uint32_t)gg.na - 1u;
+      c.na_shift = gg.na == 4 ? 2u : 1u;
+      c.tap_off0 = __shfl_sync(0xffffffffu, smem_u32(tap_off), 0);
+      c.dconst = make_sw128_desc(0);
+      c.dconst_halo = make_sw128_desc_ex(0, (uint32_t)(g.halo_w * 128), 0);
+      K1State st = {0, 0u, 0u};
       const int ways = gg.ksplit ? 2 : 1;
-      const int kq = kiters / ns, kr = kiters % ns;
-      int s_base = 0;
-      uint32_t ph_base = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < total; tile += step, ++lt) {
-        const uint32_t par = lt & 1u;
-        // profiling aid (RDSIC_TC_DBG_TS=1, tests/gpu_ru_trace.py): 16 clock64 stamps per tile of CTA 0,
-        // slots 0-5 written by issuer 0, slots 8-12 by the first epilogue warp
-        long long* tsp = (g.dbg_ts && blockIdx.x == 0 && !me && lane == 0 && lt < 250) ? g.dbg_ts + lt * 16 : nullptr;
-        if (tsp) tsp[0] = clock64();
-        const int f = gg.ksplit ? (int)me ^ (s_base & 1) : 0;  // K-split ownership by stage parity
-        int s = s_base + f;
-        uint32_t ph = ph_base;
-        if (s >= ns) { s -= ns; ph ^= 1u; }
-        int cb = f % kb;
-        const int n_own = (kiters - f + ways - 1) / ways;
-        // ---- GEMM 1: x = conv(in)
-        mbar_wait(acc1_empty, par ^ 1u);
-        tcgen05_fence_after();
-        if (tsp) tsp[1] = clock64();
-        for (int n = 0; n < n_own; ++n) {
-          mbar_wait_u32(full0 + 8u * (uint32_t)s, ph);
+      int total = g.total_tiles, step = gridDim.x;
+      asm volatile("" : "+r"(total), "+r"(step));
+      uint32_t lt = 0;
+      if (gg.dbl) {
+        // ---- dbl mode: both issuers run ONLY main loops (K-split, own accumulator of pair lt & 1); the tail GEMM
+        //      is issued by the first epilogue warp
+        for (int tile = blockIdx.x; tile < total; tile += step, ++lt) {
+          const uint32_t b = lt & 1u, use = (lt >> 1) & 1u;
+          long long* tsp = (g.dbg_ts && blockIdx.x == 0 && !me && lane == 0 && lt < 250) ? g.dbg_ts + lt * 16 : nullptr;
+          if (tsp) tsp[0] = clock64();
+          mbar_wait(&acc1_empty[b], use ^ 1u);  // pair b drained (phase 2 of tile lt - 2 done)
           tcgen05_fence_after();
-          const uint64_t da = dconst + (uint64_t)(a_u0 + (uint32_t)s * stage_u), db = da + (A_STAGE_BYTES >> 4);
+          if (tsp) tsp[1] = clock64();
+          gemm1_tile(st, c, tbase + b * (uint32_t)(2 * C) + me * (uint32_t)C, me, 2);
+          if (elect_one()) tcgen05_commit(&acc1_full[b]);
+          __syncwarp();
+          if (tsp) tsp[2] = tsp[3] = tsp[4] = tsp[5] = clock64();
+        }
+      } else {
+        const uint32_t acc1 = tbase + me * (uint32_t)C, p_t = tbase + (uint32_t)gg.p_col, acc2 = tbase + (uint32_t)gg.acc2_col;
+        for (int tile = blockIdx.x; tile < total; tile += step, ++lt) {
+          const uint32_t par = lt & 1u;
+          // profiling aid (RDSIC_TC_DBG_TS=1, tests/gpu_ru_trace.py): 16 clock64 stamps per tile of CTA 0,
+          // slots 0-5 written by issuer 0, slots 8-12 by the first epilogue warp
+          long long* tsp = (g.dbg_ts && blockIdx.x == 0 && !me && lane == 0 && lt < 250) ? g.dbg_ts + lt * 16 : nullptr;
+          if (tsp) tsp[0] = clock64();
+          // ---- GEMM 1: x = conv(in)
+          mbar_wait(&acc1_empty[0], par ^ 1u);
+          tcgen05_fence_after();
+          if (tsp) tsp[1] = clock64();
+          gemm1_tile(st, c, acc1, me, ways);
+          if (elect_one()) tcgen05_commit(&acc1_full[0]);
+          __syncwarp();
+          if (me) continue;
+          if (tsp) tsp[2] = clock64();
+          // ---- GEMM 2: norm = gamma' @ x^2, A operand from TMEM
+          if (lt == 0) mbar_wait(g_full, 0);
+          mbar_wait(&p_full[0], par);
+          if (tsp) tsp[3] = clock64();
+          mbar_wait(acc2_empty, par ^ 1u);
+          tcgen05_fence_after();
+          if (tsp) tsp[4] = clock64();
           if (elect_one()) {
-            if (cb + 1 != kb || kc_last == 4) {
-              umma_bf16(acc1, da, db, idesc, n > 0 ? 1u : 0u);
-              umma_bf16(acc1, da + 2, db + 2, idesc, 1u);
-              umma_bf16(acc1, da + 4, db + 4, idesc, 1u);
-              umma_bf16(acc1, da + 6, db + 6, idesc, 1u);
-            } else {
-              for (int k = 0; k < kc_last; ++k) umma_bf16(acc1, da + 2 * k, db + 2 * k, idesc, (n > 0 || k > 0) ? 1u : 0u);
+            for (int kb2 = 0; kb2 < gg.k2_blocks; ++kb2) {
+              const uint64_t dg = make_sw128_desc(gamma_addr + (uint32_t)(kb2 * gg.N2 * 128));
+              const int kc2 = kb2 + 1 == gg.k2_blocks ? gg.kc2_last : BK / 16;
+              for (int k = 0; k < kc2; ++k)  // 16 bf16 of K = 8 TMEM columns of the staged operand
+                umma_bf16_ts(acc2, p_t + (uint32_t)((kb2 * 4 + k) * 8), dg + 2 * k, idesc2, (kb2 | k) ? 1u : 0u);
             }
-            tcgen05_commit_u32(empty0 + 8u * (uint32_t)s);
+            tcgen05_commit(acc2_full);
           }
           __syncwarp();
-          s += ways;
-          if (s >= ns) { s -= ns; ph ^= 1u; }
-          cb += ways;
-          while (cb >= kb) cb -= kb;
+          if (tsp) tsp[5] = clock64();
         }
-        ph_base ^= (uint32_t)(kq & 1);
-        s_base += kr;
-        if (s_base >= ns) { s_base -= ns; ph_base ^= 1u; }
-        if (elect_one()) tcgen05_commit(acc1_full);
-        __syncwarp();
-        if (me) continue;
-        if (tsp) tsp[2] = clock64();
-        // ---- GEMM 2: norm = gamma' @ x^2, A operand from TMEM
-        if (lt == 0) mbar_wait(g_full, 0);
-        mbar_wait(p_full, par);
-        if (tsp) tsp[3] = clock64();
-        mbar_wait(acc2_empty, par ^ 1u);
-        tcgen05_fence_after();
-        if (tsp) tsp[4] = clock64();
-        if (elect_one()) {
-          for (int kb = 0; kb < gg.k2_blocks; ++kb) {
-            const uint64_t dg = make_sw128_desc(gamma_addr + (uint32_t)(kb * gg.N2 * 128));
-            const int kc2 = kb + 1 == gg.k2_blocks ? gg.kc2_last : BK / 16;
-            for (int k = 0; k < kc2; ++k)  // 16 bf16 of K = 8 TMEM columns of the staged operand
-              umma_bf16_ts(acc2, p_t + (uint32_t)((kb * 4 + k) * 8), dg + 2 * k, idesc2, (kb | k) ? 1u : 0u);
-          }
-          tcgen05_commit(acc2_full);
-        }
-        __syncwarp();
-        if (tsp) tsp[5] = clock64();
       }
     }
     __syncwarp();
@@ -532,6 +632,20 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
       if (best < 0 || area < best) { best = area; g.TW = tw; g.TH = th; }
     }
   }
+  // halo mode (see gemm1_tile): stride-1 multi-tap layers on maps that a 16 x 8 patch tiles exactly.  OFF by default:
+  // correct (tests/test_gpu_ops.py::test_halo_modes_in_subprocess) but measured SLOWER (ResidualUnit main loop
+  // 670 vs 520 cycles per k-iteration): it removes L2 traffic, but the bound that remains is the shared-memory
+  // port -- the MMAs read A and B from shared memory every k-step whatever wrote them, and windows that do not
+  // start on a 1024-byte swizzle atom appear to cost extra wavefronts.  See DESIGN.md section 4.
+  static const int tune_halo = getenv("RDSIC_GDN_HALO") ? atoi(getenv("RDSIC_GDN_HALO")) : 0;
+  if (tune_halo && !flat && d->stride == 1 && d->KH * d->KW >= 2 && d->KH <= 3 && d->KW <= 3 && OH % 16 == 0 && OW % 8 == 0) {
+    g.halo = 1;
+    g.TH = 16;
+    g.TW = 8;
+    g.halo_w = g.TW + d->KW - 1;
+    g.halo_h = g.TH + d->KH - 1;
+    g.a_halo_bytes = (BK * 2 * g.halo_w * g.halo_h + 1023) / 1024 * 1024;
+  }
   g.tiles_x = ceil_div(OW, g.TW);
   g.tiles_y = ceil_div(OH, g.TH);
   g.BN = C;
@@ -568,11 +682,20 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   gg.p_col = gg.dbl ? 4 * C : C * (1 + gg.ksplit);
   gg.acc2_col = gg.dbl ? 0 : (gg.p_col + C / 2 + 31) / 32 * 32;
   RDSIC_CHECK_ARG(gg.acc2_col + N2 <= 512);
-  const int stage_bytes = A_STAGE_BYTES + g.b_stage_bytes;
+  gg.na = 0;
+  int stage_bytes = A_STAGE_BYTES + g.b_stage_bytes;
   int stages = (200 * 1024 - gg.w2_bytes) / stage_bytes;
+  if (g.halo) {
+    stage_bytes = g.b_stage_bytes;
+    gg.na = C <= 96 ? 4 : 2;
+    stages = (220 * 1024 - gg.w2_bytes - gg.na * g.a_halo_bytes) / stage_bytes;
+  }
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   stages &= ~1;  // even ring depth: stage parity = owner (two producers / two issuers)
-  if (stages < 2) return RDSIC_E_ARG;
+  if (stages < 2) {
+    if (!g.halo) return RDSIC_E_ARG;
+    return RDSIC_E_UNSUPPORTED;  // (not reachable for the shapes the models use)
+  }
   g.num_stages = stages;
   RDSIC_CHECK_ARG(g.TW * d->stride <= 256 && g.TH * d->stride <= 256);
 
@@ -582,6 +705,7 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {ld_b, ld_b * W, ld_b * W * H};
     cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(g.TW * d->stride), (cuuint32_t)(g.TH * d->stride), 1};
+    if (g.halo) { box[1] = (cuuint32_t)g.halo_w; box[2] = (cuuint32_t)g.halo_h; }
     cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
     void* base = (void*)((const __nv_bfloat16*)d->in.ptr + d->in.coff);
     if (encode(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -608,7 +732,8 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
       log_set = true;
     }
   }
-  const size_t smem = (size_t)stages * stage_bytes + gg.w2_bytes + 1024 + (2 * MAX_STAGES + 12) * 8 + 16;
+  const size_t smem = (size_t)stages * stage_bytes + gg.w2_bytes + (size_t)gg.na * g.a_halo_bytes + 1024 +
+                      (2 * MAX_STAGES + 20) * 8 + 16 + 64;
   auto kern = d->tail_mode == TAIL_RU ? conv_gdn_tc_kernel<TAIL_RU>
               : d->tail_mode == TAIL_IGDN ? conv_gdn_tc_kernel<TAIL_IGDN> : conv_gdn_tc_kernel<TAIL_GDN>;
   static bool attr_set[16][4] = {};

@@ -243,3 +243,17 @@ def test_patchify_matches_unfold(C, k, s, p, B, H, W):
     want = cols.view(B, C, k * k, OH, OW).permute(0, 3, 4, 2, 1).reshape(B, OH, OW, k * k * C)
     assert torch.equal(got[..., :k * k * C], want.bfloat16().float())
     assert (got[..., k * k * C:] == 0).all()
+
+
+@pytest.mark.gpu
+def test_halo_modes_in_subprocess():
+    """The experimental halo modes (one TMA patch per channel block, shifted UMMA windows; off by default because
+    they measured slower) stay correct: the deconv / fused-layer / conv parity tests pass with them switched on.
+    The switches are read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    env = dict(os.environ, RDSIC_GDN_HALO="1", RDSIC_TC_HALO="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_ops.py", "-m", "gpu", "-q", "-x", "-k",
+                        "tcgen05 or layers_bf16 or subpel"], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RDSIC_ABI_VERSION 2
+#define RDSIC_ABI_VERSION 3
 
 typedef void* rdsic_stream_t; /* cudaStream_t */
 
@@ -163,6 +163,11 @@ typedef struct rdsic_gc_desc {
    * the ste_round value (cnn.py:177); noisy_out (optional) receives y + noise. */
   rdsic_view noise;     /* optional [B,h,w,Cs] fp32 */
   rdsic_view noisy_out; /* optional [B,h,w,Cs] fp32 */
+  /* Decoder side (GaussianConditional.dequantize after the rANS decode, cnn.py:326-328, entropy_models.py:160-167):
+   * with sym_in != NULL the quantised residual is READ from this int32 tensor (same NCHW [B,Ctot,h,w] layout and
+   * channel offset as `symbols`) instead of being computed from y, i.e. y_hat = float(sym_in) + mu; y is ignored
+   * (may be NULL).  lik then is the likelihood of the decoded symbol. */
+  const int32_t* sym_in;
 } rdsic_gc_desc;
 
 /* Layout / elementwise helpers used by the standalone module API. */
@@ -170,7 +175,7 @@ typedef struct rdsic_copy_desc {
   rdsic_view src;
   rdsic_view dst;
   int32_t B, H, W, C;
-  int32_t op; /* 0 copy/cast, 1 gelu, 2 square */
+  int32_t op; /* 0 copy/cast, 1 gelu, 2 square, 3 clamp to [0,1] (decompress: x_hat.clamp_(0, 1), cnn.py:340) */
 } rdsic_copy_desc;
 
 /* LayerNorm over channels (stf Swin block, TCM/tcm.py:214-236). */

@@ -62,7 +62,7 @@ class GCDesc(C.Structure):
         ("n_table", C.c_int32),
         ("B", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("Cs", C.c_int32), ("Ctot", C.c_int32),
         ("lik_coff", C.c_int32), ("scale_bound", C.c_float), ("lik_bound", C.c_float),
-        ("pad_", C.c_int32), ("noise", View), ("noisy_out", View),
+        ("pad_", C.c_int32), ("noise", View), ("noisy_out", View), ("sym_in", C.c_void_p),
     ]
 
 
@@ -145,7 +145,7 @@ def lib():
     L.rdsic_graph_num_kernels.argtypes = [C.c_void_p]
     L.rdsic_graph_destroy.argtypes = [C.c_void_p]
     L.rdsic_graph_destroy.restype = None
-    if L.rdsic_abi_version() != 2:
+    if L.rdsic_abi_version() != 3:
         raise RuntimeError("resdsic_b200: ABI version mismatch between the python host and the CUDA library")
     for what, T in enumerate((Op, ConvDesc, AttnDesc, EBDesc, GCDesc, CopyDesc, View, LNDesc, PatchDesc)):
         if L.rdsic_sizeof(what) != C.sizeof(T):

@@ -105,10 +105,16 @@ __global__ void __launch_bounds__(256) gc_forward_kernel(const rdsic_gc_desc d) 
   for (int pp = ty; pp < GC_TP; pp += 8) {
     const size_t pix = p0 + pp;
     if (pix >= npix || c >= d.Cs) continue;
-    const float y = ((const float*)d.y.ptr)[pix * d.y.ld + d.y.coff + c];
     const float mu = ((const float*)d.mu.ptr)[pix * d.mu.ld + d.mu.coff + c];
     const float sc = ((const float*)d.scale.ptr)[pix * d.scale.ld + d.scale.coff + c];
-    const float r = rintf(__fsub_rn(y, mu));
+    float y = 0.f, r;
+    if (d.sym_in) {  // decoder side: the symbol comes from the entropy decoder
+      const size_t bb = pix / hw, yx = pix % hw;
+      r = (float)d.sym_in[(bb * d.Ctot + d.lik_coff + c) * (size_t)hw + yx];
+    } else {
+      y = ((const float*)d.y.ptr)[pix * d.y.ld + d.y.coff + c];
+      r = rintf(__fsub_rn(y, mu));
+    }
     const float yh = __fadd_rn(r, mu);
     float yl = yh;  // where the likelihood is evaluated: y_hat (eval) or y + noise (training)
     if (d.noise.ptr) {
@@ -371,11 +377,12 @@ extern "C" int rdsic_eb_forward(const rdsic_eb_desc* d, rdsic_stream_t stream) {
 }
 
 extern "C" int rdsic_gc_forward(const rdsic_gc_desc* d, rdsic_stream_t stream) {
-  RDSIC_CHECK_ARG(d && d->y.ptr && d->mu.ptr && d->scale.ptr && d->lik && d->table);
+  RDSIC_CHECK_ARG(d && (d->y.ptr || d->sym_in) && d->mu.ptr && d->scale.ptr && d->lik && d->table);
+  RDSIC_CHECK_ARG(!(d->sym_in && d->noise.ptr));
   RDSIC_CHECK_ARG(d->B > 0 && d->h > 0 && d->w > 0 && d->Cs > 0 && d->Ctot >= d->lik_coff + d->Cs);
   RDSIC_CHECK_ARG(d->n_table >= 2 && d->n_table <= 129);
-  RDSIC_CHECK_ARG(d->y.dtype == RDSIC_F32 && d->mu.dtype == RDSIC_F32 && d->scale.dtype == RDSIC_F32);
-  RDSIC_CHECK_ARG(!d->y.nchw && !d->mu.nchw && !d->scale.nchw);
+  RDSIC_CHECK_ARG((d->sym_in || d->y.dtype == RDSIC_F32) && d->mu.dtype == RDSIC_F32 && d->scale.dtype == RDSIC_F32);
+  RDSIC_CHECK_ARG((d->sym_in || !d->y.nchw) && !d->mu.nchw && !d->scale.nchw);
   RDSIC_CHECK_ARG(!d->noise.ptr || (d->noise.dtype == RDSIC_F32 && !d->noise.nchw));
   RDSIC_CHECK_ARG(!d->noisy_out.ptr || (d->noise.ptr && d->noisy_out.dtype == RDSIC_F32 && !d->noisy_out.nchw));
   const size_t npix = (size_t)d->B * d->h * d->w;

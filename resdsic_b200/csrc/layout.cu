@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(256) copy_views_kernel(const rdsic_copy_desc d
       v = ld_elem(d.src.ptr, d.src.dtype, idx);
       if (d.op == 1) v = gelu_erf(v);
       if (d.op == 2) v = v * v;
+      if (d.op == 3) v = fminf(fmaxf(v, 0.f), 1.f);
     }
     if (src_n) tile[k][tx] = v; else tile[tx][k] = v;
   }
@@ -270,7 +271,7 @@ extern "C" int rdsic_patch_forward(const rdsic_patch_desc* d, rdsic_stream_t str
 
 extern "C" int rdsic_copy_forward(const rdsic_copy_desc* d, rdsic_stream_t stream) {
   RDSIC_CHECK_ARG(d && d->src.ptr && d->dst.ptr && d->B > 0 && d->H > 0 && d->W > 0 && d->C > 0);
-  RDSIC_CHECK_ARG(d->op >= 0 && d->op <= 2);
+  RDSIC_CHECK_ARG(d->op >= 0 && d->op <= 3);
   RDSIC_CHECK_ARG(d->B <= 65535);
   dim3 grid(ceil_div(d->H * d->W, 32), ceil_div(d->C, 32), d->B);
   copy_views_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d);

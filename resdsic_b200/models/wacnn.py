@@ -141,7 +141,32 @@ class WACNN(CompressionModel):
                                   "the int32 symbols/indexes `compress` hands to the coder (cnn.py:253-258)")
 
     def decompress(self, strings, shape):
-        raise NotImplementedError("rANS bitstream decoding stays in the reference's C++")
+        raise NotImplementedError("rANS bitstream decoding stays in the reference's C++; use slice_decoder(z_hat) for "
+                                  "everything `decompress` computes around the decoder calls (cnn.py:296-342)")
+
+    @torch.no_grad()
+    def slice_decoder(self, z_hat):
+        """Decoder-side slice loop (reference cnn.py:296-342) with the two entropy-coder calls left to the caller:
+
+            dec = net.slice_decoder(net.entropy_bottleneck.decompress(strings[1], shape))   # z_hat [B,192,h/4,w/4]
+            for i in range(net.num_slices):
+                idx = dec.indexes(i)                                   # int32 [B,32,h,w] on the device (cnn.py:322)
+                rv = decoder.decode_stream(idx.reshape(-1).tolist(), cdf, cdf_lengths, offsets)
+                dec.push_symbols(i, torch.tensor(rv, dtype=torch.int32).reshape(idx.shape))      # cnn.py:325-333
+            x_hat = dec.finish()                                       # g_s + clamp_(0, 1), cnn.py:337-340
+        """
+        if z_hat.dim() != 4 or z_hat.shape[1] != self.N:
+            raise ValueError(f"expected z_hat [B,{self.N},h,w], got {tuple(z_hat.shape)}")
+        if not z_hat.is_cuda:
+            raise RuntimeError("resdsic_b200 runs on CUDA devices only (no CPU fallback)")
+        B, _, hz, wz = z_hat.shape
+        key = ("dec", B, hz, wz, str(z_hat.device), self.precision, self._weights_key())
+        plan = self._plans.get(key)
+        if plan is None:
+            self._plans.clear()
+            plan = self._build_decoder(B, hz, wz, z_hat.device)
+            self._plans[key] = plan
+        return SliceDecoder(self, plan, z_hat)
 
     # ------------------------------------------------------------- planning
     def _weights_key(self):
@@ -330,6 +355,100 @@ class WACNN(CompressionModel):
         p.y, p.z, p.y_hat, p.means, p.scales = y, z, y_hat, means, scales
         return p
 
+    def _build_decoder(self, B, hz, wz, device, build_only=False):
+        """Programs of the decoder-side loop: `hyper` (h_mean_s || h_scale_s + everything that only needs the
+        latent means / scales), per slice `params[i]` (cc_mean || cc_scale, CDF indexes) and `update[i]`
+        (dequantise the decoded symbols, LRP, write the support slots), and `synth` (g_s, clamp).  Same
+        descriptors, buffers plan and kernels as `_build`, so for the same batch shape every value equals the
+        encoder pass's bit for bit -- which the entropy decoder relies on (identical CDF indexes)."""
+        from ..program import Program
+        ctx = Ctx(device, self.precision, build_only=build_only)
+        f32, i32 = torch.float32, torch.int32
+        p = _Plan()
+        h, w = hz * 4, wz * 4
+        M, sc_, S = self.M, self.slice_channels, self.max_support_slices
+        bf16 = ctx.precision == "bf16"
+        p.z_hat_in = torch.empty(B, self.N, hz, wz, dtype=f32, device=device)
+        p.symbols = torch.zeros(B, M, h, w, dtype=i32, device=device)
+        p.indexes = torch.empty(B, M, h, w, dtype=i32, device=device)
+        p.lik = torch.empty(B, M, h, w, dtype=f32, device=device)  # likelihood of the decoded symbols (by-product)
+        ctx_ld = M + sc_ * (S + 1)
+        means, scales = ctx.buf(B, h, w, ctx_ld), ctx.buf(B, h, w, ctx_ld)
+        y_hat = ctx.buf(B, h, w, M, f32)
+        lat_m, lat_s = means.channels(0, M), scales.channels(0, M)
+        fam = {"cc_mean": self.cc_mean_transforms, "cc_scale": self.cc_scale_transforms, "lrp": self.lrp_transforms}
+
+        # ---- hyper: z_hat -> latent means / scales, then the latent-only pre-computations (cf. _build)
+        prog = ctx.prog
+        z_hat = prog.copy(TV.nchw_of(p.z_hat_in), ctx.buf(B, hz, wz, self.N))
+        prog.fork()
+        with prog.side():
+            self.h_scale_s.emit(ctx, z_hat, last_kw=dict(out=lat_s))
+        self.h_mean_s.emit(ctx, z_hat, last_kw=dict(out=lat_m))
+        prog.join()
+        pre = {}
+        jobs = [("mu0", None), ("sc0", None)]
+        for i in range(self.num_slices):
+            if i:
+                jobs += [(("cc_mean", i), lat_m), (("cc_scale", i), lat_s)]
+            jobs.append((("lrp", i), lat_m))
+        forked = set()
+        for n, (key, src) in enumerate(jobs):
+            lane = 2 + n % (_lib.MAX_LANES - 2)
+            if lane not in forked:
+                prog.fork(lane)
+                forked.add(lane)
+            with prog.side(lane):
+                if key == "mu0":
+                    pre[key] = self._stack(ctx, self.cc_mean_transforms[0], lat_m)
+                elif key == "sc0":
+                    pre[key] = self._stack(ctx, self.cc_scale_transforms[0], lat_s)
+                else:
+                    pre[key] = fam[key[0]][key[1]][0].emit_partial(ctx, src, 0, M)
+        for lane in sorted(forked):
+            prog.join(lane)
+        p.hyper = prog
+
+        def stack_split(name, i, buf, n_extra, final=None):
+            seq = fam[name][i]
+            t = seq[0].emit_partial(ctx, buf.channels(M, n_extra), 1, M, res=pre[(name, i)], gelu=True)
+            return self._stack(ctx, seq, t, final=final, skip_first=True)
+
+        p.params, p.update = [], []
+        for i in range(self.num_slices):
+            k = min(i, S)
+            ctx.prog = prog = Program(device)
+            if i == 0:
+                mu, sc = pre["mu0"], pre["sc0"]
+            else:
+                prog.fork(1)
+                with prog.side(1):
+                    sc = stack_split("cc_scale", i, scales, sc_ * k)
+                mu = stack_split("cc_mean", i, means, sc_ * k)
+                prog.join(1)
+            # CDF indexes of the slice (build_indexes, cnn.py:322); y is not known yet: mu stands in for it
+            self.gaussian_conditional.emit(ctx, mu, sc, mu, p.lik, sc_ * i, M, y_hat_dsts=[], indexes=p.indexes)
+            p.params.append(prog)
+            ctx.prog = prog = Program(device)
+            yh_i = y_hat.channels(sc_ * i, sc_)
+            slot = means.channels(M + sc_ * k, sc_)  # slices >= S: slot S is scratch for the current slice
+            extra = dict(out2=slot, out3=scales.channels(M + sc_ * i, sc_)) if i < S else {}
+            self.gaussian_conditional.emit(ctx, mu, sc, mu, p.lik, sc_ * i, M, y_hat_dsts=[yh_i, slot], sym_in=p.symbols)
+            stack_split("lrp", i, means, sc_ * (k + 1), final=dict(epilogue=_lib.EPI_LRP, res=yh_i, out=yh_i, **extra))
+            p.update.append(prog)
+
+        # ---- synthesis + clamp (cnn.py:337-340)
+        ctx.prog = prog = Program(device)
+        x_raw = torch.empty(B, 3, h * 16, w * 16, dtype=f32, device=device)
+        p.x_hat = torch.empty(B, 3, h * 16, w * 16, dtype=f32, device=device)
+        y_hat_act = prog.copy(y_hat, ctx.buf(B, h, w, M)) if bf16 else y_hat
+        self.g_s.emit(ctx, y_hat_act, last_kw=dict(out=TV.nchw_of(x_raw)))
+        prog.copy(TV.nchw_of(x_raw), TV.nchw_of(p.x_hat), op_code=3)
+        p.synth = prog
+        p.y_hat, p.means, p.scales = y_hat, means, scales
+        p.shape = (B, h, w)
+        return p
+
     @staticmethod
     def _stack(ctx, seq, x, final=None, skip_first=False):
         """conv -> GELU -> ... -> conv (cnn.py:91-129); the GELU modules are fused into the convs."""
@@ -386,3 +505,45 @@ class WACNN(CompressionModel):
         p = self._execute(x, True)
         return {"y_symbols": p.symbols, "y_indexes": p.indexes, "z_symbols": p.z_symbols,
                 "x_hat": p.x_hat, "likelihoods": {"y": p.lik_y, "z": p.lik_z}, "shape": (p.z.H, p.z.W)}
+
+
+class SliceDecoder:
+    """One decode session over a decoder plan (see WACNN.slice_decoder).  Calls must follow the reference's
+    order: indexes(0), push_symbols(0), indexes(1), ... , finish()."""
+
+    def __init__(self, model, plan, z_hat):
+        self.model, self.plan, self._next, self._have_idx = model, plan, 0, False
+        plan.z_hat_in.copy_(z_hat)
+        self._run(plan.hyper)
+
+    def _run(self, prog):
+        prog.run_graph() if self.model.use_cuda_graph else prog.run()
+
+    def indexes(self, i):
+        if i != self._next or self._have_idx:
+            raise RuntimeError(f"slice {i}: the decoder loop is sequential (expected indexes({self._next}) / push_symbols)")
+        self._run(self.plan.params[i])
+        self._have_idx = True
+        c = self.model.slice_channels
+        return self.plan.indexes[:, c * i:c * i + c]
+
+    def push_symbols(self, i, symbols):
+        if i != self._next or not self._have_idx:
+            raise RuntimeError(f"slice {i}: call indexes({self._next}) first")
+        c = self.model.slice_channels
+        dst = self.plan.symbols[:, c * i:c * i + c]
+        if tuple(symbols.shape) != tuple(dst.shape):
+            raise ValueError(f"expected symbols of shape {tuple(dst.shape)}, got {tuple(symbols.shape)}")
+        dst.copy_(symbols.to(dst.device, torch.int32))
+        self._run(self.plan.update[i])
+        self._next, self._have_idx = i + 1, False
+
+    def finish(self):
+        if self._next != self.model.num_slices:
+            raise RuntimeError(f"only {self._next} of {self.model.num_slices} slices decoded")
+        self._run(self.plan.synth)
+        return self.plan.x_hat
+
+    @property
+    def y_hat(self):
+        return self.plan.y_hat.to_nchw()

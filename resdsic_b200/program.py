@@ -195,9 +195,11 @@ class Program:
         self.keep += [z.t, z_hat.t, lik, params, symbols]
 
     def gc(self, y: TV, mu: TV, scale: TV, y_hat_dsts, lik, lik_coff, Ctot, table, symbols=None, indexes=None,
-           scale_bound=0.11, lik_bound=1e-9, noise: TV = None, noisy_out: TV = None):
+           scale_bound=0.11, lik_bound=1e-9, noise: TV = None, noisy_out: TV = None, sym_in=None):
         d = GCDesc()
         d.y, d.mu, d.scale = y.view(), mu.view(), scale.view()
+        d.sym_in = _ptr(sym_in)
+        self.keep.append(sym_in)
         d.noise = noise.view() if noise is not None else _NULL
         d.noisy_out = noisy_out.view() if noisy_out is not None else _NULL
         self.keep += [tv.t for tv in (noise, noisy_out) if tv is not None]

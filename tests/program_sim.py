@@ -160,6 +160,9 @@ class Sim:
         mu = self._nhwc(d.mu, d.B, d.h, d.w, d.Cs).float()
         sc = self._nhwc(d.scale, d.B, d.h, d.w, d.Cs).float()
         r = torch.round(y - mu)
+        if d.sym_in:  # decoder side: symbols come from the entropy decoder
+            n_ = d.B * d.Ctot * d.h * d.w
+            r = self._flat(d.sym_in)[:n_].view(d.B, d.Ctot, d.h, d.w)[:, d.lik_coff:d.lik_coff + d.Cs].permute(0, 2, 3, 1).float()
         yh = r + mu
         yl = yh
         if d.noise.ptr:  # training mode: likelihood at y + noise
@@ -190,6 +193,8 @@ class Sim:
             src = F.gelu(src)
         if d.op == 2:
             src = src * src
+        if d.op == 3:
+            src = src.clamp(0, 1)
         dst = self._nhwc(d.dst, d.B, d.H, d.W, d.C)
         dst.copy_(src.to(dst.dtype))
 

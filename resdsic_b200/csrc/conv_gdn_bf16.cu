@@ -176,6 +176,10 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint64_t* a_empty = a_full + 4;   // [4]
   uint32_t* tmem_slot = (uint32_t*)(a_empty + 4);
   uint32_t* tap_off = tmem_slot + 1;  // [16] halo mode: window offset of each tap in 16-byte units
+  // both bias vectors staged once per CTA (16-byte aligned): the epilogue's per-chunk bias loads were its hottest
+  // stall (ncu: the first FADD after each bias LDG, stall_long_sb)
+  float* bias1_s = (float*)(((uintptr_t)(tap_off + 16) + 15) & ~(uintptr_t)15);  // [C]  conv bias (zeros if none)
+  float* bias2_s = bias1_s + MAXC;                                               // [N2] tail bias
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int C = d.Cout;
@@ -207,6 +211,8 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) bias1_s[i] = d.bias ? d.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < gg.N2; i += blockDim.x) bias2_s[i] = d.tail_bias[i];
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -457,11 +463,11 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += w[i];
         }
-        if (d.bias) {
-          const float4* bp = reinterpret_cast<const float4*>(d.bias + j * 16);
+        {
+          const float4* bp = reinterpret_cast<const float4*>(bias1_s + j * 16);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 f = __ldg(bp + i);
+            const float4 f = bp[i];
             v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
           }
         }
@@ -545,10 +551,10 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(u[i]);
         if (!row_ok) continue;
-        const float4* bp = reinterpret_cast<const float4*>(d.tail_bias + j * 16);
+        const float4* bp = reinterpret_cast<const float4*>(bias2_s + j * 16);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 f = __ldg(bp + i);
+          const float4 f = bp[i];
           v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
         }
 #pragma unroll
@@ -733,7 +739,7 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
     }
   }
   const size_t smem = (size_t)stages * stage_bytes + gg.w2_bytes + (size_t)gg.na * g.a_halo_bytes + 1024 +
-                      (2 * MAX_STAGES + 20) * 8 + 16 + 64;
+                      (2 * MAX_STAGES + 20) * 8 + 16 + 64 + 16 + 2 * MAXC * 4;
   auto kern = d->tail_mode == TAIL_RU ? conv_gdn_tc_kernel<TAIL_RU>
               : d->tail_mode == TAIL_IGDN ? conv_gdn_tc_kernel<TAIL_IGDN> : conv_gdn_tc_kernel<TAIL_GDN>;
   static bool attr_set[16][4] = {};

@@ -238,12 +238,13 @@ __device__ __forceinline__ float gelu_fast(float x) {
   const float h = 0.5f * x;
   return fmaf(h, copysignf(erf_abs, x), h);
 #else
-  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);  // beyond |x| = 8 the fitted quintic would turn over; tanh is +-1 there
-  const float x2 = xc * xc;
+  // beyond |x| = 8 the fitted quintic would turn over: freeze x^2 at 64 there, so that t stays 1.70 and tanh(x t)
+  // saturates to +-1 (bit-identical to clamping x itself for |x| <= 8, the same +-1 beyond; one FMNMX instead of two)
+  const float x2 = fminf(x * x, 64.0f);
   float t = fmaf(-3.58618502e-4f, x2, 3.70495807e-2f);
   t = fmaf(t, x2, 7.97459395e-1f);
   const float h = 0.5f * x;
-  return fmaf(h, tanh_mufu(xc * t), h);
+  return fmaf(h, tanh_mufu(x * t), h);
 #endif
 }
 #if defined(RDSIC_GELU_EXACT) || defined(RDSIC_GELU_AS)

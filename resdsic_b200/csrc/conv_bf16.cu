@@ -58,6 +58,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* a_full = acc_empty + 2;              // [2] halo mode: A patch ring
   uint64_t* a_empty = a_full + 2;
   uint32_t* tmem_slot = (uint32_t*)(a_empty + 2);
+  // the layer's bias staged once per CTA (zeros when the layer has none); 16-byte aligned for float4 reads
+  float* bias_s = (float*)(((uintptr_t)(tmem_slot + 1) + 15) & ~(uintptr_t)15);
   // halo mode smem: [num_stages x B tile][2 x A halo patch]; otherwise [num_stages x (A tile | B tile)]
   uint8_t* a_halo = smem + (size_t)g.num_stages * g.b_stage_bytes;
 
@@ -82,6 +84,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(g.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
+  for (int i = threadIdx.x; i < (d.Cout + 15) / 16 * 16; i += blockDim.x) bias_s[i] = (d.bias && i < d.Cout) ? d.bias[i] : 0.f;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -493,10 +496,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 else load16(d.aux, pix * (size_t)d.aux.ld + d.aux.coff + nb, aux);
               }
               if (d.bias) {
-                const float4* bp = reinterpret_cast<const float4*>(d.bias + nb);
+                const float4* bp = reinterpret_cast<const float4*>(bias_s + nb);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  const float4 f = __ldg(bp + i);
+                  const float4 f = bp[i];
                   v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
                 }
               }
@@ -535,7 +538,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int i = 0; i < 16; ++i) {  // deliberately not unrolled: rare path, keep the code small
             const int n = nb + i;
             if (n >= d.Cout) break;
-            float val = v[i] + (d.bias ? __ldg(d.bias + n) : 0.f);
+            float val = v[i] + bias_s[n];
             int c = n;
             size_t px = pix;
             if (d.pixel_shuffle) {
@@ -781,7 +784,7 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   }
 
   const size_t smem = (size_t)stages * stage_bytes + (g.halo ? 2 * g.a_halo_bytes : 0) + 1024 /*align slack*/ +
-                      (2 * MAX_STAGES + 8) * 8 + 16;
+                      (2 * MAX_STAGES + 8) * 8 + 16 + 16 + (size_t)((d->Cout + 15) / 16 * 16) * 4 /*staged bias*/;
   // vector epilogue: channels-last views whose 16-channel chunks are 32-byte aligned (256-bit LDG/STG)
   auto vec_ok = [](const rdsic_view& v) {
     return !v.ptr || (!v.nchw && v.ld % 16 == 0 && v.coff % 16 == 0 && ((uintptr_t)v.ptr % 32) == 0);

@@ -694,7 +694,8 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   //     the same order, K-split does not).
   static const int tune_m2 = getenv("RDSIC_TC_M2") ? atoi(getenv("RDSIC_TC_M2")) : 3;
   static const int tune_ksplit = getenv("RDSIC_TC_KSPLIT") ? atoi(getenv("RDSIC_TC_KSPLIT")) : 1;
-  const bool family = !g.halo && g.num_k_iters >= 4 &&
+  static const int tune_mink = getenv("RDSIC_TC_M2_MINK") ? atoi(getenv("RDSIC_TC_M2_MINK")) : 4;
+  const bool family = !g.halo && g.num_k_iters >= tune_mink &&
                       (4 * g.BN <= 512 || (tune_ksplit != 3 && 2 * g.BN <= 512 && g.num_k_iters >= 16));
   if (tune_m2 && family) {
     // cost of the busiest SM ~ rounds x bytes one tile streams per k-iteration (A rows + the B stage)

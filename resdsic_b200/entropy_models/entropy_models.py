@@ -6,8 +6,9 @@ parameter/buffer names and forward semantics in eval mode (round) and in
 training mode (additive U(-1/2,1/2) noise, forward VALUES only -- there is no
 autograd through the CUDA kernels).  In scope: forward (quantise + likelihood),
 quantize, dequantize, build_indexes, EntropyBottleneck.loss and the CDF-table build
-`update()`.  Out of scope per BASELINE.json (stays in the
-reference's C++): the rANS compress()/decompress().
+`update()`, and the compress()/decompress() glue around the rANS coder.  Out of
+scope per BASELINE.json (stays in the reference's C++): the rANS coder itself, `compressai.ans`,
+imported lazily like the reference does.
 """
 import ctypes
 
@@ -22,11 +23,45 @@ from ..ops import LowerBound
 from ..program import TV
 
 
+class _EntropyCoder:
+    """Proxy to the rANS coder of pip CompressAI (`compressai.ans`, C++), exactly as the reference's
+    `_EntropyCoder` (entropy_models.py:16-50) resolves it.  The coder itself is out of scope of this package
+    (BASELINE.json: "rANS bitstream coding stays in the reference's C++"): it is imported lazily, so everything
+    else works without it and the bitstream entry points fail with a clear message when it is absent."""
+
+    def __init__(self, method="ans"):
+        if method != "ans":
+            raise ValueError(f'Unknown entropy coder "{method}" (available: ans)')
+        self.name = method
+        self._encoder = self._decoder = None
+
+    @staticmethod
+    def module():
+        try:
+            from compressai import ans
+        except Exception as e:  # noqa: BLE001
+            raise RuntimeError("the rANS coder (`compressai.ans` of pip CompressAI, C++) is not importable here; "
+                               "compress()/decompress() need it -- every tensor they exchange with it is available "
+                               "through symbols_and_indexes() / update() / slice_decoder()") from e
+        return ans
+
+    def encode_with_indexes(self, *args, **kwargs):
+        if self._encoder is None:
+            self._encoder = self.module().RansEncoder()
+        return self._encoder.encode_with_indexes(*args, **kwargs)
+
+    def decode_with_indexes(self, *args, **kwargs):
+        if self._decoder is None:
+            self._decoder = self.module().RansDecoder()
+        return self._decoder.decode_with_indexes(*args, **kwargs)
+
+
 class EntropyModel(B200Module):
     """reference entropy_models.py:70-292 (buffers only; coding is out of scope)."""
 
     def __init__(self, likelihood_bound=1e-9, entropy_coder=None, entropy_coder_precision=16):
         super().__init__()
+        self.entropy_coder = _EntropyCoder(entropy_coder or "ans")
         self.entropy_coder_precision = int(entropy_coder_precision)
         self.use_likelihood_bound = likelihood_bound > 0
         self.likelihood_bound = float(likelihood_bound)
@@ -85,10 +120,40 @@ class EntropyModel(B200Module):
         if len(self._cdf_length.size()) != 1:
             raise ValueError(f"Invalid offsets size {self._cdf_length.size()}")
 
-    def compress(self, *a, **k):
-        raise NotImplementedError("rANS bitstream coding stays in the reference's C++ (BASELINE.json north_star)")
+    def _coder_tables(self):
+        self._check_cdf_size()
+        self._check_cdf_length()
+        self._check_offsets_size()
+        return (self._quantized_cdf.tolist(), self._cdf_length.reshape(-1).int().tolist(),
+                self._offset.reshape(-1).int().tolist())
 
-    decompress = compress
+    def _encode_symbols(self, symbols, indexes):
+        """reference entropy_models.py:227-238: one string per batch element (`symbols`/`indexes` int32 [B,...])."""
+        if symbols.dim() < 2:
+            raise ValueError("Invalid `inputs` size. Expected a tensor with at least 2 dimensions.")
+        if symbols.size() != indexes.size():
+            raise ValueError("`inputs` and `indexes` should have the same size.")
+        cdf, lengths, offsets = self._coder_tables()
+        symbols, indexes = symbols.cpu(), indexes.cpu()
+        return [self.entropy_coder.encode_with_indexes(symbols[i].reshape(-1).int().tolist(),
+                                                       indexes[i].reshape(-1).int().tolist(), cdf, lengths, offsets)
+                for i in range(symbols.size(0))]
+
+    def _decode_symbols(self, strings, indexes):
+        """reference entropy_models.py:241-287 up to the dequantisation: int32 symbols shaped like `indexes`."""
+        if not isinstance(strings, (tuple, list)):
+            raise ValueError("Invalid `strings` parameter type.")
+        if not len(strings) == indexes.size(0):
+            raise ValueError("Invalid strings or indexes parameters")
+        if indexes.dim() < 2:
+            raise ValueError("Invalid `indexes` size. Expected a tensor with at least 2 dimensions.")
+        cdf, lengths, offsets = self._coder_tables()
+        idx = indexes.cpu()
+        out = torch.empty(idx.size(), dtype=torch.int32)
+        for i, st in enumerate(strings):
+            values = self.entropy_coder.decode_with_indexes(st, idx[i].reshape(-1).int().tolist(), cdf, lengths, offsets)
+            out[i] = torch.tensor(values, dtype=torch.int32).reshape(out[i].size())
+        return out
 
     @staticmethod
     def dequantize(inputs, means=None):
@@ -207,6 +272,32 @@ class EntropyBottleneck(EntropyModel):
         N, Cn = size[0], size[1]
         idx = torch.arange(Cn, dtype=torch.int32).view(1, -1, *([1] * (len(size) - 2)))
         return idx.repeat(N, 1, *size[2:])
+
+    @torch.no_grad()
+    def symbols(self, x):
+        """round(x - median) as int32 NCHW (quantize "symbols" with the medians, entropy_models.py:139-152,512-519)."""
+        ctx = Ctx(x.device, "fp32")
+        z = ctx.from_nchw(x, torch.float32)
+        sym = torch.empty(z.B, z.C, z.H, z.W, dtype=torch.int32, device=x.device)
+        self.emit(ctx, z, z_hat=ctx.buf(z.B, z.H, z.W, z.C, torch.float32), symbols=sym)
+        ctx.prog.run()
+        return sym
+
+    @torch.no_grad()
+    def compress(self, x, symbols=None):
+        """reference entropy_models.py:512-519: one rANS string per batch element.  `symbols` (int32 NCHW) may be
+        passed when a forward pass has already produced them."""
+        if symbols is None:
+            symbols = self.symbols(x)
+        return self._encode_symbols(symbols, self._build_indexes(symbols.size()))
+
+    @torch.no_grad()
+    def decompress(self, strings, size):
+        """reference entropy_models.py:521-526: decoded symbols + medians, float [B,C,*size] on the module's device."""
+        output_size = (len(strings), self._quantized_cdf.size(0), *size)
+        sym = self._decode_symbols(strings, self._build_indexes(output_size))
+        med = self._get_medians().detach().reshape(1, -1, *([1] * len(size)))
+        return self.dequantize(sym.to(med.device), med)
 
 
 class GaussianConditional(EntropyModel):
@@ -334,6 +425,17 @@ class GaussianConditional(EntropyModel):
             return out
         out, _, sym, _ = self._run(inputs, torch.ones_like(inputs), means, ("sym",))
         return out if mode == "dequantize" else sym
+
+    @torch.no_grad()
+    def compress(self, inputs, indexes, means=None):
+        """reference entropy_models.py:205-238."""
+        return self._encode_symbols(self.quantize(inputs, "symbols", means), indexes)
+
+    @torch.no_grad()
+    def decompress(self, strings, indexes, means=None):
+        """reference entropy_models.py:241-287."""
+        sym = self._decode_symbols(strings, indexes)
+        return self.dequantize(sym.to(indexes.device) if means is None else sym.to(means.device), means)
 
     @torch.no_grad()
     def build_indexes(self, scales):

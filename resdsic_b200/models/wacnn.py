@@ -118,6 +118,7 @@ class WACNN(CompressionModel):
         # There is no autograd through the CUDA kernels: the backward pass of BASELINE config 4 is not ported.
         self.noise_override = None
         self._plans = {}
+        self._dec_plans = {}  # decoder-side plans (slice_decoder), separate so that encode / decode can alternate
 
     # ------------------------------------------------------------------ API
     @classmethod
@@ -136,13 +137,42 @@ class WACNN(CompressionModel):
         updated |= super().update(force=force)
         return updated
 
+    @torch.no_grad()
     def compress(self, x):
-        raise NotImplementedError("rANS bitstream coding stays in the reference's C++; use symbols_and_indexes(x) for "
-                                  "the int32 symbols/indexes `compress` hands to the coder (cnn.py:253-258)")
+        """reference cnn.py:217-274.  ONE forward pass produces every symbol and CDF index on the device
+        (`symbols_and_indexes`); the rANS coder (`compressai.ans`, the reference's own C++ dependency, imported
+        lazily) is then called exactly as the reference calls it: one string per image for z, one buffered
+        stream for the ten y slices of the whole batch, symbols in slice-major NCHW order (cnn.py:257-258)."""
+        from ..entropy_models.entropy_models import _EntropyCoder
+        gc = self.gaussian_conditional
+        cdf, cdf_lengths, offsets = gc._coder_tables()
+        r = self.symbols_and_indexes(x)
+        z_strings = self.entropy_bottleneck.compress(None, symbols=r["z_symbols"])
+        c = self.slice_channels
+        sym, idx = r["y_symbols"].cpu(), r["y_indexes"].cpu()  # one device->host copy each
+        symbols_list, indexes_list = [], []
+        for i in range(self.num_slices):
+            symbols_list.extend(sym[:, c * i:c * i + c].reshape(-1).tolist())
+            indexes_list.extend(idx[:, c * i:c * i + c].reshape(-1).tolist())
+        encoder = _EntropyCoder.module().BufferedRansEncoder()
+        encoder.encode_with_indexes(symbols_list, indexes_list, cdf, cdf_lengths, offsets)
+        return {"strings": [[encoder.flush()], z_strings], "shape": torch.Size(r["shape"])}
 
+    @torch.no_grad()
     def decompress(self, strings, shape):
-        raise NotImplementedError("rANS bitstream decoding stays in the reference's C++; use slice_decoder(z_hat) for "
-                                  "everything `decompress` computes around the decoder calls (cnn.py:296-342)")
+        """reference cnn.py:296-342: the GPU work of every slice runs through `slice_decoder`, the coder calls
+        are the reference's."""
+        from ..entropy_models.entropy_models import _EntropyCoder
+        cdf, cdf_lengths, offsets = self.gaussian_conditional._coder_tables()
+        z_hat = self.entropy_bottleneck.decompress(strings[1], shape)
+        dec = self.slice_decoder(z_hat)
+        decoder = _EntropyCoder.module().RansDecoder()
+        decoder.set_stream(strings[0][0])
+        for i in range(self.num_slices):
+            idx = dec.indexes(i)
+            rv = decoder.decode_stream(idx.reshape(-1).tolist(), cdf, cdf_lengths, offsets)
+            dec.push_symbols(i, torch.tensor(rv, dtype=torch.int32).reshape(idx.shape))
+        return {"x_hat": dec.finish()}
 
     @torch.no_grad()
     def slice_decoder(self, z_hat):
@@ -161,11 +191,11 @@ class WACNN(CompressionModel):
             raise RuntimeError("resdsic_b200 runs on CUDA devices only (no CPU fallback)")
         B, _, hz, wz = z_hat.shape
         key = ("dec", B, hz, wz, str(z_hat.device), self.precision, self._weights_key())
-        plan = self._plans.get(key)
+        plan = self._dec_plans.get(key)
         if plan is None:
-            self._plans.clear()
+            self._dec_plans.clear()  # one live decoder plan, kept next to the forward plan
             plan = self._build_decoder(B, hz, wz, z_hat.device)
-            self._plans[key] = plan
+            self._dec_plans[key] = plan
         return SliceDecoder(self, plan, z_hat)
 
     # ------------------------------------------------------------- planning
@@ -180,7 +210,7 @@ class WACNN(CompressionModel):
         key = (B, H, W, str(device), self.precision, with_symbols, self._weights_key(), mb, bool(self.training))
         plan = self._plans.get(key)
         if plan is None:
-            self._plans.clear()  # one live plan: buffers are sized for one shape
+            self._plans.clear()  # one live forward plan: buffers are sized for one shape
             if mb == 1:
                 plan = self._build(B, H, W, device, with_symbols)
                 plan.subs, plan.sub_batch = [plan], B

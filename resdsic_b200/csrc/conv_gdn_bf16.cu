@@ -639,7 +639,7 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
     }
   }
   // halo mode (see gemm1_tile): stride-1 multi-tap layers on maps that a 16 x 8 patch tiles exactly.  OFF by default:
-  // correct (tests/test_gpu_ops.py::test_halo_modes_in_subprocess) but measured SLOWER (ResidualUnit main loop
+  // correct (tests/test_gpu_ops.py::test_kernel_mode_switches_in_subprocess) but measured SLOWER (ResidualUnit main loop
   // 670 vs 520 cycles per k-iteration): it removes L2 traffic, but the bound that remains is the shared-memory
   // port -- the MMAs read A and B from shared memory every k-step whatever wrote them, and windows that do not
   // start on a 1024-byte swizzle atom appear to cost extra wavefronts.  See DESIGN.md section 4.

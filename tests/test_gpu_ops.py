@@ -246,14 +246,21 @@ def test_patchify_matches_unfold(C, k, s, p, B, H, W):
 
 
 @pytest.mark.gpu
-def test_halo_modes_in_subprocess():
-    """The experimental halo modes (one TMA patch per channel block, shifted UMMA windows; off by default because
-    they measured slower) stay correct: the deconv / fused-layer / conv parity tests pass with them switched on.
-    The switches are read once per process, hence the subprocess."""
+@pytest.mark.parametrize("env", [
+    {"RDSIC_GDN_HALO": "1", "RDSIC_TC_HALO": "1"},  # experimental halo modes (off by default: measured slower)
+    {"RDSIC_TC_M2": "2"},                            # M2 (256-row tiles) forced on every eligible layer, however small
+    {"RDSIC_TC_M2": "1"},                            # small grids with the K-split of two accumulators
+    {"RDSIC_TC_M2": "0"},                            # M2 off
+    {"RDSIC_TC_M2_MINK": "1", "RDSIC_TC_M2": "2"},   # M2 also for the 1-3 k-iteration pointwise GEMMs
+    {"RDSIC_RU_DBL": "0"},                           # single-buffered fused ResidualUnit kernel
+], ids=lambda e: ",".join(f"{k[6:]}={v}" for k, v in e.items()))
+def test_kernel_mode_switches_in_subprocess(env):
+    """Every kernel mode behind a tuning switch stays correct: the conv / deconv / fused-layer parity tests pass with
+    it selected.  The switches are read once per process, hence the subprocess."""
     import subprocess
     import sys
-    env = dict(os.environ, RDSIC_GDN_HALO="1", RDSIC_TC_HALO="1")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_ops.py", "-m", "gpu", "-q", "-x", "-k",
-                        "tcgen05 or layers_bf16 or subpel"], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+                        "tcgen05 or layers_bf16 or subpel"], cwd=root, env=dict(os.environ, **env), capture_output=True,
+                       text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -75,7 +75,6 @@ __global__ void __launch_bounds__(768) win_attn_tc_kernel(const rdsic_attn_desc 
     const int rh = (hy >= d.H - WS) + (hy >= d.H - d.shift), rw = (wx >= d.W - WS) + (wx >= d.W - d.shift);
     rid[tid] = d.shift > 0 ? 3 * rh + rw : 0;
   }
-  for (int e = tid; e < HEADS * TWD * TWD; e += NTHR) tab[e] = d.bias_table[(e % (TWD * TWD)) * HEADS + e / (TWD * TWD)];
   __syncthreads();
   {
     const int VPT = 3 * C / 8;  // 16-byte vectors per token
@@ -88,7 +87,10 @@ __global__ void __launch_bounds__(768) win_attn_tc_kernel(const rdsic_attn_desc 
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst),
                    "l"(src + pixs[tok] * (size_t)d.qkv.ld + d.qkv.coff + v * 8) : "memory");
     }
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    // the relative-position-bias table (L2-resident gather) is fetched while the window's copies are in flight
+    for (int e = tid; e < HEADS * TWD * TWD; e += NTHR) tab[e] = d.bias_table[(e % (TWD * TWD)) * HEADS + e / (TWD * TWD)];
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
 

@@ -57,7 +57,7 @@ enum { TAIL_GDN = 1, TAIL_IGDN = 2, TAIL_RU = 3 };
 struct K1Cfg {
   int ns, kb, taps, kiters, kq, kr, kc_last, halo;
   uint32_t full0, empty0, a_u0, stage_u, b_off_u, idesc;
-  uint32_t a_full0, a_empty0, patch_u0, patch_u, na_mask, na_shift, tap_off0;
+  uint32_t a_full0, a_empty0, patch_u0, patch_u, na_mask, na_shift, tap_off0, pcols;
   uint64_t dconst, dconst_halo;
 };
 struct K1State {
@@ -100,24 +100,28 @@ __device__ __forceinline__ void gemm1_tile(K1State& st, const K1Cfg& c, uint32_t
       while (cb >= c.kb) cb -= c.kb;
     }
   } else {
-    int cb = 0, tap = f, cb_cur = -1;  // taps >= 2 in halo mode, so k-iteration f (0 or 1) is tap f of block 0
+    // k-iteration n = cb * taps + q; the q-th tap of the walk uses patch unit cb * pcols + unit[q] at window
+    // offset off[q] (tables in shared memory: tap_off0 + 4 q = off, + 64 + 4 q = unit)
+    int cb = 0, tap = f, u_cur = -1;  // taps >= 2 in halo mode, so k-iteration f (0 or 1) is walk position f of block 0
     uint32_t slot_cur = 0, a_cur = 0;
     for (int n = 0; n < n_own; ++n) {
-      if (cb != cb_cur) {
-        if (cb_cur >= 0) {  // done with the previous patch (once these MMAs retire)
+      uint32_t toff, tunit;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(toff) : "r"(c.tap_off0 + 4u * (uint32_t)tap));
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tunit) : "r"(c.tap_off0 + 64u + 4u * (uint32_t)tap));
+      const int u = cb * (int)c.pcols + (int)tunit;
+      if (u != u_cur) {
+        if (u_cur >= 0) {  // done with the previous patch (once these MMAs retire)
           if (elect_one()) tcgen05_commit_u32(c.a_empty0 + 8u * slot_cur);
           __syncwarp();
         }
-        const uint32_t p = st.pa_base + (uint32_t)cb;
+        const uint32_t p = st.pa_base + (uint32_t)u;
         slot_cur = p & c.na_mask;
         mbar_wait_u32(c.a_full0 + 8u * slot_cur, (p >> c.na_shift) & 1u);
         a_cur = c.patch_u0 + slot_cur * c.patch_u;
-        cb_cur = cb;
+        u_cur = u;
       }
       mbar_wait_u32(c.full0 + 8u * (uint32_t)s, ph);
       tcgen05_fence_after();
-      uint32_t toff;
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(toff) : "r"(c.tap_off0 + 4u * (uint32_t)tap));
       const uint64_t da = c.dconst_halo + (uint64_t)(a_cur + toff);
       const uint64_t db = c.dconst + (uint64_t)(c.a_u0 + (uint32_t)s * c.stage_u);
       if (elect_one()) {
@@ -132,7 +136,7 @@ __device__ __forceinline__ void gemm1_tile(K1State& st, const K1Cfg& c, uint32_t
     }
     if (elect_one()) tcgen05_commit_u32(c.a_empty0 + 8u * slot_cur);
     __syncwarp();
-    st.pa_base += (uint32_t)c.kb;
+    st.pa_base += (uint32_t)c.kb * c.pcols;
   }
   st.ph_base ^= (uint32_t)(c.kq & 1);
   st.s_base += c.kr;
@@ -175,10 +179,12 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint64_t* a_full = g_full + 1;    // [4] halo mode: A-patch ring
   uint64_t* a_empty = a_full + 4;   // [4]
   uint32_t* tmem_slot = (uint32_t*)(a_empty + 4);
-  uint32_t* tap_off = tmem_slot + 1;  // [16] halo mode: window offset of each tap in 16-byte units
+  // halo mode tables, indexed by the position q of a tap in the K walk: [0,16) window offset in 16-byte units,
+  // [16,32) patch unit within the channel block, [32,48) tap index r * KW + s (weight column block)
+  uint32_t* tap_off = tmem_slot + 1;
   // both bias vectors staged once per CTA (16-byte aligned): the epilogue's per-chunk bias loads were its hottest
   // stall (ncu: the first FADD after each bias LDG, stall_long_sb)
-  float* bias1_s = (float*)(((uintptr_t)(tap_off + 16) + 15) & ~(uintptr_t)15);  // [C]  conv bias (zeros if none)
+  float* bias1_s = (float*)(((uintptr_t)(tap_off + 48) + 15) & ~(uintptr_t)15);  // [C]  conv bias (zeros if none)
   float* bias2_s = bias1_s + MAXC;                                               // [N2] tail bias
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -204,7 +210,18 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       mbar_init(&a_full[k], 1);
       mbar_init(&a_empty[k], gg.ksplit ? 2 : 1);  // every main-loop issuer walks every patch
     }
-    for (int tp = 0; tp < d.KH * d.KW && tp < 16; ++tp) tap_off[tp] = (uint32_t)(((tp / d.KW) * g.halo_w + tp % d.KW) * 8);
+    for (int q = 0; q < d.KH * d.KW && q < 16; ++q) {
+      if (g.halo == 2) {  // column copies: walk s-major; unit = s, window = rows r * TW .. of the copy shifted by s
+        const int sx = q / d.KH, r = q % d.KH;
+        tap_off[q] = (uint32_t)(r * g.TW * 8);
+        tap_off[16 + q] = (uint32_t)sx;
+        tap_off[32 + q] = (uint32_t)(r * d.KW + sx);
+      } else {            // one patch per channel block: walk r-major, window = (r * halo_w + s) rows into the patch
+        tap_off[q] = (uint32_t)(((q / d.KW) * g.halo_w + q % d.KW) * 8);
+        tap_off[16 + q] = 0u;
+        tap_off[32 + q] = (uint32_t)q;
+      }
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -249,8 +266,10 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         const uint32_t a_full0 = __shfl_sync(0xffffffffu, smem_u32(a_full), 0);
         const uint32_t a_empty0 = __shfl_sync(0xffffffffu, smem_u32(a_empty), 0);
         const uint32_t patch0 = __shfl_sync(0xffffffffu, smem_u32(a_halo), 0);
-        const uint32_t a_bytes = (uint32_t)(g.halo_w * g.halo_h * BK * 2), na_mask = (uint32_t)gg.na - 1u;
+        const int pcols = g.halo == 2 ? d.KW : 1, pw_px = g.halo == 2 ? g.TW : g.halo_w;
+        const uint32_t a_bytes = (uint32_t)(pw_px * g.halo_h * BK * 2), na_mask = (uint32_t)gg.na - 1u;
         const uint32_t na_shift = gg.na == 4 ? 2u : 1u;
+        const uint32_t tab0 = __shfl_sync(0xffffffffu, smem_u32(tap_off), 0);
         uint32_t pa = 0;  // patches requested so far (producer 0)
         for (int tile = blockIdx.x; tile < total; tile += step) {
           int t = tile;
@@ -263,17 +282,23 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           int s = s_base + f;
           uint32_t ph = ph_base;
           if (s >= ns) { s -= ns; ph ^= 1u; }
-          int cb = 0, tap = f, cb_loaded = -1;
+          int cb = 0, tap = f, u_loaded = -1;  // patch units of this tile requested so far (unit = cb * pcols + column)
           for (int n = 0; n <= n_own; ++n) {
-            const int cb_want = n < n_own ? cb : kb - 1;  // (n == n_own: make sure every patch of the tile was requested)
+            uint32_t tunit = 0, tidx = 0;
+            if (n < n_own) {
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tunit) : "r"(tab0 + 64u + 4u * (uint32_t)tap));
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tidx) : "r"(tab0 + 128u + 4u * (uint32_t)tap));
+            }
+            const int u_want = n < n_own ? cb * pcols + (int)tunit : kb * pcols - 1;  // (n == n_own: request the rest)
             if (pw == 0) {
-              while (cb_loaded < cb_want) {
-                ++cb_loaded;
+              while (u_loaded < u_want) {
+                ++u_loaded;
                 const uint32_t slot = pa & na_mask;
                 mbar_wait_u32(a_empty0 + 8u * slot, ((pa >> na_shift) & 1u) ^ 1u);
+                const int ucb = u_loaded / pcols, ucol = u_loaded - ucb * pcols;
                 if (elect_one()) {
                   mbar_expect_tx_u32(a_full0 + 8u * slot, a_bytes);
-                  tma_load_4d_u32(patch0 + slot * (uint32_t)g.a_halo_bytes, &tmap_a, a_full0 + 8u * slot, cb_loaded * BK, x0, y0, b);
+                  tma_load_4d_u32(patch0 + slot * (uint32_t)g.a_halo_bytes, &tmap_a, a_full0 + 8u * slot, ucb * BK, x0 + ucol, y0, b);
                 }
                 __syncwarp();
                 ++pa;
@@ -284,7 +309,7 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             const uint32_t bar = full0 + 8u * (uint32_t)s;
             if (elect_one()) {
               mbar_expect_tx_u32(bar, (uint32_t)g.b_stage_bytes);
-              tma_load_2d_u32(smem_base + (uint32_t)(s * stage_bytes), &tmap_b, bar, tap * Cin + cb * BK, 0);
+              tma_load_2d_u32(smem_base + (uint32_t)(s * stage_bytes), &tmap_b, bar, (int)tidx * Cin + cb * BK, 0);
             }
             __syncwarp();
             s += 2;
@@ -362,7 +387,8 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       c.na_shift = gg.na == 4 ? 2u : 1u;
       c.tap_off0 = __shfl_sync(0xffffffffu, smem_u32(tap_off), 0);
       c.dconst = make_sw128_desc(0);
-      c.dconst_halo = make_sw128_desc_ex(0, (uint32_t)(g.halo_w * 128), 0);
+      c.dconst_halo = make_sw128_desc_ex(0, (uint32_t)((g.halo == 2 ? g.TW : g.halo_w) * 128), 0);
+      c.pcols = g.halo == 2 ? (uint32_t)d.KW : 1u;
       K1State st = {0, 0u, 0u};
       const int ways = gg.ksplit ? 2 : 1;
       int total = g.total_tiles, step = gridDim.x;
@@ -642,15 +668,20 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   // correct (tests/test_gpu_ops.py::test_kernel_mode_switches_in_subprocess) but measured SLOWER (ResidualUnit main loop
   // 670 vs 520 cycles per k-iteration): it removes L2 traffic, but the bound that remains is the shared-memory
   // port -- the MMAs read A and B from shared memory every k-step whatever wrote them, and windows that do not
-  // start on a 1024-byte swizzle atom appear to cost extra wavefronts.  See DESIGN.md section 4.
+  // start on a 1024-byte swizzle atom were the suspect -- but variant 2 below (atom-aligned windows) is just as slow
+  // (12.7k vs 10.3k cycles per tile), so misalignment is not the cause.  See DESIGN.md section 4.
+  //   RDSIC_GDN_HALO=1: one (TH+KH-1) x (TW+KW-1) patch per channel block, windows at arbitrary row offsets;
+  //   RDSIC_GDN_HALO=2: KW column-shifted copies of a (TH+KH-1) x TW patch per channel block, so that every tap's
+  //                     window starts on a 1024-byte swizzle atom (offset r * TW rows) with the standard SBO.
   static const int tune_halo = getenv("RDSIC_GDN_HALO") ? atoi(getenv("RDSIC_GDN_HALO")) : 0;
-  if (tune_halo && !flat && d->stride == 1 && d->KH * d->KW >= 2 && d->KH <= 3 && d->KW <= 3 && OH % 16 == 0 && OW % 8 == 0) {
-    g.halo = 1;
+  if (tune_halo && !flat && d->stride == 1 && d->KH * d->KW >= 2 && d->KH <= 3 && d->KW <= 3 && OH % 16 == 0 && OW % 8 == 0 &&
+      (tune_halo != 2 || d->KH >= 2)) {
+    g.halo = tune_halo == 2 ? 2 : 1;
     g.TH = 16;
     g.TW = 8;
     g.halo_w = g.TW + d->KW - 1;
     g.halo_h = g.TH + d->KH - 1;
-    g.a_halo_bytes = (BK * 2 * g.halo_w * g.halo_h + 1023) / 1024 * 1024;
+    g.a_halo_bytes = (BK * 2 * (g.halo == 2 ? g.TW : g.halo_w) * g.halo_h + 1023) / 1024 * 1024;
   }
   g.tiles_x = ceil_div(OW, g.TW);
   g.tiles_y = ceil_div(OH, g.TH);
@@ -711,7 +742,7 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {ld_b, ld_b * W, ld_b * W * H};
     cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(g.TW * d->stride), (cuuint32_t)(g.TH * d->stride), 1};
-    if (g.halo) { box[1] = (cuuint32_t)g.halo_w; box[2] = (cuuint32_t)g.halo_h; }
+    if (g.halo) { box[1] = (cuuint32_t)(g.halo == 2 ? g.TW : g.halo_w); box[2] = (cuuint32_t)g.halo_h; }
     cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
     void* base = (void*)((const __nv_bfloat16*)d->in.ptr + d->in.coff);
     if (encode(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -739,7 +770,7 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
     }
   }
   const size_t smem = (size_t)stages * stage_bytes + gg.w2_bytes + (size_t)gg.na * g.a_halo_bytes + 1024 +
-                      (2 * MAX_STAGES + 20) * 8 + 16 + 64 + 16 + 2 * MAXC * 4;
+                      (2 * MAX_STAGES + 20) * 8 + 16 + 192 + 16 + 2 * MAXC * 4;
   auto kern = d->tail_mode == TAIL_RU ? conv_gdn_tc_kernel<TAIL_RU>
               : d->tail_mode == TAIL_IGDN ? conv_gdn_tc_kernel<TAIL_IGDN> : conv_gdn_tc_kernel<TAIL_GDN>;
   static bool attr_set[16][4] = {};

@@ -248,6 +248,7 @@ def test_patchify_matches_unfold(C, k, s, p, B, H, W):
 @pytest.mark.gpu
 @pytest.mark.parametrize("env", [
     {"RDSIC_GDN_HALO": "1", "RDSIC_TC_HALO": "1"},  # experimental halo modes (off by default: measured slower)
+    {"RDSIC_GDN_HALO": "2"},                         # halo with column-shifted, swizzle-atom-aligned patch copies
     {"RDSIC_TC_M2": "2"},                            # M2 (256-row tiles) forced on every eligible layer, however small
     {"RDSIC_TC_M2": "1"},                            # small grids with the K-split of two accumulators
     {"RDSIC_TC_M2": "0"},                            # M2 off

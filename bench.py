@@ -95,13 +95,13 @@ class ClockSampler(threading.Thread):
 
 
 def build_inputs(batch, seed):
-    from oracle import weights  # synthetic data generator only (test infrastructure, not compute)
-    return weights.make_image(batch, H, W, seed=seed)
+    from resdsic_b200.utils import synthetic  # hash-seeded synthetic images (data generator, no compute)
+    return synthetic.make_image(batch, H, W, seed=seed)
 
 
 def make_weights():
-    from oracle import weights
-    return weights.make_state_dict(seed=0)
+    from resdsic_b200.utils import synthetic
+    return synthetic.make_state_dict(seed=0)
 
 
 # ----------------------------------------------------------------------------- reference / CPU arm
@@ -169,7 +169,7 @@ def run_ours(args):
     _lib.lib()  # fail loudly if the CUDA library is missing
     sd = make_weights()
     if args.model == "stf":  # builder-defined model (no reference implementation): informational runs only
-        from oracle import weights as _w
+        from resdsic_b200.utils import synthetic as _w
         model = resdsic_b200.models["stf"]().eval()
         sd = _w.synth_state_dict(model.state_dict())
     else:

@@ -59,6 +59,7 @@ struct K1Cfg {
   uint32_t full0, empty0, a_u0, stage_u, b_off_u, idesc;
   uint32_t a_full0, a_empty0, patch_u0, patch_u, na_mask, na_shift, tap_off0, pcols;
   uint64_t dconst, dconst_halo;
+  long long* kts;  // profiling aid: per-k-iteration stamps (loop top, operands ready, issued) of one tile, or null
 };
 struct K1State {
   int s_base;
@@ -86,14 +87,17 @@ __device__ __forceinline__ void gemm1_tile(K1State& st, const K1Cfg& c, uint32_t
   if (!c.halo) {
     int cb = f % c.kb;
     for (int n = 0; n < n_own; ++n) {
+      if (c.kts && n < 64) c.kts[4 * n] = clock64();
       mbar_wait_u32(c.full0 + 8u * (uint32_t)s, ph);
       tcgen05_fence_after();
+      if (c.kts && n < 64) c.kts[4 * n + 1] = clock64();
       const uint64_t da = c.dconst + (uint64_t)(c.a_u0 + (uint32_t)s * c.stage_u), db = da + c.b_off_u;
       if (elect_one()) {
         k1_mmas(acc1, da, db, c.idesc, cb + 1 != c.kb ? 4 : c.kc_last, n == 0);
         tcgen05_commit_u32(c.empty0 + 8u * (uint32_t)s);
       }
       __syncwarp();
+      if (c.kts && n < 64) c.kts[4 * n + 2] = clock64();
       s += ways;
       if (s >= c.ns) { s -= c.ns; ph ^= 1u; }
       cb += ways;
@@ -105,6 +109,7 @@ __device__ __forceinline__ void gemm1_tile(K1State& st, const K1Cfg& c, uint32_t
     int cb = 0, tap = f, u_cur = -1;  // taps >= 2 in halo mode, so k-iteration f (0 or 1) is walk position f of block 0
     uint32_t slot_cur = 0, a_cur = 0;
     for (int n = 0; n < n_own; ++n) {
+      if (c.kts && n < 64) c.kts[4 * n] = clock64();
       uint32_t toff, tunit;
       asm volatile("ld.shared.u32 %0, [%1];" : "=r"(toff) : "r"(c.tap_off0 + 4u * (uint32_t)tap));
       asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tunit) : "r"(c.tap_off0 + 64u + 4u * (uint32_t)tap));
@@ -120,8 +125,10 @@ __device__ __forceinline__ void gemm1_tile(K1State& st, const K1Cfg& c, uint32_t
         a_cur = c.patch_u0 + slot_cur * c.patch_u;
         u_cur = u;
       }
+      if (c.kts && n < 64) c.kts[4 * n + 3] = clock64();  // (A patch ready)
       mbar_wait_u32(c.full0 + 8u * (uint32_t)s, ph);
       tcgen05_fence_after();
+      if (c.kts && n < 64) c.kts[4 * n + 1] = clock64();
       const uint64_t da = c.dconst_halo + (uint64_t)(a_cur + toff);
       const uint64_t db = c.dconst + (uint64_t)(c.a_u0 + (uint32_t)s * c.stage_u);
       if (elect_one()) {
@@ -129,6 +136,7 @@ __device__ __forceinline__ void gemm1_tile(K1State& st, const K1Cfg& c, uint32_t
         tcgen05_commit_u32(c.empty0 + 8u * (uint32_t)s);
       }
       __syncwarp();
+      if (c.kts && n < 64) c.kts[4 * n + 2] = clock64();
       s += ways;
       if (s >= c.ns) { s -= c.ns; ph ^= 1u; }
       tap += ways;
@@ -389,6 +397,7 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       c.dconst = make_sw128_desc(0);
       c.dconst_halo = make_sw128_desc_ex(0, (uint32_t)((g.halo == 2 ? g.TW : g.halo_w) * 128), 0);
       c.pcols = g.halo == 2 ? (uint32_t)d.KW : 1u;
+      c.kts = nullptr;
       K1State st = {0, 0u, 0u};
       const int ways = gg.ksplit ? 2 : 1;
       int total = g.total_tiles, step = gridDim.x;
@@ -404,6 +413,7 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           mbar_wait(&acc1_empty[b], use ^ 1u);  // pair b drained (phase 2 of tile lt - 2 done)
           tcgen05_fence_after();
           if (tsp) tsp[1] = clock64();
+          c.kts = (tsp && lt == 3) ? g.dbg_ts + 2048 : nullptr;
           gemm1_tile(st, c, tbase + b * (uint32_t)(2 * C) + me * (uint32_t)C, me, 2);
           if (elect_one()) tcgen05_commit(&acc1_full[b]);
           __syncwarp();
@@ -421,6 +431,7 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           mbar_wait(&acc1_empty[0], par ^ 1u);
           tcgen05_fence_after();
           if (tsp) tsp[1] = clock64();
+          c.kts = (tsp && lt == 3) ? g.dbg_ts + 2048 : nullptr;
           gemm1_tile(st, c, acc1, me, ways);
           if (elect_one()) tcgen05_commit(&acc1_full[0]);
           __syncwarp();

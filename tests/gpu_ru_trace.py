@@ -50,10 +50,11 @@ def main():
     print("k-loop of tile 3 (issuer 0's own k-iterations): index, gap since previous, barrier wait, issue")
     prev = None
     for k in range(64):
-        a, b, c = t[2048 + 4 * k:2048 + 4 * k + 3]
+        a, b, c, p = t[2048 + 4 * k:2048 + 4 * k + 4]
         if not c:
             continue
-        print(f"  k{k:02d} gap {a - prev if prev else 0:6d} wait {b - a:6d} issue {c - b:6d}")
+        patch = f" (A patch wait {p - a:6d})" if p else ""
+        print(f"  k{k:02d} gap {a - prev if prev else 0:6d} wait {b - a:6d} issue {c - b:6d}{patch}")
         prev = c
 
 

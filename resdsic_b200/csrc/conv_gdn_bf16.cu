@@ -57,7 +57,8 @@ enum { TAIL_GDN = 1, TAIL_IGDN = 2, TAIL_RU = 3 };
 struct K1Cfg {
   int ns, kb, taps, kiters, kq, kr, kc_last, halo;
   uint32_t full0, empty0, a_u0, stage_u, b_off_u, idesc;
-  uint32_t a_full0, a_empty0, patch_u0, patch_u, na_mask, na_shift, tap_off0, pcols;
+  uint32_t a_full0, a_empty0, patch_u0, patch_u, na_mask, na_shift, pcols;
+  int nin, nout, off_in, off_out, unit_out;  // halo walk: inner / outer extents, window offset per inner / outer step
   uint64_t dconst, dconst_halo;
   long long* kts;  // profiling aid: per-k-iteration stamps (loop top, operands ready, issued) of one tile, or null
 };
@@ -104,16 +105,16 @@ __device__ __forceinline__ void gemm1_tile(K1State& st, const K1Cfg& c, uint32_t
       while (cb >= c.kb) cb -= c.kb;
     }
   } else {
-    // k-iteration n = cb * taps + q; the q-th tap of the walk uses patch unit cb * pcols + unit[q] at window
-    // offset off[q] (tables in shared memory: tap_off0 + 4 q = off, + 64 + 4 q = unit)
-    int cb = 0, tap = f, u_cur = -1;  // taps >= 2 in halo mode, so k-iteration f (0 or 1) is walk position f of block 0
+    // k-iteration n = cb * taps + q; the walk over a block's taps has an inner and an outer counter (variant 1:
+    // outer r, inner s, one patch per block; variant 2: outer s = patch unit, inner r).  Pure register arithmetic:
+    // with the shared-memory port saturated, table reads on this thread's critical path cost 80-500 cycles each.
+    int cb = 0, i_in = f, i_out = 0, u_cur = -1;
+    while (i_in >= c.nin) { i_in -= c.nin; ++i_out; }
     uint32_t slot_cur = 0, a_cur = 0;
     for (int n = 0; n < n_own; ++n) {
       if (c.kts && n < 64) c.kts[4 * n] = clock64();
-      uint32_t toff, tunit;
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(toff) : "r"(c.tap_off0 + 4u * (uint32_t)tap));
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tunit) : "r"(c.tap_off0 + 64u + 4u * (uint32_t)tap));
-      const int u = cb * (int)c.pcols + (int)tunit;
+      const uint32_t toff = (uint32_t)(i_in * c.off_in + i_out * c.off_out);
+      const int u = cb * (int)c.pcols + i_out * c.unit_out;
       if (u != u_cur) {
         if (u_cur >= 0) {  // done with the previous patch (once these MMAs retire)
           if (elect_one()) tcgen05_commit_u32(c.a_empty0 + 8u * slot_cur);
@@ -139,8 +140,9 @@ __device__ __forceinline__ void gemm1_tile(K1State& st, const K1Cfg& c, uint32_t
       if (c.kts && n < 64) c.kts[4 * n + 2] = clock64();
       s += ways;
       if (s >= c.ns) { s -= c.ns; ph ^= 1u; }
-      tap += ways;
-      if (tap >= c.taps) { tap -= c.taps; ++cb; }
+      i_in += ways;
+      while (i_in >= c.nin) { i_in -= c.nin; ++i_out; }
+      if (i_out >= c.nout) { i_out -= c.nout; ++cb; }
     }
     if (elect_one()) tcgen05_commit_u32(c.a_empty0 + 8u * slot_cur);
     __syncwarp();
@@ -187,9 +189,7 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint64_t* a_full = g_full + 1;    // [4] halo mode: A-patch ring
   uint64_t* a_empty = a_full + 4;   // [4]
   uint32_t* tmem_slot = (uint32_t*)(a_empty + 4);
-  // halo mode tables, indexed by the position q of a tap in the K walk: [0,16) window offset in 16-byte units,
-  // [16,32) patch unit within the channel block, [32,48) tap index r * KW + s (weight column block)
-  uint32_t* tap_off = tmem_slot + 1;
+  uint32_t* tap_off = tmem_slot + 1;  // (48 words reserved)
   // both bias vectors staged once per CTA (16-byte aligned): the epilogue's per-chunk bias loads were its hottest
   // stall (ncu: the first FADD after each bias LDG, stall_long_sb)
   float* bias1_s = (float*)(((uintptr_t)(tap_off + 48) + 15) & ~(uintptr_t)15);  // [C]  conv bias (zeros if none)
@@ -217,18 +217,6 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     for (int k = 0; k < 4; ++k) {
       mbar_init(&a_full[k], 1);
       mbar_init(&a_empty[k], gg.ksplit ? 2 : 1);  // every main-loop issuer walks every patch
-    }
-    for (int q = 0; q < d.KH * d.KW && q < 16; ++q) {
-      if (g.halo == 2) {  // column copies: walk s-major; unit = s, window = rows r * TW .. of the copy shifted by s
-        const int sx = q / d.KH, r = q % d.KH;
-        tap_off[q] = (uint32_t)(r * g.TW * 8);
-        tap_off[16 + q] = (uint32_t)sx;
-        tap_off[32 + q] = (uint32_t)(r * d.KW + sx);
-      } else {            // one patch per channel block: walk r-major, window = (r * halo_w + s) rows into the patch
-        tap_off[q] = (uint32_t)(((q / d.KW) * g.halo_w + q % d.KW) * 8);
-        tap_off[16 + q] = 0u;
-        tap_off[32 + q] = (uint32_t)q;
-      }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -277,7 +265,7 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         const int pcols = g.halo == 2 ? d.KW : 1, pw_px = g.halo == 2 ? g.TW : g.halo_w;
         const uint32_t a_bytes = (uint32_t)(pw_px * g.halo_h * BK * 2), na_mask = (uint32_t)gg.na - 1u;
         const uint32_t na_shift = gg.na == 4 ? 2u : 1u;
-        const uint32_t tab0 = __shfl_sync(0xffffffffu, smem_u32(tap_off), 0);
+        const int nin = g.halo == 2 ? d.KH : d.KW, nout = g.halo == 2 ? d.KW : d.KH;
         uint32_t pa = 0;  // patches requested so far (producer 0)
         for (int tile = blockIdx.x; tile < total; tile += step) {
           int t = tile;
@@ -290,14 +278,13 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           int s = s_base + f;
           uint32_t ph = ph_base;
           if (s >= ns) { s -= ns; ph ^= 1u; }
-          int cb = 0, tap = f, u_loaded = -1;  // patch units of this tile requested so far (unit = cb * pcols + column)
+          int cb = 0, i_in = f, i_out = 0, u_loaded = -1;  // patch units of this tile requested so far
+          while (i_in >= nin) { i_in -= nin; ++i_out; }
           for (int n = 0; n <= n_own; ++n) {
-            uint32_t tunit = 0, tidx = 0;
-            if (n < n_own) {
-              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tunit) : "r"(tab0 + 64u + 4u * (uint32_t)tap));
-              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tidx) : "r"(tab0 + 128u + 4u * (uint32_t)tap));
-            }
-            const int u_want = n < n_own ? cb * pcols + (int)tunit : kb * pcols - 1;  // (n == n_own: request the rest)
+            // walk position -> (r, s): variant 2 walks s-major (outer = s = patch unit), variant 1 r-major
+            const int r = g.halo == 2 ? i_in : i_out, sx = g.halo == 2 ? i_out : i_in;
+            const int tidx = r * KW + sx, tunit = g.halo == 2 ? sx : 0;
+            const int u_want = n < n_own ? cb * pcols + tunit : kb * pcols - 1;  // (n == n_own: request the rest)
             if (pw == 0) {
               while (u_loaded < u_want) {
                 ++u_loaded;
@@ -317,13 +304,14 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             const uint32_t bar = full0 + 8u * (uint32_t)s;
             if (elect_one()) {
               mbar_expect_tx_u32(bar, (uint32_t)g.b_stage_bytes);
-              tma_load_2d_u32(smem_base + (uint32_t)(s * stage_bytes), &tmap_b, bar, (int)tidx * Cin + cb * BK, 0);
+              tma_load_2d_u32(smem_base + (uint32_t)(s * stage_bytes), &tmap_b, bar, tidx * Cin + cb * BK, 0);
             }
             __syncwarp();
             s += 2;
             if (s >= ns) { s -= ns; ph ^= 1u; }
-            tap += 2;
-            if (tap >= taps) { tap -= taps; ++cb; }
+            i_in += 2;
+            while (i_in >= nin) { i_in -= nin; ++i_out; }
+            if (i_out >= nout) { i_out -= nout; ++cb; }
           }
           ph_base ^= (uint32_t)(kq & 1);
           s_base += kr;
@@ -393,7 +381,11 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       c.patch_u = (uint32_t)g.a_halo_bytes >> 4;
       c.na_mask = (uint32_t)gg.na - 1u;
       c.na_shift = gg.na == 4 ? 2u : 1u;
-      c.tap_off0 = __shfl_sync(0xffffffffu, smem_u32(tap_off), 0);
+      c.nin = g.halo == 2 ? d.KH : d.KW;
+      c.nout = g.halo == 2 ? d.KW : d.KH;
+      c.off_in = g.halo == 2 ? g.TW * 8 : 8;            // 16-byte units: one patch row of pixels = 128 B = 8 units
+      c.off_out = g.halo == 2 ? 0 : g.halo_w * 8;
+      c.unit_out = g.halo == 2 ? 1 : 0;
       c.dconst = make_sw128_desc(0);
       c.dconst_halo = make_sw128_desc_ex(0, (uint32_t)((g.halo == 2 ? g.TW : g.halo_w) * 128), 0);
       c.pcols = g.halo == 2 ? (uint32_t)d.KW : 1u;

@@ -266,8 +266,14 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         const uint32_t a_bytes = (uint32_t)(pw_px * g.halo_h * BK * 2), na_mask = (uint32_t)gg.na - 1u;
         const uint32_t na_shift = gg.na == 4 ? 2u : 1u;
         const int nin = g.halo == 2 ? d.KH : d.KW, nout = g.halo == 2 ? d.KW : d.KH;
-        uint32_t pa = 0;  // patches requested so far (producer 0)
-        for (int tile = blockIdx.x; tile < total; tile += step) {
+        // Patches are requested `ahead` units BEFORE the weight stages of their unit (global unit index U = local tile
+        // number * units-per-tile + unit): queued behind eight weight stages in the TMA FIFO they arrived just in
+        // time or late (traced: 300-960 cycle waits at every unit change).
+        const int upt = kb * pcols;
+        const uint32_t ahead = (uint32_t)(gg.na - 1 < 2 ? gg.na - 1 : 2);
+        uint32_t pa = 0, lt = 0;  // pa: patches requested so far (producer 0) = next global unit index to request
+        const uint32_t n_local = (uint32_t)((total - (int)blockIdx.x + step - 1) / step);  // tiles of this CTA
+        for (int tile = blockIdx.x; tile < total; tile += step, ++lt) {
           int t = tile;
           const int tx = t % g.tiles_x;
           t /= g.tiles_x;
@@ -278,22 +284,30 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           int s = s_base + f;
           uint32_t ph = ph_base;
           if (s >= ns) { s -= ns; ph ^= 1u; }
-          int cb = 0, i_in = f, i_out = 0, u_loaded = -1;  // patch units of this tile requested so far
+          int cb = 0, i_in = f, i_out = 0;
           while (i_in >= nin) { i_in -= nin; ++i_out; }
           for (int n = 0; n <= n_own; ++n) {
             // walk position -> (r, s): variant 2 walks s-major (outer = s = patch unit), variant 1 r-major
             const int r = g.halo == 2 ? i_in : i_out, sx = g.halo == 2 ? i_out : i_in;
             const int tidx = r * KW + sx, tunit = g.halo == 2 ? sx : 0;
-            const int u_want = n < n_own ? cb * pcols + tunit : kb * pcols - 1;  // (n == n_own: request the rest)
-            if (pw == 0) {
-              while (u_loaded < u_want) {
-                ++u_loaded;
+            if (pw == 0 && n < n_own) {
+              // global unit wanted now: this k-iteration's unit + `ahead`, clipped to the CTA's last unit
+              uint32_t want = lt * (uint32_t)upt + (uint32_t)(cb * pcols + tunit) + ahead;
+              const uint32_t last = n_local * (uint32_t)upt - 1u;
+              if (want > last) want = last;
+              while (pa <= want) {
+                const uint32_t ut = pa / (uint32_t)upt, uu = pa - ut * (uint32_t)upt;  // local tile number, unit in tile
+                int t2 = (int)blockIdx.x + (int)ut * step;
+                const int tx2 = t2 % g.tiles_x;
+                t2 /= g.tiles_x;
+                const int ty2 = t2 % g.tiles_y, b2 = t2 / g.tiles_y;
+                const int ucb = (int)uu / pcols, ucol = (int)uu - ucb * pcols;
                 const uint32_t slot = pa & na_mask;
                 mbar_wait_u32(a_empty0 + 8u * slot, ((pa >> na_shift) & 1u) ^ 1u);
-                const int ucb = u_loaded / pcols, ucol = u_loaded - ucb * pcols;
                 if (elect_one()) {
                   mbar_expect_tx_u32(a_full0 + 8u * slot, a_bytes);
-                  tma_load_4d_u32(patch0 + slot * (uint32_t)g.a_halo_bytes, &tmap_a, a_full0 + 8u * slot, ucb * BK, x0 + ucol, y0, b);
+                  tma_load_4d_u32(patch0 + slot * (uint32_t)g.a_halo_bytes, &tmap_a, a_full0 + 8u * slot, ucb * BK,
+                                  tx2 * g.TW - d.pad_w + ucol, ty2 * g.TH - d.pad_h, b2);
                 }
                 __syncwarp();
                 ++pa;

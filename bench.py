@@ -95,13 +95,19 @@ class ClockSampler(threading.Thread):
 
 
 def build_inputs(batch, seed):
-    from resdsic_b200.utils import synthetic  # hash-seeded synthetic images (data generator, no compute)
-    return synthetic.make_image(batch, H, W, seed=seed)
+    """`torch.rand(B,3,H,W)` from a private CPU generator (the synthetic input of the BASELINE configs)."""
+    from resdsic_b200.utils import synthetic  # data generators only, no compute of the path
+    return synthetic.rand_image(batch, H, W, seed=seed)
 
 
-def make_weights():
+def make_weights(profile="refinit"):
+    """Default "refinit": the reference constructor's own random init under torch.manual_seed(0) (BASELINE.json:
+    "random-init weights"; bit-equal to the reference's, tests/test_refinit.py) -- the weights on which the
+    bf16 tolerances of the north star are asserted un-relaxed.  "stress" / "lowrate": the hash-seeded profiles."""
     from resdsic_b200.utils import synthetic
-    return synthetic.make_state_dict(seed=0)
+    if profile == "refinit":
+        return synthetic.refinit_state_dict(0)
+    return synthetic.make_state_dict(seed=0, profile=profile)
 
 
 # ----------------------------------------------------------------------------- reference / CPU arm
@@ -120,27 +126,76 @@ def time_cpu_oracle(sd, steps, warmup, batch):
     return batch * steps / dt, dt / steps
 
 
+CPU_SAMPLE_BATCH = 2  # images per CPU step: a bounded sample of the GPU arm's batch (0.4-0.5 s per image on 16 threads)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    sd = make_weights()
-    ips, per_step = time_cpu_oracle(sd, args.steps, args.warmup, batch=1)
+    sd = make_weights(args.weights)
+    b = CPU_SAMPLE_BATCH
+    ips, per_step = time_cpu_oracle(sd, args.steps, args.warmup, batch=b)
     cores = torch.get_num_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cnn forward 512x768, 1 image per step on host CPU", "precision": "fp32"},
+        "config": {"workload": f"cnn (WACNN N=192 M=320) forward 512x768, eval mode; bounded sample of the GPU arm's "
+                               f"batch-{args.batch} step: {b} images per CPU step (images are independent, the CPU "
+                               "rate does not depend on the batch)", "precision": "fp32", "weights": args.weights,
+                   "batch_per_step": b, "image": [H, W]},
         "megapixels_per_s": ips * H * W / 1e6,
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x 1 image 512x768, oracle (torch CPU fp32 restatement of "
+                         "sample": f"{args.steps} steps x {b} images 512x768, oracle (torch CPU fp32 restatement of "
                                    "the reference forward; the Python reference itself cannot travel to the GPU box)"},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def time_gpu_eager(sd, x_dev, steps=3, warmup=2):
+    """The incumbent on the same B200: the SAME PyTorch graph the reference
+    executes (the oracle's functional restatement: F.conv2d / conv_transpose2d / linear / matmul / softmax / erfc ...)
+    in eager mode on the GPU, i.e. cuDNN + cuBLAS + ATen elementwise kernels -- fp32, TF32, and
+    autocast(bf16) + channels_last.  A reported baseline (no kernel of this repo runs here)."""
+    from oracle import wacnn_oracle as O
+    dev = x_dev.device
+    res = {}
+    torch.backends.cudnn.benchmark = True
+    sd_dev = {k: v.to(dev) for k, v in sd.items()}
+    sd_cl = {k: (v.contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v) for k, v in sd_dev.items()}
+    variants = (("fp32", False, None, sd_dev, x_dev),
+                ("tf32", True, None, sd_dev, x_dev),
+                ("bf16_autocast_channels_last", True, torch.bfloat16, sd_cl, x_dev.contiguous(memory_format=torch.channels_last)))
+    for name, tf32, amp, w, x in variants:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        try:
+            def step():
+                if amp is None:
+                    return O.forward(w, x)
+                with torch.autocast("cuda", dtype=amp):
+                    return O.forward(w, x)
+            for _ in range(warmup):
+                step()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / steps
+            res[name] = {"images_per_s": x.shape[0] / (ms / 1e3), "ms_per_step": ms}
+        except Exception as e:  # (out of memory on a small card, ...): report, do not fail the bench line
+            res[name] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        torch.cuda.empty_cache()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = True
+    return res
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -167,7 +222,7 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     _lib.lib()  # fail loudly if the CUDA library is missing
-    sd = make_weights()
+    sd = make_weights(args.weights)
     if args.model == "stf":  # builder-defined model (no reference implementation): informational runs only
         from resdsic_b200.utils import synthetic as _w
         model = resdsic_b200.models["stf"]().eval()
@@ -176,6 +231,7 @@ def run_ours(args):
         model = resdsic_b200.WACNN().eval()
     model.load_state_dict(sd, strict=True)
     model = model.to(dev).set_precision(args.precision)
+    model.static_outputs = True  # results are consumed in place (ForwardPipeline snapshots them): no per-call clones
     model.micro_batches = args.micro_batches if args.micro_batches == "auto" else int(args.micro_batches)
     B = args.batch
     x_host = build_inputs(B, seed=100 + rank).pin_memory()
@@ -227,23 +283,37 @@ def run_ours(args):
         n_img = B * world * args.steps
         ips = n_img / (ms / 1e3)
         ips_e2e = n_img / (ms_e2e / 1e3)
+        fam, per_op = fam
         conv_ms, conv_n = fam["conv"]
         total_ms = sum(v[0] for v in fam.values())
         flop_per_image = FLOP_PER_IMAGE
         if args.model != "cnn":  # no survey figure: sum 2*M*N*K over the program's GEMM descriptors
-            plan = next(iter(model._plans.values()))
+            plan = model._last_plan
             flop_per_image = sum(2.0 * o.u.conv.B * o.u.conv.OH * o.u.conv.OW * o.u.conv.Cout * o.u.conv.KH * o.u.conv.KW *
                                  o.u.conv.Cin for o in plan.prog.ops if o.kind == _lib.OP_CONV) / plan.sub_batch
         # the profile covers ONE sub-batch program (the model runs `micro_batches` of them concurrently)
-        b_prog = next(iter(model._plans.values())).sub_batch
-        tf = b_prog * flop_per_image / conv_n / (conv_ms / conv_n / 1e3) / 1e12  # algorithmic FLOP per launch / avg launch time
+        b_prog = model._last_plan.sub_batch
+        fam_tf = b_prog * flop_per_image / (conv_ms / 1e3) / 1e12  # conv family: algorithmic FLOP of a step / its device time
+        # dominant kernel = the (kernel instance, layer shape) class with the largest share of the step
+        classes = {}
+        for r in per_op:
+            if r["kind"] != "conv":
+                continue
+            c = classes.setdefault(r["kernel"] + " " + r["shape"], {"ms": 0.0, "n": 0, "flop": r["flop"], "kernel": r["kernel"],
+                                                                  "shape": r["shape"], "bytes": r["bytes"]})
+            c["ms"] += r["ms"]
+            c["n"] += 1
+        dom = max(classes.values(), key=lambda c: c["ms"])
+        dom_tf = dom["flop"] / (dom["ms"] / dom["n"] / 1e3) / 1e12
+        step_tf = B * flop_per_image / (ms / args.steps / 1e3) / 1e12  # whole step (graph replay), all kernels
         traffic_bytes, traffic_note = None, None
-        tpath = os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")
-        if os.path.exists(tpath):  # DRAM bytes of the heaviest launch, from the committed ncu --set full capture
+        tpath = os.path.join(ROOT, "profiles", "r2_roofline_traffic.json")
+        if os.path.exists(tpath):  # DRAM bytes of one launch of the dominant kernel, from this round's ncu --set full capture
             with open(tpath) as fh:
                 tj = json.load(fh)
-            traffic_bytes = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-            traffic_note = f"{tj['kernel']}: algorithmic {tj['algorithmic_bytes']} B; {tj['source']}"
+            if tj.get("kernel_key") == dom["kernel"] + " " + dom["shape"]:
+                traffic_bytes = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                traffic_note = tj["source"]
         line = {
             "metric": METRIC if args.model == "cnn" else METRIC.replace("WACNN (-m cnn)", "STF (-m stf, builder-defined)"), "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -251,10 +321,10 @@ def run_ours(args):
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": (f"cnn (WACNN N=192 M=320) forward 512x768, batch {B} per GPU, eval mode" if args.model == "cnn"
                                     else f"stf (builder-defined, N=192 M=384) forward 512x768, batch {B} per GPU, eval mode"),
-                       "precision": args.precision, "batch_per_gpu": B, "image": [H, W], "parallelism": f"dp{world}",
+                       "precision": args.precision, "weights": args.weights, "batch_per_gpu": B, "image": [H, W], "parallelism": f"dp{world}",
                        "l2": f"per-step activation working set (~{0.19 * B:.1f} GB at batch {B}) exceeds the 126 MB L2; no explicit flush",
                        "cuda_graph": bool(model.use_cuda_graph),
-                       "micro_batches": len(next(iter(model._plans.values())).subs)},
+                       "micro_batches": len(model._last_plan.subs)},
             "megapixels_per_s": ips * H * W / 1e6,
             "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "api": "resdsic_b200.utils.ForwardPipeline.run (pinned host in, pinned host out, depth 2)",
@@ -262,19 +332,36 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps,
             "launches_per_step": launches_per_step,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                         "frac": tf / peaks["tf_sustained"], "traffic": traffic_bytes, "traffic_note": traffic_note,
-                         "kernel": "implicit-GEMM conv family (all conv/deconv/linear/GDN launches)",
-                         "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                         "share_of_step": conv_ms / total_ms,
-                         "families_note": "eager per-launch profile of ONE sub-batch program (micro_batches of them run per step)",
+            "roofline": {"bound": "tensor", "achieved": dom_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                         "frac": dom_tf / peaks["tf_sustained"], "frac_of_burst_peak": dom_tf / peaks["tf_burst"],
+                         "peak_burst": peaks["tf_burst"],
+                         "traffic": traffic_bytes, "traffic_note": traffic_note,
+                         "kernel": dom["kernel"], "layer": dom["shape"], "launches_per_step": dom["n"],
+                         "avg_launch_ms": dom["ms"] / dom["n"], "algorithmic_flop_per_launch": dom["flop"],
+                         "algorithmic_bytes_per_launch": dom["bytes"], "share_of_step": dom["ms"] / total_ms,
+                         "peak_source": peaks["source"] + ": sustained bf16 (kernel timed inside a long step) and burst",
+                         "timing": "CUDA events around every launch of one eager pass of the step's program (second of two passes)",
+                         "conv_family": {"achieved": fam_tf, "frac": fam_tf / peaks["tf_sustained"],
+                                         "frac_of_burst_peak": fam_tf / peaks["tf_burst"], "share_of_step": conv_ms / total_ms,
+                                         "launches_per_step": conv_n},
+                         "whole_step": {"achieved": step_tf, "frac": step_tf / peaks["tf_sustained"],
+                                        "frac_of_burst_peak": step_tf / peaks["tf_burst"],
+                                        "note": "B x 413.22 GFLOP / graph-replay step time (every kernel, launch gaps included)"},
                          "families_ms_per_step": {k: {"ms": v[0], "launches": v[1]} for k, v in fam.items()}},
         }
+        if world == 1 and not args.no_eager_baseline and args.model == "cnn":
+            eager = time_gpu_eager(sd, x_dev)
+            best = max((v["images_per_s"] for v in eager.values() if "images_per_s" in v), default=None)
+            line["gpu_eager_baseline"] = {
+                "what": "the same PyTorch graph (oracle restatement of the reference forward) in eager mode on this GPU: "
+                        "cuDNN / cuBLAS / ATen kernels, same batch and image size, inputs resident, CUDA-event timed",
+                "batch": B, "variants": eager, "best_images_per_s": best,
+                "speedup_over_best": (ips / best) if best else None}
         if world == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
-            cips, _ = time_cpu_oracle(sd, steps=1, warmup=1, batch=2)
+            cips, _ = time_cpu_oracle(sd, steps=2, warmup=1, batch=CPU_SAMPLE_BATCH)
             line["cpu_baseline"] = {"value": cips, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": "1 step x 2 images 512x768 after a 1-image warm-up (oracle, torch CPU fp32)"}
+                                    "sample": f"2 steps x {CPU_SAMPLE_BATCH} images 512x768 after a warm-up step (oracle, torch CPU fp32)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -285,7 +372,7 @@ def profile_families(model, x_dev, dump=None):
     import ctypes as C
 
     from resdsic_b200 import _lib
-    plan = next(iter(model._plans.values()))
+    plan = model._last_plan
     plan.x.copy_(x_dev)
     prog = plan.prog
     L = _lib.lib()
@@ -318,14 +405,26 @@ def profile_families(model, x_dev, dump=None):
         rec = {"i": i, "kind": k, "ms": round(t, 4)}
         if k == "conv":
             c = prog.ops[i].u.conv
-            flop = 2.0 * c.B * c.OH * c.OW * c.Cout * c.KH * c.KW * c.Cin
-            rec.update(M=c.B * c.OH * c.OW, N=c.Cout, K=c.KH * c.KW * c.Cin, k=f"{c.KH}x{c.KW}s{c.stride}",
-                       epi=c.epilogue, tc=int(c.w_dtype), tflops=round(flop / (t * 1e-3) / 1e12, 2))
+            M = c.B * c.OH * c.OW
+            flop = 2.0 * M * c.Cout * c.KH * c.KW * c.Cin
+            n_out = c.Cout
+            if c.tail_mode:  # fused second GEMM (GDN / IGDN / ResidualUnit tail): K2 = Cout, N2 = tail_n
+                flop += 2.0 * M * c.Cout * c.tail_n
+                n_out = c.tail_n
+            esz = lambda v: 0 if not v.ptr else (2 if v.dtype == _lib.BF16 else 4)
+            # algorithmic bytes: input once, outputs once, residual / gate operands once, weights once
+            nbytes = (c.B * c.H * c.W * c.Cin * esz(c.in_) + M * n_out * (esz(c.out) + esz(c.out2) + esz(c.out3) +
+                      esz(c.res) + esz(c.aux)) + c.Cout * c.KH * c.KW * c.Cin * 2 + c.tail_n * c.Cout * 2)
+            kern = (f"conv_gdn_tc_kernel<{c.tail_mode}>" if c.tail_mode else
+                    (f"conv_tc_kernel<EPI={c.epilogue}>" if c.w_dtype == _lib.BF16 else "conv_f32_kernel"))
+            shape = f"M={M} N={c.Cout} K={c.KH * c.KW * c.Cin} {c.KH}x{c.KW}s{c.stride}" + (f" tailN={c.tail_n}" if c.tail_mode else "")
+            rec.update(M=M, N=c.Cout, K=c.KH * c.KW * c.Cin, k=f"{c.KH}x{c.KW}s{c.stride}", kernel=kern, shape=shape, flop=flop,
+                       bytes=nbytes, epi=c.epilogue, tc=int(c.w_dtype), tflops=round(flop / (t * 1e-3) / 1e12, 2))
         per_op.append(rec)
     if dump:
         with open(dump, "w") as fh:
             json.dump(per_op, fh, indent=0)
-    return fam
+    return fam, per_op
 
 
 def main():
@@ -341,6 +440,9 @@ def main():
     ap.add_argument("--micro-batches", default="auto", help="sub-batches run as concurrent graphs (auto | 1 | 2 | 4 ...)")
     ap.add_argument("--model", default="cnn", choices=["cnn", "stf"], help="cnn = the headline (BASELINE.json) workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the eager-PyTorch-on-this-GPU baseline leg")
+    ap.add_argument("--weights", default="refinit", choices=["refinit", "stress", "lowrate"],
+                    help="refinit = the reference constructor's random init (seed 0); stress / lowrate = hash-seeded profiles")
     ap.add_argument("--dump-ops", default=None, help="write the per-launch device times of one step to this JSON file")
     args = ap.parse_args()
     if args.impl == "reference":

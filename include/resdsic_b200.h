@@ -8,9 +8,15 @@
  *
  * Conventions
  *   - plain C: raw device pointers + sizes, no torch types;
- *   - every function is re-entrant, keeps no global mutable state, launches on
- *     the caller's `stream` of the CURRENT device and never allocates or
- *     retains caller memory (outputs / workspaces are caller-owned);
+ *   - every function is re-entrant, launches on the caller's `stream` of the
+ *     CURRENT device and never allocates or retains caller memory (outputs /
+ *     workspaces are caller-owned).  The only process-wide state is a set of
+ *     idempotent caches written once with the same value by whichever host
+ *     thread gets there first: per-device SM count, "dynamic shared memory
+ *     opt-in done" flags per kernel, the resolved driver entry point of the
+ *     tensor-map encoder, and developer tuning knobs (RDSIC_TC_* environment
+ *     variables) read once.  Profiling / tracing hooks exist only in builds
+ *     compiled with -DRDSIC_DEBUG;
  *   - return value: 0 = ok, otherwise a negative RDSIC_E_* argument error or a
  *     positive cudaError_t; rdsic_error_string() renders either.  The Python
  *     host raises RuntimeError on non-zero, matching the reference's

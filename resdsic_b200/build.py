@@ -24,6 +24,8 @@ NVCC_FLAGS = [
     # NOTE: no --use_fast_math: the entropy kernels must keep IEEE div/sqrt and
     # un-contracted adds to track the reference bit-for-bit.
 ]
+if os.environ.get("RDSIC_DEBUG_BUILD"):  # developer builds: time-stamp / operand-skip / timeout-log hooks (tests/gpu_*_trace.py)
+    NVCC_FLAGS.append("-DRDSIC_DEBUG")
 
 
 def _nvcc():

@@ -18,6 +18,21 @@ static inline int rdsic_launch_status() {
 
 __host__ __device__ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// SM count of the current device (idempotent per-device cache: racing host threads store the same value).
+static inline int rdsic_sm_count() {
+  static int cache[32] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool track = dev >= 0 && dev < 32;
+  int sms = track ? cache[dev] : 0;
+  if (!sms) {
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    if (track) cache[dev] = sms;
+  }
+  return sms;
+}
+
 // ---- elementwise math, written to track the reference's fp32 ATen ops -------
 // nn.GELU() default: 0.5*x*(1+erf(x/sqrt(2)))
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }

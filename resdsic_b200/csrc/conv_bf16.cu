@@ -20,8 +20,10 @@
 //     epilogue (TMEM lane quarter = warp_id % 4).
 #include "tc_common.cuh"
 
+#ifdef RDSIC_DEBUG  // profiling aids (time stamps, operand-skip switches): compiled out of release builds
 long long* g_dbg_ts = nullptr;
-int g_dbg_host = 0;  // profiling aid, see rdsic_debug_read_ts
+int g_dbg_host = 0;  // see rdsic_debug_read_ts
+#endif
 
 namespace {
 
@@ -654,6 +656,7 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   // halo mode: stride-1 multi-tap convs on maps that a 16 x 8 patch tiles exactly (RDSIC_TC_HALO: 0 off,
   // 1 on, 2 on with the descriptor base-offset field derived from the window start)
   static const int tune_halo = getenv("RDSIC_TC_HALO") ? atoi(getenv("RDSIC_TC_HALO")) : 0;
+#ifdef RDSIC_DEBUG
   static long long* dbg_ts_buf = nullptr;
   if (getenv("RDSIC_TC_DBG_TS") && !dbg_ts_buf) {
     if (atoi(getenv("RDSIC_TC_DBG_TS")) == 2) {  // host-mapped: survives a trap (timeout log of mbar_wait, tc_common.cuh)
@@ -670,6 +673,7 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   g.dbg_ts = dbg_ts_buf;
   static const int dbg_skip = getenv("RDSIC_TC_DBG_SKIP") ? atoi(getenv("RDSIC_TC_DBG_SKIP")) : 0;
   g.dbg_skip_load = dbg_skip | (g_dbg_host ? 4 : 0);  // bit 2: the buffer is the timeout log, no time stamps
+#endif
 
   if (tune_halo && !flat && d->stride == 1 && d->KH * d->KW > 1 && d->KH <= 3 && d->KW <= 3 && OH % 16 == 0 && OW % 8 == 0) {
     g.halo = 1;
@@ -721,8 +725,8 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
     // grids below one wave (latent-resolution layers): split N further so that more SMs get a tile.
     // The B tensor map zero-fills rows past ceil16(Cout), so BN need not divide Cout.
     const int c16 = (d->Cout + 15) / 16 * 16;
-    if (m_tiles * ceil_div(c16, g.BN) * 2 <= 148) {
-      const int n_wanted = 148 / m_tiles;  // never more tiles than SMs: a second round costs more than it gains
+    if (m_tiles * ceil_div(c16, g.BN) * 2 <= sms) {
+      const int n_wanted = sms / m_tiles;  // never more tiles than SMs: a second round costs more than it gains
       int bn = (ceil_div(c16, n_wanted) + 15) / 16 * 16;
       if (bn < 32) bn = 32;
       if (bn < g.BN) g.BN = bn;
@@ -805,6 +809,7 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   return rdsic_launch_status();
 }
 
+#ifdef RDSIC_DEBUG
 // Profiling aid (not part of the public header): copies the issuer time stamps recorded under RDSIC_TC_DBG_TS.
 extern "C" int rdsic_debug_read_ts(long long* host, int n) {
   if (!g_dbg_ts || n > (g_dbg_host ? 16384 : 4096)) return -1;
@@ -815,3 +820,4 @@ extern "C" int rdsic_debug_read_ts(long long* host, int n) {
   cudaDeviceSynchronize();
   return (int)cudaMemcpy(host, g_dbg_ts, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost);
 }
+#endif

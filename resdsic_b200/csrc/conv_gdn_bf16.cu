@@ -709,6 +709,7 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   g.num_k_iters = d->KH * d->KW * g.kb_per_tap;
   g.b_stage_bytes = C * BK * 2;
   g.tmem_cols = 512;
+#ifdef RDSIC_DEBUG
   static const int dbg_skip = getenv("RDSIC_TC_DBG_SKIPG") ? atoi(getenv("RDSIC_TC_DBG_SKIPG")) : 0;
   g.dbg_skip_load = dbg_skip;
   {
@@ -724,6 +725,7 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
     }
     g.dbg_ts = ts_buf;
   }
+#endif
   GdnGeom gg;
   gg.N2 = N2;
   gg.k2_blocks = ceil_div(C, BK);
@@ -777,6 +779,7 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   if (encode_2d(&tb, d->weight, d->KH * d->KW * d->Cin, C) != CUDA_SUCCESS) return RDSIC_E_ARG;
   if (encode_2d(&tg, d->tail_weight, C, N2) != CUDA_SUCCESS) return RDSIC_E_ARG;
 
+#ifdef RDSIC_DEBUG
   {  // debug: barrier-timeout log (see tc_common.cuh)
     extern long long* g_dbg_ts;
     extern int g_dbg_host;
@@ -786,6 +789,7 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
       log_set = true;
     }
   }
+#endif
   const size_t smem = (size_t)stages * stage_bytes + gg.w2_bytes + (size_t)gg.na * g.a_halo_bytes + 1024 +
                       (2 * MAX_STAGES + 20) * 8 + 16 + 192 + 16 + 2 * MAXC * 4;
   auto kern = d->tail_mode == TAIL_RU ? conv_gdn_tc_kernel<TAIL_RU>

@@ -371,7 +371,7 @@ extern "C" int rdsic_eb_forward(const rdsic_eb_desc* d, rdsic_stream_t stream) {
   RDSIC_CHECK_ARG(!d->noise.ptr || (d->noise.dtype == RDSIC_F32 && !d->noise.nchw));
   RDSIC_CHECK_ARG(!d->noisy_out.ptr || (d->noise.ptr && d->noisy_out.dtype == RDSIC_F32 && !d->noisy_out.nchw));
   const size_t total = (size_t)d->B * d->h * d->w * d->C;
-  const int nblk = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  const int nblk = (int)((total + 255) / 256 < (size_t)rdsic_sm_count() * 8 ? (total + 255) / 256 : (size_t)rdsic_sm_count() * 8);
   eb_forward_kernel<<<nblk, 256, 0, (cudaStream_t)stream>>>(*d);
   return rdsic_launch_status();
 }

@@ -265,7 +265,7 @@ extern "C" int rdsic_patch_forward(const rdsic_patch_desc* d, rdsic_stream_t str
   }
   const size_t total = (size_t)d->B * d->OH * d->OW * (d->Kp / 8);
   const size_t want = (total + 255) / 256;
-  patchify_kernel<<<(unsigned)(want < 148 * 16 ? want : 148 * 16), 256, 0, (cudaStream_t)stream>>>(*d);
+  patchify_kernel<<<(unsigned)(want < (size_t)rdsic_sm_count() * 16 ? want : (size_t)rdsic_sm_count() * 16), 256, 0, (cudaStream_t)stream>>>(*d);
   return rdsic_launch_status();
 }
 

@@ -16,7 +16,6 @@ constexpr int NUM_EPI_WARPS = 12;                  // four warps per TMEM lane q
 constexpr int EPI_PARTS = NUM_EPI_WARPS / 4;       // column interleave factor between the warps of a quarter
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // TMA warp + MMA warp + epilogue warps
 constexpr int MAX_STAGES = 8;
-constexpr uint32_t SPIN_LIMIT = 1u << 22;  // a lost mbarrier signal traps instead of hanging the GPU
 
 struct TcGeom {
   int TH, TW, tiles_y, tiles_x;
@@ -48,13 +47,39 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Debug: host-mapped log for barrier timeouts (one copy per translation unit, set by tc_set_timeout_log).
+// Bounded mbarrier waits: a lost signal must not hang the GPU box, but a slow wait (profiler replay, debugger,
+// co-running kernels) must not kill the context either, so the limit is WALL TIME (%globaltimer, checked every
+// 2^14 failed probes), not an iteration count: after MBAR_TIMEOUT_NS the wait gives up with __trap().
+constexpr unsigned long long MBAR_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;  // 20 s (a forward step is ~20 ms)
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#ifdef RDSIC_DEBUG
+// Debug builds: host-mapped log for barrier timeouts (one copy per translation unit, set by tc_set_timeout_log).
 static __device__ long long* g_mbar_log = nullptr;
 static inline void tc_set_timeout_log(long long* p) { cudaMemcpyToSymbol(g_mbar_log, &p, sizeof(p)); }
+#endif
 
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
+__device__ __noinline__ void mbar_timeout(uint32_t addr, uint32_t parity) {
+#ifdef RDSIC_DEBUG
+  if (g_mbar_log && (threadIdx.x & 31) == 0) {
+    volatile long long* rec = g_mbar_log + 4 + ((blockIdx.x % 148) * 16 + (threadIdx.x / 32)) * 4;
+    rec[0] = 100;
+    rec[1] = ((long long)blockIdx.x << 32) | (threadIdx.x / 32);
+    rec[2] = addr;
+    rec[3] = parity;
+    __threadfence_system();
+    __nanosleep(2000000);
+  }
+#endif
+  __trap();
+}
+
+__device__ __forceinline__ void mbar_wait_u32(uint32_t addr, uint32_t parity) {  // shared-window address
   uint32_t done = 0, spins = 0;
+  unsigned long long t0 = 0;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -64,34 +89,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) break;
-    if (++spins > SPIN_LIMIT) {
-      if (g_mbar_log && (threadIdx.x & 31) == 0) {
-        volatile long long* rec = g_mbar_log + 4 + ((blockIdx.x % 148) * 16 + (threadIdx.x / 32)) * 4;
-        rec[0] = 100;
-        rec[1] = ((long long)blockIdx.x << 32) | (threadIdx.x / 32);
-        rec[2] = addr;
-        rec[3] = parity;
-        __threadfence_system();
-        __nanosleep(2000000);
-      }
-      __trap();
+    if ((++spins & 0x3FFFu) == 0) {
+      const unsigned long long now = globaltimer_ns();
+      if (!t0) t0 = now;
+      else if (now - t0 > MBAR_TIMEOUT_NS) mbar_timeout(addr, parity);
     }
   }
 }
-__device__ __forceinline__ void mbar_wait_u32(uint32_t addr, uint32_t parity) {  // shared-window address variant
-  uint32_t done = 0, spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins > SPIN_LIMIT) __trap();
-  }
-}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_u32(smem_u32(bar), parity); }
 // One lane of a converged warp (elect.sync).  The TMA / MMA loops are run by their WHOLE warp in uniform
 // control flow and only the issue itself is predicated: a loop entered by a single lane is divergent code,
 // where the compiler cannot use uniform registers and wraps every UTCHMMA / UTMALDG operand in an

@@ -56,6 +56,16 @@ class Ctx:
         return out
 
 
+def _tree_to(obj, dev):
+    if torch.is_tensor(obj):
+        return obj.to(dev)
+    if isinstance(obj, (tuple, list)):
+        return type(obj)(_tree_to(o, dev) for o in obj)
+    if isinstance(obj, dict):
+        return {k: _tree_to(v, dev) for k, v in obj.items()}
+    return obj
+
+
 class B200Module(nn.Module):
     """nn.Module whose compute is a resdsic_b200 program."""
 
@@ -68,6 +78,12 @@ class B200Module(nn.Module):
                 m.precision = precision
         return self
 
+    # Weight packing is one-time host-side preprocessing.  With `pack_on_host` (default) the layout transforms run on
+    # CPU copies of the parameters and only the packed result is copied to the device, so that no ATen kernel is
+    # launched on the GPU on behalf of this package (every GPU launch of an inference process is then one of the
+    # library's own kernels).  Training re-packs after every optimiser step and sets it False (device-side packing).
+    pack_on_host = True
+
     # -- packed-weight cache, invalidated when a parameter changes version/storage/device
     def _packed(self, tag, tensors, fn):
         key = (tag,) + tuple((t.data_ptr(), t._version, str(t.device), t.dtype) for t in tensors)
@@ -75,9 +91,27 @@ class B200Module(nn.Module):
         hit = cache.get(tag)
         if hit is None or hit[0] != key:
             with torch.no_grad():
-                hit = (key, fn())
+                dev = tensors[0].device
+                if B200Module.pack_on_host and dev.type == "cuda":
+                    hit = (key, _tree_to(self._call_on_host(fn), dev))
+                else:
+                    hit = (key, fn())
             cache[tag] = hit
         return hit[1]
+
+    def _call_on_host(self, fn):
+        """Run `fn` with this module's own parameters / buffers temporarily replaced by CPU copies."""
+        saved = []
+        for store in (self._parameters, self._buffers):
+            for name, t in list(store.items()):
+                if t is not None and t.device.type == "cuda":
+                    saved.append((store, name, t))
+                    store[name] = t.detach().cpu()
+        try:
+            return fn()
+        finally:
+            for store, name, t in saved:
+                store[name] = t
 
     def emit(self, ctx: Ctx, x: TV, **kw) -> TV:  # pragma: no cover - interface
         raise NotImplementedError

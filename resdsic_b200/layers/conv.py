@@ -13,6 +13,21 @@ from .. import _lib, packing
 from .base import B200Module, Ctx
 
 
+def _default_conv_init(weight, bias):
+    """The reference's EFFECTIVE init.  `CompressionModel.__init__` calls `_initialize_weights()` (the
+    Kaiming-normal / zero-bias loop, WACNN/base.py:19-20,29-34) from `super().__init__()` at cnn.py:26-27,
+    i.e. BEFORE any sub-module exists, so that loop visits nothing and every nn.Conv2d / nn.ConvTranspose2d
+    keeps torch's `reset_parameters()` default: kaiming_uniform_(a=sqrt(5)) weights and U(+-1/sqrt(fan_in))
+    biases.  Same calls in the same order as torch's `_ConvNd.reset_parameters`, so that under one
+    `torch.manual_seed` this constructor draws the reference constructor's weights bit for bit
+    (tests/test_refinit.py)."""
+    nn.init.kaiming_uniform_(weight, a=math.sqrt(5))
+    fan_in, _ = nn.init._calculate_fan_in_and_fan_out(weight)
+    if fan_in != 0:
+        bound = 1 / math.sqrt(fan_in)
+        nn.init.uniform_(bias, -bound, bound)
+
+
 class Conv2d(B200Module):
     """nn.Conv2d(in, out, k, stride, padding=k//2) with bias."""
 
@@ -25,9 +40,7 @@ class Conv2d(B200Module):
         self.padding = kernel_size // 2 if padding is None else padding
         self.weight = nn.Parameter(torch.empty(out_channels, in_channels, kernel_size, kernel_size))
         self.bias = nn.Parameter(torch.empty(out_channels))
-        # reference init: kaiming_normal_ weights, zero bias (WACNN/base.py:29-34)
-        nn.init.kaiming_normal_(self.weight)
-        nn.init.zeros_(self.bias)
+        _default_conv_init(self.weight, self.bias)
 
     def packed(self, wdt):
         return self._packed(("w", wdt), (self.weight, self.bias), lambda: (
@@ -106,8 +119,7 @@ class ConvTranspose2d(B200Module):
         self.in_channels, self.out_channels = in_channels, out_channels
         self.weight = nn.Parameter(torch.empty(in_channels, out_channels, 5, 5))
         self.bias = nn.Parameter(torch.empty(out_channels))
-        nn.init.kaiming_normal_(self.weight)
-        nn.init.zeros_(self.bias)
+        _default_conv_init(self.weight, self.bias)
 
     def packed(self, wdt):
         return self._packed(("w", wdt), (self.weight, self.bias), lambda: (

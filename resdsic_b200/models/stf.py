@@ -93,9 +93,7 @@ class SymmetricalTransFormer(WACNN):
         self.lrp_transforms = nn.ModuleList(_cc3(M + sc * min(i + 1, S + 1)) for i in range(num_slices))
         self.entropy_bottleneck = EntropyBottleneck(N)
         self.gaussian_conditional = GaussianConditional(None)
-        self.use_cuda_graph = True
-        self.micro_batches = 1
-        self._plans = {}
+        self._init_runtime()  # plans, noise_override, decoder plans ... (everything WACNN's forward / train / decode paths use)
 
     @classmethod
     def from_state_dict(cls, state_dict):

@@ -104,7 +104,17 @@ class WACNN(CompressionModel):
         self.lrp_transforms = nn.ModuleList(_cc_stack(320 + 32 * min(i + 1, 6)) for i in range(10))
         self.entropy_bottleneck = EntropyBottleneck(N)
         self.gaussian_conditional = GaussianConditional(None)
+        self._init_runtime()
+
+    MAX_PLANS = 4  # live forward plans (LRU); each owns the activation buffers + CUDA graph of one shape / mode
+
+    def _init_runtime(self):
+        """Host-side execution state (no parameters): shared by every model built on this class."""
         self.use_cuda_graph = True
+        # forward() returns FRESH tensors by default, like the reference module.  `static_outputs = True` hands
+        # out the plan's own output buffers instead (no copies; overwritten by the next forward of the same
+        # shape) -- the opt-in used by ForwardPipeline / bench.py, which snapshot or consume results at once.
+        self.static_outputs = False
         # Optionally a batch is run as `micro_batches` equal sub-batches, each its own program / CUDA graph on
         # its own stream (idea: the slice loop is a chain of ~110 small dependent launches that leaves SMs idle,
         # another sub-batch's large g_a / g_s launches could fill them).  Measured on B200 at batch 16: 1 -> 1239,
@@ -117,8 +127,9 @@ class WACNN(CompressionModel):
         # {"y": [B,320,H/16,W/16], "z": [B,192,H/64,W/64]} injects given tensors instead (parity tests).
         # There is no autograd through the CUDA kernels: the backward pass of BASELINE config 4 is not ported.
         self.noise_override = None
-        self._plans = {}
-        self._dec_plans = {}  # decoder-side plans (slice_decoder), separate so that encode / decode can alternate
+        from collections import OrderedDict
+        self._plans = OrderedDict()      # LRU: alternating forward / compress, train / eval or two image sizes
+        self._dec_plans = OrderedDict()  # must not rebuild ~300 descriptors and re-capture a graph on every call
 
     # ------------------------------------------------------------------ API
     @classmethod
@@ -190,34 +201,55 @@ class WACNN(CompressionModel):
         if not z_hat.is_cuda:
             raise RuntimeError("resdsic_b200 runs on CUDA devices only (no CPU fallback)")
         B, _, hz, wz = z_hat.shape
-        key = ("dec", B, hz, wz, str(z_hat.device), self.precision, self._weights_key())
-        plan = self._dec_plans.get(key)
-        if plan is None:
-            self._dec_plans.clear()  # one live decoder plan, kept next to the forward plan
-            plan = self._build_decoder(B, hz, wz, z_hat.device)
-            self._dec_plans[key] = plan
+        key = ("dec", B, hz, wz, str(z_hat.device), self.precision, self._weights_key())  # weights key LAST
+        plan = self._lru_get(self._dec_plans, key, lambda: self._build_decoder(B, hz, wz, z_hat.device), 2)
         return SliceDecoder(self, plan, z_hat)
 
     # ------------------------------------------------------------- planning
     def _weights_key(self):
-        return tuple(p._version for p in self.parameters())
+        """Identity of everything a plan bakes in: every parameter AND buffer (e.g. the Gaussian conditional's
+        scale table, which `update(scale_table=...)` replaces) by storage pointer and version counter.  In-place
+        edits through `.data` bump neither: call `invalidate_plans()` after those."""
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def invalidate_plans(self):
+        """Drop every cached plan / packed weight (after editing weights through `.data` or similar)."""
+        self._plans.clear()
+        self._dec_plans.clear()
+        for m in self.modules():
+            m.__dict__.pop("_pack_cache", None)
+
+    def _lru_get(self, cache, key, build, cap):
+        plan = cache.get(key)
+        if plan is None:
+            # plans of stale weights can never be hit again: drop them first, then the least recently used
+            wk = key[-1]
+            for k in [k for k in cache if k[-1] != wk]:
+                del cache[k]
+            while len(cache) >= cap:
+                cache.popitem(last=False)
+            plan = build()
+            cache[key] = plan
+        else:
+            cache.move_to_end(key)
+        return plan
 
     def _plan(self, B, H, W, device, with_symbols):
         if H % 64 or W % 64:
             raise ValueError(f"input {H}x{W} must be a multiple of 64 (pad as eval_model/__main__.py:89-101 does; "
                              "see resdsic_b200.utils.pad_to_multiple)")
         mb = 1 if self.training else self._num_micro_batches(B)
-        key = (B, H, W, str(device), self.precision, with_symbols, self._weights_key(), mb, bool(self.training))
-        plan = self._plans.get(key)
-        if plan is None:
-            self._plans.clear()  # one live forward plan: buffers are sized for one shape
+        key = (B, H, W, str(device), self.precision, with_symbols, mb, bool(self.training), self._weights_key())
+
+        def build():
             if mb == 1:
                 plan = self._build(B, H, W, device, with_symbols)
                 plan.subs, plan.sub_batch = [plan], B
-            else:
-                plan = self._build_micro(B, H, W, device, with_symbols, mb)
-            self._plans[key] = plan
-        return plan
+                return plan
+            return self._build_micro(B, H, W, device, with_symbols, mb)
+
+        self._last_plan = self._lru_get(self._plans, key, build, self.MAX_PLANS)
+        return self._last_plan
 
     def _num_micro_batches(self, B):
         mb = self.micro_batches
@@ -522,10 +554,13 @@ class WACNN(CompressionModel):
     @torch.no_grad()
     def forward(self, x):
         """reference cnn.py:143-193 (eval mode, or the forward values of training mode -- see
-        `noise_override`).  The returned tensors are the plan's static
-        output buffers: clone them if they must survive the next forward()."""
+        `noise_override`).  Returns fresh tensors, like the reference (see `static_outputs`)."""
         p = self._execute(x, False)
-        return {"x_hat": p.x_hat, "likelihoods": {"y": p.lik_y, "z": p.lik_z}}
+        o = self._out
+        return {"x_hat": o(p.x_hat), "likelihoods": {"y": o(p.lik_y), "z": o(p.lik_z)}}
+
+    def _out(self, t):
+        return t if (self.static_outputs or t is None) else t.clone()
 
     @torch.no_grad()
     def symbols_and_indexes(self, x):
@@ -533,8 +568,9 @@ class WACNN(CompressionModel):
         symbols/indexes for y (all 10 slices, NCHW [B,320,h,w]) and the z symbols,
         in contiguous device buffers (one D2H copy instead of 20 `.tolist()` syncs)."""
         p = self._execute(x, True)
-        return {"y_symbols": p.symbols, "y_indexes": p.indexes, "z_symbols": p.z_symbols,
-                "x_hat": p.x_hat, "likelihoods": {"y": p.lik_y, "z": p.lik_z}, "shape": (p.z.H, p.z.W)}
+        o = self._out
+        return {"y_symbols": o(p.symbols), "y_indexes": o(p.indexes), "z_symbols": o(p.z_symbols),
+                "x_hat": o(p.x_hat), "likelihoods": {"y": o(p.lik_y), "z": o(p.lik_z)}, "shape": (p.z.H, p.z.W)}
 
 
 class SliceDecoder:

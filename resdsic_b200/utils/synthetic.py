@@ -344,3 +344,38 @@ def synth_state_dict(reference_sd, seed: int = 0, gains=_STF_GAINS):
         assert tuple(t.shape) == shape, (name, t.shape, shape)
         sd[name] = t.to(ref.dtype).contiguous()
     return sd
+
+
+# --------------------------------------------------------------------------
+# "refinit": the reference constructor's own random init (north_star: parity on random-init weights)
+# --------------------------------------------------------------------------
+def refinit_model(seed: int = 0, N=192, M=320):
+    """`resdsic_b200.WACNN(N, M)` constructed under `torch.manual_seed(seed)` on the CPU generator.  The
+    constructor makes the same init calls in the same order as the reference's (`cnn.py:26-132`; its Kaiming
+    loop is a no-op, see layers/conv.py:_default_conv_init), so this draws the SAME 75 M weights as
+    `torch.manual_seed(seed); compress.models.WACNN(N, M)` -- asserted tensor for tensor against the imported
+    reference by tests/golden/make_golden_refinit.py, and pinned on any host by the checksums that script
+    commits (tests/test_refinit.py).  The caller's global RNG state is preserved."""
+    from ..models import WACNN
+    with torch.random.fork_rng(devices=[]):
+        torch.manual_seed(seed)
+        return WACNN(N=N, M=M)
+
+
+def refinit_state_dict(seed: int = 0, N=192, M=320):
+    return OrderedDict((k, v.detach().clone()) for k, v in refinit_model(seed, N, M).state_dict().items())
+
+
+def rand_image(B, H, W, seed: int = 1) -> torch.Tensor:
+    """`torch.rand(B,3,H,W)` (the synthetic input of the BASELINE configs) from a private CPU
+    generator, i.e. independent of the global RNG state."""
+    g = torch.Generator().manual_seed(int(seed))
+    return torch.rand(B, 3, H, W, generator=g)
+
+
+def tensor_checksum(t) -> np.ndarray:
+    """Three exact-ish numbers pinning a tensor's contents (float64 sum, strided abs-sum, last element)."""
+    t = t.detach().double().reshape(-1)
+    if t.numel() == 0:
+        return np.zeros(3)
+    return np.array([t.sum().item(), t[:: max(1, t.numel() // 7)][:7].abs().sum().item(), float(t[-1])])

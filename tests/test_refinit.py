@@ -1,0 +1,172 @@
+"""Parity on the reference's OWN random init (BASELINE.json north_star: "identical inputs and random-init
+weights").  tests/golden/make_golden_refinit.py ran the unmodified reference constructor under
+`torch.manual_seed(0)` and its forward on `torch.rand` images; here
+
+* CPU: the repo's constructor re-creates those weights (checksums), the oracle reproduces the reference outputs;
+* GPU: the CUDA forward meets the UN-RELAXED contract on every BASELINE inference configuration --
+  fp32: symbols / CDF indexes bit-exact, x_hat to 1e-5;  bf16: x_hat <= 1e-2 max abs, per-image bpp within
+  0.1 %, PSNR within 0.02 dB (tolerances exactly as BASELINE.json states them).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import resdsic_b200
+from oracle import wacnn_oracle as O
+from oracle import weights
+from tests.conftest import GOLDEN
+from tests.helpers import bpp_of
+
+DEV = "cuda:0"
+X_TOL, BPP_TOL, PSNR_TOL = 1e-2, 1e-3, 0.02  # BASELINE.json north_star, bf16 mode
+
+
+@pytest.fixture(scope="module")
+def refinit_sd():
+    return weights.refinit_state_dict(0)
+
+
+def _golden(name):
+    return np.load(os.path.join(GOLDEN, f"refinit_{name}.npz"))
+
+
+def _psnr(a, x):
+    return float(-10 * np.log10(((np.asarray(a, np.float64) - np.asarray(x, np.float64)) ** 2).mean()))
+
+
+def test_constructor_draws_the_reference_init(refinit_sd):
+    """Same init calls in the same order as the reference constructor (whose Kaiming loop is a no-op): the
+    checksums were taken from the reference's own state_dict, which make_golden_refinit.py asserted bit-equal."""
+    g = _golden("c256")
+    names = [k[3:] for k in g.files if k.startswith("ck:") and k != "ck:__total__"]
+    assert len(names) >= 15
+    for n in names:
+        np.testing.assert_array_equal(weights.tensor_checksum(refinit_sd[n]), g["ck:" + n], err_msg=n)
+    total = sum(float(v.double().sum()) for v in refinit_sd.values() if v.is_floating_point())
+    assert total == float(g["ck:__total__"][0])
+    w = refinit_sd["g_a.0.weight"]
+    assert abs(float(w.std()) - 0.0667) < 1e-3 and float(refinit_sd["g_a.0.bias"].abs().max()) > 0.05  # not Kaiming-normal / zero
+    np.testing.assert_array_equal(weights.tensor_checksum(weights.rand_image(2, 256, 256, seed=1)), g["x_ck"])
+    # the global RNG is left alone
+    torch.manual_seed(123)
+    a = torch.rand(3)
+    torch.manual_seed(123)
+    weights.refinit_state_dict(0)
+    assert torch.equal(torch.rand(3), a)
+
+
+def test_oracle_vs_reference_on_reference_init_config1(refinit_sd, scale_table):
+    """BASELINE config 1 (2 x 3 x 256 x 256, CPU): the oracle against the reference's outputs."""
+    g = _golden("c256")
+    x = weights.rand_image(2, 256, 256, seed=1)
+    ref = O.forward(refinit_sd, x, scale_table, collect=True)
+    assert np.array_equal(ref["symbols"].numpy(), g["symbols"]) and np.array_equal(ref["indexes"].numpy(), g["indexes"])
+    np.testing.assert_allclose(ref["x_hat"].numpy(), g["x_hat"], atol=2e-6, rtol=0)
+    np.testing.assert_allclose(ref["y"].numpy(), g["y"], atol=2e-6, rtol=0)
+    np.testing.assert_allclose(ref["likelihoods"]["y"].numpy(), g["lik_y"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(ref["likelihoods"]["z"].numpy(), g["lik_z"], rtol=1e-5, atol=1e-9)
+    for b in range(2):
+        got = bpp_of(ref["likelihoods"]["y"][b].numpy(), ref["likelihoods"]["z"][b].numpy(), 256 * 256)
+        assert abs(got - g["bpp"][b]) <= 1e-6 * g["bpp"][b]
+
+
+# ----------------------------------------------------------------------------- GPU
+@pytest.fixture(scope="module")
+def model(refinit_sd):
+    m = resdsic_b200.WACNN().eval()
+    m.load_state_dict(refinit_sd, strict=True)
+    return m.to(DEV)
+
+
+def _run(model, x, prec):
+    model.set_precision(prec)
+    r = model.symbols_and_indexes(x.to(DEV))
+    return dict(x_hat=r["x_hat"].cpu().numpy(), lik_y=r["likelihoods"]["y"].cpu().numpy(),
+                lik_z=r["likelihoods"]["z"].cpu().numpy(), symbols=r["y_symbols"].cpu().numpy(),
+                indexes=r["y_indexes"].cpu().numpy(), z_symbols=r["z_symbols"].cpu().numpy())
+
+
+def _check_contract(tag, got_xhat, got_ly, got_lz, ref_xhat, ref_bpp, ref_psnr, x, n_pix, x_tol):
+    """Per image: |x_hat - ref| max, bpp relative error, PSNR difference -- asserted at the BASELINE tolerances."""
+    for b in range(x.shape[0]):
+        dx = float(np.abs(got_xhat[b] - ref_xhat[b]).max())
+        bpp = bpp_of(got_ly[b], got_lz[b], n_pix)
+        d_bpp = abs(bpp - ref_bpp[b]) / ref_bpp[b]
+        d_psnr = abs(_psnr(got_xhat[b], x[b].numpy()) - ref_psnr[b])
+        print(f"{tag} img {b}: x_hat max abs {dx:.3e}  bpp {bpp:.6f} (ref {ref_bpp[b]:.6f}, rel {d_bpp:.2e})  dPSNR {d_psnr:.2e} dB")
+        assert dx <= x_tol, (tag, b, dx)
+        assert d_bpp <= BPP_TOL, (tag, b, d_bpp)
+        assert d_psnr <= PSNR_TOL, (tag, b, d_psnr)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_config1_vs_reference_golden(model, prec):
+    """BASELINE config 1: 2 x 3 x 256 x 256 against the reference's own outputs."""
+    g = _golden("c256")
+    x = weights.rand_image(2, 256, 256, seed=1)
+    got = _run(model, x, prec)
+    if prec == "fp32":
+        assert np.array_equal(got["symbols"], g["symbols"]) and np.array_equal(got["indexes"], g["indexes"])
+    else:  # integer outputs may legitimately differ where bf16 moves a value across a threshold: bounded, reported
+        print("bf16 symbol flips", (got["symbols"] != g["symbols"]).mean(), "index flips", (got["indexes"] != g["indexes"]).mean())
+        assert (got["symbols"] != g["symbols"]).mean() <= 1e-3
+    _check_contract(f"config1[{prec}]", got["x_hat"], got["lik_y"], got["lik_z"], g["x_hat"], g["bpp"], g["psnr"], x,
+                    256 * 256, 1e-5 if prec == "fp32" else X_TOL)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_config3_kodak_shape_vs_reference_golden(model, prec):
+    """BASELINE config 3's shape (1 x 3 x 512 x 768): reference x_hat on a 4x4 sub-grid, likelihoods in full."""
+    g = _golden("kodak")
+    x = weights.rand_image(1, 512, 768, seed=1)
+    got = _run(model, x, prec)
+    if prec == "fp32":
+        assert np.array_equal(got["symbols"], g["symbols"]) and np.array_equal(got["indexes"], g["indexes"])
+    sub = got["x_hat"][:, :, ::4, ::4]
+    dx = float(np.abs(sub - g["x_hat_sub"]).max())
+    bpp = bpp_of(got["lik_y"][0], got["lik_z"][0], 512 * 768)
+    d_psnr = abs(_psnr(got["x_hat"][0], x[0].numpy()) - g["psnr"][0])
+    print(f"config3[{prec}] x_hat max abs {dx:.3e} bpp {bpp:.6f} ref {g['bpp'][0]:.6f} dPSNR {d_psnr:.2e}")
+    assert dx <= (1e-5 if prec == "fp32" else X_TOL)
+    assert abs(bpp - g["bpp"][0]) <= BPP_TOL * g["bpp"][0] and d_psnr <= PSNR_TOL
+
+
+def _vs_oracle(model, refinit_sd, scale_table, x, tag, with_symbols=True):
+    ref = O.forward(refinit_sd, x, scale_table, collect=with_symbols)
+    n = x.shape[2] * x.shape[3]
+    B = x.shape[0]
+    ref_bpp = [bpp_of(ref["likelihoods"]["y"][b].numpy(), ref["likelihoods"]["z"][b].numpy(), n) for b in range(B)]
+    ref_psnr = [_psnr(ref["x_hat"][b].numpy(), x[b].numpy()) for b in range(B)]
+    got = _run(model, x, "bf16")
+    _check_contract(tag, got["x_hat"], got["lik_y"], got["lik_z"], ref["x_hat"].numpy(), ref_bpp, ref_psnr, x, n, X_TOL)
+    if with_symbols:
+        flips = (got["symbols"] != ref["symbols"].numpy()).mean()
+        print(tag, "symbol flips", flips, "index flips", (got["indexes"] != ref["indexes"].numpy()).mean())
+        assert flips <= 1e-3
+    return got, ref
+
+
+@pytest.mark.gpu
+def test_config2_batch16_256_bf16_vs_oracle(model, refinit_sd, scale_table):
+    """BASELINE config 2: 16 x 3 x 256 x 256 in bf16 on one B200, every image against the oracle."""
+    _vs_oracle(model, refinit_sd, scale_table, weights.rand_image(16, 256, 256, seed=2), "config2[bf16]")
+
+
+@pytest.mark.gpu
+def test_config3_batch_bf16_vs_oracle(model, refinit_sd, scale_table):
+    """The benchmark's workload shape (512 x 768 images, bf16) against the oracle, several images."""
+    _vs_oracle(model, refinit_sd, scale_table, weights.rand_image(3, 512, 768, seed=3), "config3[bf16]")
+
+
+@pytest.mark.gpu
+def test_config5_clic_bf16_vs_oracle(model, refinit_sd, scale_table):
+    """BASELINE config 5: 1 x 3 x 1365 x 2048 -> pad rule -> 1408 x 2048, bf16 forward + index build vs the oracle."""
+    from resdsic_b200.utils import pad_to_multiple
+    xp, pad = pad_to_multiple(weights.rand_image(1, 1365, 2048, seed=4), 64)
+    assert xp.shape[-2:] == (1408, 2048) and pad == (0, 0, 21, 22)
+    got, ref = _vs_oracle(model, refinit_sd, scale_table, xp.contiguous(), "config5[bf16]")
+    assert got["indexes"].min() >= 0 and got["indexes"].max() <= 63

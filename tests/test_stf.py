@@ -70,7 +70,7 @@ def test_stf_forward_gpu_vs_oracle(stf, precision):
     x = weights.make_image(2, 128, 192, seed=9)
     ref = _as_golden(S.forward(sd, x, table, collect=True))
     r = m.symbols_and_indexes(x.to(dev))
-    p = next(iter(m._plans.values()))
+    p = m._last_plan
     got = _collect(p, m.M)
     assert r["x_hat"].shape == (2, 3, 128, 192) and r["likelihoods"]["y"].shape == (2, 384, 8, 12)
     if precision == "fp32":

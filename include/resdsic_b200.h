@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define RDSIC_ABI_VERSION 3
+#define RDSIC_ABI_VERSION 4
 
 typedef void* rdsic_stream_t; /* cudaStream_t */
 
@@ -60,7 +60,9 @@ enum {
 
 /* One tensor view: NHWC element (b,y,x,c) lives at
  * ptr[((b*H + y)*W + x)*ld + coff + c]; with nchw != 0 it is
- * ptr[((b*C + c)*H + y)*W + x] (ld/coff ignored, C = channel count of the op). */
+ * ptr[((b*C + c)*H + y)*W + x] (ld/coff ignored, C = channel count of the op) -- except in
+ * rdsic_copy_forward, where an NCHW view may address a channel range of a wider tensor:
+ * ptr[((b*ld + coff + c)*H + y)*W + x] with ld = channel count of the underlying tensor (0 = C). */
 typedef struct rdsic_view {
   void* ptr;
   int32_t dtype; /* RDSIC_F32 | RDSIC_BF16 */
@@ -174,14 +176,35 @@ typedef struct rdsic_gc_desc {
    * channel offset as `symbols`) instead of being computed from y, i.e. y_hat = float(sym_in) + mu; y is ignored
    * (may be NULL).  lik then is the likelihood of the decoded symbol. */
   const int32_t* sym_in;
+  /* ResDSIC progressive stream (scalable/single_decoder.py:447-453): with mask.ptr != NULL (fp32 view like y,
+   * values 0/1 after Mask.apply_noise's round, layers/mask_layer.py:32-39) the conditional is evaluated with
+   * scale * mask, the stored y_hat is rint(y - mu) * mask + mu and symbols = int(rint(y - mu) * mask); the
+   * likelihood is still taken at rint(y - mu) + mu, as `gaussian_conditional_prog(y, scale * mask, mu)` does. */
+  rdsic_view mask;
 } rdsic_gc_desc;
+
+/* ResDSIC importance mask (layers/mask_layer.py:41-107, eval mode: Mask.forward followed by apply_noise's round).
+ *   mode 1 "learnable-mask-gamma":  mask = rint(pow(sigmoid(in[0]), gamma[c]))        (:64-90; gamma[c] =
+ *          relu(sum of the first scalable_levels-1-pr rows of Mask.gamma) + 1e-7, computed by the caller)
+ *   mode 2 "learnable-mask-nested": mask = rint(sigmoid(sum_i sigmoid(in[i])))         (:92-107, n_in = pr)
+ * in[i] are the fp32 outputs of Mask.mask_conv (1x1 convolutions over cat(scale, scale_prog)). */
+typedef struct rdsic_mask_desc {
+  rdsic_view in[8];
+  rdsic_view out;      /* fp32 [B,H,W,C] */
+  const float* gamma;  /* [C] fp32 (mode 1) */
+  int32_t n_in, mode;
+  int32_t B, H, W, C;
+} rdsic_mask_desc;
 
 /* Layout / elementwise helpers used by the standalone module API. */
 typedef struct rdsic_copy_desc {
   rdsic_view src;
   rdsic_view dst;
   int32_t B, H, W, C;
-  int32_t op; /* 0 copy/cast, 1 gelu, 2 square, 3 clamp to [0,1] (decompress: x_hat.clamp_(0, 1), cnn.py:340) */
+  int32_t op; /* 0 copy/cast, 1 gelu, 2 square, 3 clamp to [0,1] (decompress: x_hat.clamp_(0, 1), cnn.py:340),
+                 4 dst = src + src2 (ResDSIC: y_hat_complete = y_hat + y_hat_prog, scalable/single_decoder.py:472) */
+  int32_t pad_;
+  rdsic_view src2; /* op 4 only; same geometry as src */
 } rdsic_copy_desc;
 
 /* LayerNorm over channels (stf Swin block, TCM/tcm.py:214-236). */
@@ -205,7 +228,7 @@ typedef struct rdsic_patch_desc {
 } rdsic_patch_desc;
 
 enum { RDSIC_OP_CONV = 0, RDSIC_OP_ATTN = 1, RDSIC_OP_EB = 2, RDSIC_OP_GC = 3, RDSIC_OP_COPY = 4, RDSIC_OP_LN = 5, RDSIC_OP_PATCH = 6,
-       RDSIC_OP_FORK = 7, RDSIC_OP_JOIN = 8, RDSIC_OP_RECORD = 9, RDSIC_OP_WAIT = 10 };
+       RDSIC_OP_FORK = 7, RDSIC_OP_JOIN = 8, RDSIC_OP_RECORD = 9, RDSIC_OP_WAIT = 10, RDSIC_OP_MASK = 11 };
 
 /* One node of a forward "program" (WACNN.forward, cnn.py:143-193, is ~330 of these). */
 /* Independent branches (cc_mean || cc_scale, h_mean_s || h_scale_s, conv_a || conv_b, the context stacks of
@@ -235,13 +258,14 @@ typedef struct rdsic_op {
     rdsic_ln_desc ln;
     rdsic_patch_desc patch;
     rdsic_sync_desc sync;
+    rdsic_mask_desc mask;
   } u;
 } rdsic_op;
 
 int rdsic_abi_version(void);
 const char* rdsic_error_string(int code);
 /* sizeof(rdsic_op) etc., so the host binding can verify its struct mirror. */
-int rdsic_sizeof(int what); /* 0 op, 1 conv, 2 attn, 3 eb, 4 gc, 5 copy, 6 view, 7 ln, 8 patch */
+int rdsic_sizeof(int what); /* 0 op, 1 conv, 2 attn, 3 eb, 4 gc, 5 copy, 6 view, 7 ln, 8 patch, 9 mask */
 
 int rdsic_conv_forward(const rdsic_conv_desc* d, rdsic_stream_t stream);
 int rdsic_attn_forward(const rdsic_attn_desc* d, rdsic_stream_t stream);
@@ -281,6 +305,7 @@ int rdsic_pmf_to_quantized_cdf(const float* prob, int32_t ld, const int32_t* cdf
 int rdsic_copy_forward(const rdsic_copy_desc* d, rdsic_stream_t stream);
 int rdsic_ln_forward(const rdsic_ln_desc* d, rdsic_stream_t stream);
 int rdsic_patch_forward(const rdsic_patch_desc* d, rdsic_stream_t stream);
+int rdsic_mask_forward(const rdsic_mask_desc* d, rdsic_stream_t stream);
 
 /* Launch a whole program in order on `stream`.  *n_launched (optional) receives
  * the number of kernels launched.  Stops at the first error; *failed_op

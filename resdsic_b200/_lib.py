@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("RDSIC_LIB_PATH") or os.path.join(_PKG, "lib", "libres
 
 F32, BF16 = 0, 1
 EPI_NONE, EPI_GELU, EPI_RES_GELU, EPI_ADD_RES, EPI_GATE, EPI_GDN, EPI_IGDN, EPI_LRP = range(8)
-OP_CONV, OP_ATTN, OP_EB, OP_GC, OP_COPY, OP_LN, OP_PATCH, OP_FORK, OP_JOIN, OP_RECORD, OP_WAIT = range(11)
+OP_CONV, OP_ATTN, OP_EB, OP_GC, OP_COPY, OP_LN, OP_PATCH, OP_FORK, OP_JOIN, OP_RECORD, OP_WAIT, OP_MASK = range(12)
 SYNC_OPS = (OP_FORK, OP_JOIN, OP_RECORD, OP_WAIT)
 EB_STRIDE = 60
 
@@ -62,13 +62,18 @@ class GCDesc(C.Structure):
         ("n_table", C.c_int32),
         ("B", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("Cs", C.c_int32), ("Ctot", C.c_int32),
         ("lik_coff", C.c_int32), ("scale_bound", C.c_float), ("lik_bound", C.c_float),
-        ("pad_", C.c_int32), ("noise", View), ("noisy_out", View), ("sym_in", C.c_void_p),
+        ("pad_", C.c_int32), ("noise", View), ("noisy_out", View), ("sym_in", C.c_void_p), ("mask", View),
     ]
+
+
+class MaskDesc(C.Structure):
+    _fields_ = [("in_", View * 8), ("out", View), ("gamma", C.c_void_p), ("n_in", C.c_int32), ("mode", C.c_int32),
+                ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32)]
 
 
 class CopyDesc(C.Structure):
     _fields_ = [("src", View), ("dst", View), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
-                ("C", C.c_int32), ("op", C.c_int32)]
+                ("C", C.c_int32), ("op", C.c_int32), ("pad_", C.c_int32), ("src2", View)]
 
 
 class LNDesc(C.Structure):
@@ -92,7 +97,7 @@ MAX_EVENTS = 128
 
 class _OpUnion(C.Union):
     _fields_ = [("conv", ConvDesc), ("attn", AttnDesc), ("eb", EBDesc), ("gc", GCDesc), ("copy", CopyDesc),
-                ("ln", LNDesc), ("patch", PatchDesc), ("sync", SyncDesc)]
+                ("ln", LNDesc), ("patch", PatchDesc), ("sync", SyncDesc), ("mask", MaskDesc)]
 
 
 class Op(C.Structure):
@@ -103,7 +108,7 @@ EXPORTS = (
     "rdsic_abi_version", "rdsic_error_string", "rdsic_sizeof",
     "rdsic_conv_forward", "rdsic_attn_forward", "rdsic_eb_forward", "rdsic_gc_forward", "rdsic_eb_aux_loss",
     "rdsic_gc_cdf_sizes", "rdsic_gc_pmf", "rdsic_eb_cdf_sizes", "rdsic_eb_pmf", "rdsic_pmf_to_quantized_cdf",
-    "rdsic_copy_forward", "rdsic_ln_forward", "rdsic_patch_forward", "rdsic_run_program",
+    "rdsic_copy_forward", "rdsic_ln_forward", "rdsic_patch_forward", "rdsic_mask_forward", "rdsic_run_program",
     "rdsic_graph_create", "rdsic_graph_launch", "rdsic_graph_num_kernels", "rdsic_graph_destroy",
 )
 
@@ -128,7 +133,7 @@ def lib():
     L.rdsic_sizeof.argtypes = [C.c_int]
     for fn, T in (("rdsic_conv_forward", ConvDesc), ("rdsic_attn_forward", AttnDesc), ("rdsic_eb_forward", EBDesc),
                   ("rdsic_gc_forward", GCDesc), ("rdsic_copy_forward", CopyDesc), ("rdsic_ln_forward", LNDesc),
-                  ("rdsic_patch_forward", PatchDesc)):
+                  ("rdsic_patch_forward", PatchDesc), ("rdsic_mask_forward", MaskDesc)):
         getattr(L, fn).argtypes = [C.POINTER(T), C.c_void_p]
         getattr(L, fn).restype = C.c_int
     L.rdsic_eb_aux_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -145,9 +150,9 @@ def lib():
     L.rdsic_graph_num_kernels.argtypes = [C.c_void_p]
     L.rdsic_graph_destroy.argtypes = [C.c_void_p]
     L.rdsic_graph_destroy.restype = None
-    if L.rdsic_abi_version() != 3:
+    if L.rdsic_abi_version() != 4:
         raise RuntimeError("resdsic_b200: ABI version mismatch between the python host and the CUDA library")
-    for what, T in enumerate((Op, ConvDesc, AttnDesc, EBDesc, GCDesc, CopyDesc, View, LNDesc, PatchDesc)):
+    for what, T in enumerate((Op, ConvDesc, AttnDesc, EBDesc, GCDesc, CopyDesc, View, LNDesc, PatchDesc, MaskDesc)):
         if L.rdsic_sizeof(what) != C.sizeof(T):
             raise RuntimeError(f"resdsic_b200: struct mirror mismatch for {T.__name__}: "
                                f"C={L.rdsic_sizeof(what)} python={C.sizeof(T)}")

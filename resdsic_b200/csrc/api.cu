@@ -38,6 +38,7 @@ int rdsic_sizeof(int what) {
     case 6: return (int)sizeof(rdsic_view);
     case 7: return (int)sizeof(rdsic_ln_desc);
     case 8: return (int)sizeof(rdsic_patch_desc);
+    case 9: return (int)sizeof(rdsic_mask_desc);
     default: return -1;
   }
 }
@@ -71,6 +72,7 @@ static int run_one(const rdsic_op* op, rdsic_stream_t stream) {
     case RDSIC_OP_COPY: return rdsic_copy_forward(&op->u.copy, stream);
     case RDSIC_OP_LN: return rdsic_ln_forward(&op->u.ln, stream);
     case RDSIC_OP_PATCH: return rdsic_patch_forward(&op->u.patch, stream);
+    case RDSIC_OP_MASK: return rdsic_mask_forward(&op->u.mask, stream);
     default: return RDSIC_E_ARG;
   }
 }

@@ -106,7 +106,12 @@ __global__ void __launch_bounds__(256) gc_forward_kernel(const rdsic_gc_desc d) 
     const size_t pix = p0 + pp;
     if (pix >= npix || c >= d.Cs) continue;
     const float mu = ((const float*)d.mu.ptr)[pix * d.mu.ld + d.mu.coff + c];
-    const float sc = ((const float*)d.scale.ptr)[pix * d.scale.ld + d.scale.coff + c];
+    float sc = ((const float*)d.scale.ptr)[pix * d.scale.ld + d.scale.coff + c];
+    float msk = 1.f;
+    if (d.mask.ptr) {  // ResDSIC progressive stream: scale * mask, rint(y - mu) * mask + mu
+      msk = ((const float*)d.mask.ptr)[pix * d.mask.ld + d.mask.coff + c];
+      sc = __fmul_rn(sc, msk);
+    }
     float y = 0.f, r;
     if (d.sym_in) {  // decoder side: the symbol comes from the entropy decoder
       const size_t bb = pix / hw, yx = pix % hw;
@@ -115,8 +120,9 @@ __global__ void __launch_bounds__(256) gc_forward_kernel(const rdsic_gc_desc d) 
       y = ((const float*)d.y.ptr)[pix * d.y.ld + d.y.coff + c];
       r = rintf(__fsub_rn(y, mu));
     }
-    const float yh = __fadd_rn(r, mu);
-    float yl = yh;  // where the likelihood is evaluated: y_hat (eval) or y + noise (training)
+    const float rm = d.mask.ptr ? __fmul_rn(r, msk) : r;
+    const float yh = __fadd_rn(rm, mu);
+    float yl = __fadd_rn(r, mu);  // where the likelihood is evaluated: round(y - mu) + mu (eval) or y + noise (training)
     if (d.noise.ptr) {
       yl = __fadd_rn(y, ((const float*)d.noise.ptr)[pix * d.noise.ld + d.noise.coff + c]);
       if (d.noisy_out.ptr) ((float*)d.noisy_out.ptr)[pix * d.noisy_out.ld + d.noisy_out.coff + c] = yl;
@@ -136,7 +142,7 @@ __global__ void __launch_bounds__(256) gc_forward_kernel(const rdsic_gc_desc d) 
     for (int k = 0; k < 3; ++k)
       if (d.y_hat[k].ptr) st_elem(d.y_hat[k].ptr, d.y_hat[k].dtype, pix * d.y_hat[k].ld + d.y_hat[k].coff + c, yh);
     s_lik[tx][pp] = lik;
-    s_sym[tx][pp] = (int)r;
+    s_sym[tx][pp] = (int)rm;
     s_idx[tx][pp] = lo_i;
   }
   __syncthreads();
@@ -364,6 +370,41 @@ extern "C" int rdsic_eb_aux_loss(const float* params, const float* quantiles, co
   return rdsic_launch_status();
 }
 
+// ------------------------------------------------------------------ ResDSIC importance mask
+// layers/mask_layer.py:64-107 (eval: Mask.forward, then apply_noise's torch.round :37-38), elementwise over
+// channels-last fp32 logits.  torch.sigmoid / torch.pow / torch.round -> 1/(1+expf(-v)), powf, rintf.
+__global__ void __launch_bounds__(256) mask_forward_kernel(const rdsic_mask_desc d) {
+  const size_t total = (size_t)d.B * d.H * d.W * d.C;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t pix = e / d.C;
+    const int c = (int)(e % d.C);
+    float m;
+    if (d.mode == 1) {
+      const float v = ((const float*)d.in[0].ptr)[pix * d.in[0].ld + d.in[0].coff + c];
+      m = powf(__fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v))), d.gamma[c]);
+    } else {
+      float acc = 0.f;
+      for (int i = 0; i < d.n_in; ++i) {
+        const float v = ((const float*)d.in[i].ptr)[pix * d.in[i].ld + d.in[i].coff + c];
+        acc = __fadd_rn(acc, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v))));
+      }
+      m = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-acc)));
+    }
+    ((float*)d.out.ptr)[pix * d.out.ld + d.out.coff + c] = rintf(m);
+  }
+}
+
+extern "C" int rdsic_mask_forward(const rdsic_mask_desc* d, rdsic_stream_t stream) {
+  RDSIC_CHECK_ARG(d && d->out.ptr && d->out.dtype == RDSIC_F32 && !d->out.nchw);
+  RDSIC_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0 && d->C > 0 && (d->mode == 1 || d->mode == 2));
+  RDSIC_CHECK_ARG(d->n_in >= 1 && d->n_in <= 8 && (d->mode != 1 || (d->n_in == 1 && d->gamma)));
+  for (int i = 0; i < d->n_in; ++i) RDSIC_CHECK_ARG(d->in[i].ptr && d->in[i].dtype == RDSIC_F32 && !d->in[i].nchw);
+  const size_t total = (size_t)d->B * d->H * d->W * d->C;
+  const size_t want = (total + 255) / 256, cap = (size_t)rdsic_sm_count() * 8;
+  mask_forward_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(*d);
+  return rdsic_launch_status();
+}
+
 extern "C" int rdsic_eb_forward(const rdsic_eb_desc* d, rdsic_stream_t stream) {
   RDSIC_CHECK_ARG(d && d->z.ptr && d->z_hat.ptr && d->lik && d->params);
   RDSIC_CHECK_ARG(d->B > 0 && d->h > 0 && d->w > 0 && d->C > 0);
@@ -385,6 +426,7 @@ extern "C" int rdsic_gc_forward(const rdsic_gc_desc* d, rdsic_stream_t stream) {
   RDSIC_CHECK_ARG((d->sym_in || !d->y.nchw) && !d->mu.nchw && !d->scale.nchw);
   RDSIC_CHECK_ARG(!d->noise.ptr || (d->noise.dtype == RDSIC_F32 && !d->noise.nchw));
   RDSIC_CHECK_ARG(!d->noisy_out.ptr || (d->noise.ptr && d->noisy_out.dtype == RDSIC_F32 && !d->noisy_out.nchw));
+  RDSIC_CHECK_ARG(!d->mask.ptr || (d->mask.dtype == RDSIC_F32 && !d->mask.nchw));
   const size_t npix = (size_t)d->B * d->h * d->w;
   dim3 grid((unsigned)((npix + GC_TP - 1) / GC_TP), (unsigned)ceil_div(d->Cs, GC_TC));
   gc_forward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d);

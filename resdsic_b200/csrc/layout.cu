@@ -21,8 +21,14 @@ __global__ void __launch_bounds__(256) copy_views_kernel(const rdsic_copy_desc d
     if (src_n) { c = c0 + k; p = p0 + tx; } else { p = p0 + k; c = c0 + tx; }
     float v = 0.f;
     if (c < d.C && p < HW) {
-      size_t idx = src_n ? ((size_t)b * d.C + c) * HW + p : ((size_t)b * HW + p) * d.src.ld + d.src.coff + c;
+      size_t idx = src_n ? ((size_t)b * (d.src.ld > 0 ? d.src.ld : d.C) + d.src.coff + c) * HW + p
+                         : ((size_t)b * HW + p) * d.src.ld + d.src.coff + c;
       v = ld_elem(d.src.ptr, d.src.dtype, idx);
+      if (d.op == 4) {
+        const size_t i2 = d.src2.nchw ? ((size_t)b * (d.src2.ld > 0 ? d.src2.ld : d.C) + d.src2.coff + c) * HW + p
+                                      : ((size_t)b * HW + p) * d.src2.ld + d.src2.coff + c;
+        v = __fadd_rn(v, ld_elem(d.src2.ptr, d.src2.dtype, i2));
+      }
       if (d.op == 1) v = gelu_erf(v);
       if (d.op == 2) v = v * v;
       if (d.op == 3) v = fminf(fmaxf(v, 0.f), 1.f);
@@ -35,7 +41,8 @@ __global__ void __launch_bounds__(256) copy_views_kernel(const rdsic_copy_desc d
     float v;
     if (dst_n) { c = c0 + k; p = p0 + tx; v = tile[k][tx]; } else { p = p0 + k; c = c0 + tx; v = tile[tx][k]; }
     if (c < d.C && p < HW) {
-      size_t idx = dst_n ? ((size_t)b * d.C + c) * HW + p : ((size_t)b * HW + p) * d.dst.ld + d.dst.coff + c;
+      size_t idx = dst_n ? ((size_t)b * (d.dst.ld > 0 ? d.dst.ld : d.C) + d.dst.coff + c) * HW + p
+                         : ((size_t)b * HW + p) * d.dst.ld + d.dst.coff + c;
       st_elem(d.dst.ptr, d.dst.dtype, idx, v);
     }
   }
@@ -271,7 +278,8 @@ extern "C" int rdsic_patch_forward(const rdsic_patch_desc* d, rdsic_stream_t str
 
 extern "C" int rdsic_copy_forward(const rdsic_copy_desc* d, rdsic_stream_t stream) {
   RDSIC_CHECK_ARG(d && d->src.ptr && d->dst.ptr && d->B > 0 && d->H > 0 && d->W > 0 && d->C > 0);
-  RDSIC_CHECK_ARG(d->op >= 0 && d->op <= 3);
+  RDSIC_CHECK_ARG(d->op >= 0 && d->op <= 4);
+  RDSIC_CHECK_ARG(d->op != 4 || (d->src2.ptr && d->src2.nchw == d->src.nchw));
   RDSIC_CHECK_ARG(d->B <= 65535);
   dim3 grid(ceil_div(d->H * d->W, 32), ceil_div(d->C, 32), d->B);
   copy_views_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d);

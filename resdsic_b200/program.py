@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import BF16, F32, AttnDesc, ConvDesc, CopyDesc, EBDesc, GCDesc, LNDesc, Op, PatchDesc, View
+from ._lib import BF16, F32, AttnDesc, ConvDesc, CopyDesc, EBDesc, GCDesc, LNDesc, MaskDesc, Op, PatchDesc, View
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
@@ -34,6 +34,17 @@ class TV:
         B, C_, H, W = t.shape
         assert t.is_contiguous()
         return TV(t, B, H, W, C_, nchw=True)
+
+    @staticmethod
+    def nchw_channels(t, off, n, H=None, W=None, total=None):
+        """Channels [off, off+n) of a contiguous NCHW tensor as an NCHW view (copy ops only: `ld` = channel count
+        of the underlying tensor, `coff` = channel offset).  `H, W, total` may reinterpret the per-image memory
+        as [total, H, W] -- e.g. the reference's plain `reshape` of y_base (scalable/single_decoder.py:226-230)."""
+        B, C_, Ht, Wt = t.shape
+        assert t.is_contiguous()
+        H, W, total = (Ht if H is None else H), (Wt if W is None else W), (C_ if total is None else total)
+        assert total * H * W == C_ * Ht * Wt and off + n <= total
+        return TV(t, B, H, W, n, ld=total, coff=off, nchw=True)
 
     def channels(self, off, n):
         """Channel sub-range [off, off+n) of the same pixels (torch chunk / cat as addressing)."""
@@ -195,9 +206,12 @@ class Program:
         self.keep += [z.t, z_hat.t, lik, params, symbols]
 
     def gc(self, y: TV, mu: TV, scale: TV, y_hat_dsts, lik, lik_coff, Ctot, table, symbols=None, indexes=None,
-           scale_bound=0.11, lik_bound=1e-9, noise: TV = None, noisy_out: TV = None, sym_in=None):
+           scale_bound=0.11, lik_bound=1e-9, noise: TV = None, noisy_out: TV = None, sym_in=None, mask: TV = None):
         d = GCDesc()
         d.y, d.mu, d.scale = y.view(), mu.view(), scale.view()
+        d.mask = mask.view() if mask is not None else _NULL
+        if mask is not None:
+            self.keep.append(mask.t)
         d.sym_in = _ptr(sym_in)
         self.keep.append(sym_in)
         d.noise = noise.view() if noise is not None else _NULL
@@ -215,16 +229,32 @@ class Program:
         self._append(op)
         self.keep += [y.t, mu.t, scale.t, lik, table, symbols, indexes] + [tv.t for tv in y_hat_dsts]
 
-    def copy(self, src: TV, dst: TV, op_code=0):
+    def copy(self, src: TV, dst: TV, op_code=0, src2: TV = None):
         d = CopyDesc()
         d.src, d.dst = src.view(), dst.view()
+        d.src2 = src2.view() if src2 is not None else _NULL
         d.B, d.H, d.W, d.C, d.op = src.B, src.H, src.W, src.C, op_code
+        assert (op_code == 4) == (src2 is not None)
         op = Op()
         op.kind = _lib.OP_COPY
         op.u.copy = d
         self._append(op)
-        self.keep += [src.t, dst.t]
+        self.keep += [src.t, dst.t] + ([src2.t] if src2 is not None else [])
         return dst
+
+    def mask(self, ins, out: TV, mode, gamma=None):
+        """ResDSIC importance mask (layers/mask_layer.py:64-107 + the eval-mode round of apply_noise)."""
+        d = MaskDesc()
+        for i, tv in enumerate(ins):
+            d.in_[i] = tv.view()
+        d.out, d.gamma, d.n_in, d.mode = out.view(), _ptr(gamma), len(ins), mode
+        d.B, d.H, d.W, d.C = out.B, out.H, out.W, out.C
+        op = Op()
+        op.kind = _lib.OP_MASK
+        op.u.mask = d
+        self._append(op)
+        self.keep += [tv.t for tv in ins] + [out.t, gamma]
+        return out
 
     def patchify(self, x: TV, out: TV, KH, KW, stride, pad):
         d = PatchDesc()

@@ -43,6 +43,14 @@ class Sim:
             return flat[: B * Cf * H * W].view(B, Cf, H, W).permute(0, 2, 3, 1)[..., :Cn]
         return torch.as_strided(flat, (B, H, W, Cn), (H * W * v.ld, W * v.ld, v.ld, 1), v.coff)
 
+    def _nhwc_copy(self, v, B, H, W, Cn):
+        """Copy-op addressing: NCHW views honour ld (channels of the underlying tensor) and coff."""
+        flat = self._flat(v.ptr)
+        if v.nchw:
+            Cf = v.ld if v.ld > 0 else Cn
+            return flat[: B * Cf * H * W].view(B, Cf, H, W).permute(0, 2, 3, 1)[..., v.coff:v.coff + Cn]
+        return torch.as_strided(flat, (B, H, W, Cn), (H * W * v.ld, W * v.ld, v.ld, 1), v.coff)
+
     # ------------------------------------------------------------------ ops
     def conv(self, d):
         x = self._nhwc(d.in_, d.B, d.H, d.W, d.Cin).float()
@@ -163,8 +171,13 @@ class Sim:
         if d.sym_in:  # decoder side: symbols come from the entropy decoder
             n_ = d.B * d.Ctot * d.h * d.w
             r = self._flat(d.sym_in)[:n_].view(d.B, d.Ctot, d.h, d.w)[:, d.lik_coff:d.lik_coff + d.Cs].permute(0, 2, 3, 1).float()
-        yh = r + mu
-        yl = yh
+        rm = r
+        if d.mask.ptr:  # ResDSIC progressive stream
+            m = self._nhwc(d.mask, d.B, d.h, d.w, d.Cs).float()
+            sc = sc * m
+            rm = r * m
+        yh = rm + mu
+        yl = r + mu
         if d.noise.ptr:  # training mode: likelihood at y + noise
             yl = y + self._nhwc(d.noise, d.B, d.h, d.w, d.Cs).float()
             if d.noisy_out.ptr:
@@ -183,19 +196,29 @@ class Sim:
         sl = slice(d.lik_coff, d.lik_coff + d.Cs)
         self._flat(d.lik)[:n].view(d.B, d.Ctot, d.h, d.w)[:, sl].copy_(lik.permute(0, 3, 1, 2))
         if d.symbols:
-            self._flat(d.symbols)[:n].view(d.B, d.Ctot, d.h, d.w)[:, sl].copy_(r.permute(0, 3, 1, 2).int())
+            self._flat(d.symbols)[:n].view(d.B, d.Ctot, d.h, d.w)[:, sl].copy_(rm.permute(0, 3, 1, 2).int())
         if d.indexes:
             self._flat(d.indexes)[:n].view(d.B, d.Ctot, d.h, d.w)[:, sl].copy_(idx.permute(0, 3, 1, 2))
 
+    def mask(self, d):
+        ins = [self._nhwc(d.in_[i], d.B, d.H, d.W, d.C).float() for i in range(d.n_in)]
+        if d.mode == 1:
+            m = torch.pow(torch.sigmoid(ins[0]), self._flat(d.gamma)[: d.C])
+        else:
+            m = torch.sigmoid(sum(torch.sigmoid(t) for t in ins))
+        self._nhwc(d.out, d.B, d.H, d.W, d.C).copy_(torch.round(m))
+
     def copy(self, d):
-        src = self._nhwc(d.src, d.B, d.H, d.W, d.C).float()
+        src = self._nhwc_copy(d.src, d.B, d.H, d.W, d.C).float()
+        if d.op == 4:
+            src = src + self._nhwc_copy(d.src2, d.B, d.H, d.W, d.C).float()
         if d.op == 1:
             src = F.gelu(src)
         if d.op == 2:
             src = src * src
         if d.op == 3:
             src = src.clamp(0, 1)
-        dst = self._nhwc(d.dst, d.B, d.H, d.W, d.C)
+        dst = self._nhwc_copy(d.dst, d.B, d.H, d.W, d.C)
         dst.copy_(src.to(dst.dtype))
 
     def patch(self, d):
@@ -214,7 +237,8 @@ class Sim:
 
     def run(self):
         disp = {_lib.OP_CONV: ("conv", self.conv), _lib.OP_ATTN: ("attn", self.attn), _lib.OP_EB: ("eb", self.eb),
-                _lib.OP_GC: ("gc", self.gc), _lib.OP_COPY: ("copy", self.copy), _lib.OP_LN: ("ln", self.ln), _lib.OP_PATCH: ("patch", self.patch)}
+                _lib.OP_GC: ("gc", self.gc), _lib.OP_COPY: ("copy", self.copy), _lib.OP_LN: ("ln", self.ln), _lib.OP_PATCH: ("patch", self.patch),
+                _lib.OP_MASK: ("mask", self.mask)}
         for op in self.prog.ops:
             if op.kind in _lib.SYNC_OPS:
                 continue  # lanes are a scheduling hint: program order is always a valid execution

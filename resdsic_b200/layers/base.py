@@ -128,9 +128,10 @@ class B200Module(nn.Module):
 class Sequential(nn.Sequential, B200Module):
     """nn.Sequential of B200 modules (keeps the reference's integer child names)."""
 
-    def emit(self, ctx, x, last_kw=None, **kw):
-        """`last_kw`: extra emit() arguments for the final module (output placement/dtype)."""
-        mods = list(self)
+    def emit(self, ctx, x, last_kw=None, mods=None, **kw):
+        """`last_kw`: extra emit() arguments for the final module (output placement/dtype).  `mods`: emit this
+        sub-chain instead of all children (see emit_modules)."""
+        mods = list(self) if mods is None else list(mods)
         i = 0
         while i < len(mods):
             m = mods[i]
@@ -158,6 +159,12 @@ class Sequential(nn.Sequential, B200Module):
         return x
 
     forward = B200Module.forward
+
+
+def emit_modules(ctx, mods, x, last_kw=None):
+    """Emit a chain of modules with the conv->GELU / conv->GDN fusions of Sequential.emit -- used on sub-ranges of a
+    Sequential (the scalable models split g_a after its sixth child, scalable/single_decoder.py:196-202)."""
+    return Sequential.emit(None, ctx, x, last_kw=last_kw, mods=mods)
 
 
 class GELU(B200Module):

@@ -1,0 +1,250 @@
+"""ResDSIC scalable codecs: the reference's `-m icd` / `-m imd` models
+(models/WACNN/scalable/single_decoder.py:25-504, multiple_decoder.py:19-250) on the B200 kernel library.
+
+A base stream (the WACNN of models/wacnn.py) plus a PROGRESSIVE stream: a second analysis transform on
+`cat(reshape(y_base), x)` (:226-230,357-358), a second hyperprior and context stack, and per quality level an
+importance mask (layers/mask_layer.py) that decides which progressive latents are sent;
+`y_hat_q = y_hat_base + y_hat_prog_q` goes through the synthesis transform (one shared decoder for `icd`, a base /
+enhancement pair for `imd`).  Same constructor arguments, parameter names and output dictionary as the reference.
+
+The whole multi-quality forward is ONE program: the base stream is computed once (the reference recomputes it
+for every quality level, :397-420), the latent-only pre-computations of the progressive context transforms are
+shared between levels, and every level's slice loop reuses the kernels / emitters of the base model.
+Evaluation mode only (round masks); `compress` / `decompress` of the progressive stream stay with the reference
+(per-slice rANS strings, :613-624) -- `symbols_and_indexes` returns what they consume.
+"""
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..entropy_models import EntropyBottleneck, GaussianConditional
+from ..layers import GDN, GELU, Ctx, Sequential, Win_noShift_Attention, conv, conv3x3, deconv, subpel_conv3x3
+from ..layers.base import emit_modules
+from ..layers.mask_layer import ONES, ZEROS, Mask
+from ..program import TV
+from .wacnn import WACNN, _cc_stack, _Plan, get_scale_table
+
+
+class scalable_icd(WACNN):
+    """reference scalable/single_decoder.py:25 (registry key "icd")."""
+
+    def __init__(self, N=192, M=320, mask_policy="learnable-mask-gamma", lambda_list=(0.05,), lrp_prog=True,
+                 independent_lrp=False, **kwargs):
+        super().__init__(N=N, M=M, **kwargs)
+        assert lambda_list is not None
+        self.halve = 8
+        self.level = 5
+        self.factor = self.halve ** 2
+        assert N % self.factor == 0
+        self.T = N // self.factor + 3
+        self.mask_policy = mask_policy
+        self.scalable_levels = len(lambda_list)
+        self.lmbda_list = list(lambda_list)
+        self.lmbda_index_list = dict(zip(self.lmbda_list, range(len(self.lmbda_list))))
+        # ---- same construction order as the reference (:59-160): the constructor draws the same init stream
+        self.masking = Mask(mask_policy, self.scalable_levels, M)
+        self.independent_lrp, self.lrp_prog = independent_lrp, lrp_prog
+        if independent_lrp:
+            assert lrp_prog is True
+            self.lrp_transforms_prog = nn.ModuleList(_cc_stack(320 + 32 * min(i + 1, 6)) for i in range(10))
+        self.entropy_bottleneck_prog = EntropyBottleneck(N)
+        self.gaussian_conditional_prog = GaussianConditional(None)
+        self.g_a_progressive = Sequential(
+            conv(self.T, N, kernel_size=5, stride=2), GDN(N),
+            conv(N, N, kernel_size=5, stride=2), GDN(N),
+            Win_noShift_Attention(dim=N, num_heads=8, window_size=8, shift_size=4),
+            conv(N, N, kernel_size=5, stride=2), GDN(N),
+            conv(N, M, kernel_size=5, stride=2))
+        self.h_a_prog = Sequential(conv3x3(320, 320), GELU(), conv3x3(320, 288), GELU(), conv3x3(288, 256, stride=2), GELU(),
+                                   conv3x3(256, 224), GELU(), conv3x3(224, 192, stride=2))
+
+        def h_s():
+            return Sequential(conv3x3(192, 192), GELU(), subpel_conv3x3(192, 224, 2), GELU(), conv3x3(224, 256), GELU(),
+                              subpel_conv3x3(256, 288, 2), GELU(), conv3x3(288, 320))
+
+        self.h_mean_s_prog = h_s()
+        self.h_scale_s_prog = h_s()
+        self.cc_mean_transforms_prog = nn.ModuleList(_cc_stack(320 + 32 * min(i, 5)) for i in range(10))
+        self.cc_scale_transforms_prog = nn.ModuleList(_cc_stack(320 + 32 * min(i, 5)) for i in range(10))
+        if mask_policy == "learnable-mask":  # (stale policy name kept by the reference, :162-164)
+            self.gamma = nn.Parameter(torch.ones((self.scalable_levels - 2, M)))
+            self.mask_conv = Sequential(conv(2 * M, M, kernel_size=1, stride=1))
+
+    # ------------------------------------------------------------------ API
+    def define_quality(self, quality):
+        """reference :232-239"""
+        if quality is None:
+            return list(self.lmbda_list)
+        return list(quality) if isinstance(quality, (list, tuple)) else [quality]
+
+    def _quality_index(self, p):
+        return self.lmbda_index_list[p] if p in self.lmbda_index_list else p
+
+    def update(self, scale_table=None, force=False):
+        """reference :276-288"""
+        if scale_table is None:
+            scale_table = get_scale_table()
+        updated = self.gaussian_conditional.update_scale_table(scale_table, force=force)
+        updated = self.gaussian_conditional_prog.update_scale_table(scale_table, force=force)
+        self.entropy_bottleneck_prog.update()
+        self.entropy_bottleneck.update()
+        return updated
+
+    def _synthesis(self, q):
+        return self.g_s
+
+    @torch.no_grad()
+    def forward(self, x, quality=None, training=True):
+        """reference :343-504.  Returns {"x_hat": [Q,B,3,H,W], "likelihoods": {"y": [1,10*B,32,h,w] (slice-major, as the reference's cat over dim 0), "z", "z_prog",
+        "y_prog": [Qp,B,M,h,w] (ones if no level uses the progressive stream)}, "y": [Q,B,M,h,w], "z_hat_prog", "z_hat"}."""
+        p = self._execute_scalable(x, self.define_quality(quality), False)
+        o = self._out
+        return {"x_hat": o(p.x_hat), "likelihoods": {"y": o(p.lik_y), "z": o(p.lik_z), "z_prog": o(p.lik_z_prog), "y_prog": o(p.lik_y_prog)},
+                "y": o(p.y_hat_q), "z_hat_prog": o(p.z_hat_prog), "z_hat": o(p.z_hat_out)}
+
+    @torch.no_grad()
+    def symbols_and_indexes(self, x, quality=0):
+        """Everything `compress(x, quality)` (:510-647) computes before the entropy-coder calls, on the device:
+        base-stream symbols / CDF indexes / z symbols and, for quality != 0, the progressive stream's masked
+        symbols, CDF indexes (of scale_prog * mask) and z_prog symbols."""
+        p = self._execute_scalable(x, [quality], True)
+        o = self._out
+        r = {"y_symbols": o(p.symbols), "y_indexes": o(p.indexes), "z_symbols": o(p.z_symbols), "x_hat": o(p.x_hat[0]),
+             "shape": (p.z.H, p.z.W)}
+        if p.prog_symbols is not None:
+            r.update(y_prog_symbols=o(p.prog_symbols), y_prog_indexes=o(p.prog_indexes), z_prog_symbols=o(p.z_prog_symbols))
+        return r
+
+    def compress(self, x, quality=0.0):
+        raise NotImplementedError("the scalable models' bitstream glue (per-slice rANS strings of the progressive stream, "
+                                  "scalable/single_decoder.py:510-647) stays with the reference; use symbols_and_indexes()")
+
+    def decompress(self, strings, shape, quality=None):
+        raise NotImplementedError("scalable decompress (scalable/single_decoder.py:650-773) stays with the reference")
+
+    # ------------------------------------------------------------- planning
+    def _execute_scalable(self, x, qualities, with_symbols):
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError(f"expected [B,3,H,W] input, got {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise RuntimeError("resdsic_b200 runs on CUDA devices only (no CPU fallback)")
+        if self.training:
+            raise RuntimeError("the scalable models are evaluation-only in resdsic_b200 (call .eval())")
+        B, _, H, W = x.shape
+        if H % 64 or W % 64:
+            raise ValueError(f"input {H}x{W} must be a multiple of 64")
+        qs = tuple(self._quality_index(q) for q in qualities)
+        key = ("scalable", B, H, W, str(x.device), self.precision, with_symbols, qs, self._weights_key())
+        plan = self._lru_get(self._plans, key, lambda: self._build_scalable(B, H, W, x.device, qs, with_symbols), self.MAX_PLANS)
+        self._last_plan = plan
+        plan.x.copy_(x)
+        plan.prog.run_graph() if self.use_cuda_graph else plan.prog.run()
+        self.last_num_launches = plan.prog.num_launches
+        return plan
+
+    def _build_scalable(self, B, H, W, device, qs, with_symbols, build_only=False):
+        ctx = Ctx(device, self.precision, build_only=build_only)
+        f32, i32 = torch.float32, torch.int32
+        bf16 = ctx.precision == "bf16"
+        prog = ctx.prog
+        p = _Plan()
+        h, w = H // 16, W // 16
+        M, N = self.M, self.N
+        new = lambda *shape, dtype=f32: torch.empty(*shape, dtype=dtype, device=device)
+        p.x = new(B, 3, H, W)
+        # ---- g_a in two parts (split_ga, :196-202): y_base = g_a[:6](x) (before the third GDN), y = g_a[6:](y_base)
+        mods = list(self.g_a)
+        y_base = emit_modules(ctx, mods[: self.level + 1], TV.nchw_of(p.x))
+        y = ctx.buf(B, h, w, M, f32)
+        y_act = ctx.buf(B, h, w, M) if bf16 else y
+        emit_modules(ctx, mods[self.level + 1:], y_base, last_kw=dict(out=y, out2=y_act) if bf16 else dict(out=y))
+        # ---- concatenate (:226-230): the NCHW memory of y_base [B,N,H/8,W/8] REINTERPRETED as [B,N/64,H,W], cat x
+        xp = new(B, self.T, H, W)
+        prog.copy(y_base, TV.nchw_channels(xp, 0, N, H=H // 8, W=W // 8, total=self.T * self.factor))
+        prog.copy(TV.nchw_of(p.x), TV.nchw_channels(xp, self.T - 3, 3))
+        y_prog = ctx.buf(B, h, w, M, f32)
+        y_prog_act = ctx.buf(B, h, w, M) if bf16 else y_prog
+        self.g_a_progressive.emit(ctx, TV.nchw_of(xp), last_kw=dict(out=y_prog, out2=y_prog_act) if bf16 else dict(out=y_prog))
+        # ---- the two hyperpriors
+        hz, wz = h // 4, w // 4
+        p.lik_z, p.lik_z_prog = new(B, N, hz, wz), new(B, N, hz, wz)
+        p.z_symbols = new(B, N, hz, wz, dtype=i32) if with_symbols else None
+        p.z_prog_symbols = new(B, N, hz, wz, dtype=i32) if with_symbols else None
+        z, z_hat, means, scales = self._emit_hyperprior(ctx, y_act, self.h_a, self.entropy_bottleneck, self.h_mean_s,
+                                                        self.h_scale_s, p.lik_z, p.z_symbols)
+        z_p, z_hat_p, means_p, scales_p = self._emit_hyperprior(ctx, y_prog_act, self.h_a_prog, self.entropy_bottleneck_prog,
+                                                                self.h_mean_s_prog, self.h_scale_s_prog, p.lik_z_prog,
+                                                                p.z_prog_symbols)
+        p.z_hat_out, p.z_hat_prog = new(B, N, hz, wz), new(B, N, hz, wz)
+        prog.copy(z_hat, TV.nchw_of(p.z_hat_out))
+        prog.copy(z_hat_p, TV.nchw_of(p.z_hat_prog))
+        # ---- base slice loop, ONCE (identical for every quality level in the reference)
+        # forward(): likelihoods["y"] is [1, 10*B, 32, h, w], slice-major -- the reference concatenates the ten slice
+        # likelihoods along dim 0 (:480); with_symbols keeps the standard [B,M,h,w] layout next to symbols / indexes
+        p.lik_y = new(B, M, h, w) if with_symbols else new(1, self.num_slices * B, self.slice_channels, h, w)
+        p.symbols = new(B, M, h, w, dtype=i32) if with_symbols else None
+        p.indexes = new(B, M, h, w, dtype=i32) if with_symbols else None
+        fam = {"cc_mean": self.cc_mean_transforms, "cc_scale": self.cc_scale_transforms, "lrp": self.lrp_transforms}
+        pre = self._emit_slice_precompute(ctx, fam, means, scales)
+        y_hat = self._emit_slice_loop(ctx, fam, pre, self.gaussian_conditional, y, means, scales, p.lik_y, p.symbols, p.indexes,
+                                      lik_slice_major=not with_symbols)
+        # ---- progressive stream per quality level
+        prog_qs = [q for q in qs if q != 0]
+        p.lik_y_prog = new(len(prog_qs), B, M, h, w) if prog_qs else torch.ones(1, B, M, h, w, dtype=f32, device=device)
+        p.prog_symbols = new(B, M, h, w, dtype=i32) if (with_symbols and prog_qs) else None
+        p.prog_indexes = new(B, M, h, w, dtype=i32) if (with_symbols and prog_qs) else None
+        fam_p = {"cc_mean": self.cc_mean_transforms_prog, "cc_scale": self.cc_scale_transforms_prog,
+                 "lrp": self.lrp_transforms_prog if self.independent_lrp else self.lrp_transforms}
+        pre_p = self._emit_slice_precompute(ctx, fam_p, means_p, scales_p) if prog_qs else None
+        lat_s, lat_sp = scales.channels(0, M), scales_p.channels(0, M)
+        mask_cache, first = {}, True
+        p.x_hat = new(len(qs), B, 3, H, W)
+        p.y_hat_q = new(len(qs), B, M, h, w)
+        p.masks = {}
+        jp = 0
+        for j, q in enumerate(qs):
+            y_hat_q = y_hat
+            if q != 0:
+                kind = self.masking.kind(q)
+                assert kind != ZEROS
+                mask = None if kind == ONES else self.masking.emit(ctx, lat_s, lat_sp, q, mask_cache)
+                p.masks[q] = mask
+                if first:
+                    mq, sq = means_p, scales_p
+                else:  # later levels: private support slots over a copy of the progressive latents
+                    mq, sq = ctx.buf(B, h, w, means_p.ld), ctx.buf(B, h, w, scales_p.ld)
+                    prog.copy(means_p.channels(0, M), mq.channels(0, M))
+                    prog.copy(scales_p.channels(0, M), sq.channels(0, M))
+                first = False
+                y_hat_p = self._emit_slice_loop(ctx, fam_p, pre_p, self.gaussian_conditional_prog, y_prog, mq, sq,
+                                                p.lik_y_prog[jp], p.prog_symbols, p.prog_indexes, mask=mask, lrp=self.lrp_prog)
+                jp += 1
+                y_hat_q = prog.copy(y_hat, ctx.buf(B, h, w, M, f32), op_code=4, src2=y_hat_p)  # y_hat_complete (:472)
+            prog.copy(y_hat_q, TV.nchw_of(p.y_hat_q[j]))
+            act = prog.copy(y_hat_q, ctx.buf(B, h, w, M)) if bf16 else y_hat_q
+            self._synthesis(q).emit(ctx, act, last_kw=dict(out=TV.nchw_of(p.x_hat[j])))
+        p.prog = prog
+        p.y, p.z, p.y_hat, p.means, p.scales, p.y_prog, p.y_base = y, z, y_hat, means, scales, y_prog, y_base
+        p.subs, p.sub_batch = [p], B
+        return p
+
+
+class scalable_imd(scalable_icd):
+    """reference scalable/multiple_decoder.py:19 (registry key "imd"): `icd` with a base decoder g_s[0]
+    (quality 0) and an enhancement decoder g_s[1] (:36-50,225)."""
+
+    def __init__(self, N=192, M=320, mask_policy="learnable-mask-gamma", lambda_list=(0.05,), lrp_prog=True,
+                 independent_lrp=False, **kwargs):
+        super().__init__(N=N, M=M, mask_policy=mask_policy, lambda_list=lambda_list, lrp_prog=lrp_prog,
+                         independent_lrp=independent_lrp, **kwargs)
+        self.g_s = nn.ModuleList(
+            Sequential(
+                Win_noShift_Attention(dim=M, num_heads=8, window_size=4, shift_size=2),
+                deconv(M, N, kernel_size=5, stride=2), GDN(N, inverse=True),
+                deconv(N, N, kernel_size=5, stride=2), GDN(N, inverse=True),
+                Win_noShift_Attention(dim=N, num_heads=8, window_size=8, shift_size=4),
+                deconv(N, N, kernel_size=5, stride=2), GDN(N, inverse=True),
+                deconv(N, 3, kernel_size=5, stride=2)) for _ in range(2))
+
+    def _synthesis(self, q):
+        return self.g_s[0 if q == 0 else 1]

@@ -299,49 +299,69 @@ class WACNN(CompressionModel):
         # ---- g_a: y kept fp32 (it is quantised against mu)
         bf16 = ctx.precision == "bf16"
         h, w = H // 16, W // 16
-        M, sc_ = self.M, self.slice_channels
+        M = self.M
         y = ctx.buf(B, h, w, M, f32)
         y_act = ctx.buf(B, h, w, M) if bf16 else y  # bf16 twin of y: A operand of h_a
         self.g_a.emit(ctx, TV.nchw_of(p.x), last_kw=dict(out=y, out2=y_act) if bf16 else dict(out=y))
-        # ---- h_a -> z (fp32) -> EB
-        z = self.h_a.emit(ctx, y_act, last_kw=dict(out_dtype=f32))
-        p.lik_z = out_tensor("lik_z", B, z.C, z.H, z.W)
-        p.z_symbols = out_tensor("z_symbols", B, z.C, z.H, z.W, dtype=torch.int32) if with_symbols else None
+        # ---- h_a -> z (fp32) -> EB -> hyper-synthesis straight into the support buffers
         p.noise_y = p.noise_z = None
         if self.training:
             p.noise_y = ctx.buf(B, h, w, M, f32)
-            p.noise_z = ctx.buf(B, z.H, z.W, z.C, f32)
-        z_hat, _ = self.entropy_bottleneck.emit(ctx, z, lik=p.lik_z, symbols=p.z_symbols, noise=p.noise_z)
-        # ---- hyper-synthesis straight into the support buffers
-        S = self.max_support_slices
+            p.noise_z = ctx.buf(B, h // 4, w // 4, self.N, f32)
+        p.lik_z = out_tensor("lik_z", B, self.N, h // 4, w // 4)
+        p.z_symbols = out_tensor("z_symbols", B, self.N, h // 4, w // 4, dtype=torch.int32) if with_symbols else None
+        z, z_hat, means, scales = self._emit_hyperprior(ctx, y_act, self.h_a, self.entropy_bottleneck, self.h_mean_s,
+                                                        self.h_scale_s, p.lik_z, p.z_symbols, p.noise_z)
+        # ---- slice loop
+        p.lik_y = out_tensor("lik_y", B, M, h, w)
+        p.symbols = out_tensor("symbols", B, M, h, w, dtype=torch.int32) if with_symbols else None
+        p.indexes = out_tensor("indexes", B, M, h, w, dtype=torch.int32) if with_symbols else None
+        fam = {"cc_mean": self.cc_mean_transforms, "cc_scale": self.cc_scale_transforms, "lrp": self.lrp_transforms}
+        pre = self._emit_slice_precompute(ctx, fam, means, scales)
+        y_hat = self._emit_slice_loop(ctx, fam, pre, self.gaussian_conditional, y, means, scales, p.lik_y, p.symbols,
+                                      p.indexes, noise=p.noise_y)
+        # ---- g_s
+        p.x_hat = out_tensor("x_hat", B, 3, H, W)
+        y_hat_act = ctx.prog.copy(y_hat, ctx.buf(B, h, w, M)) if bf16 else y_hat
+        self.g_s.emit(ctx, y_hat_act, last_kw=dict(out=TV.nchw_of(p.x_hat)))
+        p.prog = ctx.prog
+        p.y, p.z, p.y_hat, p.means, p.scales = y, z, y_hat, means, scales
+        return p
+
+    # ------------------------------------------------------------- program pieces (shared with the scalable models)
+    def _emit_hyperprior(self, ctx, y_act, h_a, eb, h_mean_s, h_scale_s, lik_z, z_symbols, noise_z=None):
+        """h_a -> z (fp32) -> EntropyBottleneck -> h_mean_s || h_scale_s written straight into the slice loop's
+        context buffers (cnn.py:146-157).  Returns (z, z_hat, means, scales)."""
+        f32 = torch.float32
+        M, sc_, S = self.M, self.slice_channels, self.max_support_slices
+        z = h_a.emit(ctx, y_act, last_kw=dict(out_dtype=f32))
+        z_hat, _ = eb.emit(ctx, z, lik=lik_z, symbols=z_symbols, noise=noise_z)
         ctx_ld = M + sc_ * (S + 1)  # latent | S support slots | one scratch slot
+        B, h, w = y_act.B, y_act.H, y_act.W
         means = ctx.buf(B, h, w, ctx_ld)
         scales = ctx.buf(B, h, w, ctx_ld)
         ctx.prog.fork()  # the two hyper-synthesis stacks are independent
         with ctx.prog.side():
-            self.h_scale_s.emit(ctx, z_hat, last_kw=dict(out=scales.channels(0, M)))
-        self.h_mean_s.emit(ctx, z_hat, last_kw=dict(out=means.channels(0, M)))
+            h_scale_s.emit(ctx, z_hat, last_kw=dict(out=scales.channels(0, M)))
+        h_mean_s.emit(ctx, z_hat, last_kw=dict(out=means.channels(0, M)))
         ctx.prog.join()
-        # ---- slice loop
-        y_hat = ctx.buf(B, h, w, M, f32)  # fp32 master copy of y_hat (LRP residual + g_s input)
-        p.lik_y = out_tensor("lik_y", B, M, h, w)
-        p.symbols = out_tensor("symbols", B, M, h, w, dtype=torch.int32) if with_symbols else None
-        p.indexes = out_tensor("indexes", B, M, h, w, dtype=torch.int32) if with_symbols else None
-        prog = ctx.prog
-        lat_m, lat_s = means.channels(0, M), scales.channels(0, M)
+        return z, z_hat, means, scales
 
-        # -- off the serial chain: everything that only needs latent_means / latent_scales.
-        #    * slice 0 has no support: its whole cc_mean / cc_scale stacks;
-        #    * every other context transform: the latent-only part of its first conv,
-        #      conv(cat(latent, support); W) = conv(latent; W[:, :320]) + conv(support; W[:, 320:]),
-        #      as fp32 partial sums that the in-chain conv adds in its epilogue.
+    def _emit_slice_precompute(self, ctx, fam, means, scales):
+        """Off the serial chain: everything that only needs latent_means / latent_scales.
+          * slice 0 has no support: its whole cc_mean / cc_scale stacks;
+          * every other context transform: the latent-only part of its first conv,
+            conv(cat(latent, support); W) = conv(latent; W[:, :320]) + conv(support; W[:, 320:]),
+            as fp32 partial sums that the in-chain conv adds in its epilogue.
+        Returns {"out": key -> TV, "ev": key -> event id}."""
+        prog, M = ctx.prog, self.M
+        lat_m, lat_s = means.channels(0, M), scales.channels(0, M)
         pre, pre_ev = {}, {}
         jobs = [("mu0", None), ("sc0", None)]
         for i in range(self.num_slices):
             if i:
                 jobs += [(("cc_mean", i), lat_m), (("cc_scale", i), lat_s)]
             jobs.append((("lrp", i), lat_m))
-        fam = {"cc_mean": self.cc_mean_transforms, "cc_scale": self.cc_scale_transforms, "lrp": self.lrp_transforms}
         forked = set()
         for n, (key, src) in enumerate(jobs):
             lane = 2 + n % (_lib.MAX_LANES - 2)
@@ -350,18 +370,35 @@ class WACNN(CompressionModel):
                 forked.add(lane)
             with prog.side(lane):
                 if key == "mu0":
-                    pre[key] = self._stack(ctx, self.cc_mean_transforms[0], lat_m)
+                    pre[key] = self._stack(ctx, fam["cc_mean"][0], lat_m)
                 elif key == "sc0":
-                    pre[key] = self._stack(ctx, self.cc_scale_transforms[0], lat_s)
+                    pre[key] = self._stack(ctx, fam["cc_scale"][0], lat_s)
                 else:
                     pre[key] = fam[key[0]][key[1]][0].emit_partial(ctx, src, 0, M)
                 pre_ev[key] = prog.record()
+        return {"out": pre, "ev": pre_ev}
+
+    def _emit_slice_loop(self, ctx, fam, pre, gc, y, means, scales, lik_y, symbols, indexes, noise=None, mask=None,
+                         lrp=True, lik_slice_major=False):
+        """The channel-slice context loop (cnn.py:161-187) over the context buffers `means` / `scales`
+        ([B,h,w,320 + 6*32]: latents | five support slots | scratch).  `mask` (fp32 [B,h,w,320]) selects the
+        ResDSIC progressive-stream arithmetic of the Gaussian conditional (scalable/single_decoder.py:447-453);
+        `lrp=False` skips the latent residual prediction (scalable `lrp_prog=False`).  `lik_slice_major`: `lik_y`
+        is laid out [num_slices * B, 32, h, w] (slice-major), the shape the scalable models' `torch.cat(..., dim=0)`
+        produces (scalable/single_decoder.py:480); symbols / indexes must then be None.  Returns the fp32 y_hat."""
+        assert not (lik_slice_major and (symbols is not None or indexes is not None))
+        prog = ctx.prog
+        B, h, w = y.B, y.H, y.W
+        M, sc_, S = self.M, self.slice_channels, self.max_support_slices
+        ctx_ld = means.ld
+        y_hat = ctx.buf(B, h, w, M, torch.float32)  # fp32 master copy of y_hat (LRP residual + g_s input)
+        pre_out, pre_ev = pre["out"], pre["ev"]
 
         def stack_split(name, i, buf, n_extra, final=None):
             """Context transform whose first conv only sees the `n_extra` support channels of `buf`."""
             prog.wait(pre_ev[(name, i)])
             seq = fam[name][i]
-            t = seq[0].emit_partial(ctx, buf.channels(M, n_extra), 1, M, res=pre[(name, i)], gelu=True)
+            t = seq[0].emit_partial(ctx, buf.channels(M, n_extra), 1, M, res=pre_out[(name, i)], gelu=True)
             return self._stack(ctx, seq, t, final=final, skip_first=True)
 
         def slice_ops(i, scale_lane):
@@ -370,7 +407,7 @@ class WACNN(CompressionModel):
             if i == 0:
                 prog.wait(pre_ev["mu0"])
                 prog.wait(pre_ev["sc0"])
-                mu, sc = pre["mu0"], pre["sc0"]
+                mu, sc = pre_out["mu0"], pre_out["sc0"]
             else:
                 prog.fork(scale_lane)  # cc_mean || cc_scale (cnn.py:167-173 are independent given the support)
                 with prog.side(scale_lane):
@@ -386,12 +423,20 @@ class WACNN(CompressionModel):
                 # slices >= max_support share one support set, so they are independent of each other: each
                 # gets a private copy of the support + its own y_hat slot and may run concurrently
                 lrp_buf = ctx.buf(B, h, w, ctx_ld)
-                prog.copy(means.channels(M, sc_ * S), lrp_buf.channels(M, sc_ * S))
+                if lrp:
+                    prog.copy(means.channels(M, sc_ * S), lrp_buf.channels(M, sc_ * S))
                 slot, extra = lrp_buf.channels(M + sc_ * S, sc_), {}
-            self.gaussian_conditional.emit(ctx, y.channels(sc_ * i, sc_), sc, mu, p.lik_y, sc_ * i, M,
-                                           y_hat_dsts=[yh_i, slot], symbols=p.symbols, indexes=p.indexes,
-                                           noise=p.noise_y.channels(sc_ * i, sc_) if p.noise_y is not None else None)
-            stack_split("lrp", i, lrp_buf, sc_ * (k + 1), final=dict(epilogue=_lib.EPI_LRP, res=yh_i, out=yh_i, **extra))
+            dsts = [yh_i, slot]
+            if not lrp and i < S:
+                dsts.append(scales.channels(M + sc_ * i, sc_))  # no LRP pass: the GC output IS the support slice
+            lik_i, coff_i, ctot = lik_y, sc_ * i, M
+            if lik_slice_major:
+                lik_i, coff_i, ctot = lik_y.view(self.num_slices, B, sc_, h, w)[i], 0, sc_
+            gc.emit(ctx, y.channels(sc_ * i, sc_), sc, mu, lik_i, coff_i, ctot, y_hat_dsts=dsts, symbols=symbols,
+                    indexes=indexes, noise=noise.channels(sc_ * i, sc_) if noise is not None else None,
+                    mask=mask.channels(sc_ * i, sc_) if mask is not None else None)
+            if lrp:
+                stack_split("lrp", i, lrp_buf, sc_ * (k + 1), final=dict(epilogue=_lib.EPI_LRP, res=yh_i, out=yh_i, **extra))
 
         for i in range(S):  # serial chain: slice i+1 needs the refined slice i
             slice_ops(i, 1)
@@ -409,13 +454,7 @@ class WACNN(CompressionModel):
         for n, i in enumerate(tail):
             if 2 + 2 * n + 1 < _lib.MAX_LANES:
                 prog.join(2 + 2 * n)
-        # ---- g_s
-        p.x_hat = out_tensor("x_hat", B, 3, H, W)
-        y_hat_act = ctx.prog.copy(y_hat, ctx.buf(B, h, w, M)) if bf16 else y_hat
-        self.g_s.emit(ctx, y_hat_act, last_kw=dict(out=TV.nchw_of(p.x_hat)))
-        p.prog = ctx.prog
-        p.y, p.z, p.y_hat, p.means, p.scales = y, z, y_hat, means, scales
-        return p
+        return y_hat
 
     def _build_decoder(self, B, hz, wz, device, build_only=False):
         """Programs of the decoder-side loop: `hyper` (h_mean_s || h_scale_s + everything that only needs the

@@ -317,7 +317,7 @@ def synth_state_dict(reference_sd, seed: int = 0, gains=_STF_GAINS):
                 g = v
         if ref.numel() == 0 or leaf in ("pedestal", "bound", "target", "relative_position_index", "scale_bound"):
             t = ref.clone()
-        elif name.startswith("entropy_bottleneck."):
+        elif name.split(".")[0].startswith("entropy_bottleneck"):  # (also entropy_bottleneck_prog of the scalable models)
             if leaf.startswith("_matrix"):
                 t = ref.clone() + hash_symmetric(name, shape, 0.2, seed)
             elif leaf.startswith("_bias"):

@@ -45,15 +45,19 @@ constexpr int ISSUER2_WARP = 2 + NUM_EPI_WARPS;
 constexpr int PRODUCER2_WARP = ISSUER2_WARP + 1;
 constexpr int CONV_THREADS = NUM_THREADS + 64;
 
-template <int EPI, bool PLAIN>
+template <int EPI, bool PLAIN, bool PAIR>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const rdsic_conv_desc d, const TcGeom g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // PAIR (cta_group::2) is a template parameter: a kernel that contains cta_group::2 instructions can only be launched
+  // in clusters of two, so the 1-CTA instantiations must not contain any; the PAIR instantiation in turn drops the
+  // halo / M2 / K-split / MC variants
+  const int m_halo = PAIR ? 0 : g.halo, m_m2 = PAIR ? 0 : g.m2, m_ksplit = PAIR ? 0 : g.ksplit, m_mc = PAIR ? 0 : g.mc;
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int stage_bytes = g.halo ? g.b_stage_bytes : g.a_stage_bytes + g.b_stage_bytes;
-  uint64_t* full_bar = (uint64_t*)(smem + (size_t)g.num_stages * stage_bytes + (g.halo ? 2 * g.a_halo_bytes : 0));
+  const int stage_bytes = m_halo ? g.b_stage_bytes : g.a_stage_bytes + g.b_stage_bytes;
+  uint64_t* full_bar = (uint64_t*)(smem + (size_t)g.num_stages * stage_bytes + (m_halo ? 2 * g.a_halo_bytes : 0));
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* acc_full = empty_bar + MAX_STAGES;   // [2] MMA -> epilogue
   uint64_t* acc_empty = acc_full + 2;            // [2] epilogue -> MMA
@@ -72,30 +76,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_b) : "memory");
     for (int s = 0; s < g.num_stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], g.m2 ? 2 : 1);  // M2: both issuers drain every stage
+      mbar_init(&empty_bar[s], (m_m2 ? 2 : 1) * (m_mc ? 2 : 1));  // M2: both issuers drain every stage; MC: both CTAs' issuers
     }
     for (int k = 0; k < 2; ++k) {
-      mbar_init(&acc_full[k], (g.ksplit || g.m2) ? 2 : 1);
-      mbar_init(&acc_empty[k], NUM_EPI_WARPS);
+      mbar_init(&acc_full[k], (m_ksplit || m_m2) ? 2 : 1);
+      mbar_init(&acc_empty[k], NUM_EPI_WARPS * (PAIR ? 2 : 1));  // PAIR: the leader's barrier collects both CTAs' epilogue warps
       mbar_init(&a_full[k], 1);
       mbar_init(&a_empty[k], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // one warp allocates TMEM (and later frees it)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(g.tmem_cols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  if (warp == 1) {  // one warp allocates TMEM (and later frees it); PAIR: the same warp of both CTAs, as one allocation
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(g.tmem_cols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(g.tmem_cols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
   }
   for (int i = threadIdx.x; i < (d.Cout + 15) / 16 * 16; i += blockDim.x) bias_s[i] = (d.bias && i < d.Cout) ? d.bias[i] : 0.f;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  if (m_mc || PAIR) cluster_sync_all();  // the peer's barriers are initialised before any remote copy / commit / arrive targets them
   const uint32_t tmem_base = *tmem_slot;
+  const TileWalk wk = make_walk(g);
+  const uint32_t b_half_off = (uint32_t)(wk.crank * (g.BN / 2) * BK * 2);  // MC: this CTA's half of the B stage
+  const int n_half = wk.crank * (g.BN / 2);                                 // MC / PAIR: first B row this CTA loads
 
   if (warp == 0 || warp == PRODUCER2_WARP) {
     // ================= TMA producers =================
     // NOTE: no integer division inside the per-stage loops -- this warp's latency paces the whole pipeline.
-    if (g.halo) {
+    if (m_halo) {
       if (lane == 0 && warp == 0) {
         int s = 0, as = 0;
         uint32_t ph = 0, aph = 0;
@@ -137,24 +150,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       const uint32_t full0 = __shfl_sync(0xffffffffu, smem_u32(full_bar), 0);
       const uint32_t empty0 = __shfl_sync(0xffffffffu, smem_u32(empty_bar), 0);
-      int ns = g.num_stages, kb = g.kb_per_tap, kiters = d.KH * d.KW * g.kb_per_tap, total = g.total_tiles, step = gridDim.x;
+      const uint32_t lead_full0 = PAIR ? mapa_u32(full0, 0u) : full0;  // PAIR: the leader CTA's full barriers
+      int ns = g.num_stages, kb = g.kb_per_tap, kiters = d.KH * d.KW * g.kb_per_tap, total = g.walk_total, step = wk.step;
       int KW = d.KW, Cin = d.Cin;
       asm volatile("" : "+r"(ns), "+r"(kb), "+r"(kiters), "+r"(total), "+r"(step), "+r"(KW), "+r"(Cin));
       const int kq = kiters / ns, kr = kiters % ns;
       int s_base = 0;
       uint32_t ph_base = 0;
-      if (g.m2) {
+      if (m_m2) {
         // M2: one producer walks every stage in ring order (a stage carries a 256-row A box, so the per-stage
         // issue chain is amortised over twice the MMAs; the ring depth may be odd)
         if (pw == 0) {
           int s = 0;
           uint32_t ph = 0;
-          for (int tile = blockIdx.x; tile < total; tile += step) {
-            const int nt = tile % g.n_tiles;
-            int t = tile / g.n_tiles;
-            const int tx = t % g.tiles_x;
-            t /= g.tiles_x;
-            const int ty = t % g.tiles_y, b = t / g.tiles_y;
+          for (int q = wk.first; q < total; q += step) {
+            int nt, tx, ty, b;
+            tile_of(g, wk, q, nt, tx, ty, b);
             const int x0 = tx * g.TW * d.stride - d.pad_w, y0 = ty * g.TH * d.stride - d.pad_h, n0 = nt * g.BN;
             int cb = 0, r = 0, sx = 0, kcol = 0;
             for (int n = 0; n < kiters; ++n) {
@@ -163,7 +174,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               if (elect_one()) {
                 mbar_expect_tx_u32(bar, tx_bytes);
                 if (!(g.dbg_skip_load & 1)) tma_load_4d_u32(a_dst, &tmap_a, bar, cb * BK, x0 + sx, y0 + r, b);
-                if (!(g.dbg_skip_load & 2)) tma_load_2d_u32(a_dst + a_bytes, &tmap_b, bar, kcol + cb * BK, n0);
+                if (m_mc) tma_load_2d_mc_u32(a_dst + a_bytes + b_half_off, &tmap_b, bar, kcol + cb * BK, n0 + n_half, 3);
+                else if (!(g.dbg_skip_load & 2)) tma_load_2d_u32(a_dst + a_bytes, &tmap_b, bar, kcol + cb * BK, n0);
               }
               __syncwarp();
               if (++s == ns) { s = 0; ph ^= 1u; }
@@ -174,14 +186,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               }
             }
           }
+          // MC drain: leave only when both CTAs have released every stage for the last time -- no multicast commit
+          // of the peer may arrive on this CTA's barriers after it has exited
+          if (m_mc)
+            for (int n = 0; n < ns; ++n) {
+              mbar_wait_u32(empty0 + 8u * (uint32_t)s, ph ^ 1u);
+              if (++s == ns) { s = 0; ph ^= 1u; }
+            }
         }
       } else
-      for (int tile = blockIdx.x; tile < total; tile += step) {
-        const int nt = tile % g.n_tiles;
-        int t = tile / g.n_tiles;
-        const int tx = t % g.tiles_x;
-        t /= g.tiles_x;
-        const int ty = t % g.tiles_y, b = t / g.tiles_y;
+      for (int q = wk.first; q < total; q += step) {
+        int nt, tx, ty, b;
+        tile_of(g, wk, q, nt, tx, ty, b);
         const int x0 = tx * g.TW * d.stride - d.pad_w, y0 = ty * g.TH * d.stride - d.pad_h, n0 = nt * g.BN;
         // this producer's first k-iteration of the tile (the first whose stage has its parity): stage, filter
         // tap and channel block
@@ -196,10 +212,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int n = 0; n < n_own; ++n) {
           mbar_wait_u32(empty0 + 8u * (uint32_t)s, ph ^ 1u);
           const uint32_t a_dst = smem_base + (uint32_t)(s * stage_bytes), bar = full0 + 8u * (uint32_t)s;
-          if (elect_one()) {
+          if (PAIR) {
+            // both CTAs' boxes complete on the LEADER's full barrier, which expects the bytes of both
+            const uint32_t lbar = lead_full0 + 8u * (uint32_t)s;
+            if (elect_one()) {
+              if (wk.crank == 0) mbar_expect_tx_u32(bar, 2u * tx_bytes);
+              tma_load_4d_2sm_u32(a_dst, &tmap_a, lbar, cb * BK, x0 + sx, y0 + r, b);
+              tma_load_2d_2sm_u32(a_dst + a_bytes, &tmap_b, lbar, kcol + cb * BK, n0 + n_half);
+            }
+          } else if (elect_one()) {
             mbar_expect_tx_u32(bar, tx_bytes);
             if (!(g.dbg_skip_load & 1)) tma_load_4d_u32(a_dst, &tmap_a, bar, cb * BK, x0 + sx, y0 + r, b);
-            if (!(g.dbg_skip_load & 2)) tma_load_2d_u32(a_dst + a_bytes, &tmap_b, bar, kcol + cb * BK, n0);
+            if (m_mc) tma_load_2d_mc_u32(a_dst + a_bytes + b_half_off, &tmap_b, bar, kcol + cb * BK, n0 + n_half, 3);
+            else if (!(g.dbg_skip_load & 2)) tma_load_2d_u32(a_dst + a_bytes, &tmap_b, bar, kcol + cb * BK, n0);
           }
           __syncwarp();
           s += 2;
@@ -215,6 +240,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         s_base += kr;
         if (s_base >= ns) { s_base -= ns; ph_base ^= 1u; }
       }
+      if ((m_mc || PAIR) && !m_m2) {  // MC / PAIR drain of this producer's stages (see the M2 producer)
+        int s = s_base;
+        uint32_t ph = ph_base;
+        for (int n = 0; n < ns; ++n) {
+          if ((s & 1) == pw) mbar_wait_u32(empty0 + 8u * (uint32_t)s, ph ^ 1u);
+          if (++s == ns) { s = 0; ph ^= 1u; }
+        }
+      }
     }
     __syncwarp();
   } else if (warp == 1 || warp == ISSUER2_WARP) {
@@ -223,7 +256,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t idesc = make_idesc(g.BN);
     const int taps = d.KH * d.KW;
     const int kc_last = (d.Cin - (g.kb_per_tap - 1) * BK) / 16;  // valid 16-wide K steps of a tap's last block
-    if (g.halo) {
+    if (m_halo) {
       if (lane == 0 && !me) {  // (experimental mode, divergent single-lane issue)
         int s = 0, as = 0;
         uint32_t ph = 0, lt = 0, aph = 0;
@@ -275,20 +308,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t full0 = __shfl_sync(0xffffffffu, smem_u32(full_bar), 0);
       const uint64_t dconst = make_sw128_desc(0);                   // everything but the start-address field
       const uint32_t a_u0 = (smem_base & 0x3FFFFu) >> 4, stage_u = (uint32_t)stage_bytes >> 4;
-      int ns = g.num_stages, kb = g.kb_per_tap, kiters = taps * g.kb_per_tap, total = g.total_tiles, step = gridDim.x;
+      int ns = g.num_stages, kb = g.kb_per_tap, kiters = taps * g.kb_per_tap, total = g.walk_total, step = wk.step;
       asm volatile("" : "+r"(ns), "+r"(kb), "+r"(kiters), "+r"(total), "+r"(step));
-      const int ways = g.ksplit ? 2 : 1;
+      const bool mc = m_mc != 0;
+      const int ways = m_ksplit ? 2 : 1;
       const int kq = kiters / ns, kr = kiters % ns;                  // per-tile advance of the stage ring
       int s_base = 0, dbg_n = 0;
       uint32_t ph_base = 0, lt = 0;
-      if (g.m2) {
+      if (PAIR) {
+        // PAIR: the leader CTA's first issuer warp issues every UMMA for both CTAs (256 x BN per K step); K runs
+        // sequentially in one accumulator per SM, i.e. in the single-issuer summation order
+        if (!me && wk.crank == 0) {
+          const uint32_t idesc2 = make_idesc(g.BN, 2 * BM);
+          const uint32_t b_off = (uint32_t)g.a_stage_bytes >> 4;
+          int s = 0, cb = 0;
+          uint32_t ph = 0;
+          for (int q = wk.first; q < total; q += step, ++lt) {
+            const uint32_t buf = g.acc_bufs == 2 ? (lt & 1u) : 0u, cph = g.acc_bufs == 2 ? ((lt >> 1) & 1u) : (lt & 1u);
+            mbar_wait(&acc_empty[buf], cph ^ 1u);  // both CTAs' epilogues have drained this accumulator buffer
+            tcgen05_fence_after();
+            const uint32_t acc = tbase + buf * (uint32_t)g.acc_stride;
+            for (int n = 0; n < kiters; ++n) {
+              mbar_wait_u32(full0 + 8u * (uint32_t)s, ph);  // both CTAs' A boxes and B halves have landed
+              tcgen05_fence_after();
+              const uint64_t da = dconst + (uint64_t)(a_u0 + (uint32_t)s * stage_u), db = da + b_off;
+              if (elect_one()) {
+                if (cb + 1 != kb || kc_last == 4) {
+                  umma_bf16_2sm(acc, da, db, idesc2, n > 0 ? 1u : 0u);
+                  umma_bf16_2sm(acc, da + 2, db + 2, idesc2, 1u);
+                  umma_bf16_2sm(acc, da + 4, db + 4, idesc2, 1u);
+                  umma_bf16_2sm(acc, da + 6, db + 6, idesc2, 1u);
+                } else {
+                  for (int k = 0; k < kc_last; ++k) umma_bf16_2sm(acc, da + 2 * k, db + 2 * k, idesc2, (n > 0 || k > 0) ? 1u : 0u);
+                }
+                tcgen05_commit_2sm_mc_u32(empty0 + 8u * (uint32_t)s, 3);  // frees the stage in BOTH CTAs
+              }
+              __syncwarp();
+              if (++s == ns) { s = 0; ph ^= 1u; }
+              if (++cb == kb) cb = 0;
+            }
+            if (elect_one()) tcgen05_commit_2sm_mc_u32(smem_u32(&acc_full[buf]), 3);
+            __syncwarp();
+          }
+        }
+      } else if (m_m2) {
         // M2: both issuers visit EVERY stage in ring order; issuer `me` multiplies rows [128 me, 128 me + 128) of
         // the 256-row A stage with the shared B stage into its own accumulator (columns me * BN).  K runs
         // sequentially in one accumulator, so the fp32 summation order equals the single-issuer path's.
         const uint32_t a_half = me * (uint32_t)(A_STAGE_BYTES >> 4), b_off = (uint32_t)g.a_stage_bytes >> 4;
         int s = 0, cb = 0;
         uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < total; tile += step, ++lt) {
+        for (int q = wk.first; q < total; q += step, ++lt) {
           const uint32_t buf = g.acc_bufs == 2 ? (lt & 1u) : 0u, cph = g.acc_bufs == 2 ? ((lt >> 1) & 1u) : (lt & 1u);
           mbar_wait(&acc_empty[buf], cph ^ 1u);
           tcgen05_fence_after();
@@ -307,7 +377,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               } else {
                 for (int k = 0; k < kc_last; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (n > 0 || k > 0) ? 1u : 0u);
               }
-              tcgen05_commit_u32(empty0 + 8u * (uint32_t)s);
+              if (mc) tcgen05_commit_mc_u32(empty0 + 8u * (uint32_t)s, 3);
+              else tcgen05_commit_u32(empty0 + 8u * (uint32_t)s);
             }
             __syncwarp();
             if (++s == ns) { s = 0; ph ^= 1u; }
@@ -316,11 +387,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (elect_one()) tcgen05_commit(&acc_full[buf]);
           __syncwarp();
         }
-      } else if (g.ksplit || !me)
-      for (int tile = blockIdx.x; tile < total; tile += step, ++lt) {
+      } else if (m_ksplit || !me)
+      for (int q = wk.first; q < total; q += step, ++lt) {
         const uint32_t buf = g.acc_bufs == 2 ? (lt & 1u) : 0u, cph = g.acc_bufs == 2 ? ((lt >> 1) & 1u) : (lt & 1u);
         // this issuer's first k-iteration of the tile: K-split ownership is by stage parity (see the producers)
-        const int f = g.ksplit ? (int)me ^ (s_base & 1) : 0;
+        const int f = m_ksplit ? (int)me ^ (s_base & 1) : 0;
         int s = s_base + f;
         uint32_t ph = ph_base;
         if (s >= ns) { s -= ns; ph ^= 1u; }
@@ -328,7 +399,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int n_own = (kiters - f + ways - 1) / ways;
         mbar_wait(&acc_empty[buf], cph ^ 1u);  // epilogue has drained this accumulator buffer
         const uint32_t acc = tbase + buf * (uint32_t)g.acc_stride + me * (uint32_t)g.BN;
-        if (g.ksplit) {
+        if (m_ksplit) {
           // two issuers, alternate k-iterations, own accumulators; while one polls its barrier the other issues
           tcgen05_fence_after();
           for (int n = 0; n < n_own; ++n) {
@@ -347,7 +418,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               } else {
                 for (int k = 0; k < kc_last; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (n > 0 || k > 0) ? 1u : 0u);
               }
-              tcgen05_commit_u32(empty0 + 8u * (uint32_t)s);
+              if (mc) tcgen05_commit_mc_u32(empty0 + 8u * (uint32_t)s, 3);
+              else tcgen05_commit_u32(empty0 + 8u * (uint32_t)s);
             }
             __syncwarp();
             if (ts) g.dbg_ts[dbg_n++ * 4 + 3] = clock64();
@@ -382,7 +454,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (elect_one()) {
               if (kc > 2) umma_bf16(acc, da + 4, db + 4, idesc, 1u);
               if (kc > 3) umma_bf16(acc, da + 6, db + 6, idesc, 1u);
-              tcgen05_commit_u32(ebar);  // frees the smem slot when these MMAs retire
+              if (mc) tcgen05_commit_mc_u32(ebar, 3);
+              else tcgen05_commit_u32(ebar);  // frees the smem slot when these MMAs retire
             }
             __syncwarp();
             if (ts) g.dbg_ts[dbg_n++ * 4 + 3] = clock64();
@@ -408,21 +481,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int ml = q * 32 + lane;
     // row -> pixel of the patch; M2 tiles have a second 128-row half (rows ml + 128, accumulator columns + BN)
     const int dyh[2] = {ml / g.TW, (ml + BM) / g.TW}, dxh[2] = {ml % g.TW, (ml + BM) % g.TW};
-    const int nh = g.m2 ? 2 : 1;
+    const int nh = m_m2 ? 2 : 1;
     const int nchunks = g.BN / 16;
     uint32_t lt = 0;
-    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++lt) {
-      const int nt = tile % g.n_tiles;
-      int t = tile / g.n_tiles;
-      const int tx = t % g.tiles_x;
-      t /= g.tiles_x;
-      const int ty = t % g.tiles_y, b = t / g.tiles_y;
+    for (int tq = wk.first; tq < g.walk_total; tq += wk.step, ++lt) {
+      int nt, tx, ty, b;
+      const bool tile_ok = tile_of(g, wk, tq, nt, tx, ty, b);
       const int n0 = nt * g.BN;
       const uint32_t buf = g.acc_bufs == 2 ? (lt & 1u) : 0u, aph = g.acc_bufs == 2 ? ((lt >> 1) & 1u) : (lt & 1u);
       bool waited = false;
       for (int h = 0; h < nh; ++h) {
       const int oy = ty * g.TH + dyh[h], ox = tx * g.TW + dxh[h];
-      const bool row_ok = oy < d.OH && ox < d.OW;
+      const bool row_ok = tile_ok && oy < d.OH && ox < d.OW;
       const size_t pix = ((size_t)b * d.OHt + (oy * d.osy + d.ooy)) * d.OWt + (ox * d.osx + d.oox);
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)g.acc_stride + (uint32_t)(h * g.BN);
 
@@ -458,7 +528,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             uint32_t ua[16], ub[16];
             tmem_ld16_issue(trow + (uint32_t)(ja * 16), ua);
             if (has_b) tmem_ld16_issue(trow + (uint32_t)(jb * 16), ub);
-            if (g.ksplit) {  // add the second issuer's accumulator (fixed order: even + odd k-iterations)
+            if (m_ksplit) {  // add the second issuer's accumulator (fixed order: even + odd k-iterations)
               uint32_t uc[16];
               tmem_ld16_issue(trow + (uint32_t)(g.BN + ja * 16), uc);
               tmem_ld_wait();
@@ -527,7 +597,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int j = half; j < nchunks; j += EPI_PARTS) {
           float v[16];
           tmem_ld16(trow + (uint32_t)(j * 16), v);
-          if (g.ksplit) {
+          if (m_ksplit) {
             float w[16];
             tmem_ld16(trow + (uint32_t)(g.BN + j * 16), w);
 #pragma unroll
@@ -562,32 +632,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // this warp's TMEM reads of the buffer are complete (tcgen05.wait::ld inside tmem_ld16): hand it back
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster_u32(mapa_u32(smem_u32(&acc_empty[buf]), 0u));  // the leader's barrier
+        else mbar_arrive(&acc_empty[buf]);
+      }
     }
   }
 
   // ---- teardown
   tcgen05_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // neither CTA frees TMEM / exits while the other may still use the pair's resources
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(g.tmem_cols));
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(g.tmem_cols));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(g.tmem_cols));
   }
 }
 
 typedef void (*ConvTcKernel)(const CUtensorMap, const CUtensorMap, const rdsic_conv_desc, const TcGeom);
 
-template <bool PLAIN>
+template <bool PLAIN, bool PAIR>
 ConvTcKernel pick_kernel(int epi) {
   switch (epi) {
-    case RDSIC_EPI_GELU: return conv_tc_kernel<RDSIC_EPI_GELU, PLAIN>;
-    case RDSIC_EPI_RES_GELU: return conv_tc_kernel<RDSIC_EPI_RES_GELU, PLAIN>;
-    case RDSIC_EPI_ADD_RES: return conv_tc_kernel<RDSIC_EPI_ADD_RES, PLAIN>;
-    case RDSIC_EPI_GATE: return conv_tc_kernel<RDSIC_EPI_GATE, PLAIN>;
-    case RDSIC_EPI_GDN: return conv_tc_kernel<RDSIC_EPI_GDN, PLAIN>;
-    case RDSIC_EPI_IGDN: return conv_tc_kernel<RDSIC_EPI_IGDN, PLAIN>;
-    case RDSIC_EPI_LRP: return conv_tc_kernel<RDSIC_EPI_LRP, PLAIN>;
-    default: return conv_tc_kernel<RDSIC_EPI_NONE, PLAIN>;
+    case RDSIC_EPI_GELU: return conv_tc_kernel<RDSIC_EPI_GELU, PLAIN, PAIR>;
+    case RDSIC_EPI_RES_GELU: return conv_tc_kernel<RDSIC_EPI_RES_GELU, PLAIN, PAIR>;
+    case RDSIC_EPI_ADD_RES: return conv_tc_kernel<RDSIC_EPI_ADD_RES, PLAIN, PAIR>;
+    case RDSIC_EPI_GATE: return conv_tc_kernel<RDSIC_EPI_GATE, PLAIN, PAIR>;
+    case RDSIC_EPI_GDN: return conv_tc_kernel<RDSIC_EPI_GDN, PLAIN, PAIR>;
+    case RDSIC_EPI_IGDN: return conv_tc_kernel<RDSIC_EPI_IGDN, PLAIN, PAIR>;
+    case RDSIC_EPI_LRP: return conv_tc_kernel<RDSIC_EPI_LRP, PLAIN, PAIR>;
+    default: return conv_tc_kernel<RDSIC_EPI_NONE, PLAIN, PAIR>;
   }
 }
 
@@ -699,7 +774,17 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   static const int tune_m2 = getenv("RDSIC_TC_M2") ? atoi(getenv("RDSIC_TC_M2")) : 3;
   static const int tune_ksplit = getenv("RDSIC_TC_KSPLIT") ? atoi(getenv("RDSIC_TC_KSPLIT")) : 1;
   static const int tune_mink = getenv("RDSIC_TC_M2_MINK") ? atoi(getenv("RDSIC_TC_M2_MINK")) : 4;
-  const bool family = !g.halo && g.num_k_iters >= tune_mink &&
+  // PAIR mode (cta_group::2, see TcGeom) replaces M2 / K-split on the wide, long-K layers.  Measured per layer at
+  // batch 24 (profiles/r2_pair_vs_m2.txt): N = 224 3x3 layers -5 ... -21 %, 5x5 s2 N = 192 -10 %, N = 1152 (BN 192)
+  // -17 %; but N <= 128 and the pointwise layers are 10-60 % SLOWER in pairs: there one k-iteration's tensor time
+  // (2 BN cycles) is below what the single issuing thread needs per k-iteration, and M2 / per-SM issuers give each
+  // SM its own issue stream.  Hence: pairs for BN >= 192 with at least 8 k-iterations.  RDSIC_TC_PAIR: 0 off,
+  // 1 this rule (default), 3 every layer with two M tiles.
+  static const int tune_pair = getenv("RDSIC_TC_PAIR") ? atoi(getenv("RDSIC_TC_PAIR")) : 1;
+  const long tiles128_all = (long)B * ceil_div(OW, g.TW) * ceil_div(OH, g.TH);
+  const bool want_pair = tune_pair && !g.halo && sms >= 2 && tiles128_all >= 2 &&
+                         (tune_pair == 3 || (g.BN >= 192 && g.num_k_iters >= 8));
+  const bool family = !g.halo && !want_pair && g.num_k_iters >= tune_mink &&
                       (4 * g.BN <= 512 || (tune_ksplit != 3 && 2 * g.BN <= 512 && g.num_k_iters >= 16));
   if (tune_m2 && family) {
     // cost of the busiest SM ~ rounds x bytes one tile streams per k-iteration (A rows + the B stage)
@@ -734,7 +819,16 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   }
   g.n_tiles = ceil_div(d->Cout, g.BN);
   g.total_tiles = m_tiles * g.n_tiles;
-  g.b_stage_bytes = g.BN * BK * 2;
+  g.m_tiles = m_tiles;
+  // MC mode (see TcGeom): CTA pairs share every B stage through TMA multicast.  RDSIC_TC_MC: 0 off, 1 on wherever
+  // there are two M tiles (default), 2 only for grids of at least one wave.
+  // (measured: correct, and no faster than without -- the shared-memory port, not L2, bounds these tiles -- so off
+  // by default; PAIR mode is the one that relieves the port)
+  static const int tune_mc = getenv("RDSIC_TC_MC") ? atoi(getenv("RDSIC_TC_MC")) : 0;
+  g.pair = want_pair && m_tiles >= 2;
+  g.mc = !g.pair && tune_mc && !g.halo && m_tiles >= 2 && sms >= 2 && (tune_mc != 2 || g.total_tiles >= sms);
+  g.walk_total = (g.mc || g.pair) ? ceil_div(m_tiles, 2) * g.n_tiles : g.total_tiles;
+  g.b_stage_bytes = (g.pair ? g.BN / 2 : g.BN) * BK * 2;  // PAIR: each CTA stages half of the B box
   const int stage_bytes = g.halo ? g.b_stage_bytes : g.a_stage_bytes + g.b_stage_bytes;
   // one persistent CTA per SM owns the whole shared memory: as deep a TMA ring as fits (the ring keeps
   // running across tiles, so even 2-3-iteration pointwise GEMMs keep many stages in flight)
@@ -752,7 +846,7 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   // The decision uses only layer properties (Cout, K) -- never the grid-dependent N split above -- so that the
   // fp32 summation order, hence every output bit, is independent of batch size and image size.
   const int bn_layer = pick_bn(d->Cout);
-  g.ksplit = tune_ksplit && !g.m2 && tune_m2 != 3 && !g.halo && g.num_k_iters >= 4 &&
+  g.ksplit = tune_ksplit && !g.m2 && !g.pair && tune_m2 != 3 && !g.halo && g.num_k_iters >= 4 &&
              (4 * bn_layer <= 512 || (tune_ksplit != 3 && 2 * bn_layer <= 512 && g.num_k_iters >= 16));
   g.acc_stride = g.BN * (1 + (g.ksplit | g.m2));
   g.acc_bufs = 2 * g.acc_stride <= 512 ? 2 : 1;
@@ -780,7 +874,7 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
     const int n_rows = (d->Cout + 15) / 16 * 16;  // the host pads the packed weight to ceil16(Cout) rows
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)n_rows};
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)g.BN};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)((g.mc || g.pair) ? g.BN / 2 : g.BN)};  // MC / PAIR: each CTA of a pair loads half
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)d->weight, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -796,13 +890,33 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   };
   const bool plain = !d->pixel_shuffle && d->Cout % 16 == 0 && vec_ok(d->out) && vec_ok(d->out2) && vec_ok(d->out3) &&
                      vec_ok(d->res) && vec_ok(d->aux) && (!d->bias || ((uintptr_t)d->bias % 16) == 0);
-  ConvTcKernel kern = plain ? pick_kernel<true>(d->epilogue) : pick_kernel<false>(d->epilogue);
+  ConvTcKernel kern = g.pair ? (plain ? pick_kernel<true, true>(d->epilogue) : pick_kernel<false, true>(d->epilogue))
+                             : (plain ? pick_kernel<true, false>(d->epilogue) : pick_kernel<false, false>(d->epilogue));
   // opt in to >48 KB dynamic smem: per (device, kernel); idempotent, so a race between host threads is harmless
-  static bool attr_set[16][2][8] = {};
-  if (!track || !attr_set[dev][plain][d->epilogue]) {
+  static bool attr_set[16][4][8] = {};
+  const int kvar = (plain ? 1 : 0) + (g.pair ? 2 : 0);
+  if (!track || !attr_set[dev][kvar][d->epilogue]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
-    if (track) attr_set[dev][plain][d->epilogue] = true;
+    if (track) attr_set[dev][kvar][d->epilogue] = true;
+  }
+  if (g.mc || g.pair) {
+    const int grid = 2 * g.walk_total < (sms & ~1) ? 2 * g.walk_total : (sms & ~1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(CONV_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, dd, g);
+    if (e != cudaSuccess) return (int)e;
+    return rdsic_launch_status();
   }
   const int grid = g.total_tiles < sms ? g.total_tiles : sms;
   kern<<<grid, CONV_THREADS, smem, stream>>>(ta, tb, dd, g);

@@ -55,7 +55,7 @@ enum { TAIL_GDN = 1, TAIL_IGDN = 2, TAIL_RU = 3 };
 // kernel shows L2->SM traffic 4.6 x the algorithmic bytes at 11.7 TB/s, i.e. at the chip's L2 throughput cap, and
 // the nine-fold re-read of A is 40 % of it.  Result: correct, but slower (see rdsic_conv_gdn_forward_bf16).
 struct K1Cfg {
-  int ns, kb, taps, kiters, kq, kr, kc_last, halo;
+  int ns, kb, taps, kiters, kq, kr, kc_last, halo, mc;
   uint32_t full0, empty0, a_u0, stage_u, b_off_u, idesc;
   uint32_t a_full0, a_empty0, patch_u0, patch_u, na_mask, na_shift, pcols;
   int nin, nout, off_in, off_out, unit_out;  // halo walk: inner / outer extents, window offset per inner / outer step
@@ -95,7 +95,8 @@ __device__ __forceinline__ void gemm1_tile(K1State& st, const K1Cfg& c, uint32_t
       const uint64_t da = c.dconst + (uint64_t)(c.a_u0 + (uint32_t)s * c.stage_u), db = da + c.b_off_u;
       if (elect_one()) {
         k1_mmas(acc1, da, db, c.idesc, cb + 1 != c.kb ? 4 : c.kc_last, n == 0);
-        tcgen05_commit_u32(c.empty0 + 8u * (uint32_t)s);
+        if (c.mc) tcgen05_commit_mc_u32(c.empty0 + 8u * (uint32_t)s, 3);
+        else tcgen05_commit_u32(c.empty0 + 8u * (uint32_t)s);
       }
       __syncwarp();
       if (c.kts && n < 64) c.kts[4 * n + 2] = clock64();
@@ -204,7 +205,7 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_g) : "memory");
     for (int s = 0; s < g.num_stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], g.mc ? 2 : 1);  // MC: the issuers of both CTAs of the pair release a stage
     }
     for (int k = 0; k < 2; ++k) {
       mbar_init(&acc1_full[k], gg.ksplit ? 2 : 1);
@@ -229,7 +230,9 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  if (g.mc) cluster_sync_all();  // the peer's barriers are initialised before any multicast copy / commit targets them
   const uint32_t tmem_base = *tmem_slot;
+  const TileWalk wk = make_walk(g);
 
   if (warp == 0 || warp == G_PRODUCER2_WARP) {
     // ================= TMA producers =================
@@ -249,8 +252,10 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       const uint32_t full0 = __shfl_sync(0xffffffffu, smem_u32(full_bar), 0);
       const uint32_t empty0 = __shfl_sync(0xffffffffu, smem_u32(empty_bar), 0);
-      int ns = g.num_stages, kb = g.kb_per_tap, kiters = d.KH * d.KW * g.kb_per_tap, total = g.total_tiles, step = gridDim.x;
+      int ns = g.num_stages, kb = g.kb_per_tap, kiters = d.KH * d.KW * g.kb_per_tap, total = g.walk_total, step = wk.step;
       int KW = d.KW, Cin = d.Cin;
+      const uint32_t b_half_off = (uint32_t)(wk.crank * (C / 2) * BK * 2);  // MC: this CTA's half of the B stage
+      const int n_half = wk.crank * (C / 2);
       asm volatile("" : "+r"(ns), "+r"(kb), "+r"(kiters), "+r"(total), "+r"(step), "+r"(KW), "+r"(Cin));
       const int kq = kiters / ns, kr = kiters % ns;
       int s_base = 0;
@@ -273,7 +278,7 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         const uint32_t ahead = (uint32_t)(gg.na - 1 < 2 ? gg.na - 1 : 2);
         uint32_t pa = 0, lt = 0;  // pa: patches requested so far (producer 0) = next global unit index to request
         const uint32_t n_local = (uint32_t)((total - (int)blockIdx.x + step - 1) / step);  // tiles of this CTA
-        for (int tile = blockIdx.x; tile < total; tile += step, ++lt) {
+        for (int tile = blockIdx.x; tile < total; tile += step, ++lt) {  // (halo mode never runs in MC pairs)
           int t = tile;
           const int tx = t % g.tiles_x;
           t /= g.tiles_x;
@@ -332,11 +337,9 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           if (s_base >= ns) { s_base -= ns; ph_base ^= 1u; }
         }
       } else
-      for (int tile = blockIdx.x; tile < total; tile += step) {
-        int t = tile;
-        const int tx = t % g.tiles_x;
-        t /= g.tiles_x;
-        const int ty = t % g.tiles_y, b = t / g.tiles_y;
+      for (int q = wk.first; q < total; q += step) {
+        int nt, tx, ty, b;
+        tile_of(g, wk, q, nt, tx, ty, b);
         const int x0 = tx * g.TW * d.stride - d.pad_w, y0 = ty * g.TH * d.stride - d.pad_h;
         const int f = pw ^ (s_base & 1);  // ownership by stage parity (even ring depth), see conv_bf16.cu
         const int n_own = (kiters - f + 1) / 2;
@@ -352,7 +355,8 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           if (elect_one()) {
             mbar_expect_tx_u32(bar, tx_bytes);
             if (!(g.dbg_skip_load & 1)) tma_load_4d_u32(a_dst, &tmap_a, bar, cb * BK, x0 + sx, y0 + r, b);
-            tma_load_2d_u32(a_dst + A_STAGE_BYTES, &tmap_b, bar, kcol + cb * BK, 0);
+            if (g.mc) tma_load_2d_mc_u32(a_dst + A_STAGE_BYTES + b_half_off, &tmap_b, bar, kcol + cb * BK, n_half, 3);
+            else tma_load_2d_u32(a_dst + A_STAGE_BYTES, &tmap_b, bar, kcol + cb * BK, 0);
           }
           __syncwarp();
           s += 2;
@@ -367,6 +371,14 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         ph_base ^= (uint32_t)(kq & 1);
         s_base += kr;
         if (s_base >= ns) { s_base -= ns; ph_base ^= 1u; }
+      }
+      if (g.mc) {  // MC drain: no multicast commit of the peer may arrive on this CTA's barriers after it has exited
+        int s = s_base;
+        uint32_t ph = ph_base;
+        for (int n = 0; n < ns; ++n) {
+          if ((s & 1) == pw) mbar_wait_u32(empty0 + 8u * (uint32_t)s, ph ^ 1u);
+          if (++s == ns) { s = 0; ph ^= 1u; }
+        }
       }
     }
     __syncwarp();
@@ -383,6 +395,7 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       c.kq = c.kiters / c.ns; c.kr = c.kiters % c.ns;
       c.kc_last = (d.Cin - (g.kb_per_tap - 1) * BK) / 16;
       c.halo = g.halo;
+      c.mc = g.mc;
       c.full0 = __shfl_sync(0xffffffffu, smem_u32(full_bar), 0);
       c.empty0 = __shfl_sync(0xffffffffu, smem_u32(empty_bar), 0);
       c.a_u0 = (smem_base & 0x3FFFFu) >> 4;
@@ -406,13 +419,13 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       c.kts = nullptr;
       K1State st = {0, 0u, 0u};
       const int ways = gg.ksplit ? 2 : 1;
-      int total = g.total_tiles, step = gridDim.x;
+      int total = g.walk_total, step = wk.step;
       asm volatile("" : "+r"(total), "+r"(step));
       uint32_t lt = 0;
       if (gg.dbl) {
         // ---- dbl mode: both issuers run ONLY main loops (K-split, own accumulator of pair lt & 1); the tail GEMM
         //      is issued by the first epilogue warp
-        for (int tile = blockIdx.x; tile < total; tile += step, ++lt) {
+        for (int q = wk.first; q < total; q += step, ++lt) {
           const uint32_t b = lt & 1u, use = (lt >> 1) & 1u;
           long long* tsp = (g.dbg_ts && blockIdx.x == 0 && !me && lane == 0 && lt < 250) ? g.dbg_ts + lt * 16 : nullptr;
           if (tsp) tsp[0] = clock64();
@@ -427,7 +440,7 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
       } else {
         const uint32_t acc1 = tbase + me * (uint32_t)C, p_t = tbase + (uint32_t)gg.p_col, acc2 = tbase + (uint32_t)gg.acc2_col;
-        for (int tile = blockIdx.x; tile < total; tile += step, ++lt) {
+        for (int q = wk.first; q < total; q += step, ++lt) {
           const uint32_t par = lt & 1u;
           // profiling aid (RDSIC_TC_DBG_TS=1, tests/gpu_ru_trace.py): 16 clock64 stamps per tile of CTA 0,
           // slots 0-5 written by issuer 0, slots 8-12 by the first epilogue warp
@@ -473,13 +486,11 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const int nchunks1 = C / 16, nchunks2 = gg.N2 / 16;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     uint32_t lt = 0;
-    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++lt) {
-      int t = tile;
-      const int tx = t % g.tiles_x;
-      t /= g.tiles_x;
-      const int ty = t % g.tiles_y, b = t / g.tiles_y;
+    for (int tq = wk.first; tq < g.walk_total; tq += wk.step, ++lt) {
+      int nt, tx, ty, b;
+      const bool tile_ok = tile_of(g, wk, tq, nt, tx, ty, b);
       const int oy = ty * g.TH + dy, ox = tx * g.TW + dx;
-      const bool row_ok = oy < d.OH && ox < d.OW;
+      const bool row_ok = tile_ok && oy < d.OH && ox < d.OW;
       const size_t pix = ((size_t)b * d.OHt + (oy * d.osy + d.ooy)) * d.OWt + (ox * d.osx + d.oox);
       const uint32_t par = lt & 1u;
       // dbl: accumulator / staged-operand buffer of this tile and the parity of ITS barriers
@@ -705,6 +716,11 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   g.BN = C;
   g.n_tiles = 1;
   g.total_tiles = B * g.tiles_y * g.tiles_x;
+  g.m_tiles = g.total_tiles;
+  static const int tune_mc = getenv("RDSIC_TC_MC") ? atoi(getenv("RDSIC_TC_MC")) : 0;  // measured: no gain, off
+  int sms = rdsic_sm_count();
+  g.mc = tune_mc && !g.halo && g.m_tiles >= 2 && sms >= 2 && (tune_mc != 2 || g.total_tiles >= sms);  // see TcGeom
+  g.walk_total = g.mc ? ceil_div(g.m_tiles, 2) : g.total_tiles;
   g.kb_per_tap = ceil_div(d->Cin, BK);
   g.num_k_iters = d->KH * d->KW * g.kb_per_tap;
   g.b_stage_bytes = C * BK * 2;
@@ -768,16 +784,16 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return RDSIC_E_ARG;
   }
-  auto encode_2d = [&](CUtensorMap* tm, const void* ptr, int K, int rows) {
+  auto encode_2d = [&](CUtensorMap* tm, const void* ptr, int K, int rows, int box_rows) {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)rows};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   };
-  if (encode_2d(&tb, d->weight, d->KH * d->KW * d->Cin, C) != CUDA_SUCCESS) return RDSIC_E_ARG;
-  if (encode_2d(&tg, d->tail_weight, C, N2) != CUDA_SUCCESS) return RDSIC_E_ARG;
+  if (encode_2d(&tb, d->weight, d->KH * d->KW * d->Cin, C, g.mc ? C / 2 : C) != CUDA_SUCCESS) return RDSIC_E_ARG;  // MC: half per CTA
+  if (encode_2d(&tg, d->tail_weight, C, N2, N2) != CUDA_SUCCESS) return RDSIC_E_ARG;
 
 #ifdef RDSIC_DEBUG
   {  // debug: barrier-timeout log (see tc_common.cuh)
@@ -803,9 +819,24 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
     if (e != cudaSuccess) return (int)e;
     if (track) attr_set[dev][d->tail_mode] = true;
   }
-  int sms = 0;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (sms <= 0) sms = 148;
+  if (g.mc) {
+    const int grid = 2 * g.walk_total < (sms & ~1) ? 2 * g.walk_total : (sms & ~1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(G_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tg, dd, g, gg);
+    if (e != cudaSuccess) return (int)e;
+    return rdsic_launch_status();
+  }
   const int grid = g.total_tiles < sms ? g.total_tiles : sms;
   kern<<<grid, G_THREADS, smem, stream>>>(ta, tb, tg, dd, g, gg);
   return rdsic_launch_status();

@@ -33,7 +33,45 @@ struct TcGeom {
   // warps each own a 128-row half (own accumulator) and share every B stage, which halves the weight bytes
   // streamed from L2 per output row.  a_stage_bytes = 16 KB (plain) or 32 KB (M2).
   int m2, a_stage_bytes;
+  // MC mode (B multicast in CTA pairs): the kernel is launched in clusters of two CTAs that walk pair-tiles -- two
+  // M tiles with the SAME n tile -- in lockstep.  Each CTA loads its own A box and HALF of the B box, multicast into
+  // the shared memory of both (cp.async.bulk.tensor ... .multicast::cluster), so the weight bytes every SM pulls
+  // from L2 halve; every issuer's tcgen05.commit releases the stage in both CTAs (multicast commit), so a stage is
+  // refilled only when both SMs have finished reading it.  Pure data movement: the fp32 summation order is unchanged.
+  int mc, m_tiles, walk_total;  // walk_total: pair-tiles (mc / pair) or tiles
+  // PAIR mode (cta_group::2): the two CTAs of a cluster -- two SMs of one TPC -- execute ONE 256 x BN UMMA per K step.
+  // Each CTA stages its own 128-row A box and HALF of the B box (rows [rank * BN/2, +BN/2)); the leader CTA's issuer
+  // warp issues tcgen05.mma.cta_group::2 for both, each SM accumulating its 128 rows in its own TMEM.  Per k-iteration
+  // an SM's shared-memory port then carries 2 (A + B/2) bytes instead of 2 (A + B) -- the port, not L2, is what bounds
+  // the 1-CTA tiles (MC mode halves the L2 bytes of B and measures no faster) -- and one MMA issue covers 256 rows.
+  // Both CTAs' TMA loads complete on the LEADER's full barrier; the leader's commits are multicast to both CTAs'
+  // empty / accumulator-full barriers; both CTAs' epilogue warps arrive on the leader's accumulator-empty barrier.
+  int pair;
 };
+
+// walk of a persistent CTA over its tiles: q = first, first + step, ... < g.walk_total; tile_of() maps q to
+// (n tile, m tile); m tiles past g.m_tiles (the odd one out of the last pair) decode to an out-of-range image
+// index, so their TMA boxes are zero-filled and the epilogue stores nothing
+struct TileWalk {
+  int first, step, crank;
+};
+__device__ __forceinline__ TileWalk make_walk(const TcGeom& g) {
+  TileWalk w;
+  if (g.mc || g.pair) { w.first = (int)(blockIdx.x >> 1); w.step = (int)(gridDim.x >> 1); w.crank = (int)(blockIdx.x & 1u); }
+  else { w.first = (int)blockIdx.x; w.step = (int)gridDim.x; w.crank = 0; }
+  return w;
+}
+__device__ __forceinline__ bool tile_of(const TcGeom& g, const TileWalk& w, int q, int& nt, int& tx, int& ty, int& b) {
+  nt = q % g.n_tiles;
+  int t = q / g.n_tiles;
+  if (g.mc || g.pair) t = 2 * t + w.crank;
+  const bool valid = t < g.m_tiles;
+  tx = t % g.tiles_x;
+  t /= g.tiles_x;
+  ty = t % g.tiles_y;
+  b = t / g.tiles_y;
+  return valid;
+}
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -144,6 +182,56 @@ __device__ __forceinline__ void tma_load_2d_u32(uint32_t dst, const CUtensorMap*
       ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// MC mode: the box goes to the same shared-memory offset of every CTA in `mask`, and completes `bytes` on the
+// mbarrier at the same offset of each of them
+__device__ __forceinline__ void tma_load_2d_mc_u32(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// arrives (once the issuer's earlier MMAs retire) on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tcgen05_commit_mc_u32(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+// ---- cta_group::2 (PAIR mode) forms
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta_rank) {  // same offset in CTA `cta_rank`'s window
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster_u32(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: the data lands in the executing CTA's shared memory, the bytes complete on `bar`, a
+// shared::cluster address that may lie in the peer (leader) CTA
+__device__ __forceinline__ void tma_load_4d_2sm_u32(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm_u32(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_2sm_mc_u32(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+// D[tmem, 256 rows over the CTA pair] (+)= A * B^T; issued by ONE thread of the leader CTA
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {  // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -183,8 +271,8 @@ __device__ __forceinline__ uint64_t make_sw128_desc_ex(uint32_t smem_addr, uint3
 }
 
 // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=bn
-__device__ __forceinline__ uint32_t make_idesc(int bn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(int bn, int m = BM) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // tcgen05.ld is asynchronous: issue any number of loads, then tmem_ld_wait(), then pass every destination

@@ -254,6 +254,9 @@ def test_patchify_matches_unfold(C, k, s, p, B, H, W):
     {"RDSIC_TC_M2": "0"},                            # M2 off
     {"RDSIC_TC_M2_MINK": "1", "RDSIC_TC_M2": "2"},   # M2 also for the 1-3 k-iteration pointwise GEMMs
     {"RDSIC_RU_DBL": "0"},                           # single-buffered fused ResidualUnit kernel
+    {"RDSIC_TC_PAIR": "3"},                          # cta_group::2 CTA pairs on EVERY layer with two M tiles (default: wide long-K layers)
+    {"RDSIC_TC_PAIR": "0"},                          # no CTA pairs (M2 / single-issuer tiles everywhere)
+    {"RDSIC_TC_PAIR": "0", "RDSIC_TC_MC": "1"},      # 1-CTA tiles with the B stage multicast across a CTA pair
 ], ids=lambda e: ",".join(f"{k[6:]}={v}" for k, v in e.items()))
 def test_kernel_mode_switches_in_subprocess(env):
     """Every kernel mode behind a tuning switch stays correct: the conv / deconv / fused-layer parity tests pass with

@@ -12,6 +12,8 @@
 // Floating-point op order follows the reference exactly:
 // explicit __fmul_rn/__fadd_rn/__fsub_rn keep nvcc from contracting into FMAs
 // where the reference rounds twice.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -52,13 +54,23 @@ __device__ __forceinline__ float eb_logits(const float* __restrict__ p, float v)
 
 __device__ __forceinline__ float sigmoid_ref(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
 
-__global__ void eb_forward_kernel(const rdsic_eb_desc d) {
+// One persistent block per SM.  Consecutive threads take consecutive channels (z is channels-last), so reading the
+// 60 per-channel parameters straight from global memory makes every one of the ~120 loads per element touch 32
+// different cache lines (the first version: 41 us for 0.44 M elements).  The table (C x 60 floats, 46 KB at C = 192)
+// is therefore staged once per block in shared memory, at a row pitch of 61 words so that the 32 channels of a warp
+// fall into 32 different banks.
+constexpr int EB_PITCH = RDSIC_EB_STRIDE + 1;
+__global__ void __launch_bounds__(256) eb_forward_kernel(const rdsic_eb_desc d) {
+  extern __shared__ float s_par[];  // [C][EB_PITCH]
+  for (int i = threadIdx.x; i < d.C * RDSIC_EB_STRIDE; i += blockDim.x)
+    s_par[(i / RDSIC_EB_STRIDE) * EB_PITCH + i % RDSIC_EB_STRIDE] = d.params[i];
+  __syncthreads();
   const size_t total = (size_t)d.B * d.h * d.w * d.C;
   const int hw = d.h * d.w;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(e % d.C);
     const size_t pix = e / d.C;
-    const float* p = d.params + (size_t)c * RDSIC_EB_STRIDE;
+    const float* p = s_par + (size_t)c * EB_PITCH;
     const float med = p[EB_MED];
     const float z = ((const float*)d.z.ptr)[pix * d.z.ld + d.z.coff + c];
     const float r = rintf(__fsub_rn(z, med));  // torch.round = half-to-even
@@ -86,6 +98,37 @@ __global__ void eb_forward_kernel(const rdsic_eb_desc d) {
 constexpr int GC_TP = 32;  // pixels per tile
 constexpr int GC_TC = 32;  // channels per tile
 
+// one element of GaussianConditional.forward + quantise + index build (the reference's fp32 op order)
+struct GcOut {
+  float yh, yl, lik;
+  int sym, idx;
+};
+__device__ __forceinline__ GcOut gc_element(const rdsic_gc_desc& d, const float* s_tab, int nt, float y, float mu, float sc,
+                                            float msk, float noise, bool has_mask, bool has_noise, bool from_sym, float r_in) {
+  GcOut o;
+  if (has_mask) sc = __fmul_rn(sc, msk);  // ResDSIC progressive stream: scale * mask, rint(y - mu) * mask + mu
+  const float r = from_sym ? r_in : rintf(__fsub_rn(y, mu));
+  const float rm = has_mask ? __fmul_rn(r, msk) : r;
+  o.yh = __fadd_rn(rm, mu);
+  o.yl = __fadd_rn(r, mu);  // where the likelihood is evaluated: round(y - mu) + mu (eval) or y + noise (training)
+  if (has_noise) o.yl = __fadd_rn(y, noise);
+  const float cst = -0.70710678118654752440f;  // float(-(2 ** -0.5))
+  const float v = fabsf(__fsub_rn(o.yl, mu));
+  const float s = fmaxf(sc, d.scale_bound);
+  const float up = __fmul_rn(0.5f, erfcf(__fmul_rn(cst, __fdiv_rn(__fsub_rn(0.5f, v), s))));
+  const float lo = __fmul_rn(0.5f, erfcf(__fmul_rn(cst, __fdiv_rn(__fsub_rn(-0.5f, v), s))));
+  o.lik = fmaxf(__fsub_rn(up, lo), d.lik_bound);
+  // idx = #{t in table[:-1] : t < s}  ==  (n-1) - #{t : s <= t}; table ascending
+  int lo_i = 0, hi_i = nt;
+  while (lo_i < hi_i) {
+    const int mid = (lo_i + hi_i) >> 1;
+    if (s_tab[mid] < s) lo_i = mid + 1; else hi_i = mid;
+  }
+  o.sym = (int)rm;
+  o.idx = lo_i;
+  return o;
+}
+
 __global__ void __launch_bounds__(256) gc_forward_kernel(const rdsic_gc_desc d) {
   __shared__ float s_lik[GC_TC][GC_TP + 1];
   __shared__ int s_sym[GC_TC][GC_TP + 1];
@@ -100,50 +143,29 @@ __global__ void __launch_bounds__(256) gc_forward_kernel(const rdsic_gc_desc d) 
   for (int i = threadIdx.x; i < nt; i += blockDim.x) s_tab[i] = d.table[i];
   __syncthreads();
 
-  const float cst = -0.70710678118654752440f;  // float(-(2 ** -0.5))
   const int c = c0 + tx;
   for (int pp = ty; pp < GC_TP; pp += 8) {
     const size_t pix = p0 + pp;
     if (pix >= npix || c >= d.Cs) continue;
     const float mu = ((const float*)d.mu.ptr)[pix * d.mu.ld + d.mu.coff + c];
-    float sc = ((const float*)d.scale.ptr)[pix * d.scale.ld + d.scale.coff + c];
-    float msk = 1.f;
-    if (d.mask.ptr) {  // ResDSIC progressive stream: scale * mask, rint(y - mu) * mask + mu
-      msk = ((const float*)d.mask.ptr)[pix * d.mask.ld + d.mask.coff + c];
-      sc = __fmul_rn(sc, msk);
-    }
-    float y = 0.f, r;
+    const float sc = ((const float*)d.scale.ptr)[pix * d.scale.ld + d.scale.coff + c];
+    const float msk = d.mask.ptr ? ((const float*)d.mask.ptr)[pix * d.mask.ld + d.mask.coff + c] : 1.f;
+    float y = 0.f, r = 0.f;
     if (d.sym_in) {  // decoder side: the symbol comes from the entropy decoder
       const size_t bb = pix / hw, yx = pix % hw;
       r = (float)d.sym_in[(bb * d.Ctot + d.lik_coff + c) * (size_t)hw + yx];
     } else {
       y = ((const float*)d.y.ptr)[pix * d.y.ld + d.y.coff + c];
-      r = rintf(__fsub_rn(y, mu));
     }
-    const float rm = d.mask.ptr ? __fmul_rn(r, msk) : r;
-    const float yh = __fadd_rn(rm, mu);
-    float yl = __fadd_rn(r, mu);  // where the likelihood is evaluated: round(y - mu) + mu (eval) or y + noise (training)
-    if (d.noise.ptr) {
-      yl = __fadd_rn(y, ((const float*)d.noise.ptr)[pix * d.noise.ld + d.noise.coff + c]);
-      if (d.noisy_out.ptr) ((float*)d.noisy_out.ptr)[pix * d.noisy_out.ld + d.noisy_out.coff + c] = yl;
-    }
-    const float v = fabsf(__fsub_rn(yl, mu));
-    const float s = fmaxf(sc, d.scale_bound);
-    const float up = __fmul_rn(0.5f, erfcf(__fmul_rn(cst, __fdiv_rn(__fsub_rn(0.5f, v), s))));
-    const float lo = __fmul_rn(0.5f, erfcf(__fmul_rn(cst, __fdiv_rn(__fsub_rn(-0.5f, v), s))));
-    const float lik = fmaxf(__fsub_rn(up, lo), d.lik_bound);
-    // idx = #{t in table[:-1] : t < s}  ==  (n-1) - #{t : s <= t}; table ascending
-    int lo_i = 0, hi_i = nt;
-    while (lo_i < hi_i) {
-      const int mid = (lo_i + hi_i) >> 1;
-      if (s_tab[mid] < s) lo_i = mid + 1; else hi_i = mid;
-    }
+    const float nz = d.noise.ptr ? ((const float*)d.noise.ptr)[pix * d.noise.ld + d.noise.coff + c] : 0.f;
+    const GcOut o = gc_element(d, s_tab, nt, y, mu, sc, msk, nz, d.mask.ptr != nullptr, d.noise.ptr != nullptr, d.sym_in != nullptr, r);
+    if (d.noise.ptr && d.noisy_out.ptr) ((float*)d.noisy_out.ptr)[pix * d.noisy_out.ld + d.noisy_out.coff + c] = o.yl;
 #pragma unroll
     for (int k = 0; k < 3; ++k)
-      if (d.y_hat[k].ptr) st_elem(d.y_hat[k].ptr, d.y_hat[k].dtype, pix * d.y_hat[k].ld + d.y_hat[k].coff + c, yh);
-    s_lik[tx][pp] = lik;
-    s_sym[tx][pp] = (int)rm;
-    s_idx[tx][pp] = lo_i;
+      if (d.y_hat[k].ptr) st_elem(d.y_hat[k].ptr, d.y_hat[k].dtype, pix * d.y_hat[k].ld + d.y_hat[k].coff + c, o.yh);
+    s_lik[tx][pp] = o.lik;
+    s_sym[tx][pp] = o.sym;
+    s_idx[tx][pp] = o.idx;
   }
   __syncthreads();
   // transposed write-out: tx = pixel (contiguous in NCHW), ty strides channels
@@ -157,6 +179,91 @@ __global__ void __launch_bounds__(256) gc_forward_kernel(const rdsic_gc_desc d) 
       d.lik[o] = s_lik[cc][tx];
       if (d.symbols) d.symbols[o] = s_sym[cc][tx];
       if (d.indexes) d.indexes[o] = s_idx[cc][tx];
+    }
+  }
+}
+
+// 128-bit form of the same kernel (the host selects it when every view allows it: channel counts / offsets / row
+// pitches that are multiples of 4 floats, 16-byte aligned bases, h*w a multiple of 4).  A tile is still 32 pixels x
+// 32 channels; on the way in a thread owns 4 consecutive CHANNELS of one pixel (one LDG.128 per operand, a warp
+// reads four 128-byte pixel rows), on the way out -- through a shared-memory transpose -- 4 consecutive PIXELS of one
+// channel (one STG.128 each for likelihood / symbols / indexes in the module's NCHW output).
+constexpr int GC_VP = GC_TP + 4;  // transposed tile pitch: rows stay 16-byte aligned
+__device__ __forceinline__ float4 ldg4(const rdsic_view& v, size_t pix, int c) {
+  return __ldg(reinterpret_cast<const float4*>((const float*)v.ptr + pix * v.ld + v.coff + c));
+}
+__global__ void __launch_bounds__(256) gc_forward_vec_kernel(const rdsic_gc_desc d) {
+  __shared__ __align__(16) float s_lik[GC_TC][GC_VP];
+  __shared__ __align__(16) int s_sym[GC_TC][GC_VP];
+  __shared__ __align__(16) int s_idx[GC_TC][GC_VP];
+  __shared__ float s_tab[128];
+  const int hw = d.h * d.w;
+  const size_t npix = (size_t)d.B * hw;
+  const size_t p0 = (size_t)blockIdx.x * GC_TP;
+  const int c0 = blockIdx.y * GC_TC;
+  const int nt = d.n_table - 1;
+  for (int i = threadIdx.x; i < nt; i += blockDim.x) s_tab[i] = d.table[i];
+  __syncthreads();
+
+  {
+    const int cg = threadIdx.x % 8, pp = threadIdx.x / 8;  // 8 channel quads x 32 pixels
+    const size_t pix = p0 + pp;
+    const int c = c0 + 4 * cg;
+    if (pix < npix && c < d.Cs) {
+      const bool has_mask = d.mask.ptr != nullptr, has_noise = d.noise.ptr != nullptr, from_sym = d.sym_in != nullptr;
+      const float4 mu4 = ldg4(d.mu, pix, c), sc4 = ldg4(d.scale, pix, c);
+      float4 y4 = make_float4(0.f, 0.f, 0.f, 0.f), m4 = make_float4(1.f, 1.f, 1.f, 1.f), n4 = y4, r4 = y4;
+      if (from_sym) {
+        const size_t bb = pix / hw, yx = pix % hw;
+        const int32_t* sp = d.sym_in + (bb * d.Ctot + d.lik_coff + c) * (size_t)hw + yx;
+        r4 = make_float4((float)sp[0], (float)sp[hw], (float)sp[2 * (size_t)hw], (float)sp[3 * (size_t)hw]);
+      } else {
+        y4 = ldg4(d.y, pix, c);
+      }
+      if (has_mask) m4 = ldg4(d.mask, pix, c);
+      if (has_noise) n4 = ldg4(d.noise, pix, c);
+      const float ys[4] = {y4.x, y4.y, y4.z, y4.w}, mus[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, scs[4] = {sc4.x, sc4.y, sc4.z, sc4.w};
+      const float ms[4] = {m4.x, m4.y, m4.z, m4.w}, ns[4] = {n4.x, n4.y, n4.z, n4.w}, rs[4] = {r4.x, r4.y, r4.z, r4.w};
+      float yh[4], yl[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const GcOut o = gc_element(d, s_tab, nt, ys[i], mus[i], scs[i], ms[i], ns[i], has_mask, has_noise, from_sym, rs[i]);
+        yh[i] = o.yh;
+        yl[i] = o.yl;
+        s_lik[4 * cg + i][pp] = o.lik;
+        s_sym[4 * cg + i][pp] = o.sym;
+        s_idx[4 * cg + i][pp] = o.idx;
+      }
+      if (has_noise && d.noisy_out.ptr)
+        *reinterpret_cast<float4*>((float*)d.noisy_out.ptr + pix * d.noisy_out.ld + d.noisy_out.coff + c) = make_float4(yl[0], yl[1], yl[2], yl[3]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const rdsic_view& v = d.y_hat[k];
+        if (!v.ptr) continue;
+        const size_t e = pix * v.ld + v.coff + c;
+        if (v.dtype == RDSIC_BF16) {
+          __nv_bfloat162 a = __floats2bfloat162_rn(yh[0], yh[1]), b = __floats2bfloat162_rn(yh[2], yh[3]);
+          uint2 u;
+          u.x = *reinterpret_cast<uint32_t*>(&a);
+          u.y = *reinterpret_cast<uint32_t*>(&b);
+          *reinterpret_cast<uint2*>((__nv_bfloat16*)v.ptr + e) = u;
+        } else {
+          *reinterpret_cast<float4*>((float*)v.ptr + e) = make_float4(yh[0], yh[1], yh[2], yh[3]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int pg = threadIdx.x % 8, cc = threadIdx.x / 8;  // 8 pixel quads x 32 channels
+    const size_t pix = p0 + 4 * pg;
+    const int ch = c0 + cc;
+    if (pix < npix && ch < d.Cs) {  // npix and p0 are multiples of 4: a quad is inside the tensor and inside one image
+      const size_t b = pix / hw, yx = pix % hw;
+      const size_t o = (b * d.Ctot + d.lik_coff + ch) * (size_t)hw + yx;
+      *reinterpret_cast<float4*>(d.lik + o) = *reinterpret_cast<const float4*>(&s_lik[cc][4 * pg]);
+      if (d.symbols) *reinterpret_cast<int4*>(d.symbols + o) = *reinterpret_cast<const int4*>(&s_sym[cc][4 * pg]);
+      if (d.indexes) *reinterpret_cast<int4*>(d.indexes + o) = *reinterpret_cast<const int4*>(&s_idx[cc][4 * pg]);
     }
   }
 }
@@ -412,8 +519,15 @@ extern "C" int rdsic_eb_forward(const rdsic_eb_desc* d, rdsic_stream_t stream) {
   RDSIC_CHECK_ARG(!d->noise.ptr || (d->noise.dtype == RDSIC_F32 && !d->noise.nchw));
   RDSIC_CHECK_ARG(!d->noisy_out.ptr || (d->noise.ptr && d->noisy_out.dtype == RDSIC_F32 && !d->noisy_out.nchw));
   const size_t total = (size_t)d->B * d->h * d->w * d->C;
-  const int nblk = (int)((total + 255) / 256 < (size_t)rdsic_sm_count() * 8 ? (total + 255) / 256 : (size_t)rdsic_sm_count() * 8);
-  eb_forward_kernel<<<nblk, 256, 0, (cudaStream_t)stream>>>(*d);
+  const size_t smem = (size_t)d->C * EB_PITCH * sizeof(float);
+  RDSIC_CHECK_ARG(smem <= 200 * 1024);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(eb_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const size_t want = (total + 255) / 256, cap = (size_t)rdsic_sm_count() * 2;
+  const int nblk = (int)(want < cap ? want : cap);
+  eb_forward_kernel<<<nblk, 256, smem, (cudaStream_t)stream>>>(*d);
   return rdsic_launch_status();
 }
 
@@ -429,6 +543,16 @@ extern "C" int rdsic_gc_forward(const rdsic_gc_desc* d, rdsic_stream_t stream) {
   RDSIC_CHECK_ARG(!d->mask.ptr || (d->mask.dtype == RDSIC_F32 && !d->mask.nchw));
   const size_t npix = (size_t)d->B * d->h * d->w;
   dim3 grid((unsigned)((npix + GC_TP - 1) / GC_TP), (unsigned)ceil_div(d->Cs, GC_TC));
-  gc_forward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d);
+  // 128-bit path: every view addressed in whole float4 / bf16x4 units, NCHW quads inside one image
+  auto v4 = [](const rdsic_view& v, int esz) {
+    return !v.ptr || (v.ld % 4 == 0 && v.coff % 4 == 0 && ((uintptr_t)v.ptr % (size_t)(4 * esz)) == 0);
+  };
+  bool vec = d->Cs % 4 == 0 && (d->h * d->w) % 4 == 0 && d->lik_coff >= 0 && v4(d->mu, 4) && v4(d->scale, 4) &&
+             (d->sym_in || v4(d->y, 4)) && v4(d->noise, 4) && v4(d->noisy_out, 4) && v4(d->mask, 4) &&
+             ((uintptr_t)d->lik % 16) == 0 && ((uintptr_t)d->symbols % 16) == 0 && ((uintptr_t)d->indexes % 16) == 0;
+  for (int k = 0; k < 3; ++k) vec = vec && v4(d->y_hat[k], d->y_hat[k].dtype == RDSIC_BF16 ? 2 : 4);
+  static const int tune_vec = getenv("RDSIC_GC_VEC") ? atoi(getenv("RDSIC_GC_VEC")) : 1;
+  if (vec && tune_vec) gc_forward_vec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d);
+  else gc_forward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d);
   return rdsic_launch_status();
 }

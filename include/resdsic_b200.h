@@ -28,13 +28,14 @@
 #ifndef RESDSIC_B200_H
 #define RESDSIC_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define RDSIC_ABI_VERSION 4
+#define RDSIC_ABI_VERSION 5
 
 typedef void* rdsic_stream_t; /* cudaStream_t */
 
@@ -306,6 +307,61 @@ int rdsic_copy_forward(const rdsic_copy_desc* d, rdsic_stream_t stream);
 int rdsic_ln_forward(const rdsic_ln_desc* d, rdsic_stream_t stream);
 int rdsic_patch_forward(const rdsic_patch_desc* d, rdsic_stream_t stream);
 int rdsic_mask_forward(const rdsic_mask_desc* d, rdsic_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Training: backward ("_bwd") twins of the forward kernels, fp32 (BASELINE config 4; SURVEY 8b "+ _bwd twins").
+ * They replace what torch autograd runs for the reference's training step (training/step.py:42-56 with
+ * RateDistortionLoss, training/loss.py:6-30); resdsic_b200/training/functions.py wraps each forward / backward
+ * pair as a torch.autograd.Function.  All tensors fp32; `g_*` / `d*` are gradients. */
+
+/* d input of a convolution: in = d x [B,H,W,Cin] (WRITTEN), out = d(conv output) [B,OH,OW,Cout] (read, Cout % 16 == 0),
+ * geometry (KH, KW, stride, pad, OH, OW) of the FORWARD conv; wt_dgrad = the forward weight packed [Cin][KH*KW*Cout]
+ * (tap-major, output-channel-minor).  Also the backward of nn.Linear / the GDN contraction (1x1), and -- with the
+ * roles of in/out swapped by the caller -- nothing else: a transposed conv's d input is rdsic_conv_forward. */
+int rdsic_conv_dgrad_f32(const rdsic_conv_desc* d, const float* wt_dgrad, rdsic_stream_t stream);
+/* d weight (+ d bias, optional): in = x (read, NHWC or NCHW), out = d(conv output) (read); dw [Cout][KH*KW*Cin] in the
+ * forward's packed layout and db [Cout] are zeroed, then accumulated with fp32 atomics (pixels split over CTAs).
+ * A transposed conv's d weight is the same call with x and d out exchanged (WACNN/utils.py:126-134). */
+int rdsic_conv_wgrad_f32(const rdsic_conv_desc* d, float* dw, float* db, rdsic_stream_t stream);
+
+/* Elementwise forward / backward nodes over flat fp32 arrays of n elements (unused operands NULL):
+ *   ADD o0=a+b | GELU_FWD o0=gelu(a) | GELU_BWD o0=a*gelu'(b) | GATE_FWD o0=a*sigmoid(b)+c (layers.py:83-89) |
+ *   GATE_BWD (a=g, b=gate operand, c=logits) o0=d operand, o1=d logits | GDN_FWD o0=a*rsqrt(b) (alpha>0: a*sqrt(b);
+ *   gdn.py:70-75) | GDN_BWD (a=g, b=x, c=norm) o0=d x (direct term), o1=d norm | SQUARE_FWD o0=a^2 | SQUARE_BWD
+ *   o0=2*a*b | LRP_FWD o0=a+0.5*tanh(b) (cnn.py:179-182) | LRP_BWD o0=a*0.5*(1-tanh(b)^2) | RECIP_SCALE o0=alpha/a |
+ *   DIFF_SCALE o0=alpha*(a-b) | SCALE o0=alpha*a | MUL o0=a*b. */
+enum { RDSIC_PW_ADD = 0, RDSIC_PW_GELU_FWD, RDSIC_PW_GELU_BWD, RDSIC_PW_GATE_FWD, RDSIC_PW_GATE_BWD, RDSIC_PW_GDN_FWD,
+       RDSIC_PW_GDN_BWD, RDSIC_PW_SQUARE_FWD, RDSIC_PW_SQUARE_BWD, RDSIC_PW_LRP_FWD, RDSIC_PW_LRP_BWD,
+       RDSIC_PW_RECIP_SCALE, RDSIC_PW_DIFF_SCALE, RDSIC_PW_SCALE, RDSIC_PW_MUL };
+int rdsic_pointwise_f32(int op, size_t n, const float* a, const float* b, const float* c, float* o0, float* o1, float alpha,
+                        rdsic_stream_t stream);
+/* nn.PixelShuffle(2) on NHWC: in [B,H,W,4C] -> out [B,2H,2W,C]; inverse != 0: the other way (its backward). */
+int rdsic_pixel_shuffle_f32(int inverse, const float* in, float* out, int B, int H, int W, int C, rdsic_stream_t stream);
+
+/* Backward of rdsic_attn_forward (win_attention.py:94-112): d->qkv = the forward's qkv, dout = d out [B,H,W,C];
+ * writes dqkv [B,H,W,3C] (every element once) and accumulates d relative_position_bias_table
+ * [(2*ws-1)^2][heads] (zeroed first). */
+int rdsic_attn_backward_f32(const rdsic_attn_desc* d, const rdsic_view* dout, const rdsic_view* dqkv, float* dbias,
+                            rdsic_stream_t stream);
+
+/* Backward of rdsic_gc_forward in noise (training) mode: d carries the forward's y / mu / scale / noise views and
+ * bounds; g_lik has the layout of d->lik (NCHW [B,Ctot,h,w], slice at lik_coff); g_yhat (optional) = gradient of
+ * y_hat = ste_round(y - mu) + mu (cnn.py:177; identity to y, zero to mu).  LowerBound rule of ops/bound_ops.py:25-27
+ * on scale (0.11) and on the likelihood (1e-9).  Writes dy, dmu, dscale [B,h,w,Cs]. */
+int rdsic_gc_backward(const rdsic_gc_desc* d, const float* g_lik, const rdsic_view* g_yhat, const rdsic_view* dy,
+                      const rdsic_view* dmu, const rdsic_view* dscale, rdsic_stream_t stream);
+/* Backward of rdsic_eb_forward in noise mode (entropy_models.py:401-434, sign detached :429-430): g_lik NCHW [B,C,h,w];
+ * g_zhat (optional) = gradient of z_hat = ste_round(z - median) + median (identity to z); writes dz [B,h,w,C] and
+ * dparams [C][RDSIC_EB_STRIDE] = gradient w.r.t. the PACKED parameters (softplus(matrix) | bias | tanh(factor)). */
+int rdsic_eb_backward(const rdsic_eb_desc* d, const float* g_lik, const rdsic_view* g_zhat, const rdsic_view* dz,
+                      float* dparams, rdsic_stream_t stream);
+/* Backward of rdsic_eb_aux_loss w.r.t. `quantiles` only (entropy_models.py:396-399): dquantiles [C][3], g = d loss. */
+int rdsic_eb_aux_backward(const float* params, const float* quantiles, const float* target, int C, float g,
+                          float* dquantiles, rdsic_stream_t stream);
+/* Reductions of RateDistortionLoss (training/loss.py:24-28), fp64 accumulation into *out (device, zeroed here):
+ *   SUM sum(a) | SUM_LOG sum(log a) | SSE sum((a-b)^2). */
+enum { RDSIC_RED_SUM = 0, RDSIC_RED_SUM_LOG = 1, RDSIC_RED_SSE = 2 };
+int rdsic_reduce_f32(int op, size_t n, const float* a, const float* b, double* out, rdsic_stream_t stream);
 
 /* Launch a whole program in order on `stream`.  *n_launched (optional) receives
  * the number of kernels launched.  Stops at the first error; *failed_op

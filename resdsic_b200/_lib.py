@@ -110,7 +110,13 @@ EXPORTS = (
     "rdsic_gc_cdf_sizes", "rdsic_gc_pmf", "rdsic_eb_cdf_sizes", "rdsic_eb_pmf", "rdsic_pmf_to_quantized_cdf",
     "rdsic_copy_forward", "rdsic_ln_forward", "rdsic_patch_forward", "rdsic_mask_forward", "rdsic_run_program",
     "rdsic_graph_create", "rdsic_graph_launch", "rdsic_graph_num_kernels", "rdsic_graph_destroy",
+    # training: backward twins (include/resdsic_b200.h, "Training")
+    "rdsic_conv_dgrad_f32", "rdsic_conv_wgrad_f32", "rdsic_pointwise_f32", "rdsic_pixel_shuffle_f32",
+    "rdsic_attn_backward_f32", "rdsic_gc_backward", "rdsic_eb_backward", "rdsic_eb_aux_backward", "rdsic_reduce_f32",
 )
+(PW_ADD, PW_GELU_FWD, PW_GELU_BWD, PW_GATE_FWD, PW_GATE_BWD, PW_GDN_FWD, PW_GDN_BWD, PW_SQUARE_FWD, PW_SQUARE_BWD,
+ PW_LRP_FWD, PW_LRP_BWD, PW_RECIP_SCALE, PW_DIFF_SCALE, PW_SCALE, PW_MUL) = range(15)
+RED_SUM, RED_SUM_LOG, RED_SSE = range(3)
 
 _lib = None
 
@@ -150,7 +156,19 @@ def lib():
     L.rdsic_graph_num_kernels.argtypes = [C.c_void_p]
     L.rdsic_graph_destroy.argtypes = [C.c_void_p]
     L.rdsic_graph_destroy.restype = None
-    if L.rdsic_abi_version() != 4:
+    pv = C.POINTER(View)
+    for fn, args in (("rdsic_conv_dgrad_f32", [C.POINTER(ConvDesc), vp, vp]),
+                     ("rdsic_conv_wgrad_f32", [C.POINTER(ConvDesc), vp, vp, vp]),
+                     ("rdsic_pointwise_f32", [C.c_int, C.c_size_t, vp, vp, vp, vp, vp, C.c_float, vp]),
+                     ("rdsic_pixel_shuffle_f32", [C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+                     ("rdsic_attn_backward_f32", [C.POINTER(AttnDesc), pv, pv, vp, vp]),
+                     ("rdsic_gc_backward", [C.POINTER(GCDesc), vp, pv, pv, pv, pv, vp]),
+                     ("rdsic_eb_backward", [C.POINTER(EBDesc), vp, pv, pv, vp, vp]),
+                     ("rdsic_eb_aux_backward", [vp, vp, vp, C.c_int, C.c_float, vp, vp]),
+                     ("rdsic_reduce_f32", [C.c_int, C.c_size_t, vp, vp, vp, vp])):
+        getattr(L, fn).argtypes = args
+        getattr(L, fn).restype = C.c_int
+    if L.rdsic_abi_version() != 5:
         raise RuntimeError("resdsic_b200: ABI version mismatch between the python host and the CUDA library")
     for what, T in enumerate((Op, ConvDesc, AttnDesc, EBDesc, GCDesc, CopyDesc, View, LNDesc, PatchDesc, MaskDesc)):
         if L.rdsic_sizeof(what) != C.sizeof(T):

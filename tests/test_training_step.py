@@ -1,0 +1,382 @@
+"""Rate-distortion TRAINING step (BASELINE config 4; SURVEY 8e / 8b "_bwd twins").
+
+* op level (-m gpu): every autograd node of resdsic_b200/training/functions.py -- forward AND backward are CUDA
+  kernels of the library -- against torch CPU autograd of the same operator, with the reference's custom gradient
+  rules (LowerBound ops/bound_ops.py:21-27, ste_round ops/ops.py:34, detached sign entropy_models.py:429-430);
+* model level (-m gpu): loss terms and EVERY parameter's gradient against goldens produced by the UNMODIFIED
+  reference (`net.train()`, RateDistortionLoss, lambda = 0.0035, loss.backward(), aux_loss().backward();
+  tests/golden/make_golden_rdstep.py);
+* CPU: the LowerBound rule, the bucketed gradient all-reduce on 2 gloo ranks, and "no CPU fallback".
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import resdsic_b200
+from oracle import wacnn_oracle as O
+from oracle import weights
+from resdsic_b200.ops import LowerBoundFunction, ste_round
+from tests.conftest import GOLDEN
+
+DEV = "cuda:0"
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def _nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+# ----------------------------------------------------------------------------- CPU
+def test_lower_bound_gradient_rule():
+    """ops/bound_ops.py:25-27: pass where x >= bound or where the gradient is negative."""
+    x = torch.tensor([0.05, 0.05, 0.5, 0.5], requires_grad=True)
+    y = LowerBoundFunction.apply(x, torch.tensor([0.11]))
+    assert torch.equal(y.detach(), torch.tensor([0.11, 0.11, 0.5, 0.5]))
+    y.backward(torch.tensor([1.0, -1.0, 1.0, -1.0]))
+    assert torch.equal(x.grad, torch.tensor([0.0, -1.0, 1.0, -1.0]))
+    t = torch.tensor([0.4, 1.5, -2.5], requires_grad=True)
+    r = ste_round(t)
+    assert torch.equal(r.detach(), torch.tensor([0.0, 2.0, -2.0]))
+    r.sum().backward()
+    assert torch.equal(t.grad, torch.ones(3))
+
+
+def test_training_refuses_cpu_tensors():
+    from resdsic_b200.training import train_forward
+    with pytest.raises(RuntimeError, match="CUDA"):
+        train_forward(resdsic_b200.WACNN(), torch.zeros(1, 3, 64, 64))
+
+
+def _reducer_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from resdsic_b200.training import GradBucketReducer
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 4), torch.nn.Linear(4, 2))
+    red = GradBucketReducer(net.parameters(), bucket_bytes=60)  # several buckets
+    x = torch.arange(16, dtype=torch.float32).reshape(2, 8) * (rank + 1) / 10
+    for _ in range(2):  # two steps: the reducer re-arms
+        net.zero_grad()
+        net(x).square().sum().backward()
+        n = red.finish()
+    # reference: gradients of the two ranks' batches averaged
+    ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 4), torch.nn.Linear(4, 2))
+    ref.load_state_dict(net.state_dict())
+    tot = None
+    for r in range(world):
+        ref.zero_grad()
+        ref(torch.arange(16, dtype=torch.float32).reshape(2, 8) * (r + 1) / 10).square().sum().backward()
+        g = [p.grad.clone() for p in ref.parameters()]
+        tot = g if tot is None else [a + b for a, b in zip(tot, g)]
+    err = max((p.grad - t / world).abs().max().item() for p, t in zip(net.parameters(), tot))
+    q.put((rank, n, len(red.buckets), err))
+    dist.destroy_process_group()
+
+
+def test_bucketed_gradient_allreduce_two_ranks_gloo():
+    """The data-parallel collective of config 4 (host logic, gloo, world size 2): bucketed, asynchronous,
+    hook-driven; the result equals the mean of the per-rank gradients."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_reducer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, n, nb, err in res:
+        assert nb >= 3 and n == nb, (n, nb)
+        assert err <= 1e-6, err
+
+
+# ----------------------------------------------------------------------------- GPU: op level
+@pytest.mark.gpu
+@pytest.mark.parametrize("cin,cout,k,s,B,hw", [
+    (32, 48, 3, 1, 2, (9, 7)), (16, 32, 5, 2, 2, (12, 16)), (48, 32, 3, 2, 1, (8, 12)), (64, 96, 1, 1, 2, (5, 6)),
+    (3, 32, 5, 2, 2, (16, 16)), (352, 224, 3, 1, 1, (8, 12))])
+def test_conv_backward_vs_torch(cin, cout, k, s, B, hw):
+    from resdsic_b200.training import functions as Fn
+    x = weights.hash_symmetric(f"bw.x{cin}{hw}", (B, cin, *hw), 1.0)
+    w = weights.hash_symmetric(f"bw.w{cin}{cout}{k}", (cout, cin, k, k), (3.0 / (cin * k * k)) ** 0.5)
+    b = weights.hash_symmetric(f"bw.b{cout}", (cout,), 0.1)
+    xr, wr, br = (t.clone().requires_grad_() for t in (x, w, b))
+    ref = F.conv2d(xr, wr, br, stride=s, padding=k // 2)
+    g = weights.hash_symmetric(f"bw.g{cout}{hw}", tuple(ref.shape), 1.0)
+    ref.backward(g)
+    xg, wg, bg = (t.clone().to(DEV).requires_grad_() for t in (_nhwc(x), w, b))
+    out = Fn.ConvFn.apply(xg, wg, bg, s, k // 2)
+    out.backward(_nhwc(g).to(DEV))
+    assert _rel(_nchw(out), ref) <= 2e-6
+    assert _rel(_nchw(xg.grad), xr.grad) <= 2e-6
+    assert _rel(wg.grad, wr.grad) <= 2e-6
+    assert _rel(bg.grad, br.grad) <= 2e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cin,cout", [(48, 32), (32, 3)])
+def test_deconv_backward_vs_torch(cin, cout):
+    from resdsic_b200.training import functions as Fn
+    x = weights.hash_symmetric(f"bd.x{cin}", (2, cin, 6, 10), 1.0)
+    w = weights.hash_symmetric(f"bd.w{cin}{cout}", (cin, cout, 5, 5), (12.0 / (cin * 25)) ** 0.5)
+    b = weights.hash_symmetric(f"bd.b{cout}", (cout,), 0.1)
+    xr, wr, br = (t.clone().requires_grad_() for t in (x, w, b))
+    ref = F.conv_transpose2d(xr, wr, br, stride=2, padding=2, output_padding=1)
+    g = weights.hash_symmetric(f"bd.g{cout}", tuple(ref.shape), 1.0)
+    ref.backward(g)
+    xg, wg, bg = (t.clone().to(DEV).requires_grad_() for t in (_nhwc(x), w, b))
+    out = Fn.DeconvFn.apply(xg, wg, bg)
+    out.backward(_nhwc(g).to(DEV))
+    assert _rel(_nchw(out), ref) <= 2e-6
+    assert _rel(_nchw(xg.grad), xr.grad) <= 2e-6
+    assert _rel(wg.grad, wr.grad) <= 2e-6
+    assert _rel(bg.grad, br.grad) <= 2e-6
+
+
+@pytest.mark.gpu
+def test_pointwise_nodes_vs_torch():
+    from resdsic_b200.training import functions as Fn
+    shp = (2, 5, 7, 16)
+    a, b, c = (weights.hash_symmetric(f"pw.{n}", shp, 2.0) for n in "abc")
+    g = weights.hash_symmetric("pw.g", shp, 1.0)
+    cases = {
+        "gelu": (lambda a, b, c: F.gelu(a), lambda a, b, c: Fn.GeluFn.apply(a)),
+        "gate": (lambda a, b, c: a * torch.sigmoid(b) + c, lambda a, b, c: Fn.GateFn.apply(a, b, c)),
+        "lrp": (lambda a, b, c: a + 0.5 * torch.tanh(b), lambda a, b, c: Fn.LrpFn.apply(a, b)),
+        "square": (lambda a, b, c: a * a, lambda a, b, c: Fn.SquareFn.apply(a)),
+        "add": (lambda a, b, c: a + b, lambda a, b, c: Fn.AddFn.apply(a, b)),
+        "gdn": (lambda a, b, c: a * torch.rsqrt(b.abs() + 0.5), lambda a, b, c: Fn.GdnScaleFn.apply(a, b.abs() + 0.5, False)),
+        "igdn": (lambda a, b, c: a * torch.sqrt(b.abs() + 0.5), lambda a, b, c: Fn.GdnScaleFn.apply(a, b.abs() + 0.5, True)),
+        "shuffle": (lambda a, b, c: _nhwc(F.pixel_shuffle(_nchw(a), 2)), lambda a, b, c: Fn.PixelShuffleFn.apply(a)),
+    }
+    for name, (ref_fn, fn) in cases.items():
+        rs = [t.clone().requires_grad_() for t in (a, b, c)]
+        gs = [t.clone().to(DEV).requires_grad_() for t in (a, b, c)]
+        ref = ref_fn(*rs)
+        gg = g if ref.shape == g.shape else weights.hash_symmetric("pw.g2", tuple(ref.shape), 1.0)
+        ref.backward(gg)
+        out = fn(*gs)
+        out.backward(gg.to(DEV))
+        assert _rel(out, ref) <= 2e-6, name
+        for r, t in zip(rs, gs):
+            if r.grad is not None:
+                assert _rel(t.grad, r.grad) <= 3e-6, name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,ws,shift,hw", [(192, 8, 4, (16, 24)), (320, 4, 2, (8, 12)), (192, 8, 0, (8, 8))])
+def test_window_attention_backward_vs_torch(C, ws, shift, hw):
+    """d qkv and d relative_position_bias_table against torch autograd of the oracle's restatement of
+    win_attention.py:84-115,153-207 (identity qkv / proj weights isolate the attention core)."""
+    from resdsic_b200.layers.win_attention import relative_position_index
+    from resdsic_b200.training import functions as Fn
+    heads, d = 8, C // 8
+    B, (H, W) = 2, hw
+    qkv = weights.hash_symmetric(f"at.qkv{C}{hw}", (B, H, W, 3 * C), 1.5)
+    table = weights.hash_symmetric(f"at.tab{ws}", ((2 * ws - 1) ** 2, heads), 0.5)
+    g = weights.hash_symmetric(f"at.g{C}{hw}", (B, H, W, C), 1.0)
+
+    def ref_core(qkv, table):
+        hs, wsft = (torch.arange(H) + shift) % H, (torch.arange(W) + shift) % W
+        sh = qkv[:, hs][:, :, wsft]
+        nWh, nWw, Nt = H // ws, W // ws, ws * ws
+        win = sh.reshape(B, nWh, ws, nWw, ws, 3 * C).permute(0, 1, 3, 2, 4, 5).reshape(B * nWh * nWw, Nt, 3 * C)
+        t = win.reshape(-1, Nt, 3, heads, d).permute(2, 0, 3, 1, 4)
+        q, k, v = t[0] * (d ** -0.5), t[1], t[2]
+        attn = q @ k.transpose(-2, -1) + table[relative_position_index(ws).reshape(-1)].reshape(Nt, Nt, heads).permute(2, 0, 1)[None]
+        if shift > 0:
+            rid = O.shift_region_id(H, W, ws, shift).reshape(nWh, ws, nWw, ws).permute(0, 2, 1, 3).reshape(nWh * nWw, Nt)
+            mask = torch.where(rid[:, None, :] != rid[:, :, None], -100.0, 0.0)
+            attn = (attn.reshape(B, nWh * nWw, heads, Nt, Nt) + mask[None, :, None]).reshape(-1, heads, Nt, Nt)
+        o = (torch.softmax(attn, -1) @ v).transpose(1, 2).reshape(-1, Nt, C)
+        o = o.reshape(B, nWh, nWw, ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(B, H, W, C)
+        out = torch.empty_like(o)
+        out[:, hs[:, None], wsft[None, :]] = o
+        return out
+
+    qr, tr = qkv.clone().requires_grad_(), table.clone().requires_grad_()
+    ref = ref_core(qr, tr)
+    ref.backward(g)
+    qg, tg = qkv.clone().to(DEV).requires_grad_(), table.clone().to(DEV).requires_grad_()
+    out = Fn.WindowAttentionFn.apply(qg, tg, heads, ws, shift, d ** -0.5)
+    out.backward(g.to(DEV))
+    assert _rel(out, ref) <= 3e-6
+    assert _rel(qg.grad, qr.grad) <= 5e-6
+    assert _rel(tg.grad, tr.grad) <= 2e-5  # (atomic accumulation over windows)
+
+
+@pytest.mark.gpu
+def test_gaussian_conditional_backward_vs_torch():
+    """Noise-mode likelihood + ste_round with both LowerBound rules; scales straddle the 0.11 bound and some
+    likelihoods hit the 1e-9 bound."""
+    from resdsic_b200.training import functions as Fn
+    shp = (2, 6, 8, 32)
+    y = weights.hash_symmetric("gcb.y", shp, 6.0)
+    mu = weights.hash_symmetric("gcb.mu", shp, 2.0)
+    scale = weights.hash_symmetric("gcb.s", shp, 1.0).abs() * 0.6 + 0.02
+    scale.view(-1)[::7] = 0.01  # far below the bound -> tiny likelihoods for large |y - mu|
+    noise = weights.hash_symmetric("gcb.n", shp, 0.5)
+    g_lik = weights.hash_symmetric("gcb.gl", (2, 32, 6, 8), 1.0)
+    g_yh = weights.hash_symmetric("gcb.gy", shp, 1.0)
+    table = weights.scale_table()
+
+    yr, mr, sr = (t.clone().requires_grad_() for t in (y, mu, scale))
+    v = torch.abs(yr + noise - mr)
+    sg = LowerBoundFunction.apply(sr, torch.tensor([0.11]))
+    c = float(-(2 ** -0.5))
+    lik = 0.5 * torch.erfc(c * ((0.5 - v) / sg)) - 0.5 * torch.erfc(c * ((-0.5 - v) / sg))
+    lik = LowerBoundFunction.apply(lik, torch.tensor([1e-9]))
+    y_hat = ste_round(yr - mr) + mr
+    torch.autograd.backward([_nchw(lik), y_hat], [g_lik, g_yh])
+
+    yg, mg, sgp = (t.clone().to(DEV).requires_grad_() for t in (y, mu, scale))
+    lik_g, yh_g = Fn.GaussianConditionalFn.apply(yg, mg, sgp, noise.to(DEV), table.to(DEV), 0.11, 1e-9)
+    torch.autograd.backward([lik_g, yh_g], [g_lik.to(DEV), g_yh.to(DEV)])
+    assert (lik_g.detach().cpu() == 1e-9).any() and (scale < 0.11).any()
+    np.testing.assert_allclose(lik_g.detach().cpu().numpy(), _nchw(lik).detach().numpy(), rtol=3e-4, atol=1e-9)
+    assert torch.equal(yh_g.detach().cpu(), y_hat.detach())
+    for got, ref in ((yg.grad, yr.grad), (mg.grad, mr.grad), (sgp.grad, sr.grad)):
+        assert _rel(got, ref) <= 2e-4  # CUDA erfc / exp vs libm
+
+
+@pytest.mark.gpu
+def test_entropy_bottleneck_backward_vs_torch(synthetic_sd):
+    """d z and the gradient of all 13 EntropyBottleneck parameter tensors (through the packed-parameter gradient
+    and torch's softplus / tanh), sign detached; plus aux_loss -> quantiles."""
+    from resdsic_b200.training import functions as Fn
+    from resdsic_b200.training.model import aux_loss, packed_entropy_bottleneck
+    B, h, w, C = 2, 4, 6, 192
+    z = weights.hash_symmetric("ebb.z", (B, C, h, w), 4.0)
+    noise = weights.hash_symmetric("ebb.n", (B, C, h, w), 0.5)
+    g_lik = weights.hash_symmetric("ebb.gl", (B, C, h, w), 1.0)
+    g_zh = weights.hash_symmetric("ebb.gz", (B, C, h, w), 1.0)
+    p = "entropy_bottleneck"
+    names = [f"_matrix{i}" for i in range(5)] + [f"_bias{i}" for i in range(5)] + [f"_factor{i}" for i in range(4)]
+    prm = {n: synthetic_sd[f"{p}.{n}"].clone().requires_grad_() for n in names}
+    quant = synthetic_sd[f"{p}.quantiles"].clone().requires_grad_()
+
+    def logits(v):
+        for k in range(5):
+            v = torch.matmul(F.softplus(prm[f"_matrix{k}"]), v) + prm[f"_bias{k}"]
+            if k < 4:
+                v = v + torch.tanh(prm[f"_factor{k}"]) * torch.tanh(v)
+        return v
+
+    zr = z.clone().requires_grad_()
+    v = (zr + noise).permute(1, 0, 2, 3).reshape(C, 1, -1)
+    lo, up = logits(v - 0.5), logits(v + 0.5)
+    sign = -torch.sign(lo + up).detach()
+    lik = torch.abs(torch.sigmoid(sign * up) - torch.sigmoid(sign * lo))
+    lik = LowerBoundFunction.apply(lik, torch.tensor([1e-9])).reshape(C, B, h, w).permute(1, 0, 2, 3)
+    med = quant[:, :, 1:2].detach().reshape(1, C, 1, 1)
+    z_hat = ste_round(zr - med) + med
+    torch.autograd.backward([lik, z_hat], [g_lik, g_zh])
+
+    m = resdsic_b200.WACNN()
+    m.load_state_dict(synthetic_sd, strict=True)
+    m = m.to(DEV)
+    eb = m.entropy_bottleneck
+    zg = _nhwc(z).to(DEV).requires_grad_()
+    lik_g, zh_g = Fn.EntropyBottleneckFn.apply(zg, packed_entropy_bottleneck(eb), _nhwc(noise).to(DEV), 1e-9)
+    torch.autograd.backward([lik_g, zh_g], [g_lik.to(DEV), _nhwc(g_zh).to(DEV)])
+    np.testing.assert_allclose(lik_g.detach().cpu().numpy(), lik.detach().numpy(), rtol=2e-4, atol=1e-9)
+    assert torch.equal(_nchw(zh_g.detach()).cpu(), z_hat.detach())
+    assert _rel(_nchw(zg.grad), zr.grad) <= 2e-4
+    for n in names:
+        assert _rel(getattr(eb, n).grad, prm[n].grad) <= 5e-4, n
+    # aux loss: gradient to the quantiles only
+    m.zero_grad()
+    al = aux_loss(m)
+    al.backward()
+    ref_aux = torch.abs(logits(quant) - synthetic_sd[f"{p}.target"]).sum()
+    (gq,) = torch.autograd.grad(ref_aux, quant)
+    assert abs(al.item() - ref_aux.item()) <= 1e-5 * abs(ref_aux.item())
+    assert _rel(eb.quantiles.grad, gq) <= 1e-5
+    assert all(getattr(eb, n).grad is None or getattr(eb, n).grad.abs().sum() == 0 for n in names)
+
+
+# ----------------------------------------------------------------------------- GPU: the whole step vs the reference
+def _rd_step(case):
+    from resdsic_b200.training import RateDistortionLoss, aux_loss, train_forward
+    from tests.golden.make_golden_rdstep import CASES, sample_index
+    gold = np.load(os.path.join(GOLDEN, f"wacnn_{case}.npz"))
+    wkind, B, H, W = CASES[case]
+    sd = weights.refinit_state_dict(0) if wkind == "refinit" else weights.make_state_dict(seed=0)
+    net = resdsic_b200.WACNN().train()
+    net.load_state_dict(sd, strict=True)
+    net = net.to(DEV)
+    x = weights.rand_image(B, H, W, seed=int(gold["image_seed"])).to(DEV)
+    noise = {"y": torch.from_numpy(gold["noise_y"]), "z": torch.from_numpy(gold["noise_z"])}
+    crit = RateDistortionLoss(lmbda=float(gold["lmbda"]))
+    out = train_forward(net, x, noise=noise)
+    oc = crit(out, x)
+    oc["loss"].backward()
+    params = dict(net.named_parameters())
+    rows = []
+    for k, name in enumerate(gold["names"]):
+        name = str(name)
+        g = params[name].grad
+        if g is None:  # quantiles: d loss / d median = -1 + 1 = 0 exactly in the reference (cnn.py:152-154); no edge here
+            assert float(gold["grad_norm"][k]) == 0.0, name
+            continue
+        g64 = g.detach().double().reshape(-1)
+        smp = g.detach().reshape(-1)[torch.from_numpy(sample_index(k, g.numel())).to(g.device)].cpu().numpy()
+        rows.append((name, g64.norm().item(), float(gold["grad_norm"][k]), smp, gold["grad_samples"][k]))
+    net.zero_grad()
+    al = aux_loss(net)
+    al.backward()
+    return gold, oc, rows, al, net
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,tol_norm,tol_global,tol_sample", [
+    ("rdstep_c256", 1e-4, 1e-5, 1e-3),          # the reference's own init at config 4's image size: no symbol flips
+    ("rdstep_hash_c128", 5e-2, 5e-3, 1.0)])      # hash-seeded "stress" weights: see the docstring
+def test_rd_training_step_matches_reference(case, tol_norm, tol_global, tol_sample):
+    """Loss terms and EVERY parameter's gradient of one RD step vs the unmodified reference (lambda = 0.0035, fp32).
+    On the reference's init (config 4, 2 x 3 x 256 x 256) the per-parameter gradient norms agree to 1e-6 (asserted:
+    1e-4, the bar of the round-1 verdict) and sampled entries to 1e-5 of the parameter's RMS gradient.  On the
+    "stress" weights (symbols up to +-15) a handful of round(y - mu) ties fall the other way under a different fp32
+    summation order -- a different, equally valid y_hat -- so gradients of the parameters downstream of those
+    symbols legitimately differ at the 1e-3 ... 1e-2 level (as in the forward tests)."""
+    gold, oc, rows, al, net = _rd_step(case)
+    for k in ("loss", "bpp_loss", "mse_loss"):
+        ref = float(gold[k])
+        assert abs(oc[k].item() - ref) <= 1e-4 * abs(ref), (k, oc[k].item(), ref)
+    assert abs(al.item() - float(gold["aux_loss"])) <= 1e-5 * float(gold["aux_loss"])
+    gq = net.entropy_bottleneck.quantiles.grad.cpu().numpy()
+    np.testing.assert_allclose(gq, gold["aux_grad_quantiles"], rtol=1e-4, atol=1e-7)
+    biggest = max(r[2] for r in rows)
+    worst, worst_name, worst_s = 0.0, None, 0.0
+    tot_err = tot_ref = 0.0
+    for name, got, ref, smp, smp_ref in rows:
+        tot_err += (got - ref) ** 2
+        tot_ref += ref ** 2
+        if ref >= 1e-6 * biggest:
+            rel = abs(got - ref) / ref
+            if rel > worst:
+                worst, worst_name = rel, name
+            rms = ref / math.sqrt(max(1, net.get_parameter(name).numel()))
+            worst_s = max(worst_s, float(np.abs(smp - smp_ref).max() / rms))
+        else:
+            assert got <= 1e-5 * biggest, (name, got, ref)
+    print(f"{case}: worst per-parameter grad-norm rel err {worst:.2e} ({worst_name}); worst sampled-entry err / rms "
+          f"{worst_s:.2e}; global {math.sqrt(tot_err / tot_ref):.2e}")
+    assert worst <= tol_norm, (worst, worst_name)
+    assert math.sqrt(tot_err / tot_ref) <= tol_global
+    assert worst_s <= tol_sample, worst_s

@@ -28,6 +28,8 @@ from .wacnn import WACNN, _cc_stack, _Plan, get_scale_table
 class scalable_icd(WACNN):
     """reference scalable/single_decoder.py:25 (registry key "icd")."""
 
+    train_forward_impl = None  # no differentiable training forward for this model: train() gives forward values only
+
     def __init__(self, N=192, M=320, mask_policy="learnable-mask-gamma", lambda_list=(0.05,), lrp_prog=True,
                  independent_lrp=False, **kwargs):
         super().__init__(N=N, M=M, **kwargs)

@@ -66,6 +66,8 @@ def _cc3(cin):
 class SymmetricalTransFormer(WACNN):
     """STF.  forward(x) -> {"x_hat", "likelihoods": {"y", "z"}} like every registry model."""
 
+    train_forward_impl = None  # no differentiable training forward for this model: train() gives forward values only
+
     def __init__(self, N=192, M=384, embed_dim=48, depths=(2, 2, 6, 2), num_heads=(3, 6, 12, 24), window_size=4,
                  num_slices=12, max_support_slices=6, **kwargs):
         CompressionModel.__init__(self)

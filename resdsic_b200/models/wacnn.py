@@ -37,9 +37,13 @@ class CompressionModel(B200Module):
     bitstream-side and stay with the reference)."""
 
     def aux_loss(self):
-        """reference WACNN/base.py:22-27: sum of EntropyBottleneck.loss() over the bottleneck modules
-        (forward value; the CUDA path has no autograd)."""
+        """reference WACNN/base.py:22-27: sum of EntropyBottleneck.loss() over the bottleneck modules.  With autograd
+        enabled the result carries a gradient to `.quantiles` (the aux optimiser's parameters, train.py:59-68),
+        computed by the library's backward kernel (resdsic_b200/training)."""
         from ..entropy_models import EntropyBottleneck
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from ..training.model import aux_loss_of
+            return sum(aux_loss_of(m) for m in self.modules() if isinstance(m, EntropyBottleneck))
         return sum(m.loss() for m in self.modules() if isinstance(m, EntropyBottleneck))
 
     def update(self, force=False):
@@ -590,10 +594,24 @@ class WACNN(CompressionModel):
         self.last_num_launches = sum(sp.prog.num_launches for sp in plan.subs)
         return plan
 
-    @torch.no_grad()
     def forward(self, x):
-        """reference cnn.py:143-193 (eval mode, or the forward values of training mode -- see
-        `noise_override`).  Returns fresh tensors, like the reference (see `static_outputs`)."""
+        """reference cnn.py:143-193.  Eval mode (and any call under `torch.no_grad()`): the planned program /
+        CUDA graph in `self.precision`; returns fresh tensors, like the reference (see `static_outputs`).
+        `.train()` with autograd enabled: the differentiable fp32 training forward (resdsic_b200/training) over the
+        same parameters -- `criterion(model(x), x)["loss"].backward()` works as in training/step.py:42-49."""
+        if self.training and torch.is_grad_enabled() and type(self).train_forward_impl is not None:
+            return type(self).train_forward_impl(self, x, noise=self.noise_override)
+        with torch.no_grad():
+            return self._forward_planned(x)
+
+    @staticmethod
+    def _train_forward(model, x, noise=None):
+        from ..training.model import train_forward
+        return train_forward(model, x, noise=noise)
+
+    train_forward_impl = _train_forward  # subclasses without a training forward set this to None
+
+    def _forward_planned(self, x):
         p = self._execute(x, False)
         o = self._out
         return {"x_hat": o(p.x_hat), "likelihoods": {"y": o(p.lik_y), "z": o(p.lik_z)}}

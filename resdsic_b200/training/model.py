@@ -145,8 +145,13 @@ def train_forward(model, x, noise=None):
     return {"x_hat": x_hat, "likelihoods": {"y": Fn.CatNchwFn.apply(*y_liks), "z": z_lik}}
 
 
-def aux_loss(model):
-    """CompressionModel.aux_loss (WACNN/base.py:22-27) with a gradient to `.quantiles` (train.py:59-68)."""
-    eb = model.entropy_bottleneck
+def aux_loss_of(eb):
+    """EntropyBottleneck.loss (entropy_models.py:396-399) with a gradient to `.quantiles` only."""
     packed = packed_entropy_bottleneck(eb).detach()
     return Fn.AuxLossFn.apply(eb.quantiles, packed, eb.target.float())
+
+
+def aux_loss(model):
+    """CompressionModel.aux_loss (WACNN/base.py:22-27): gradient to the `.quantiles` parameters (train.py:59-68)."""
+    from ..entropy_models import EntropyBottleneck
+    return sum(aux_loss_of(m) for m in model.modules() if isinstance(m, EntropyBottleneck))

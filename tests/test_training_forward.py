@@ -4,7 +4,7 @@ WACNN.forward in `.train()` mode (cnn.py:143-193) and aux_loss (WACNN/base.py:22
 
 Golden: tests/golden/wacnn_train_c64x128.npz, produced by the UNMODIFIED reference in train() mode
 (tests/golden/make_golden_train.py), with the reference's own noise draws stored alongside.
-There is no autograd through the CUDA kernels; only forward values are checked."""
+Forward values only; gradients are covered by tests/test_training_step.py."""
 import os
 
 import numpy as np
@@ -83,14 +83,21 @@ def test_training_forward_fp32_vs_reference_golden(model, gold):
     try:
         model.noise_override = _noise(gold)
         x = weights.make_image(B, H, W, seed=int(gold["image_seed"])).to("cuda:0")
-        out = model(x)
+        out = model(x)  # autograd enabled: the differentiable training forward (resdsic_b200/training)
+        assert out["x_hat"].requires_grad and out["likelihoods"]["y"].requires_grad
+        _check(out["x_hat"].detach().cpu().numpy(), out["likelihoods"]["y"].detach().cpu().numpy(),
+               out["likelihoods"]["z"].detach().cpu().numpy(), gold, 1e-3)
+        with torch.no_grad():  # no autograd: the planned program with the noise views (forward values only)
+            out = model(x)
+        assert not out["x_hat"].requires_grad
         _check(out["x_hat"].cpu().numpy(), out["likelihoods"]["y"].cpu().numpy(), out["likelihoods"]["z"].cpu().numpy(),
                gold, 1e-3)
         # own device-side draw: a different noise sample each call, same x_hat (ste_round path is noise-free)
         model.noise_override = None
-        a = {k: v.clone() for k, v in model(x)["likelihoods"].items()}
-        xa = model(x)["x_hat"].clone()
-        b = model(x)
+        with torch.no_grad():
+            a = {k: v.clone() for k, v in model(x)["likelihoods"].items()}
+            xa = model(x)["x_hat"].clone()
+            b = model(x)
         assert not torch.equal(a["y"], b["likelihoods"]["y"]) and not torch.equal(a["z"], b["likelihoods"]["z"])
         assert torch.equal(xa, b["x_hat"])
         assert (b["likelihoods"]["y"] > 0).all() and (b["likelihoods"]["y"] <= 1).all()

@@ -312,7 +312,7 @@ def test_entropy_bottleneck_backward_vs_torch(synthetic_sd):
 
 # ----------------------------------------------------------------------------- GPU: the whole step vs the reference
 def _rd_step(case):
-    from resdsic_b200.training import RateDistortionLoss, aux_loss, train_forward
+    from resdsic_b200.training import RateDistortionLoss
     from tests.golden.make_golden_rdstep import CASES, sample_index
     gold = np.load(os.path.join(GOLDEN, f"wacnn_{case}.npz"))
     wkind, B, H, W = CASES[case]
@@ -323,7 +323,8 @@ def _rd_step(case):
     x = weights.rand_image(B, H, W, seed=int(gold["image_seed"])).to(DEV)
     noise = {"y": torch.from_numpy(gold["noise_y"]), "z": torch.from_numpy(gold["noise_z"])}
     crit = RateDistortionLoss(lmbda=float(gold["lmbda"]))
-    out = train_forward(net, x, noise=noise)
+    net.noise_override = noise  # (tests only: the reference's own draws; normally drawn on the device)
+    out = net(x)                # the module surface train.py uses: train() mode + autograd -> differentiable forward
     oc = crit(out, x)
     oc["loss"].backward()
     params = dict(net.named_parameters())
@@ -338,7 +339,7 @@ def _rd_step(case):
         smp = g.detach().reshape(-1)[torch.from_numpy(sample_index(k, g.numel())).to(g.device)].cpu().numpy()
         rows.append((name, g64.norm().item(), float(gold["grad_norm"][k]), smp, gold["grad_samples"][k]))
     net.zero_grad()
-    al = aux_loss(net)
+    al = net.aux_loss()
     al.backward()
     return gold, oc, rows, al, net
 

@@ -367,6 +367,211 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------- training workload (BASELINE config 4)
+TRAIN_METRIC = "WACNN (-m cnn) rate-distortion training step images/s at 256x256 (lambda = 0.0035, fp32)"
+TRAIN_H = TRAIN_W = 256
+
+
+def _train_objects(dev, world):
+    """Model, criterion and the two optimisers exactly as train.py:55-89 / training/step.py:18-56 set them up:
+    Adam over every parameter but the `.quantiles`, a second Adam over the `.quantiles`, clip 1.0."""
+    import resdsic_b200
+    from resdsic_b200.training import GradBucketReducer, RateDistortionLoss
+    net = resdsic_b200.WACNN().train()
+    net.load_state_dict(make_weights("refinit"), strict=True)
+    net = net.to(dev)
+    main = [p for n, p in net.named_parameters() if not n.endswith(".quantiles") and p.requires_grad]
+    aux = [p for n, p in net.named_parameters() if n.endswith(".quantiles") and p.requires_grad]
+    opt = torch.optim.Adam(main, lr=1e-4)
+    aux_opt = torch.optim.Adam(aux, lr=1e-3)
+    crit = RateDistortionLoss(lmbda=0.0035)
+    reducer = GradBucketReducer(main + aux) if world > 1 else None
+    return net, crit, opt, aux_opt, reducer, main
+
+
+def _train_step(net, crit, opt, aux_opt, reducer, main, x, ev=None):
+    """training/step.py:36-56, one batch.  `ev`: optional dict of CUDA events recorded at the phase boundaries."""
+    def mark(k):
+        if ev is not None:
+            ev[k].record()
+    opt.zero_grad(set_to_none=True)
+    aux_opt.zero_grad(set_to_none=True)
+    mark("t0")
+    out = net(x)
+    oc = crit(out, x)
+    mark("fwd")
+    oc["loss"].backward()
+    aux = net.aux_loss()
+    aux.backward()
+    mark("bwd")
+    if reducer is not None:
+        reducer.finish()  # waits for the bucketed all-reduces that overlapped the backward pass
+    mark("red")
+    aux_opt.step()
+    torch.nn.utils.clip_grad_norm_(main, 1.0)
+    opt.step()
+    mark("opt")
+    return oc["loss"]
+
+
+def time_gpu_eager_train(x_dev, steps=2, warmup=1):
+    """The incumbent for config 4 on this GPU: the same PyTorch graph (oracle restatement of the training-mode forward)
+    with torch autograd + cuDNN/cuBLAS backward, RD loss, Adam -- fp32 and TF32.  (The oracle's round() passes no
+    straight-through gradient, so its backward graph is, if anything, slightly smaller than the reference's.)"""
+    import math
+    from oracle import wacnn_oracle as O
+    dev = x_dev.device
+    res = {}
+    B = x_dev.shape[0]
+    for name, tf32 in (("fp32", False), ("tf32", True)):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        try:
+            sd = {k: v.to(dev).clone().requires_grad_(v.is_floating_point()) for k, v in make_weights("refinit").items()}
+            params = [v for v in sd.values() if v.requires_grad]
+            opt = torch.optim.Adam(params, lr=1e-4)
+            noise = {"y": torch.rand(B, 320, TRAIN_H // 16, TRAIN_W // 16, device=dev) - 0.5,
+                     "z": torch.rand(B, 192, TRAIN_H // 64, TRAIN_W // 64, device=dev) - 0.5}
+
+            def step():
+                opt.zero_grad(set_to_none=True)
+                out = O.forward.__wrapped__(sd, x_dev, noise=noise)  # (the oracle's forward is decorated no_grad)
+                npx = B * TRAIN_H * TRAIN_W
+                bpp = sum(torch.log(l).sum() / (-math.log(2) * npx) for l in out["likelihoods"].values())
+                loss = 0.0035 * 255 ** 2 * torch.nn.functional.mse_loss(out["x_hat"], x_dev) + bpp
+                loss.backward()
+                torch.nn.utils.clip_grad_norm_(params, 1.0)
+                opt.step()
+            for _ in range(warmup):
+                step()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / steps
+            res[name] = {"images_per_s": B / (ms / 1e3), "ms_per_step": ms}
+        except Exception as e:
+            res[name] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        torch.cuda.empty_cache()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = True
+    return res
+
+
+def run_train(args):
+    """`--workload train`: BASELINE config 4 -- one RD training step (forward, loss, backward, aux step, clip, Adam) per
+    GPU on a batch of 16 x 3 x 256 x 256, fp32 kernels of this library; N > 1: one process per GPU, the bucketed
+    gradient all-reduce (NCCL) overlapping the backward pass is the only collective.  An extra line, not the headline."""
+    import torch.distributed as dist
+
+    from resdsic_b200 import _lib
+    from resdsic_b200.training import functions as Fn
+    from resdsic_b200.utils import max_over_ranks, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(dev)
+
+    _lib.lib()
+    B = args.batch if args.batch != 24 else 16
+    net, crit, opt, aux_opt, reducer, main = _train_objects(dev, world)
+    x_host = synthetic.rand_image(B, TRAIN_H, TRAIN_W, seed=300 + rank).pin_memory()
+    x_dev = x_host.to(dev)
+    for _ in range(max(3, args.warmup)):
+        _train_step(net, crit, opt, aux_opt, reducer, main, x_dev)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    keys = ("t0", "fwd", "bwd", "red", "opt")
+    evs = [{k: torch.cuda.Event(enable_timing=True) for k in keys} for _ in range(args.steps)]
+    n0 = Fn.LAUNCHES[0]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        _train_step(net, crit, opt, aux_opt, reducer, main, x_dev, evs[i])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = Fn.LAUNCHES[0] - n0
+    clocks = sampler.stop() if rank == 0 else None
+    phase = {b: sum(e[a].elapsed_time(e[b]) for e in evs) / args.steps for a, b in zip(keys[:-1], keys[1:])}
+
+    # end to end: the batch comes from pinned host memory every step and the loss is read back on the host
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        xb = x_host.to(dev, non_blocking=True)
+        loss = _train_step(net, crit, opt, aux_opt, reducer, main, xb)
+        loss_host.copy_(loss.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        float(loss_host)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    # the collective alone (not overlapped): all-reduce of every gradient bucket, back to back
+    ar_ms, grad_bytes = None, sum(p.numel() * 4 for p in net.parameters())
+    if world > 1:
+        flats = [torch.zeros(sum(p.numel() for p in b), device=dev) for b in reducer.buckets]
+        for _ in range(2):
+            for f in flats:
+                dist.all_reduce(f)
+        barrier()
+        e0.record()
+        for f in flats:
+            dist.all_reduce(f)
+        e1.record()
+        barrier()
+        ar_ms = e0.elapsed_time(e1)
+        del flats
+    vals = [ms, ms_e2e, phase["fwd"], phase["bwd"], phase["red"], phase["opt"]] + ([ar_ms] if ar_ms is not None else [])
+    vals = max_over_ranks(vals, device=dev)
+    if rank == 0:
+        ms, ms_e2e = vals[0], vals[1]
+        n_img = B * world * args.steps
+        line = {
+            "metric": TRAIN_METRIC, "value": n_img / (ms / 1e3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"cnn (WACNN N=192 M=320) RD training step (BASELINE config 4): batch {B} x 3 x 256 x 256 per "
+                                   "GPU, lambda 0.0035, forward + loss + backward + aux step + clip 1.0 + Adam",
+                       "precision": "fp32", "weights": "refinit", "batch_per_gpu": B, "image": [TRAIN_H, TRAIN_W],
+                       "parallelism": f"dp{world}", "collective": "bucketed NCCL all-reduce of the gradients (25 MB buckets) on a side "
+                                                                  "stream, overlapping backward" if world > 1 else "none (1 GPU)",
+                       "l2": "activations + saved tensors of a step exceed the 126 MB L2; no explicit flush"},
+            "e2e": {"value": n_img / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                    "d2h_bytes_per_step": 4, "api": "model(x) / RateDistortionLoss / loss.backward() / optimizer.step() "
+                                                    "(training/step.py's calls), batch from pinned host memory, loss read on the host"},
+            "gpu_launches": launches, "launches_per_step": launches // args.steps, "clocks": clocks,
+            "phases_ms": {"forward_and_loss": vals[2], "backward": vals[3], "allreduce_exposed_after_backward": vals[4],
+                          "aux_step_clip_adam": vals[5],
+                          "allreduce_alone": vals[6] if ar_ms is not None else None, "gradient_bytes": grad_bytes},
+        }
+        if world == 1 and not args.no_eager_baseline:
+            eager = time_gpu_eager_train(x_dev)
+            best = max((v["images_per_s"] for v in eager.values() if "images_per_s" in v), default=None)
+            line["gpu_eager_baseline"] = {"what": "the same training step as torch eager autograd on this GPU (oracle graph, cuDNN / "
+                                                  "cuBLAS), same batch", "variants": eager, "best_images_per_s": best,
+                                          "speedup_over_best": (line["value"] / best) if best else None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def profile_families(model, x_dev, dump=None):
     """Device time per kernel family for ONE forward, CUDA events around every launch (eager)."""
     import ctypes as C
@@ -415,7 +620,9 @@ def profile_families(model, x_dev, dump=None):
             # algorithmic bytes: input once, outputs once, residual / gate operands once, weights once
             nbytes = (c.B * c.H * c.W * c.Cin * esz(c.in_) + M * n_out * (esz(c.out) + esz(c.out2) + esz(c.out3) +
                       esz(c.res) + esz(c.aux)) + c.Cout * c.KH * c.KW * c.Cin * 2 + c.tail_n * c.Cout * 2)
-            kern = (f"conv_gdn_tc_kernel<{c.tail_mode}>" if c.tail_mode else
+            ru_pair = (c.tail_mode == 3 and c.tail_n == 2 * c.Cout and 5 * c.Cout <= 512 and 64 < c.Cin <= 128 and c.KH * c.KW >= 2
+                       and c.stride == 1 and os.environ.get("RDSIC_RU_PAIR", "1") != "0")  # ru_pair_bf16.cu's eligibility rule
+            kern = ("ru_pair_tc_kernel" if ru_pair else f"conv_gdn_tc_kernel<{c.tail_mode}>" if c.tail_mode else
                     (f"conv_tc_kernel<EPI={c.epilogue}>" if c.w_dtype == _lib.BF16 else "conv_f32_kernel"))
             shape = f"M={M} N={c.Cout} K={c.KH * c.KW * c.Cin} {c.KH}x{c.KW}s{c.stride}" + (f" tailN={c.tail_n}" if c.tail_mode else "")
             rec.update(M=M, N=c.Cout, K=c.KH * c.KW * c.Cin, k=f"{c.KH}x{c.KW}s{c.stride}", kernel=kern, shape=shape, flop=flop,
@@ -433,6 +640,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="forward", choices=["forward", "train"],
+                    help="forward = the headline (BASELINE configs[2]); train = the RD training step of config 4 (extra line)")
     ap.add_argument("--precision", default=os.environ.get("RESDSIC_PRECISION", "bf16"), choices=["fp32", "bf16"])
     # 24 images x 1536 latent pixels = 144 of the 256-row tiles of the slice-loop GEMMs: one full wave of the 148
     # SMs (batch 16 fills 96 of them, batch 32 needs a second, 30 %-full wave).  Sweep: DESIGN.md section 5.
@@ -447,6 +656,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "train":
+        run_train(args)
     else:
         run_ours(args)
 

@@ -643,6 +643,7 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 }  // namespace
 
 int rdsic_conv_validate(const rdsic_conv_desc* d);
+int rdsic_ru_pair_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream);  // ru_pair_bf16.cu
 
 // conv (+bias) followed by a second, pointwise GEMM in one launch (d->tail_mode):
 //   1 GDN / 2 inverse GDN: tail_weight = packed bf16 gamma' [C][C], tail_bias = fp32 beta' [C], tail_n = C;
@@ -672,6 +673,10 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
     return RDSIC_E_ALIGN;
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return RDSIC_E_UNSUPPORTED;
+  if (d->tail_mode == TAIL_RU) {  // ResidualUnit tail on CTA pairs with resident weights where the layer qualifies
+    rc = rdsic_ru_pair_forward_bf16(d, stream);
+    if (rc != -1) return rc;
+  }
 
   TcGeom g = {};
   int B = d->B, H = d->H, W = d->W, OH = d->OH, OW = d->OW;
@@ -756,7 +761,8 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   RDSIC_CHECK_ARG(gg.acc2_col + N2 <= 512);
   gg.na = 0;
   int stage_bytes = A_STAGE_BYTES + g.b_stage_bytes;
-  int stages = (200 * 1024 - gg.w2_bytes) / stage_bytes;
+  static const int tune_smem_kb = getenv("RDSIC_GDN_SMEM_KB") ? atoi(getenv("RDSIC_GDN_SMEM_KB")) : 200;
+  int stages = (tune_smem_kb * 1024 - gg.w2_bytes) / stage_bytes;
   if (g.halo) {
     stage_bytes = g.b_stage_bytes;
     gg.na = C <= 96 ? 4 : 2;

@@ -143,6 +143,31 @@ def test_tcgen05_conv_vs_oracle(cin, cout, k, s, B, hw):
     np.testing.assert_allclose(out.numpy(), ref.numpy(), rtol=8e-3, atol=8e-3)
 
 
+@pytest.mark.parametrize("N,B,hw", [(192, 2, (16, 24)), (192, 3, (8, 16)), (192, 1, (19, 13)), (192, 2, (64, 96)), (192, 5, (128, 192)),
+                                    (320, 1, (8, 12))])
+def test_fused_residual_unit_vs_torch(N, B, hw):
+    """Fused ResidualUnit (1x1 head launch + conv3x3 -> GELU -> conv1x1 -> +x -> GELU in ONE kernel: the CTA-pair kernel
+    ru_pair_tc_kernel for N = 192, conv_gdn_tc_kernel<3> otherwise) against torch on the same bf16-rounded weights and
+    input, with the intermediate activations rounded to bf16 where the kernels round them.  Shapes: an even and an odd
+    number of 128-row tiles (the odd one out of the last CTA pair), ragged edges, one tile per CTA, several tiles per persistent CTA (accumulator double-buffering, barrier phases), N = 320."""
+    from resdsic_b200.layers import ResidualUnit
+    import torch.nn.functional as F
+    ru = ResidualUnit(N)
+    with torch.no_grad():
+        for i, (cin, k) in zip((0, 2, 4), ((N, 1), (N // 2, 3), (N // 2, 1))):
+            ru.conv[i].weight.copy_(weights.hash_symmetric(f"ru.w{N}{i}", ru.conv[i].weight.shape, (3.0 / (cin * k * k)) ** 0.5))
+            ru.conv[i].bias.copy_(weights.hash_symmetric(f"ru.b{N}{i}", ru.conv[i].bias.shape, 0.2))
+    x = weights.hash_symmetric(f"ru.x{N}{hw}", (B, N, *hw), 1.5)
+    g = lambda v: F.gelu(v)
+    c = [ru.conv[i] for i in (0, 2, 4)]
+    xb = _bf(x)
+    t = _bf(g(F.conv2d(xb, _bf(c[0].weight.detach()), c[0].bias.detach())))
+    t = _bf(g(F.conv2d(t, _bf(c[1].weight.detach()), c[1].bias.detach(), padding=1)))
+    ref = g(F.conv2d(t, _bf(c[2].weight.detach()), c[2].bias.detach()) + xb)
+    out = ru.to(DEV).set_precision("bf16")(x.to(DEV)).cpu()
+    np.testing.assert_allclose(out.numpy(), ref.numpy(), rtol=8e-3, atol=8e-3)
+
+
 @pytest.mark.parametrize("cin,cout", [(192, 192), (320, 192), (192, 3)])
 def test_tcgen05_deconv_vs_oracle(cin, cout):
     from resdsic_b200.layers import ConvTranspose2d
@@ -253,7 +278,8 @@ def test_patchify_matches_unfold(C, k, s, p, B, H, W):
     {"RDSIC_TC_M2": "1"},                            # small grids with the K-split of two accumulators
     {"RDSIC_TC_M2": "0"},                            # M2 off
     {"RDSIC_TC_M2_MINK": "1", "RDSIC_TC_M2": "2"},   # M2 also for the 1-3 k-iteration pointwise GEMMs
-    {"RDSIC_RU_DBL": "0"},                           # single-buffered fused ResidualUnit kernel
+    {"RDSIC_RU_DBL": "0", "RDSIC_RU_PAIR": "0"},     # single-buffered fused ResidualUnit kernel
+    {"RDSIC_RU_PAIR": "0"},                          # 1-CTA double-buffered fused ResidualUnit kernel (default: CTA pairs)
     {"RDSIC_TC_PAIR": "3"},                          # cta_group::2 CTA pairs on EVERY layer with two M tiles (default: wide long-K layers)
     {"RDSIC_TC_PAIR": "0"},                          # no CTA pairs (M2 / single-issuer tiles everywhere)
     {"RDSIC_TC_PAIR": "0", "RDSIC_TC_MC": "1"},      # 1-CTA tiles with the B stage multicast across a CTA pair
@@ -265,6 +291,6 @@ def test_kernel_mode_switches_in_subprocess(env):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_ops.py", "-m", "gpu", "-q", "-x", "-k",
-                        "tcgen05 or layers_bf16 or subpel"], cwd=root, env=dict(os.environ, **env), capture_output=True,
+                        "tcgen05 or layers_bf16 or subpel or fused_residual"], cwd=root, env=dict(os.environ, **env), capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -16,17 +16,22 @@
 //     channel block's patch and then issues its 9 taps back to back.
 // Per 128-row tile L2->SM carries 46 KB of patches + 49 KB of residual instead of 567 KB.
 //
-// Roles per CTA (16 warps): warp 0 TMA producer, warps 1 / 14 MMA issuers -- active in the LEADER CTA only, issuer k
-// taking channel block k of every tap into its own accumulator (the K-split of the 1-CTA kernel: even / odd
-// k-iterations ARE channel block 0 / 1, so the fp32 summation order is the same) with cta_group::2 UMMAs (256 x 96 x 16)
-// for both SMs -- warps 2..13 epilogue, warp 15 (leader) issues the tail GEMMs.
-// TMEM (512 columns per SM, C = 96): two accumulator pairs [b*2C, b*2C + 2C), two staged operands P[b] at 4C + b*C/2;
-// the tail accumulator (2C columns) of tile t overlays pair t & 1, which phase 1 has just drained.
+// Roles per CTA (16 warps): warp 0 TMA producer; warp 1 MMA issuer and warp 14 tail-GEMM issuer -- active in the LEADER
+// CTA only, issuing cta_group::2 UMMAs (256 x 96 x 16) for both SMs; warps 2..13 epilogue; warp 15 idle.  With both
+// operands resident one issuer is enough (54 MMAs per tile, ~5k cycles, hidden behind the epilogue), so K runs through
+// ONE accumulator (channel block 0's nine taps, then channel block 1's).
+// TMEM (512 columns per SM, C = 96): acc1[b] at b*C (two buffers), staged operands P[b] at 2C + b*C/2, the tail
+// accumulator acc2 (2C columns, one buffer) at 3C: 480 columns.
+// Epilogue order (skewed by one tile): P1(0); then per tile lt: P1(lt+1), P2(lt).  P1 stages gelu(acc1 + b2) as the tail
+// operand, P2 finishes out = gelu(acc2 + b3 + x).  The tail GEMM of lt (remote arrivals of 24 warps, 6 MMAs behind
+// whatever main loop is queued, the multicast commit: 3-4k cycles, exposed in the unskewed order) runs under P1(lt+1);
+// the main loop of lt+2 is released by P1(lt) (acc1[b] drained) and runs under P2(lt-1) .. P2(lt).
 // Barriers: both CTAs' patches complete on the LEADER's a_full[slot]; the leader's commits are multicast to both CTAs'
-// a_empty[slot] / acc1_full / acc2_full; both CTAs' epilogue warps arrive on the leader's p_full / acc1_empty (count 24).
-// Patch slots: 4, slot = (2 * local tile + channel block) & 3 -- issuer k only ever sees slots k and k + 2, filled and
-// released in its own order (a ring shared by both issuers lets one wait on a barrier the other is a lap behind on:
-// the parity wait then aliases; found the hard way).
+// a_empty[slot] / acc1_full[b] / acc2_full; both CTAs' epilogue warps arrive on the leader's p_full[b] (P[b] staged and
+// acc1[b] drained: releases the tail GEMM of lt and the main loop of lt+2) and acc2_empty (count 24 each).
+// Patch slots: 4, slot = (2 * local tile + channel block) & 3, filled and consumed in one order by one producer / issuer.
+// (An earlier form with a ring shared by two issuers let one wait on a barrier the other was a lap behind on: the parity
+// wait aliases and a stage is overwritten unconsumed -- found the hard way.)
 #include "tc_common.cuh"
 
 #ifdef RDSIC_DEBUG
@@ -40,14 +45,12 @@
 namespace {
 
 constexpr int RP_EPI_WARPS = 12;
-constexpr int RP_ISSUER2_WARP = 2 + RP_EPI_WARPS;
-constexpr int RP_TAIL_WARP = RP_ISSUER2_WARP + 1;  // issues the tail GEMMs (leader CTA)
+constexpr int RP_TAIL_WARP = 2 + RP_EPI_WARPS;          // issues the tail GEMMs (leader CTA); warp 15 is idle
 constexpr int RP_THREADS = 128 + 32 * RP_EPI_WARPS;
 constexpr int RP_PARTS = RP_EPI_WARPS / 4;
-constexpr int RP_MAXC = 96;                            // 5 C <= 512 TMEM columns
-constexpr int RP_CHUNKS1 = RP_MAXC / 16 / RP_PARTS;    // phase-1 chunks per warp (2)
+constexpr int RP_MAXC = 96;                              // 5 C <= 512 TMEM columns
+constexpr int RP_CHUNKS1 = RP_MAXC / 16 / RP_PARTS;      // phase-1 chunks per warp (2)
 constexpr int RP_CHUNKS2 = 2 * RP_MAXC / 16 / RP_PARTS;  // phase-2 chunks per warp (4)
-
 constexpr int RP_SLOTS = 4;
 
 struct RuPairGeom {
@@ -55,7 +58,6 @@ struct RuPairGeom {
   int halo_w, halo_h, patch_bytes, patch_tx;  // (TW+KW-1) x (TH+KH-1) pixels x 128 B; patch_bytes rounded up to 1 KB
   long long* ts;  // RDSIC_DEBUG builds (RDSIC_RP_TS = device address of an int64 buffer): clock64 stamps of CTA 0, 16 per local tile
   int dbg;        // RDSIC_DEBUG builds (RDSIC_RP_DBG): bit1 = no epilogue math / stores (results are garbage)
-  int paired;     // RDSIC_RP_ORDER=2: epilogue order P1(a) P1(b) P2(a) P2(b) instead of P1 P2 per tile (measured slower)
   int b_blk_bytes, w3_blk_bytes;  // one resident k-block of this CTA's half: (C/2) x 128 B, (N2/2) x 128 B
 };
 
@@ -74,6 +76,13 @@ __device__ __forceinline__ void rp_tmem_st8(uint32_t taddr, const uint32_t* r) {
                : "memory");
 }
 __device__ __forceinline__ void rp_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// explicit shared-window load: in a cluster kernel the generic address of a shared array is rebuilt from the CTA id
+// at every use (~25 uniform instructions per bias vector in the first version of this epilogue)
+__device__ __forceinline__ float4 rp_lds128(uint32_t addr) {
+  float4 f;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "r"(addr));
+  return f;
+}
 
 __global__ void __launch_bounds__(RP_THREADS, 1)
 ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -83,12 +92,12 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint8_t* b_res = smem + (size_t)RP_SLOTS * rg.patch_bytes;         // [kiters][C/2 rows x 128 B]
   uint8_t* w3_res = b_res + (size_t)rg.kiters * rg.b_blk_bytes;      // [k2_blocks][N2/2 rows x 128 B]
   uint64_t* a_full = (uint64_t*)(w3_res + (size_t)rg.k2_blocks * rg.w3_blk_bytes);  // [RP_SLOTS] LEADER's copy
-  uint64_t* a_empty = a_full + RP_SLOTS;         // [RP_SLOTS] local, multicast commit of the slot's issuer
-  uint64_t* acc1_full = a_empty + RP_SLOTS;      // [2] local, multicast commit of both issuers
-  uint64_t* acc1_empty = acc1_full + 2;          // [2] LEADER's copy collects both CTAs' epilogue warps
-  uint64_t* p_full = acc1_empty + 2;             // [2] LEADER's copy
-  uint64_t* acc2_full = p_full + 2;              // [2] local, multicast commit of the tail issuer
-  uint64_t* w_full = acc2_full + 2;              // LEADER's copy: resident weights of both CTAs have landed
+  uint64_t* a_empty = a_full + RP_SLOTS;         // [RP_SLOTS] local, multicast commit of the issuer
+  uint64_t* acc1_full = a_empty + RP_SLOTS;      // [2] local, multicast commit of the issuer
+  uint64_t* p_full = acc1_full + 2;              // [2] LEADER's copy: P[b] staged and acc1[b] drained by both CTAs
+  uint64_t* acc2_full = p_full + 2;              // local, multicast commit of the tail issuer
+  uint64_t* acc2_empty = acc2_full + 1;          // LEADER's copy: acc2 drained by both CTAs
+  uint64_t* w_full = acc2_empty + 1;             // LEADER's copy: resident weights of both CTAs have landed
   uint32_t* tmem_slot = (uint32_t*)(w_full + 1);
   float* bias1_s = (float*)(((uintptr_t)(tmem_slot + 1) + 15) & ~(uintptr_t)15);  // [C]
   float* bias2_s = bias1_s + RP_MAXC;                                             // [N2]
@@ -102,15 +111,14 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_g) : "memory");
     for (int s = 0; s < RP_SLOTS; ++s) {
       mbar_init(&a_full[s], 1);
-      mbar_init(&a_empty[s], 1);  // every patch is consumed by exactly one issuer (its channel block's)
+      mbar_init(&a_empty[s], 1);
     }
     for (int k = 0; k < 2; ++k) {
-      mbar_init(&acc1_full[k], 2);
-      mbar_init(&acc1_empty[k], 2 * RP_EPI_WARPS);
+      mbar_init(&acc1_full[k], 1);
       mbar_init(&p_full[k], 2 * RP_EPI_WARPS);
     }
-    mbar_init(&acc2_full[0], 1);
-    mbar_init(&acc2_full[1], 1);
+    mbar_init(acc2_full, 1);
+    mbar_init(acc2_empty, 2 * RP_EPI_WARPS);
     mbar_init(w_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -127,6 +135,8 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   const TileWalk wk = make_walk(g);
   const bool leader = wk.crank == 0;
+  // TMEM columns
+  const uint32_t P_COL = (uint32_t)(2 * C), ACC2_COL = (uint32_t)(3 * C);
 
   if (warp == 0) {
     // ================= TMA producer (whole warp, elected lane issues) =================
@@ -171,10 +181,9 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // release of the LAST fill of every slot
     for (int n = 0; n < RP_SLOTS; ++n, ++u) mbar_wait_u32(a_empty0 + 8u * (u & (RP_SLOTS - 1)), ((u >> 2) & 1u) ^ 1u);
     __syncwarp();
-  } else if (warp == 1 || warp == RP_ISSUER2_WARP) {
-    // ================= MMA issuers: leader CTA only =================
+  } else if (warp == 1) {
+    // ================= MMA issuer: leader CTA only =================
     if (leader) {
-      const uint32_t me = warp == 1 ? 0u : 1u;
       const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t a_full0 = __shfl_sync(0xffffffffu, smem_u32(a_full), 0);
       const uint32_t a_empty0 = __shfl_sync(0xffffffffu, smem_u32(a_empty), 0);
@@ -185,40 +194,43 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const uint32_t idesc = make_idesc(C, 2 * BM);
       int kb = rg.kb, total = g.walk_total, step = wk.step, KH = d.KH, KW = d.KW, hw8 = rg.halo_w * 8;
       asm volatile("" : "+r"(kb), "+r"(total), "+r"(step), "+r"(KH), "+r"(KW), "+r"(hw8));
-      const int kc = (int)me + 1 != kb ? 4 : rg.kc_last;  // valid 16-wide K steps of this issuer's channel block
       mbar_wait(w_full, 0);  // both CTAs' resident weights are in place
       tcgen05_fence_after();
       uint32_t lt = 0;
       for (int q = wk.first; q < total; q += step, ++lt) {
         const uint32_t b = lt & 1u, use = (lt >> 1) & 1u;
-        const uint32_t u = 2u * lt + me, slot = u & (RP_SLOTS - 1), ph = (u >> 2) & 1u;
-        long long* tsp = RP_TS(lane == 0, me * 3);
+        long long* tsp = RP_TS(lane == 0, 0);
         if (tsp) tsp[0] = clock64();
-        mbar_wait(&acc1_empty[b], use ^ 1u);  // pair b drained by BOTH CTAs (phase 2 of tile lt - 2)
-        mbar_wait_u32(a_full0 + 8u * slot, ph);  // both CTAs' patches of this channel block have landed
+        mbar_wait(&p_full[b], use ^ 1u);  // acc1[b] drained by BOTH CTAs (phase 1 of tile lt - 2)
         tcgen05_fence_after();
         if (tsp) tsp[1] = clock64();
-        const uint32_t acc = tbase + b * (uint32_t)(2 * C) + me * (uint32_t)C;
-        const uint64_t da0 = dconst_halo + (uint64_t)(patch_u0 + slot * patch_u);
-        const uint64_t db0 = dconst + (uint64_t)(b_u0 + me * bblk_u);
-        if (elect_one()) {
-          int tap = 0;
-          for (int r = 0; r < KH; ++r)
-            for (int sx = 0; sx < KW; ++sx, ++tap) {
-              const uint64_t da = da0 + (uint64_t)(uint32_t)(r * hw8 + sx * 8);         // window shifted by (r, sx) pixels
-              const uint64_t db = db0 + (uint64_t)((uint32_t)(tap * kb) * bblk_u);      // resident k-block tap * kb + me
-              if (kc == 4) {
-                umma_bf16_2sm(acc, da, db, idesc, tap ? 1u : 0u);
-                umma_bf16_2sm(acc, da + 2, db + 2, idesc, 1u);
-                umma_bf16_2sm(acc, da + 4, db + 4, idesc, 1u);
-                umma_bf16_2sm(acc, da + 6, db + 6, idesc, 1u);
-              } else {
-                for (int k = 0; k < kc; ++k) umma_bf16_2sm(acc, da + 2 * k, db + 2 * k, idesc, (tap || k) ? 1u : 0u);
+        const uint32_t acc = tbase + b * (uint32_t)C;
+        for (uint32_t cb = 0; cb < 2; ++cb) {
+          const uint32_t u = 2u * lt + cb, slot = u & (RP_SLOTS - 1), ph = (u >> 2) & 1u;
+          mbar_wait_u32(a_full0 + 8u * slot, ph);  // both CTAs' patches of this channel block have landed
+          tcgen05_fence_after();
+          const uint64_t da0 = dconst_halo + (uint64_t)(patch_u0 + slot * patch_u);
+          const uint64_t db0 = dconst + (uint64_t)(b_u0 + cb * bblk_u);
+          const int kc = (int)cb + 1 != kb ? 4 : rg.kc_last;  // valid 16-wide K steps of this channel block
+          if (elect_one()) {
+            int tap = 0;
+            for (int r = 0; r < KH; ++r)
+              for (int sx = 0; sx < KW; ++sx, ++tap) {
+                const uint64_t da = da0 + (uint64_t)(uint32_t)(r * hw8 + sx * 8);     // window shifted by (r, sx) pixels
+                const uint64_t db = db0 + (uint64_t)((uint32_t)(tap * kb) * bblk_u);  // resident k-block tap * kb + cb
+                if (kc == 4) {
+                  umma_bf16_2sm(acc, da, db, idesc, (cb | (uint32_t)tap) ? 1u : 0u);
+                  umma_bf16_2sm(acc, da + 2, db + 2, idesc, 1u);
+                  umma_bf16_2sm(acc, da + 4, db + 4, idesc, 1u);
+                  umma_bf16_2sm(acc, da + 6, db + 6, idesc, 1u);
+                } else {
+                  for (int k = 0; k < kc; ++k) umma_bf16_2sm(acc, da + 2 * k, db + 2 * k, idesc, (cb | (uint32_t)tap | (uint32_t)k) ? 1u : 0u);
+                }
               }
-            }
-          tcgen05_commit_2sm_mc_u32(a_empty0 + 8u * slot, 3);  // frees the patch slot in BOTH CTAs
+            tcgen05_commit_2sm_mc_u32(a_empty0 + 8u * slot, 3);  // frees the patch slot in BOTH CTAs
+          }
+          __syncwarp();
         }
-        __syncwarp();
         if (elect_one()) tcgen05_commit_2sm_mc_u32(smem_u32(&acc1_full[b]), 3);
         __syncwarp();
         if (tsp) tsp[2] = clock64();
@@ -227,7 +239,7 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     __syncwarp();
   } else if (warp == RP_TAIL_WARP) {
     // ================= tail-GEMM issuer: leader CTA only =================
-    // tail GEMM of tile lt for BOTH CTAs: A = P[b] (each SM's own TMEM), B = resident W3 halves, D over pair b
+    // tail GEMM of tile lt for BOTH CTAs: A = P[b] (each SM's own TMEM), B = resident W3 halves, D = acc2
     if (leader) {
       const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t w3_addr = __shfl_sync(0xffffffffu, smem_u32(w3_res), 0);
@@ -239,10 +251,11 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int q = wk.first; q < total; q += step, ++lt) {
         const uint32_t b = lt & 1u, par1 = (lt >> 1) & 1u;
         long long* tsp = RP_TS(lane == 0, 0);
-        mbar_wait(&p_full[b], par1);  // all 24 epilogue warps of the pair have staged P[b] and consumed pair b
+        mbar_wait(&p_full[b], par1);             // all 24 epilogue warps of the pair have staged P[b]
+        mbar_wait(acc2_empty, (lt & 1u) ^ 1u);   // ... and drained acc2 (phase 2 of tile lt - 1)
         tcgen05_fence_after();
         if (tsp) tsp[6] = clock64();
-        const uint32_t p_t = tbase + (uint32_t)(4 * C) + b * (uint32_t)(C / 2), acc2 = tbase + b * (uint32_t)(2 * C);
+        const uint32_t p_t = tbase + P_COL + b * (uint32_t)(C / 2), acc2 = tbase + ACC2_COL;
         if (elect_one()) {
           for (int kb2 = 0; kb2 < rg.k2_blocks; ++kb2) {
             const uint64_t dg = make_sw128_desc(w3_addr + (uint32_t)(kb2 * rg.w3_blk_bytes));
@@ -250,93 +263,93 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             for (int k = 0; k < kc2; ++k)  // 16 bf16 of K = 8 TMEM columns of the staged operand
               umma_bf16_ts_2sm(acc2, p_t + (uint32_t)((kb2 * 4 + k) * 8), dg + 2 * k, idesc2, (kb2 | k) ? 1u : 0u);
           }
-          tcgen05_commit_2sm_mc_u32(smem_u32(&acc2_full[b]), 3);
+          tcgen05_commit_2sm_mc_u32(smem_u32(acc2_full), 3);
         }
         __syncwarp();
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp < RP_TAIL_WARP) {
     // ================= epilogue warps (both CTAs) =================
-    // Per tile: P1 (stage the tail operand), wait for the tail GEMM, P2.  rg.paired processes two tiles in the order
-    // P1(a) P1(b) P2(a) P2(b) so that the tail GEMM of a runs under P1(b) -- measured SLOWER (257 vs 225 us): the main loop
-    // of b, released only by the previous P2(b), and the residual loads are then exposed instead (tests/gpu_ru_pair_probe3.py).
     const int q = warp % 4, part = (warp - 2) / 4;
     const int ml = q * 32 + lane;
     const int dy = ml / g.TW, dx = ml % g.TW;
     const int nchunks1 = C / 16, nchunks2 = rg.N2 / 16;
-    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const uint32_t lead_p_full0 = mapa_u32(smem_u32(p_full), 0u), lead_acc1_empty0 = mapa_u32(smem_u32(acc1_empty), 0u);
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t lead_p_full0 = mapa_u32(smem_u32(p_full), 0u), lead_acc2_empty = mapa_u32(smem_u32(acc2_empty), 0u);
+    const uint32_t acc1_full0 = smem_u32(acc1_full), acc2_full_a = smem_u32(acc2_full);
+    const uint32_t bias1_a = smem_u32(bias1_s), bias2_a = smem_u32(bias2_s);
+    const int total = g.walk_total, step = wk.step;
 
-    // ---- phase 1 of local tile lt: t = gelu(acc1[block 0] + acc1[block 1] + b2) -> bf16 -> TMEM operand P[lt & 1]
+    // ---- phase 1 of local tile lt: t = gelu(acc1 + b2) -> bf16 -> TMEM operand P[lt & 1]
     auto phase1 = [&](uint32_t lt) {
       const uint32_t bsel = lt & 1u, par1 = (lt >> 1) & 1u;
-      const uint32_t acc1_c = bsel * (uint32_t)(2 * C), p_c = (uint32_t)(4 * C) + bsel * (uint32_t)(C / 2);
+      const uint32_t acc1_t = tlane + bsel * (uint32_t)C, p_t = tlane + P_COL + bsel * (uint32_t)(C / 2);
       long long* tsp = RP_TS(warp == 2 && lane == 0, 0);
       if (tsp) tsp[7] = clock64();
-      mbar_wait(&acc1_full[bsel], par1);
+      mbar_wait_u32(acc1_full0 + 8u * bsel, par1);
       tcgen05_fence_after();
       if (tsp) tsp[8] = clock64();
+      uint32_t ua[RP_CHUNKS1][16];
+#pragma unroll
+      for (int ci = 0; ci < RP_CHUNKS1; ++ci)
+        if (part + RP_PARTS * ci < nchunks1) tmem_ld16_issue(acc1_t + (uint32_t)((part + RP_PARTS * ci) * 16), ua[ci]);
+      tmem_ld_wait();
 #pragma unroll
       for (int ci = 0; ci < RP_CHUNKS1; ++ci) {
         const int j = part + RP_PARTS * ci;
         if (j >= nchunks1) break;
-        uint32_t ua[16], ub[16];
-        tmem_ld16_issue(tmem_base + lane_off + acc1_c + (uint32_t)(j * 16), ua);
-        tmem_ld16_issue(tmem_base + lane_off + acc1_c + (uint32_t)(C + j * 16), ub);
-        tmem_ld_wait();
-        tmem_ld_fence(ua);
-        tmem_ld_fence(ub);
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ua[i]) + __uint_as_float(ub[i]);  // fixed order: block 0 + block 1
-        const float4* bp = reinterpret_cast<const float4*>(bias1_s + j * 16);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 f = bp[i];
-          v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
-        }
+        tmem_ld_fence(ua[ci]);
         uint32_t st[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          __nv_bfloat162 h = RP_NOMATH ? __floats2bfloat162_rn(v[2 * i], v[2 * i + 1])
-                                          : __floats2bfloat162_rn(gelu_fast(v[2 * i]), gelu_fast(v[2 * i + 1]));
-          st[i] = *reinterpret_cast<uint32_t*>(&h);
+        for (int i = 0; i < 4; ++i) {
+          const float4 f = rp_lds128(bias1_a + (uint32_t)((j * 16 + 4 * i) * 4));
+          const float v0 = __uint_as_float(ua[ci][4 * i]) + f.x, v1 = __uint_as_float(ua[ci][4 * i + 1]) + f.y;
+          const float v2 = __uint_as_float(ua[ci][4 * i + 2]) + f.z, v3 = __uint_as_float(ua[ci][4 * i + 3]) + f.w;
+          __nv_bfloat162 h0 = RP_NOMATH ? __floats2bfloat162_rn(v0, v1) : __floats2bfloat162_rn(gelu_fast(v0), gelu_fast(v1));
+          __nv_bfloat162 h1 = RP_NOMATH ? __floats2bfloat162_rn(v2, v3) : __floats2bfloat162_rn(gelu_fast(v2), gelu_fast(v3));
+          st[2 * i] = *reinterpret_cast<uint32_t*>(&h0);
+          st[2 * i + 1] = *reinterpret_cast<uint32_t*>(&h1);
         }
-        rp_tmem_st8(tmem_base + lane_off + p_c + (uint32_t)(j * 8), st);
+        rp_tmem_st8(p_t + (uint32_t)(j * 8), st);
       }
       rp_tmem_st_wait();
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster_u32(lead_p_full0 + 8u * bsel);  // operand staged, pair bsel consumed
+      if (lane == 0) mbar_arrive_cluster_u32(lead_p_full0 + 8u * bsel);  // P[bsel] staged, acc1[bsel] drained
       if (tsp) tsp[9] = clock64();
     };
 
-    // ---- phase 2 of local tile lt (walk position tq): out = gelu(acc2 + b3 + x)
-    auto phase2 = [&](uint32_t lt, int tq) {
+    uint32_t lt = 0;
+    if (wk.first < total) phase1(0);
+    for (int tq = wk.first; tq < total; tq += step, ++lt) {
       int nt, tx, ty, b;
       const bool tile_ok = tile_of(g, wk, tq, nt, tx, ty, b);
       const int oy = ty * g.TH + dy, ox = tx * g.TW + dx;
       const bool row_ok = tile_ok && oy < d.OH && ox < d.OW;
       const size_t pix = ((size_t)b * d.OHt + (oy * d.osy + d.ooy)) * d.OWt + (ox * d.osx + d.oox);
-      const uint32_t bsel = lt & 1u, par1 = (lt >> 1) & 1u;
-      const uint32_t acc2_c = bsel * (uint32_t)(2 * C);  // the tail accumulator overlays pair bsel
-      uint32_t xs[RP_CHUNKS2][8];                         // residual x (packed bf16): loads in flight across the barrier wait
-      {
-        const __nv_bfloat16* resp = (const __nv_bfloat16*)d.res.ptr + pix * (size_t)d.res.ld + d.res.coff;
+      const __nv_bfloat16* resp = (const __nv_bfloat16*)d.res.ptr + pix * (size_t)d.res.ld + d.res.coff;
+      __nv_bfloat16* outp = (__nv_bfloat16*)d.out.ptr + pix * (size_t)d.out.ld + d.out.coff;
+      // residual x of this tile (packed bf16): in flight while phase 1 of the NEXT tile is computed.  (Right after the
+      // previous phase 2 the load/store unit is still draining that phase's stores -- 32 sectors per STG.256 -- and these
+      // loads stall the warp for up to ~3k cycles; issuing them after phase 1 instead moves the same time into phase 2's
+      // wait for the data: measured equal, tests/gpu_ru_pair_probe3.py.)
+      uint32_t xs[RP_CHUNKS2][8];
 #pragma unroll
-        for (int ci = 0; ci < RP_CHUNKS2; ++ci) {
-          const int j = part + RP_PARTS * ci;
-          if (j < nchunks2 && row_ok) {
-            const Pack8 r = ldg256(resp + j * 16);
+      for (int ci = 0; ci < RP_CHUNKS2; ++ci) {
+        const int j = part + RP_PARTS * ci;
+        if (j < nchunks2 && row_ok) {
+          const Pack8 r = ldg256(resp + j * 16);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) xs[ci][i] = r.w[i];
-          }
+          for (int i = 0; i < 8; ++i) xs[ci][i] = r.w[i];
         }
       }
+      if (tq + step < total) phase1(lt + 1);
+
+      // ---- phase 2 of tile lt: out = gelu(acc2 + b3 + x)
       long long* tsp = RP_TS(warp == 2 && lane == 0, 0);
       if (tsp) tsp[10] = clock64();
-      mbar_wait(&acc2_full[bsel], par1);
+      mbar_wait_u32(acc2_full_a, lt & 1u);
       tcgen05_fence_after();
       if (tsp) tsp[11] = clock64();
 #pragma unroll
@@ -345,8 +358,8 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (ja >= nchunks2) break;
         const bool has_b = jb < nchunks2;
         uint32_t ua[16], ub[16];
-        tmem_ld16_issue(tmem_base + lane_off + acc2_c + (uint32_t)(ja * 16), ua);
-        if (has_b) tmem_ld16_issue(tmem_base + lane_off + acc2_c + (uint32_t)(jb * 16), ub);
+        tmem_ld16_issue(tlane + ACC2_COL + (uint32_t)(ja * 16), ua);
+        if (has_b) tmem_ld16_issue(tlane + ACC2_COL + (uint32_t)(jb * 16), ub);
         tmem_ld_wait();
         tmem_ld_fence(ua);
         if (has_b) tmem_ld_fence(ub);
@@ -356,36 +369,26 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const int ci = cp + hb, j = hb ? jb : ja;
           const uint32_t* u = hb ? ub : ua;
           if (!row_ok || RP_NOMATH) continue;
-          float v[16];
-          const float4* bp = reinterpret_cast<const float4*>(bias2_s + j * 16);
+          Pack8 o;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 f = bp[i];
-            v[4 * i] = __uint_as_float(u[4 * i]) + f.x; v[4 * i + 1] = __uint_as_float(u[4 * i + 1]) + f.y;
-            v[4 * i + 2] = __uint_as_float(u[4 * i + 2]) + f.z; v[4 * i + 3] = __uint_as_float(u[4 * i + 3]) + f.w;
+            const float4 f = rp_lds128(bias2_a + (uint32_t)((j * 16 + 4 * i) * 4));
+            const uint32_t xa = xs[ci][2 * i], xb = xs[ci][2 * i + 1];
+            const float v0 = gelu_fast(__uint_as_float(u[4 * i]) + f.x + __uint_as_float(xa << 16));
+            const float v1 = gelu_fast(__uint_as_float(u[4 * i + 1]) + f.y + __uint_as_float(xa & 0xFFFF0000u));
+            const float v2 = gelu_fast(__uint_as_float(u[4 * i + 2]) + f.z + __uint_as_float(xb << 16));
+            const float v3 = gelu_fast(__uint_as_float(u[4 * i + 3]) + f.w + __uint_as_float(xb & 0xFFFF0000u));
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
+            o.w[2 * i] = *reinterpret_cast<uint32_t*>(&h0);
+            o.w[2 * i + 1] = *reinterpret_cast<uint32_t*>(&h1);
           }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float x0 = __uint_as_float(xs[ci][i] << 16), x1 = __uint_as_float(xs[ci][i] & 0xFFFF0000u);
-            v[2 * i] = gelu_fast(v[2 * i] + x0);
-            v[2 * i + 1] = gelu_fast(v[2 * i + 1] + x1);
-          }
-          store16(d.out, pix * (size_t)d.out.ld + d.out.coff + j * 16, v, false);
+          stg256(outp + j * 16, o);
         }
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster_u32(lead_acc1_empty0 + 8u * bsel);  // pair bsel (acc1 + overlaid acc2) is free
+      if (lane == 0) mbar_arrive_cluster_u32(lead_acc2_empty);  // acc2 drained: the next tail GEMM may overwrite it
       if (tsp) tsp[12] = clock64();
-    };
-
-    uint32_t lt = 0;
-    for (int tq = wk.first; tq < g.walk_total; tq += (rg.paired ? 2 : 1) * wk.step, lt += (rg.paired ? 2u : 1u)) {
-      const uint32_t n = (rg.paired && tq + wk.step < g.walk_total) ? 2u : 1u;
-#pragma unroll 1
-      for (uint32_t h = 0; h < n; ++h) phase1(lt + h);
-#pragma unroll 1
-      for (uint32_t h = 0; h < n; ++h) phase2(lt + h, tq + (int)h * wk.step);
     }
   }
 
@@ -411,7 +414,7 @@ int rdsic_ru_pair_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   if (!encode) return RDSIC_E_UNSUPPORTED;
   TcGeom g = {};
   const int B = d->B, H = d->H, W = d->W, OH = d->OH, OW = d->OW;
-  if (d->stride != 1 || d->KH > 3 || d->KW > 3 || d->osy != 1 || d->osx != 1) return -1;
+  if (d->stride != 1 || d->KH > 3 || d->KW > 3 || d->osy != 1 || d->osx != 1 || d->out.dtype != RDSIC_BF16) return -1;
   g.TH = 16;  // 8 consecutive pixels of a patch row = one 1024-byte swizzle atom (8 rows of the A operand)
   g.TW = 8;
   g.tiles_x = ceil_div(OW, g.TW);
@@ -434,10 +437,8 @@ int rdsic_ru_pair_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   rg.N2 = N2;
   static const int tune_dbg = getenv("RDSIC_RP_DBG") ? atoi(getenv("RDSIC_RP_DBG")) : 0;
   static const long long tune_ts = getenv("RDSIC_RP_TS") ? atoll(getenv("RDSIC_RP_TS")) : 0;
-  static const int tune_order = getenv("RDSIC_RP_ORDER") ? atoi(getenv("RDSIC_RP_ORDER")) : 1;
   rg.dbg = tune_dbg;
   rg.ts = (long long*)tune_ts;
-  rg.paired = tune_order == 2;
   rg.k2_blocks = ceil_div(C, BK);
   rg.kc2_last = (C - (rg.k2_blocks - 1) * BK) / 16;
   rg.b_blk_bytes = (C / 2) * BK * 2;

@@ -45,6 +45,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // WS: window side (8 or 4); DH: head dim (multiple of 8); one warp per head (blockDim = 32 * heads).
 template <int WS, int DH>
 __global__ void __launch_bounds__(768) win_attn_tc_kernel(const rdsic_attn_desc d) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int NTOK = WS * WS;
   const int HEADS = d.heads, C = HEADS * DH, LD = 3 * C + 8;  // +8 bf16: conflict-free fragment loads
   const int NTHR = 32 * HEADS;
@@ -217,8 +219,7 @@ int launch_tc(const rdsic_attn_desc* d, cudaStream_t stream) {
     if (e != cudaSuccess) return (int)e;
   }
   const int nblk = d->B * (d->H / WS) * (d->W / WS);
-  kern<<<nblk, 32 * d->heads, smem, stream>>>(*d);
-  return rdsic_launch_status();
+  return rdsic_launch(kern, dim3((unsigned)nblk), 32 * d->heads, smem, stream, false, *d);
 }
 
 }  // namespace

@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const rdsic_conv_desc d, const TcGeom g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  pdl_trigger();
   // PAIR (cta_group::2) is a template parameter: a kernel that contains cta_group::2 instructions can only be launched
   // in clusters of two, so the 1-CTA instantiations must not contain any; the PAIR instantiation in turn drops the
   // halo / M2 / K-split / MC variants
@@ -95,6 +96,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
   }
+  // PDL: everything above touched only this CTA's own state; from here on global memory is read (the bias may have been
+  // packed by the immediately preceding kernel), so wait for the prerequisite grids first
+  pdl_wait();
   for (int i = threadIdx.x; i < (d.Cout + 15) / 16 * 16; i += blockDim.x) bias_s[i] = (d.bias && i < d.Cout) ? d.bias[i] : 0.f;
   tcgen05_fence_before();
   __syncthreads();
@@ -902,25 +906,10 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   }
   if (g.mc || g.pair) {
     const int grid = 2 * g.walk_total < (sms & ~1) ? 2 * g.walk_total : (sms & ~1);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(CONV_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, dd, g);
-    if (e != cudaSuccess) return (int)e;
-    return rdsic_launch_status();
+    return rdsic_launch(kern, dim3((unsigned)grid), CONV_THREADS, smem, stream, true, ta, tb, dd, g);
   }
   const int grid = g.total_tiles < sms ? g.total_tiles : sms;
-  kern<<<grid, CONV_THREADS, smem, stream>>>(ta, tb, dd, g);
-  return rdsic_launch_status();
+  return rdsic_launch(kern, dim3((unsigned)grid), CONV_THREADS, smem, stream, false, ta, tb, dd, g);
 }
 
 #ifdef RDSIC_DEBUG

@@ -175,6 +175,7 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                    const __grid_constant__ CUtensorMap tmap_g, const rdsic_conv_desc d, const TcGeom g,
                    const GdnGeom gg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  pdl_trigger();
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int stage_bytes = g.halo ? g.b_stage_bytes : A_STAGE_BYTES + g.b_stage_bytes;
   uint8_t* gamma_s = smem + (size_t)g.num_stages * stage_bytes;  // 1024-aligned: stage sizes are multiples of 2048
@@ -225,6 +226,7 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
+  pdl_wait();  // PDL: barrier init / TMEM allocation above overlap the previous kernel's tail; global memory from here on
   for (int i = threadIdx.x; i < C; i += blockDim.x) bias1_s[i] = d.bias ? d.bias[i] : 0.f;
   for (int i = threadIdx.x; i < gg.N2; i += blockDim.x) bias2_s[i] = d.tail_bias[i];
   tcgen05_fence_before();
@@ -827,23 +829,8 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   }
   if (g.mc) {
     const int grid = 2 * g.walk_total < (sms & ~1) ? 2 * g.walk_total : (sms & ~1);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(G_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tg, dd, g, gg);
-    if (e != cudaSuccess) return (int)e;
-    return rdsic_launch_status();
+    return rdsic_launch(kern, dim3((unsigned)grid), G_THREADS, smem, stream, true, ta, tb, tg, dd, g, gg);
   }
   const int grid = g.total_tiles < sms ? g.total_tiles : sms;
-  kern<<<grid, G_THREADS, smem, stream>>>(ta, tb, tg, dd, g, gg);
-  return rdsic_launch_status();
+  return rdsic_launch(kern, dim3((unsigned)grid), G_THREADS, smem, stream, false, ta, tb, tg, dd, g, gg);
 }

@@ -61,6 +61,8 @@ __device__ __forceinline__ float sigmoid_ref(float x) { return __fdiv_rn(1.0f, _
 // fall into 32 different banks.
 constexpr int EB_PITCH = RDSIC_EB_STRIDE + 1;
 __global__ void __launch_bounds__(256) eb_forward_kernel(const rdsic_eb_desc d) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_par[];  // [C][EB_PITCH]
   for (int i = threadIdx.x; i < d.C * RDSIC_EB_STRIDE; i += blockDim.x)
     s_par[(i / RDSIC_EB_STRIDE) * EB_PITCH + i % RDSIC_EB_STRIDE] = d.params[i];
@@ -130,6 +132,8 @@ __device__ __forceinline__ GcOut gc_element(const rdsic_gc_desc& d, const float*
 }
 
 __global__ void __launch_bounds__(256) gc_forward_kernel(const rdsic_gc_desc d) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_lik[GC_TC][GC_TP + 1];
   __shared__ int s_sym[GC_TC][GC_TP + 1];
   __shared__ int s_idx[GC_TC][GC_TP + 1];
@@ -193,6 +197,8 @@ __device__ __forceinline__ float4 ldg4(const rdsic_view& v, size_t pix, int c) {
   return __ldg(reinterpret_cast<const float4*>((const float*)v.ptr + pix * v.ld + v.coff + c));
 }
 __global__ void __launch_bounds__(256) gc_forward_vec_kernel(const rdsic_gc_desc d) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) float s_lik[GC_TC][GC_VP];
   __shared__ __align__(16) int s_sym[GC_TC][GC_VP];
   __shared__ __align__(16) int s_idx[GC_TC][GC_VP];
@@ -481,6 +487,8 @@ extern "C" int rdsic_eb_aux_loss(const float* params, const float* quantiles, co
 // layers/mask_layer.py:64-107 (eval: Mask.forward, then apply_noise's torch.round :37-38), elementwise over
 // channels-last fp32 logits.  torch.sigmoid / torch.pow / torch.round -> 1/(1+expf(-v)), powf, rintf.
 __global__ void __launch_bounds__(256) mask_forward_kernel(const rdsic_mask_desc d) {
+  pdl_trigger();
+  pdl_wait();
   const size_t total = (size_t)d.B * d.H * d.W * d.C;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const size_t pix = e / d.C;
@@ -508,8 +516,7 @@ extern "C" int rdsic_mask_forward(const rdsic_mask_desc* d, rdsic_stream_t strea
   for (int i = 0; i < d->n_in; ++i) RDSIC_CHECK_ARG(d->in[i].ptr && d->in[i].dtype == RDSIC_F32 && !d->in[i].nchw);
   const size_t total = (size_t)d->B * d->H * d->W * d->C;
   const size_t want = (total + 255) / 256, cap = (size_t)rdsic_sm_count() * 8;
-  mask_forward_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(*d);
-  return rdsic_launch_status();
+  return rdsic_launch(mask_forward_kernel, dim3((unsigned)(want < cap ? want : cap)), 256, 0, (cudaStream_t)stream, false, *d);
 }
 
 extern "C" int rdsic_eb_forward(const rdsic_eb_desc* d, rdsic_stream_t stream) {
@@ -527,8 +534,7 @@ extern "C" int rdsic_eb_forward(const rdsic_eb_desc* d, rdsic_stream_t stream) {
   }
   const size_t want = (total + 255) / 256, cap = (size_t)rdsic_sm_count() * 2;
   const int nblk = (int)(want < cap ? want : cap);
-  eb_forward_kernel<<<nblk, 256, smem, (cudaStream_t)stream>>>(*d);
-  return rdsic_launch_status();
+  return rdsic_launch(eb_forward_kernel, dim3((unsigned)nblk), 256, smem, (cudaStream_t)stream, false, *d);
 }
 
 extern "C" int rdsic_gc_forward(const rdsic_gc_desc* d, rdsic_stream_t stream) {
@@ -552,7 +558,6 @@ extern "C" int rdsic_gc_forward(const rdsic_gc_desc* d, rdsic_stream_t stream) {
              ((uintptr_t)d->lik % 16) == 0 && ((uintptr_t)d->symbols % 16) == 0 && ((uintptr_t)d->indexes % 16) == 0;
   for (int k = 0; k < 3; ++k) vec = vec && v4(d->y_hat[k], d->y_hat[k].dtype == RDSIC_BF16 ? 2 : 4);
   static const int tune_vec = getenv("RDSIC_GC_VEC") ? atoi(getenv("RDSIC_GC_VEC")) : 1;
-  if (vec && tune_vec) gc_forward_vec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d);
-  else gc_forward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d);
-  return rdsic_launch_status();
+  if (vec && tune_vec) return rdsic_launch(gc_forward_vec_kernel, grid, 256, 0, (cudaStream_t)stream, false, *d);
+  return rdsic_launch(gc_forward_kernel, grid, 256, 0, (cudaStream_t)stream, false, *d);
 }

@@ -9,6 +9,8 @@ namespace {
 // 32x32 smem-tiled transpose-copy: both the NHWC and the NCHW side are accessed
 // with 128-byte coalesced rows whichever direction we go.
 __global__ void __launch_bounds__(256) copy_views_kernel(const rdsic_copy_desc d) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int HW = d.H * d.W;
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
@@ -149,6 +151,8 @@ __global__ void __launch_bounds__(256) layernorm_generic_kernel(const rdsic_ln_d
 
 // one thread per 8-element (16-byte) chunk of a patch row
 __global__ void __launch_bounds__(256) patchify_kernel(const rdsic_patch_desc d) {
+  pdl_trigger();
+  pdl_wait();
   const int chunks = d.Kp / 8;
   const size_t total = (size_t)d.B * d.OH * d.OW * chunks;
   const int Kreal = d.KH * d.KW * d.C;
@@ -203,6 +207,8 @@ __global__ void __launch_bounds__(256) patchify_kernel(const rdsic_patch_desc d)
 constexpr int PT_H = 4, PT_W = 64, PT_MAX_K = 128, PT_MAX_TILE = 9216;  // tile floats (36 KB) + table < 48 KB
 
 __global__ void __launch_bounds__(256) patchify_tiled_kernel(const rdsic_patch_desc d, int tiles_x, int tiles_y) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[PT_MAX_TILE];
   __shared__ int lut[PT_MAX_K];
   const int rows = (PT_H - 1) * d.stride + d.KH, cols = (PT_W - 1) * d.stride + d.KW, pitch = cols | 1;  // odd pitch
@@ -266,8 +272,7 @@ extern "C" int rdsic_patch_forward(const rdsic_patch_desc* d, rdsic_stream_t str
     if (d->src.nchw && d->src.dtype == RDSIC_F32 && d->dst.dtype == RDSIC_BF16 && d->Kp <= PT_MAX_K &&
         tile_floats <= PT_MAX_TILE) {
       const int tiles_x = ceil_div(d->OW, PT_W), tiles_y = ceil_div(d->OH, PT_H);
-      patchify_tiled_kernel<<<(unsigned)((size_t)d->B * tiles_y * tiles_x), 256, 0, (cudaStream_t)stream>>>(*d, tiles_x, tiles_y);
-      return rdsic_launch_status();
+      return rdsic_launch(patchify_tiled_kernel, dim3((unsigned)((size_t)d->B * tiles_y * tiles_x)), 256, 0, (cudaStream_t)stream, false, *d, tiles_x, tiles_y);
     }
   }
   const size_t total = (size_t)d->B * d->OH * d->OW * (d->Kp / 8);
@@ -282,8 +287,7 @@ extern "C" int rdsic_copy_forward(const rdsic_copy_desc* d, rdsic_stream_t strea
   RDSIC_CHECK_ARG(d->op != 4 || (d->src2.ptr && d->src2.nchw == d->src.nchw));
   RDSIC_CHECK_ARG(d->B <= 65535);
   dim3 grid(ceil_div(d->H * d->W, 32), ceil_div(d->C, 32), d->B);
-  copy_views_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d);
-  return rdsic_launch_status();
+  return rdsic_launch(copy_views_kernel, grid, 256, 0, (cudaStream_t)stream, false, *d);
 }
 
 extern "C" int rdsic_ln_forward(const rdsic_ln_desc* d, rdsic_stream_t stream) {

@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(RP_THREADS, 1)
 ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_g, const rdsic_conv_desc d, const TcGeom g, const RuPairGeom rg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  pdl_trigger();
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* b_res = smem + (size_t)RP_SLOTS * rg.patch_bytes;         // [kiters][C/2 rows x 128 B]
   uint8_t* w3_res = b_res + (size_t)rg.kiters * rg.b_blk_bytes;      // [k2_blocks][N2/2 rows x 128 B]
@@ -126,6 +127,7 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
   }
+  pdl_wait();  // PDL: barrier init / TMEM allocation above overlap the previous kernel's tail; global memory from here on
   for (int i = threadIdx.x; i < C; i += blockDim.x) bias1_s[i] = d.bias ? d.bias[i] : 0.f;
   for (int i = threadIdx.x; i < rg.N2; i += blockDim.x) bias2_s[i] = d.tail_bias[i];
   tcgen05_fence_before();
@@ -487,19 +489,5 @@ int rdsic_ru_pair_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
     if (track) attr_set[dev] = true;
   }
   const int grid = 2 * g.walk_total < (sms & ~1) ? 2 * g.walk_total : (sms & ~1);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(RP_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, ru_pair_tc_kernel, ta, tb, tg, *d, g, rg);
-  if (e != cudaSuccess) return (int)e;
-  return rdsic_launch_status();
+  return rdsic_launch(ru_pair_tc_kernel, dim3((unsigned)grid), RP_THREADS, smem, stream, true, ta, tb, tg, *d, g, rg);
 }

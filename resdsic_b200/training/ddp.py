@@ -80,11 +80,9 @@ class GradBucketReducer:
             st = self._comm_stream(dev)
             if st is not None:
                 torch.cuda.current_stream(dev).wait_stream(st)
-            off = 0
-            for p in self.buckets[i]:
-                n = p.numel()
-                p.grad.copy_(flat[off:off + n].view_as(p.grad))
-                off += n
+            sizes = [p.numel() for p in self.buckets[i]]
+            views = [c.view_as(p.grad) for c, p in zip(flat.split(sizes), self.buckets[i])]
+            torch._foreach_copy_([p.grad for p in self.buckets[i]], views)  # one multi-tensor copy per bucket, not one per parameter
         n_buckets = len(self._work)
         self.reset()
         return n_buckets

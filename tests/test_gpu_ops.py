@@ -280,6 +280,7 @@ def test_patchify_matches_unfold(C, k, s, p, B, H, W):
     {"RDSIC_TC_M2_MINK": "1", "RDSIC_TC_M2": "2"},   # M2 also for the 1-3 k-iteration pointwise GEMMs
     {"RDSIC_RU_DBL": "0", "RDSIC_RU_PAIR": "0"},     # single-buffered fused ResidualUnit kernel
     {"RDSIC_RU_PAIR": "0"},                          # 1-CTA double-buffered fused ResidualUnit kernel (default: CTA pairs)
+    {"RDSIC_PDL": "1"},                              # programmatic dependent launch on every forward kernel (default off: measured slower)
     {"RDSIC_TC_PAIR": "3"},                          # cta_group::2 CTA pairs on EVERY layer with two M tiles (default: wide long-K layers)
     {"RDSIC_TC_PAIR": "0"},                          # no CTA pairs (M2 / single-issuer tiles everywhere)
     {"RDSIC_TC_PAIR": "0", "RDSIC_TC_MC": "1"},      # 1-CTA tiles with the B stage multicast across a CTA pair

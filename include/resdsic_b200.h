@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define RDSIC_ABI_VERSION 5
+#define RDSIC_ABI_VERSION 6
 
 typedef void* rdsic_stream_t; /* cudaStream_t */
 
@@ -362,6 +362,21 @@ int rdsic_eb_aux_backward(const float* params, const float* quantiles, const flo
  *   SUM sum(a) | SUM_LOG sum(log a) | SSE sum((a-b)^2). */
 enum { RDSIC_RED_SUM = 0, RDSIC_RED_SUM_LOG = 1, RDSIC_RED_SSE = 2 };
 int rdsic_reduce_f32(int op, size_t n, const float* a, const float* b, double* out, rdsic_stream_t stream);
+
+/*
+ * Host-facing image I/O (csrc/image_io.cu): what the reference's evaluation loop (eval_model/__main__.py:133-147) does
+ * on the host with fp32 images and full likelihood tensors, done on the device so that 1 byte per sample and 8 bytes
+ * per image cross PCIe.  All pointers are device pointers, 16-byte aligned; NCHW contiguous tensors of n samples.
+ *   u8_to_f32: dst = src / 255 (torchvision ToTensor)      f32_to_u8: dst = round(clamp(src, 0, 1) * 255)
+ *   rate_per_image: bits[b] = -(sum log2 lik_y[b] + sum log2 lik_z[b]) -- the rate term of RateDistortionLoss
+ *   (training/loss.py:14-22) per image before the division by the pixel count; ny / nz = elements per image;
+ *   workspace: rdsic_rate_workspace_doubles(B) doubles; fp64, fixed summation order.
+ */
+int rdsic_image_u8_to_f32(const uint8_t* src, float* dst, size_t n, rdsic_stream_t stream);
+int rdsic_image_f32_to_u8(const float* src, uint8_t* dst, size_t n, rdsic_stream_t stream);
+int rdsic_rate_per_image(const float* lik_y, size_t ny, const float* lik_z, size_t nz, int B, double* workspace, double* bits,
+                         rdsic_stream_t stream);
+int rdsic_rate_workspace_doubles(int B);
 
 /* Launch a whole program in order on `stream`.  *n_launched (optional) receives
  * the number of kernels launched.  Stops at the first error; *failed_op

@@ -113,6 +113,8 @@ EXPORTS = (
     # training: backward twins (include/resdsic_b200.h, "Training")
     "rdsic_conv_dgrad_f32", "rdsic_conv_wgrad_f32", "rdsic_pointwise_f32", "rdsic_pixel_shuffle_f32",
     "rdsic_attn_backward_f32", "rdsic_gc_backward", "rdsic_eb_backward", "rdsic_eb_aux_backward", "rdsic_reduce_f32",
+    # host-facing image I/O (csrc/image_io.cu)
+    "rdsic_image_u8_to_f32", "rdsic_image_f32_to_u8", "rdsic_rate_per_image", "rdsic_rate_workspace_doubles",
 )
 (PW_ADD, PW_GELU_FWD, PW_GELU_BWD, PW_GATE_FWD, PW_GATE_BWD, PW_GDN_FWD, PW_GDN_BWD, PW_SQUARE_FWD, PW_SQUARE_BWD,
  PW_LRP_FWD, PW_LRP_BWD, PW_RECIP_SCALE, PW_DIFF_SCALE, PW_SCALE, PW_MUL) = range(15)
@@ -168,7 +170,12 @@ def lib():
                      ("rdsic_reduce_f32", [C.c_int, C.c_size_t, vp, vp, vp, vp])):
         getattr(L, fn).argtypes = args
         getattr(L, fn).restype = C.c_int
-    if L.rdsic_abi_version() != 5:
+    for fn, args in (("rdsic_image_u8_to_f32", [vp, vp, C.c_size_t, vp]), ("rdsic_image_f32_to_u8", [vp, vp, C.c_size_t, vp]),
+                     ("rdsic_rate_per_image", [vp, C.c_size_t, vp, C.c_size_t, C.c_int, vp, vp, vp]),
+                     ("rdsic_rate_workspace_doubles", [C.c_int])):
+        getattr(L, fn).argtypes = args
+        getattr(L, fn).restype = C.c_int
+    if L.rdsic_abi_version() != 6:
         raise RuntimeError("resdsic_b200: ABI version mismatch between the python host and the CUDA library")
     for what, T in enumerate((Op, ConvDesc, AttnDesc, EBDesc, GCDesc, CopyDesc, View, LNDesc, PatchDesc, MaskDesc)):
         if L.rdsic_sizeof(what) != C.sizeof(T):

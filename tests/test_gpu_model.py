@@ -119,6 +119,32 @@ def test_forward_pipeline_matches_direct_calls(model):
     assert pipe.h2d_bytes == 2 * 3 * 64 * 128 * 4
 
 
+def test_compact_pipeline_uint8_io_and_per_image_rate(model):
+    """compact=True: uint8 images in, uint8 x_hat + per-image bits out (csrc/image_io.cu).  The device-side conversions
+    reproduce the host arithmetic bit for bit (v / 255; round(clamp * 255)); bits[b] equals -sum(log2 lik) of the direct
+    call to 1e-6 relative (log2f on the device vs torch.log2 on the host, fp64 accumulation on both sides)."""
+    from resdsic_b200.utils import ForwardPipeline
+    model.set_precision("fp32")
+    g = torch.Generator().manual_seed(5)
+    batches = [torch.randint(0, 256, (3, 3, 64, 128), dtype=torch.uint8, generator=g).pin_memory() for _ in range(4)]
+    want = []
+    for hb in batches:
+        o = model((hb.float() / 255.0).to(DEV))
+        xh = (o["x_hat"].clamp(0, 1) * 255.0).round().to(torch.uint8).cpu()
+        bits = -(o["likelihoods"]["y"].double().log2().sum(dim=(1, 2, 3)) + o["likelihoods"]["z"].double().log2().sum(dim=(1, 2, 3))).cpu()
+        want.append((xh, bits))
+    got = {}
+    pipe = ForwardPipeline(model, batches[0], depth=2, compact=True)
+    n = pipe.run(batches, on_result=lambda i, xh, bits: got.__setitem__(i, (xh.clone(), bits.clone())))
+    assert n == 4 and sorted(got) == list(range(4))
+    for i in range(4):
+        assert torch.equal(got[i][0], want[i][0]), i
+        assert torch.allclose(got[i][1], want[i][1], rtol=1e-6, atol=0), (got[i][1], want[i][1])
+    assert pipe.h2d_bytes == 3 * 3 * 64 * 128 and pipe.d2h_bytes == 3 * 3 * 64 * 128 + 3 * 8
+    with pytest.raises(ValueError):
+        ForwardPipeline(model, batches[0], compact=False)
+
+
 def test_config2_batch16_256_bf16_properties(model):
     """BASELINE config 2: batch 16 x 256 x 256 in bf16 mode -- output contract, finite likelihoods in (0,1],
     determinism, and per-image independence (image k alone == image k inside the batch, bit for bit)."""

@@ -215,6 +215,12 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        try:  # one slice of the host cores per rank: the copy-issuing threads of the N processes do not migrate over each other
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            os.sched_setaffinity(0, cores[local * per:(local + 1) * per] or cores)
+        except (AttributeError, OSError):
+            pass
 
     def barrier():
         if world > 1:

@@ -37,9 +37,13 @@
 #ifdef RDSIC_DEBUG
 #define RP_TS(cond, off) ((rg.ts && blockIdx.x == 0 && (cond) && lt < 60) ? rg.ts + lt * 16 + (off) : nullptr)
 #define RP_NOMATH (rg.dbg & 2)
+#define RP_NOSTORE (rg.dbg & 4)
+#define RP_NORES (rg.dbg & 8)
 #else
 #define RP_TS(cond, off) ((long long*)nullptr)
 #define RP_NOMATH 0
+#define RP_NOSTORE 0
+#define RP_NORES 0
 #endif
 
 namespace {
@@ -57,7 +61,7 @@ struct RuPairGeom {
   int kiters, kb, kc_last, k2_blocks, kc2_last, N2;
   int halo_w, halo_h, patch_bytes, patch_tx;  // (TW+KW-1) x (TH+KH-1) pixels x 128 B; patch_bytes rounded up to 1 KB
   long long* ts;  // RDSIC_DEBUG builds (RDSIC_RP_TS = device address of an int64 buffer): clock64 stamps of CTA 0, 16 per local tile
-  int dbg;        // RDSIC_DEBUG builds (RDSIC_RP_DBG): bit1 = no epilogue math / stores (results are garbage)
+  int dbg;        // RDSIC_DEBUG builds (RDSIC_RP_DBG): 2 = no epilogue math / stores, 4 = no stores, 8 = no residual loads (garbage results)
   int b_blk_bytes, w3_blk_bytes;  // one resident k-block of this CTA's half: (C/2) x 128 B, (N2/2) x 128 B
 };
 
@@ -340,7 +344,7 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
       for (int ci = 0; ci < RP_CHUNKS2; ++ci) {
         const int j = part + RP_PARTS * ci;
-        if (j < nchunks2 && row_ok) {
+        if (j < nchunks2 && row_ok && !RP_NORES) {
           const Pack8 r = ldg256(resp + j * 16);
 #pragma unroll
           for (int i = 0; i < 8; ++i) xs[ci][i] = r.w[i];
@@ -384,7 +388,7 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             o.w[2 * i] = *reinterpret_cast<uint32_t*>(&h0);
             o.w[2 * i + 1] = *reinterpret_cast<uint32_t*>(&h1);
           }
-          stg256(outp + j * 16, o);
+          if (!RP_NOSTORE || o.w[0] == 0x12345678u) stg256(outp + j * 16, o);
         }
       }
       tcgen05_fence_before();

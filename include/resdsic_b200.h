@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define RDSIC_ABI_VERSION 6
+#define RDSIC_ABI_VERSION 7
 
 typedef void* rdsic_stream_t; /* cudaStream_t */
 
@@ -110,6 +110,14 @@ typedef struct rdsic_conv_desc {
   const void* tail_weight;
   const float* tail_bias;
   int32_t tail_n;
+  /* Grouped form (bf16 tensor-core path only; groups <= 1: an ordinary convolution).  The Cout output channels are
+   * `groups` equal blocks; block g is an independent convolution with ITS OWN Cin input channels, which start at channel
+   * in.coff + g * in_group_stride of the input view (0: every group reads the same channels), and its own rows of the
+   * packed weight [Cout][KH*KW*Cin] / bias / res / out channels.  One launch then replaces `groups` launches of identical
+   * shape -- the cc_mean_i / cc_scale_i pairs and the mutually independent slices 5..9 of the slice loop
+   * (cnn.py:165-184): per-launch floor ~11 us against ~1 us of tensor time for the narrow layers. */
+  int32_t groups;
+  int32_t in_group_stride;
   int32_t pad_;
 } rdsic_conv_desc;
 

@@ -35,7 +35,7 @@ class ConvDesc(C.Structure):
         ("pixel_shuffle", C.c_int32), ("epilogue", C.c_int32), ("a_square", C.c_int32),
         ("out", View), ("res", View), ("aux", View), ("out2", View), ("out3", View),
         ("out2_square", C.c_int32), ("tail_mode", C.c_int32), ("tail_weight", C.c_void_p), ("tail_bias", C.c_void_p),
-        ("tail_n", C.c_int32), ("pad_", C.c_int32),
+        ("tail_n", C.c_int32), ("groups", C.c_int32), ("in_group_stride", C.c_int32), ("pad_", C.c_int32),
     ]
 
 
@@ -175,7 +175,7 @@ def lib():
                      ("rdsic_rate_workspace_doubles", [C.c_int])):
         getattr(L, fn).argtypes = args
         getattr(L, fn).restype = C.c_int
-    if L.rdsic_abi_version() != 6:
+    if L.rdsic_abi_version() != 7:
         raise RuntimeError("resdsic_b200: ABI version mismatch between the python host and the CUDA library")
     for what, T in enumerate((Op, ConvDesc, AttnDesc, EBDesc, GCDesc, CopyDesc, View, LNDesc, PatchDesc, MaskDesc)):
         if L.rdsic_sizeof(what) != C.sizeof(T):

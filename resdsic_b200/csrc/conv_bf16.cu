@@ -171,13 +171,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             int nt, tx, ty, b;
             tile_of(g, wk, q, nt, tx, ty, b);
             const int x0 = tx * g.TW * d.stride - d.pad_w, y0 = ty * g.TH * d.stride - d.pad_h, n0 = nt * g.BN;
+            const int ag = nt * g.a_group_stride;  // grouped conv: this n tile's input channels
             int cb = 0, r = 0, sx = 0, kcol = 0;
             for (int n = 0; n < kiters; ++n) {
               mbar_wait_u32(empty0 + 8u * (uint32_t)s, ph ^ 1u);
               const uint32_t a_dst = smem_base + (uint32_t)(s * stage_bytes), bar = full0 + 8u * (uint32_t)s;
               if (elect_one()) {
                 mbar_expect_tx_u32(bar, tx_bytes);
-                if (!(g.dbg_skip_load & 1)) tma_load_4d_u32(a_dst, &tmap_a, bar, cb * BK, x0 + sx, y0 + r, b);
+                if (!(g.dbg_skip_load & 1)) tma_load_4d_u32(a_dst, &tmap_a, bar, ag + cb * BK, x0 + sx, y0 + r, b);
                 if (m_mc) tma_load_2d_mc_u32(a_dst + a_bytes + b_half_off, &tmap_b, bar, kcol + cb * BK, n0 + n_half, 3);
                 else if (!(g.dbg_skip_load & 2)) tma_load_2d_u32(a_dst + a_bytes, &tmap_b, bar, kcol + cb * BK, n0);
               }
@@ -203,6 +204,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         int nt, tx, ty, b;
         tile_of(g, wk, q, nt, tx, ty, b);
         const int x0 = tx * g.TW * d.stride - d.pad_w, y0 = ty * g.TH * d.stride - d.pad_h, n0 = nt * g.BN;
+        const int ag = nt * g.a_group_stride;  // grouped conv: this n tile's input channels
         // this producer's first k-iteration of the tile (the first whose stage has its parity): stage, filter
         // tap and channel block
         const int f = pw ^ (s_base & 1);
@@ -221,12 +223,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint32_t lbar = lead_full0 + 8u * (uint32_t)s;
             if (elect_one()) {
               if (wk.crank == 0) mbar_expect_tx_u32(bar, 2u * tx_bytes);
-              tma_load_4d_2sm_u32(a_dst, &tmap_a, lbar, cb * BK, x0 + sx, y0 + r, b);
+              tma_load_4d_2sm_u32(a_dst, &tmap_a, lbar, ag + cb * BK, x0 + sx, y0 + r, b);
               tma_load_2d_2sm_u32(a_dst + a_bytes, &tmap_b, lbar, kcol + cb * BK, n0 + n_half);
             }
           } else if (elect_one()) {
             mbar_expect_tx_u32(bar, tx_bytes);
-            if (!(g.dbg_skip_load & 1)) tma_load_4d_u32(a_dst, &tmap_a, bar, cb * BK, x0 + sx, y0 + r, b);
+            if (!(g.dbg_skip_load & 1)) tma_load_4d_u32(a_dst, &tmap_a, bar, ag + cb * BK, x0 + sx, y0 + r, b);
             if (m_mc) tma_load_2d_mc_u32(a_dst + a_bytes + b_half_off, &tmap_b, bar, kcol + cb * BK, n0 + n_half, 3);
             else if (!(g.dbg_skip_load & 2)) tma_load_2d_u32(a_dst + a_bytes, &tmap_b, bar, kcol + cb * BK, n0);
           }
@@ -754,7 +756,7 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   g.dbg_skip_load = dbg_skip | (g_dbg_host ? 4 : 0);  // bit 2: the buffer is the timeout log, no time stamps
 #endif
 
-  if (tune_halo && !flat && d->stride == 1 && d->KH * d->KW > 1 && d->KH <= 3 && d->KW <= 3 && OH % 16 == 0 && OW % 8 == 0) {
+  if (tune_halo && d->groups <= 1 && !flat && d->stride == 1 && d->KH * d->KW > 1 && d->KH <= 3 && d->KW <= 3 && OH % 16 == 0 && OW % 8 == 0) {
     g.halo = 1;
     g.halo_base_off = tune_halo == 2;
     g.TH = 16;
@@ -763,7 +765,12 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
     g.halo_h = g.TH + d->KH - 1;
     g.a_halo_bytes = (BK * 2 * g.halo_w * g.halo_h + 1023) / 1024 * 1024;
   }
-  g.BN = pick_bn(d->Cout);
+  const int groups = d->groups > 1 ? d->groups : 1;
+  if (groups > 1) {  // grouped form: one n tile per group
+    RDSIC_CHECK_ARG((d->Cout / groups) % 16 == 0 && d->Cout / groups <= 256 && d->in_group_stride % 8 == 0 && !g.halo);
+    g.a_group_stride = d->in_group_stride;
+  }
+  g.BN = groups > 1 ? d->Cout / groups : pick_bn(d->Cout);
   g.kb_per_tap = ceil_div(d->Cin, BK);
   g.num_k_iters = d->KH * d->KW * g.kb_per_tap;
   g.a_stage_bytes = A_STAGE_BYTES;
@@ -810,7 +817,7 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   g.tiles_y = ceil_div(OH, g.TH);
   const int m_tiles = B * g.tiles_y * g.tiles_x;
   static const int tune_split = getenv("RDSIC_TC_SPLIT_N") ? atoi(getenv("RDSIC_TC_SPLIT_N")) : 1;
-  if (tune_split) {
+  if (tune_split && groups == 1) {
     // grids below one wave (latent-resolution layers): split N further so that more SMs get a tile.
     // The B tensor map zero-fills rows past ceil16(Cout), so BN need not divide Cout.
     const int c16 = (d->Cout + 15) / 16 * 16;
@@ -830,7 +837,7 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   // by default; PAIR mode is the one that relieves the port)
   static const int tune_mc = getenv("RDSIC_TC_MC") ? atoi(getenv("RDSIC_TC_MC")) : 0;
   g.pair = want_pair && m_tiles >= 2;
-  g.mc = !g.pair && tune_mc && !g.halo && m_tiles >= 2 && sms >= 2 && (tune_mc != 2 || g.total_tiles >= sms);
+  g.mc = !g.pair && tune_mc && groups == 1 && !g.halo && m_tiles >= 2 && sms >= 2 && (tune_mc != 2 || g.total_tiles >= sms);
   g.walk_total = (g.mc || g.pair) ? ceil_div(m_tiles, 2) * g.n_tiles : g.total_tiles;
   g.b_stage_bytes = (g.pair ? g.BN / 2 : g.BN) * BK * 2;  // PAIR: each CTA stages half of the B box
   const int stage_bytes = g.halo ? g.b_stage_bytes : g.a_stage_bytes + g.b_stage_bytes;
@@ -849,7 +856,7 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   // epilogue (>= 16 k-iterations).
   // The decision uses only layer properties (Cout, K) -- never the grid-dependent N split above -- so that the
   // fp32 summation order, hence every output bit, is independent of batch size and image size.
-  const int bn_layer = pick_bn(d->Cout);
+  const int bn_layer = groups > 1 ? g.BN : pick_bn(d->Cout);
   g.ksplit = tune_ksplit && !g.m2 && !g.pair && tune_m2 != 3 && !g.halo && g.num_k_iters >= 4 &&
              (4 * bn_layer <= 512 || (tune_ksplit != 3 && 2 * bn_layer <= 512 && g.num_k_iters >= 16));
   g.acc_stride = g.BN * (1 + (g.ksplit | g.m2));
@@ -862,7 +869,7 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   CUtensorMap ta, tb;
   {
     const cuuint64_t ld_b = (cuuint64_t)d->in.ld * 2;
-    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t dims[4] = {(cuuint64_t)(d->Cin + (groups - 1) * g.a_group_stride), (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {ld_b, ld_b * W, ld_b * W * H};
     cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(g.TW * d->stride), (cuuint32_t)(g.TH * d->stride), 1};
     if (g.halo) { box[1] = (cuuint32_t)g.halo_w; box[2] = (cuuint32_t)g.halo_h; }

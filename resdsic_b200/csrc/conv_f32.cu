@@ -214,7 +214,9 @@ int rdsic_conv_validate(const rdsic_conv_desc* d) {
   RDSIC_CHECK_ARG(d->epilogue >= RDSIC_EPI_NONE && d->epilogue <= RDSIC_EPI_LRP);
   if (epi_needs_res(d->epilogue)) RDSIC_CHECK_ARG(d->res.ptr != nullptr);
   if (d->epilogue == RDSIC_EPI_GATE) RDSIC_CHECK_ARG(d->aux.ptr != nullptr);
-  if (!d->in.nchw) RDSIC_CHECK_ARG(d->in.ld >= d->Cin + d->in.coff);
+  const int groups = d->groups > 1 ? d->groups : 1;
+  if (!d->in.nchw) RDSIC_CHECK_ARG(d->in.ld >= d->Cin + d->in.coff + (groups - 1) * d->in_group_stride);
+  if (groups > 1) RDSIC_CHECK_ARG(d->Cout % groups == 0 && d->in_group_stride >= 0 && !d->in.nchw && !d->tail_mode && !d->pixel_shuffle);
   return 0;
 }
 
@@ -222,6 +224,7 @@ int rdsic_conv_forward_f32(const rdsic_conv_desc* d, cudaStream_t stream) {
   int rc = rdsic_conv_validate(d);
   if (rc) return rc;
   RDSIC_CHECK_ARG(d->in.dtype == RDSIC_F32 && d->w_dtype == RDSIC_F32);
+  if (d->groups > 1) return RDSIC_E_UNSUPPORTED;  // grouped form: tensor-core path only
   const int M = d->B * d->OH * d->OW;
   dim3 grid(ceil_div(M, BM), ceil_div(d->Cout, BN));
   const bool fast = !d->in.nchw && d->Cin % BK == 0 && d->in.ld % 4 == 0 && d->in.coff % 4 == 0 &&

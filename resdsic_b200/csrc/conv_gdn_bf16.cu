@@ -661,7 +661,7 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   RDSIC_CHECK_ARG(d->tail_weight && d->tail_bias && d->tail_mode >= TAIL_GDN && d->tail_mode <= TAIL_RU);
   RDSIC_CHECK_ARG(d->epilogue == RDSIC_EPI_NONE && !d->aux.ptr && !d->out2.ptr && !d->out3.ptr);
   RDSIC_CHECK_ARG(C % 16 == 0 && N2 % 16 == 0 && N2 >= 32 && N2 <= MAXC && C + C / 2 + N2 <= 512);
-  RDSIC_CHECK_ARG(d->Cin % 16 == 0 && !d->pixel_shuffle && !d->a_square);
+  RDSIC_CHECK_ARG(d->Cin % 16 == 0 && !d->pixel_shuffle && !d->a_square && d->groups <= 1);
   if (d->tail_mode == TAIL_RU) {
     RDSIC_CHECK_ARG(d->res.ptr && d->res.dtype == RDSIC_BF16 && !d->res.nchw);
     if (d->res.ld % 16 || d->res.coff % 16 || ((uintptr_t)d->res.ptr % 32)) return RDSIC_E_ALIGN;

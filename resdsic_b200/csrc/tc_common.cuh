@@ -47,6 +47,9 @@ struct TcGeom {
   // Both CTAs' TMA loads complete on the LEADER's full barrier; the leader's commits are multicast to both CTAs'
   // empty / accumulator-full barriers; both CTAs' epilogue warps arrive on the leader's accumulator-empty barrier.
   int pair;
+  // grouped convolution (rdsic_conv_desc.groups): n tile nt is group nt (BN = Cout / groups); its A boxes start at
+  // channel nt * a_group_stride of the input view
+  int a_group_stride;
 };
 
 // walk of a persistent CTA over its tiles: q = first, first + step, ... < g.walk_total; tile_of() maps q to

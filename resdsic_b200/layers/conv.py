@@ -108,6 +108,48 @@ def _emit_partial(self, ctx, x, part, split, out=None, res=None, gelu=False, out
 Conv2d.emit_partial = _emit_partial
 
 
+def _packed_cols(conv, wdt, c0, c1):
+    """Packed weight of `conv` restricted to input channels [c0, c1) (cached per conv and range)."""
+    return conv._packed(("cols", wdt, c0, c1), (conv.weight, conv.bias), lambda: (
+        packing.pack_conv_weight(conv.weight[:, c0:c1], wdt), conv.bias.detach().float().contiguous()))
+
+
+def emit_grouped(ctx, owner, tag, convs, x, in_group_stride, cols=None, bias=True, **kw):
+    """ONE launch for several convolutions of identical shape (the grouped form of rdsic_conv_desc): `convs[g]`
+    convolves the channels `x.C` wide that start `g * in_group_stride` channels after `x`'s first (0: all share `x`)
+    and produces output channels [g * Cout, (g + 1) * Cout) of the result.  `cols = (c0, c1)` restricts every conv to
+    the input-channel range [c0, c1) of its weight (the split-K forms of the slice loop, cf. `Conv2d.emit_partial`);
+    `bias=False` leaves the bias to another part of the split.  Remaining keywords (epilogue, res, out, out2 ...) go
+    to `Program.conv`.  The concatenated weight / bias are cached on `owner` under `tag` and rebuilt when any member's
+    packed tensors change."""
+    c = convs[0]
+    wdt = ctx.wdt_for(x)
+    c0, c1 = cols if cols is not None else (0, c.in_channels)
+    assert x.C == c1 - c0 and all(m.weight.shape == c.weight.shape for m in convs), (x.C, c0, c1)
+    parts = [_packed_cols(m, wdt, c0, c1) for m in convs]
+    key = tuple((w.data_ptr(), b.data_ptr()) for w, b in parts)
+    cache = owner.__dict__.setdefault("_group_pack_cache", {})
+    hit = cache.get((tag, wdt, c0, c1))
+    if hit is None or hit[0] != key:
+        with torch.no_grad():
+            hit = (key, (torch.cat([w[:c.out_channels] for w, _ in parts], 0).contiguous(),
+                         torch.cat([b for _, b in parts], 0).contiguous()), parts)  # (parts kept alive: the key holds their addresses)
+        cache[(tag, wdt, c0, c1)] = hit
+    w, b = hit[1]
+    G, k, s_, p = len(convs), c.kernel_size, c.stride, c.padding
+    OH, OW = (x.H + 2 * p - k) // s_ + 1, (x.W + 2 * p - k) // s_ + 1
+    out = kw.pop("out", None)
+    out_dtype = kw.pop("out_dtype", None)
+    if out is None:
+        out = ctx.buf(x.B, OH, OW, G * c.out_channels, out_dtype)
+    if kw.pop("gelu", False):
+        kw["epilogue"] = _lib.EPI_RES_GELU if kw.get("res") is not None else _lib.EPI_GELU
+    elif "epilogue" not in kw and kw.get("res") is not None:
+        kw["epilogue"] = _lib.EPI_ADD_RES
+    return ctx.prog.conv(x, w, b if bias else None, G * c.out_channels, k, k, s_, p, p, out, OH=OH, OW=OW,
+                         groups=G, in_group_stride=in_group_stride, **kw)
+
+
 class ConvTranspose2d(B200Module):
     """nn.ConvTranspose2d(in, out, 5, stride=2, padding=2, output_padding=1): four
     sub-pixel phase GEMMs (3x3, 3x2, 2x3, 2x2 taps), output exactly 2x the input."""

@@ -16,6 +16,8 @@ every cc_mean / cc_scale / lrp input is just "the first Cin channels".
 """
 import math
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -125,6 +127,10 @@ class WACNN(CompressionModel):
         # 2 -> 1205, 4 -> 869 images/s -- persistent one-CTA-per-SM kernels of two graphs serialise instead of
         # interleaving -- so the default is 1.  Outputs are bit-identical for any setting.
         self.micro_batches = 1
+        # bf16 eval forward: the slice loop's context transforms as GROUPED launches (cc_mean_i + cc_scale_i in one, the
+        # five mutually independent slices >= max_support_slices in one; `_emit_slice_loop_grouped`).  RDSIC_GROUPED=0
+        # restores one launch per convolution.
+        self.grouped_slice_loop = os.environ.get("RDSIC_GROUPED", "1") != "0"
         # Training mode (`.train()`): forward VALUES of the reference's training forward -- likelihoods at
         # y / z + U(-1/2,1/2) noise (entropy_models.py:131-137), y_hat / z_hat by ste_round as in eval mode
         # (cnn.py:152-154,177).  The noise is drawn on the device per call; `noise_override` =
@@ -321,9 +327,13 @@ class WACNN(CompressionModel):
         p.symbols = out_tensor("symbols", B, M, h, w, dtype=torch.int32) if with_symbols else None
         p.indexes = out_tensor("indexes", B, M, h, w, dtype=torch.int32) if with_symbols else None
         fam = {"cc_mean": self.cc_mean_transforms, "cc_scale": self.cc_scale_transforms, "lrp": self.lrp_transforms}
-        pre = self._emit_slice_precompute(ctx, fam, means, scales)
-        y_hat = self._emit_slice_loop(ctx, fam, pre, self.gaussian_conditional, y, means, scales, p.lik_y, p.symbols,
-                                      p.indexes, noise=p.noise_y)
+        if bf16 and p.noise_y is None and self.grouped_slice_loop:
+            y_hat = self._emit_slice_loop_grouped(ctx, fam, self.gaussian_conditional, y, means, scales, p.lik_y, p.symbols,
+                                                  p.indexes)
+        else:
+            pre = self._emit_slice_precompute(ctx, fam, means, scales)
+            y_hat = self._emit_slice_loop(ctx, fam, pre, self.gaussian_conditional, y, means, scales, p.lik_y, p.symbols,
+                                          p.indexes, noise=p.noise_y)
         # ---- g_s
         p.x_hat = out_tensor("x_hat", B, 3, H, W)
         y_hat_act = ctx.prog.copy(y_hat, ctx.buf(B, h, w, M)) if bf16 else y_hat
@@ -460,6 +470,119 @@ class WACNN(CompressionModel):
                 prog.join(2 + 2 * n)
         return y_hat
 
+    def _emit_slice_loop_grouped(self, ctx, fam, gc, y, means, scales, lik_y, symbols, indexes):
+        """The slice loop (cnn.py:161-187) of the bf16 eval forward with grouped launches (rdsic_conv_desc.groups):
+          * slices 1 .. S-1 (serial chain): cc_mean_i and cc_scale_i -- same shapes, same support input -- are ONE
+            launch per layer (2 groups); their LRP stacks stay single;
+          * slices S .. 9 depend only on slices 0 .. S-1, not on each other: all ten cc stacks are ONE launch per
+            layer (10 groups, ordered mean_S..mean_9, scale_S..scale_9 so that mu / scale come out as two contiguous
+            160-channel blocks), ONE GaussianConditional launch covers their 160 channels, and the five LRP stacks are
+            ONE launch per layer (5 groups).  The LRP's first conv is split three ways over its input
+            cat(latent means, support, own slice): latent part pre-computed, support part shared by the five groups,
+            own-slice part reading the bf16 copy of y_hat the GaussianConditional kernel writes;
+          * the latent-only parts of the tail (inputs shared) are three wide convolutions instead of fifteen.
+        Per output element the arithmetic of the cc stacks is that of the ungrouped path (same split, same K order),
+        so symbols and CDF indexes equal the decoder-side loop's bit for bit; the three-way LRP split is mirrored by
+        `_build_decoder` for the same reason.  ~95 fewer launches per forward."""
+        from ..layers.conv import emit_grouped
+        prog = ctx.prog
+        f32 = torch.float32
+        B, h, w = y.B, y.H, y.W
+        M, sc_, S, NS = self.M, self.slice_channels, self.max_support_slices, self.num_slices
+        T = NS - S                                  # tail slices
+        lat_m, lat_s = means.channels(0, M), scales.channels(0, M)
+        convs = {k: [[m for m in seq if hasattr(m, "weight")] for seq in fam[k]] for k in fam}
+        C0 = convs["cc_mean"][0][0].out_channels    # 224
+        y_hat = ctx.buf(B, h, w, M, f32)            # fp32 master copy of y_hat (LRP residual + g_s input)
+
+        # ---------------- off the serial chain: everything that only needs the latent means / scales
+        lanes = list(range(2, _lib.MAX_LANES))
+        jobs, ev, pre = [], {}, {}
+        pre_cc = {i: ctx.buf(B, h, w, 2 * C0, f32) for i in range(1, S)}       # [mean_i | scale_i] latent partial sums
+        pre_tail_cc = ctx.buf(B, h, w, 2 * T * C0, f32)                         # [mean_S.. | scale_S..]
+        pre_tail_lrp = ctx.buf(B, h, w, T * C0, f32)
+        jobs.append(("mu0", lambda: pre.__setitem__("mu0", self._stack(ctx, fam["cc_mean"][0], lat_m))))
+        jobs.append(("sc0", lambda: pre.__setitem__("sc0", self._stack(ctx, fam["cc_scale"][0], lat_s))))
+        for i in range(S):
+            if i:
+                jobs.append((("cc", i), lambda i=i: (
+                    convs["cc_mean"][i][0].emit_partial(ctx, lat_m, 0, M, out=pre_cc[i].channels(0, C0)),
+                    convs["cc_scale"][i][0].emit_partial(ctx, lat_s, 0, M, out=pre_cc[i].channels(C0, C0)))))
+            jobs.append((("lrp", i), lambda i=i: pre.__setitem__(("lrp", i), convs["lrp"][i][0].emit_partial(ctx, lat_m, 0, M))))
+        jobs.append(("tail_cc_m", lambda: emit_grouped(ctx, self, "pre_tail_m", [convs["cc_mean"][i][0] for i in range(S, NS)], lat_m, 0,
+                                                       cols=(0, M), bias=False, out=pre_tail_cc.channels(0, T * C0))))
+        jobs.append(("tail_cc_s", lambda: emit_grouped(ctx, self, "pre_tail_s", [convs["cc_scale"][i][0] for i in range(S, NS)], lat_s, 0,
+                                                       cols=(0, M), bias=False, out=pre_tail_cc.channels(T * C0, T * C0))))
+        jobs.append(("tail_lrp", lambda: emit_grouped(ctx, self, "pre_tail_l", [convs["lrp"][i][0] for i in range(S, NS)], lat_m, 0,
+                                                      cols=(0, M), bias=False, out=pre_tail_lrp)))
+        forked = set()
+        for n, (key, fn) in enumerate(jobs):
+            lane = lanes[n % len(lanes)]
+            if lane not in forked:
+                prog.fork(lane)
+                forked.add(lane)
+            with prog.side(lane):
+                fn()
+                ev[key] = prog.record()
+
+        def rest_of_stack(stack_convs, t, tag, stride_of, final=None):
+            """Layers 1 .. 4 of G stacks at once: layer l's input channels of group g start g * stride_of(l) after t's."""
+            G = len(stack_convs)
+            for l in range(1, 5):
+                layer = [cs[l] for cs in stack_convs]
+                x = t.channels(0, layer[0].in_channels)
+                kw = dict(gelu=True) if l < 4 else (final if final is not None else dict(out_dtype=f32))
+                t = emit_grouped(ctx, self, (tag, l), layer, x, stride_of(l), **kw)
+            return t
+
+        # ---------------- slices 0 .. S-1: the serial chain
+        for i in range(S):
+            k = i
+            if i == 0:
+                prog.wait(ev["mu0"])
+                prog.wait(ev["sc0"])
+                mu, sc = pre["mu0"], pre["sc0"]
+            else:
+                prog.wait(ev[("cc", i)])
+                pair = [convs["cc_mean"][i], convs["cc_scale"][i]]
+                t = emit_grouped(ctx, self, ("cc0", i), [cs[0] for cs in pair], means.channels(M, sc_ * k), 0,
+                                 cols=(M, M + sc_ * k), res=pre_cc[i], gelu=True)
+                ms = rest_of_stack(pair, t, ("cc", i), lambda l, pair=pair: pair[0][l].in_channels)
+                mu, sc = ms.channels(0, sc_), ms.channels(sc_, sc_)
+            yh_i = y_hat.channels(sc_ * i, sc_)
+            slot = means.channels(M + sc_ * i, sc_)
+            gc.emit(ctx, y.channels(sc_ * i, sc_), sc, mu, lik_y, sc_ * i, M, y_hat_dsts=[yh_i, slot], symbols=symbols, indexes=indexes)
+            prog.wait(ev[("lrp", i)])
+            seq = convs["lrp"][i]
+            t = seq[0].emit_partial(ctx, means.channels(M, sc_ * (k + 1)), 1, M, res=pre[("lrp", i)], gelu=True)
+            for c in seq[1:4]:
+                t = c.emit(ctx, t, gelu=True)
+            seq[4].emit(ctx, t, epilogue=_lib.EPI_LRP, res=yh_i, out=yh_i, out2=slot)  # refined slice: support of later slices
+
+        # ---------------- slices S .. 9: one grouped launch per layer
+        support = means.channels(M, sc_ * S)
+        for key in ("tail_cc_m", "tail_cc_s", "tail_lrp"):
+            prog.wait(ev[key])
+        tail_cc = [convs["cc_mean"][i] for i in range(S, NS)] + [convs["cc_scale"][i] for i in range(S, NS)]
+        t = emit_grouped(ctx, self, "tail_cc0", [cs[0] for cs in tail_cc], support, 0, cols=(M, M + sc_ * S), res=pre_tail_cc,
+                         gelu=True)
+        ms = rest_of_stack(tail_cc, t, "tail_cc", lambda l: tail_cc[0][l].in_channels)
+        mu, sc = ms.channels(0, sc_ * T), ms.channels(sc_ * T, sc_ * T)
+        yh_tail = y_hat.channels(sc_ * S, sc_ * T)
+        yh_tail_act = ctx.buf(B, h, w, sc_ * T)     # bf16 copy: A operand of the LRP's own-slice part
+        gc.emit(ctx, y.channels(sc_ * S, sc_ * T), sc, mu, lik_y, sc_ * S, M, y_hat_dsts=[yh_tail, yh_tail_act], symbols=symbols,
+                indexes=indexes)
+        tail_lrp = [convs["lrp"][i] for i in range(S, NS)]
+        part = emit_grouped(ctx, self, "tail_lrp0a", [cs[0] for cs in tail_lrp], support, 0, cols=(M, M + sc_ * S), bias=False,
+                            res=pre_tail_lrp, out_dtype=f32)
+        t = emit_grouped(ctx, self, "tail_lrp0b", [cs[0] for cs in tail_lrp], yh_tail_act.channels(0, sc_), sc_,
+                         cols=(M + sc_ * S, M + sc_ * (S + 1)), res=part, gelu=True)
+        rest_of_stack(tail_lrp, t, "tail_lrp", lambda l: tail_lrp[0][l].in_channels,
+                      final=dict(epilogue=_lib.EPI_LRP, res=yh_tail, out=yh_tail))
+        for lane in forked:
+            prog.join(lane)
+        return y_hat
+
     def _build_decoder(self, B, hz, wz, device, build_only=False):
         """Programs of the decoder-side loop: `hyper` (h_mean_s || h_scale_s + everything that only needs the
         latent means / scales), per slice `params[i]` (cc_mean || cc_scale, CDF indexes) and `update[i]`
@@ -539,7 +662,20 @@ class WACNN(CompressionModel):
             slot = means.channels(M + sc_ * k, sc_)  # slices >= S: slot S is scratch for the current slice
             extra = dict(out2=slot, out3=scales.channels(M + sc_ * i, sc_)) if i < S else {}
             self.gaussian_conditional.emit(ctx, mu, sc, mu, p.lik, sc_ * i, M, y_hat_dsts=[yh_i, slot], sym_in=p.symbols)
-            stack_split("lrp", i, means, sc_ * (k + 1), final=dict(epilogue=_lib.EPI_LRP, res=yh_i, out=yh_i, **extra))
+            final = dict(epilogue=_lib.EPI_LRP, res=yh_i, out=yh_i, **extra)
+            if bf16 and self.grouped_slice_loop and i >= S:
+                # the forward's grouped tail (`_emit_slice_loop_grouped`) splits this LRP's first conv three ways (latent |
+                # support | own slice); the same split here keeps x_hat bit-identical between the two passes
+                from ..layers.conv import emit_grouped
+                seq = fam["lrp"][i]
+                first = [m for m in seq if hasattr(m, "weight")][0]
+                part = emit_grouped(ctx, self, ("dec_lrp0a", i), [first], means.channels(M, sc_ * S), 0, cols=(M, M + sc_ * S),
+                                    bias=False, res=pre[("lrp", i)], out_dtype=f32)
+                t = emit_grouped(ctx, self, ("dec_lrp0b", i), [first], slot, 0, cols=(M + sc_ * S, M + sc_ * (S + 1)), res=part,
+                                 gelu=True)
+                self._stack(ctx, seq, t, final=final, skip_first=True)
+            else:
+                stack_split("lrp", i, means, sc_ * (k + 1), final=final)
             p.update.append(prog)
 
         # ---- synthesis + clamp (cnn.py:337-340)

@@ -146,7 +146,11 @@ class Program:
     # ------------------------------------------------------------- builders
     def conv(self, x: TV, weight, bias, Cout, KH, KW, stride, pad_h, pad_w, out: TV, epilogue=_lib.EPI_NONE,
              res: TV = None, aux: TV = None, out2: TV = None, out3: TV = None, a_square=False, pixel_shuffle=0,
-             OH=None, OW=None, osy=1, osx=1, ooy=0, oox=0, Cin=None, out2_square=False, gdn=None, tail=None):
+             OH=None, OW=None, osy=1, osx=1, ooy=0, oox=0, Cin=None, out2_square=False, gdn=None, tail=None,
+             groups=1, in_group_stride=0):
+        """`groups` > 1: grouped form (include/resdsic_b200.h): `x` views the FIRST group's Cin channels, group g's
+        start `g * in_group_stride` channels further into the same buffer (0: shared input); `weight` / `bias` / `res` /
+        `out` carry the groups' Cout / groups channels back to back."""
         d = ConvDesc()
         d.in_ = x.view()
         d.B, d.H, d.W, d.Cin = x.B, x.H, x.W, (x.C if Cin is None else Cin)
@@ -160,6 +164,7 @@ class Program:
         d.pixel_shuffle, d.epilogue, d.a_square = pixel_shuffle, epilogue, int(a_square)
         d.out = out.view()
         d.out2_square = int(out2_square)
+        d.groups, d.in_group_stride = (groups, in_group_stride) if groups > 1 else (0, 0)
         if gdn is not None:  # (gamma' packed bf16, beta' fp32, inverse)
             d.tail_weight, d.tail_bias, d.tail_mode, d.tail_n = gdn[0].data_ptr(), gdn[1].data_ptr(), 2 if gdn[2] else 1, Cout
             self.keep += [gdn[0], gdn[1]]

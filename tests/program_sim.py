@@ -53,7 +53,10 @@ class Sim:
 
     # ------------------------------------------------------------------ ops
     def conv(self, d):
-        x = self._nhwc(d.in_, d.B, d.H, d.W, d.Cin).float()
+        G = d.groups if d.groups > 1 else 1
+        # grouped form: group g reads Cin channels starting g * in_group_stride channels into the view
+        x = torch.cat([self._nhwc(d.in_, d.B, d.H, d.W, d.in_group_stride * g + d.Cin)[..., d.in_group_stride * g:].float()
+                       for g in range(G)], dim=-1)
         if d.a_square:
             x = x * x
         wflat = self._flat(d.weight)[: d.Cout * d.KH * d.KW * d.Cin].float()  # (rows may be padded past Cout)
@@ -62,7 +65,7 @@ class Sim:
         need_h = (d.OH - 1) * d.stride + d.KH - d.pad_h
         need_w = (d.OW - 1) * d.stride + d.KW - d.pad_w
         xp = F.pad(x.permute(0, 3, 1, 2), (d.pad_w, max(0, need_w - d.W), d.pad_h, max(0, need_h - d.H)))
-        v = F.conv2d(xp, w, bias, stride=d.stride)[:, :, : d.OH, : d.OW]  # [B,Cout,OH,OW]
+        v = F.conv2d(xp, w, bias, stride=d.stride, groups=G)[:, :, : d.OH, : d.OW]  # [B,Cout,OH,OW]
         assert v.shape[2:] == (d.OH, d.OW), (v.shape, d.OH, d.OW)
         if d.pixel_shuffle:
             v = F.pixel_shuffle(v, 2)

@@ -32,7 +32,7 @@ def gold():
 def test_library_loaded_is_in_tree():
     L = resdsic_b200._lib.lib()
     assert os.path.realpath(resdsic_b200._lib.LIB_PATH).startswith(os.path.realpath(os.path.dirname(resdsic_b200.__file__)))
-    assert L.rdsic_abi_version() == 6
+    assert L.rdsic_abi_version() == 7
 
 
 def test_gaussian_conditional_bit_exact_integers(model, gold, scale_table):
@@ -168,6 +168,40 @@ def test_fused_residual_unit_vs_torch(N, B, hw):
     np.testing.assert_allclose(out.numpy(), ref.numpy(), rtol=8e-3, atol=8e-3)
 
 
+@pytest.mark.parametrize("G,cin,cout,shared,B,hw", [(2, 224, 176, False, 2, (16, 24)), (10, 160, 224, True, 1, (16, 24)),
+                                                    (10, 64, 32, False, 3, (32, 48)), (5, 32, 224, False, 1, (8, 12)),
+                                                    (2, 176, 128, False, 24, (32, 48))])
+def test_grouped_conv_vs_torch(G, cin, cout, shared, B, hw):
+    """Grouped form of the implicit GEMM (rdsic_conv_desc.groups: one launch for G convolutions of identical shape --
+    the slice loop's cc_mean / cc_scale pairs and its five independent tail slices) against torch's grouped conv on
+    the same bf16-rounded operands; `shared`: every group reads the same input channels (in_group_stride = 0).
+    Covers partial last K blocks (Cin = 176, 160, 224: the next group's channels sit in the unused half of the TMA box),
+    one and many tiles per CTA, PAIR / M2 / single-issuer tile modes."""
+    from resdsic_b200.layers import Conv2d, Ctx
+    from resdsic_b200.layers.conv import emit_grouped
+    import torch.nn.functional as F
+    convs = [Conv2d(cin, cout, 3, 1) for _ in range(G)]
+    with torch.no_grad():
+        for g, c in enumerate(convs):
+            c.weight.copy_(weights.hash_symmetric(f"grp.w{G}{cin}{cout}{g}", c.weight.shape, (3.0 / (cin * 9)) ** 0.5))
+            c.bias.copy_(weights.hash_symmetric(f"grp.b{G}{cin}{cout}{g}", c.bias.shape, 0.1))
+        convs = [c.to(DEV).set_precision("bf16") for c in convs]
+    Ct = cin if shared else G * cin
+    x = weights.hash_symmetric(f"grp.x{G}{cin}{hw}", (B, Ct, *hw), 1.0)
+    xin = _bf(x) if not shared else _bf(x).repeat(1, G, 1, 1)
+    wcat = torch.cat([_bf(c.weight.detach().cpu()) for c in convs], 0)
+    bcat = torch.cat([c.bias.detach().cpu() for c in convs], 0)
+    ref = F.gelu(F.conv2d(xin, wcat, bcat, padding=1, groups=G))
+    ctx = Ctx(torch.device(DEV), "bf16")
+    xt = ctx.from_nchw(x.to(DEV), torch.bfloat16)
+    holder = convs[0]
+    out = emit_grouped(ctx, holder, "t", convs, xt.channels(0, cin), 0 if shared else cin, gelu=True, out_dtype=torch.float32)
+    res = ctx.to_nchw(out)
+    ctx.prog.run()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(res.cpu().numpy(), ref.numpy(), rtol=8e-3, atol=8e-3)
+
+
 @pytest.mark.parametrize("cin,cout", [(192, 192), (320, 192), (192, 3)])
 def test_tcgen05_deconv_vs_oracle(cin, cout):
     from resdsic_b200.layers import ConvTranspose2d
@@ -292,6 +326,6 @@ def test_kernel_mode_switches_in_subprocess(env):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_ops.py", "-m", "gpu", "-q", "-x", "-k",
-                        "tcgen05 or layers_bf16 or subpel or fused_residual"], cwd=root, env=dict(os.environ, **env), capture_output=True,
+                        "tcgen05 or layers_bf16 or subpel or fused_residual or grouped"], cwd=root, env=dict(os.environ, **env), capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -29,7 +29,10 @@
 // Barriers: both CTAs' patches complete on the LEADER's a_full[slot]; the leader's commits are multicast to both CTAs'
 // a_empty[slot] / acc1_full[b] / acc2_full; both CTAs' epilogue warps arrive on the leader's p_full[b] (P[b] staged and
 // acc1[b] drained: releases the tail GEMM of lt and the main loop of lt+2) and acc2_empty (count 24 each).
-// Patch slots: 4, slot = (2 * local tile + channel block) & 3, filled and consumed in one order by one producer / issuer.
+// Patch slots: 2 (one per channel block: the main loop runs ~10k cycles ahead of the epilogue, it does not need more),
+// filled and consumed in one order by one producer / issuer.  The shared memory they free holds the RESIDUAL tile
+// (128 rows x 192 channels, three swizzled 16 KB blocks loaded by a fourth TMA-issuing warp): per-lane LDG.256 of the
+// residual -- 32 sectors per instruction, issued in bursts between compute phases -- cost 39 of 230 us per launch.
 // (An earlier form with a ring shared by two issuers let one wait on a barrier the other was a lap behind on: the parity
 // wait aliases and a stage is overwritten unconsumed -- found the hard way.)
 #include "tc_common.cuh"
@@ -49,13 +52,16 @@
 namespace {
 
 constexpr int RP_EPI_WARPS = 12;
-constexpr int RP_TAIL_WARP = 2 + RP_EPI_WARPS;          // issues the tail GEMMs (leader CTA); warp 15 is idle
+constexpr int RP_TAIL_WARP = 2 + RP_EPI_WARPS;          // issues the tail GEMMs (leader CTA)
 constexpr int RP_THREADS = 128 + 32 * RP_EPI_WARPS;
 constexpr int RP_PARTS = RP_EPI_WARPS / 4;
 constexpr int RP_MAXC = 96;                              // 5 C <= 512 TMEM columns
 constexpr int RP_CHUNKS1 = RP_MAXC / 16 / RP_PARTS;      // phase-1 chunks per warp (2)
 constexpr int RP_CHUNKS2 = 2 * RP_MAXC / 16 / RP_PARTS;  // phase-2 chunks per warp (4)
-constexpr int RP_SLOTS = 4;
+constexpr int RP_SLOTS = 2;       // one patch slot per channel block (the main loop runs far ahead of the epilogue anyway)
+constexpr int RP_SLOT_SHIFT = 1;  // log2(RP_SLOTS)
+constexpr int RP_RES_WARP = RP_TAIL_WARP + 1;  // TMA producer of the residual tiles
+constexpr int RP_RES_BLOCK = BM * BK * 2;      // one 64-channel block of a residual tile: 128 rows x 128 B
 
 struct RuPairGeom {
   int kiters, kb, kc_last, k2_blocks, kc2_last, N2;
@@ -90,22 +96,26 @@ __device__ __forceinline__ float4 rp_lds128(uint32_t addr) {
 
 __global__ void __launch_bounds__(RP_THREADS, 1)
 ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const __grid_constant__ CUtensorMap tmap_g, const rdsic_conv_desc d, const TcGeom g, const RuPairGeom rg) {
+                  const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_r, const rdsic_conv_desc d,
+                  const TcGeom g, const RuPairGeom rg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   pdl_trigger();
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // Every byte of the 227 KB is spoken for, so there is no slack for re-aligning the window: the dynamic window of a
+  // kernel without static shared memory starts 1 KB into the SM's shared memory, i.e. 1024-aligned (checked below).
+  uint8_t* smem = smem_raw;
   uint8_t* b_res = smem + (size_t)RP_SLOTS * rg.patch_bytes;         // [kiters][C/2 rows x 128 B]
   uint8_t* w3_res = b_res + (size_t)rg.kiters * rg.b_blk_bytes;      // [k2_blocks][N2/2 rows x 128 B]
-  uint64_t* a_full = (uint64_t*)(w3_res + (size_t)rg.k2_blocks * rg.w3_blk_bytes);  // [RP_SLOTS] LEADER's copy
+  uint8_t* res_s = w3_res + (size_t)rg.k2_blocks * rg.w3_blk_bytes;  // residual tile: N2/64 blocks of [128 rows x 128 B]
+  uint64_t* a_full = (uint64_t*)(res_s + (size_t)(rg.N2 / BK) * RP_RES_BLOCK);      // [RP_SLOTS] LEADER's copy
   uint64_t* a_empty = a_full + RP_SLOTS;         // [RP_SLOTS] local, multicast commit of the issuer
   uint64_t* acc1_full = a_empty + RP_SLOTS;      // [2] local, multicast commit of the issuer
   uint64_t* p_full = acc1_full + 2;              // [2] LEADER's copy: P[b] staged and acc1[b] drained by both CTAs
   uint64_t* acc2_full = p_full + 2;              // local, multicast commit of the tail issuer
   uint64_t* acc2_empty = acc2_full + 1;          // LEADER's copy: acc2 drained by both CTAs
   uint64_t* w_full = acc2_empty + 1;             // LEADER's copy: resident weights of both CTAs have landed
-  uint32_t* tmem_slot = (uint32_t*)(w_full + 1);
-  float* bias1_s = (float*)(((uintptr_t)(tmem_slot + 1) + 15) & ~(uintptr_t)15);  // [C]
-  float* bias2_s = bias1_s + RP_MAXC;                                             // [N2]
+  uint64_t* r_full = w_full + 1;                 // local: this CTA's residual tile has landed
+  uint64_t* r_empty = r_full + 1;                // local: ... and has been read by the twelve epilogue warps
+  uint32_t* tmem_slot = (uint32_t*)(r_empty + 1);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int C = d.Cout;
@@ -125,6 +135,9 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     mbar_init(acc2_full, 1);
     mbar_init(acc2_empty, 2 * RP_EPI_WARPS);
     mbar_init(w_full, 1);
+    mbar_init(r_full, 1);
+    mbar_init(r_empty, RP_EPI_WARPS);
+    if (smem_u32(smem_raw) & 1023u) __trap();  // (see the carve-up above)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // the same warp of both CTAs: one allocation for the pair
@@ -132,8 +145,6 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
   }
   pdl_wait();  // PDL: barrier init / TMEM allocation above overlap the previous kernel's tail; global memory from here on
-  for (int i = threadIdx.x; i < C; i += blockDim.x) bias1_s[i] = d.bias ? d.bias[i] : 0.f;
-  for (int i = threadIdx.x; i < rg.N2; i += blockDim.x) bias2_s[i] = d.tail_bias[i];
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -167,14 +178,14 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
       __syncwarp();
     }
-    // patches in consumption order: u = 2 * local tile + channel block, slot u & 3, phase (u >> 2) & 1
+    // patches in consumption order: u = 2 * local tile + channel block, slot u % RP_SLOTS, phase (u / RP_SLOTS) & 1
     uint32_t u = 0;
     for (int q = wk.first; q < total; q += step) {
       int nt, tx, ty, b;
       tile_of(g, wk, q, nt, tx, ty, b);
       const int x0 = tx * g.TW - d.pad_w, y0 = ty * g.TH - d.pad_h;
       for (int cb = 0; cb < 2; ++cb, ++u) {
-        const uint32_t slot = u & (RP_SLOTS - 1), ph = (u >> 2) & 1u;
+        const uint32_t slot = u & (RP_SLOTS - 1), ph = (u >> RP_SLOT_SHIFT) & 1u;
         mbar_wait_u32(a_empty0 + 8u * slot, ph ^ 1u);
         if (elect_one()) {
           if (leader) mbar_expect_tx_u32(a_full0 + 8u * slot, 2u * (uint32_t)rg.patch_tx);
@@ -185,7 +196,7 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     // drain: no multicast commit of the leader may arrive on this CTA's barriers after it has exited -- wait for the
     // release of the LAST fill of every slot
-    for (int n = 0; n < RP_SLOTS; ++n, ++u) mbar_wait_u32(a_empty0 + 8u * (u & (RP_SLOTS - 1)), ((u >> 2) & 1u) ^ 1u);
+    for (int n = 0; n < RP_SLOTS; ++n, ++u) mbar_wait_u32(a_empty0 + 8u * (u & (RP_SLOTS - 1)), ((u >> RP_SLOT_SHIFT) & 1u) ^ 1u);
     __syncwarp();
   } else if (warp == 1) {
     // ================= MMA issuer: leader CTA only =================
@@ -212,7 +223,7 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (tsp) tsp[1] = clock64();
         const uint32_t acc = tbase + b * (uint32_t)C;
         for (uint32_t cb = 0; cb < 2; ++cb) {
-          const uint32_t u = 2u * lt + cb, slot = u & (RP_SLOTS - 1), ph = (u >> 2) & 1u;
+          const uint32_t u = 2u * lt + cb, slot = u & (RP_SLOTS - 1), ph = (u >> RP_SLOT_SHIFT) & 1u;
           mbar_wait_u32(a_full0 + 8u * slot, ph);  // both CTAs' patches of this channel block have landed
           tcgen05_fence_after();
           const uint64_t da0 = dconst_halo + (uint64_t)(patch_u0 + slot * patch_u);
@@ -275,6 +286,29 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
     }
     __syncwarp();
+  } else if (warp == RP_RES_WARP) {
+    // ================= residual producer (both CTAs): the tile's x rows as N2/64 swizzled [128 rows x 128 B] blocks
+    // (the per-lane 32-byte LDG.256 of the first versions -- 32 sectors per instruction, issued in bursts between
+    // compute phases and overlapped with nothing -- cost 39 of 230 us per launch.  Sending the OUTPUT through the same
+    // buffer and a TMA store was also built: correct, but 8 us slower than per-lane STG.256 -- store, wait for its
+    // shared-memory reads, then the next tile's load serialise on the one buffer there is room for.)
+    const uint32_t res0 = __shfl_sync(0xffffffffu, smem_u32(res_s), 0);
+    const uint32_t rf = __shfl_sync(0xffffffffu, smem_u32(r_full), 0), re = __shfl_sync(0xffffffffu, smem_u32(r_empty), 0);
+    int total = g.walk_total, step = wk.step, nblk = rg.N2 / BK;
+    asm volatile("" : "+r"(total), "+r"(step), "+r"(nblk));
+    uint32_t lt = 0;
+    for (int q = wk.first; q < total; q += step, ++lt) {
+      int nt, tx, ty, b;
+      tile_of(g, wk, q, nt, tx, ty, b);
+      mbar_wait_u32(re, (lt & 1u) ^ 1u);  // phase 2 of the previous tile has read the buffer
+      if (elect_one()) {
+        mbar_expect_tx_u32(rf, (uint32_t)(nblk * RP_RES_BLOCK));
+        for (int k = 0; k < nblk; ++k)
+          tma_load_4d_u32(res0 + (uint32_t)(k * RP_RES_BLOCK), &tmap_r, rf, k * BK, tx * g.TW, ty * g.TH, b);
+      }
+      __syncwarp();
+    }
+    __syncwarp();
   } else if (warp < RP_TAIL_WARP) {
     // ================= epilogue warps (both CTAs) =================
     const int q = warp % 4, part = (warp - 2) / 4;
@@ -284,7 +318,10 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t lead_p_full0 = mapa_u32(smem_u32(p_full), 0u), lead_acc2_empty = mapa_u32(smem_u32(acc2_empty), 0u);
     const uint32_t acc1_full0 = smem_u32(acc1_full), acc2_full_a = smem_u32(acc2_full);
-    const uint32_t bias1_a = smem_u32(bias1_s), bias2_a = smem_u32(bias2_s);
+    const float4* bias1_g = reinterpret_cast<const float4*>(d.bias);        // 384 + 768 B, L1-resident after the first tile
+    const float4* bias2_g = reinterpret_cast<const float4*>(d.tail_bias);
+    const uint32_t res_row = smem_u32(res_s) + (uint32_t)(ml * 128), r_full_a = smem_u32(r_full), r_empty_a = smem_u32(r_empty);
+    const uint32_t rsw = (uint32_t)(ml & 7);  // 128B swizzle: 16-byte chunk index ^ (row & 7)
     const int total = g.walk_total, step = wk.step;
 
     // ---- phase 1 of local tile lt: t = gelu(acc1 + b2) -> bf16 -> TMEM operand P[lt & 1]
@@ -309,7 +346,7 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         uint32_t st[8];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 f = rp_lds128(bias1_a + (uint32_t)((j * 16 + 4 * i) * 4));
+          const float4 f = __ldg(bias1_g + j * 4 + i);
           const float v0 = __uint_as_float(ua[ci][4 * i]) + f.x, v1 = __uint_as_float(ua[ci][4 * i + 1]) + f.y;
           const float v2 = __uint_as_float(ua[ci][4 * i + 2]) + f.z, v3 = __uint_as_float(ua[ci][4 * i + 3]) + f.w;
           __nv_bfloat162 h0 = RP_NOMATH ? __floats2bfloat162_rn(v0, v1) : __floats2bfloat162_rn(gelu_fast(v0), gelu_fast(v1));
@@ -334,22 +371,7 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int oy = ty * g.TH + dy, ox = tx * g.TW + dx;
       const bool row_ok = tile_ok && oy < d.OH && ox < d.OW;
       const size_t pix = ((size_t)b * d.OHt + (oy * d.osy + d.ooy)) * d.OWt + (ox * d.osx + d.oox);
-      const __nv_bfloat16* resp = (const __nv_bfloat16*)d.res.ptr + pix * (size_t)d.res.ld + d.res.coff;
       __nv_bfloat16* outp = (__nv_bfloat16*)d.out.ptr + pix * (size_t)d.out.ld + d.out.coff;
-      // residual x of this tile (packed bf16): in flight while phase 1 of the NEXT tile is computed.  (Right after the
-      // previous phase 2 the load/store unit is still draining that phase's stores -- 32 sectors per STG.256 -- and these
-      // loads stall the warp for up to ~3k cycles; issuing them after phase 1 instead moves the same time into phase 2's
-      // wait for the data: measured equal, tests/gpu_ru_pair_probe3.py.)
-      uint32_t xs[RP_CHUNKS2][8];
-#pragma unroll
-      for (int ci = 0; ci < RP_CHUNKS2; ++ci) {
-        const int j = part + RP_PARTS * ci;
-        if (j < nchunks2 && row_ok && !RP_NORES) {
-          const Pack8 r = ldg256(resp + j * 16);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) xs[ci][i] = r.w[i];
-        }
-      }
       if (tq + step < total) phase1(lt + 1);
 
       // ---- phase 2 of tile lt: out = gelu(acc2 + b3 + x)
@@ -357,6 +379,7 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if (tsp) tsp[10] = clock64();
       mbar_wait_u32(acc2_full_a, lt & 1u);
       tcgen05_fence_after();
+      mbar_wait_u32(r_full_a, lt & 1u);  // the tile's residual rows are in shared memory
       if (tsp) tsp[11] = clock64();
 #pragma unroll
       for (int cp = 0; cp < RP_CHUNKS2; cp += 2) {
@@ -372,14 +395,22 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
         for (int hb = 0; hb < 2; ++hb) {
           if (hb == 1 && !has_b) break;
-          const int ci = cp + hb, j = hb ? jb : ja;
+          const int j = hb ? jb : ja;
           const uint32_t* u = hb ? ub : ua;
           if (!row_ok || RP_NOMATH) continue;
           Pack8 o;
+          // residual: 16 channels = two 16-byte chunks of this row's 128-byte line in block j / 4
+          const uint32_t rb = res_row + (uint32_t)((j >> 2) * RP_RES_BLOCK), c16 = (uint32_t)((j & 3) * 2);
+          uint32_t xr[8];
+          {
+            const float4 r0 = rp_lds128(rb + ((c16 ^ rsw) << 4)), r1 = rp_lds128(rb + (((c16 + 1) ^ rsw) << 4));
+            xr[0] = __float_as_uint(r0.x); xr[1] = __float_as_uint(r0.y); xr[2] = __float_as_uint(r0.z); xr[3] = __float_as_uint(r0.w);
+            xr[4] = __float_as_uint(r1.x); xr[5] = __float_as_uint(r1.y); xr[6] = __float_as_uint(r1.z); xr[7] = __float_as_uint(r1.w);
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 f = rp_lds128(bias2_a + (uint32_t)((j * 16 + 4 * i) * 4));
-            const uint32_t xa = xs[ci][2 * i], xb = xs[ci][2 * i + 1];
+            const float4 f = __ldg(bias2_g + j * 4 + i);
+            const uint32_t xa = xr[2 * i], xb = xr[2 * i + 1];
             const float v0 = gelu_fast(__uint_as_float(u[4 * i]) + f.x + __uint_as_float(xa << 16));
             const float v1 = gelu_fast(__uint_as_float(u[4 * i + 1]) + f.y + __uint_as_float(xa & 0xFFFF0000u));
             const float v2 = gelu_fast(__uint_as_float(u[4 * i + 2]) + f.z + __uint_as_float(xb << 16));
@@ -388,12 +419,15 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             o.w[2 * i] = *reinterpret_cast<uint32_t*>(&h0);
             o.w[2 * i + 1] = *reinterpret_cast<uint32_t*>(&h1);
           }
-          if (!RP_NOSTORE || o.w[0] == 0x12345678u) stg256(outp + j * 16, o);
+          if (!RP_NOSTORE) stg256(outp + j * 16, o);
         }
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster_u32(lead_acc2_empty);  // acc2 drained: the next tail GEMM may overwrite it
+      if (lane == 0) {
+        mbar_arrive_cluster_u32(lead_acc2_empty);  // acc2 drained: the next tail GEMM may overwrite it
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(r_empty_a) : "memory");  // this warp has read its residual rows
+      }
       if (tsp) tsp[12] = clock64();
     }
   }
@@ -455,9 +489,9 @@ int rdsic_ru_pair_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   rg.patch_tx = rg.halo_w * rg.halo_h * BK * 2;
   rg.patch_bytes = (rg.patch_tx + 1023) / 1024 * 1024;
   const size_t resident = (size_t)rg.kiters * rg.b_blk_bytes + (size_t)rg.k2_blocks * rg.w3_blk_bytes;
-  const size_t fixed = 1024 + (2 * RP_SLOTS + 9) * 8 + 4 + 16 + 3 * RP_MAXC * 4;
-  const size_t smem = (size_t)RP_SLOTS * rg.patch_bytes + resident + fixed;
-  if (smem > 227u * 1024u) return -1;
+  const size_t fixed = (2 * RP_SLOTS + 10) * 8 + 16;  // barriers + TMEM slot (no alignment slack: see the kernel's carve-up)
+  const size_t smem = (size_t)RP_SLOTS * rg.patch_bytes + resident + (size_t)(N2 / BK) * RP_RES_BLOCK + fixed;
+  if (smem > 227u * 1024u || N2 % BK || !d->bias || ((uintptr_t)d->bias % 16) || ((uintptr_t)d->tail_bias % 16)) return -1;
   g.num_stages = RP_SLOTS;
 
   CUtensorMap ta, tb, tg;
@@ -482,6 +516,19 @@ int rdsic_ru_pair_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   };
   if (encode_2d(&tb, d->weight, d->KH * d->KW * d->Cin, C, C / 2) != CUDA_SUCCESS) return RDSIC_E_ARG;
   if (encode_2d(&tg, d->tail_weight, C, N2, N2 / 2) != CUDA_SUCCESS) return RDSIC_E_ARG;
+  CUtensorMap tr;
+  {  // residual x: [B, OH, OW, N2] bf16 view, one 8 x 16-pixel x 64-channel box per block of a tile
+    const cuuint64_t ld_b = (cuuint64_t)d->res.ld * 2;
+    cuuint64_t dims[4] = {(cuuint64_t)N2, (cuuint64_t)d->OWt, (cuuint64_t)d->OHt, (cuuint64_t)B};
+    cuuint64_t strides[3] = {ld_b, ld_b * d->OWt, ld_b * d->OWt * d->OHt};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)g.TW, (cuuint32_t)g.TH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    void* base = (void*)((const __nv_bfloat16*)d->res.ptr + d->res.coff);
+    if (d->ooy || d->oox || d->OHt != OH || d->OWt != OW) return -1;
+    if (encode(&tr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return RDSIC_E_ARG;
+  }
 
   static bool attr_set[16] = {};
   int dev = 0;
@@ -493,5 +540,5 @@ int rdsic_ru_pair_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
     if (track) attr_set[dev] = true;
   }
   const int grid = 2 * g.walk_total < (sms & ~1) ? 2 * g.walk_total : (sms & ~1);
-  return rdsic_launch(ru_pair_tc_kernel, dim3((unsigned)grid), RP_THREADS, smem, stream, true, ta, tb, tg, *d, g, rg);
+  return rdsic_launch(ru_pair_tc_kernel, dim3((unsigned)grid), RP_THREADS, smem, stream, true, ta, tb, tg, tr, *d, g, rg);
 }

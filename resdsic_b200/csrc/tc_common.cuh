@@ -203,8 +203,13 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta_rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
   return r;
 }
+// Arrive on an mbarrier of (possibly) the peer CTA.  Default semantics (.release at CTA scope), as CUTLASS's
+// ClusterBarrier::arrive: what these arrivals hand over is tensor-memory state, ordered by the tcgen05 fences around
+// them, never generic memory.  The first version asked for `.release.cluster`: ncu showed the resulting ERRBAR
+// (stall_membar) as the hottest line of the pair kernels -- the arriving lane waits until its own STG.256 stores of
+// the tile are visible cluster-wide, 1-2k cycles per tile, before it can signal that an accumulator is free.
 __device__ __forceinline__ void mbar_arrive_cluster_u32(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads of a CTA pair: the data lands in the executing CTA's shared memory, the bytes complete on `bar`, a
 // shared::cluster address that may lie in the peer (leader) CTA

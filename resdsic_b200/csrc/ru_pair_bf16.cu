@@ -116,6 +116,7 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint64_t* r_full = w_full + 1;                 // local: this CTA's residual tile has landed
   uint64_t* r_empty = r_full + 1;                // local: ... and has been read by the twelve epilogue warps
   uint32_t* tmem_slot = (uint32_t*)(r_empty + 1);
+  float* bias2_s = (float*)(((uintptr_t)(tmem_slot + 1) + 15) & ~(uintptr_t)15);  // [N2] tail bias; b2 is read through L1
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int C = d.Cout;
@@ -145,6 +146,7 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
   }
   pdl_wait();  // PDL: barrier init / TMEM allocation above overlap the previous kernel's tail; global memory from here on
+  for (int i = threadIdx.x; i < rg.N2; i += blockDim.x) bias2_s[i] = d.tail_bias[i];
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -319,7 +321,7 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const uint32_t lead_p_full0 = mapa_u32(smem_u32(p_full), 0u), lead_acc2_empty = mapa_u32(smem_u32(acc2_empty), 0u);
     const uint32_t acc1_full0 = smem_u32(acc1_full), acc2_full_a = smem_u32(acc2_full);
     const float4* bias1_g = reinterpret_cast<const float4*>(d.bias);        // 384 + 768 B, L1-resident after the first tile
-    const float4* bias2_g = reinterpret_cast<const float4*>(d.tail_bias);
+    const uint32_t bias2_a = smem_u32(bias2_s);
     const uint32_t res_row = smem_u32(res_s) + (uint32_t)(ml * 128), r_full_a = smem_u32(r_full), r_empty_a = smem_u32(r_empty);
     const uint32_t rsw = (uint32_t)(ml & 7);  // 128B swizzle: 16-byte chunk index ^ (row & 7)
     const int total = g.walk_total, step = wk.step;
@@ -409,7 +411,7 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 f = __ldg(bias2_g + j * 4 + i);
+            const float4 f = rp_lds128(bias2_a + (uint32_t)((j * 16 + 4 * i) * 4));
             const uint32_t xa = xr[2 * i], xb = xr[2 * i + 1];
             const float v0 = gelu_fast(__uint_as_float(u[4 * i]) + f.x + __uint_as_float(xa << 16));
             const float v1 = gelu_fast(__uint_as_float(u[4 * i + 1]) + f.y + __uint_as_float(xa & 0xFFFF0000u));
@@ -489,7 +491,7 @@ int rdsic_ru_pair_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   rg.patch_tx = rg.halo_w * rg.halo_h * BK * 2;
   rg.patch_bytes = (rg.patch_tx + 1023) / 1024 * 1024;
   const size_t resident = (size_t)rg.kiters * rg.b_blk_bytes + (size_t)rg.k2_blocks * rg.w3_blk_bytes;
-  const size_t fixed = (2 * RP_SLOTS + 10) * 8 + 16;  // barriers + TMEM slot (no alignment slack: see the kernel's carve-up)
+  const size_t fixed = (2 * RP_SLOTS + 10) * 8 + 16 + 2 * RP_MAXC * 4;  // barriers + TMEM slot + tail bias (no alignment slack: see the kernel's carve-up)
   const size_t smem = (size_t)RP_SLOTS * rg.patch_bytes + resident + (size_t)(N2 / BK) * RP_RES_BLOCK + fixed;
   if (smem > 227u * 1024u || N2 % BK || !d->bias || ((uintptr_t)d->bias % 16) || ((uintptr_t)d->tail_bias % 16)) return -1;
   g.num_stages = RP_SLOTS;

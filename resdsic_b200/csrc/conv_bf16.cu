@@ -574,10 +574,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 else load16(d.aux, pix * (size_t)d.aux.ld + d.aux.coff + nb, aux);
               }
               if (d.bias) {
-                const float4* bp = reinterpret_cast<const float4*>(bias_s + nb);
+                const uint32_t bp = smem_u32(bias_s + nb);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  const float4 f = bp[i];
+                  const float4 f = lds128(bp + 16u * i);
                   v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
                 }
               }

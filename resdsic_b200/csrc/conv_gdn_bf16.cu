@@ -520,10 +520,10 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           for (int i = 0; i < 16; ++i) v[i] += w[i];
         }
         {
-          const float4* bp = reinterpret_cast<const float4*>(bias1_s + j * 16);
+          const uint32_t bp = smem_u32(bias1_s + j * 16);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 f = bp[i];
+            const float4 f = lds128(bp + 16u * i);
             v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
           }
         }
@@ -607,10 +607,10 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(u[i]);
         if (!row_ok) continue;
-        const float4* bp = reinterpret_cast<const float4*>(bias2_s + j * 16);
+        const uint32_t bp = smem_u32(bias2_s + j * 16);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 f = bp[i];
+          const float4 f = lds128(bp + 16u * i);
           v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
         }
 #pragma unroll

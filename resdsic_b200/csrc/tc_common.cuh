@@ -366,6 +366,14 @@ __device__ __forceinline__ float epi_apply(float v, float res, float aux) {
   return v;
 }
 
+// explicit shared-window 128-bit load (bias vectors staged per CTA): through a generic pointer the compiler emits LD.E.128,
+// whose longer round trip showed as long-scoreboard stalls on the first FADD of every epilogue chunk (ncu, round 2)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 f;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "r"(addr));
+  return f;
+}
+
 // 16 consecutive channels of one pixel = one 32-byte (bf16) or two 32-byte (fp32) accesses; sm_100 has
 // 256-bit LDG/STG, and the host guarantees 32-byte alignment of every chunk on the PLAIN path.
 struct Pack8 {

@@ -90,7 +90,9 @@ typedef struct rdsic_conv_desc {
   int32_t Cout, KH, KW, stride, pad_h, pad_w;
   int32_t OH, OW;         /* GEMM output grid */
   int32_t OHt, OWt, osy, osx, ooy, oox;
-  int32_t pixel_shuffle;  /* 0 or 2 */
+  int32_t pixel_shuffle;  /* 0; 2: nn.PixelShuffle(2), GEMM column n = 4 c + s; 3: the same with the weight rows packed
+                           * sub-position-major, column n = s * Cout/4 + c (bf16 path: 16 consecutive columns are then
+                           * 16 consecutive channels of ONE output pixel, i.e. one 32-byte store) */
   int32_t epilogue;       /* RDSIC_EPI_* */
   int32_t a_square;       /* square the A operand (GDN) */
   rdsic_view out;         /* [B,OHt,OWt,Cout(/4)] */

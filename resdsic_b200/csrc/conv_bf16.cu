@@ -583,6 +583,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               }
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = epi_apply<EPI>(v[i], NEED_RES ? res[i] : 0.f, NEED_AUX ? aux[i] : 0.f);
+              if (d.pixel_shuffle == 3) {  // columns are sub-position-major: this chunk is 16 channels of ONE shuffled pixel
+                const int Cq = d.Cout >> 2, sp = nb / Cq, cq = nb - sp * Cq;
+                const size_t px = ((size_t)b * d.OHt + (2 * oy + (sp >> 1))) * d.OWt + (2 * ox + (sp & 1));
+                store16(d.out, px * (size_t)d.out.ld + d.out.coff + cq, v, false);
+                continue;
+              }
               store16(d.out, pix * (size_t)d.out.ld + d.out.coff + nb, v, false);
               if (d.out2.ptr) store16(d.out2, pix * (size_t)d.out2.ld + d.out2.coff + nb, v, d.out2_square != 0);
               if (d.out3.ptr) store16(d.out3, pix * (size_t)d.out3.ld + d.out3.coff + nb, v, false);
@@ -899,7 +905,9 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   auto vec_ok = [](const rdsic_view& v) {
     return !v.ptr || (!v.nchw && v.ld % 16 == 0 && v.coff % 16 == 0 && ((uintptr_t)v.ptr % 32) == 0);
   };
-  const bool plain = !d->pixel_shuffle && d->Cout % 16 == 0 && vec_ok(d->out) && vec_ok(d->out2) && vec_ok(d->out3) &&
+  if (d->pixel_shuffle == 3)  // phase-major pixel shuffle: vector epilogue only
+    RDSIC_CHECK_ARG((d->Cout / 4) % 16 == 0 && !d->res.ptr && !d->aux.ptr && !d->out2.ptr && !d->out3.ptr && vec_ok(d->out));
+  const bool plain = d->pixel_shuffle != 2 && d->Cout % 16 == 0 && vec_ok(d->out) && vec_ok(d->out2) && vec_ok(d->out3) &&
                      vec_ok(d->res) && vec_ok(d->aux) && (!d->bias || ((uintptr_t)d->bias % 16) == 0);
   ConvTcKernel kern = g.pair ? (plain ? pick_kernel<true, true>(d->epilogue) : pick_kernel<false, true>(d->epilogue))
                              : (plain ? pick_kernel<true, false>(d->epilogue) : pick_kernel<false, false>(d->epilogue));

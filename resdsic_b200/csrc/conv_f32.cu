@@ -210,7 +210,7 @@ int rdsic_conv_validate(const rdsic_conv_desc* d) {
   RDSIC_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0);
   RDSIC_CHECK_ARG(d->KH > 0 && d->KW > 0 && d->stride > 0 && d->OH > 0 && d->OW > 0);
   RDSIC_CHECK_ARG(d->OHt > 0 && d->OWt > 0 && d->osy > 0 && d->osx > 0);
-  RDSIC_CHECK_ARG(d->pixel_shuffle == 0 || (d->pixel_shuffle == 2 && d->Cout % 4 == 0));
+  RDSIC_CHECK_ARG(d->pixel_shuffle == 0 || ((d->pixel_shuffle == 2 || d->pixel_shuffle == 3) && d->Cout % 4 == 0));
   RDSIC_CHECK_ARG(d->epilogue >= RDSIC_EPI_NONE && d->epilogue <= RDSIC_EPI_LRP);
   if (epi_needs_res(d->epilogue)) RDSIC_CHECK_ARG(d->res.ptr != nullptr);
   if (d->epilogue == RDSIC_EPI_GATE) RDSIC_CHECK_ARG(d->aux.ptr != nullptr);
@@ -224,7 +224,7 @@ int rdsic_conv_forward_f32(const rdsic_conv_desc* d, cudaStream_t stream) {
   int rc = rdsic_conv_validate(d);
   if (rc) return rc;
   RDSIC_CHECK_ARG(d->in.dtype == RDSIC_F32 && d->w_dtype == RDSIC_F32);
-  if (d->groups > 1) return RDSIC_E_UNSUPPORTED;  // grouped form: tensor-core path only
+  if (d->groups > 1 || d->pixel_shuffle == 3) return RDSIC_E_UNSUPPORTED;  // grouped / phase-major forms: tensor-core path only
   const int M = d->B * d->OH * d->OW;
   dim3 grid(ceil_div(M, BM), ceil_div(d->Cout, BN));
   const bool fast = !d->in.nchw && d->Cin % BK == 0 && d->in.ld % 4 == 0 && d->in.coff % 4 == 0 &&

@@ -68,6 +68,17 @@ class Conv2d(B200Module):
             x, k, s, p = patches, 1, 1, 0
         else:
             w, b = self.packed(ctx.wdt_for(x))
+        if pixel_shuffle == 2 and ctx.wdt_for(x) == torch.bfloat16 and (self.out_channels // 4) % 16 == 0 and not kw \
+                and (out is None or (out.ld % 16 == 0 and out.coff % 16 == 0)):
+            # PixelShuffle with the weight rows packed sub-position-major (column s * C/4 + c instead of 4 c + s): 16
+            # consecutive GEMM columns are then 16 channels of one shuffled pixel -- the vector epilogue applies
+            # (the scalar path cost 150 us for h_s's 256 -> 4 x 288 layer against 35 us of tensor time)
+            Cq = self.out_channels // 4
+            w, b = self._packed(("ps3", ctx.wdt_for(x)), (self.weight, self.bias), lambda: (
+                packing.pack_conv_weight(self.weight.view(Cq, 4, *self.weight.shape[1:]).transpose(0, 1).reshape(self.weight.shape),
+                                         ctx.wdt_for(x)),
+                self.bias.detach().float().view(Cq, 4).t().reshape(-1).contiguous()))
+            pixel_shuffle = 3
         if tail is not None:
             kw["tail"] = tail
         if out is None:

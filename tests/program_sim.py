@@ -67,6 +67,9 @@ class Sim:
         xp = F.pad(x.permute(0, 3, 1, 2), (d.pad_w, max(0, need_w - d.W), d.pad_h, max(0, need_h - d.H)))
         v = F.conv2d(xp, w, bias, stride=d.stride, groups=G)[:, :, : d.OH, : d.OW]  # [B,Cout,OH,OW]
         assert v.shape[2:] == (d.OH, d.OW), (v.shape, d.OH, d.OW)
+        if d.pixel_shuffle == 3:  # columns packed sub-position-major (s * C/4 + c): back to nn.PixelShuffle's 4 c + s
+            Cq = d.Cout // 4
+            v = v.reshape(v.shape[0], 4, Cq, *v.shape[2:]).transpose(1, 2).reshape(v.shape)
         if d.pixel_shuffle:
             v = F.pixel_shuffle(v, 2)
             Cv, sy, sx, oy, ox = d.Cout // 4, 1, 1, 0, 0

@@ -691,6 +691,7 @@ int pick_bn(int cout) {
 }  // namespace
 
 int rdsic_conv_validate(const rdsic_conv_desc* d);
+int rdsic_halo_pair_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream);  // halo_pair_bf16.cu
 
 int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   int rc = rdsic_conv_validate(d);
@@ -702,6 +703,8 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   RDSIC_CHECK_ARG(d->stride == 1 || d->stride == 2);
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return RDSIC_E_UNSUPPORTED;
+  rc = rdsic_halo_pair_forward_bf16(d, stream);  // narrow image head on big maps: input read once (halo patches)
+  if (rc != -1) return rc;
 
   TcGeom g = {};
   int B = d->B, H = d->H, W = d->W, OH = d->OH, OW = d->OW;

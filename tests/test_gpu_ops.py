@@ -202,14 +202,17 @@ def test_grouped_conv_vs_torch(G, cin, cout, shared, B, hw):
     np.testing.assert_allclose(res.cpu().numpy(), ref.numpy(), rtol=8e-3, atol=8e-3)
 
 
-@pytest.mark.parametrize("cin,cout", [(192, 192), (320, 192), (192, 3)])
-def test_tcgen05_deconv_vs_oracle(cin, cout):
+@pytest.mark.parametrize("cin,cout,B,hw", [(192, 192, 2, (6, 10)), (320, 192, 2, (6, 10)), (192, 3, 2, (6, 10)),
+                                           (192, 3, 3, (128, 96)), (192, 3, 2, (122, 99))])
+def test_tcgen05_deconv_vs_oracle(cin, cout, B, hw):
+    """(the two large 192 -> 3 cases run halo_pair_tc_kernel -- the image head on CTA pairs with halo patches --, the
+    second one with ragged tile edges and an odd number of tiles)"""
     from resdsic_b200.layers import ConvTranspose2d
     d = ConvTranspose2d(cin, cout)
     with torch.no_grad():
         d.weight.copy_(weights.hash_symmetric(f"tc.dw{cin}{cout}", d.weight.shape, (12.0 / (cin * 25)) ** 0.5))
         d.bias.copy_(weights.hash_symmetric(f"tc.db{cin}{cout}", d.bias.shape, 0.1))
-    x = weights.hash_symmetric(f"tc.dx{cin}", (2, cin, 6, 10), 1.0)
+    x = weights.hash_symmetric(f"tc.dx{cin}{hw}", (B, cin, *hw), 1.0)
     ref = torch.nn.functional.conv_transpose2d(_bf(x), _bf(d.weight.detach()), d.bias.detach(), stride=2, padding=2,
                                                output_padding=1)
     out = d.to(DEV).set_precision("bf16")(x.to(DEV)).cpu()

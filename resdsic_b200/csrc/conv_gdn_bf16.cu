@@ -645,7 +645,8 @@ conv_gdn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 }  // namespace
 
 int rdsic_conv_validate(const rdsic_conv_desc* d);
-int rdsic_ru_pair_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream);  // ru_pair_bf16.cu
+int rdsic_ru_pair_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream);   // ru_pair_bf16.cu
+int rdsic_gdn_pair_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream);  // gdn_pair_bf16.cu
 
 // conv (+bias) followed by a second, pointwise GEMM in one launch (d->tail_mode):
 //   1 GDN / 2 inverse GDN: tail_weight = packed bf16 gamma' [C][C], tail_bias = fp32 beta' [C], tail_n = C;
@@ -677,6 +678,9 @@ int rdsic_conv_gdn_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   if (!encode) return RDSIC_E_UNSUPPORTED;
   if (d->tail_mode == TAIL_RU) {  // ResidualUnit tail on CTA pairs with resident weights where the layer qualifies
     rc = rdsic_ru_pair_forward_bf16(d, stream);
+    if (rc != -1) return rc;
+  } else {  // long-K conv / deconv phase + GDN on CTA pairs (half the B reads per SM)
+    rc = rdsic_gdn_pair_forward_bf16(d, stream);
     if (rc != -1) return rc;
   }
 

@@ -68,6 +68,37 @@ def test_entropy_bottleneck(model, gold):
     np.testing.assert_allclose(lik.cpu().numpy(), gold["eb_lik"], rtol=1e-4, atol=1e-9)
 
 
+@pytest.mark.parametrize("kind,cin,B,hw", [("deconv", 192, 4, (64, 96)), ("deconv", 320, 3, (50, 70)), ("conv", 192, 3, (128, 192)),
+                                           ("deconv", 192, 1, (12, 20))])
+def test_fused_conv_gdn_vs_torch(kind, cin, B, hw):
+    """conv / deconv + GDN in ONE kernel against torch on bf16-rounded operands, with x and x^2 rounded to bf16 where the
+    kernels round them.  The large cases run gdn_pair_tc_kernel (CTA pairs; a ragged one with an odd tile count and
+    Cin = 320), the small one conv_gdn_tc_kernel; stride-2 conv + GDN and the four deconv phases + inverse GDN."""
+    from resdsic_b200.layers import GDN, Conv2d, ConvTranspose2d, Sequential
+    import torch.nn.functional as F
+    C = 192
+    inverse = kind == "deconv"
+    first = ConvTranspose2d(cin, C) if inverse else Conv2d(cin, C, 5, 2)
+    gdn = GDN(C, inverse=inverse)
+    with torch.no_grad():
+        first.weight.copy_(weights.hash_symmetric(f"cg.w{kind}{cin}", first.weight.shape, (6.0 / (cin * 25)) ** 0.5))
+        first.bias.copy_(weights.hash_symmetric(f"cg.b{kind}{cin}", first.bias.shape, 0.1))
+        gdn.gamma.copy_(gdn.gamma_reparam.init(0.02 * torch.eye(C) + 0.002 * weights.hash_symmetric(f"cg.g{kind}", (C, C), 1.0).abs()))
+        gdn.beta.copy_(gdn.beta_reparam.init(1.0 + 0.3 * weights.hash_symmetric(f"cg.be{kind}", (C,), 1.0).abs()))
+    seq = Sequential(first, gdn)
+    x = weights.hash_symmetric(f"cg.x{kind}{cin}{hw}", (B, cin, *hw), 1.0)
+    if inverse:
+        y = F.conv_transpose2d(_bf(x), _bf(first.weight.detach()), first.bias.detach(), stride=2, padding=2, output_padding=1)
+    else:
+        y = F.conv2d(_bf(x), _bf(first.weight.detach()), first.bias.detach(), stride=2, padding=2)
+    from resdsic_b200 import packing
+    gam, beta = packing.pack_gdn(gdn.beta, gdn.gamma, torch.bfloat16)
+    norm = F.conv2d(_bf(y * y), gam.float()[:C, :C, None, None], beta.float())
+    ref = _bf(y) * (torch.sqrt(norm) if inverse else torch.rsqrt(norm))
+    out = seq.to(DEV).set_precision("bf16")(x.to(DEV)).cpu()
+    np.testing.assert_allclose(out.numpy(), ref.numpy(), rtol=1e-2, atol=1e-2)
+
+
 @pytest.mark.parametrize("name,mod,key", [
     ("attn8", lambda m: m.g_a[4].conv_b[0], "attn8_x"),
     ("attn4", lambda m: m.g_a[8].conv_b[0], "attn4_x"),
@@ -317,6 +348,7 @@ def test_patchify_matches_unfold(C, k, s, p, B, H, W):
     {"RDSIC_TC_M2_MINK": "1", "RDSIC_TC_M2": "2"},   # M2 also for the 1-3 k-iteration pointwise GEMMs
     {"RDSIC_RU_DBL": "0", "RDSIC_RU_PAIR": "0"},     # single-buffered fused ResidualUnit kernel
     {"RDSIC_RU_PAIR": "0"},                          # 1-CTA double-buffered fused ResidualUnit kernel (default: CTA pairs)
+    {"RDSIC_GDN_PAIR": "0", "RDSIC_HALO_PAIR": "0"},  # 1-CTA conv + GDN kernels, generic image head
     {"RDSIC_PDL": "1"},                              # programmatic dependent launch on every forward kernel (default off: measured slower)
     {"RDSIC_TC_PAIR": "3"},                          # cta_group::2 CTA pairs on EVERY layer with two M tiles (default: wide long-K layers)
     {"RDSIC_TC_PAIR": "0"},                          # no CTA pairs (M2 / single-issuer tiles everywhere)
@@ -329,6 +361,6 @@ def test_kernel_mode_switches_in_subprocess(env):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_ops.py", "-m", "gpu", "-q", "-x", "-k",
-                        "tcgen05 or layers_bf16 or subpel or fused_residual or grouped"], cwd=root, env=dict(os.environ, **env), capture_output=True,
+                        "tcgen05 or layers_bf16 or subpel or fused_ or grouped"], cwd=root, env=dict(os.environ, **env), capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

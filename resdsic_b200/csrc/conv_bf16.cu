@@ -802,8 +802,11 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   // 1 this rule (default), 3 every layer with two M tiles.
   static const int tune_pair = getenv("RDSIC_TC_PAIR") ? atoi(getenv("RDSIC_TC_PAIR")) : 1;
   const long tiles128_all = (long)B * ceil_div(OW, g.TW) * ceil_div(OH, g.TH);
+  // (round 2, after the remote arrivals lost their cluster-scope release: the big pointwise layers -- RU heads, qkv,
+  // proj, gate at H/4 -- gain ~8 % in pairs, N = 160 / 176 long-K layers gain too; BN <= 128 still loses)
   const bool want_pair = tune_pair && !g.halo && sms >= 2 && tiles128_all >= 2 &&
-                         (tune_pair == 3 || (g.BN >= 192 && g.num_k_iters >= 8));
+                         (tune_pair == 3 || (g.BN >= 160 && g.num_k_iters >= 8) ||
+                          (tune_pair != 2 && d->KH * d->KW == 1 && g.BN >= 96 && tiles128_all >= 8L * sms));
   const bool family = !g.halo && !want_pair && g.num_k_iters >= tune_mink &&
                       (4 * g.BN <= 512 || (tune_ksplit != 3 && 2 * g.BN <= 512 && g.num_k_iters >= 16));
   if (tune_m2 && family) {

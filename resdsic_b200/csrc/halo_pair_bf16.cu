@@ -13,17 +13,17 @@
 // the ResidualUnit kernels (4 KB of A + 1.5 KB of B).  With N = 12 the layer is bound by delivering its ACTIVATIONS to the
 // tensor core nine times, whatever feeds shared memory.
 //
-// Roles per CTA (7 warps): warp 0 TMA producer, warps 1 / 2 MMA issuers (leader CTA only; alternate filter taps, own
-// accumulators summed by the epilogue in a fixed order: with N = 16 an MMA is bound by its 4 KB A read from shared memory,
-// ~32 cycles, and one issuing thread needs ~65 per instruction), warps 3..6 epilogue (one per TMEM lane quarter).
-// TMEM: two buffers of two 16-column accumulators.  Barriers: both CTAs' patches complete on the LEADER's a_full[slot];
-// the leader's commits are multicast to both CTAs' a_empty[slot] / acc_full[b]; both CTAs' epilogue warps arrive on the
-// leader's acc_empty[b] (count 8).
+// Roles per CTA (6 warps): warp 0 TMA producer, warp 1 MMA issuer (leader CTA only), warps 2..5 epilogue (one per TMEM
+// lane quarter).  TMEM: two 16-column accumulators (double-buffered across tiles).  (A second issuer warp -- alternate
+// taps into a second accumulator -- was measured: no gain, the operand port is the bound; dropped, K runs sequentially.)
+// The kernel serves this layer at EVERY map size, so that a pixel's bits do not depend on the batch / image size.
+// Barriers: both CTAs' patches complete on the LEADER's a_full[slot]; the leader's commits are multicast to both CTAs'
+// a_empty[slot] / acc_full[b]; both CTAs' epilogue warps arrive on the leader's acc_empty[b] (count 8).
 #include "tc_common.cuh"
 
 namespace {
 
-constexpr int HP_THREADS = 32 * 7;
+constexpr int HP_THREADS = 32 * 6;
 constexpr int HP_SLOTS = 6;   // patch ring (u = local tile * kb + channel block; one producer, one issuer, in order)
 constexpr int HP_BN = 16;
 
@@ -52,17 +52,17 @@ halo_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_b) : "memory");
     for (int s = 0; s < HP_SLOTS; ++s) {
       mbar_init(&a_full[s], 1);
-      mbar_init(&a_empty[s], 2);  // both issuers read every patch
+      mbar_init(&a_empty[s], 1);
     }
     for (int k = 0; k < 2; ++k) {
-      mbar_init(&acc_full[k], 2);
+      mbar_init(&acc_full[k], 1);
       mbar_init(&acc_empty[k], 8);
     }
     mbar_init(w_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(64));
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
   }
   pdl_wait();
@@ -112,10 +112,9 @@ halo_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // drain: no multicast commit of the leader may arrive on this CTA's barriers after it has exited
     for (int n = 0; n < HP_SLOTS; ++n, ++u) mbar_wait_u32(a_empty0 + 8u * (u % HP_SLOTS), ((u / HP_SLOTS) & 1u) ^ 1u);
     __syncwarp();
-  } else if (warp == 1 || warp == 2) {
-    // ================= MMA issuers: leader CTA only =================
+  } else if (warp == 1) {
+    // ================= MMA issuer: leader CTA only =================
     if (leader) {
-      const int me = warp - 1;
       const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t a_full0 = __shfl_sync(0xffffffffu, smem_u32(a_full), 0);
       const uint32_t a_empty0 = __shfl_sync(0xffffffffu, smem_u32(a_empty), 0);
@@ -133,7 +132,7 @@ halo_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const uint32_t b = lt & 1u, use = (lt >> 1) & 1u;
         mbar_wait(&acc_empty[b], use ^ 1u);
         tcgen05_fence_after();
-        const uint32_t acc = tbase + b * (uint32_t)(2 * HP_BN) + (uint32_t)(me * HP_BN);
+        const uint32_t acc = tbase + b * (uint32_t)HP_BN;
         for (int cb = 0; cb < kb; ++cb, ++u) {
           const uint32_t slot = u % HP_SLOTS, ph = (u / HP_SLOTS) & 1u;
           mbar_wait_u32(a_full0 + 8u * slot, ph);
@@ -145,10 +144,9 @@ halo_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             int tap = 0;
             for (int r = 0; r < KH; ++r)
               for (int sx = 0; sx < KW; ++sx, ++tap) {
-                if ((tap & 1) != me) continue;  // this issuer's taps; its first MMA of the tile (cb 0, tap me) overwrites
                 const uint64_t da = da0 + (uint64_t)(uint32_t)(r * hw8 + sx * 8);
                 const uint64_t db = db0 + (uint64_t)((uint32_t)(tap * kb) * bblk_u);
-                for (int k = 0; k < kc; ++k) umma_bf16_2sm(acc, da + 2 * k, db + 2 * k, idesc, (cb | (tap >> 1) | k) ? 1u : 0u);
+                for (int k = 0; k < kc; ++k) umma_bf16_2sm(acc, da + 2 * k, db + 2 * k, idesc, (cb | tap | k) ? 1u : 0u);
               }
             tcgen05_commit_2sm_mc_u32(a_empty0 + 8u * slot, 3);
           }
@@ -177,11 +175,8 @@ halo_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t bsel = lt & 1u, par = (lt >> 1) & 1u;
       mbar_wait(&acc_full[bsel], par);
       tcgen05_fence_after();
-      float v[16], w2[16];
-      tmem_ld16(tlane + bsel * (uint32_t)(2 * HP_BN), v);
-      tmem_ld16(tlane + bsel * (uint32_t)(2 * HP_BN) + (uint32_t)HP_BN, w2);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] += w2[i];  // fixed order: even taps + odd taps
+      float v[16];
+      tmem_ld16(tlane + bsel * (uint32_t)HP_BN, v);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_u32(lead_acc_empty0 + 8u * bsel);  // accumulator read: the issuer may reuse it
@@ -210,7 +205,7 @@ halo_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   cluster_sync_all();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64));
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32));
   }
 }
 
@@ -237,7 +232,7 @@ int rdsic_halo_pair_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) 
   g.n_tiles = 1;
   g.total_tiles = B * g.tiles_y * g.tiles_x;
   g.m_tiles = g.total_tiles;
-  if (g.m_tiles < 2 * sms) return -1;  // a bandwidth kernel for the big maps; small ones stay on the generic path
+  if (g.m_tiles < 2) return -1;
   g.pair = 1;
   g.walk_total = ceil_div(g.m_tiles, 2);
   HaloPairGeom hg;

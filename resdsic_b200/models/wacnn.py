@@ -526,12 +526,12 @@ class WACNN(CompressionModel):
                 ev[key] = prog.record()
 
         def rest_of_stack(stack_convs, t, tag, stride_of, final=None):
-            """Layers 1 .. 4 of G stacks at once: layer l's input channels of group g start g * stride_of(l) after t's."""
-            G = len(stack_convs)
-            for l in range(1, 5):
+            """Layers 1 .. of G stacks at once: layer l's input channels of group g start g * stride_of(l) after t's."""
+            depth = len(stack_convs[0])
+            for l in range(1, depth):
                 layer = [cs[l] for cs in stack_convs]
                 x = t.channels(0, layer[0].in_channels)
-                kw = dict(gelu=True) if l < 4 else (final if final is not None else dict(out_dtype=f32))
+                kw = dict(gelu=True) if l < depth - 1 else (final if final is not None else dict(out_dtype=f32))
                 t = emit_grouped(ctx, self, (tag, l), layer, x, stride_of(l), **kw)
             return t
 
@@ -555,9 +555,9 @@ class WACNN(CompressionModel):
             prog.wait(ev[("lrp", i)])
             seq = convs["lrp"][i]
             t = seq[0].emit_partial(ctx, means.channels(M, sc_ * (k + 1)), 1, M, res=pre[("lrp", i)], gelu=True)
-            for c in seq[1:4]:
+            for c in seq[1:-1]:
                 t = c.emit(ctx, t, gelu=True)
-            seq[4].emit(ctx, t, epilogue=_lib.EPI_LRP, res=yh_i, out=yh_i, out2=slot)  # refined slice: support of later slices
+            seq[-1].emit(ctx, t, epilogue=_lib.EPI_LRP, res=yh_i, out=yh_i, out2=slot)  # refined slice: support of later slices
 
         # ---------------- slices S .. 9: one grouped launch per layer
         support = means.channels(M, sc_ * S)

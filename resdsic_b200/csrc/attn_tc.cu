@@ -37,6 +37,11 @@ __device__ __forceinline__ void ldmatrix_x1_trans(uint32_t& r0, const void* smem
   const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
   asm volatile("ldmatrix.sync.aligned.m8n8.x1.trans.shared.b16 {%0}, [%1];" : "=r"(r0) : "r"(addr));
 }
+__device__ __forceinline__ float exp2f_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -91,13 +96,16 @@ __global__ void __launch_bounds__(768) win_attn_tc_kernel(const rdsic_attn_desc 
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     // the relative-position-bias table (L2-resident gather) is fetched while the window's copies are in flight
-    for (int e = tid; e < HEADS * TWD * TWD; e += NTHR) tab[e] = d.bias_table[(e % (TWD * TWD)) * HEADS + e / (TWD * TWD)];
+    // (pre-multiplied by log2(e): the softmax below runs in base 2 -- one FMUL per score less than __expf)
+    for (int e = tid; e < HEADS * TWD * TWD; e += NTHR)
+      tab[e] = d.bias_table[(e % (TWD * TWD)) * HEADS + e / (TWD * TWD)] * 1.4426950408889634f;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
 
   const int head = warp;
   const int g = lane / 4, t = lane % 4;
+  const bool masked = d.shift > 0 && (wh == nWh - 1 || ww == nWw - 1);  // any token of this window in a wrapped region
   const __nv_bfloat16* Q = qkv + head * DH;
   const __nv_bfloat16* K = qkv + C + head * DH;
   const __nv_bfloat16* V = qkv + 2 * C + head * DH;
@@ -133,17 +141,21 @@ __global__ void __launch_bounds__(768) win_attn_tc_kernel(const rdsic_attn_desc 
     // ---- scale, relative-position bias, shift mask, softmax (rows i0 and i1; a row lives in one quad)
     const int hi0 = i0 / WS, wi0 = i0 % WS, hi1 = i1 / WS, wi1 = i1 % WS;
     const int r0 = rid[i0], r1 = rid[i1];
+    const float scale2 = d.scale * 1.4426950408889634f;  // scores in units of log2(e): exp(v) == exp2(v')
     float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < NT_S; ++nt) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int j = nt * 8 + 2 * t + e;
-        const int hj = j / WS, wj = j % WS, rj = rid[j];
-        float v0 = s[nt][e] * d.scale + tb[(hi0 - hj + WS - 1) * TWD + (wi0 - wj + WS - 1)];
-        float v1 = s[nt][2 + e] * d.scale + tb[(hi1 - hj + WS - 1) * TWD + (wi1 - wj + WS - 1)];
-        if (rj != r0) v0 += -100.0f;
-        if (rj != r1) v1 += -100.0f;
+        const int hj = j / WS, wj = j % WS;
+        float v0 = fmaf(s[nt][e], scale2, tb[(hi0 - hj + WS - 1) * TWD + (wi0 - wj + WS - 1)]);
+        float v1 = fmaf(s[nt][2 + e], scale2, tb[(hi1 - hj + WS - 1) * TWD + (wi1 - wj + WS - 1)]);
+        if (masked) {  // block-uniform: only the windows of the last row / column carry the shift mask (-100)
+          const int rj = rid[j];
+          if (rj != r0) v0 += -100.0f * 1.4426950408889634f;
+          if (rj != r1) v1 += -100.0f * 1.4426950408889634f;
+        }
         s[nt][e] = v0;
         s[nt][2 + e] = v1;
         m0 = fmaxf(m0, v0);
@@ -159,8 +171,8 @@ __global__ void __launch_bounds__(768) win_attn_tc_kernel(const rdsic_attn_desc 
     for (int nt = 0; nt < NT_S; ++nt) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        s[nt][e] = __expf(s[nt][e] - m0);
-        s[nt][2 + e] = __expf(s[nt][2 + e] - m1);
+        s[nt][e] = exp2f_fast(s[nt][e] - m0);
+        s[nt][2 + e] = exp2f_fast(s[nt][2 + e] - m1);
         l0 += s[nt][e];
         l1 += s[nt][2 + e];
       }

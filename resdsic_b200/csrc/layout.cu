@@ -230,20 +230,30 @@ __global__ void __launch_bounds__(256) patchify_tiled_kernel(const rdsic_patch_d
     lut[k] = off;
   }
   const float* src = (const float*)d.src.ptr;
-  for (int e = threadIdx.x; e < d.C * rows * cols; e += blockDim.x) {
-    const int rx = e % cols;
-    int q = e / cols;
-    const int ry = q % rows, c = q / rows;
-    const int iy = iy0 + ry, ix = ix0 + rx;
-    float v = 0.f;
-    if (iy >= 0 && iy < d.H && ix >= 0 && ix < d.W) v = __ldg(src + (((size_t)b * d.C + c) * d.H + iy) * d.W + ix);
-    tile[c * plane + ry * pitch + rx] = v;
+  {
+    // (c, ry, rx) advance incrementally: e += blockDim.x is (+dq rows, +dr columns) -- the e % cols / e / cols / q % rows
+    // form of the first version spent most of the loop in integer division by run-time values
+    const int step = (int)blockDim.x, dq = step / cols, dr = step - dq * cols;
+    int rx = (int)threadIdx.x % cols, q = (int)threadIdx.x / cols;
+    int ry = q % rows, c = q / rows;
+    for (int e = threadIdx.x; e < d.C * rows * cols; e += step) {
+      const int iy = iy0 + ry, ix = ix0 + rx;
+      float v = 0.f;
+      if (iy >= 0 && iy < d.H && ix >= 0 && ix < d.W) v = __ldg(src + (((size_t)b * d.C + c) * d.H + iy) * d.W + ix);
+      tile[c * plane + ry * pitch + rx] = v;
+      rx += dr;
+      ry += dq;
+      if (rx >= cols) { rx -= cols; ++ry; }
+      while (ry >= rows) { ry -= rows; ++c; }
+    }
   }
   __syncthreads();
   const int chunks = d.Kp / 8;
   __nv_bfloat16* dst = (__nv_bfloat16*)d.dst.ptr;
-  for (int e = threadIdx.x; e < PT_H * PT_W * chunks; e += blockDim.x) {
-    const int ch = e % chunks, p = e / chunks;
+  const int pstep = (int)blockDim.x / chunks, cstep = (int)blockDim.x - pstep * chunks;
+  int ch = (int)threadIdx.x % chunks, p = (int)threadIdx.x / chunks;
+  for (int e = threadIdx.x; e < PT_H * PT_W * chunks; e += blockDim.x, p += pstep, ch += cstep) {
+    if (ch >= chunks) { ch -= chunks; ++p; }
     const int lx = p % PT_W, ly = p / PT_W;
     const int ox = ox0 + lx, oy = oy0 + ly;
     if (ox >= d.OW || oy >= d.OH) continue;

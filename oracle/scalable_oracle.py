@@ -44,7 +44,7 @@ def mask(policy, levels, scale, scale_prog, pr, sd, p="masking"):
     policies (single_decoder.py:399-401)."""
     if policy == "two-levels":
         return torch.zeros_like(scale) if pr == 0 else torch.ones_like(scale)
-    inp = torch.cat([scale, scale_prog], 1)
+    inp = torch.cat([scale, scale_prog], 1) if scale_prog is not None else None  # (None: only the constant cases below are reachable)
     if policy == "learnable-mask-gamma":
         if pr == 0:
             return torch.zeros_like(scale)
@@ -66,9 +66,13 @@ def mask(policy, levels, scale, scale_prog, pr, sd, p="masking"):
 
 
 @torch.no_grad()
-def forward(sd, x, qualities, policy, levels, lrp_prog=True, independent_lrp=False, multiple_decoder=False, table=None):
+def forward(sd, x, qualities, policy, levels, lrp_prog=True, independent_lrp=False, multiple_decoder=False, table=None,
+            joiner_policy=None):
     """scalable_icd.forward / scalable_imd.forward for a list of quality INDICES.  With `table` also returns the
-    int32 symbols / indexes of both streams for the LAST quality (what compress hands the coder)."""
+    int32 symbols / indexes of both streams for the LAST quality (what compress hands the coder).
+    `joiner_policy` (not None): conditional_scalable_icd.forward (conditional_single_decoder.py:112-271) -- the mask is
+    computed without the progressive scales (:163), the progressive likelihood is taken at the UNMASKED scale (:221) and
+    the two reconstructions of a slice are merged by `merge` (:103-113)."""
     B, _, H, W = x.shape
     y_base, y = g_a_split(x, sd)
     y = O.attention_block(y, sd, "g_a.8", 4, 2)
@@ -84,7 +88,7 @@ def forward(sd, x, qualities, policy, levels, lrp_prog=True, independent_lrp=Fal
     for q in qualities:
         y_hat_q = base["y_hat"]
         if q != 0:
-            m = mask(policy, levels, lat_s, lat_sp, q, sd)
+            m = mask(policy, levels, lat_s, lat_sp if joiner_policy is None else None, q, sd)
             masks[q] = m
             ys, ms = y_prog.chunk(10, 1), m.chunk(10, 1)
             hat, lk, syms, idxs = [], [], [], []
@@ -93,7 +97,8 @@ def forward(sd, x, qualities, policy, levels, lrp_prog=True, independent_lrp=Fal
                 mean_sup = torch.cat([lat_mp] + sup, 1)
                 mu = O.cc_stack(mean_sup, sd, f"cc_mean_transforms_prog.{i}")[:, :, :hh, :ww]
                 sc = O.cc_stack(torch.cat([lat_sp] + sup, 1), sd, f"cc_scale_transforms_prog.{i}")[:, :, :hh, :ww]
-                sc = sc * ms[i]
+                if joiner_policy is None:
+                    sc = sc * ms[i]
                 r = torch.round(ys[i] - mu)
                 lk.append(O.gaussian_likelihood(r + mu, sc, mu))  # gaussian_conditional_prog(y, scale*mask, mu), :447
                 yh = r * ms[i] + mu  # :451
@@ -105,7 +110,13 @@ def forward(sd, x, qualities, policy, levels, lrp_prog=True, independent_lrp=Fal
                     yh = yh + 0.5 * torch.tanh(O.cc_stack(torch.cat([mean_sup, yh], 1), sd, f"{fam}.{i}"))
                 hat.append(yh)
             liks_p.append(torch.cat(lk, 1))
-            y_hat_q = base["y_hat"] + torch.cat(hat, 1)
+            if joiner_policy in (None, "residual"):
+                y_hat_q = base["y_hat"] + torch.cat(hat, 1)
+            elif joiner_policy in ("concatenation", "cac"):
+                y_hat_q = base["y_hat"]
+            else:  # "conditional": joiner[i](cat(y_hat_slice, y_hat_prog_slice))
+                mains = base["y_hat"].chunk(10, 1)
+                y_hat_q = torch.cat([joiner(torch.cat([mains[i], hat[i]], 1), sd, f"joiner.{i}") for i in range(10)], 1)
             if table is not None:
                 out["prog_symbols"], out["prog_indexes"] = torch.cat(syms, 1), torch.cat(idxs, 1)
         y_hats.append(y_hat_q)
@@ -119,6 +130,13 @@ def forward(sd, x, qualities, policy, levels, lrp_prog=True, independent_lrp=Fal
     if table is not None:
         out["symbols"], out["indexes"] = base["symbols"], base["indexes"]
     return out
+
+
+def joiner(t, sd, p):
+    """conditional_single_decoder.py:39-48"""
+    t = O.gelu(O.conv(t, sd, p + ".0"))
+    t = O.gelu(O.conv(t, sd, p + ".2"))
+    return O.conv(t, sd, p + ".4")
 
 
 def g_s(y_hat, sd, p="g_s"):

@@ -1,15 +1,16 @@
 """Model registry -- mirror of the reference's `compress/models/__init__.py:22-62`
 for the model families BASELINE.json names (`-m/-a cnn|stf`)."""
-from .scalable import scalable_icd, scalable_imd
+from .scalable import conditional_scalable_icd, scalable_icd, scalable_imd
 from .stf import SymmetricalTransFormer
 from .wacnn import WACNN
 
 models = {
     "cnn": WACNN,
-    # ResDSIC scalable codecs (reference models/__init__.py:22-29).  The conditional variants
-    # ("cicd" / "cimd": a per-slice joiner network) and "ind" are not provided.
+    # ResDSIC scalable codecs (reference models/__init__.py:22-29).  "cimd" (two decoders + joiner) and
+    # "ind" (independent entropy models) are not provided.
     "icd": scalable_icd,
     "imd": scalable_imd,
+    "cicd": conditional_scalable_icd,
     # the reference README's `-m stf`; the reference tree itself has no STF model, so this
     # entry is builder-defined (see models/stf.py) -- every block it is made of is pinned to the reference
     "stf": SymmetricalTransFormer,
@@ -23,6 +24,11 @@ def configure_model(args):
         raise KeyError(f"unknown model {name!r}; available: {sorted(models)}")
     if name == "stf":
         return models[name]()  # STF fixes its widths (N=192, M=384), like the upstream `-m stf`
+    if name == "cicd":  # reference models/__init__.py:42-47
+        return models[name](N=getattr(args, "N", 192), M=getattr(args, "M", 320),
+                            mask_policy=getattr(args, "mask_policy", "two-levels"),
+                            lambda_list=getattr(args, "lambda_list", [0.0035, 0.065]),
+                            joiner_policy=getattr(args, "joiner_policy", "conditional"))
     if name in ("icd", "imd"):  # reference models/__init__.py:49-54
         return models[name](N=getattr(args, "N", 192), M=getattr(args, "M", 320),
                             mask_policy=getattr(args, "mask_policy", "two-levels"),
@@ -30,4 +36,4 @@ def configure_model(args):
     return models[name](N=getattr(args, "N", 192), M=getattr(args, "M", 320))
 
 
-__all__ = ["models", "configure_model", "WACNN", "SymmetricalTransFormer", "scalable_icd", "scalable_imd"]
+__all__ = ["models", "configure_model", "WACNN", "SymmetricalTransFormer", "scalable_icd", "scalable_imd", "conditional_scalable_icd"]

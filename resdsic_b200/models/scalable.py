@@ -95,6 +95,15 @@ class scalable_icd(WACNN):
     def _synthesis(self, q):
         return self.g_s
 
+    def _computed_mask(self, ctx, lat_s, lat_sp, q, cache):
+        """Importance mask of a quality level whose mask is neither all zeros nor all ones (:397-401)."""
+        return self.masking.emit(ctx, lat_s, lat_sp, q, cache)
+
+    def _merge(self, ctx, y_hat, y_hat_p):
+        """y_hat_complete = y_hat_base + y_hat_prog (:472)."""
+        B, h, w, M = y_hat.B, y_hat.H, y_hat.W, self.M
+        return ctx.prog.copy(y_hat, ctx.buf(B, h, w, M, torch.float32), op_code=4, src2=y_hat_p)
+
     @torch.no_grad()
     def forward(self, x, quality=None, training=True):
         """reference :343-504.  Returns {"x_hat": [Q,B,3,H,W], "likelihoods": {"y": [1,10*B,32,h,w] (slice-major, as the reference's cat over dim 0), "z", "z_prog",
@@ -209,7 +218,7 @@ class scalable_icd(WACNN):
             if q != 0:
                 kind = self.masking.kind(q)
                 assert kind != ZEROS
-                mask = None if kind == ONES else self.masking.emit(ctx, lat_s, lat_sp, q, mask_cache)
+                mask = None if kind == ONES else self._computed_mask(ctx, lat_s, lat_sp, q, mask_cache)
                 p.masks[q] = mask
                 if first:
                     mq, sq = means_p, scales_p
@@ -221,7 +230,7 @@ class scalable_icd(WACNN):
                 y_hat_p = self._emit_slice_loop(ctx, fam_p, pre_p, self.gaussian_conditional_prog, y_prog, mq, sq,
                                                 p.lik_y_prog[jp], p.prog_symbols, p.prog_indexes, mask=mask, lrp=self.lrp_prog)
                 jp += 1
-                y_hat_q = prog.copy(y_hat, ctx.buf(B, h, w, M, f32), op_code=4, src2=y_hat_p)  # y_hat_complete (:472)
+                y_hat_q = self._merge(ctx, y_hat, y_hat_p)
             prog.copy(y_hat_q, TV.nchw_of(p.y_hat_q[j]))
             act = prog.copy(y_hat_q, ctx.buf(B, h, w, M)) if bf16 else y_hat_q
             self._synthesis(q).emit(ctx, act, last_kw=dict(out=TV.nchw_of(p.x_hat[j])))
@@ -250,3 +259,61 @@ class scalable_imd(scalable_icd):
 
     def _synthesis(self, q):
         return self.g_s[0 if q == 0 else 1]
+
+
+class conditional_scalable_icd(scalable_icd):
+    """reference scalable/conditional_single_decoder.py:18 (registry key "cicd"): `icd` whose base and progressive
+    reconstructions of a slice are MERGED by a policy instead of summed (:103-113) -- "conditional": a per-slice
+    joiner network conv3x3(64,64)-GELU-conv3x3(64,64)-GELU-conv3x3(64,32) on cat(y_hat_slice, y_hat_prog_slice)
+    (:39-48); "residual": the sum; "concatenation" / "cac": the base reconstruction alone.  The reference calls
+    `self.masking(latent_scales, pr=quality)` WITHOUT the progressive scales (:163), so only the constant masks are
+    reachable (two-levels, or the end points of the learnable policies: anything else trips Mask.forward's
+    `assert scale_prog is not None`, mask_layer.py:74,98), and with an all-ones mask its unmasked likelihood /
+    masked reconstruction (:221-225) coincide with `icd`'s.  Like the reference's, the default constructor arguments
+    (`mask_policy="learnable-mask"`, one lambda) do not construct (`gamma` of -1 rows, single_decoder.py:162-164)."""
+
+    def __init__(self, N=192, M=320, mask_policy="learnable-mask", lambda_list=(0.05,), lrp_prog=True,
+                 independent_lrp=False, joiner_policy="conditional", **kwargs):
+        super().__init__(N=N, M=M, mask_policy=mask_policy, lambda_list=lambda_list, lrp_prog=lrp_prog,
+                         independent_lrp=independent_lrp, **kwargs)
+        self.joiner_policy = joiner_policy
+        if joiner_policy == "conditional":
+            self.joiner = nn.ModuleList(
+                Sequential(conv(64, 64, stride=1, kernel_size=3), GELU(), conv(64, 64, stride=1, kernel_size=3), GELU(),
+                           conv(64, 32, stride=1, kernel_size=3)) for _ in range(10))
+        elif joiner_policy == "cac":  # (the reference overwrites the policy string with this module, :49-54; kept as a module here)
+            self.joiner_cac = conv(M, M, kernel_size=1, stride=1)
+        elif joiner_policy not in ("residual", "concatenation"):
+            raise NotImplementedError(f"joiner policy {joiner_policy!r} (block_concatenation changes the decoder width: not provided)")
+
+    def _computed_mask(self, ctx, lat_s, lat_sp, q, cache):
+        raise AssertionError("scale_prog is None: the reference's cicd forward reaches only all-zero / all-one masks "
+                             "(conditional_single_decoder.py:163, mask_layer.py:74,98)")
+
+    def _merge(self, ctx, y_hat, y_hat_p):
+        if self.joiner_policy == "residual":
+            return super()._merge(ctx, y_hat, y_hat_p)
+        if self.joiner_policy in ("concatenation", "cac"):
+            return y_hat
+        from ..layers.conv import emit_grouped
+        B, h, w, M, sc_ = y_hat.B, y_hat.H, y_hat.W, self.M, self.slice_channels
+        f32 = torch.float32
+        bf16 = ctx.precision == "bf16"
+        stacks = [[m for m in seq if hasattr(m, "weight")] for seq in self.joiner]
+        a = ctx.prog.copy(y_hat, ctx.buf(B, h, w, M)) if bf16 else y_hat      # A operands of the joiner's first conv
+        b = ctx.prog.copy(y_hat_p, ctx.buf(B, h, w, M)) if bf16 else y_hat_p
+        out = ctx.buf(B, h, w, M, f32)
+        if bf16:
+            # all ten joiners as grouped launches; conv(cat(main_i, prog_i); W) = conv(main_i; W[:, :32]) + conv(prog_i; W[:, 32:])
+            first = [cs[0] for cs in stacks]
+            part = emit_grouped(ctx, self, "join0a", first, a.channels(0, sc_), sc_, cols=(0, sc_), bias=False, out_dtype=f32)
+            t = emit_grouped(ctx, self, "join0b", first, b.channels(0, sc_), sc_, cols=(sc_, 2 * sc_), res=part, gelu=True)
+            t = emit_grouped(ctx, self, "join1", [cs[1] for cs in stacks], t.channels(0, 64), 64, gelu=True)
+            emit_grouped(ctx, self, "join2", [cs[2] for cs in stacks], t.channels(0, 64), 64, out=out)
+            return out
+        for i, cs in enumerate(stacks):
+            part = emit_grouped(ctx, self, ("join0a", i), [cs[0]], a.channels(sc_ * i, sc_), 0, cols=(0, sc_), bias=False, out_dtype=f32)
+            t = emit_grouped(ctx, self, ("join0b", i), [cs[0]], b.channels(sc_ * i, sc_), 0, cols=(sc_, 2 * sc_), res=part, gelu=True)
+            t = cs[1].emit(ctx, t, gelu=True)
+            cs[2].emit(ctx, t, out=out.channels(sc_ * i, sc_))
+        return out

@@ -27,6 +27,8 @@ CASES = {
     "icd_nested": ("icd", dict(lambda_list=[0.0035, 0.01, 0.02, 0.065], mask_policy="learnable-mask-nested", lrp_prog=True,
                                independent_lrp=True), [0.01, 0.02], (1, 64, 64)),  # (pr = levels-1 indexes past mask_conv in the reference)
     "icd_nolrp": ("icd", dict(lambda_list=[0.0035, 0.065], mask_policy="two-levels", lrp_prog=False), [0.065], (1, 64, 64)),
+    "cicd_two": ("cicd", dict(lambda_list=[0.0035, 0.065], mask_policy="two-levels", lrp_prog=True, joiner_policy="conditional"),
+                 None, (1, 64, 64)),
 }
 GAINS = ((r"^g_(a|s|a_progressive)\.", 0.7071), (r"^g_a(_progressive)?\.7\.weight$", 2.5), (r"^h_a(_prog)?\.8\.weight$", 3.0),
                               (r"^h_(mean|scale)_s(_prog)?\.8\.weight$", 1.5), (r"^cc_scale_transforms(_prog)?\.\d\.8\.weight$", 1.5),
@@ -48,12 +50,14 @@ def case_state_dict(ref_sd):
     return out
 
 
-def main():
+def main(only=None):
     import resdsic_b200
     torch.set_num_threads(8)
     ref_shim.install()
     from compress.models import models as RM
     for name, (key, kw, quality, (B, H, W)) in CASES.items():
+        if only and name not in only:
+            continue
         torch.manual_seed(0)
         net = RM[key](N=192, M=320, **kw).eval()
         torch.manual_seed(0)
@@ -80,4 +84,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1:])

@@ -1,4 +1,4 @@
-"""ResDSIC scalable models (`-m icd` / `-m imd`, reference models/WACNN/scalable/*.py +
+"""ResDSIC scalable models (`-m icd` / `-m imd` / `-m cicd`, reference models/WACNN/scalable/*.py +
 layers/mask_layer.py) against goldens produced by the UNMODIFIED reference (tests/golden/make_golden_scalable.py).
 
 CPU: registry / constructor contract, the oracle restatement and the host-side program (run by the descriptor
@@ -63,6 +63,13 @@ def test_registry_and_constructor_contract():
     assert tuple(g.masking.gamma.shape) == (1, 320) and tuple(g.masking.mask_conv[0].weight.shape) == (320, 640, 1, 1)
     with pytest.raises(NotImplementedError):
         resdsic_b200.models["icd"](lambda_list=[1, 2, 3], mask_policy="point-based-std").masking.kind(1)
+    # cicd (conditional_single_decoder.py): the per-slice joiner stacks; like the reference, its default arguments do not construct
+    class Cc:
+        model, N, M, mask_policy, lambda_list, joiner_policy = "cicd", 192, 320, "two-levels", [0.0035, 0.065], "conditional"
+    c = resdsic_b200.configure_model(Cc)
+    assert isinstance(c, resdsic_b200.models["icd"]) and len(c.joiner) == 10 and tuple(c.joiner[3][4].weight.shape) == (32, 64, 3, 3)
+    with pytest.raises(RuntimeError):
+        resdsic_b200.models["cicd"]()
     with pytest.raises(RuntimeError, match="CUDA"):
         m.eval()(torch.zeros(1, 3, 64, 64))
 
@@ -74,7 +81,8 @@ def test_oracle_reproduces_reference(name):
     assert list(g["qualities"]) == qs
     key, kw = CASES[name][0], CASES[name][1]
     o = SO.forward(sd, x, qs, kw["mask_policy"], len(kw["lambda_list"]), lrp_prog=kw.get("lrp_prog", True),
-                   independent_lrp=kw.get("independent_lrp", False), multiple_decoder=key == "imd")
+                   independent_lrp=kw.get("independent_lrp", False), multiple_decoder=key == "imd",
+                   joiner_policy=kw.get("joiner_policy"))
     B = x.shape[0]
     got = dict(x_hat=o["x_hat"].numpy(), y=o["y"].numpy(), z_hat=o["z_hat"].numpy(), z_hat_prog=o["z_hat_prog"].numpy(),
                lik_z=o["likelihoods"]["z"].numpy(), lik_z_prog=o["likelihoods"]["z_prog"].numpy(),
@@ -100,7 +108,8 @@ def test_host_program_reproduces_reference(name):
     table = weights.scale_table()
     key, kw = CASES[name][0], CASES[name][1]
     o = SO.forward(sd, x, qs[-1:], kw["mask_policy"], len(kw["lambda_list"]), lrp_prog=kw.get("lrp_prog", True),
-                   independent_lrp=kw.get("independent_lrp", False), multiple_decoder=key == "imd", table=table)
+                   independent_lrp=kw.get("independent_lrp", False), multiple_decoder=key == "imd", table=table,
+                   joiner_policy=kw.get("joiner_policy"))
     ps = m._build_scalable(B, H, W, "cpu", tuple(qs[-1:]), True, build_only=True)
     ps.x.copy_(x)
     run_on_cpu(ps.prog)

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define RDSIC_ABI_VERSION 7
+#define RDSIC_ABI_VERSION 8
 
 typedef void* rdsic_stream_t; /* cudaStream_t */
 
@@ -176,7 +176,9 @@ typedef struct rdsic_gc_desc {
   int32_t n_table;
   int32_t B, h, w, Cs, Ctot, lik_coff;
   float scale_bound, lik_bound;
-  int32_t pad_;
+  /* ResDSIC `cimd` (scalable/conditional_multiple_decoder.py:210): when non-zero the conditional is evaluated with
+   * scale * mask + scale_eps (the reference adds 1e-7 to the masked scale before the likelihood); 0 = off. */
+  float scale_eps;
   /* Training mode (GaussianConditional.forward with quantize "noise", entropy_models.py:131-137,
    * 646-661): with noise.ptr != NULL, lik is evaluated at |y + noise - mu|; y_hat / symbols keep
    * the ste_round value (cnn.py:177); noisy_out (optional) receives y + noise. */

@@ -1,6 +1,8 @@
 """TEST INFRASTRUCTURE -- CPU restatement (torch fp32, functional) of the ResDSIC scalable models' forward
 (reference models/WACNN/scalable/single_decoder.py:343-504 `scalable_icd`, multiple_decoder.py:116-250
-`scalable_imd`) and of `Mask.forward` + eval-mode `apply_noise` (layers/mask_layer.py:32-113).  Not product code.
+`scalable_imd`, conditional_single_decoder.py:109-271 `conditional_scalable_icd`, conditional_multiple_decoder.py:
+104-268 `conditional_scalable_imd`, independent.py:289-461 `ResWACNNIndependentEntropy`) and of `Mask.forward` +
+eval-mode `apply_noise` (layers/mask_layer.py:32-113).  Not product code.
 Pinned against the unmodified reference by tests/golden/scalable_*.npz (tests/golden/make_golden_scalable.py).
 """
 import torch
@@ -67,12 +69,17 @@ def mask(policy, levels, scale, scale_prog, pr, sd, p="masking"):
 
 @torch.no_grad()
 def forward(sd, x, qualities, policy, levels, lrp_prog=True, independent_lrp=False, multiple_decoder=False, table=None,
-            joiner_policy=None):
+            joiner_policy=None, variant=None):
     """scalable_icd.forward / scalable_imd.forward for a list of quality INDICES.  With `table` also returns the
     int32 symbols / indexes of both streams for the LAST quality (what compress hands the coder).
     `joiner_policy` (not None): conditional_scalable_icd.forward (conditional_single_decoder.py:112-271) -- the mask is
     computed without the progressive scales (:163), the progressive likelihood is taken at the UNMASKED scale (:221) and
-    the two reconstructions of a slice are merged by `merge` (:103-113)."""
+    the two reconstructions of a slice are merged by `merge` (:103-113).
+    `variant="cimd"`: conditional_scalable_imd.forward -- the mask IS computed from both scales
+    (conditional_multiple_decoder.py:158), the progressive likelihood is taken at scale * mask + 1e-7 (:210; compress,
+    inherited from `icd`, indexes scale * mask) and there are two decoders (:236).
+    `variant="ind"`: ResWACNNIndependentEntropy.forward -- the mask of extract_mask is never applied
+    (independent.py:318-392), i.e. an all-ones mask for every quality != 0."""
     B, _, H, W = x.shape
     y_base, y = g_a_split(x, sd)
     y = O.attention_block(y, sd, "g_a.8", 4, 2)
@@ -88,7 +95,10 @@ def forward(sd, x, qualities, policy, levels, lrp_prog=True, independent_lrp=Fal
     for q in qualities:
         y_hat_q = base["y_hat"]
         if q != 0:
-            m = mask(policy, levels, lat_s, lat_sp if joiner_policy is None else None, q, sd)
+            if variant == "ind":
+                m = torch.ones_like(lat_s)
+            else:
+                m = mask(policy, levels, lat_s, lat_sp if (joiner_policy is None or variant == "cimd") else None, q, sd)
             masks[q] = m
             ys, ms = y_prog.chunk(10, 1), m.chunk(10, 1)
             hat, lk, syms, idxs = [], [], [], []
@@ -97,10 +107,11 @@ def forward(sd, x, qualities, policy, levels, lrp_prog=True, independent_lrp=Fal
                 mean_sup = torch.cat([lat_mp] + sup, 1)
                 mu = O.cc_stack(mean_sup, sd, f"cc_mean_transforms_prog.{i}")[:, :, :hh, :ww]
                 sc = O.cc_stack(torch.cat([lat_sp] + sup, 1), sd, f"cc_scale_transforms_prog.{i}")[:, :, :hh, :ww]
-                if joiner_policy is None:
+                if joiner_policy is None or variant == "cimd":
                     sc = sc * ms[i]
                 r = torch.round(ys[i] - mu)
-                lk.append(O.gaussian_likelihood(r + mu, sc, mu))  # gaussian_conditional_prog(y, scale*mask, mu), :447
+                sc_lik = sc + 1e-7 if variant == "cimd" else sc
+                lk.append(O.gaussian_likelihood(r + mu, sc_lik, mu))  # gaussian_conditional_prog(y, scale*mask, mu), :447
                 yh = r * ms[i] + mu  # :451
                 if table is not None:
                     syms.append((r * ms[i]).to(torch.int32))

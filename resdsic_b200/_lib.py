@@ -62,7 +62,7 @@ class GCDesc(C.Structure):
         ("n_table", C.c_int32),
         ("B", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("Cs", C.c_int32), ("Ctot", C.c_int32),
         ("lik_coff", C.c_int32), ("scale_bound", C.c_float), ("lik_bound", C.c_float),
-        ("pad_", C.c_int32), ("noise", View), ("noisy_out", View), ("sym_in", C.c_void_p), ("mask", View),
+        ("scale_eps", C.c_float), ("noise", View), ("noisy_out", View), ("sym_in", C.c_void_p), ("mask", View),
     ]
 
 
@@ -175,7 +175,7 @@ def lib():
                      ("rdsic_rate_workspace_doubles", [C.c_int])):
         getattr(L, fn).argtypes = args
         getattr(L, fn).restype = C.c_int
-    if L.rdsic_abi_version() != 7:
+    if L.rdsic_abi_version() != 8:
         raise RuntimeError("resdsic_b200: ABI version mismatch between the python host and the CUDA library")
     for what, T in enumerate((Op, ConvDesc, AttnDesc, EBDesc, GCDesc, CopyDesc, View, LNDesc, PatchDesc, MaskDesc)):
         if L.rdsic_sizeof(what) != C.sizeof(T):

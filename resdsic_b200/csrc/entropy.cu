@@ -109,6 +109,7 @@ __device__ __forceinline__ GcOut gc_element(const rdsic_gc_desc& d, const float*
                                             float msk, float noise, bool has_mask, bool has_noise, bool from_sym, float r_in) {
   GcOut o;
   if (has_mask) sc = __fmul_rn(sc, msk);  // ResDSIC progressive stream: scale * mask, rint(y - mu) * mask + mu
+  if (d.scale_eps != 0.f) sc = __fadd_rn(sc, d.scale_eps);  // cimd: scale * mask + 1e-7
   const float r = from_sym ? r_in : rintf(__fsub_rn(y, mu));
   const float rm = has_mask ? __fmul_rn(r, msk) : r;
   o.yh = __fadd_rn(rm, mu);

@@ -371,13 +371,15 @@ class GaussianConditional(EntropyModel):
         return self._packed(("table", str(device)), (t,), lambda: t.detach().float().to(device).contiguous())
 
     def emit(self, ctx: Ctx, y, scale, mu, lik, lik_coff, Ctot, y_hat_dsts=(), symbols=None, indexes=None, noise=None,
-             noisy_out=None, sym_in=None, mask=None):
+             noisy_out=None, sym_in=None, mask=None, scale_eps=0.0):
         """`noise` (fp32 view like y) selects the training-mode likelihood at y + noise (entropy_models.py:646-661);
         the y_hat destinations keep the ste_round value (cnn.py:177).  `mask` (fp32 view like y): the ResDSIC
-        progressive stream (scalable/single_decoder.py:447-453)."""
+        progressive stream (scalable/single_decoder.py:447-453); `scale_eps`: added to scale * mask before the
+        likelihood (`cimd`, scalable/conditional_multiple_decoder.py:210)."""
         ctx.prog.gc(y, mu, scale, list(y_hat_dsts), lik, lik_coff, Ctot, self.table(ctx.device), symbols=symbols,
                     indexes=indexes, scale_bound=self.scale_bound_value,
-                    lik_bound=self.likelihood_bound, noise=noise, noisy_out=noisy_out, sym_in=sym_in, mask=mask)
+                    lik_bound=self.likelihood_bound, noise=noise, noisy_out=noisy_out, sym_in=sym_in, mask=mask,
+                    scale_eps=scale_eps)
 
     def _run(self, inputs, scales, means, want, noise=None):
         B, Cn, H, W = inputs.shape

@@ -1,5 +1,6 @@
-"""ResDSIC scalable codecs: the reference's `-m icd` / `-m imd` models
-(models/WACNN/scalable/single_decoder.py:25-504, multiple_decoder.py:19-250) on the B200 kernel library.
+"""ResDSIC scalable codecs: the reference's `-m icd` / `-m imd` / `-m cicd` / `-m cimd` / `-m ind`
+models (models/WACNN/scalable/single_decoder.py:25-504, multiple_decoder.py:19-250, conditional_single_decoder.py,
+conditional_multiple_decoder.py, shared.py + independent.py) on the B200 kernel library.
 
 A base stream (the WACNN of models/wacnn.py) plus a PROGRESSIVE stream: a second analysis transform on
 `cat(reshape(y_base), x)` (:226-230,357-358), a second hyperprior and context stack, and per quality level an
@@ -29,6 +30,8 @@ class scalable_icd(WACNN):
     """reference scalable/single_decoder.py:25 (registry key "icd")."""
 
     train_forward_impl = None  # no differentiable training forward for this model: train() gives forward values only
+    prog_scale_eps = 0.0       # added to scale_prog * mask before the progressive likelihood (`cimd` only)
+    returns_y = True           # forward()'s dict carries "y" (every variant but `cimd`)
 
     def __init__(self, N=192, M=320, mask_policy="learnable-mask-gamma", lambda_list=(0.05,), lrp_prog=True,
                  independent_lrp=False, **kwargs):
@@ -95,6 +98,10 @@ class scalable_icd(WACNN):
     def _synthesis(self, q):
         return self.g_s
 
+    def _mask_kind(self, q):
+        """ZEROS / ONES for the constant masks, None for a computed one."""
+        return self.masking.kind(q)
+
     def _computed_mask(self, ctx, lat_s, lat_sp, q, cache):
         """Importance mask of a quality level whose mask is neither all zeros nor all ones (:397-401)."""
         return self.masking.emit(ctx, lat_s, lat_sp, q, cache)
@@ -110,8 +117,11 @@ class scalable_icd(WACNN):
         "y_prog": [Qp,B,M,h,w] (ones if no level uses the progressive stream)}, "y": [Q,B,M,h,w], "z_hat_prog", "z_hat"}."""
         p = self._execute_scalable(x, self.define_quality(quality), False)
         o = self._out
-        return {"x_hat": o(p.x_hat), "likelihoods": {"y": o(p.lik_y), "z": o(p.lik_z), "z_prog": o(p.lik_z_prog), "y_prog": o(p.lik_y_prog)},
-                "y": o(p.y_hat_q), "z_hat_prog": o(p.z_hat_prog), "z_hat": o(p.z_hat_out)}
+        r = {"x_hat": o(p.x_hat), "likelihoods": {"y": o(p.lik_y), "z": o(p.lik_z), "z_prog": o(p.lik_z_prog), "y_prog": o(p.lik_y_prog)},
+             "y": o(p.y_hat_q), "z_hat_prog": o(p.z_hat_prog), "z_hat": o(p.z_hat_out)}
+        if not self.returns_y:
+            del r["y"]
+        return r
 
     @torch.no_grad()
     def symbols_and_indexes(self, x, quality=0):
@@ -216,7 +226,7 @@ class scalable_icd(WACNN):
         for j, q in enumerate(qs):
             y_hat_q = y_hat
             if q != 0:
-                kind = self.masking.kind(q)
+                kind = self._mask_kind(q)
                 assert kind != ZEROS
                 mask = None if kind == ONES else self._computed_mask(ctx, lat_s, lat_sp, q, mask_cache)
                 p.masks[q] = mask
@@ -228,7 +238,9 @@ class scalable_icd(WACNN):
                     prog.copy(scales_p.channels(0, M), sq.channels(0, M))
                 first = False
                 y_hat_p = self._emit_slice_loop(ctx, fam_p, pre_p, self.gaussian_conditional_prog, y_prog, mq, sq,
-                                                p.lik_y_prog[jp], p.prog_symbols, p.prog_indexes, mask=mask, lrp=self.lrp_prog)
+                                                p.lik_y_prog[jp], p.prog_symbols, p.prog_indexes, mask=mask, lrp=self.lrp_prog,
+                                                # compress() (single_decoder.py:583, inherited by every variant) indexes scale * mask
+                                                scale_eps=0.0 if with_symbols else self.prog_scale_eps)
                 jp += 1
                 y_hat_q = self._merge(ctx, y_hat, y_hat_p)
             prog.copy(y_hat_q, TV.nchw_of(p.y_hat_q[j]))
@@ -317,3 +329,113 @@ class conditional_scalable_icd(scalable_icd):
             t = cs[1].emit(ctx, t, gelu=True)
             cs[2].emit(ctx, t, out=out.channels(sc_ * i, sc_))
         return out
+
+
+def _synthesis_pair(M, N):
+    """Base / enhancement decoder pair (multiple_decoder.py:36-50)."""
+    return nn.ModuleList(
+        Sequential(
+            Win_noShift_Attention(dim=M, num_heads=8, window_size=4, shift_size=2),
+            deconv(M, N, kernel_size=5, stride=2), GDN(N, inverse=True),
+            deconv(N, N, kernel_size=5, stride=2), GDN(N, inverse=True),
+            Win_noShift_Attention(dim=N, num_heads=8, window_size=8, shift_size=4),
+            deconv(N, N, kernel_size=5, stride=2), GDN(N, inverse=True),
+            deconv(N, 3, kernel_size=5, stride=2)) for _ in range(2))
+
+
+class conditional_scalable_imd(conditional_scalable_icd):
+    """reference scalable/conditional_multiple_decoder.py:20 (registry key "cimd"): `cicd` with a base / enhancement
+    decoder pair (:43-55,236).  Unlike `cicd`, its forward hands the progressive scales to `Mask.forward` (:158), so the
+    computed masks of the learnable policies ARE reachable; the progressive likelihood is taken at
+    `scale_prog * mask + 1e-7` (:210) and the forward dictionary has no "y" entry (:262-267).  compress() is `icd`'s
+    (inherited in the reference), so `symbols_and_indexes` indexes `scale_prog * mask` without the 1e-7.
+    `joiner_policy="concatenation"` (a 2M-wide enhancement decoder fed with cat(base, progressive), :41,230) is not
+    provided."""
+
+    prog_scale_eps = 1e-7
+    returns_y = False
+
+    def __init__(self, N=192, M=320, mask_policy="learnable-mask", lambda_list=(0.05,), lrp_prog=True,
+                 independent_lrp=False, joiner_policy="conditional", **kwargs):
+        if joiner_policy == "concatenation":
+            raise NotImplementedError("cimd with joiner_policy='concatenation' (2M-wide enhancement decoder, "
+                                      "conditional_multiple_decoder.py:41) is not provided")
+        super().__init__(N=N, M=M, mask_policy=mask_policy, lambda_list=lambda_list, lrp_prog=lrp_prog,
+                         independent_lrp=independent_lrp, joiner_policy=joiner_policy, **kwargs)
+        self.g_s = _synthesis_pair(M, N)
+
+    def _synthesis(self, q):
+        return self.g_s[0 if q == 0 else 1]
+
+    def _computed_mask(self, ctx, lat_s, lat_sp, q, cache):
+        return scalable_icd._computed_mask(self, ctx, lat_s, lat_sp, q, cache)
+
+
+class ResWACNNIndependentEntropy(scalable_icd):
+    """reference scalable/shared.py:23 + scalable/independent.py:24 (registry key "ind"): base and progressive streams
+    with independent hyperpriors / context stacks and NO importance mask on the data path -- `extract_mask`
+    (shared.py:191-229) is evaluated by the reference's forward and compress but its result is never applied
+    (independent.py:318-392,545-580: the `block_mask` lines are commented out), so every quality index != 0 sends the
+    whole progressive stream.  Parameters follow the reference's names and construction order (`gamma` / `mask_conv`
+    of the "learnable-mask" policy live on the model itself, shared.py:69-71, and stay unused); `multiple_decoder`
+    selects a base / enhancement decoder pair (independent.py:129-143,438-441)."""
+
+    MASK_POLICIES = ("point-based-std", "learnable-mask", "all-one", "all-zero", "two-levels")
+
+    def __init__(self, N=192, M=320, mask_policy="two-levels", lambda_list=(0.0035, 0.065), lrp_prog=True,
+                 independent_lrp=False, multiple_decoder=False, **kwargs):
+        WACNN.__init__(self, N=N, M=M, **kwargs)
+        assert lambda_list is not None
+        self.halve, self.level = 8, 5
+        self.factor = self.halve ** 2
+        assert N % self.factor == 0
+        self.T = N // self.factor + 3
+        self.mask_policy = mask_policy
+        self.scalable_levels = len(lambda_list)
+        self.lmbda_list = list(lambda_list)
+        self.lmbda_index_list = dict(zip(self.lmbda_list, range(len(self.lmbda_list))))
+        # ---- shared.py:54-71 (the constructor draws the reference's init stream in the reference's order)
+        self.entropy_bottleneck = EntropyBottleneck(N)
+        self.entropy_bottleneck_prog = EntropyBottleneck(N)
+        self.gaussian_conditional = GaussianConditional(None)
+        self.gaussian_conditional_prog = GaussianConditional(None)
+        self.g_a_progressive = Sequential(
+            conv(self.T, N, kernel_size=5, stride=2), GDN(N),
+            conv(N, N, kernel_size=5, stride=2), GDN(N),
+            Win_noShift_Attention(dim=N, num_heads=8, window_size=8, shift_size=4),
+            conv(N, N, kernel_size=5, stride=2), GDN(N),
+            conv(N, M, kernel_size=5, stride=2))
+        if mask_policy == "learnable-mask":
+            self.gamma = nn.Parameter(torch.ones((self.scalable_levels - 1, M)))
+            self.mask_conv = Sequential(conv(M, M, kernel_size=1, stride=1))
+        # ---- independent.py:42-127
+        self.multiple_decoder = multiple_decoder
+        self.h_a_prog = Sequential(conv3x3(320, 320), GELU(), conv3x3(320, 288), GELU(), conv3x3(288, 256, stride=2), GELU(),
+                                   conv3x3(256, 224), GELU(), conv3x3(224, 192, stride=2))
+
+        def h_s():
+            return Sequential(conv3x3(192, 192), GELU(), subpel_conv3x3(192, 224, 2), GELU(), conv3x3(224, 256), GELU(),
+                              subpel_conv3x3(256, 288, 2), GELU(), conv3x3(288, 320))
+
+        self.h_mean_s_prog = h_s()
+        self.h_scale_s_prog = h_s()
+        self.cc_mean_transforms_prog = nn.ModuleList(_cc_stack(320 + 32 * min(i, 5)) for i in range(10))
+        self.cc_scale_transforms_prog = nn.ModuleList(_cc_stack(320 + 32 * min(i, 5)) for i in range(10))
+        self.independent_lrp = independent_lrp
+        if independent_lrp:
+            self.lrp_transforms_prog = nn.ModuleList(_cc_stack(320 + 32 * min(i + 1, 6)) for i in range(10))
+        self.lrp_prog = lrp_prog
+        self.entropy_bottleneck = EntropyBottleneck(N)
+        self.entropy_bottleneck_prog = EntropyBottleneck(N)
+        self.gaussian_conditional = GaussianConditional(None)
+        self.gaussian_conditional_prog = GaussianConditional(None)
+        if multiple_decoder:
+            self.g_s = _synthesis_pair(M, N)
+
+    def _mask_kind(self, q):
+        if self.mask_policy not in self.MASK_POLICIES:
+            raise NotImplementedError(self.mask_policy)  # shared.py:229
+        return ZEROS if q == 0 else ONES
+
+    def _synthesis(self, q):
+        return self.g_s[0 if q == 0 else 1] if self.multiple_decoder else self.g_s

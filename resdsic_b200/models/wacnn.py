@@ -393,13 +393,14 @@ class WACNN(CompressionModel):
         return {"out": pre, "ev": pre_ev}
 
     def _emit_slice_loop(self, ctx, fam, pre, gc, y, means, scales, lik_y, symbols, indexes, noise=None, mask=None,
-                         lrp=True, lik_slice_major=False):
+                         lrp=True, lik_slice_major=False, scale_eps=0.0):
         """The channel-slice context loop (cnn.py:161-187) over the context buffers `means` / `scales`
         ([B,h,w,320 + 6*32]: latents | five support slots | scratch).  `mask` (fp32 [B,h,w,320]) selects the
         ResDSIC progressive-stream arithmetic of the Gaussian conditional (scalable/single_decoder.py:447-453);
         `lrp=False` skips the latent residual prediction (scalable `lrp_prog=False`).  `lik_slice_major`: `lik_y`
         is laid out [num_slices * B, 32, h, w] (slice-major), the shape the scalable models' `torch.cat(..., dim=0)`
-        produces (scalable/single_decoder.py:480); symbols / indexes must then be None.  Returns the fp32 y_hat."""
+        produces (scalable/single_decoder.py:480); symbols / indexes must then be None.  `scale_eps`: see
+        GaussianConditional.emit (`cimd`).  Returns the fp32 y_hat."""
         assert not (lik_slice_major and (symbols is not None or indexes is not None))
         prog = ctx.prog
         B, h, w = y.B, y.H, y.W
@@ -448,7 +449,7 @@ class WACNN(CompressionModel):
                 lik_i, coff_i, ctot = lik_y.view(self.num_slices, B, sc_, h, w)[i], 0, sc_
             gc.emit(ctx, y.channels(sc_ * i, sc_), sc, mu, lik_i, coff_i, ctot, y_hat_dsts=dsts, symbols=symbols,
                     indexes=indexes, noise=noise.channels(sc_ * i, sc_) if noise is not None else None,
-                    mask=mask.channels(sc_ * i, sc_) if mask is not None else None)
+                    mask=mask.channels(sc_ * i, sc_) if mask is not None else None, scale_eps=scale_eps)
             if lrp:
                 stack_split("lrp", i, lrp_buf, sc_ * (k + 1), final=dict(epilogue=_lib.EPI_LRP, res=yh_i, out=yh_i, **extra))
 

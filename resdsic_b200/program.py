@@ -211,8 +211,9 @@ class Program:
         self.keep += [z.t, z_hat.t, lik, params, symbols]
 
     def gc(self, y: TV, mu: TV, scale: TV, y_hat_dsts, lik, lik_coff, Ctot, table, symbols=None, indexes=None,
-           scale_bound=0.11, lik_bound=1e-9, noise: TV = None, noisy_out: TV = None, sym_in=None, mask: TV = None):
+           scale_bound=0.11, lik_bound=1e-9, noise: TV = None, noisy_out: TV = None, sym_in=None, mask: TV = None, scale_eps=0.0):
         d = GCDesc()
+        d.scale_eps = scale_eps
         d.y, d.mu, d.scale = y.view(), mu.view(), scale.view()
         d.mask = mask.view() if mask is not None else _NULL
         if mask is not None:

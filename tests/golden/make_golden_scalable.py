@@ -1,5 +1,6 @@
 """Golden fixtures for the ResDSIC scalable models: run the UNMODIFIED reference
-`scalable_icd` / `scalable_imd` (imported through oracle/ref_shim.py) in eval mode.
+`scalable_icd` / `scalable_imd` / `conditional_scalable_icd` / `conditional_scalable_imd` /
+`ResWACNNIndependentEntropy` (imported through oracle/ref_shim.py) in eval mode.
 
     python tests/golden/make_golden_scalable.py        (build container only)
 
@@ -29,6 +30,15 @@ CASES = {
     "icd_nolrp": ("icd", dict(lambda_list=[0.0035, 0.065], mask_policy="two-levels", lrp_prog=False), [0.065], (1, 64, 64)),
     "cicd_two": ("cicd", dict(lambda_list=[0.0035, 0.065], mask_policy="two-levels", lrp_prog=True, joiner_policy="conditional"),
                  None, (1, 64, 64)),
+    # cimd: computed (learnable) masks ARE reachable, likelihood at scale * mask + 1e-7, two decoders, no "y" output
+    "cimd_gamma": ("cimd", dict(lambda_list=[0.0035, 0.02, 0.065], mask_policy="learnable-mask-gamma", lrp_prog=True,
+                                joiner_policy="conditional"), None, (1, 64, 64)),
+    "cimd_res": ("cimd", dict(lambda_list=[0.0035, 0.065], mask_policy="two-levels", lrp_prog=True, joiner_policy="residual"),
+                 [0.065], (1, 64, 64)),
+    # ind: independent entropy models, no mask on the data path; single decoder / decoder pair + independent LRP
+    "ind_two": ("ind", dict(lambda_list=[0.0035, 0.065], mask_policy="two-levels", lrp_prog=True), None, (1, 64, 64)),
+    "ind_md": ("ind", dict(lambda_list=[0.0035, 0.065], mask_policy="learnable-mask", lrp_prog=True, independent_lrp=True,
+                           multiple_decoder=True), None, (1, 64, 64)),
 }
 GAINS = ((r"^g_(a|s|a_progressive)\.", 0.7071), (r"^g_a(_progressive)?\.7\.weight$", 2.5), (r"^h_a(_prog)?\.8\.weight$", 3.0),
                               (r"^h_(mean|scale)_s(_prog)?\.8\.weight$", 1.5), (r"^cc_scale_transforms(_prog)?\.\d\.8\.weight$", 1.5),
@@ -38,7 +48,8 @@ GAINS = ((r"^g_(a|s|a_progressive)\.", 0.7071), (r"^g_a(_progressive)?\.7\.weigh
 
 def case_state_dict(ref_sd):
     """Hash-seeded weights keyed on the model's own state_dict; GDN parameters keep the reference's init values."""
-    sd = weights.synth_state_dict({k: v for k, v in ref_sd.items() if not k.endswith((".beta", ".gamma"))}, seed=0, gains=GAINS)
+    sd = weights.synth_state_dict({k: v for k, v in ref_sd.items() if not k.endswith((".beta", ".gamma")) and k != "gamma"},
+                                  seed=0, gains=GAINS)
     out = {}
     for k, v in ref_sd.items():
         if k == "masking.gamma":
@@ -72,8 +83,10 @@ def main(only=None):
         with torch.no_grad():
             out = net(x, quality=quality)
         res = {"x_hat": out["x_hat"], "lik_y": out["likelihoods"]["y"], "lik_z": out["likelihoods"]["z"],
-               "lik_z_prog": out["likelihoods"]["z_prog"], "lik_y_prog": out["likelihoods"]["y_prog"], "y": out["y"],
+               "lik_z_prog": out["likelihoods"]["z_prog"], "lik_y_prog": out["likelihoods"]["y_prog"],
                "z_hat": out["z_hat"], "z_hat_prog": out["z_hat_prog"]}
+        if "y" in out:  # (cimd's forward does not return it)
+            res["y"] = out["y"]
         res = {k: v.detach().numpy() for k, v in res.items()}
         qs = [net.lmbda_index_list[q] for q in (quality if quality is not None else net.lmbda_list)]
         res["qualities"] = np.array(qs)

@@ -182,6 +182,8 @@ class Sim:
             m = self._nhwc(d.mask, d.B, d.h, d.w, d.Cs).float()
             sc = sc * m
             rm = r * m
+        if d.scale_eps != 0.0:  # cimd: scale * mask + 1e-7
+            sc = sc + torch.tensor(d.scale_eps, dtype=torch.float32)
         yh = rm + mu
         yl = r + mu
         if d.noise.ptr:  # training mode: likelihood at y + noise

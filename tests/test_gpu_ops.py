@@ -32,7 +32,7 @@ def gold():
 def test_library_loaded_is_in_tree():
     L = resdsic_b200._lib.lib()
     assert os.path.realpath(resdsic_b200._lib.LIB_PATH).startswith(os.path.realpath(os.path.dirname(resdsic_b200.__file__)))
-    assert L.rdsic_abi_version() == 7
+    assert L.rdsic_abi_version() == 8
 
 
 def test_gaussian_conditional_bit_exact_integers(model, gold, scale_table):

@@ -3,8 +3,10 @@
 // Same contract as attn_f32.cu (reference layers/win_attention.py:94-112,159-200): roll, window partition /
 // reverse are addressing; (q*scale) k^T + relative-position bias + shift mask (-100), softmax, @ v.
 //
-// One CTA = one window, one warp = one head.  The window's q|k|v rows are staged once in shared memory with
-// 128-bit coalesced loads (each token's 3C channels are contiguous in the qkv GEMM output).  Per 16-row
+// One CTA = one window x one GROUP of heads (hpc heads per CTA, blockDim = 32 * hpc), one warp = one head.  The
+// group's q|k|v columns of the window's tokens are staged once in shared memory with 128-bit coalesced loads (three
+// contiguous hpc*DH-channel chunks per token of the qkv GEMM output).  hpc = all heads unless the window would not
+// fit in shared memory (see heads_per_cta: splitting for occupancy was measured slower).  Per 16-row
 // block of queries:  S = Q K^T with mma.sync m16n8k16 (+ one m16n8k8 for the d mod 16 = 8 tail: d = 24 / 40),
 // softmax on the accumulator fragments (quad shuffles), then the probabilities are re-used *in registers*
 // as the A operand of P V (the accumulator layout of two n8 tiles is exactly one k16 A fragment);
@@ -47,14 +49,16 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// WS: window side (8 or 4); DH: head dim (multiple of 8); one warp per head (blockDim = 32 * heads).
+// WS: window side (8 or 4); DH: head dim (multiple of 8); one warp per head; `hpc` heads per CTA (blockDim = 32 * hpc,
+// gridDim = windows * heads / hpc, the head groups of a window in neighbouring CTAs).
 template <int WS, int DH>
-__global__ void __launch_bounds__(768) win_attn_tc_kernel(const rdsic_attn_desc d) {
+__global__ void __launch_bounds__(768) win_attn_tc_kernel(const rdsic_attn_desc d, const int hpc) {
   pdl_trigger();
   pdl_wait();
   constexpr int NTOK = WS * WS;
-  const int HEADS = d.heads, C = HEADS * DH, LD = 3 * C + 8;  // +8 bf16: conflict-free fragment loads
+  const int HEADS = hpc, C = d.heads * DH, CG = HEADS * DH, LD = 3 * CG + 8;  // +8 bf16: conflict-free fragment loads
   const int NTHR = 32 * HEADS;
+  const int groups = d.heads / hpc;
   constexpr int RB = NTOK / 16;      // 16-row query blocks
   constexpr int NT_S = NTOK / 8;     // n8 tiles of S (keys)
   constexpr int KS_PV = NTOK / 16;   // k16 steps of P V
@@ -69,23 +73,24 @@ __global__ void __launch_bounds__(768) win_attn_tc_kernel(const rdsic_attn_desc 
   int* rid = (int*)(tab + HEADS * TWD * TWD);                 // [NTOK] shift-mask region id
 
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
-  int win = blockIdx.x;
+  int win = blockIdx.x / groups;
+  const int head0 = (blockIdx.x % groups) * hpc;  // first head of this CTA's group
   const int nWw = d.W / WS, nWh = d.H / WS;
   const int ww = win % nWw;
   win /= nWw;
   const int wh = win % nWh, b = win / nWh;
 
-  if (tid < NTOK) {
-    const int hy = wh * WS + tid / WS, wx = ww * WS + tid % WS;  // shifted-frame position of token tid
+  for (int tk = tid; tk < NTOK; tk += NTHR) {
+    const int hy = wh * WS + tk / WS, wx = ww * WS + tk % WS;  // shifted-frame position of token tk
     const int oy = (hy + d.shift) % d.H, ox = (wx + d.shift) % d.W;
-    pixs[tid] = ((size_t)b * d.H + oy) * d.W + ox;
+    pixs[tk] = ((size_t)b * d.H + oy) * d.W + ox;
     const int rh = (hy >= d.H - WS) + (hy >= d.H - d.shift), rw = (wx >= d.W - WS) + (wx >= d.W - d.shift);
-    rid[tid] = d.shift > 0 ? 3 * rh + rw : 0;
+    rid[tk] = d.shift > 0 ? 3 * rh + rw : 0;
   }
   __syncthreads();
   {
-    const int VPT = 3 * C / 8;  // 16-byte vectors per token
-    const __nv_bfloat16* src = (const __nv_bfloat16*)d.qkv.ptr;
+    const int VPC = CG / 8;  // 16-byte vectors per token and q / k / v chunk
+    const __nv_bfloat16* src = (const __nv_bfloat16*)d.qkv.ptr + head0 * DH;
     // asynchronous 16-byte copies: all of a thread's ~18 loads are in flight at once (a plain load/store
     // loop serialised them -- ~1 us of DRAM latency each -- and made the staging 80 % of the kernel's time)
     // (token per warp, vector per lane: no integer division in the loop -- the e / VPT form of the first version
@@ -93,14 +98,18 @@ __global__ void __launch_bounds__(768) win_attn_tc_kernel(const rdsic_attn_desc 
     for (int tok = warp; tok < NTOK; tok += HEADS) {
       const __nv_bfloat16* row = src + pixs[tok] * (size_t)d.qkv.ld + d.qkv.coff;
       const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(qkv + tok * LD);
-      for (int v = lane; v < VPT; v += 32)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 16u * (uint32_t)v), "l"(row + v * 8) : "memory");
+#pragma unroll
+      for (int part = 0; part < 3; ++part)
+        for (int v = lane; v < VPC; v += 32)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 16u * (uint32_t)(part * VPC + v)),
+                       "l"(row + part * C + v * 8)
+                       : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     // the relative-position-bias table (L2-resident gather) is fetched while the window's copies are in flight
     // (pre-multiplied by log2(e): the softmax below runs in base 2 -- one FMUL per score less than __expf)
     for (int e = tid; e < HEADS * TWD * TWD; e += NTHR)
-      tab[e] = d.bias_table[(e % (TWD * TWD)) * HEADS + e / (TWD * TWD)] * 1.4426950408889634f;
+      tab[e] = d.bias_table[(e % (TWD * TWD)) * d.heads + head0 + e / (TWD * TWD)] * 1.4426950408889634f;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
@@ -109,8 +118,8 @@ __global__ void __launch_bounds__(768) win_attn_tc_kernel(const rdsic_attn_desc 
   const int g = lane / 4, t = lane % 4;
   const bool masked = d.shift > 0 && (wh == nWh - 1 || ww == nWw - 1);  // any token of this window in a wrapped region
   const __nv_bfloat16* Q = qkv + head * DH;
-  const __nv_bfloat16* K = qkv + C + head * DH;
-  const __nv_bfloat16* V = qkv + 2 * C + head * DH;
+  const __nv_bfloat16* K = qkv + CG + head * DH;
+  const __nv_bfloat16* V = qkv + 2 * CG + head * DH;
   const float* tb = tab + head * TWD * TWD;
 
 #pragma unroll 1
@@ -212,8 +221,8 @@ __global__ void __launch_bounds__(768) win_attn_tc_kernel(const rdsic_attn_desc 
   }
   __syncthreads();
   {
-    const int VPT = C / 8;
-    __nv_bfloat16* dst = (__nv_bfloat16*)d.out.ptr;
+    const int VPT = CG / 8;
+    __nv_bfloat16* dst = (__nv_bfloat16*)d.out.ptr + head0 * DH;
     for (int tok = warp; tok < NTOK; tok += HEADS) {
       __nv_bfloat16* row = dst + pixs[tok] * (size_t)d.out.ld + d.out.coff;
       for (int v = lane; v < VPT; v += 32)
@@ -222,18 +231,35 @@ __global__ void __launch_bounds__(768) win_attn_tc_kernel(const rdsic_attn_desc 
   }
 }
 
+// heads per CTA: the whole window in one CTA unless its staging buffer would not fit an SM's shared memory (then the
+// heads are split over neighbouring CTAs).  MEASURED (tests/gpu_attn_bench.py, batch 24 x 128 x 192 x C192, w8): 8 heads
+// per CTA 385 us, 4 -> 440 us, 2 -> 654 us, 1 -> 1200 us: the kernel is instruction-issue bound (ncu: 69 % of the issue
+// slots), and the per-token staging / write-back instructions do not shrink with the group while the CTA count grows --
+// more resident CTAs buy nothing.  RDSIC_ATTN_HPC (read once) overrides for such A/B measurements.
+int heads_per_cta(int heads, int dh, int ntok) {
+  static const int forced = [] {
+    const char* e = getenv("RDSIC_ATTN_HPC");
+    return e ? atoi(e) : 0;
+  }();
+  if (forced > 0 && heads % forced == 0 && (forced * dh) % 8 == 0) return forced;
+  int hpc = heads;
+  while (hpc % 2 == 0 && ((hpc / 2) * dh) % 8 == 0 && (size_t)ntok * (3 * hpc * dh + 8) * 2 > 200 * 1024) hpc /= 2;
+  return hpc;
+}
+
 template <int WS, int DH>
 int launch_tc(const rdsic_attn_desc* d, cudaStream_t stream) {
   constexpr int NTOK = WS * WS, TWD = 2 * WS - 1;
-  const int C = d->heads * DH, LD = 3 * C + 8;
-  const size_t smem = (size_t)NTOK * LD * 2 + (size_t)d->heads * TWD * TWD * 4 + NTOK * 4 + NTOK * 8 + 16;
+  const int hpc = heads_per_cta(d->heads, DH, NTOK);
+  const int LD = 3 * hpc * DH + 8;
+  const size_t smem = (size_t)NTOK * LD * 2 + (size_t)hpc * TWD * TWD * 4 + NTOK * 4 + NTOK * 8 + 16;
   auto kern = win_attn_tc_kernel<WS, DH>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  const int nblk = d->B * (d->H / WS) * (d->W / WS);
-  return rdsic_launch(kern, dim3((unsigned)nblk), 32 * d->heads, smem, stream, false, *d);
+  const int nblk = d->B * (d->H / WS) * (d->W / WS) * (d->heads / hpc);
+  return rdsic_launch(kern, dim3((unsigned)nblk), 32 * hpc, smem, stream, false, *d, hpc);
 }
 
 }  // namespace

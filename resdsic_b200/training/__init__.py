@@ -9,7 +9,7 @@
 (reference training/step.py:42-56).  Multi-GPU: one process per GPU + `GradBucketReducer` (ddp.py).
 """
 from .ddp import GradBucketReducer
-from .loss import RateDistortionLoss
+from .loss import RateDistortionLoss, ScalableRateDistortionLoss
 from .model import aux_loss, train_forward
 
-__all__ = ["train_forward", "aux_loss", "RateDistortionLoss", "GradBucketReducer"]
+__all__ = ["train_forward", "aux_loss", "RateDistortionLoss", "ScalableRateDistortionLoss", "GradBucketReducer"]

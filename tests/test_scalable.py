@@ -170,3 +170,52 @@ def test_cuda_forward_vs_reference_golden(name, prec):
     assert r["y_symbols"].dtype == torch.int32 and int(r["y_indexes"].max()) <= 63
     if qs[-1] != 0:
         assert r["y_prog_symbols"].shape == r["y_symbols"].shape and int(r["y_prog_indexes"].min()) >= 0
+
+
+# ----------------------------------------------------------------------------- ScalableRateDistortionLoss
+def _loss_formula(t, x, lmbda, weight=255 ** 2):
+    """training/loss.py:33-89 restated in fp64 (checker of the golden and of the device criterion)."""
+    import math
+    B, _, H, W = x.shape
+    den = -math.log(2) * B * H * W
+    L = t["x_hat"].shape[0]
+    mse = ((x.double().unsqueeze(0) - t["x_hat"].double()) ** 2).mean(dim=(1, 2, 3, 4))
+    b = {k: torch.log(t[k].double()).sum() / den for k in ("lik_y", "lik_z", "lik_z_prog", "lik_y_prog")}
+    bpp = b["lik_y_prog"] + b["lik_z_prog"] + L * (b["lik_y"] + b["lik_z"])
+    return dict(mse_loss=mse, bpp_loss=bpp, loss=bpp + weight * (torch.tensor(lmbda, dtype=torch.float64) * mse).mean())
+
+
+def test_scalable_loss_golden_is_the_reference_formula():
+    from tests.golden.make_golden_scalable_loss import LMBDA, load_case
+    g = np.load(os.path.join(GOLDEN, "scalable_loss.npz"))
+    t, x = load_case()
+    f = _loss_formula(t, x, LMBDA)
+    for k in ("mse_loss", "bpp_loss", "loss"):
+        np.testing.assert_allclose(f[k].numpy(), g[k], rtol=2e-6, err_msg=k)
+
+
+@pytest.mark.gpu
+def test_scalable_rate_distortion_loss_vs_reference_golden():
+    """The device criterion (reduction kernels + autograd.Functions) against the unmodified reference's values and the
+    gradients its backward sends into x_hat and every likelihood tensor."""
+    from resdsic_b200.training import ScalableRateDistortionLoss
+    from tests.golden.make_golden_scalable_loss import KEYS, LMBDA, load_case
+    g = np.load(os.path.join(GOLDEN, "scalable_loss.npz"))
+    t, x = load_case()
+    t = {k: v.to(DEV).requires_grad_(True) for k, v in t.items()}
+    out = {"x_hat": t["x_hat"], "likelihoods": {"y": t["lik_y"], "z": t["lik_z"], "z_prog": t["lik_z_prog"], "y_prog": t["lik_y_prog"]}}
+    crit = ScalableRateDistortionLoss(lmbda_list=LMBDA, device=DEV)
+    res = crit(out, x.to(DEV))
+    assert set(res) == {"mse_loss", "bpp_hype_base", "bpp_main_base", "bpp_base", "bpp_hype_scale", "bpp_main_scale",
+                        "bpp_scalable", "bpp_loss", "loss"}
+    for k in res:
+        np.testing.assert_allclose(res[k].detach().cpu().numpy(), g[k], rtol=2e-6, err_msg=k)
+    res["loss"].backward()
+    for k in KEYS:
+        gr = t[k].grad.double()
+        np.testing.assert_allclose(gr.norm().item(), float(g[f"grad_l2_{k}"]), rtol=1e-5, err_msg=k)
+        np.testing.assert_allclose(gr.sum().item(), float(g[f"grad_sum_{k}"]), rtol=1e-5, err_msg=k)
+    # an explicit lambda list overrides the constructor's (training/loss.py:59-62)
+    other = crit(out, x.to(DEV), lmbda=[0.1, 0.2, 0.3])["loss"].item()
+    want = _loss_formula({k: v.detach().cpu() for k, v in t.items()}, x, [0.1, 0.2, 0.3])["loss"].item()
+    assert abs(other - want) <= 2e-6 * abs(want)

@@ -11,8 +11,9 @@ enhancement pair for `imd`).  Same constructor arguments, parameter names and ou
 The whole multi-quality forward is ONE program: the base stream is computed once (the reference recomputes it
 for every quality level, :397-420), the latent-only pre-computations of the progressive context transforms are
 shared between levels, and every level's slice loop reuses the kernels / emitters of the base model.
-Evaluation mode only (round masks); `compress` / `decompress` of the progressive stream stay with the reference
-(per-slice rANS strings, :613-624) -- `symbols_and_indexes` returns what they consume.
+Evaluation mode only (round masks).  `compress` / `decompress` (:510-773) are provided like the base model's: every
+tensor the rANS coder consumes is produced on the device (`symbols_and_indexes`, decoder plans), the coder itself
+(`compressai.ans`) stays the reference's dependency.
 """
 import torch
 import torch.nn as nn
@@ -23,7 +24,7 @@ from ..layers import GDN, GELU, Ctx, Sequential, Win_noShift_Attention, conv, co
 from ..layers.base import emit_modules
 from ..layers.mask_layer import ONES, ZEROS, Mask
 from ..program import TV
-from .wacnn import WACNN, _cc_stack, _Plan, get_scale_table
+from .wacnn import WACNN, SliceDecoder, _cc_stack, _Plan, get_scale_table
 
 
 class scalable_icd(WACNN):
@@ -102,8 +103,9 @@ class scalable_icd(WACNN):
         """ZEROS / ONES for the constant masks, None for a computed one."""
         return self.masking.kind(q)
 
-    def _computed_mask(self, ctx, lat_s, lat_sp, q, cache):
-        """Importance mask of a quality level whose mask is neither all zeros nor all ones (:397-401)."""
+    def _computed_mask(self, ctx, lat_s, lat_sp, q, cache, coding=False):
+        """Importance mask of a quality level whose mask is neither all zeros nor all ones (:397-401).  `coding`: the
+        call comes from the compress / decompress side (:558,692) rather than from forward."""
         return self.masking.emit(ctx, lat_s, lat_sp, q, cache)
 
     def _merge(self, ctx, y_hat, y_hat_p):
@@ -136,12 +138,108 @@ class scalable_icd(WACNN):
             r.update(y_prog_symbols=o(p.prog_symbols), y_prog_indexes=o(p.prog_indexes), z_prog_symbols=o(p.z_prog_symbols))
         return r
 
+    @torch.no_grad()
     def compress(self, x, quality=0.0):
-        raise NotImplementedError("the scalable models' bitstream glue (per-slice rANS strings of the progressive stream, "
-                                  "scalable/single_decoder.py:510-647) stays with the reference; use symbols_and_indexes()")
+        """reference :510-647 (every variant inherits or restates it).  ONE program (`symbols_and_indexes`) produces
+        every symbol and CDF index of both streams on the device; the rANS coder (`compressai.ans`, imported lazily) is
+        called as the reference calls it: one string per image for z / z_prog, one buffered stream for the ten base
+        slices of the whole batch, and per progressive slice one string per image (`gaussian_conditional_prog.compress`,
+        :613-616).  Returns {"strings": [y_strings, z_strings(, z_prog_strings, progressive_strings)], "shape": [...]}."""
+        from ..entropy_models.entropy_models import _EntropyCoder
+        cdf, cdf_lengths, offsets = self.gaussian_conditional._coder_tables()
+        if self._quality_index(quality) != 0:
+            self.gaussian_conditional_prog._coder_tables()  # (fail before the forward pass if update() was not called)
+        r = self.symbols_and_indexes(x, quality=quality)
+        z_strings = self.entropy_bottleneck.compress(None, symbols=r["z_symbols"])
+        c = self.slice_channels
+        sym, idx = r["y_symbols"].cpu(), r["y_indexes"].cpu()
+        symbols_list, indexes_list = [], []
+        for i in range(self.num_slices):
+            symbols_list.extend(sym[:, c * i:c * i + c].reshape(-1).tolist())
+            indexes_list.extend(idx[:, c * i:c * i + c].reshape(-1).tolist())
+        encoder = _EntropyCoder.module().BufferedRansEncoder()
+        encoder.encode_with_indexes(symbols_list, indexes_list, cdf, cdf_lengths, offsets)
+        y_strings = [encoder.flush()]
+        shape = torch.Size(r["shape"])
+        if "y_prog_symbols" not in r:
+            return {"strings": [y_strings, z_strings], "shape": [shape]}
+        z_prog_strings = self.entropy_bottleneck_prog.compress(None, symbols=r["z_prog_symbols"])
+        ps, pi = r["y_prog_symbols"].cpu(), r["y_prog_indexes"].cpu()
+        progressive = [self.gaussian_conditional_prog._encode_symbols(ps[:, c * i:c * i + c], pi[:, c * i:c * i + c])
+                       for i in range(self.num_slices)]
+        return {"strings": [y_strings, z_strings, z_prog_strings, progressive], "shape": [shape, shape]}
 
+    @torch.no_grad()
     def decompress(self, strings, shape, quality=None):
-        raise NotImplementedError("scalable decompress (scalable/single_decoder.py:650-773) stays with the reference")
+        """reference :657-773.  The GPU work of every slice of both streams runs through decoder plans built from the
+        same emitters as the forward program (bit-identical CDF indexes); the coder calls are the reference's."""
+        from ..entropy_models.entropy_models import _EntropyCoder
+        if quality is None:
+            raise TypeError("decompress() needs the quality level the strings were coded at")
+        q = self._quality_index(quality)
+        cdf, cdf_lengths, offsets = self.gaussian_conditional._coder_tables()
+        z_hat = self.entropy_bottleneck.decompress(strings[1], shape[0])
+        if not z_hat.is_cuda:
+            raise RuntimeError("resdsic_b200 runs on CUDA devices only (no CPU fallback)")
+        z_hat_prog = self.entropy_bottleneck_prog.decompress(strings[2], shape[-1]) if q != 0 else None
+        B, _, hz, wz = z_hat.shape
+        key = ("sdec", B, hz, wz, str(z_hat.device), self.precision, q, self._weights_key())
+        plan = self._lru_get(self._dec_plans, key, lambda: self._build_scalable_decoder(B, hz, wz, z_hat.device, q), 2)
+        run = (lambda prog: prog.run_graph()) if self.use_cuda_graph else (lambda prog: prog.run())
+        base = SliceDecoder(self, plan.base, z_hat)
+        prog = None
+        if q != 0:
+            prog = SliceDecoder(self, plan.prog, z_hat_prog)
+            if plan.mask_prog is not None:
+                run(plan.mask_prog)
+        decoder = _EntropyCoder.module().RansDecoder()
+        decoder.set_stream(strings[0][0])
+        for i in range(self.num_slices):
+            idx = base.indexes(i)
+            rv = decoder.decode_stream(idx.reshape(-1).tolist(), cdf, cdf_lengths, offsets)
+            base.push_symbols(i, torch.tensor(rv, dtype=torch.int32).reshape(idx.shape))
+            if prog is not None:
+                idx_p = prog.indexes(i)
+                prog.push_symbols(i, self.gaussian_conditional_prog._decode_symbols(strings[-1][i], idx_p))
+        run(plan.synth)
+        return {"x_hat": self._out(plan.x_hat)}
+
+    def _build_scalable_decoder(self, B, hz, wz, device, q, build_only=False):
+        """Decoder plans of the base stream and (q != 0) of the progressive stream + the importance mask, and the
+        `synth` program: merge (`_merge`), g_s, clamp."""
+        from ..program import Program
+        ctx = Ctx(device, self.precision, build_only=build_only)
+        f32 = torch.float32
+        bf16 = ctx.precision == "bf16"
+        h, w, M = hz * 4, wz * 4, self.M
+        p = _Plan()
+        fam = {"cc_mean": self.cc_mean_transforms, "cc_scale": self.cc_scale_transforms, "lrp": self.lrp_transforms}
+        p.base = self._emit_decoder_hyper(ctx, B, hz, wz, self.h_mean_s, self.h_scale_s, fam)
+        self._emit_decoder_slices(ctx, p.base, fam, self.gaussian_conditional)
+        p.prog = p.mask_prog = None
+        y_hat = p.base.y_hat
+        if q != 0:
+            fam_p = {"cc_mean": self.cc_mean_transforms_prog, "cc_scale": self.cc_scale_transforms_prog,
+                     "lrp": self.lrp_transforms_prog if self.independent_lrp else self.lrp_transforms}
+            p.prog = self._emit_decoder_hyper(ctx, B, hz, wz, self.h_mean_s_prog, self.h_scale_s_prog, fam_p, lrp=self.lrp_prog)
+            kind = self._mask_kind(q)
+            assert kind != ZEROS
+            mask = None
+            if kind != ONES:
+                ctx.prog = p.mask_prog = Program(device)
+                mask = self._computed_mask(ctx, p.base.scales.channels(0, M), p.prog.scales.channels(0, M), q, {}, coding=True)
+            self._emit_decoder_slices(ctx, p.prog, fam_p, self.gaussian_conditional_prog, mask=mask, lrp=self.lrp_prog)
+        ctx.prog = prog = Program(device)
+        if q != 0:
+            y_hat = self._merge(ctx, p.base.y_hat, p.prog.y_hat)
+        x_raw = torch.empty(B, 3, h * 16, w * 16, dtype=f32, device=device)
+        p.x_hat = torch.empty(B, 3, h * 16, w * 16, dtype=f32, device=device)
+        act = prog.copy(y_hat, ctx.buf(B, h, w, M)) if bf16 else y_hat
+        self._synthesis(q).emit(ctx, act, last_kw=dict(out=TV.nchw_of(x_raw)))
+        prog.copy(TV.nchw_of(x_raw), TV.nchw_of(p.x_hat), op_code=3)  # clamp_(0, 1), :771
+        p.synth = prog
+        p.y_hat_q = y_hat
+        return p
 
     # ------------------------------------------------------------- planning
     def _execute_scalable(self, x, qualities, with_symbols):
@@ -228,7 +326,7 @@ class scalable_icd(WACNN):
             if q != 0:
                 kind = self._mask_kind(q)
                 assert kind != ZEROS
-                mask = None if kind == ONES else self._computed_mask(ctx, lat_s, lat_sp, q, mask_cache)
+                mask = None if kind == ONES else self._computed_mask(ctx, lat_s, lat_sp, q, mask_cache, coding=with_symbols)
                 p.masks[q] = mask
                 if first:
                     mq, sq = means_p, scales_p
@@ -298,7 +396,9 @@ class conditional_scalable_icd(scalable_icd):
         elif joiner_policy not in ("residual", "concatenation"):
             raise NotImplementedError(f"joiner policy {joiner_policy!r} (block_concatenation changes the decoder width: not provided)")
 
-    def _computed_mask(self, ctx, lat_s, lat_sp, q, cache):
+    def _computed_mask(self, ctx, lat_s, lat_sp, q, cache, coding=False):
+        if coding:  # compress / decompress are `icd`'s (inherited): they do pass the progressive scales (:558,692)
+            return super()._computed_mask(ctx, lat_s, lat_sp, q, cache, coding)
         raise AssertionError("scale_prog is None: the reference's cicd forward reaches only all-zero / all-one masks "
                              "(conditional_single_decoder.py:163, mask_layer.py:74,98)")
 
@@ -367,8 +467,8 @@ class conditional_scalable_imd(conditional_scalable_icd):
     def _synthesis(self, q):
         return self.g_s[0 if q == 0 else 1]
 
-    def _computed_mask(self, ctx, lat_s, lat_sp, q, cache):
-        return scalable_icd._computed_mask(self, ctx, lat_s, lat_sp, q, cache)
+    def _computed_mask(self, ctx, lat_s, lat_sp, q, cache, coding=False):
+        return scalable_icd._computed_mask(self, ctx, lat_s, lat_sp, q, cache, coding)
 
 
 class ResWACNNIndependentEntropy(scalable_icd):

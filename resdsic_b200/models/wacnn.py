@@ -592,35 +592,55 @@ class WACNN(CompressionModel):
         encoder pass's bit for bit -- which the entropy decoder relies on (identical CDF indexes)."""
         from ..program import Program
         ctx = Ctx(device, self.precision, build_only=build_only)
+        f32 = torch.float32
+        h, w = hz * 4, wz * 4
+        bf16 = ctx.precision == "bf16"
+        fam = {"cc_mean": self.cc_mean_transforms, "cc_scale": self.cc_scale_transforms, "lrp": self.lrp_transforms}
+        p = self._emit_decoder_hyper(ctx, B, hz, wz, self.h_mean_s, self.h_scale_s, fam)
+        self._emit_decoder_slices(ctx, p, fam, self.gaussian_conditional, grouped_tail=bf16 and self.grouped_slice_loop)
+        # ---- synthesis + clamp (cnn.py:337-340)
+        ctx.prog = prog = Program(device)
+        x_raw = torch.empty(B, 3, h * 16, w * 16, dtype=f32, device=device)
+        p.x_hat = torch.empty(B, 3, h * 16, w * 16, dtype=f32, device=device)
+        y_hat_act = prog.copy(p.y_hat, ctx.buf(B, h, w, self.M)) if bf16 else p.y_hat
+        self.g_s.emit(ctx, y_hat_act, last_kw=dict(out=TV.nchw_of(x_raw)))
+        prog.copy(TV.nchw_of(x_raw), TV.nchw_of(p.x_hat), op_code=3)
+        p.synth = prog
+        return p
+
+    def _emit_decoder_hyper(self, ctx, B, hz, wz, h_mean_s, h_scale_s, fam, lrp=True):
+        """Decoder plan of ONE latent stream, first half: its buffers and the `hyper` program (z_hat -> latent means /
+        scales, then the latent-only pre-computations of the context transforms, cf. `_emit_slice_precompute`)."""
+        from ..program import Program
+        device = ctx.device
         f32, i32 = torch.float32, torch.int32
         p = _Plan()
         h, w = hz * 4, wz * 4
         M, sc_, S = self.M, self.slice_channels, self.max_support_slices
-        bf16 = ctx.precision == "bf16"
         p.z_hat_in = torch.empty(B, self.N, hz, wz, dtype=f32, device=device)
         p.symbols = torch.zeros(B, M, h, w, dtype=i32, device=device)
         p.indexes = torch.empty(B, M, h, w, dtype=i32, device=device)
         p.lik = torch.empty(B, M, h, w, dtype=f32, device=device)  # likelihood of the decoded symbols (by-product)
         ctx_ld = M + sc_ * (S + 1)
         means, scales = ctx.buf(B, h, w, ctx_ld), ctx.buf(B, h, w, ctx_ld)
-        y_hat = ctx.buf(B, h, w, M, f32)
+        p.y_hat = ctx.buf(B, h, w, M, f32)
         lat_m, lat_s = means.channels(0, M), scales.channels(0, M)
-        fam = {"cc_mean": self.cc_mean_transforms, "cc_scale": self.cc_scale_transforms, "lrp": self.lrp_transforms}
 
         # ---- hyper: z_hat -> latent means / scales, then the latent-only pre-computations (cf. _build)
-        prog = ctx.prog
+        ctx.prog = prog = Program(device)
         z_hat = prog.copy(TV.nchw_of(p.z_hat_in), ctx.buf(B, hz, wz, self.N))
         prog.fork()
         with prog.side():
-            self.h_scale_s.emit(ctx, z_hat, last_kw=dict(out=lat_s))
-        self.h_mean_s.emit(ctx, z_hat, last_kw=dict(out=lat_m))
+            h_scale_s.emit(ctx, z_hat, last_kw=dict(out=lat_s))
+        h_mean_s.emit(ctx, z_hat, last_kw=dict(out=lat_m))
         prog.join()
         pre = {}
         jobs = [("mu0", None), ("sc0", None)]
         for i in range(self.num_slices):
             if i:
                 jobs += [(("cc_mean", i), lat_m), (("cc_scale", i), lat_s)]
-            jobs.append((("lrp", i), lat_m))
+            if lrp:
+                jobs.append((("lrp", i), lat_m))
         forked = set()
         for n, (key, src) in enumerate(jobs):
             lane = 2 + n % (_lib.MAX_LANES - 2)
@@ -629,14 +649,28 @@ class WACNN(CompressionModel):
                 forked.add(lane)
             with prog.side(lane):
                 if key == "mu0":
-                    pre[key] = self._stack(ctx, self.cc_mean_transforms[0], lat_m)
+                    pre[key] = self._stack(ctx, fam["cc_mean"][0], lat_m)
                 elif key == "sc0":
-                    pre[key] = self._stack(ctx, self.cc_scale_transforms[0], lat_s)
+                    pre[key] = self._stack(ctx, fam["cc_scale"][0], lat_s)
                 else:
                     pre[key] = fam[key[0]][key[1]][0].emit_partial(ctx, src, 0, M)
         for lane in sorted(forked):
             prog.join(lane)
         p.hyper = prog
+        p.pre, p.means, p.scales = pre, means, scales
+        p.shape = (B, h, w)
+        return p
+
+    def _emit_decoder_slices(self, ctx, p, fam, gc, grouped_tail=False, mask=None, lrp=True):
+        """Second half of a stream's decoder plan: per slice `params[i]` (cc_mean || cc_scale, CDF indexes) and
+        `update[i]` (dequantise the decoded symbols, LRP, write the support slots).  `mask` / `lrp`: the ResDSIC
+        progressive stream (see `_emit_slice_loop`); `grouped_tail`: mirror the grouped forward's LRP split."""
+        from ..program import Program
+        device = ctx.device
+        f32 = torch.float32
+        B, h, w = p.shape
+        M, sc_, S = self.M, self.slice_channels, self.max_support_slices
+        means, scales, y_hat, pre = p.means, p.scales, p.y_hat, p.pre
 
         def stack_split(name, i, buf, n_extra, final=None):
             seq = fam[name][i]
@@ -655,16 +689,22 @@ class WACNN(CompressionModel):
                     sc = stack_split("cc_scale", i, scales, sc_ * k)
                 mu = stack_split("cc_mean", i, means, sc_ * k)
                 prog.join(1)
+            mask_i = mask.channels(sc_ * i, sc_) if mask is not None else None
             # CDF indexes of the slice (build_indexes, cnn.py:322); y is not known yet: mu stands in for it
-            self.gaussian_conditional.emit(ctx, mu, sc, mu, p.lik, sc_ * i, M, y_hat_dsts=[], indexes=p.indexes)
+            gc.emit(ctx, mu, sc, mu, p.lik, sc_ * i, M, y_hat_dsts=[], indexes=p.indexes, mask=mask_i)
             p.params.append(prog)
             ctx.prog = prog = Program(device)
             yh_i = y_hat.channels(sc_ * i, sc_)
             slot = means.channels(M + sc_ * k, sc_)  # slices >= S: slot S is scratch for the current slice
             extra = dict(out2=slot, out3=scales.channels(M + sc_ * i, sc_)) if i < S else {}
-            self.gaussian_conditional.emit(ctx, mu, sc, mu, p.lik, sc_ * i, M, y_hat_dsts=[yh_i, slot], sym_in=p.symbols)
+            dsts = [yh_i, slot]
+            if not lrp and i < S:
+                dsts.append(scales.channels(M + sc_ * i, sc_))  # no LRP pass: the dequantised slice IS the support slice
+            gc.emit(ctx, mu, sc, mu, p.lik, sc_ * i, M, y_hat_dsts=dsts, sym_in=p.symbols, mask=mask_i)
             final = dict(epilogue=_lib.EPI_LRP, res=yh_i, out=yh_i, **extra)
-            if bf16 and self.grouped_slice_loop and i >= S:
+            if not lrp:
+                pass
+            elif grouped_tail and i >= S:
                 # the forward's grouped tail (`_emit_slice_loop_grouped`) splits this LRP's first conv three ways (latent |
                 # support | own slice); the same split here keeps x_hat bit-identical between the two passes
                 from ..layers.conv import emit_grouped
@@ -678,18 +718,6 @@ class WACNN(CompressionModel):
             else:
                 stack_split("lrp", i, means, sc_ * (k + 1), final=final)
             p.update.append(prog)
-
-        # ---- synthesis + clamp (cnn.py:337-340)
-        ctx.prog = prog = Program(device)
-        x_raw = torch.empty(B, 3, h * 16, w * 16, dtype=f32, device=device)
-        p.x_hat = torch.empty(B, 3, h * 16, w * 16, dtype=f32, device=device)
-        y_hat_act = prog.copy(y_hat, ctx.buf(B, h, w, M)) if bf16 else y_hat
-        self.g_s.emit(ctx, y_hat_act, last_kw=dict(out=TV.nchw_of(x_raw)))
-        prog.copy(TV.nchw_of(x_raw), TV.nchw_of(p.x_hat), op_code=3)
-        p.synth = prog
-        p.y_hat, p.means, p.scales = y_hat, means, scales
-        p.shape = (B, h, w)
-        return p
 
     @staticmethod
     def _stack(ctx, seq, x, final=None, skip_first=False):
@@ -773,6 +801,8 @@ class SliceDecoder:
 
     def __init__(self, model, plan, z_hat):
         self.model, self.plan, self._next, self._have_idx = model, plan, 0, False
+        if tuple(z_hat.shape) != tuple(plan.z_hat_in.shape):
+            raise ValueError(f"expected z_hat of shape {tuple(plan.z_hat_in.shape)}, got {tuple(z_hat.shape)}")
         plan.z_hat_in.copy_(z_hat)
         self._run(plan.hyper)
 

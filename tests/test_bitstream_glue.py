@@ -114,3 +114,42 @@ def test_compress_decompress_round_trip(fake_ans, synthetic_sd, precision):
     sc = (weights.hash_uniform("glue.s", (2, 32, 4, 4)) * 20).cuda()
     ix = gc.build_indexes(sc)
     assert torch.equal(gc.decompress(gc.compress(y, ix, mu), ix, mu), torch.round(y - mu) + mu)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name,quality", [("icd_gamma", 0.02), ("icd_gamma", 0.065), ("icd_gamma", 0.0035), ("imd_two", 0.065),
+                                          ("cimd_gamma", 0.02), ("ind_md", 0.065), ("icd_nolrp", 0.065)])
+def test_scalable_compress_decompress_round_trip(fake_ans, name, quality, precision):
+    """ResDSIC scalable models (scalable/single_decoder.py:510-773): compress() hands the coder the symbols / indexes of
+    `symbols_and_indexes`, in the reference's string layout; decompress() asks for exactly the encoder's CDF indexes
+    (the stand-in decoder asserts it, slice by slice, both streams) and returns clamp(x_hat of the encoder pass)."""
+    from tests.golden.make_golden_scalable import CASES, case_state_dict
+    key, kw, _, (B, H, W) = CASES[name]
+    m = resdsic_b200.models[key](N=192, M=320, **kw).eval()
+    m.load_state_dict(case_state_dict(m.state_dict()), strict=True)
+    m = m.to("cuda:0").set_precision(precision)
+    with pytest.raises(ValueError, match="Uninitialized CDFs"):
+        m.compress(torch.zeros(B, 3, H, W, device="cuda:0"), quality=quality)
+    m.update()
+    x = weights.make_image(B, H, W, seed=5).cuda()
+    q = m.lmbda_index_list[quality]
+    out = m.compress(x, quality=quality)
+    want = m.symbols_and_indexes(x, quality=quality)
+    x_fwd = want["x_hat"].clamp(0, 1).clone()
+    h, w = H // 16, W // 16
+    assert list(out) == ["strings", "shape"] and len(out["strings"]) == (2 if q == 0 else 4) and len(out["shape"]) == (1 if q == 0 else 2)
+    assert tuple(out["shape"][0]) == (h // 4, w // 4)
+    sym, idx = pickle.loads(out["strings"][0][0])
+    assert len(sym) == B * 320 * h * w and sym[:B * 32 * h * w] == want["y_symbols"][:, :32].reshape(-1).tolist()
+    assert idx[-B * 32 * h * w:] == want["y_indexes"][:, 288:].reshape(-1).tolist()
+    assert len(out["strings"][1]) == B
+    if q != 0:
+        assert len(out["strings"][2]) == B and len(out["strings"][3]) == 10 and all(len(s) == B for s in out["strings"][3])
+        ps, pi = pickle.loads(out["strings"][3][7][B - 1])  # slice 7, last image
+        assert ps == want["y_prog_symbols"][B - 1, 224:256].reshape(-1).tolist()
+        assert pi == want["y_prog_indexes"][B - 1, 224:256].reshape(-1).tolist()
+    rec = m.decompress(out["strings"], out["shape"], quality)
+    assert list(rec) == ["x_hat"] and torch.equal(rec["x_hat"], x_fwd)
+    # the quality may also be given as the level index (:658-661)
+    assert torch.equal(m.decompress(out["strings"], out["shape"], q)["x_hat"], x_fwd)

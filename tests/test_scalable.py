@@ -219,3 +219,41 @@ def test_scalable_rate_distortion_loss_vs_reference_golden():
     other = crit(out, x.to(DEV), lmbda=[0.1, 0.2, 0.3])["loss"].item()
     want = _loss_formula({k: v.detach().cpu() for k, v in t.items()}, x, [0.1, 0.2, 0.3])["loss"].item()
     assert abs(other - want) <= 2e-6 * abs(want)
+
+
+# ----------------------------------------------------------------------------- compress / decompress (decoder plans)
+DEC_CASES = [("icd_gamma", 1), ("icd_gamma", 2), ("imd_two", 1), ("icd_nolrp", 1), ("cimd_gamma", 1), ("ind_md", 1), ("icd_gamma", 0)]
+
+
+@pytest.mark.parametrize("name,q", DEC_CASES)
+def test_scalable_decoder_programs_match_encoder_program(name, q):
+    """decompress()'s plans (base + progressive stream, mask, merge, g_s; scalable/single_decoder.py:657-773) interpreted
+    on the CPU against the encoder-side program of compress(): same CDF indexes slice by slice, and with the encoder's
+    symbols pushed back the reconstruction equals clamp(x_hat of the encoder pass)."""
+    m, sd, quality, qs, x = _model(name)
+    B, _, H, W = x.shape
+    enc = m._build_scalable(B, H, W, "cpu", (q,), True, build_only=True)
+    enc.x.copy_(x)
+    run_on_cpu(enc.prog)
+    dec = m._build_scalable_decoder(B, H // 64, W // 64, "cpu", q, build_only=True)
+    streams = [(dec.base, enc.z_hat_out, enc.symbols, enc.indexes)]
+    if q != 0:
+        streams.append((dec.prog, enc.z_hat_prog, enc.prog_symbols, enc.prog_indexes))
+    else:
+        assert dec.prog is None and dec.mask_prog is None
+    for st, z_hat, _, _ in streams:
+        st.z_hat_in.copy_(z_hat)
+        run_on_cpu(st.hyper)
+    assert (dec.mask_prog is not None) == (q != 0 and m._mask_kind(q) is None)
+    if dec.mask_prog is not None:
+        run_on_cpu(dec.mask_prog)
+    for i in range(10):
+        sl = slice(32 * i, 32 * i + 32)
+        for st, _, sym, idx in streams:
+            run_on_cpu(st.params[i])
+            assert (st.indexes[:, sl] != idx[:, sl]).float().mean() <= 1e-3, (name, q, i)
+            st.symbols[:, sl].copy_(sym[:, sl])
+            run_on_cpu(st.update[i])
+    run_on_cpu(dec.synth)
+    want = enc.x_hat[0].clamp(0, 1)
+    assert (dec.x_hat - want).abs().max() <= 1e-4, (name, q, (dec.x_hat - want).abs().max())

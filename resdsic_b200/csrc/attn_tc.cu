@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(768) win_attn_tc_kernel(const rdsic_attn_desc 
   const __nv_bfloat16* V = qkv + 2 * CG + head * DH;
   const float* tb = tab + head * TWD * TWD;
 
-#pragma unroll 1
+#pragma unroll
   for (int rb = 0; rb < RB; ++rb) {
     const int i0 = rb * 16 + g, i1 = i0 + 8;
     // ---- S = Q K^T
@@ -151,27 +151,40 @@ __global__ void __launch_bounds__(768) win_attn_tc_kernel(const rdsic_attn_desc 
     }
     // ---- scale, relative-position bias, shift mask, softmax (rows i0 and i1; a row lives in one quad)
     const int hi0 = i0 / WS, wi0 = i0 % WS, hi1 = i1 / WS, wi1 = i1 % WS;
-    const int r0 = rid[i0], r1 = rid[i1];
     const float scale2 = d.scale * 1.4426950408889634f;  // scores in units of log2(e): exp(v) == exp2(v')
     float m0 = -INFINITY, m1 = -INFINITY;
+    // (key j = nt * 8 + 2t + e sits at window row nt * 8 / WS + ..., column (2t + e) % WS: per-thread base pointers, the
+    // nt / e parts of the table index are compile-time offsets)
+    const float* tb0 = tb + (hi0 + WS - 1) * TWD + (wi0 + WS - 1);
+    const float* tb1 = tb + (hi1 + WS - 1) * TWD + (wi1 + WS - 1);
 #pragma unroll
     for (int nt = 0; nt < NT_S; ++nt) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int j = nt * 8 + 2 * t + e;
-        const int hj = j / WS, wj = j % WS;
-        float v0 = fmaf(s[nt][e], scale2, tb[(hi0 - hj + WS - 1) * TWD + (wi0 - wj + WS - 1)]);
-        float v1 = fmaf(s[nt][2 + e], scale2, tb[(hi1 - hj + WS - 1) * TWD + (wi1 - wj + WS - 1)]);
-        if (masked) {  // block-uniform: only the windows of the last row / column carry the shift mask (-100)
-          const int rj = rid[j];
-          if (rj != r0) v0 += -100.0f * 1.4426950408889634f;
-          if (rj != r1) v1 += -100.0f * 1.4426950408889634f;
-        }
+        const int off = (j / WS) * TWD + (j % WS);
+        const float v0 = fmaf(s[nt][e], scale2, tb0[-off]);
+        const float v1 = fmaf(s[nt][2 + e], scale2, tb1[-off]);
         s[nt][e] = v0;
         s[nt][2 + e] = v1;
-        m0 = fmaxf(m0, v0);
-        m1 = fmaxf(m1, v1);
       }
+    }
+    if (masked) {  // block-uniform: only the windows of the last row / column carry the shift mask (-100)
+      const int r0 = rid[i0], r1 = rid[i1];
+#pragma unroll
+      for (int nt = 0; nt < NT_S; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int rj = rid[nt * 8 + 2 * t + e];
+          if (rj != r0) s[nt][e] += -100.0f * 1.4426950408889634f;
+          if (rj != r1) s[nt][2 + e] += -100.0f * 1.4426950408889634f;
+        }
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT_S; ++nt) {
+      m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+      m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
     }
     m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
     m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
@@ -193,23 +206,28 @@ __global__ void __launch_bounds__(768) win_attn_tc_kernel(const rdsic_attn_desc 
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
-    // ---- O = P V  (P stays in registers: two S n8-tiles form one k16 A fragment)
+    // ---- O = P V  (P stays in registers, UNNORMALISED in (0, 1] -- the row's 1 / sum scales the 2 x NT_O outputs
+    //      instead of the 2 x NTOK / 4 probabilities; two S n8-tiles form one k16 A fragment)
     float o[NT_O][4];
 #pragma unroll
     for (int nt = 0; nt < NT_O; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < KS_PV; ++kk) {
       uint32_t a[4];
-      a[0] = pack_bf16(s[2 * kk][0] * inv0, s[2 * kk][1] * inv0);
-      a[1] = pack_bf16(s[2 * kk][2] * inv1, s[2 * kk][3] * inv1);
-      a[2] = pack_bf16(s[2 * kk + 1][0] * inv0, s[2 * kk + 1][1] * inv0);
-      a[3] = pack_bf16(s[2 * kk + 1][2] * inv1, s[2 * kk + 1][3] * inv1);
+      a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+      a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+      a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
 #pragma unroll
       for (int nt = 0; nt < NT_O; ++nt) {
         uint32_t b0, b1;  // B[k = token][n = channel] from row-major V: transposed 8x8 loads
         ldmatrix_x2_trans(b0, b1, V + (kk * 16 + (lane & 15)) * LD + nt * 8);
         mma_16816(o[nt], a, b0, b1);
       }
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT_O; ++nt) {
+      o[nt][0] *= inv0; o[nt][1] *= inv0; o[nt][2] *= inv1; o[nt][3] *= inv1;
     }
     // ---- the block's output replaces its (already consumed) Q rows of this head
     __syncwarp();

@@ -327,16 +327,19 @@ class WACNN(CompressionModel):
         p.symbols = out_tensor("symbols", B, M, h, w, dtype=torch.int32) if with_symbols else None
         p.indexes = out_tensor("indexes", B, M, h, w, dtype=torch.int32) if with_symbols else None
         fam = {"cc_mean": self.cc_mean_transforms, "cc_scale": self.cc_scale_transforms, "lrp": self.lrp_transforms}
+        y_hat_act = None
         if bf16 and p.noise_y is None and self.grouped_slice_loop:
+            y_hat_act = ctx.buf(B, h, w, M)
             y_hat = self._emit_slice_loop_grouped(ctx, fam, self.gaussian_conditional, y, means, scales, p.lik_y, p.symbols,
-                                                  p.indexes)
+                                                  p.indexes, y_hat_act=y_hat_act)
         else:
             pre = self._emit_slice_precompute(ctx, fam, means, scales)
             y_hat = self._emit_slice_loop(ctx, fam, pre, self.gaussian_conditional, y, means, scales, p.lik_y, p.symbols,
                                           p.indexes, noise=p.noise_y)
         # ---- g_s
         p.x_hat = out_tensor("x_hat", B, 3, H, W)
-        y_hat_act = ctx.prog.copy(y_hat, ctx.buf(B, h, w, M)) if bf16 else y_hat
+        if y_hat_act is None:
+            y_hat_act = ctx.prog.copy(y_hat, ctx.buf(B, h, w, M)) if bf16 else y_hat
         self.g_s.emit(ctx, y_hat_act, last_kw=dict(out=TV.nchw_of(p.x_hat)))
         p.prog = ctx.prog
         p.y, p.z, p.y_hat, p.means, p.scales = y, z, y_hat, means, scales
@@ -471,7 +474,7 @@ class WACNN(CompressionModel):
                 prog.join(2 + 2 * n)
         return y_hat
 
-    def _emit_slice_loop_grouped(self, ctx, fam, gc, y, means, scales, lik_y, symbols, indexes):
+    def _emit_slice_loop_grouped(self, ctx, fam, gc, y, means, scales, lik_y, symbols, indexes, y_hat_act=None):
         """The slice loop (cnn.py:161-187) of the bf16 eval forward with grouped launches (rdsic_conv_desc.groups):
           * slices 1 .. S-1 (serial chain): cc_mean_i and cc_scale_i -- same shapes, same support input -- are ONE
             launch per layer (2 groups); their LRP stacks stay single;
@@ -484,7 +487,8 @@ class WACNN(CompressionModel):
           * the latent-only parts of the tail (inputs shared) are three wide convolutions instead of fifteen.
         Per output element the arithmetic of the cc stacks is that of the ungrouped path (same split, same K order),
         so symbols and CDF indexes equal the decoder-side loop's bit for bit; the three-way LRP split is mirrored by
-        `_build_decoder` for the same reason.  ~95 fewer launches per forward."""
+        `_build_decoder` for the same reason.  ~95 fewer launches per forward.  `y_hat_act` (bf16 [B,h,w,M]): the LRP
+        epilogues also write the refined slices there -- g_s's input, without a separate fp32 -> bf16 copy launch."""
         from ..layers.conv import emit_grouped
         prog = ctx.prog
         f32 = torch.float32
@@ -558,7 +562,8 @@ class WACNN(CompressionModel):
             t = seq[0].emit_partial(ctx, means.channels(M, sc_ * (k + 1)), 1, M, res=pre[("lrp", i)], gelu=True)
             for c in seq[1:-1]:
                 t = c.emit(ctx, t, gelu=True)
-            seq[-1].emit(ctx, t, epilogue=_lib.EPI_LRP, res=yh_i, out=yh_i, out2=slot)  # refined slice: support of later slices
+            act = dict(out3=y_hat_act.channels(sc_ * i, sc_)) if y_hat_act is not None else {}
+            seq[-1].emit(ctx, t, epilogue=_lib.EPI_LRP, res=yh_i, out=yh_i, out2=slot, **act)  # refined slice: support of later slices
 
         # ---------------- slices S .. 9: one grouped launch per layer
         support = means.channels(M, sc_ * S)
@@ -578,8 +583,9 @@ class WACNN(CompressionModel):
                             res=pre_tail_lrp, out_dtype=f32)
         t = emit_grouped(ctx, self, "tail_lrp0b", [cs[0] for cs in tail_lrp], yh_tail_act.channels(0, sc_), sc_,
                          cols=(M + sc_ * S, M + sc_ * (S + 1)), res=part, gelu=True)
+        act = dict(out2=y_hat_act.channels(sc_ * S, sc_ * T)) if y_hat_act is not None else {}
         rest_of_stack(tail_lrp, t, "tail_lrp", lambda l: tail_lrp[0][l].in_channels,
-                      final=dict(epilogue=_lib.EPI_LRP, res=yh_tail, out=yh_tail))
+                      final=dict(epilogue=_lib.EPI_LRP, res=yh_tail, out=yh_tail, **act))
         for lane in forked:
             prog.join(lane)
         return y_hat

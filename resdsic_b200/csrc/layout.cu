@@ -270,12 +270,105 @@ __global__ void __launch_bounds__(256) patchify_tiled_kernel(const rdsic_patch_d
   }
 }
 
+// The network's first layer exactly (conv 5x5 s2 p2 on a 3-channel NCHW fp32 image, K = 75 padded to 80): every
+// extent a compile-time constant.  ncu of the table-driven tiled kernel above on this layer: 216 us for 113 MB in +
+// 377 MB out = 0.30 of the HBM copy bandwidth at 65 % issue-slot use -- instruction-bound (~2100 instructions per
+// thread: per-element index arithmetic in the window load, 8 table + 8 data shared-memory loads per 16 output bytes).
+// Here one thread owns one output pixel: its 75 inputs are shared-memory loads at immediate offsets from one base,
+// packed to 40 registers, transposed through a per-warp shared buffer (176-byte pixel pitch: conflict-free 128-bit
+// writes) so that every global store instruction writes 512 contiguous bytes.  ~330 instructions per thread.  The
+// window's rows are stored with even and odd columns apart, so the stride-2 reads of a warp (column 2 * lx + s) are
+// consecutive words; the transpose buffer takes over the window's shared memory once every thread has its values
+// (45 KB per CTA: five CTAs per SM).
+constexpr int PF_C = 3, PF_K = 5, PF_S = 2, PF_P = 2, PF_KP = 80, PF_TH = 4, PF_TW = 64;
+constexpr int PF_ROWS = (PF_TH - 1) * PF_S + PF_K, PF_COLS = (PF_TW - 1) * PF_S + PF_K, PF_PITCH = 132;
+constexpr int PF_PLANE = PF_ROWS * PF_PITCH, PF_OPITCH = 176;  // bytes per pixel in the transpose buffer
+constexpr int PF_HALF = 66;  // a window row is stored de-interleaved: even columns at [0, 66), odd ones at [66, 132)
+constexpr int PF_TILE_BYTES = PF_C * PF_PLANE * 4, PF_OBUF_BYTES = 8 * 32 * PF_OPITCH;
+constexpr int PF_SMEM = PF_OBUF_BYTES > PF_TILE_BYTES ? PF_OBUF_BYTES : PF_TILE_BYTES;  // the transpose buffer re-uses the window's space
+
+__global__ void __launch_bounds__(256) patchify_first_kernel(const rdsic_patch_desc d, int tiles_x, int tiles_y) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) uint8_t pf_smem[];
+  float* tile = reinterpret_cast<float*>(pf_smem);                    // [3][11][132]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* obuf = pf_smem + warp * 32 * PF_OPITCH;  // this warp's 32 pixels x 160 (+16) bytes (after the window is consumed)
+  int t = blockIdx.x;
+  const int tx = t % tiles_x;
+  t /= tiles_x;
+  const int ty = t % tiles_y, b = t / tiles_y;
+  const int ox0 = tx * PF_TW, oy0 = ty * PF_TH;
+  const int ix0 = ox0 * PF_S - PF_P, iy0 = oy0 * PF_S - PF_P;
+  const float* src = (const float*)d.src.ptr + (size_t)b * PF_C * d.H * d.W;
+  // ---- input window: one (channel, row) per warp pass, coalesced along x
+  for (int row = warp; row < PF_C * PF_ROWS; row += 8) {
+    const int c = row / PF_ROWS, ry = row - c * PF_ROWS;
+    const int iy = iy0 + ry;
+    const bool row_ok = iy >= 0 && iy < d.H;
+    const float* sp = src + ((size_t)c * d.H + (row_ok ? iy : 0)) * d.W;
+    float* tp = tile + c * PF_PLANE + ry * PF_PITCH;
+#pragma unroll
+    for (int x = lane; x < PF_COLS; x += 32) {
+      const int ix = ix0 + x;
+      tp[(x & 1) * PF_HALF + (x >> 1)] = (row_ok && ix >= 0 && ix < d.W) ? __ldg(sp + ix) : 0.f;
+    }
+  }
+  __syncthreads();
+  // ---- one output pixel per thread: warp w covers row ly = w / 2, columns (w & 1) * 32 + lane
+  const int ly = warp >> 1, lx = ((warp & 1) << 5) + lane;
+  const float* base = tile + (ly * PF_S) * PF_PITCH + lx;  // column 2 * lx + s -> (s & 1) * 66 + lx + (s >> 1)
+  uint32_t w[PF_KP / 2];
+#pragma unroll
+  for (int k2 = 0; k2 < PF_KP / 2; ++k2) {
+    float f[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int k = 2 * k2 + u;  // k = (r * 5 + s) * 3 + c: tap-major, channel-minor (the packed weight's K order)
+      if (k < PF_K * PF_K * PF_C) {
+        const int tap = k / PF_C, c = k - tap * PF_C, r = tap / PF_K, sx = tap - r * PF_K;
+        f[u] = base[c * PF_PLANE + r * PF_PITCH + (sx & 1) * PF_HALF + (sx >> 1)];
+      } else {
+        f[u] = 0.f;
+      }
+    }
+    __nv_bfloat162 hh = __floats2bfloat162_rn(f[0], f[1]);
+    w[k2] = *reinterpret_cast<uint32_t*>(&hh);
+  }
+  __syncthreads();  // every thread holds its pixel: the window's space becomes the transpose buffer
+#pragma unroll
+  for (int j = 0; j < PF_KP / 8; ++j)
+    *reinterpret_cast<uint4*>(obuf + lane * PF_OPITCH + j * 16) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+  __syncwarp();
+  // ---- the warp's 32 x 160 bytes in destination order: chunk q = pixel * 10 + j
+  const int oy = oy0 + ly, oxw = ox0 + ((warp & 1) << 5);
+  if (oy < d.OH) {
+    __nv_bfloat16* dst = (__nv_bfloat16*)d.dst.ptr + d.dst.coff;
+    const size_t pix0 = ((size_t)b * d.OH + oy) * d.OW + oxw;
+#pragma unroll
+    for (int it = 0; it < PF_KP / 8; ++it) {
+      const int q = it * 32 + lane, px = q / (PF_KP / 8), j = q - px * (PF_KP / 8);
+      if (oxw + px < d.OW)
+        *reinterpret_cast<uint4*>(dst + (pix0 + px) * (size_t)d.dst.ld + j * 8) =
+            *reinterpret_cast<const uint4*>(obuf + px * PF_OPITCH + j * 16);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int rdsic_patch_forward(const rdsic_patch_desc* d, rdsic_stream_t stream) {
   RDSIC_CHECK_ARG(d && d->src.ptr && d->dst.ptr && d->B > 0 && d->C > 0 && d->KH > 0 && d->KW > 0 && d->stride > 0);
   RDSIC_CHECK_ARG(d->Kp % 16 == 0 && d->Kp >= d->KH * d->KW * d->C && !d->dst.nchw);
   if (d->dst.ld % 8 || d->dst.coff % 8 || ((uintptr_t)d->dst.ptr % 16)) return RDSIC_E_ALIGN;
+  static const int tune_first = getenv("RDSIC_PATCH_FIRST") ? atoi(getenv("RDSIC_PATCH_FIRST")) : 1;
+  if (tune_first && d->src.nchw && d->src.dtype == RDSIC_F32 && d->dst.dtype == RDSIC_BF16 && d->C == PF_C && d->KH == PF_K &&
+      d->KW == PF_K && d->stride == PF_S && d->pad == PF_P && d->Kp == PF_KP) {
+    static_assert(PF_SMEM <= 48 * 1024, "fits the default dynamic shared memory limit");
+    const int tiles_x = ceil_div(d->OW, PF_TW), tiles_y = ceil_div(d->OH, PF_TH);
+    return rdsic_launch(patchify_first_kernel, dim3((unsigned)((size_t)d->B * tiles_y * tiles_x)), 256, PF_SMEM, (cudaStream_t)stream,
+                        false, *d, tiles_x, tiles_y);
+  }
   {
     const int rows = (PT_H - 1) * d->stride + d->KH, cols = (PT_W - 1) * d->stride + d->KW;
     const long tile_floats = (long)d->C * rows * (cols | 1);

@@ -55,6 +55,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   // in clusters of two, so the 1-CTA instantiations must not contain any; the PAIR instantiation in turn drops the
   // halo / M2 / K-split / MC variants
   const int m_halo = PAIR ? 0 : g.halo, m_m2 = PAIR ? 0 : g.m2, m_ksplit = PAIR ? 0 : g.ksplit, m_mc = PAIR ? 0 : g.mc;
+  // PAIR + M2 ("P2"): every CTA of the pair stages a 256-row A box (two 128-row halves), the leader issues TWO
+  // cta_group::2 UMMAs per K step (half h of both CTAs into accumulator columns h * BN) against the same B stage: 512
+  // rows per pair and weight stage, i.e. half the weight bytes per output row of the plain pair tile
+  const int m_p2 = PAIR ? g.m2 : 0;
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int stage_bytes = m_halo ? g.b_stage_bytes : g.a_stage_bytes + g.b_stage_bytes;
@@ -344,8 +348,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   umma_bf16_2sm(acc, da + 2, db + 2, idesc2, 1u);
                   umma_bf16_2sm(acc, da + 4, db + 4, idesc2, 1u);
                   umma_bf16_2sm(acc, da + 6, db + 6, idesc2, 1u);
+                  if (m_p2) {  // second 128-row half of both CTAs' A boxes, same B stage
+                    const uint64_t da2 = da + (A_STAGE_BYTES >> 4);
+                    const uint32_t acc2 = acc + (uint32_t)g.BN;
+                    umma_bf16_2sm(acc2, da2, db, idesc2, n > 0 ? 1u : 0u);
+                    umma_bf16_2sm(acc2, da2 + 2, db + 2, idesc2, 1u);
+                    umma_bf16_2sm(acc2, da2 + 4, db + 4, idesc2, 1u);
+                    umma_bf16_2sm(acc2, da2 + 6, db + 6, idesc2, 1u);
+                  }
                 } else {
                   for (int k = 0; k < kc_last; ++k) umma_bf16_2sm(acc, da + 2 * k, db + 2 * k, idesc2, (n > 0 || k > 0) ? 1u : 0u);
+                  if (m_p2)
+                    for (int k = 0; k < kc_last; ++k)
+                      umma_bf16_2sm(acc + (uint32_t)g.BN, da + (A_STAGE_BYTES >> 4) + 2 * k, db + 2 * k, idesc2, (n > 0 || k > 0) ? 1u : 0u);
                 }
                 tcgen05_commit_2sm_mc_u32(empty0 + 8u * (uint32_t)s, 3);  // frees the stage in BOTH CTAs
               }
@@ -487,7 +502,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int ml = q * 32 + lane;
     // row -> pixel of the patch; M2 tiles have a second 128-row half (rows ml + 128, accumulator columns + BN)
     const int dyh[2] = {ml / g.TW, (ml + BM) / g.TW}, dxh[2] = {ml % g.TW, (ml + BM) % g.TW};
-    const int nh = m_m2 ? 2 : 1;
+    const int nh = (m_m2 || m_p2) ? 2 : 1;
     const int nchunks = g.BN / 16;
     uint32_t lt = 0;
     for (int tq = wk.first; tq < g.walk_total; tq += wk.step, ++lt) {
@@ -825,6 +840,34 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
       g.a_stage_bytes = 2 * A_STAGE_BYTES;
     }
   }
+  // PAIR + M2 (see the kernel): for the pair layers whose grid is a few rounds of pair tiles -- the latent-resolution
+  // slice loop: 144 pair tiles on 74 pairs stream the whole weight matrix twice per SM -- a 256-row box per CTA halves
+  // the rounds and the weight bytes per output row.  Needs two accumulators of BN columns (one set when 4 BN > 512: the
+  // epilogue of a tile is then not hidden behind the next tile's main loop, hence only long-K layers).
+  // RDSIC_TC_P2: 0 off, 1 this rule (default), 2 wherever it fits, 3 the rule without the several-n-tiles condition.
+  static const int tune_p2 = getenv("RDSIC_TC_P2") ? atoi(getenv("RDSIC_TC_P2")) : 1;
+  if (tune_p2 && want_pair && !g.halo && 2 * g.BN <= 512 && groups == 1) {
+    const int n_t = ceil_div(d->Cout, g.BN), slots = sms / 2;
+    int th2 = 0, tw2 = 0;
+    const long area2 = pick_patch(2 * BM, &th2, &tw2);
+    const long tiles256 = area2 > 0 ? (long)B * (area2 / (2 * BM)) : 0;
+    const long rounds128 = ((tiles128_all + 1) / 2 * n_t + slots - 1) / slots, rounds256 = ((tiles256 + 1) / 2 * n_t + slots - 1) / slots;
+    const long cost128 = rounds128 * (A_STAGE_BYTES + g.BN * BK), cost256 = rounds256 * (2 * A_STAGE_BYTES + g.BN * BK);
+    // MEASURED per layer at batch 24 (bench.py --dump-ops, RDSIC_TC_P2 = 0 / 2): N = 320 (two n tiles of 160; 3x3 and
+    // 5x5 s2 at M = 36 864) -9 ... -12 %; but single-n-tile layers LOSE (N = 224: +9 ... +27 %, N = 192: +5 ... +9 %, the
+    // M = 147 456 5x5 s2 layer +7 %): their grid becomes ONE round of 512-row tiles whose whole epilogue is exposed, while
+    // two rounds of 256-row tiles hide the first epilogue behind the second main loop.  Hence: at least two rounds of
+    // 512-row tiles (several n tiles), where the halved weight traffic is what is left.
+    const bool rule = tiles128_all <= 8L * sms && n_t >= 2 && rounds256 >= 2 && cost256 < cost128 &&
+                      (4 * g.BN <= 512 || g.num_k_iters >= 16);
+    const bool broad = tiles128_all <= 8L * sms && rounds128 >= 2 && cost256 < cost128 && (4 * g.BN <= 512 || g.num_k_iters >= 16);
+    if (area2 > 0 && tiles256 >= 2 && (tune_p2 == 2 || (tune_p2 == 3 && broad) || rule)) {
+      g.m2 = 1;
+      g.TH = th2;
+      g.TW = tw2;
+      g.a_stage_bytes = 2 * A_STAGE_BYTES;
+    }
+  }
   g.tiles_x = ceil_div(OW, g.TW);
   g.tiles_y = ceil_div(OH, g.TH);
   const int m_tiles = B * g.tiles_y * g.tiles_x;
@@ -859,7 +902,7 @@ int rdsic_conv_forward_bf16(const rdsic_conv_desc* d, cudaStream_t stream) {
   int stages = ((g.m2 ? 220 : 200) * 1024 - (g.halo ? 2 * g.a_halo_bytes : 0)) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (tune_stages > 0 && tune_stages < stages) stages = tune_stages;
-  if (!g.halo && !g.m2) stages &= ~1;  // even ring depth: stage parity = owner (two producers / two issuers)
+  if (!g.halo && (!g.m2 || g.pair)) stages &= ~1;  // even ring depth: stage parity = owner (two producers / two issuers)
   if (stages < 2) return RDSIC_E_ARG;
   g.num_stages = stages;
   // K-split across two issuer warps (see the kernel's header comment) wherever both accumulators fit TMEM.

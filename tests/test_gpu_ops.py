@@ -353,6 +353,10 @@ def test_patchify_matches_unfold(C, k, s, p, B, H, W):
     {"RDSIC_TC_PAIR": "3"},                          # cta_group::2 CTA pairs on EVERY layer with two M tiles (default: wide long-K layers)
     {"RDSIC_TC_PAIR": "0"},                          # no CTA pairs (M2 / single-issuer tiles everywhere)
     {"RDSIC_TC_PAIR": "0", "RDSIC_TC_MC": "1"},      # 1-CTA tiles with the B stage multicast across a CTA pair
+    {"RDSIC_TC_PAIR": "3", "RDSIC_TC_P2": "2"},      # CTA pairs with 256-row A boxes (two accumulators per pair tile) wherever they fit
+    {"RDSIC_ATTN_PIPE": "1"},                        # persistent double-buffered attention core (default off: measured slower)
+    {"RDSIC_ATTN_HPC": "4"},                         # attention: a window's heads split over two CTAs
+    {"RDSIC_PATCH_FIRST": "0"},                      # first layer's im2col through the table-driven tiled kernel
 ], ids=lambda e: ",".join(f"{k[6:]}={v}" for k, v in e.items()))
 def test_kernel_mode_switches_in_subprocess(env):
     """Every kernel mode behind a tuning switch stays correct: the conv / deconv / fused-layer parity tests pass with
@@ -361,6 +365,6 @@ def test_kernel_mode_switches_in_subprocess(env):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_ops.py", "-m", "gpu", "-q", "-x", "-k",
-                        "tcgen05 or layers_bf16 or subpel or fused_ or grouped"], cwd=root, env=dict(os.environ, **env), capture_output=True,
+                        "tcgen05 or layers_bf16 or subpel or fused_ or grouped or attention or patchify"], cwd=root, env=dict(os.environ, **env), capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

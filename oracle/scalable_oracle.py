@@ -132,7 +132,10 @@ def forward(sd, x, qualities, policy, levels, lrp_prog=True, independent_lrp=Fal
                 out["prog_symbols"], out["prog_indexes"] = torch.cat(syms, 1), torch.cat(idxs, 1)
         y_hats.append(y_hat_q)
         gs = "g_s" if not multiple_decoder else ("g_s.0" if q == 0 else "g_s.1")
-        x_hats.append(g_s(y_hat_q, sd, gs))
+        g_in = y_hat_q
+        if variant == "cimd" and joiner_policy == "concatenation" and q != 0:
+            g_in = torch.cat([y_hat_q, torch.cat(hat, 1)], 1)  # conditional_multiple_decoder.py:230: a 2M-wide g_s[1]
+        x_hats.append(g_s(g_in, sd, gs))
     lik_y = base["y_likelihoods"].unsqueeze(0)
     out.update(x_hat=torch.stack(x_hats), y=torch.stack(y_hats), z_hat=z_hat, z_hat_prog=z_hat_p, masks=masks,
                likelihoods={"y": lik_y, "z": z_lik, "z_prog": z_lik_p,

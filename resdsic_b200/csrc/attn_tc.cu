@@ -436,6 +436,7 @@ int rdsic_attn_forward_tc(const rdsic_attn_desc* d, cudaStream_t stream) {
   const int dh = d->C / d->heads;
   if (d->ws == 8 && dh == 24) return launch_tc<8, 24>(d, stream);
   if (d->ws == 4 && dh == 40) return launch_tc<4, 40>(d, stream);
+  if (d->ws == 4 && dh == 80) return launch_tc<4, 80>(d, stream);  // cimd "concatenation": the 2M = 640-wide decoder head
   if (d->ws == 4 && dh == 16) return launch_tc<4, 16>(d, stream);  // stf: window 4, head_dim 16, 3..24 heads
   if (d->ws == 4 && dh == 32) return launch_tc<4, 32>(d, stream);
   if (d->ws == 8 && dh == 32) return launch_tc<8, 32>(d, stream);

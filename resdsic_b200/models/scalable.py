@@ -108,6 +108,12 @@ class scalable_icd(WACNN):
         call comes from the compress / decompress side (:558,692) rather than from forward."""
         return self.masking.emit(ctx, lat_s, lat_sp, q, cache)
 
+    def _synthesis_input(self, ctx, q, y_hat_q, y_hat_p):
+        """What g_s sees at quality index q: the merged latent (as a bf16 copy in bf16 mode)."""
+        if ctx.precision == "bf16":
+            return ctx.prog.copy(y_hat_q, ctx.buf(y_hat_q.B, y_hat_q.H, y_hat_q.W, self.M))
+        return y_hat_q
+
     def _merge(self, ctx, y_hat, y_hat_p):
         """y_hat_complete = y_hat_base + y_hat_prog (:472)."""
         B, h, w, M = y_hat.B, y_hat.H, y_hat.W, self.M
@@ -234,7 +240,7 @@ class scalable_icd(WACNN):
             y_hat = self._merge(ctx, p.base.y_hat, p.prog.y_hat)
         x_raw = torch.empty(B, 3, h * 16, w * 16, dtype=f32, device=device)
         p.x_hat = torch.empty(B, 3, h * 16, w * 16, dtype=f32, device=device)
-        act = prog.copy(y_hat, ctx.buf(B, h, w, M)) if bf16 else y_hat
+        act = self._synthesis_input(ctx, q, y_hat, p.prog.y_hat if q != 0 else None)
         self._synthesis(q).emit(ctx, act, last_kw=dict(out=TV.nchw_of(x_raw)))
         prog.copy(TV.nchw_of(x_raw), TV.nchw_of(p.x_hat), op_code=3)  # clamp_(0, 1), :771
         p.synth = prog
@@ -341,8 +347,10 @@ class scalable_icd(WACNN):
                                                 scale_eps=0.0 if with_symbols else self.prog_scale_eps)
                 jp += 1
                 y_hat_q = self._merge(ctx, y_hat, y_hat_p)
+            else:
+                y_hat_p = None
             prog.copy(y_hat_q, TV.nchw_of(p.y_hat_q[j]))
-            act = prog.copy(y_hat_q, ctx.buf(B, h, w, M)) if bf16 else y_hat_q
+            act = self._synthesis_input(ctx, q, y_hat_q, y_hat_p)
             self._synthesis(q).emit(ctx, act, last_kw=dict(out=TV.nchw_of(p.x_hat[j])))
         p.prog = prog
         p.y, p.z, p.y_hat, p.means, p.scales, p.y_prog, p.y_base = y, z, y_hat, means, scales, y_prog, y_base
@@ -431,16 +439,17 @@ class conditional_scalable_icd(scalable_icd):
         return out
 
 
-def _synthesis_pair(M, N):
-    """Base / enhancement decoder pair (multiple_decoder.py:36-50)."""
+def _synthesis_pair(M, N, dims=None):
+    """Base / enhancement decoder pair (multiple_decoder.py:36-50); `dims`: input width of each decoder."""
+    dims = dims or [M, M]
     return nn.ModuleList(
         Sequential(
-            Win_noShift_Attention(dim=M, num_heads=8, window_size=4, shift_size=2),
-            deconv(M, N, kernel_size=5, stride=2), GDN(N, inverse=True),
+            Win_noShift_Attention(dim=dims[i], num_heads=8, window_size=4, shift_size=2),
+            deconv(dims[i], N, kernel_size=5, stride=2), GDN(N, inverse=True),
             deconv(N, N, kernel_size=5, stride=2), GDN(N, inverse=True),
             Win_noShift_Attention(dim=N, num_heads=8, window_size=8, shift_size=4),
             deconv(N, N, kernel_size=5, stride=2), GDN(N, inverse=True),
-            deconv(N, 3, kernel_size=5, stride=2)) for _ in range(2))
+            deconv(N, 3, kernel_size=5, stride=2)) for i in range(2))
 
 
 class conditional_scalable_imd(conditional_scalable_icd):
@@ -449,20 +458,27 @@ class conditional_scalable_imd(conditional_scalable_icd):
     computed masks of the learnable policies ARE reachable; the progressive likelihood is taken at
     `scale_prog * mask + 1e-7` (:210) and the forward dictionary has no "y" entry (:262-267).  compress() is `icd`'s
     (inherited in the reference), so `symbols_and_indexes` indexes `scale_prog * mask` without the 1e-7.
-    `joiner_policy="concatenation"` (a 2M-wide enhancement decoder fed with cat(base, progressive), :41,230) is not
-    provided."""
+    `joiner_policy="concatenation"`: the enhancement decoder g_s[1] is 2M wide and is fed with
+    cat(base reconstruction, progressive reconstruction) (:41,230; `merge` returns the base alone for this policy)."""
 
     prog_scale_eps = 1e-7
     returns_y = False
 
     def __init__(self, N=192, M=320, mask_policy="learnable-mask", lambda_list=(0.05,), lrp_prog=True,
                  independent_lrp=False, joiner_policy="conditional", **kwargs):
-        if joiner_policy == "concatenation":
-            raise NotImplementedError("cimd with joiner_policy='concatenation' (2M-wide enhancement decoder, "
-                                      "conditional_multiple_decoder.py:41) is not provided")
         super().__init__(N=N, M=M, mask_policy=mask_policy, lambda_list=lambda_list, lrp_prog=lrp_prog,
                          independent_lrp=independent_lrp, joiner_policy=joiner_policy, **kwargs)
-        self.g_s = _synthesis_pair(M, N)
+        self.dimensions_M = [M, 2 * M if joiner_policy == "concatenation" else M]
+        self.g_s = _synthesis_pair(M, N, self.dimensions_M)
+
+    def _synthesis_input(self, ctx, q, y_hat_q, y_hat_p):
+        if self.joiner_policy != "concatenation" or q == 0:
+            return super()._synthesis_input(ctx, q, y_hat_q, y_hat_p)
+        B, h, w, M = y_hat_q.B, y_hat_q.H, y_hat_q.W, self.M  # cat(y_hat_complete (= base), y_hat_prog), :230
+        cat = ctx.buf(B, h, w, 2 * M) if ctx.precision == "bf16" else ctx.buf(B, h, w, 2 * M, torch.float32)
+        ctx.prog.copy(y_hat_q, cat.channels(0, M))
+        ctx.prog.copy(y_hat_p, cat.channels(M, M))
+        return cat
 
     def _synthesis(self, q):
         return self.g_s[0 if q == 0 else 1]

@@ -35,6 +35,8 @@ CASES = {
                                 joiner_policy="conditional"), None, (1, 64, 64)),
     "cimd_res": ("cimd", dict(lambda_list=[0.0035, 0.065], mask_policy="two-levels", lrp_prog=True, joiner_policy="residual"),
                  [0.065], (1, 64, 64)),
+    "cimd_cat": ("cimd", dict(lambda_list=[0.0035, 0.065], mask_policy="two-levels", lrp_prog=True, joiner_policy="concatenation"),
+                 None, (1, 64, 64)),  # 2M-wide enhancement decoder fed with cat(base, progressive)
     # ind: independent entropy models, no mask on the data path; single decoder / decoder pair + independent LRP
     "ind_two": ("ind", dict(lambda_list=[0.0035, 0.065], mask_policy="two-levels", lrp_prog=True), None, (1, 64, 64)),
     "ind_md": ("ind", dict(lambda_list=[0.0035, 0.065], mask_policy="learnable-mask", lrp_prog=True, independent_lrp=True,

@@ -119,7 +119,7 @@ def test_compress_decompress_round_trip(fake_ans, synthetic_sd, precision):
 @pytest.mark.gpu
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("name,quality", [("icd_gamma", 0.02), ("icd_gamma", 0.065), ("icd_gamma", 0.0035), ("imd_two", 0.065),
-                                          ("cimd_gamma", 0.02), ("ind_md", 0.065), ("icd_nolrp", 0.065)])
+                                          ("cimd_gamma", 0.02), ("cimd_cat", 0.065), ("ind_md", 0.065), ("icd_nolrp", 0.065)])
 def test_scalable_compress_decompress_round_trip(fake_ans, name, quality, precision):
     """ResDSIC scalable models (scalable/single_decoder.py:510-773): compress() hands the coder the symbols / indexes of
     `symbols_and_indexes`, in the reference's string layout; decompress() asks for exactly the encoder's CDF indexes

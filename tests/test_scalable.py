@@ -84,8 +84,8 @@ def test_registry_and_constructor_contract():
         model = "cimd"
     cm = resdsic_b200.configure_model(Cm)
     assert isinstance(cm, resdsic_b200.models["cicd"]) and len(cm.g_s) == 2 and len(cm.joiner) == 10 and not cm.returns_y
-    with pytest.raises(NotImplementedError):
-        resdsic_b200.models["cimd"](lambda_list=[1, 2], mask_policy="two-levels", joiner_policy="concatenation")
+    cc = resdsic_b200.models["cimd"](lambda_list=[1, 2], mask_policy="two-levels", joiner_policy="concatenation")
+    assert cc.dimensions_M == [320, 640] and tuple(cc.g_s[1][1].weight.shape)[0] == 640 and tuple(cc.g_s[0][1].weight.shape)[0] == 320
     class Ci:
         model, N, M, mask_policy, lambda_list, lrp_prog, independent_lrp, multiple_decoder = "ind", 192, 320, "learnable-mask", [0.0035, 0.065], True, True, True
     ci = resdsic_b200.configure_model(Ci)
@@ -222,7 +222,8 @@ def test_scalable_rate_distortion_loss_vs_reference_golden():
 
 
 # ----------------------------------------------------------------------------- compress / decompress (decoder plans)
-DEC_CASES = [("icd_gamma", 1), ("icd_gamma", 2), ("imd_two", 1), ("icd_nolrp", 1), ("cimd_gamma", 1), ("ind_md", 1), ("icd_gamma", 0)]
+DEC_CASES = [("icd_gamma", 1), ("icd_gamma", 2), ("imd_two", 1), ("icd_nolrp", 1), ("cimd_gamma", 1), ("cimd_cat", 1), ("ind_md", 1),
+             ("icd_gamma", 0)]
 
 
 @pytest.mark.parametrize("name,q", DEC_CASES)

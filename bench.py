@@ -507,7 +507,7 @@ def run_train(args):
         torch.cuda.synchronize(dev)
 
     _lib.lib()
-    B = args.batch if args.batch != 24 else 16
+    B = args.batch
     net, crit, opt, aux_opt, reducer, main = _train_objects(dev, world)
     x_host = synthetic.rand_image(B, TRAIN_H, TRAIN_W, seed=300 + rank).pin_memory()
     x_dev = x_host.to(dev)
@@ -665,9 +665,10 @@ def main():
     ap.add_argument("--workload", default="forward", choices=["forward", "train"],
                     help="forward = the headline (BASELINE configs[2]); train = the RD training step of config 4 (extra line)")
     ap.add_argument("--precision", default=os.environ.get("RESDSIC_PRECISION", "bf16"), choices=["fp32", "bf16"])
-    # 24 images x 1536 latent pixels = 144 of the 256-row tiles of the slice-loop GEMMs: one full wave of the 148
-    # SMs (batch 16 fills 96 of them, batch 32 needs a second, 30 %-full wave).  Sweep: DESIGN.md section 5.
-    ap.add_argument("--batch", type=int, default=24, help="images per GPU per step")
+    # forward: 48 images x 1536 latent pixels = 288 of the 256-row tiles of the slice-loop GEMMs = two full waves of the
+    # 74 CTA pairs (24 -> one wave: 2 % slower per image, the per-launch prologues weigh twice as much; 64 / 96 -> equal
+    # to 48 within noise: the step runs into the board's power cap).  Sweep: DESIGN.md section 5.  train: 16 (config 4).
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default: 48 forward, 16 train)")
     ap.add_argument("--micro-batches", default="auto", help="sub-batches run as concurrent graphs (auto | 1 | 2 | 4 ...)")
     ap.add_argument("--model", default="cnn", choices=["cnn", "stf"], help="cnn = the headline (BASELINE.json) workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -676,6 +677,8 @@ def main():
                     help="refinit = the reference constructor's random init (seed 0); stress / lowrate = hash-seeded profiles")
     ap.add_argument("--dump-ops", default=None, help="write the per-launch device times of one step to this JSON file")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 16 if args.workload == "train" else 48
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "train":

@@ -2,7 +2,7 @@
 # Round-2 evidence, per kernel: a handful of ncu metrics (duration, tensor-pipe activity, DRAM bytes / throughput,
 # issue-slot use, registers) for EVERY launch of ~2 steps of the bench command, after a plain run of the same command
 # that exited 0.  profiles/step_table.py then cuts out one whole step and writes the per-kernel-class table.
-#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash profiles/collect_r2_step.sh'
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash profiles/collect_r2_step.sh'   (default workload: batch 48)
 set -u
 mkdir -p gpurun_out
 B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-eager-baseline"

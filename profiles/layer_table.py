@@ -29,7 +29,7 @@ def main(csv_path, ops_path):
         a["flop"] += o.get("flop", 0.0)
         a["alg"] += o.get("bytes", 0.0)
     tot = sum(a["t"] for a in agg.values())
-    print(f"# One step (batch 24 x 512 x 768, bf16) by layer class: {len(step)} launches, {tot / 1e3:.2f} ms serialised under ncu\n")
+    print(f"# One step (bench.py default: batch 48 x 512 x 768, bf16) by layer class: {len(step)} launches, {tot / 1e3:.2f} ms serialised under ncu\n")
     print("ncu per-launch duration / tensor-pipe activity / DRAM bytes; TFLOP/s = algorithmic FLOP / ncu duration; "
           "`DRAM / alg` = measured DRAM bytes over the layer's algorithmic bytes (in + out + weights).\n")
     print("| kernel | layer | launches | us each | share | tensor % | TFLOP/s | DRAM GB/s | DRAM / alg |")

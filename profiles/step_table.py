@@ -66,7 +66,7 @@ def main(path):
         a["xbar"] += l.get(XB, 0.0)
         a["regs"] = max(a["regs"], l.get(RG, 0.0))
     tot = sum(a["t"] for a in agg.values())
-    print(f"# One step of `bench.py` (batch 24 x 512 x 768, bf16), per kernel class: {len(step)} launches, {tot / 1e3:.2f} ms serialised under ncu\n")
+    print(f"# One step of `bench.py` (bench.py default: batch 48 x 512 x 768, bf16), per kernel class: {len(step)} launches, {tot / 1e3:.2f} ms serialised under ncu\n")
     print(f"HBM peak (measured copy bandwidth) = {hbm:.0f} GB/s.  `tensor %` = sm__pipe_tensor_cycles_active (time-weighted), `DRAM GB/s` = "
           "(dram read + write bytes) / duration, `L2->SM MB` = l1tex__m_xbar2l1tex_read_bytes per launch.\n")
     print("| kernel | launches | us total | share | tensor % | issue % | DRAM MB / launch | DRAM GB/s | of HBM peak | L2->SM MB / launch | regs |")

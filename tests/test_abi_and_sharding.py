@@ -103,3 +103,21 @@ def test_two_rank_shards_equal_single_rank_result():
     run_on_cpu(full.prog)
     np.testing.assert_array_equal(sym, full.symbols.numpy())
     np.testing.assert_allclose(x_hat, full.x_hat.numpy(), rtol=0, atol=1e-6)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): one JSON line with the contract's keys,
+    on the arm's metric / unit, no GPU needed.  (Smallest run: one warm-up at 256 x 256, one timed 2-image step.)"""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "2"], cwd=root,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "images/s" and line["higher_is_better"] is True
+    assert line["metric"] == "WACNN (-m cnn) forward images/s at 768x512" and line["value"] > 0 and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "batch-48" in line["config"]["workload"]

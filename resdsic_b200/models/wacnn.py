@@ -357,12 +357,42 @@ class WACNN(CompressionModel):
         B, h, w = y_act.B, y_act.H, y_act.W
         means = ctx.buf(B, h, w, ctx_ld)
         scales = ctx.buf(B, h, w, ctx_ld)
+        if ctx.precision == "bf16" and self.grouped_slice_loop and noise_z is None:
+            self._emit_hyper_synthesis_grouped(ctx, h_mean_s, h_scale_s, z_hat, means.channels(0, M), scales.channels(0, M))
+            return z, z_hat, means, scales
         ctx.prog.fork()  # the two hyper-synthesis stacks are independent
         with ctx.prog.side():
             h_scale_s.emit(ctx, z_hat, last_kw=dict(out=scales.channels(0, M)))
         h_mean_s.emit(ctx, z_hat, last_kw=dict(out=means.channels(0, M)))
         ctx.prog.join()
         return z, z_hat, means, scales
+
+    def _emit_hyper_synthesis_grouped(self, ctx, h_mean_s, h_scale_s, z_hat, out_m, out_s):
+        """h_mean_s || h_scale_s (cnn.py:68-90, identical shapes, same input) with their plain 3x3 convolutions as
+        2-group launches: conv0 of both stacks reads z_hat, conv4 of both reads the two halves of one buffer the
+        sub-pixel convolutions write side by side; the sub-pixel convolutions (PixelShuffle store addressing) and the
+        last convolutions (separate destinations: the context buffers) stay one launch per stack on two lanes.  Per
+        output element the arithmetic is that of the ungrouped stacks (a group is an n tile), so the decoder-side plan,
+        which emits the stacks separately, still reproduces every bit.  Two launches less per forward."""
+        from ..layers.conv import emit_grouped
+        prog = ctx.prog
+        stacks = [list(h_mean_s), list(h_scale_s)]
+        c0, s2, c4, s6, c8 = ([st[k] for st in stacks] for k in (0, 2, 4, 6, 8))
+        B, hz, wz = z_hat.B, z_hat.H, z_hat.W
+        n0, n2, n4 = c0[0].out_channels, c4[0].in_channels, c4[0].out_channels
+        t = emit_grouped(ctx, self, ("hs0", id(h_mean_s)), c0, z_hat, 0, gelu=True)                     # [B,hz,wz,2*192]
+        u = ctx.buf(B, 2 * hz, 2 * wz, 2 * n2)
+        prog.fork()
+        with prog.side():
+            s2[1].emit(ctx, t.channels(n0, n0), gelu=True, out=u.channels(n2, n2))
+        s2[0].emit(ctx, t.channels(0, n0), gelu=True, out=u.channels(0, n2))
+        prog.join()
+        t = emit_grouped(ctx, self, ("hs4", id(h_mean_s)), c4, u.channels(0, n2), n2, gelu=True)         # [B,2hz,2wz,2*256]
+        prog.fork()
+        with prog.side():
+            c8[1].emit(ctx, s6[1].emit(ctx, t.channels(n4, n4), gelu=True), out=out_s)
+        c8[0].emit(ctx, s6[0].emit(ctx, t.channels(0, n4), gelu=True), out=out_m)
+        prog.join()
 
     def _emit_slice_precompute(self, ctx, fam, means, scales):
         """Off the serial chain: everything that only needs latent_means / latent_scales.

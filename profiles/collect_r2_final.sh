@@ -13,6 +13,7 @@ import json
 d=json.loads(open('gpurun_out/r2_plain.json').read().strip().splitlines()[-1])['roofline']
 print(d['kernel'] + ' ' + d['layer'])")
 echo "dominant kernel: $KEY"
+if [ "${SKIP_FULL:-0}" != "1" ]; then  # (SKIP_FULL=1: keep the committed capture of the unchanged dominant kernel)
 timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:ru_pair_tc_kernel" -s 2 -c 1 \
     -o gpurun_out/r2_prof_ru_pair $B > gpurun_out/r2_ncu_ru_pair.log 2>&1
 ncu -i gpurun_out/r2_prof_ru_pair.ncu-rep --page raw --csv > gpurun_out/r2_prof_ru_pair_raw.csv 2>/dev/null
@@ -20,6 +21,7 @@ ncu -i gpurun_out/r2_prof_ru_pair.ncu-rep --page source --csv > gpurun_out/r2_pr
 rm -f gpurun_out/r2_prof_ru_pair.ncu-rep
 python profiles/make_traffic_json.py gpurun_out/r2_prof_ru_pair_raw.csv "$KEY" profiles/r2_roofline_traffic.json > /dev/null
 cp profiles/r2_roofline_traffic.json gpurun_out/r2_roofline_traffic.json
+fi
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap \
     --format=csv -lms 200 > gpurun_out/r2_final_clocks.csv &
 SMI=$!

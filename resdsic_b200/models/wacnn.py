@@ -131,6 +131,7 @@ class WACNN(CompressionModel):
         # five mutually independent slices >= max_support_slices in one; `_emit_slice_loop_grouped`).  RDSIC_GROUPED=0
         # restores one launch per convolution.
         self.grouped_slice_loop = os.environ.get("RDSIC_GROUPED", "1") != "0"
+        self.grouped_hyper_synthesis = os.environ.get("RDSIC_HYPER_GROUPED", "1") != "0"
         # Training mode (`.train()`): forward VALUES of the reference's training forward -- likelihoods at
         # y / z + U(-1/2,1/2) noise (entropy_models.py:131-137), y_hat / z_hat by ste_round as in eval mode
         # (cnn.py:152-154,177).  The noise is drawn on the device per call; `noise_override` =
@@ -357,7 +358,7 @@ class WACNN(CompressionModel):
         B, h, w = y_act.B, y_act.H, y_act.W
         means = ctx.buf(B, h, w, ctx_ld)
         scales = ctx.buf(B, h, w, ctx_ld)
-        if ctx.precision == "bf16" and self.grouped_slice_loop and noise_z is None:
+        if ctx.precision == "bf16" and self.grouped_slice_loop and self.grouped_hyper_synthesis and noise_z is None:
             self._emit_hyper_synthesis_grouped(ctx, h_mean_s, h_scale_s, z_hat, means.channels(0, M), scales.channels(0, M))
             return z, z_hat, means, scales
         ctx.prog.fork()  # the two hyper-synthesis stacks are independent

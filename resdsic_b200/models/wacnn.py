@@ -358,7 +358,10 @@ class WACNN(CompressionModel):
         B, h, w = y_act.B, y_act.H, y_act.W
         means = ctx.buf(B, h, w, ctx_ld)
         scales = ctx.buf(B, h, w, ctx_ld)
-        if ctx.precision == "bf16" and self.grouped_slice_loop and self.grouped_hyper_synthesis and noise_z is None:
+        plain = [m for k, m in enumerate(h_mean_s) if k in (0, 4)] if len(h_mean_s) == 9 else []
+        groupable = len(plain) == 2 and all(hasattr(m, "weight") and m.out_channels <= 256 and m.out_channels % 16 == 0 and
+                                            m.in_channels % 8 == 0 for m in plain)  # (a group is one n tile of <= 256 columns)
+        if ctx.precision == "bf16" and self.grouped_slice_loop and self.grouped_hyper_synthesis and noise_z is None and groupable:
             self._emit_hyper_synthesis_grouped(ctx, h_mean_s, h_scale_s, z_hat, means.channels(0, M), scales.channels(0, M))
             return z, z_hat, means, scales
         ctx.prog.fork()  # the two hyper-synthesis stacks are independent

@@ -60,12 +60,22 @@ class Sim:
         if d.a_square:
             x = x * x
         wflat = self._flat(d.weight)[: d.Cout * d.KH * d.KW * d.Cin].float()  # (rows may be padded past Cout)
-        w = wflat.view(d.Cout, d.KH, d.KW, d.Cin).permute(0, 3, 1, 2)
+        w = wflat.view(d.Cout, d.KH, d.KW, d.Cin).permute(0, 3, 1, 2).contiguous()
         bias = self._flat(d.bias)[: d.Cout] if d.bias else None
         need_h = (d.OH - 1) * d.stride + d.KH - d.pad_h
         need_w = (d.OW - 1) * d.stride + d.KW - d.pad_w
-        xp = F.pad(x.permute(0, 3, 1, 2), (d.pad_w, max(0, need_w - d.W), d.pad_h, max(0, need_h - d.H)))
-        v = F.conv2d(xp, w, bias, stride=d.stride, groups=G)[:, :, : d.OH, : d.OW]  # [B,Cout,OH,OW]
+        # (plain NCHW-contiguous operands everywhere: the CPU convolution's summation order depends on the memory format, and
+        # a grouped launch must reproduce the ungrouped launches of the same layers bit for bit, as the GPU kernel does)
+        xp = F.pad(x.permute(0, 3, 1, 2), (d.pad_w, max(0, need_w - d.W), d.pad_h, max(0, need_h - d.H))).contiguous()
+        if G == 1:
+            v = F.conv2d(xp, w, bias, stride=d.stride)
+        else:
+            # a group is an n tile of the same GEMM: evaluate each as its own convolution, so that the values equal those of
+            # the ungrouped launches of the same layers bit for bit (F.conv2d(groups=G) may sum in another order)
+            Cg = d.Cout // G
+            v = torch.cat([F.conv2d(xp[:, g * d.Cin:(g + 1) * d.Cin].contiguous(), w[g * Cg:(g + 1) * Cg].contiguous(),
+                                    bias[g * Cg:(g + 1) * Cg] if bias is not None else None, stride=d.stride) for g in range(G)], 1)
+        v = v[:, :, : d.OH, : d.OW]  # [B,Cout,OH,OW]
         assert v.shape[2:] == (d.OH, d.OW), (v.shape, d.OH, d.OW)
         if d.pixel_shuffle == 3:  # columns packed sub-position-major (s * C/4 + c): back to nn.PixelShuffle's 4 c + s
             Cq = d.Cout // 4

@@ -170,3 +170,23 @@ def test_config5_clic_bf16_vs_oracle(model, refinit_sd, scale_table):
     assert xp.shape[-2:] == (1408, 2048) and pad == (0, 0, 21, 22)
     got, ref = _vs_oracle(model, refinit_sd, scale_table, xp.contiguous(), "config5[bf16]")
     assert got["indexes"].min() >= 0 and got["indexes"].max() <= 63
+
+
+def test_bf16_program_config1_on_the_cpu_simulator(refinit_sd):
+    """The bf16 eval program of config 1 (the grouped slice loop, grouped hyper-synthesis convs, fused conv + GDN /
+    ResidualUnit descriptors, the bf16 y_hat outputs of the LRP epilogues: what the GPU replays as one graph) interpreted
+    by tests/program_sim.py -- bf16-rounded operands, fp32 accumulation -- meets the north-star tolerances against the
+    reference's own outputs without a GPU: the HOST side of the bf16 path is checked by the CPU suite."""
+    from tests.program_sim import run_on_cpu
+    g = _golden("c256")
+    m = resdsic_b200.WACNN().eval()
+    m.load_state_dict(refinit_sd, strict=True)
+    m.set_precision("bf16")
+    x = weights.rand_image(2, 256, 256, seed=1)
+    p = m._build(2, 256, 256, "cpu", True, build_only=True)
+    assert p.prog.num_launches < 200
+    p.x.copy_(x)
+    run_on_cpu(p.prog)
+    assert (p.symbols.numpy() != g["symbols"]).mean() <= 1e-3 and (p.indexes.numpy() != g["indexes"]).mean() <= 1e-3
+    _check_contract("config1[bf16, simulator]", p.x_hat.numpy(), p.lik_y.numpy(), p.lik_z.numpy(), g["x_hat"], g["bpp"], g["psnr"], x,
+                    256 * 256, X_TOL)

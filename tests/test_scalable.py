@@ -258,3 +258,47 @@ def test_scalable_decoder_programs_match_encoder_program(name, q):
     run_on_cpu(dec.synth)
     want = enc.x_hat[0].clamp(0, 1)
     assert (dec.x_hat - want).abs().max() <= 1e-4, (name, q, (dec.x_hat - want).abs().max())
+
+
+@pytest.mark.parametrize("name", ["icd_gamma", "imd_two", "cimd_cat", "ind_md"])
+def test_bf16_host_program_on_the_cpu_simulator(name):
+    """The bf16 program of the scalable forward (grouped joiner launches, grouped hyper-synthesis convs, bf16 merge /
+    concatenation copies) interpreted on the CPU: statistical agreement with the reference golden (the gate of the GPU
+    bf16 test), and its encoder / decoder plans agree on EVERY CDF index and on x_hat bit for bit although the encoder
+    groups launches the decoder issues one by one (a group is an n tile of the same GEMM; the simulator evaluates it as
+    its own convolution on plain contiguous operands, like the ungrouped launch)."""
+    m, sd, quality, qs, x = _model(name)
+    m.set_precision("bf16")
+    g = np.load(os.path.join(GOLDEN, f"scalable_{name}.npz"))
+    B, _, H, W = x.shape
+    p = m._build_scalable(B, H, W, "cpu", tuple(qs), False, build_only=True)
+    p.x.copy_(x)
+    run_on_cpu(p.prog)
+    dx = np.abs(p.x_hat.numpy() - g["x_hat"])
+    n = B * H * W
+    got = dict(lik_y=p.lik_y.numpy(), lik_z=p.lik_z.numpy(), lik_z_prog=p.lik_z_prog.numpy(), lik_y_prog=p.lik_y_prog.numpy())
+    bpp = lambda d: sum(np.log(d[k].astype(np.float64)).sum() for k in ("lik_y", "lik_z", "lik_z_prog", "lik_y_prog")) / (-np.log(2) * n)
+    print(f"sim[{name},bf16] x_hat max {dx.max():.3e} mean {dx.mean():.3e} bpp {bpp(got):.4f} ref {bpp(g):.4f}")
+    assert dx.mean() <= 5e-3 and dx.max() <= 0.2
+    assert abs(bpp(got) - bpp(g)) <= 2e-2 * bpp(g)
+    # encoder-side (compress) program vs decoder plans, last quality: identical indexes, x_hat = clamp(encoder x_hat)
+    q = qs[-1]
+    enc = m._build_scalable(B, H, W, "cpu", (q,), True, build_only=True)
+    enc.x.copy_(x)
+    run_on_cpu(enc.prog)
+    dec = m._build_scalable_decoder(B, H // 64, W // 64, "cpu", q, build_only=True)
+    streams = [(dec.base, enc.z_hat_out, enc.symbols, enc.indexes)] + ([(dec.prog, enc.z_hat_prog, enc.prog_symbols, enc.prog_indexes)] if q else [])
+    for st, z_hat, _, _ in streams:
+        st.z_hat_in.copy_(z_hat)
+        run_on_cpu(st.hyper)
+    if dec.mask_prog is not None:
+        run_on_cpu(dec.mask_prog)
+    for i in range(10):
+        sl = slice(32 * i, 32 * i + 32)
+        for st, _, sym, idx in streams:
+            run_on_cpu(st.params[i])
+            assert torch.equal(st.indexes[:, sl], idx[:, sl]), (name, i, (st.indexes[:, sl] != idx[:, sl]).float().mean())
+            st.symbols[:, sl].copy_(sym[:, sl])
+            run_on_cpu(st.update[i])
+    run_on_cpu(dec.synth)
+    assert torch.equal(dec.x_hat, enc.x_hat[0].clamp(0, 1)), (name, (dec.x_hat - enc.x_hat[0].clamp(0, 1)).abs().max())

@@ -101,3 +101,31 @@ def test_decoder_is_bit_identical_to_encoder_pass(model, precision, graph):
     finally:
         model.set_precision("fp32")
         model.use_cuda_graph = True
+
+
+def test_bf16_encoder_and_decoder_programs_agree_bit_for_bit_on_the_cpu_simulator(synthetic_sd):
+    """bf16 mode, no GPU: the encoder-side program (grouped slice loop, grouped hyper-synthesis convs, grouped tail with the
+    three-way LRP split) and the decoder plan (one launch per convolution, mirrored LRP split) produce the same CDF index
+    for every latent and, with the encoder's symbols pushed back, the same x_hat -- what the entropy decoder relies on.
+    The simulator evaluates a group as its own convolution, as the GPU kernel evaluates it as its own n tile."""
+    m = resdsic_b200.WACNN().eval()
+    m.load_state_dict(synthetic_sd, strict=True)
+    m.set_precision("bf16")
+    Bq, Hq, Wq = 2, 128, 192
+    enc = m._build(Bq, Hq, Wq, "cpu", True, build_only=True)
+    assert enc.prog.num_launches < 200
+    enc.x.copy_(weights.make_image(Bq, Hq, Wq, seed=3))
+    run_on_cpu(enc.prog)
+    med = m.entropy_bottleneck._get_medians().detach().view(1, -1, 1, 1)
+    z_hat = enc.z_symbols.float() + med  # what EntropyBottleneck.decompress hands the decoder (entropy_models.py:521-526)
+    dec = m._build_decoder(Bq, Hq // 64, Wq // 64, "cpu", build_only=True)
+    dec.z_hat_in.copy_(z_hat)
+    run_on_cpu(dec.hyper)
+    for i in range(10):
+        sl = slice(32 * i, 32 * i + 32)
+        run_on_cpu(dec.params[i])
+        assert torch.equal(dec.indexes[:, sl], enc.indexes[:, sl]), (i, (dec.indexes[:, sl] != enc.indexes[:, sl]).float().mean())
+        dec.symbols[:, sl].copy_(enc.symbols[:, sl])
+        run_on_cpu(dec.update[i])
+    run_on_cpu(dec.synth)
+    assert torch.equal(dec.x_hat, enc.x_hat.clamp(0, 1))
